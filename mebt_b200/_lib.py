@@ -1,0 +1,67 @@
+"""ctypes binding of libmebt_b200.so (the C ABI declared in include/mebt_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a Python exception
+is raised.  Loading the library does not need a GPU (it links cudart statically); calling a compute
+entry point without an sm_100 device fails with the library's own error message.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libmebt_b200.so"
+
+
+class MebtError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not _LIB_PATH.exists():
+        raise MebtError(
+            f"{_LIB_PATH} is missing: build it with `python -m mebt_b200.build` "
+            "(mebt_b200 has no CPU / PyTorch fallback path)")
+    return ctypes.CDLL(str(_LIB_PATH))
+
+
+_lib = _load()
+_lib.mebt_last_error.restype = c_char_p
+_lib.mebt_version.restype = c_char_p
+
+# name -> argtypes; every function returns int
+_SIGNATURES: dict[str, list] = {
+    "mebt_device_check": [],
+    "mebt_gemm_bf16": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                       c_void_p, c_void_p, c_int, c_int, c_void_p],
+}
+
+
+def _bind():
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(_lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+
+
+_bind()
+
+
+def version() -> str:
+    return _lib.mebt_version().decode()
+
+
+def last_error() -> str:
+    return _lib.mebt_last_error().decode()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise MebtError(f"{what or 'mebt_b200'} failed (code {rc}): {last_error()}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(_lib, name)(*args), name)
+
+
+lib = _lib

@@ -1,0 +1,320 @@
+// K2/K4: persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )        bf16 operands, fp32 accumulation in TMEM
+//
+// Replaces the cuBLAS addmm/mm calls behind nn.Linear on the MeBT hot path
+// (reference: mebt/modules/gpt.py:126-128 q/k/v, :140 proj, :150-155 mlp, :248 head) and, with the
+// MN-major operand modes, their dgrad/wgrad counterparts that autograd would dispatch.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0    : TMA producer  - cp.async.bulk.tensor tiles into a STAGES-deep smem ring (128B swizzle)
+//   warp 1    : MMA issuer    - one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
+//   warps 2-5 : epilogue      - tcgen05.ld the fp32 accumulator, bias / GELU / residual, store
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+//
+// Operand majors: "K-major" = reduction dim contiguous (A is [M,K] row-major, B is [N,K] row-major,
+// i.e. torch Linear weights).  "MN-major" = the M (or N) dim contiguous (A given as [K,M], B as [K,N]).
+#include "common.cuh"
+
+namespace mebt {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  const float* bias;                   // [N] or nullptr
+  const __nv_bfloat16* residual;       // [M, ldres] or nullptr
+  int ldres;
+  void* C;
+  int ldc;
+  int gelu;
+  int out_fp32;
+  int accumulate;                      // C += result (fp32 output only)
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const GemmParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  constexpr uint32_t TMEM_COLS = 2 * BN;   // 128, 256 or 512 (power of two >= 32)
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tma_a);
+    prefetch_tensormap(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.num_m_blocks) * BM;
+        const int n0 = (tile / p.num_m_blocks) * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * L::STAGE_BYTES;
+          uint8_t* sB = sA + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_2d(sA, &tma_a, &full_bar[stage], kb * BK, m0);               // box [64 k][128 m]
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)                                      // box [64 m][64 k]
+              tma_load_2d(sA + i * (BK * 128), &tma_a, &full_bar[stage], m0 + i * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sB, &tma_b, &full_bar[stage], kb * BK, n0);               // box [64 k][BN n]
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)                                      // box [64 n][64 k]
+              tma_load_2d(sB + i * (BK * 128), &tma_b, &full_bar[stage], n0 + i * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sB = sA + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major : advance 16 elements (32 B) inside the 128 B swizzle row; SBO = 8 rows * 128 B
+            // MN-major: advance 16 k-rows (2048 B); LBO = next 64-wide MN atom (BK rows * 128 B), SBO = 8 k-rows
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sA + k * (UMMA_K * 128), BK * 128, 1024)
+                                     : make_smem_desc_sw128(sA + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sB + k * (UMMA_K * 128), BK * 128, 1024)
+                                     : make_smem_desc_sw128(sB + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
+          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile % p.num_m_blocks) * BM;
+      const int n0 = (tile / p.num_m_blocks) * BN;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        const int col = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (p.gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (row_ok) {
+          if (p.residual != nullptr) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + size_t(row) * p.ldres + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = __ldg(r4 + j);
+              const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z),
+                           d = unpack_bf16x2(u.w);
+              v[8 * j + 0] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b.x; v[8 * j + 3] += b.y;
+              v[8 * j + 4] += c2.x; v[8 * j + 5] += c2.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
+            }
+          }
+          if (p.out_fp32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + size_t(row) * p.ldc + col);
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o = o4[j];
+                o.x += v[4 * j + 0]; o.y += v[4 * j + 1]; o.z += v[4 * j + 2]; o.w += v[4 * j + 3];
+                o4[j] = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + size_t(row) * p.ldc + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              o4[j] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_gemm(const void* A, const void* B, const GemmParams& p, int lda, int ldb, cudaStream_t stream) {
+  constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  using L = SmemLayout<BN, STAGES>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = get_tensor_map_2d(&ta, A, 2, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, BK, BM);
+  else       rc = get_tensor_map_2d(&ta, A, 2, uint64_t(p.M), uint64_t(p.K), uint64_t(lda) * 2, 64, BK);
+  if (rc) return rc;
+  if (!B_MN) rc = get_tensor_map_2d(&tb, B, 2, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, BK, BN);
+  else       rc = get_tensor_map_2d(&tb, B, 2, uint64_t(p.N), uint64_t(p.K), uint64_t(ldb) * 2, 64, BK);
+  if (rc) return rc;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MEBT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  MEBT_LAUNCH_OK("gemm_bf16_kernel");
+  return MEBT_OK;
+}
+
+template <int BN>
+int dispatch_major(int a_mn, int b_mn, const void* A, const void* B, const GemmParams& p, int lda, int ldb,
+                   cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(A, B, p, lda, ldb, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(A, B, p, lda, ldb, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(A, B, p, lda, ldb, stream);
+  return launch_gemm<BN, true, true>(A, B, p, lda, ldb, stream);
+}
+
+}  // namespace
+
+int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+              int K, const float* bias, const void* residual, int ldres, int flags, cudaStream_t stream) {
+  MEBT_REQUIRE(M > 0 && N > 0 && K > 0, MEBT_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  MEBT_REQUIRE(N % 64 == 0, MEBT_ERR_SHAPE, "gemm: N=%d must be a multiple of 64", N);
+  MEBT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, MEBT_ERR_SHAPE, "gemm: lda/ldb must be multiples of 8 elements");
+  const bool out_fp32 = (flags & MEBT_GEMM_OUT_FP32) != 0;
+  MEBT_REQUIRE(ldc % (out_fp32 ? 4 : 8) == 0, MEBT_ERR_SHAPE, "gemm: ldc=%d breaks 16-byte row alignment", ldc);
+  MEBT_REQUIRE(!(flags & MEBT_GEMM_ACCUMULATE) || out_fp32, MEBT_ERR_UNSUPPORTED,
+               "gemm: accumulate needs fp32 output");
+  MEBT_REQUIRE(residual == nullptr || ldres % 8 == 0, MEBT_ERR_SHAPE, "gemm: ldres must be a multiple of 8");
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.ldres = ldres;
+  p.C = C; p.ldc = ldc;
+  p.gelu = (flags & MEBT_GEMM_GELU) ? 1 : 0;
+  p.out_fp32 = out_fp32 ? 1 : 0;
+  p.accumulate = (flags & MEBT_GEMM_ACCUMULATE) ? 1 : 0;
+  p.num_m_blocks = (M + BM - 1) / BM;
+  p.num_k_blocks = (K + BK - 1) / BK;
+  // Tile-width choice: the widest BN that still yields at least ~one wave of tiles.
+  int bn = 64;
+  if (N % 256 == 0 && int64_t(p.num_m_blocks) * (N / 256) >= sm_count()) bn = 256;
+  else if (N % 128 == 0 && int64_t(p.num_m_blocks) * (N / 128) >= sm_count()) bn = 128;
+  if (flags & MEBT_GEMM_FORCE_BN256) { MEBT_REQUIRE(N % 256 == 0, MEBT_ERR_SHAPE, "BN256 needs N%%256==0"); bn = 256; }
+  if (flags & MEBT_GEMM_FORCE_BN128) { MEBT_REQUIRE(N % 128 == 0, MEBT_ERR_SHAPE, "BN128 needs N%%128==0"); bn = 128; }
+  if (flags & MEBT_GEMM_FORCE_BN64) bn = 64;
+  p.num_n_blocks = N / bn;
+  switch (bn) {
+    case 256: return dispatch_major<256>(a_mn, b_mn, A, B, p, lda, ldb, stream);
+    case 128: return dispatch_major<128>(a_mn, b_mn, A, B, p, lda, ldb, stream);
+    default: return dispatch_major<64>(a_mn, b_mn, A, B, p, lda, ldb, stream);
+  }
+}
+
+}  // namespace mebt
+
+extern "C" int mebt_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C,
+                              int ldc, int M, int N, int K, const float* bias, const void* residual, int ldres,
+                              int flags, void* stream) {
+  return mebt::gemm_bf16(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, bias, residual, ldres, flags,
+                         static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,134 @@
+// Host-side runtime shared by every op: error strings, device check, TMA tensor-map cache.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace mebt {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_last_error("CUDA error %d (%s) at %s", int(e), cudaGetErrorString(e), what);
+  return MEBT_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+// ---- tensor map cache ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t inner, outer, stride;
+  uint32_t box_inner, box_outer, elem;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return size_t(h);
+  }
+};
+
+int get_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.inner = inner; key.outer = outer; key.stride = row_stride_bytes;
+  key.box_inner = box_inner; key.box_outer = box_outer; key.elem = uint32_t(elem_bytes);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return MEBT_OK; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  MEBT_REQUIRE(fn != nullptr, MEBT_ERR_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  MEBT_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (row_stride_bytes & 15) == 0, MEBT_ERR_SHAPE,
+               "TMA operand must be 16-byte aligned (ptr=%p stride=%llu)", ptr, (unsigned long long)row_stride_bytes);
+  MEBT_REQUIRE(box_inner * uint32_t(elem_bytes) == 128 && box_outer >= 1 && box_outer <= 256, MEBT_ERR_SHAPE,
+               "TMA box must be 128 bytes wide and <= 256 rows (got %u x %u)", box_inner, box_outer);
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MEBT_REQUIRE(r == CUDA_SUCCESS, MEBT_ERR_CUDA,
+               "cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu stride=%llu box=%ux%u", int(r), ptr,
+               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
+               box_outer);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, m);
+  }
+  *out = m;
+  return MEBT_OK;
+}
+
+}  // namespace mebt
+
+extern "C" {
+
+const char* mebt_last_error(void) { return mebt::g_last_error; }
+
+const char* mebt_version(void) { return "mebt_b200 0.1 (sm_100a)"; }
+
+int mebt_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return mebt::cuda_fail(e, "cudaGetDevice");
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    mebt::set_last_error("mebt_b200 needs an sm_100-class GPU (Blackwell B200); found sm_%d%d", major, minor);
+    return MEBT_ERR_DEVICE;
+  }
+  return MEBT_OK;
+}
+
+}  // extern "C"
