@@ -61,6 +61,114 @@ enum {
 int mebt_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
                    int M, int N, int K, const float* bias, const void* residual, int ldres, int flags, void* stream);
 
+
+/* ---- dtypes --------------------------------------------------------------------------------- */
+enum { MEBT_DTYPE_BF16 = 0, MEBT_DTYPE_FP32 = 1 };
+
+/* ---- K1 : embedding stem -------------------------------------------------------------------- */
+/*
+ * contexts[b,i,:] = tok_emb[x[b, ctx_idx[b,i]]] + pos_emb[ctx_idx[b,i]]
+ * targets [b,i,:] = mask_emb + pos_emb[tgt_idx[b,i]]        latents[b,l,:] = sos_emb[l]
+ * Replaces the gather / nn.Embedding / pos_emb.repeat + gather / mask_emb.repeat / sos_emb.repeat chain at
+ * mebt/transformer.py:298-317 (reconstruct_mask) and :255-277 (forward).
+ * x_indices/ctx_idx/tgt_idx: int64, row strides in elements (index tensors may be views of a permutation).
+ * tok_emb [V,D], pos_emb [n_pos,D], mask_emb [D], sos_emb [L,D]: fp32 parameters.  Outputs: [B*NC,D], [B*NT,D],
+ * [B*L,D] in out_dtype.  Out-of-range ids/positions are skipped and flagged (mebt_check_index_errors).
+ */
+int mebt_embed_gather(const int64_t* x_indices, int x_stride, const int64_t* ctx_idx, int ctx_stride,
+                      const int64_t* tgt_idx, int tgt_stride, const float* tok_emb, const float* pos_emb,
+                      const float* mask_emb, const float* sos_emb, void* contexts, void* targets, void* latents, int B,
+                      int NC, int NT, int L, int D, int V, int n_pos, int out_dtype, void* stream);
+
+/* nn.LayerNorm(D), eps inside the sqrt (mebt/modules/gpt.py:147-148 ln1/ln2, :216 ln_f).  gamma/beta fp32.
+ * mean_out / rstd_out: optional fp32 [rows] (saved for backward). */
+int mebt_layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const float* beta, void* y, int ldy,
+                   int out_dtype, int rows, int D, float eps, float* mean_out, float* rstd_out, void* stream);
+
+/* ---- K8 : write sampled ids back -------------------------------------------------------------- */
+/* x[b, tgt_idx[b,i]] = ids[b,i]; replaces the two sparse_coo_tensor(...).to_dense() + where at
+ * mebt/transformer.py:413-439, :571-585, :615-629. */
+int mebt_scatter_ids(int64_t* x, int x_stride, const int64_t* tgt_idx, int tgt_stride, const int64_t* ids, int B, int NT,
+                     int N, void* stream);
+
+/* ---- K10 : codebook row gather ---------------------------------------------------------------- */
+/* out = E[enc]; channel_first=0 -> [batch*S, C] (Codebook.dictionary_lookup, modules/codebook.py:99-101);
+ * channel_first=1 -> [batch, C, S], fusing the shift_dim of mebt/vqgan.py:91-92 / codebook.py:61-62. */
+int mebt_row_gather(const int64_t* enc, const float* E, float* out, int batch, int S, int C, int K, int channel_first,
+                    void* stream);
+
+/* fp32 -> bf16 (master weights -> tensor-core operands). n % 4 == 0. */
+int mebt_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream);
+
+/* Reads and clears the device-side index-error flag. SYNCHRONISES the stream: tests / debug only. */
+int mebt_check_index_errors(void* stream);
+
+/* ---- K5 : masked cross-entropy ---------------------------------------------------------------- */
+/*
+ * Per row r of logits [rows, V] (row stride ld): row_loss[r] = (1-eps) * (lse - x_t) + eps * (lse - mean x),
+ * row_rank[r] = #{v : x_v > x_t}  (top-1 hit <=> 0, top-5 hit <=> < 5), and optionally
+ * dlogits = grad_scale * (softmax - (1-eps) onehot - eps/V) in the logits dtype (may alias logits).
+ * Replaces F.cross_entropy(reduction='sum', label_smoothing) at mebt/transformer.py:726 and the topk(5) of
+ * accuracy() (mebt/utils.py:80-94).  V % 4 == 0, V <= 16384.
+ */
+int mebt_masked_ce(const void* logits, long long ld, int dtype, const int64_t* targets, int rows, int V,
+                   float label_smoothing, float* row_loss, int* row_rank, void* dlogits, long long ld_d,
+                   float grad_scale, void* stream);
+/* out3 = {sum row_loss, #rank==0, #rank<5}; fixed-order (deterministic) reduction. row_rank may be NULL. */
+int mebt_ce_reduce(const float* row_loss, const int* row_rank, int rows, float* out3, void* stream);
+
+/* ---- K6 : sampling from logits ---------------------------------------------------------------- */
+/*
+ * ids[r] = argmax_v (p_v / sum p) / q_v with p = softmax(top_k_filter(logits / (temperature + 1e-8))),
+ * scores[r] = p[ids[r]].  q: Exp(1) noise [rows, V] supplied by the caller (parity mode, = the reference's
+ * exponential_ draw) or, when noise == NULL, generated in-kernel with Philox4x32-10(seed, offset).
+ * probs (optional, fp32 [rows, V]) receives the softmax the reference returns with return_probs=True.
+ * Replaces sample_from_logits + gumbel_sort + top_k_logits, mebt/transformer.py:843-895 (a full 16384-way sort
+ * per row and ~10 passes over [B,NT,V] become one pass).  top_k <= 0 disables the filter; top_p in (0,1) is
+ * not implemented (MEBT_ERR_UNSUPPORTED).
+ */
+int mebt_sample_logits(const void* logits, long long ld, int dtype, int rows, int V, float temperature, int top_k,
+                       float top_p, const float* noise, unsigned long long seed, unsigned long long offset,
+                       int64_t* ids, float* scores, float* probs, void* stream);
+
+/* ---- K7 : confidence re-masking ---------------------------------------------------------------- */
+/*
+ * order = argsort_desc((score / sum score) / q^ctemp); next_ctx = cat[ctx, tgt[order[:n_new]]],
+ * next_tgt = tgt[order[n_new:]].  Replaces MaskGen.gumbel_top_k + the gathers of generate_next_mask
+ * (mebt/mask_sampler.py:178-187, :226-234).  noise q [B,NT] Exp(1) or NULL (Philox).  Ties: lower index first.
+ * Outputs are optional (NULL to skip); order_out int64 [B,NT].  NT <= 16384.
+ */
+int mebt_remask_sort(const float* score, const float* noise, float ctemp, const int64_t* ctx_idx, int ctx_stride,
+                     const int64_t* tgt_idx, int tgt_stride, int B, int NC, int NT, int n_new, unsigned long long seed,
+                     unsigned long long offset, int64_t* next_ctx, int64_t* next_tgt, int64_t* order_out, void* stream);
+
+/* ---- K9 : codebook nearest neighbour ---------------------------------------------------------- */
+/* out[k] = sum_c E[k,c]^2 (the |E|^2 term of modules/codebook.py:55; constant while the VQGAN is frozen). */
+int mebt_row_sqnorm(const float* E, int K, int C, float* out, void* stream);
+size_t mebt_vq_argmin_workspace_bytes(long long M);
+/*
+ * out_idx[b*S + s] = argmin_k |z[b,:,s] - E[k]|^2, fp32-accurate, lowest index on exact ties.
+ * z is channel-first [batch, C, S] exactly as VQGAN.encode hands it to the codebook; replaces
+ * shift_dim/flatten + distance matrix + argmin at mebt/modules/codebook.py:52-57.
+ */
+int mebt_vq_argmin(const float* z_channel_first, int batch, int C, int S, const float* E, const float* e_sqnorm, int K,
+                   int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3 : latent attention --------------------------------------------------------------------- */
+/*
+ * O[b,q,h,:] = softmax_k(Q[b,q,h,:].K[b,k,h,:] / sqrt(head_dim)) V[b,k,h,:], bf16 in/out, fp32 softmax, flash-style
+ * (no [B,h,NQ,NK] matrix), tcgen05 QK^T and PV.  Replaces the bmm/softmax/bmm of CrossAttention.forward,
+ * mebt/modules/gpt.py:131-137.  Keys/values come from up to two sources that are walked back to back, which is
+ * how lt2l's torch.cat([sos_emb, targets]) (gpt.py:175) is consumed without materialising it:
+ *   Q  : rows b*NQ+q  of a [B*NQ,  ldq] buffer, head h at columns q_col0 + 64h
+ *   KV1: rows b*NK1+k of a [B*NK1, ld1] buffer, K at k1_col0 + 64h, V at v1_col0 + 64h   (NK1 may be 0)
+ *   KV2: same with NK2 (0 = absent).            O: [B*NQ, ldo], head h at columns 64h.
+ * NK1 + NK2 == 0 gives O = 0 (the reference's empty softmax).  lse: optional fp32 [B,H,NQ] (for backward).
+ */
+int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0,
+                              int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, void* O, int ldo,
+                              float* lse, int B, int H, int NQ, int head_dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ entry point without an sm_100 device fails with the library's own error message.
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "libmebt_b200.so"
@@ -34,6 +34,27 @@ _SIGNATURES: dict[str, list] = {
     "mebt_device_check": [],
     "mebt_gemm_bf16": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                        c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "mebt_embed_gather": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                          c_void_p],
+    "mebt_layernorm": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                       c_void_p, c_void_p, c_void_p],
+    "mebt_scatter_ids": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    "mebt_row_gather": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "mebt_cast_f32_to_bf16": [c_void_p, c_void_p, c_longlong, c_void_p],
+    "mebt_check_index_errors": [c_void_p],
+    "mebt_masked_ce": [c_void_p, c_longlong, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                       c_longlong, c_float, c_void_p],
+    "mebt_ce_reduce": [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "mebt_sample_logits": [c_void_p, c_longlong, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p, c_uint64,
+                           c_uint64, c_void_p, c_void_p, c_void_p, c_void_p],
+    "mebt_remask_sort": [c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                         c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p],
+    "mebt_row_sqnorm": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "mebt_vq_argmin": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                       c_void_p],
+    "mebt_latent_attention_fwd": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                  c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
 
 
@@ -45,6 +66,8 @@ def _bind():
 
 
 _bind()
+_lib.mebt_vq_argmin_workspace_bytes.argtypes = [c_longlong]
+_lib.mebt_vq_argmin_workspace_bytes.restype = c_size_t
 
 
 def version() -> str:

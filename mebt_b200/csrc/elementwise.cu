@@ -1,0 +1,353 @@
+// Memory-bound kernels of the MeBT hot path: K1 embedding stem, LayerNorm, K8 id scatter, K10 codebook
+// row gather, dtype casts.  All are HBM-bound: one warp per row, 16-byte vectorised coalesced access,
+// warp-shuffle reductions, no shared-memory staging needed (every byte is touched once).
+#include "common.cuh"
+
+namespace mebt {
+namespace {
+
+constexpr int ROWS_PER_BLOCK = 8;   // 8 warps, one row each
+
+template <typename T> struct Vec4 {};   // 4 elements
+template <> struct Vec4<float> {
+  using type = float4;
+  __device__ static float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ static void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  using type = uint2;
+  __device__ static float4 load(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  __device__ static void store(__nv_bfloat16* p, float4 v) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K1: contexts = tok_emb[x[ctx_idx]] + pos_emb[ctx_idx]; targets = mask_emb + pos_emb[tgt_idx];
+//     latents = sos_emb (broadcast over the batch).   reference: mebt/transformer.py:298-317
+// ---------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void embed_gather_kernel(const int64_t* __restrict__ x, int x_stride, const int64_t* __restrict__ ctx_idx,
+                                    int ctx_stride, const int64_t* __restrict__ tgt_idx, int tgt_stride,
+                                    const float* __restrict__ tok_emb, const float* __restrict__ pos_emb,
+                                    const float* __restrict__ mask_emb, const float* __restrict__ sos_emb,
+                                    OutT* __restrict__ contexts, OutT* __restrict__ targets, OutT* __restrict__ latents,
+                                    int B, int NC, int NT, int L, int D, int V, int n_pos, int* __restrict__ err_flag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + warp;
+  const long long n_ctx = (long long)B * NC, n_tgt = (long long)B * NT, n_lat = (long long)B * L;
+  if (row >= n_ctx + n_tgt + n_lat) return;
+  const float* src_a;
+  const float* src_b = nullptr;
+  OutT* dst;
+  if (row < n_ctx) {
+    const int b = int(row / NC), i = int(row % NC);
+    const long long pos = ctx_idx[(long long)b * ctx_stride + i];
+    if (pos < 0 || pos >= n_pos) { if (lane == 0) atomicExch(err_flag, 1); return; }
+    const long long tok = x[(long long)b * x_stride + pos];
+    if (tok < 0 || tok >= V) { if (lane == 0) atomicExch(err_flag, 2); return; }
+    src_a = tok_emb + tok * D;
+    src_b = pos_emb + pos * D;
+    dst = contexts + row * D;
+  } else if (row < n_ctx + n_tgt) {
+    const long long r = row - n_ctx;
+    const int b = int(r / NT), i = int(r % NT);
+    const long long pos = tgt_idx[(long long)b * tgt_stride + i];
+    if (pos < 0 || pos >= n_pos) { if (lane == 0) atomicExch(err_flag, 1); return; }
+    src_a = mask_emb;
+    src_b = pos_emb + pos * D;
+    dst = targets + r * D;
+  } else {
+    const long long r = row - n_ctx - n_tgt;
+    src_a = sos_emb + (r % L) * D;
+    dst = latents + r * D;
+  }
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(src_a + c));
+    if (src_b != nullptr) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(src_b + c));
+      // reference order: pos_emb row + token row (transformer.py:311-312); fp32 add is commutative
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
+    Vec4<OutT>::store(dst + c, a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (eps inside the sqrt, biased variance) — nn.LayerNorm, gpt.py:147-148,216.
+// Two-pass in registers (mean, then centred sum of squares) in fp32.
+// ---------------------------------------------------------------------------------------------
+template <typename InT, typename OutT, int MAX_VEC>   // MAX_VEC float4 groups per lane: D <= 128 * MAX_VEC
+__global__ void layernorm_kernel(const InT* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, OutT* __restrict__ y, int ldy, int rows, int D,
+                                 float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + warp;
+  if (row >= rows) return;
+  const InT* xr = x + row * ldx;
+  float4 v[MAX_VEC];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < D) {
+      v[i] = Vec4<InT>::load(xr + c);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / float(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < D) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c2 * c2 + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / float(D) + eps);
+  if (lane == 0) {
+    if (mean_out != nullptr) mean_out[row] = mean;
+    if (rstd_out != nullptr) rstd_out[row] = rstd;
+  }
+  OutT* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < D) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      Vec4<OutT>::store(yr + c, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8: x[b, tgt_idx[b,i]] = ids[b,i]  (the sparse-COO write-back of transformer.py:413-439 ≡ scatter)
+// ---------------------------------------------------------------------------------------------
+__global__ void scatter_ids_kernel(int64_t* __restrict__ x, int x_stride, const int64_t* __restrict__ tgt_idx,
+                                   int tgt_stride, const int64_t* __restrict__ ids, int B, int NT, int N,
+                                   int* __restrict__ err_flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * NT) return;
+  const int b = int(i / NT), j = int(i % NT);
+  const long long pos = tgt_idx[(long long)b * tgt_stride + j];
+  if (pos < 0 || pos >= N) { atomicExch(err_flag, 1); return; }
+  x[(long long)b * x_stride + pos] = ids[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10: codebook row gather, F.embedding (codebook.py:61, vqgan.py:91), optional channel-first output
+//      (fusing shift_dim(h, -1, 1) of codebook.py:62 / vqgan.py:92).
+// ---------------------------------------------------------------------------------------------
+__global__ void row_gather_kernel(const int64_t* __restrict__ enc, const float* __restrict__ E, float* __restrict__ out,
+                                  long long M, int C, int K, int* __restrict__ err_flag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + warp;
+  if (row >= M) return;
+  const long long code = enc[row];
+  if (code < 0 || code >= K) { if (lane == 0) atomicExch(err_flag, 1); return; }
+  const float4* src = reinterpret_cast<const float4*>(E + code * C);
+  float4* dst = reinterpret_cast<float4*>(out + row * C);
+  for (int c = lane; c < C / 4; c += 32) dst[c] = __ldg(src + c);
+}
+
+// out[b, c, s] = E[enc[b, s], c];  32x32 tile transposed through shared memory so both sides coalesce
+__global__ void row_gather_cf_kernel(const int64_t* __restrict__ enc, const float* __restrict__ E,
+                                     float* __restrict__ out, int S, int C, int K, int* __restrict__ err_flag) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int s = s0 + r;
+    float v = 0.f;
+    if (s < S && c0 + tx < C) {
+      const long long code = enc[(long long)b * S + s];
+      if (code < 0 || code >= K) atomicExch(err_flag, 1);
+      else v = __ldg(E + code * C + c0 + tx);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, s = s0 + tx;
+    if (c < C && s < S) out[((long long)b * C + c) * S + s] = tile[tx][r];
+  }
+}
+
+// fp32 -> bf16 cast (weights master copy -> tensor-core operand)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    Vec4<__nv_bfloat16>::store(out + i * 4, v);
+  }
+}
+
+int* device_err_flag() {
+  static int* flag = nullptr;
+  if (flag == nullptr) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+template <typename InT, typename OutT>
+int launch_ln(const void* x, int ldx, const float* g, const float* b, void* y, int ldy, int rows, int D, float eps,
+              float* mean, float* rstd, cudaStream_t st) {
+  const int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  const InT* xi = static_cast<const InT*>(x);
+  OutT* yo = static_cast<OutT*>(y);
+  if (D <= 256) layernorm_kernel<InT, OutT, 2><<<grid, 256, 0, st>>>(xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd);
+  else if (D <= 512) layernorm_kernel<InT, OutT, 4><<<grid, 256, 0, st>>>(xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd);
+  else if (D <= 1024) layernorm_kernel<InT, OutT, 8><<<grid, 256, 0, st>>>(xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd);
+  else layernorm_kernel<InT, OutT, 16><<<grid, 256, 0, st>>>(xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd);
+  MEBT_LAUNCH_OK("layernorm_kernel");
+  return MEBT_OK;
+}
+
+}  // namespace
+
+int* err_flag_ptr() { return device_err_flag(); }
+
+int embed_gather(const int64_t* x, int x_stride, const int64_t* ctx_idx, int ctx_stride, const int64_t* tgt_idx,
+                 int tgt_stride, const float* tok_emb, const float* pos_emb, const float* mask_emb,
+                 const float* sos_emb, void* contexts, void* targets, void* latents, int B, int NC, int NT, int L, int D,
+                 int V, int n_pos, int out_dtype, cudaStream_t st) {
+  MEBT_REQUIRE(B > 0 && NC >= 0 && NT >= 0 && L >= 0 && D > 0 && D % 4 == 0, MEBT_ERR_SHAPE,
+               "embed_gather: bad shape B=%d NC=%d NT=%d L=%d D=%d", B, NC, NT, L, D);
+  int* flag = device_err_flag();
+  MEBT_REQUIRE(flag != nullptr, MEBT_ERR_CUDA, "embed_gather: cannot allocate error flag");
+  const long long rows = (long long)B * (NC + NT + L);
+  if (rows == 0) return MEBT_OK;
+  const int grid = int((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  if (out_dtype == MEBT_DTYPE_BF16)
+    embed_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        x, x_stride, ctx_idx, ctx_stride, tgt_idx, tgt_stride, tok_emb, pos_emb, mask_emb, sos_emb,
+        static_cast<__nv_bfloat16*>(contexts), static_cast<__nv_bfloat16*>(targets),
+        static_cast<__nv_bfloat16*>(latents), B, NC, NT, L, D, V, n_pos, flag);
+  else if (out_dtype == MEBT_DTYPE_FP32)
+    embed_gather_kernel<float><<<grid, 256, 0, st>>>(x, x_stride, ctx_idx, ctx_stride, tgt_idx, tgt_stride, tok_emb,
+                                                      pos_emb, mask_emb, sos_emb, static_cast<float*>(contexts),
+                                                      static_cast<float*>(targets), static_cast<float*>(latents), B,
+                                                      NC, NT, L, D, V, n_pos, flag);
+  else
+    MEBT_REQUIRE(false, MEBT_ERR_DTYPE, "embed_gather: unsupported out dtype %d", out_dtype);
+  MEBT_LAUNCH_OK("embed_gather_kernel");
+  return MEBT_OK;
+}
+
+int layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const float* beta, void* y, int ldy,
+              int out_dtype, int rows, int D, float eps, float* mean, float* rstd, cudaStream_t st) {
+  MEBT_REQUIRE(rows >= 0 && D > 0 && D % 4 == 0 && D <= 2048, MEBT_ERR_SHAPE, "layernorm: bad shape rows=%d D=%d",
+               rows, D);
+  MEBT_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, MEBT_ERR_SHAPE, "layernorm: row strides must be multiples of 4");
+  if (rows == 0) return MEBT_OK;
+  if (in_dtype == MEBT_DTYPE_BF16 && out_dtype == MEBT_DTYPE_BF16)
+    return launch_ln<__nv_bfloat16, __nv_bfloat16>(x, ldx, gamma, beta, y, ldy, rows, D, eps, mean, rstd, st);
+  if (in_dtype == MEBT_DTYPE_FP32 && out_dtype == MEBT_DTYPE_BF16)
+    return launch_ln<float, __nv_bfloat16>(x, ldx, gamma, beta, y, ldy, rows, D, eps, mean, rstd, st);
+  if (in_dtype == MEBT_DTYPE_FP32 && out_dtype == MEBT_DTYPE_FP32)
+    return launch_ln<float, float>(x, ldx, gamma, beta, y, ldy, rows, D, eps, mean, rstd, st);
+  if (in_dtype == MEBT_DTYPE_BF16 && out_dtype == MEBT_DTYPE_FP32)
+    return launch_ln<__nv_bfloat16, float>(x, ldx, gamma, beta, y, ldy, rows, D, eps, mean, rstd, st);
+  MEBT_REQUIRE(false, MEBT_ERR_DTYPE, "layernorm: unsupported dtypes %d -> %d", in_dtype, out_dtype);
+  return MEBT_OK;
+}
+
+}  // namespace mebt
+
+extern "C" {
+
+int mebt_embed_gather(const int64_t* x_indices, int x_stride, const int64_t* ctx_idx, int ctx_stride,
+                      const int64_t* tgt_idx, int tgt_stride, const float* tok_emb, const float* pos_emb,
+                      const float* mask_emb, const float* sos_emb, void* contexts, void* targets, void* latents, int B,
+                      int NC, int NT, int L, int D, int V, int n_pos, int out_dtype, void* stream) {
+  return mebt::embed_gather(x_indices, x_stride, ctx_idx, ctx_stride, tgt_idx, tgt_stride, tok_emb, pos_emb, mask_emb,
+                            sos_emb, contexts, targets, latents, B, NC, NT, L, D, V, n_pos, out_dtype,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int mebt_layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const float* beta, void* y, int ldy,
+                   int out_dtype, int rows, int D, float eps, float* mean_out, float* rstd_out, void* stream) {
+  return mebt::layernorm(x, ldx, in_dtype, gamma, beta, y, ldy, out_dtype, rows, D, eps, mean_out, rstd_out,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int mebt_scatter_ids(int64_t* x, int x_stride, const int64_t* tgt_idx, int tgt_stride, const int64_t* ids, int B, int NT,
+                     int N, void* stream) {
+  MEBT_REQUIRE(B >= 0 && NT >= 0 && N > 0, MEBT_ERR_SHAPE, "scatter_ids: bad shape");
+  const long long n = (long long)B * NT;
+  if (n == 0) return MEBT_OK;
+  int* flag = mebt::err_flag_ptr();
+  MEBT_REQUIRE(flag != nullptr, MEBT_ERR_CUDA, "scatter_ids: cannot allocate error flag");
+  mebt::scatter_ids_kernel<<<int((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, x_stride, tgt_idx, tgt_stride, ids, B, NT, N, flag);
+  MEBT_LAUNCH_OK("scatter_ids_kernel");
+  return MEBT_OK;
+}
+
+int mebt_row_gather(const int64_t* enc, const float* E, float* out, int batch, int S, int C, int K, int channel_first,
+                    void* stream) {
+  MEBT_REQUIRE(batch >= 0 && S >= 0 && C > 0 && K > 0, MEBT_ERR_SHAPE, "row_gather: bad shape");
+  const long long M = (long long)batch * S;
+  if (M == 0) return MEBT_OK;
+  int* flag = mebt::err_flag_ptr();
+  MEBT_REQUIRE(flag != nullptr, MEBT_ERR_CUDA, "row_gather: cannot allocate error flag");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (channel_first) {
+    dim3 grid((S + 31) / 32, (C + 31) / 32, batch), block(32, 8);
+    mebt::row_gather_cf_kernel<<<grid, block, 0, st>>>(enc, E, out, S, C, K, flag);
+  } else {
+    MEBT_REQUIRE(C % 4 == 0, MEBT_ERR_SHAPE, "row_gather: C must be a multiple of 4");
+    mebt::row_gather_kernel<<<int((M + mebt::ROWS_PER_BLOCK - 1) / mebt::ROWS_PER_BLOCK), 256, 0, st>>>(enc, E, out, M,
+                                                                                                          C, K, flag);
+  }
+  MEBT_LAUNCH_OK("row_gather_kernel");
+  return MEBT_OK;
+}
+
+int mebt_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream) {
+  MEBT_REQUIRE(n >= 0 && n % 4 == 0, MEBT_ERR_SHAPE, "cast: n must be a multiple of 4");
+  if (n == 0) return MEBT_OK;
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mebt::cast_f32_bf16_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, static_cast<__nv_bfloat16*>(out), n4);
+  MEBT_LAUNCH_OK("cast_f32_bf16_kernel");
+  return MEBT_OK;
+}
+
+// Index-range violations are recorded on the device (kernels never read out of bounds); this reads and
+// clears the flag.  It synchronises the stream, so call it from tests / debug paths only.
+int mebt_check_index_errors(void* stream) {
+  int* flag = mebt::err_flag_ptr();
+  MEBT_REQUIRE(flag != nullptr, MEBT_ERR_CUDA, "cannot allocate error flag");
+  int h = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MEBT_CUDA_OK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MEBT_CUDA_OK(cudaStreamSynchronize(st));
+  if (h != 0) {
+    cudaMemsetAsync(flag, 0, sizeof(int), st);
+    mebt::set_last_error("index out of range detected on device (kind %d)", h);
+    return MEBT_ERR_SHAPE;
+  }
+  return MEBT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,393 @@
+// K5 / K6: consumers of the 16384-way logit rows.  One CTA (256 threads) owns one row and keeps it in
+// registers (64 values per thread), so each logit is read from HBM exactly once:
+//   K5 masked cross-entropy (+ label smoothing, + rank of the target for top-1/top-5, + dlogits)
+//      reference: F.cross_entropy(sum) at mebt/transformer.py:726 and accuracy() at mebt/utils.py:80-94
+//   K6 temperature / top-k / softmax / Exp-race ("Gumbel") argmax / confidence score
+//      reference: sample_from_logits + gumbel_sort, mebt/transformer.py:843-889 / :826-841
+#include "common.cuh"
+
+namespace mebt {
+namespace {
+
+constexpr int LT = 256;          // threads per row
+constexpr int MAX_V4 = 16;       // float4 groups per thread  -> V <= 256 * 16 * 4 = 16384
+
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < LT / 32; ++i) r = fmaxf(r, red[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < LT / 32; ++i) r += red[i];   // fixed order: deterministic
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ int block_sum_int(int v, int* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = 0;
+#pragma unroll
+  for (int i = 0; i < LT / 32; ++i) r += red[i];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LT) masked_ce_kernel(const T* __restrict__ logits, long long ld,
+                                                       const int64_t* __restrict__ targets, int V, float smoothing,
+                                                       float* __restrict__ row_loss, int* __restrict__ row_rank,
+                                                       T* __restrict__ dlogits, long long ldd, float grad_scale) {
+  __shared__ float red[LT / 32];
+  __shared__ int redi[LT / 32];
+  const long long row = blockIdx.x;
+  const T* xr = logits + row * ld;
+  const int tgt = int(targets[row]);
+  float4 v[MAX_V4];
+  float m = -INFINITY, total = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) {
+    const int c = (threadIdx.x + LT * i) * 4;
+    if (c < V) {
+      v[i] = load4<T>(xr + c);
+      m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+      total += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  m = block_max(m, red);
+  total = block_sum(total, red);
+  const float xt = (tgt >= 0 && tgt < V) ? float(xr[tgt]) : 0.f;
+  float se = 0.f;
+  int rank = 0;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) {
+    const int c = (threadIdx.x + LT * i) * 4;
+    if (c < V) {
+      se += (expf(v[i].x - m) + expf(v[i].y - m)) + (expf(v[i].z - m) + expf(v[i].w - m));
+      rank += (v[i].x > xt) + (v[i].y > xt) + (v[i].z > xt) + (v[i].w > xt);
+    }
+  }
+  se = block_sum(se, red);
+  rank = block_sum_int(rank, redi);
+  const float lse = m + logf(se);
+  if (threadIdx.x == 0) {
+    const float nll = lse - xt;
+    const float smooth = lse - total / float(V);
+    row_loss[row] = (1.f - smoothing) * nll + smoothing * smooth;
+    if (row_rank != nullptr) row_rank[row] = rank;
+  }
+  if (dlogits != nullptr) {
+    // d(sum CE)/dlogit_v = softmax_v - (1-eps) [v == t] - eps / V, times the upstream scale
+    T* dr = dlogits + row * ldd;
+    const float inv = 1.f / se, u = smoothing / float(V);
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i) {
+      const int c = (threadIdx.x + LT * i) * 4;
+      if (c < V) {
+        float4 g;
+        g.x = expf(v[i].x - m) * inv - u;
+        g.y = expf(v[i].y - m) * inv - u;
+        g.z = expf(v[i].z - m) * inv - u;
+        g.w = expf(v[i].w - m) * inv - u;
+        if (tgt >= c && tgt < c + 4) (&g.x)[tgt - c] -= (1.f - smoothing);
+        g.x *= grad_scale; g.y *= grad_scale; g.z *= grad_scale; g.w *= grad_scale;
+        store4<T>(dr + c, g);
+      }
+    }
+  }
+}
+
+// deterministic single-CTA reduction of the per-row results: out = {ce_sum, n_top1, n_top5}
+__global__ void ce_reduce_kernel(const float* __restrict__ row_loss, const int* __restrict__ row_rank, int rows,
+                                 float* __restrict__ out) {
+  __shared__ double sd[1024];
+  __shared__ int s1[1024], s5[1024];
+  double acc = 0.0;
+  int n1 = 0, n5 = 0;
+  for (int i = threadIdx.x; i < rows; i += 1024) {
+    acc += double(row_loss[i]);
+    if (row_rank != nullptr) {
+      const int r = row_rank[i];
+      n1 += (r == 0);
+      n5 += (r < 5);
+    }
+  }
+  sd[threadIdx.x] = acc; s1[threadIdx.x] = n1; s5[threadIdx.x] = n5;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sd[threadIdx.x] += sd[threadIdx.x + o];
+      s1[threadIdx.x] += s1[threadIdx.x + o];
+      s5[threadIdx.x] += s5[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = float(sd[0]);
+    out[1] = float(s1[0]);
+    out[2] = float(s5[0]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_order_key(float f) {   // monotone float -> uint32
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Philox4x32-10 (Salmon et al.), counter = (row, group, offset_lo, offset_hi), key = seed
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float exp1_from_bits(uint32_t x) {   // Exp(1) draw; u in (0, 1]
+  const float u = (float(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  return -__logf(u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LT) sample_logits_kernel(const T* __restrict__ logits, long long ld, int V,
+                                                           float temp_div, int top_k, const float* __restrict__ noise,
+                                                           unsigned long long seed, unsigned long long offset,
+                                                           int64_t* __restrict__ ids, float* __restrict__ scores,
+                                                           float* __restrict__ probs_out) {
+  __shared__ float red[LT / 32];
+  __shared__ int hist[256];
+  __shared__ uint32_t sel_prefix;
+  __shared__ int sel_remaining;
+  __shared__ float best_val[LT / 32];
+  __shared__ int best_idx[LT / 32];
+  const long long row = blockIdx.x;
+  const T* xr = logits + row * ld;
+  float4 v[MAX_V4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) {
+    const int c = (threadIdx.x + LT * i) * 4;
+    if (c < V) {
+      float4 t = load4<T>(xr + c);
+      // logits.float() / (temperature + 1e-8), true division as on the CPU path (transformer.py:859-860)
+      t.x = __fdiv_rn(t.x, temp_div); t.y = __fdiv_rn(t.y, temp_div);
+      t.z = __fdiv_rn(t.z, temp_div); t.w = __fdiv_rn(t.w, temp_div);
+      // NaN scrub (transformer.py:866-868), without the host sync
+      if (t.x != t.x) t.x = -INFINITY;
+      if (t.y != t.y) t.y = -INFINITY;
+      if (t.z != t.z) t.z = -INFINITY;
+      if (t.w != t.w) t.w = -INFINITY;
+      v[i] = t;
+    } else {
+      v[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+  }
+
+  if (top_k > 0 && top_k < V) {
+    // k-th largest value by 4-pass radix select on the order-preserving key (top_k_logits, transformer.py:891-895:
+    // everything strictly below the k-th largest value becomes -inf; ties with it survive)
+    if (threadIdx.x == 0) { sel_prefix = 0; sel_remaining = top_k; }
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      hist[threadIdx.x] = 0;
+      __syncthreads();
+      const uint32_t prefix = sel_prefix;
+      const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+#pragma unroll
+      for (int i = 0; i < MAX_V4; ++i) {
+        const int c = (threadIdx.x + LT * i) * 4;
+        if (c < V) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t key = float_order_key((&v[i].x)[j]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int remaining = sel_remaining, b = 255;
+        for (; b > 0; --b) {
+          if (hist[b] >= remaining) break;
+          remaining -= hist[b];
+        }
+        sel_prefix = prefix | (uint32_t(b) << shift);
+        sel_remaining = remaining;
+      }
+      __syncthreads();
+    }
+    const uint32_t kth = sel_prefix;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (float_order_key((&v[i].x)[j]) < kth) (&v[i].x)[j] = -INFINITY;
+  }
+
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+  m = block_max(m, red);
+  float se = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) {
+    v[i].x = expf(v[i].x - m); v[i].y = expf(v[i].y - m); v[i].z = expf(v[i].z - m); v[i].w = expf(v[i].w - m);
+    se += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  se = block_sum(se, red);
+  // probs = softmax; psum = probs.sum() as gumbel_sort renormalises (transformer.py:834)
+  float psum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) {
+    v[i].x = __fdiv_rn(v[i].x, se); v[i].y = __fdiv_rn(v[i].y, se);
+    v[i].z = __fdiv_rn(v[i].z, se); v[i].w = __fdiv_rn(v[i].w, se);
+    psum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  psum = block_sum(psum, red);
+
+  float best = -1.f, best_p = 0.f;
+  int besti = 0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) {
+    const int c = (threadIdx.x + LT * i) * 4;
+    if (c < V) {
+      if (probs_out != nullptr) *reinterpret_cast<float4*>(probs_out + row * V + c) = v[i];
+      float4 q;
+      if (noise != nullptr) {
+        q = __ldg(reinterpret_cast<const float4*>(noise + row * V + c));
+      } else {
+        const uint4 r = philox4x32(make_uint4(uint32_t(row), uint32_t(c >> 2) | (uint32_t(row >> 32) << 16),
+                                              uint32_t(offset), uint32_t(offset >> 32)),
+                                   make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+        q = make_float4(exp1_from_bits(r.x), exp1_from_bits(r.y), exp1_from_bits(r.z), exp1_from_bits(r.w));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p = (&v[i].x)[j];
+        // (p / sum p) / q, zeroed where p == 0 (transformer.py:834-838); first index wins ties
+        const float race = p > 0.f ? __fdiv_rn(__fdiv_rn(p, psum), (&q.x)[j]) : 0.f;
+        if (race > best) { best = race; besti = c + j; best_p = p; }
+      }
+    }
+  }
+  // block arg-max, lowest index on ties
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    const float op = __shfl_xor_sync(0xffffffffu, best_p, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; best_p = op; }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    best_val[threadIdx.x >> 5] = best;
+    best_idx[threadIdx.x >> 5] = besti;
+    red[threadIdx.x >> 5] = best_p;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < LT / 32; ++w)
+      if (best_val[w] > best || (best_val[w] == best && best_idx[w] < besti)) {
+        best = best_val[w]; besti = best_idx[w]; best_p = red[w];
+      }
+    ids[row] = besti;
+    if (scores != nullptr) scores[row] = best_p;
+  }
+}
+
+}  // namespace
+}  // namespace mebt
+
+extern "C" {
+
+int mebt_masked_ce(const void* logits, long long ld, int dtype, const int64_t* targets, int rows, int V,
+                   float label_smoothing, float* row_loss, int* row_rank, void* dlogits, long long ld_d,
+                   float grad_scale, void* stream) {
+  using namespace mebt;
+  MEBT_REQUIRE(rows >= 0 && V > 0 && V % 4 == 0 && V <= LT * MAX_V4 * 4, MEBT_ERR_SHAPE,
+               "masked_ce: V=%d must be a multiple of 4 and <= %d", V, LT * MAX_V4 * 4);
+  MEBT_REQUIRE(ld % 4 == 0 && (dlogits == nullptr || ld_d % 4 == 0), MEBT_ERR_SHAPE, "masked_ce: bad row stride");
+  if (rows == 0) return MEBT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MEBT_DTYPE_FP32)
+    masked_ce_kernel<float><<<rows, LT, 0, st>>>(static_cast<const float*>(logits), ld, targets, V, label_smoothing,
+                                                 row_loss, row_rank, static_cast<float*>(dlogits), ld_d, grad_scale);
+  else if (dtype == MEBT_DTYPE_BF16)
+    masked_ce_kernel<__nv_bfloat16><<<rows, LT, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, targets, V,
+                                                         label_smoothing, row_loss, row_rank,
+                                                         static_cast<__nv_bfloat16*>(dlogits), ld_d, grad_scale);
+  else
+    MEBT_REQUIRE(false, MEBT_ERR_DTYPE, "masked_ce: unsupported dtype %d", dtype);
+  MEBT_LAUNCH_OK("masked_ce_kernel");
+  return MEBT_OK;
+}
+
+int mebt_ce_reduce(const float* row_loss, const int* row_rank, int rows, float* out3, void* stream) {
+  MEBT_REQUIRE(rows >= 0, MEBT_ERR_SHAPE, "ce_reduce: bad rows");
+  mebt::ce_reduce_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(row_loss, row_rank, rows, out3);
+  MEBT_LAUNCH_OK("ce_reduce_kernel");
+  return MEBT_OK;
+}
+
+int mebt_sample_logits(const void* logits, long long ld, int dtype, int rows, int V, float temperature, int top_k,
+                       float top_p, const float* noise, unsigned long long seed, unsigned long long offset,
+                       int64_t* ids, float* scores, float* probs, void* stream) {
+  using namespace mebt;
+  MEBT_REQUIRE(rows >= 0 && V > 0 && V % 4 == 0 && V <= LT * MAX_V4 * 4, MEBT_ERR_SHAPE,
+               "sample_logits: V=%d must be a multiple of 4 and <= %d", V, LT * MAX_V4 * 4);
+  MEBT_REQUIRE(ld % 4 == 0, MEBT_ERR_SHAPE, "sample_logits: bad row stride");
+  MEBT_REQUIRE(!(top_p > 0.f && top_p < 1.f), MEBT_ERR_UNSUPPORTED,
+               "sample_logits: nucleus (top_p) filtering is not implemented on the device path yet");
+  if (rows == 0) return MEBT_OK;
+  // python: temperature + 1e-8 in double, then cast to fp32 for the tensor division
+  const float temp_div = float(double(temperature) + 1e-8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MEBT_DTYPE_FP32)
+    sample_logits_kernel<float><<<rows, LT, 0, st>>>(static_cast<const float*>(logits), ld, V, temp_div, top_k, noise,
+                                                     seed, offset, ids, scores, probs);
+  else if (dtype == MEBT_DTYPE_BF16)
+    sample_logits_kernel<__nv_bfloat16><<<rows, LT, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, V,
+                                                             temp_div, top_k, noise, seed, offset, ids, scores, probs);
+  else
+    MEBT_REQUIRE(false, MEBT_ERR_DTYPE, "sample_logits: unsupported dtype %d", dtype);
+  MEBT_LAUNCH_OK("sample_logits_kernel");
+  return MEBT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+"""Tensor-level wrappers over the C ABI (include/mebt_b200.h).
+
+torch is used for device memory and streams only: every function below hands raw device pointers to a
+hand-written sm_100a kernel and raises `MebtError` on any failure.  There is no eager/PyTorch fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import MebtError, call
+
+BF16, FP32 = 0, 1
+GEMM_GELU, GEMM_OUT_FP32, GEMM_ACCUMULATE = 1, 2, 4
+
+_DT = {torch.bfloat16: BF16, torch.float32: FP32}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise MebtError("mebt_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _rows2d(t: torch.Tensor):
+    """(rows, cols, row_stride) of a tensor viewed as 2-D with a unit-stride last dim."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise MebtError(f"expected a 2-D tensor with contiguous rows, got shape {tuple(t.shape)} stride {t.stride()}")
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, bias=None, residual=None, gelu=False, out=None, out_dtype=torch.bfloat16,
+         a_mn_major=False, b_mn_major=False, accumulate=False, flags_extra=0) -> torch.Tensor:
+    """out[M,N] = act(A @ B^T + bias) + residual.  a: [M,K] (or [K,M] if a_mn_major); b: [N,K] (or [K,N])."""
+    _need_cuda(a, b, bias, residual, out)
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise MebtError("gemm operands must be bf16")
+    ar, ac, lda = _rows2d(a)
+    br, bc, ldb = _rows2d(b)
+    M, K = (ac, ar) if a_mn_major else (ar, ac)
+    N, Kb = (bc, br) if b_mn_major else (br, bc)
+    if K != Kb:
+        raise MebtError(f"gemm: reduction dims differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    orr, occ, ldc = _rows2d(out)
+    if (orr, occ) != (M, N):
+        raise MebtError("gemm: bad out shape")
+    flags = flags_extra
+    if gelu:
+        flags |= GEMM_GELU
+    if out.dtype == torch.float32:
+        flags |= GEMM_OUT_FP32
+    elif out.dtype != torch.bfloat16:
+        raise MebtError("gemm: out must be bf16 or fp32")
+    if accumulate:
+        flags |= GEMM_ACCUMULATE
+    ldres = 0
+    if residual is not None:
+        rr, rc, ldres = _rows2d(residual)
+        if (rr, rc) != (M, N) or residual.dtype != torch.bfloat16:
+            raise MebtError("gemm: residual must be bf16 [M,N]")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise MebtError("gemm: bias must be contiguous fp32 [N]")
+    call("mebt_gemm_bf16", a.data_ptr(), lda, int(a_mn_major), b.data_ptr(), ldb, int(b_mn_major), out.data_ptr(), ldc,
+         M, N, K, _ptr(bias), _ptr(residual), ldres, flags, _stream())
+    return out
+
+
+def embed_gather(x_indices, ctx_idx, tgt_idx, tok_emb, pos_emb, mask_emb, sos_emb, out_dtype=torch.bfloat16):
+    """Stem of reconstruct_mask -> (contexts [B*NC,D], targets [B*NT,D], latents [B*L,D])."""
+    _need_cuda(x_indices, ctx_idx, tgt_idx, tok_emb, pos_emb, mask_emb, sos_emb)
+    B, N = x_indices.shape
+    NC, NT = ctx_idx.shape[1], tgt_idx.shape[1]
+    V, D = tok_emb.shape
+    pos2 = pos_emb.reshape(-1, D)
+    sos2 = sos_emb.reshape(-1, D)
+    L = sos2.shape[0]
+    for t in (x_indices, ctx_idx, tgt_idx):
+        if t.dtype != torch.int64 or (t.shape[1] > 0 and t.stride(1) != 1):
+            raise MebtError("index tensors must be int64 with unit inner stride")
+    for t in (tok_emb, pos2, mask_emb, sos2):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise MebtError("embedding tables must be contiguous fp32")
+    dev = x_indices.device
+    ctx = torch.empty(B * NC, D, device=dev, dtype=out_dtype)
+    tgt = torch.empty(B * NT, D, device=dev, dtype=out_dtype)
+    lat = torch.empty(B * L, D, device=dev, dtype=out_dtype)
+    call("mebt_embed_gather", x_indices.data_ptr(), x_indices.stride(0), ctx_idx.data_ptr(),
+         ctx_idx.stride(0) if NC > 0 else 0, tgt_idx.data_ptr(), tgt_idx.stride(0) if NT > 0 else 0,
+         tok_emb.data_ptr(), pos2.data_ptr(), mask_emb.data_ptr(), sos2.data_ptr(), ctx.data_ptr(), tgt.data_ptr(),
+         lat.data_ptr(), B, NC, NT, L, D, V, pos2.shape[0], _DT[out_dtype], _stream())
+    return ctx, tgt, lat
+
+
+def layernorm(x, gamma, beta, out=None, out_dtype=None, eps=1e-5, save_stats=False):
+    _need_cuda(x, gamma, beta)
+    rows, D, ldx = _rows2d(x)
+    if out is None:
+        out = torch.empty(rows, D, device=x.device, dtype=out_dtype or x.dtype)
+    _, _, ldy = _rows2d(out)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    call("mebt_layernorm", x.data_ptr(), ldx, _DT[x.dtype], gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), ldy,
+         _DT[out.dtype], rows, D, float(eps), _ptr(mean), _ptr(rstd), _stream())
+    return (out, mean, rstd) if save_stats else out
+
+
+def attention(q, q_col0, kv1, k1_col0, v1_col0, nk1, kv2, k2_col0, v2_col0, nk2, B, H, NQ, out=None, lse=None):
+    """q: [B*NQ, ldq] bf16 buffer; kv1/kv2: [B*NK, ld] buffers (or None).  Returns O [B*NQ, H*64] bf16."""
+    _need_cuda(q, kv1, kv2)
+    D = H * 64
+    if out is None:
+        out = torch.empty(B * NQ, D, device=q.device, dtype=torch.bfloat16)
+    call("mebt_latent_attention_fwd", q.data_ptr(), q.stride(0), q_col0,
+         _ptr(kv1) if nk1 > 0 else None, kv1.stride(0) if nk1 > 0 else 0, k1_col0, v1_col0, nk1,
+         _ptr(kv2) if nk2 > 0 else None, kv2.stride(0) if nk2 > 0 else 0, k2_col0, v2_col0, nk2,
+         out.data_ptr(), out.stride(0), _ptr(lse), B, H, NQ, 64, _stream())
+    return out
+
+
+def scatter_ids(x, tgt_idx, ids):
+    """x[b, tgt_idx[b,i]] = ids[b,i] in place."""
+    _need_cuda(x, tgt_idx, ids)
+    B, N = x.shape
+    NT = tgt_idx.shape[1]
+    ids = ids.contiguous()
+    call("mebt_scatter_ids", x.data_ptr(), x.stride(0), tgt_idx.data_ptr(), tgt_idx.stride(0) if NT else 0,
+         ids.data_ptr(), B, NT, N, _stream())
+    return x
+
+
+def masked_ce(logits, targets, label_smoothing=0.0, dlogits=None, grad_scale=1.0):
+    """-> (stats fp32[3] = {ce_sum, n_top1, n_top5}, row_loss fp32 [rows]).  logits: [rows, V] fp32/bf16."""
+    _need_cuda(logits, targets)
+    rows, V, ld = _rows2d(logits)
+    targets = targets.reshape(-1).contiguous()
+    row_loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    row_rank = torch.empty(rows, device=logits.device, dtype=torch.int32)
+    ldd = 0
+    if dlogits is not None:
+        _, _, ldd = _rows2d(dlogits)
+        if dlogits.dtype != logits.dtype:
+            raise MebtError("dlogits dtype must match logits")
+    call("mebt_masked_ce", logits.data_ptr(), ld, _DT[logits.dtype], targets.data_ptr(), rows, V,
+         float(label_smoothing), row_loss.data_ptr(), row_rank.data_ptr(), _ptr(dlogits), ldd, float(grad_scale),
+         _stream())
+    stats = torch.empty(3, device=logits.device, dtype=torch.float32)
+    call("mebt_ce_reduce", row_loss.data_ptr(), row_rank.data_ptr(), rows, stats.data_ptr(), _stream())
+    return stats, row_loss
+
+
+def sample_logits(logits, temperature=1.0, top_k=None, top_p=None, noise=None, seed=0, offset=0, return_probs=False):
+    """logits [rows, V] -> (ids int64 [rows], scores fp32 [rows], probs fp32 [rows,V] | None)."""
+    _need_cuda(logits, noise)
+    rows, V, ld = _rows2d(logits)
+    ids = torch.empty(rows, device=logits.device, dtype=torch.int64)
+    scores = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    probs = torch.empty(rows, V, device=logits.device, dtype=torch.float32) if return_probs else None
+    if noise is not None:
+        if noise.dtype != torch.float32 or not noise.is_contiguous() or noise.numel() != rows * V:
+            raise MebtError("noise must be contiguous fp32 [rows, V]")
+    call("mebt_sample_logits", logits.data_ptr(), ld, _DT[logits.dtype], rows, V, float(temperature),
+         int(top_k) if top_k else 0, float(top_p) if top_p is not None else 0.0, _ptr(noise), int(seed), int(offset),
+         ids.data_ptr(), scores.data_ptr(), _ptr(probs), _stream())
+    return ids, scores, probs
+
+
+def remask_sort(score, ctx_idx, tgt_idx, n_new, ctemp, noise=None, seed=0, offset=0, want_order=False):
+    """-> (next_ctx [B,NC+n_new], next_tgt [B,NT-n_new], order | None)."""
+    _need_cuda(score, ctx_idx, tgt_idx, noise)
+    B, NT = score.shape
+    NC = ctx_idx.shape[1]
+    score = score.contiguous().float()
+    dev = score.device
+    next_ctx = torch.empty(B, NC + n_new, device=dev, dtype=torch.int64)
+    next_tgt = torch.empty(B, NT - n_new, device=dev, dtype=torch.int64)
+    order = torch.empty(B, NT, device=dev, dtype=torch.int64) if want_order else None
+    if noise is not None:
+        noise = noise.contiguous().float()
+    call("mebt_remask_sort", score.data_ptr(), _ptr(noise), float(ctemp), ctx_idx.data_ptr(),
+         ctx_idx.stride(0) if NC else 0, tgt_idx.data_ptr(), tgt_idx.stride(0), B, NC, NT, int(n_new), int(seed),
+         int(offset), next_ctx.data_ptr(), next_tgt.data_ptr(), _ptr(order), _stream())
+    return next_ctx, next_tgt, order
+
+
+def row_sqnorm(E):
+    _need_cuda(E)
+    K, C = E.shape
+    out = torch.empty(K, device=E.device, dtype=torch.float32)
+    call("mebt_row_sqnorm", E.data_ptr(), K, C, out.data_ptr(), _stream())
+    return out
+
+
+def vq_argmin(z, E, e_sqnorm=None):
+    """z: [b, C, ...] fp32 channel-first; E: [K, C] fp32 -> encodings int64 [b, ...]."""
+    _need_cuda(z, E)
+    z = z.contiguous()
+    b, C = z.shape[:2]
+    S = z[0, 0].numel()
+    K = E.shape[0]
+    if e_sqnorm is None:
+        e_sqnorm = row_sqnorm(E)
+    out = torch.empty(b * S, device=z.device, dtype=torch.int64)
+    ws_bytes = _lib.lib.mebt_vq_argmin_workspace_bytes(b * S)
+    ws = torch.empty(ws_bytes, device=z.device, dtype=torch.uint8)
+    call("mebt_vq_argmin", z.data_ptr(), b, C, S, E.data_ptr(), e_sqnorm.data_ptr(), K, out.data_ptr(), ws.data_ptr(),
+         ws_bytes, _stream())
+    return out.view(b, *z.shape[2:])
+
+
+def row_gather(enc, E, channel_first=False):
+    """F.embedding(enc, E); channel_first=True returns [b, C, ...] like shift_dim(h, -1, 1)."""
+    _need_cuda(enc, E)
+    enc = enc.contiguous()
+    K, C = E.shape
+    b = enc.shape[0]
+    S = enc[0].numel()
+    if channel_first:
+        out = torch.empty(b, C, *enc.shape[1:], device=enc.device, dtype=torch.float32)
+    else:
+        out = torch.empty(*enc.shape, C, device=enc.device, dtype=torch.float32)
+    call("mebt_row_gather", enc.data_ptr(), E.data_ptr(), out.data_ptr(), b, S, C, K, int(channel_first), _stream())
+    return out
+
+
+def cast_bf16(x):
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    call("mebt_cast_f32_to_bf16", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
+def check_index_errors():
+    call("mebt_check_index_errors", _stream())

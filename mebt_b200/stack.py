@@ -1,0 +1,143 @@
+"""The MeBT layer stack composed from the C-ABI kernels, one kernel call per op.
+
+This is the op-by-op composition used by the drop-in `GPT` / `Block` / `CrossAttention` modules.  Activations
+are bf16 2-D buffers ([B*rows, D]); accumulation, LayerNorm statistics, softmax and logits are fp32.
+
+Reference behaviour reproduced (mebt/modules/gpt.py:159-195, :234-253):
+  * ln1 is applied to BOTH the query stream and the key stream of a block (same parameters);
+  * the attention residual is added to the *normalised* query, `x = ln1(q) + attn`;
+  * contexts are never updated by the four latent modes; the head reads `targets` only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Mapping
+
+import torch
+
+from . import ops
+
+LATENT_MODES = ("latent_enc", "latent_self", "latent_dec", "lt2l")
+
+
+@dataclass
+class LayerWeights:
+    mode: str
+    ln1_w: torch.Tensor
+    ln1_b: torch.Tensor
+    ln2_w: torch.Tensor
+    ln2_b: torch.Tensor
+    w_qkv: torch.Tensor      # bf16 [3D, D] rows = (query, key, value)
+    b_qkv: torch.Tensor      # fp32 [3D]
+    w_proj: torch.Tensor     # bf16 [D, D]
+    b_proj: torch.Tensor
+    w_fc1: torch.Tensor      # bf16 [4D, D]
+    b_fc1: torch.Tensor
+    w_fc2: torch.Tensor      # bf16 [D, 4D]
+    b_fc2: torch.Tensor
+
+
+class WeightPack:
+    """bf16 tensor-core operands built from fp32 parameters named as in the reference state_dict."""
+
+    def __init__(self, params: Mapping[str, torch.Tensor], modes, n_head: int, prefix: str = "transformer."):
+        self.modes = list(modes)
+        self.n_head = n_head
+        self.layers: list[LayerWeights] = []
+        f32 = lambda t: t.detach().float().contiguous()
+        for i, mode in enumerate(self.modes):
+            p = f"{prefix}blocks.{i}."
+            wq, wk, wv = (params[p + f"attn.{n}.weight"].detach().float() for n in ("query", "key", "value"))
+            bq, bk, bv = (params[p + f"attn.{n}.bias"].detach().float() for n in ("query", "key", "value"))
+            self.layers.append(LayerWeights(
+                mode=mode,
+                ln1_w=f32(params[p + "ln1.weight"]), ln1_b=f32(params[p + "ln1.bias"]),
+                ln2_w=f32(params[p + "ln2.weight"]), ln2_b=f32(params[p + "ln2.bias"]),
+                w_qkv=ops.cast_bf16(torch.cat([wq, wk, wv], 0)), b_qkv=torch.cat([bq, bk, bv]).contiguous(),
+                w_proj=ops.cast_bf16(f32(params[p + "attn.proj.weight"])), b_proj=f32(params[p + "attn.proj.bias"]),
+                w_fc1=ops.cast_bf16(f32(params[p + "mlp.0.weight"])), b_fc1=f32(params[p + "mlp.0.bias"]),
+                w_fc2=ops.cast_bf16(f32(params[p + "mlp.2.weight"])), b_fc2=f32(params[p + "mlp.2.bias"])))
+        self.lnf_w = f32(params[prefix + "ln_f.weight"])
+        self.lnf_b = f32(params[prefix + "ln_f.bias"])
+        self.w_head = ops.cast_bf16(f32(params[prefix + "head.weight"]))
+        self.D = self.lnf_w.numel()
+
+    def last_live_layer(self) -> int:
+        """Blocks after the last one writing `targets` cannot reach the logits (gpt.py:247 reads targets only)."""
+        live = -1
+        for i, m in enumerate(self.modes):
+            if m in ("latent_dec", "maskgit"):
+                live = i
+        return live
+
+
+def attention_core(w: LayerWeights, n_head: int, B: int, qn, kn1, nk1: int, kn2=None, nk2: int = 0, q_is_k1=False):
+    """q/k/v projections + attention for one block.  qn: ln1(query) [B*NQ, D]; kn1/kn2: ln1(key sources).
+    q_is_k1: the first key source is the query stream itself (latent_self, lt2l, maskgit) -> one fused QKV GEMM."""
+    D = qn.shape[1]
+    NQ = qn.shape[0] // B
+    if q_is_k1:
+        qkv = ops.gemm(qn, w.w_qkv, w.b_qkv)                      # [B*NQ, 3D]
+        q_buf, q_col, kv1, k1c, v1c = qkv, 0, qkv, D, 2 * D
+    else:
+        q_buf, q_col = ops.gemm(qn, w.w_qkv[:D], w.b_qkv[:D]), 0   # [B*NQ, D]
+        kv1, k1c, v1c = None, 0, 0
+        if nk1 > 0:
+            kv1 = ops.gemm(kn1, w.w_qkv[D:], w.b_qkv[D:])          # [B*NK1, 2D]
+            k1c, v1c = 0, D
+    kv2 = None
+    if nk2 > 0:
+        kv2 = ops.gemm(kn2, w.w_qkv[D:], w.b_qkv[D:])
+    return ops.attention(q_buf, q_col, kv1, k1c, v1c, nk1, kv2, 0, D, nk2, B, n_head, NQ)
+
+
+def block_forward(w: LayerWeights, n_head: int, B: int, lat, ctx, tgt):
+    """One Block (gpt.py:159-195) on 2-D bf16 streams; returns the updated (lat, ctx, tgt)."""
+    mode = w.mode
+    L = lat.shape[0] // B
+    NC = ctx.shape[0] // B
+    NT = tgt.shape[0] // B
+    ln1 = lambda t: ops.layernorm(t, w.ln1_w, w.ln1_b)
+    if mode == "latent_enc":
+        qn = ln1(lat)
+        att = attention_core(w, n_head, B, qn, ln1(ctx) if NC > 0 else None, NC)
+    elif mode == "latent_self":
+        qn = ln1(lat)
+        att = attention_core(w, n_head, B, qn, None, L, q_is_k1=True)
+    elif mode == "latent_dec":
+        qn = ln1(tgt)
+        att = attention_core(w, n_head, B, qn, ln1(lat), L)
+    elif mode == "lt2l":
+        qn = ln1(lat)
+        att = attention_core(w, n_head, B, qn, None, L, ln1(tgt) if NT > 0 else None, NT, q_is_k1=True)
+    elif mode == "maskgit":
+        D = lat.shape[1]
+        both = torch.cat([ctx.view(B, NC, D), tgt.view(B, NT, D)], 1).reshape(B * (NC + NT), D)
+        qn = ln1(both)
+        att = attention_core(w, n_head, B, qn, None, NC + NT, q_is_k1=True)
+    else:
+        raise ValueError(f"unknown block mode {mode!r}")
+    x = ops.gemm(att, w.w_proj, w.b_proj, residual=qn)            # x = ln1(q) + proj(attn)
+    h = ops.layernorm(x, w.ln2_w, w.ln2_b)
+    u = ops.gemm(h, w.w_fc1, w.b_fc1, gelu=True)
+    x = ops.gemm(u, w.w_fc2, w.b_fc2, residual=x)                 # x + mlp(ln2(x))
+    if mode in ("latent_enc", "latent_self", "lt2l"):
+        lat = x
+    elif mode == "latent_dec":
+        tgt = x
+    else:
+        D = x.shape[1]
+        x3 = x.view(B, NC + NT, D)
+        ctx, tgt = x3[:, :NC].reshape(B * NC, D), x3[:, NC:].reshape(B * NT, D)
+    return lat, ctx, tgt
+
+
+def stack_forward(pack: WeightPack, B: int, lat, ctx, tgt, logits_dtype=torch.float32, skip_dead=True):
+    """GPT.forward (gpt.py:234-253) in eval mode: blocks -> ln_f(targets) -> head.  Returns logits [B*NT, V]."""
+    last = pack.last_live_layer() if skip_dead else len(pack.layers) - 1
+    for i, w in enumerate(pack.layers):
+        if i > last:
+            break
+        lat, ctx, tgt = block_forward(w, pack.n_head, B, lat, ctx, tgt)
+    xf = ops.layernorm(tgt, pack.lnf_w, pack.lnf_b)
+    return ops.gemm(xf, pack.w_head, out_dtype=logits_dtype)

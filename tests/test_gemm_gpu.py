@@ -1,0 +1,64 @@
+"""tcgen05 GEMM (K2/K4) against a torch fp32 matmul of the same bf16-rounded operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GELU, OUT_FP32, ACC, BN256, BN128, BN64 = 1, 2, 4, 16, 32, 64
+
+CASES = [
+    # M, N, K, a_mn, b_mn, flags, bias, resid
+    (128, 64, 64, 0, 0, BN64, False, False),
+    (128, 128, 64, 0, 0, BN128, False, False),
+    (128, 256, 256, 0, 0, BN256, False, False),
+    (256, 512, 1024, 0, 0, BN256, True, False),
+    (1536, 1024, 1024, 0, 0, 0, True, True),
+    (1536, 4096, 1024, 0, 0, GELU, True, False),
+    (1536, 1024, 4096, 0, 0, 0, True, True),
+    (1000, 768, 1024, 0, 0, 0, True, True),            # ragged M
+    (3, 256, 256, 0, 0, 0, True, False),               # tiny M
+    (3072, 16384, 1024, 0, 0, OUT_FP32, False, False),  # head
+    (333, 256, 256, 0, 0, OUT_FP32, True, False),
+    (128, 64, 64, 0, 1, BN64, False, False),
+    (128, 64, 64, 1, 0, BN64, False, False),
+    (128, 128, 128, 1, 1, BN128, False, False),
+    (1536, 1024, 4096, 0, 1, 0, False, False),          # dgrad shape
+    (1024, 4096, 1536, 1, 1, OUT_FP32, False, False),   # wgrad shape (K = tokens)
+    (1024, 1024, 1000, 1, 1, OUT_FP32 | ACC, False, False),  # ragged K + accumulate
+    (1536, 1024, 1024, 0, 1, BN256, True, True),
+    (1536, 1024, 1024, 1, 0, BN128, True, False),
+]
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,flags,bias,resid", CASES)
+def test_gemm(M, N, K, a_mn, b_mn, flags, bias, resid):
+    from mebt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    A_st = A.t().contiguous() if a_mn else A
+    B_st = B.t().contiguous() if b_mn else B
+    bias_t = torch.randn(N, device="cuda", generator=g) if bias else None
+    res_t = torch.randn(M, N, device="cuda", generator=g).bfloat16() if resid else None
+    out_fp32 = bool(flags & OUT_FP32)
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    C0 = None
+    if flags & ACC:
+        C0 = torch.randn(M, N, device="cuda", generator=g)
+        C.copy_(C0)
+    ops.gemm(A_st, B_st, bias_t, res_t, gelu=bool(flags & GELU), out=C, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn),
+             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64))
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    if bias:
+        ref = ref + bias_t
+    if flags & GELU:
+        ref = torch.nn.functional.gelu(ref)
+    if resid:
+        ref = ref + res_t.float()
+    if C0 is not None:
+        ref = ref + C0
+    assert not torch.isnan(C.float()).any()
+    rel = (C.float() - ref).abs().max().item() / (ref.abs().max().item() + 1e-9)
+    # bf16 output: half an ulp of bf16 (2^-9) relative to the row scale; fp32 output: accumulation order only
+    assert rel < (1e-4 if out_fp32 else 6e-3), rel
