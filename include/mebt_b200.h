@@ -169,6 +169,37 @@ int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV
                               int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, void* O, int ldo,
                               float* lse, int B, int H, int NQ, int head_dim, void* stream);
 
+/* ---- the layer stack in one call ---------------------------------------------------------------- */
+enum {
+  MEBT_MODE_LATENT_ENC = 0,  /* q = latents, kv = contexts            -> latents   (gpt.py:167-169) */
+  MEBT_MODE_LATENT_SELF = 1, /* q = kv = latents                      -> latents   (gpt.py:164-166) */
+  MEBT_MODE_LATENT_DEC = 2,  /* q = targets, kv = latents             -> targets   (gpt.py:170-172) */
+  MEBT_MODE_LT2L = 3,        /* q = latents, kv = cat[latents,targets]-> latents   (gpt.py:173-175) */
+  MEBT_MODE_MASKGIT = 4      /* q = kv = cat[contexts,targets]        -> both      (gpt.py:176-178) */
+};
+/* One Block's parameters. Device pointers; *_w matrices are bf16 [out,in] row-major (nn.Linear layout),
+ * w_qkv = rows (query | key | value) stacked to [3D, D]; LayerNorm and bias vectors are fp32. */
+typedef struct mebt_layer {
+  int mode;
+  const float* ln1_w; const float* ln1_b; const float* ln2_w; const float* ln2_b;
+  const void* w_qkv;  const float* b_qkv;
+  const void* w_proj; const float* b_proj;
+  const void* w_fc1;  const float* b_fc1;
+  const void* w_fc2;  const float* b_fc2;
+} mebt_layer_t;
+
+size_t mebt_stack_forward_workspace_bytes(int B, int L, int NC, int NT, int D);
+/*
+ * GPT.forward (mebt/modules/gpt.py:234-253) in eval mode: n_layers Blocks threaded over the three streams, then
+ * logits = head(ln_f(targets)).  `layers` is a HOST array.  lat [B*L,D], ctx [B*NC,D], tgt [B*NT,D]: bf16 streams
+ * as produced by mebt_embed_gather; lat and tgt are updated in place, ctx is read-only for the latent modes.
+ * logits: [B*NT, V] in logits_dtype, or NULL to stop after the blocks.  Blocks that cannot reach the logits
+ * (after the last latent_dec) are skipped.  All launches go to `stream`; nothing synchronises.
+ */
+int mebt_stack_forward(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                       const void* w_head, int B, int L, int NC, int NT, int D, int H, int V, void* lat, void* ctx,
+                       void* tgt, void* logits, int logits_dtype, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

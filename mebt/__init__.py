@@ -1,0 +1,5 @@
+"""Import alias: `mebt.*` resolves to the mebt_b200 drop-in so that reference-facing scripts and config
+`target:` strings (`mebt.transformer.Net2NetTransformer`, `mebt.mask_sampler.MaskGen`) work unchanged."""
+from mebt_b200.mask_sampler import MaskGen  # noqa: F401
+from mebt_b200.transformer import Net2NetTransformer  # noqa: F401
+from mebt_b200.vqgan import VQGAN  # noqa: F401

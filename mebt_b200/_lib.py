@@ -65,7 +65,20 @@ def _bind():
         fn.restype = c_int
 
 
+
+
+class LayerStruct(ctypes.Structure):
+    """mebt_layer_t"""
+    _fields_ = [("mode", c_int)] + [(n, c_void_p) for n in (
+        "ln1_w", "ln1_b", "ln2_w", "ln2_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+
+
+_SIGNATURES["mebt_stack_forward"] = [ctypes.POINTER(LayerStruct), c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_void_p, c_size_t, c_void_p]
 _bind()
+_lib.mebt_stack_forward_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
+_lib.mebt_stack_forward_workspace_bytes.restype = c_size_t
 _lib.mebt_vq_argmin_workspace_bytes.argtypes = [c_longlong]
 _lib.mebt_vq_argmin_workspace_bytes.restype = c_size_t
 

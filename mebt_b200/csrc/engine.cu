@@ -1,0 +1,187 @@
+// Whole-stack forward in one C-ABI call: the 24-block MeBT layer stack launched back to back from C++ so that
+// the per-op host cost is a kernel launch, not a Python round trip (and the sequence can be captured in a CUDA
+// graph by the caller, since every launch goes to the caller's stream and nothing synchronises).
+//
+// reference: GPT.forward, mebt/modules/gpt.py:234-253, and Block.forward, :159-195:
+//   q^ = ln1(q), k^ = ln1(k) (same ln1), x = q^ + proj(attn(q^, k^)), out = x + fc2(gelu(fc1(ln2(x)))).
+#include "common.cuh"
+
+namespace mebt {
+
+int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+              int K, const float* bias, const void* residual, int ldres, int flags, cudaStream_t stream);
+int layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const float* beta, void* y, int ldy,
+              int out_dtype, int rows, int D, float eps, float* mean, float* rstd, cudaStream_t st);
+
+namespace {
+
+struct Workspace {
+  char* base;
+  size_t used, cap;
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    void* p = base + used;
+    used += bytes;
+    return used <= cap ? p : nullptr;
+  }
+};
+
+size_t stack_workspace_bytes(int B, int L, int NC, int NT, int D) {
+  const size_t q_rows = size_t(B) * size_t(L > NC + NT ? L : NC + NT);
+  const size_t k_rows = q_rows;
+  size_t total = 0;
+  auto add = [&](size_t rows, size_t cols) { total += ((rows * cols * 2) + 255) & ~size_t(255); };
+  add(q_rows, D);        // qn
+  add(k_rows, D);        // kn
+  add(q_rows, 3 * D);    // q / qkv
+  add(k_rows, 2 * D);    // kv
+  add(q_rows, D);        // att
+  add(q_rows, D);        // x
+  add(q_rows, D);        // h
+  add(q_rows, 4 * D);    // u
+  add(q_rows, D);        // maskgit concat stream
+  return total + 4096;
+}
+
+}  // namespace
+}  // namespace mebt
+
+extern "C" {
+
+size_t mebt_stack_forward_workspace_bytes(int B, int L, int NC, int NT, int D) {
+  return mebt::stack_workspace_bytes(B, L, NC, NT, D);
+}
+
+int mebt_stack_forward(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                       const void* w_head, int B, int L, int NC, int NT, int D, int H, int V, void* lat, void* ctx,
+                       void* tgt, void* logits, int logits_dtype, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  using namespace mebt;
+  MEBT_REQUIRE(B > 0 && L > 0 && NC >= 0 && NT > 0 && D > 0 && H > 0 && D == H * 64, MEBT_ERR_SHAPE,
+               "stack_forward: bad shape B=%d L=%d NC=%d NT=%d D=%d H=%d (head_dim must be 64)", B, L, NC, NT, D, H);
+  MEBT_REQUIRE(workspace != nullptr && workspace_bytes >= stack_workspace_bytes(B, L, NC, NT, D), MEBT_ERR_WORKSPACE,
+               "stack_forward: workspace too small (%zu < %zu)", workspace_bytes, stack_workspace_bytes(B, L, NC, NT, D));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace ws{static_cast<char*>(workspace), 0, workspace_bytes};
+  const int maxq = L > NC + NT ? L : NC + NT;
+  const size_t qr = size_t(B) * maxq, kr = qr;
+  void* qn = ws.take(qr * D * 2);
+  void* kn = ws.take(kr * D * 2);
+  void* qkv = ws.take(qr * 3 * D * 2);
+  void* kv = ws.take(kr * 2 * D * 2);
+  void* att = ws.take(qr * D * 2);
+  void* x = ws.take(qr * D * 2);
+  void* h = ws.take(qr * D * 2);
+  void* u = ws.take(qr * 4 * D * 2);
+  void* cat = ws.take(qr * D * 2);
+  MEBT_REQUIRE(cat != nullptr, MEBT_ERR_WORKSPACE, "stack_forward: workspace exhausted");
+
+  // blocks after the last one that writes `targets` cannot influence the logits (gpt.py:247)
+  int last = -1;
+  for (int i = 0; i < n_layers; ++i)
+    if (layers[i].mode == MEBT_MODE_LATENT_DEC || layers[i].mode == MEBT_MODE_MASKGIT) last = i;
+
+  auto LN = [&](const void* in, const float* g, const float* b, void* out, int rows) {
+    return layernorm(in, D, MEBT_DTYPE_BF16, g, b, out, D, MEBT_DTYPE_BF16, rows, D, 1e-5f, nullptr, nullptr, st);
+  };
+  auto GEMM = [&](const void* A, const void* W, int ldw, void* C, int ldc, int M, int N, int K, const float* bias,
+                  const void* res, int flags) {
+    return gemm_bf16(A, K, 0, W, ldw, 0, C, ldc, M, N, K, bias, res, N, flags, st);
+  };
+  int rc;
+#define TRY(expr) do { rc = (expr); if (rc != MEBT_OK) return rc; } while (0)
+
+  for (int i = 0; i <= last; ++i) {
+    const mebt_layer_t& w = layers[i];
+    const __nv_bfloat16* wqkv = static_cast<const __nv_bfloat16*>(w.w_qkv);
+    const __nv_bfloat16* w_kv = wqkv + size_t(D) * D;       // rows D..3D = (key, value)
+    const float* b_kv = w.b_qkv + D;
+    void* q_stream;      // the stream this block rewrites
+    int nq;
+    const void *Qb, *KV1 = nullptr, *KV2 = nullptr;
+    int ldq, ld1 = 0, ld2 = 0, k1c = 0, v1c = 0, nk1 = 0, nk2 = 0;
+    switch (w.mode) {
+      case MEBT_MODE_LATENT_ENC:
+        q_stream = lat; nq = L;
+        TRY(LN(lat, w.ln1_w, w.ln1_b, qn, B * L));
+        TRY(GEMM(qn, wqkv, D, qkv, D, B * L, D, D, w.b_qkv, nullptr, 0));
+        Qb = qkv; ldq = D;
+        if (NC > 0) {
+          TRY(LN(ctx, w.ln1_w, w.ln1_b, kn, B * NC));
+          TRY(GEMM(kn, w_kv, D, kv, 2 * D, B * NC, 2 * D, D, b_kv, nullptr, 0));
+          KV1 = kv; ld1 = 2 * D; k1c = 0; v1c = D; nk1 = NC;
+        }
+        break;
+      case MEBT_MODE_LATENT_SELF:
+        q_stream = lat; nq = L;
+        TRY(LN(lat, w.ln1_w, w.ln1_b, qn, B * L));
+        TRY(GEMM(qn, wqkv, D, qkv, 3 * D, B * L, 3 * D, D, w.b_qkv, nullptr, 0));
+        Qb = qkv; ldq = 3 * D; KV1 = qkv; ld1 = 3 * D; k1c = D; v1c = 2 * D; nk1 = L;
+        break;
+      case MEBT_MODE_LATENT_DEC:
+        q_stream = tgt; nq = NT;
+        TRY(LN(tgt, w.ln1_w, w.ln1_b, qn, B * NT));
+        TRY(GEMM(qn, wqkv, D, qkv, D, B * NT, D, D, w.b_qkv, nullptr, 0));
+        Qb = qkv; ldq = D;
+        TRY(LN(lat, w.ln1_w, w.ln1_b, kn, B * L));
+        TRY(GEMM(kn, w_kv, D, kv, 2 * D, B * L, 2 * D, D, b_kv, nullptr, 0));
+        KV1 = kv; ld1 = 2 * D; k1c = 0; v1c = D; nk1 = L;
+        break;
+      case MEBT_MODE_LT2L:
+        q_stream = lat; nq = L;
+        TRY(LN(lat, w.ln1_w, w.ln1_b, qn, B * L));
+        TRY(GEMM(qn, wqkv, D, qkv, 3 * D, B * L, 3 * D, D, w.b_qkv, nullptr, 0));
+        Qb = qkv; ldq = 3 * D; KV1 = qkv; ld1 = 3 * D; k1c = D; v1c = 2 * D; nk1 = L;
+        TRY(LN(tgt, w.ln1_w, w.ln1_b, kn, B * NT));
+        TRY(GEMM(kn, w_kv, D, kv, 2 * D, B * NT, 2 * D, D, b_kv, nullptr, 0));
+        KV2 = kv; ld2 = 2 * D; nk2 = NT;
+        break;
+      case MEBT_MODE_MASKGIT: {
+        // q = k = cat[contexts, targets] per batch element (gpt.py:176-178)
+        const int n = NC + NT;
+        for (int b = 0; b < B; ++b) {
+          char* dst = static_cast<char*>(cat) + size_t(b) * n * D * 2;
+          if (NC > 0)
+            MEBT_CUDA_OK(cudaMemcpyAsync(dst, static_cast<char*>(ctx) + size_t(b) * NC * D * 2, size_t(NC) * D * 2,
+                                         cudaMemcpyDeviceToDevice, st));
+          MEBT_CUDA_OK(cudaMemcpyAsync(dst + size_t(NC) * D * 2, static_cast<char*>(tgt) + size_t(b) * NT * D * 2,
+                                       size_t(NT) * D * 2, cudaMemcpyDeviceToDevice, st));
+        }
+        q_stream = cat; nq = n;
+        TRY(LN(cat, w.ln1_w, w.ln1_b, qn, B * n));
+        TRY(GEMM(qn, wqkv, D, qkv, 3 * D, B * n, 3 * D, D, w.b_qkv, nullptr, 0));
+        Qb = qkv; ldq = 3 * D; KV1 = qkv; ld1 = 3 * D; k1c = D; v1c = 2 * D; nk1 = n;
+        break;
+      }
+      default:
+        MEBT_REQUIRE(false, MEBT_ERR_UNSUPPORTED, "stack_forward: unknown block mode %d", w.mode);
+    }
+    TRY(mebt_latent_attention_fwd(Qb, ldq, 0, KV1, ld1, k1c, v1c, nk1, KV2, ld2, 0, D, nk2, att, D, nullptr, B, H, nq,
+                                  64, stream));
+    const int rows = B * nq;
+    TRY(GEMM(att, w.w_proj, D, x, D, rows, D, D, w.b_proj, qn, 0));                    // x = ln1(q) + proj(att)
+    TRY(LN(x, w.ln2_w, w.ln2_b, h, rows));
+    TRY(GEMM(h, w.w_fc1, D, u, 4 * D, rows, 4 * D, D, w.b_fc1, nullptr, MEBT_GEMM_GELU));
+    TRY(GEMM(u, w.w_fc2, 4 * D, q_stream, D, rows, D, 4 * D, w.b_fc2, x, 0));          // stream = x + mlp(ln2(x))
+    if (w.mode == MEBT_MODE_MASKGIT) {
+      const int n = NC + NT;
+      for (int b = 0; b < B; ++b) {
+        const char* src = static_cast<const char*>(cat) + size_t(b) * n * D * 2;
+        if (NC > 0)
+          MEBT_CUDA_OK(cudaMemcpyAsync(static_cast<char*>(ctx) + size_t(b) * NC * D * 2, src, size_t(NC) * D * 2,
+                                       cudaMemcpyDeviceToDevice, st));
+        MEBT_CUDA_OK(cudaMemcpyAsync(static_cast<char*>(tgt) + size_t(b) * NT * D * 2, src + size_t(NC) * D * 2,
+                                     size_t(NT) * D * 2, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+  }
+  if (logits != nullptr) {
+    TRY(LN(tgt, lnf_w, lnf_b, h, B * NT));
+    TRY(gemm_bf16(h, D, 0, w_head, D, 0, logits, V, B * NT, V, D, nullptr, nullptr, 0,
+                  logits_dtype == MEBT_DTYPE_FP32 ? MEBT_GEMM_OUT_FP32 : 0, st));
+  }
+#undef TRY
+  return MEBT_OK;
+}
+
+}  // extern "C"

@@ -15,8 +15,9 @@ from typing import Mapping
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
+MODE_IDS = {"latent_enc": 0, "latent_self": 1, "latent_dec": 2, "lt2l": 3, "maskgit": 4}
 LATENT_MODES = ("latent_enc", "latent_self", "latent_dec", "lt2l")
 
 
@@ -61,6 +62,17 @@ class WeightPack:
         self.lnf_b = f32(params[prefix + "ln_f.bias"])
         self.w_head = ops.cast_bf16(f32(params[prefix + "head.weight"]))
         self.D = self.lnf_w.numel()
+        self.V = self.w_head.shape[0]
+        # host array of mebt_layer_t for the one-call engine
+        arr = (_lib.LayerStruct * len(self.layers))()
+        for i, w in enumerate(self.layers):
+            if w.mode not in MODE_IDS:
+                raise ValueError(f"unknown block mode {w.mode!r}")
+            arr[i].mode = MODE_IDS[w.mode]
+            for f in ("ln1_w", "ln1_b", "ln2_w", "ln2_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1",
+                      "w_fc2", "b_fc2"):
+                setattr(arr[i], f, getattr(w, f).data_ptr())
+        self.c_layers = arr
 
     def last_live_layer(self) -> int:
         """Blocks after the last one writing `targets` cannot reach the logits (gpt.py:247 reads targets only)."""
@@ -132,8 +144,38 @@ def block_forward(w: LayerWeights, n_head: int, B: int, lat, ctx, tgt):
     return lat, ctx, tgt
 
 
-def stack_forward(pack: WeightPack, B: int, lat, ctx, tgt, logits_dtype=torch.float32, skip_dead=True):
-    """GPT.forward (gpt.py:234-253) in eval mode: blocks -> ln_f(targets) -> head.  Returns logits [B*NT, V]."""
+_workspaces: dict = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def stack_forward(pack: WeightPack, B: int, lat, ctx, tgt, logits_dtype=torch.float32):
+    """GPT.forward (gpt.py:234-253) in eval mode through the one-call C++ engine (`mebt_stack_forward`).
+    lat/tgt are updated in place.  Returns logits [B*NT, V]."""
+    D = pack.D
+    L, NC, NT = lat.shape[0] // B, ctx.shape[0] // B, tgt.shape[0] // B
+    for t in (lat, ctx, tgt):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous():
+            raise _lib.MebtError("stack_forward streams must be contiguous bf16")
+    logits = torch.empty(B * NT, pack.V, device=lat.device, dtype=logits_dtype)
+    nbytes = _lib.lib.mebt_stack_forward_workspace_bytes(B, L, NC, NT, D)
+    ws = _workspace(lat.device, nbytes)
+    _lib.call("mebt_stack_forward", pack.c_layers, len(pack.layers), pack.lnf_w.data_ptr(), pack.lnf_b.data_ptr(),
+              pack.w_head.data_ptr(), B, L, NC, NT, D, pack.n_head, pack.V, lat.data_ptr(), ctx.data_ptr(),
+              tgt.data_ptr(), logits.data_ptr(), ops._DT[logits_dtype], ws.data_ptr(), ws.numel(),
+              torch.cuda.current_stream().cuda_stream)
+    return logits
+
+
+def stack_forward_ops(pack: WeightPack, B: int, lat, ctx, tgt, logits_dtype=torch.float32, skip_dead=True):
+    """Same computation composed op by op from Python (one C-ABI call per kernel); used by the per-module
+    drop-in API and as a cross-check of the engine."""
     last = pack.last_live_layer() if skip_dead else len(pack.layers) - 1
     for i, w in enumerate(pack.layers):
         if i > last:

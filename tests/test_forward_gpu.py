@@ -12,9 +12,9 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-2
 
 
-def _run_stack(cfg, P, x, ctx_idx, tgt_idx):
+def _run_stack(cfg, P, x, ctx_idx, tgt_idx, engine=True):
     from mebt_b200 import ops
-    from mebt_b200.stack import WeightPack, stack_forward
+    from mebt_b200.stack import WeightPack, stack_forward, stack_forward_ops
     dev = {k: v.cuda() for k, v in P.items()}
     modes = list(cfg["mode"]) + ["maskgit"] * (cfg["n_layer"] - len(cfg["mode"]))
     pack = WeightPack(dev, modes, cfg["n_head"])
@@ -22,7 +22,7 @@ def _run_stack(cfg, P, x, ctx_idx, tgt_idx):
     xi = x.reshape(B, -1).cuda()
     ctx, tgt, lat = ops.embed_gather(xi, ctx_idx.cuda(), tgt_idx.cuda(), dev["tok_emb.weight"], dev["pos_emb"],
                                      dev["mask_emb"], dev["sos_emb"])
-    logits = stack_forward(pack, B, lat, ctx, tgt)
+    logits = (stack_forward if engine else stack_forward_ops)(pack, B, lat, ctx, tgt)
     ops.check_index_errors()
     return logits.view(B, tgt_idx.shape[1], -1).cpu()
 
@@ -48,6 +48,9 @@ def test_stack_forward_vs_oracle_and_golden(name):
         ref = O.reconstruct_mask(P, cfg, x, ctx_idx, tgt_idx)
         logits = _run_stack(cfg, P, x, ctx_idx, tgt_idx)
         _check(logits, ref)
+        if nc == int(z["ncs"][-1]):
+            # the one-call C++ engine and the op-by-op composition launch the same kernels: identical bits
+            assert torch.equal(logits, _run_stack(cfg, P, x, ctx_idx, tgt_idx, engine=False))
         # the fixture holds what the unmodified reference produced
         sub = torch.from_numpy(z[f"nc{nc}_sub"])
         scale = float(np.abs(z[f"nc{nc}_rowmax"]).max())

@@ -109,7 +109,7 @@ def test_masked_ce(dtype, smoothing):
     assert int(stats[1]) == n1 and int(stats[2]) == n5
     ref_rows = F.cross_entropy(logits.float(), tg, reduction="none", label_smoothing=smoothing)
     assert (row_loss.cpu() - ref_rows).abs().max() < 2e-5
-    tol = 1e-6 if dtype == torch.float32 else 4e-3
+    tol = 5e-6 if dtype == torch.float32 else 4e-3   # expf ulps on the (softmax - 0.9) entry
     assert (d_logits.float().cpu() - 0.5 * lg.grad).abs().max() < tol
 
 
