@@ -39,6 +39,15 @@ const char* mebt_version(void);
 const char* mebt_last_error(void);
 /* 0 iff the current CUDA device is sm_100-class (B200). */
 int mebt_device_check(void);
+/* Number of mebt_b200 kernels launched by this process so far (bench.py's `gpu_launches`). */
+unsigned long long mebt_launch_count(void);
+/* Per-kernel-family timing with CUDA events recorded on each launch's own stream.  Families (index into the
+ * report arrays, length 10): 0 gemm (work = flops), 1 attention (flops), 2 layernorm, 3 embed, 4 sample, 5 ce,
+ * 6 remask, 7 scatter, 8 vq, 9 other (work = algorithmic bytes).  mebt_profile_report synchronises the device,
+ * fills the sums since the last report and clears them.  Profiling serialises nothing but adds two event records
+ * per launch: keep it off inside timed throughput regions. */
+void mebt_profile_enable(int on);
+int mebt_profile_report(double* time_ms, double* work, long long* launches);
 
 /* ---- K2 / K4 : dense contractions ---------------------------------------------------------- */
 enum {

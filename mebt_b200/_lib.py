@@ -77,6 +77,14 @@ _SIGNATURES["mebt_stack_forward"] = [ctypes.POINTER(LayerStruct), c_int, c_void_
                                      c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p, c_size_t, c_void_p]
 _bind()
+_lib.mebt_launch_count.argtypes = []
+_lib.mebt_launch_count.restype = ctypes.c_ulonglong
+_lib.mebt_profile_enable.argtypes = [c_int]
+_lib.mebt_profile_enable.restype = None
+_SIGNATURES["mebt_profile_report"] = [c_void_p, c_void_p, c_void_p]
+_lib.mebt_profile_report.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(ctypes.c_longlong)]
+_lib.mebt_profile_report.restype = c_int
 _lib.mebt_stack_forward_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
 _lib.mebt_stack_forward_workspace_bytes.restype = c_size_t
 _lib.mebt_vq_argmin_workspace_bytes.argtypes = [c_longlong]
@@ -98,6 +106,27 @@ def check(rc: int, what: str = "") -> None:
 
 def call(name: str, *args) -> None:
     check(getattr(_lib, name)(*args), name)
+
+
+FAMILIES = ("gemm", "attention", "layernorm", "embed", "sample", "ce", "remask", "scatter", "vq", "other")
+
+
+def launch_count() -> int:
+    return int(_lib.mebt_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    _lib.mebt_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """-> {family: dict(ms=..., work=..., launches=...)} since the last report (synchronises the device)."""
+    n = len(FAMILIES)
+    t = (ctypes.c_double * n)()
+    w = (ctypes.c_double * n)()
+    c = (ctypes.c_longlong * n)()
+    check(_lib.mebt_profile_report(t, w, c), "mebt_profile_report")
+    return {f: dict(ms=t[i], work=w[i], launches=int(c[i])) for i, f in enumerate(FAMILIES)}
 
 
 lib = _lib

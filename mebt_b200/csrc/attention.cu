@@ -289,7 +289,11 @@ extern "C" int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, con
     attr = true;
   }
   dim3 grid((NQ + AT_BQ - 1) / AT_BQ, H, B);
-  latent_attention_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, t1, t2, p);
+  {
+    LaunchScope ls(FAM_ATTENTION, 4.0 * double(B) * H * double(NQ) * double(NK1 + NK2) * AT_HS,
+                   static_cast<cudaStream_t>(stream));
+    latent_attention_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, t1, t2, p);
+  }
   MEBT_LAUNCH_OK("latent_attention_fwd_kernel");
   return MEBT_OK;
 }

@@ -47,6 +47,19 @@ int get_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_
 
 int sm_count();
 
+// ---- lightweight in-library accounting (bench.py's gpu_launches and per-kernel roofline numbers) ----------
+enum KernelFamily : int {
+  FAM_GEMM = 0, FAM_ATTENTION = 1, FAM_LAYERNORM = 2, FAM_EMBED = 3, FAM_SAMPLE = 4, FAM_CE = 5, FAM_REMASK = 6,
+  FAM_SCATTER = 7, FAM_VQ = 8, FAM_OTHER = 9, FAM_COUNT = 10
+};
+void note_launch(int family, double work, cudaStream_t st, bool begin);
+// RAII: counts the launch and, when profiling is enabled, brackets it with CUDA events on its stream.
+struct LaunchScope {
+  int family; cudaStream_t st;
+  LaunchScope(int fam, double work, cudaStream_t s) : family(fam), st(s) { note_launch(fam, work, s, true); }
+  ~LaunchScope() { note_launch(family, 0.0, st, false); }
+};
+
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
 // Device helpers

@@ -210,6 +210,7 @@ template <typename InT, typename OutT>
 int launch_ln(const void* x, int ldx, const float* g, const float* b, void* y, int ldy, int rows, int D, float eps,
               float* mean, float* rstd, cudaStream_t st) {
   const int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  LaunchScope ls(FAM_LAYERNORM, double(rows) * D * double(sizeof(InT) + sizeof(OutT)), st);
   const InT* xi = static_cast<const InT*>(x);
   OutT* yo = static_cast<OutT*>(y);
   if (D <= 256) layernorm_kernel<InT, OutT, 2><<<grid, 256, 0, st>>>(xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd);
@@ -235,6 +236,8 @@ int embed_gather(const int64_t* x, int x_stride, const int64_t* ctx_idx, int ctx
   const long long rows = (long long)B * (NC + NT + L);
   if (rows == 0) return MEBT_OK;
   const int grid = int((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  const double e = out_dtype == MEBT_DTYPE_BF16 ? 2.0 : 4.0;
+  LaunchScope ls(FAM_EMBED, double(B) * (NC * (16.0 + 8.0 * D + e * D) + NT * (8.0 + 4.0 * D + e * D) + L * (4.0 + e) * D), st);
   if (out_dtype == MEBT_DTYPE_BF16)
     embed_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
         x, x_stride, ctx_idx, ctx_stride, tgt_idx, tgt_stride, tok_emb, pos_emb, mask_emb, sos_emb,
@@ -295,6 +298,7 @@ int mebt_scatter_ids(int64_t* x, int x_stride, const int64_t* tgt_idx, int tgt_s
   if (n == 0) return MEBT_OK;
   int* flag = mebt::err_flag_ptr();
   MEBT_REQUIRE(flag != nullptr, MEBT_ERR_CUDA, "scatter_ids: cannot allocate error flag");
+  mebt::LaunchScope ls(mebt::FAM_SCATTER, double(n) * 24.0, static_cast<cudaStream_t>(stream));
   mebt::scatter_ids_kernel<<<int((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, x_stride, tgt_idx, tgt_stride, ids, B, NT, N, flag);
   MEBT_LAUNCH_OK("scatter_ids_kernel");
@@ -309,6 +313,7 @@ int mebt_row_gather(const int64_t* enc, const float* E, float* out, int batch, i
   int* flag = mebt::err_flag_ptr();
   MEBT_REQUIRE(flag != nullptr, MEBT_ERR_CUDA, "row_gather: cannot allocate error flag");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mebt::LaunchScope ls(mebt::FAM_VQ, double(M) * (8.0 + 8.0 * C), st);
   if (channel_first) {
     dim3 grid((S + 31) / 32, (C + 31) / 32, batch), block(32, 8);
     mebt::row_gather_cf_kernel<<<grid, block, 0, st>>>(enc, E, out, S, C, K, flag);
@@ -327,6 +332,7 @@ int mebt_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream)
   const long long n4 = n / 4;
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  mebt::LaunchScope ls(mebt::FAM_OTHER, double(n) * 6.0, static_cast<cudaStream_t>(stream));
   mebt::cast_f32_bf16_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, static_cast<__nv_bfloat16*>(out), n4);
   MEBT_LAUNCH_OK("cast_f32_bf16_kernel");

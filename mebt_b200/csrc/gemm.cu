@@ -258,7 +258,10 @@ int launch_gemm(const void* A, const void* B, const GemmParams& p, int lda, int 
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  {
+    LaunchScope ls(FAM_GEMM, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  }
   MEBT_LAUNCH_OK("gemm_bf16_kernel");
   return MEBT_OK;
 }

@@ -345,6 +345,8 @@ int mebt_masked_ce(const void* logits, long long ld, int dtype, const int64_t* t
   MEBT_REQUIRE(ld % 4 == 0 && (dlogits == nullptr || ld_d % 4 == 0), MEBT_ERR_SHAPE, "masked_ce: bad row stride");
   if (rows == 0) return MEBT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double eb = dtype == MEBT_DTYPE_FP32 ? 4.0 : 2.0;
+  LaunchScope ls(FAM_CE, double(rows) * (double(V) * eb * (dlogits != nullptr ? 2.0 : 1.0) + 16.0), st);
   if (dtype == MEBT_DTYPE_FP32)
     masked_ce_kernel<float><<<rows, LT, 0, st>>>(static_cast<const float*>(logits), ld, targets, V, label_smoothing,
                                                  row_loss, row_rank, static_cast<float*>(dlogits), ld_d, grad_scale);
@@ -360,6 +362,7 @@ int mebt_masked_ce(const void* logits, long long ld, int dtype, const int64_t* t
 
 int mebt_ce_reduce(const float* row_loss, const int* row_rank, int rows, float* out3, void* stream) {
   MEBT_REQUIRE(rows >= 0, MEBT_ERR_SHAPE, "ce_reduce: bad rows");
+  mebt::LaunchScope ls(mebt::FAM_OTHER, double(rows) * 8.0, static_cast<cudaStream_t>(stream));
   mebt::ce_reduce_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(row_loss, row_rank, rows, out3);
   MEBT_LAUNCH_OK("ce_reduce_kernel");
   return MEBT_OK;
@@ -378,6 +381,8 @@ int mebt_sample_logits(const void* logits, long long ld, int dtype, int rows, in
   // python: temperature + 1e-8 in double, then cast to fp32 for the tensor division
   const float temp_div = float(double(temperature) + 1e-8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double eb = dtype == MEBT_DTYPE_FP32 ? 4.0 : 2.0;
+  LaunchScope ls(FAM_SAMPLE, double(rows) * (double(V) * (eb + (noise != nullptr ? 4.0 : 0.0) + (probs != nullptr ? 4.0 : 0.0)) + 12.0), st);
   if (dtype == MEBT_DTYPE_FP32)
     sample_logits_kernel<float><<<rows, LT, 0, st>>>(static_cast<const float*>(logits), ld, V, temp_div, top_k, noise,
                                                      seed, offset, ids, scores, probs);

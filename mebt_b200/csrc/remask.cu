@@ -126,6 +126,8 @@ extern "C" int mebt_remask_sort(const float* score, const float* noise, float ct
     MEBT_CUDA_OK(cudaFuncSetAttribute(remask_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(128 * 1024)));
     configured = 128 * 1024;
   }
+  LaunchScope ls(FAM_REMASK, double(B) * (double(NT) * (4.0 + (noise != nullptr ? 4.0 : 0.0) + 16.0) + double(NC) * 16.0),
+                 static_cast<cudaStream_t>(stream));
   remask_sort_kernel<<<B, RT, smem, static_cast<cudaStream_t>(stream)>>>(score, noise, ctemp, ctx_idx, ctx_stride,
                                                                          tgt_idx, tgt_stride, NC, NT, n_new, n_pow2,
                                                                          seed, offset, next_ctx, next_tgt, order_out);

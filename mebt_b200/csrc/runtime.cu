@@ -4,6 +4,7 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -34,6 +35,35 @@ int sm_count() {
       cached = 148;
   }
   return cached;
+}
+
+// ---- launch accounting / per-family event timing ------------------------------------------------
+struct ProfRec { cudaEvent_t e0, e1; int family; double work; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static unsigned long long g_launches[FAM_COUNT] = {0};
+
+static cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void note_launch(int family, double work, cudaStream_t st, bool begin) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  if (begin) {
+    ++g_launches[family];
+    if (g_prof_on) {
+      ProfRec r{take_event(), take_event(), family, work};
+      cudaEventRecord(r.e0, st);
+      g_prof.push_back(r);
+    }
+  } else if (g_prof_on && !g_prof.empty()) {
+    cudaEventRecord(g_prof.back().e1, st);
+  }
 }
 
 // ---- tensor map cache ------------------------------------------------------------------------
@@ -116,6 +146,37 @@ extern "C" {
 const char* mebt_last_error(void) { return mebt::g_last_error; }
 
 const char* mebt_version(void) { return "mebt_b200 0.1 (sm_100a)"; }
+
+unsigned long long mebt_launch_count(void) {
+  std::lock_guard<std::mutex> g(mebt::g_prof_mu);
+  unsigned long long n = 0;
+  for (int i = 0; i < mebt::FAM_COUNT; ++i) n += mebt::g_launches[i];
+  return n;
+}
+
+void mebt_profile_enable(int on) {
+  std::lock_guard<std::mutex> g(mebt::g_prof_mu);
+  mebt::g_prof_on = on != 0;
+}
+
+int mebt_profile_report(double* time_ms, double* work, long long* launches) {
+  using namespace mebt;
+  MEBT_CUDA_OK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  for (int i = 0; i < FAM_COUNT; ++i) { time_ms[i] = 0.0; work[i] = 0.0; launches[i] = 0; }
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      time_ms[r.family] += ms;
+      work[r.family] += r.work;
+      launches[r.family] += 1;
+    }
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  return MEBT_OK;
+}
 
 int mebt_device_check(void) {
   int dev = 0;

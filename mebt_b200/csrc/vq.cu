@@ -185,6 +185,7 @@ int mebt_vq_argmin(const float* z_channel_first, int batch, int C, int S, const 
   while (m_blocks * splits < 2 * sm_count() && (K / (splits * 2)) >= VQ_BN * 4 && (K % (splits * 2 * VQ_BN)) == 0) splits *= 2;
   const int codes_per_cta = ((K + splits - 1) / splits + VQ_BN - 1) / VQ_BN * VQ_BN;
   dim3 grid(m_blocks, (K + codes_per_cta - 1) / codes_per_cta);
+  LaunchScope ls(FAM_VQ, 2.0 * double(M) * double(K) * double(C), st);
   vq_argmin_kernel<<<grid, VQ_THREADS, smem, st>>>(z_channel_first, S, C, E, e_sqnorm, K, M, codes_per_cta, packed);
   MEBT_LAUNCH_OK("vq_argmin_kernel");
   vq_unpack_kernel<<<int((M + 255) / 256), 256, 0, st>>>(packed, out_idx, M);

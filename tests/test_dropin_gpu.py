@@ -91,7 +91,7 @@ def test_draft_and_revise_teacher_forced_parity():
             ids, scores, _ = ops.sample_logits(ref_logits.view(-1, 16384).cuda(), T, k, None, noise=q.view(-1, 16384).cuda())
             assert torch.equal(ids.cpu().view_as(ref_ids), ref_ids)                   # selections: bit-exact
             ref_scores = ref_probs.gather(-1, ref_ids.unsqueeze(-1)).squeeze(-1)
-            assert torch.allclose(scores.cpu().view_as(ref_scores), ref_scores, rtol=3e-6, atol=1e-12)
+            assert torch.allclose(scores.cpu().view_as(ref_scores), ref_scores, rtol=5e-6, atol=1e-12)
             xg = x.cuda()
             ops.scatter_ids(xg, gt, ids.view(B, -1))
             x = x.scatter(1, t, ref_ids)
