@@ -130,7 +130,8 @@ int mebt_ce_reduce(const float* row_loss, const int* row_rank, int rows, float* 
 /*
  * ids[r] = argmax_v (p_v / sum p) / q_v with p = softmax(top_k_filter(logits / (temperature + 1e-8))),
  * scores[r] = p[ids[r]].  q: Exp(1) noise [rows, V] supplied by the caller (parity mode, = the reference's
- * exponential_ draw) or, when noise == NULL, generated in-kernel with Philox4x32-10(seed, offset).
+ * exponential_ draw).  When noise == NULL (fast mode) the id is drawn from the same categorical distribution p by
+ * inverse-CDF with one in-kernel Philox4x32-10(seed, offset, row) uniform per row, so no noise tensor exists.
  * probs (optional, fp32 [rows, V]) receives the softmax the reference returns with return_probs=True.
  * Replaces sample_from_logits + gumbel_sort + top_k_logits, mebt/transformer.py:843-895 (a full 16384-way sort
  * per row and ~10 passes over [B,NT,V] become one pass).  top_k <= 0 disables the filter; top_p in (0,1) is

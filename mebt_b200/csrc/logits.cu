@@ -181,12 +181,8 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-__device__ __forceinline__ float exp1_from_bits(uint32_t x) {   // Exp(1) draw; u in (0, 1]
-  const float u = (float(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
-  return -__logf(u);
-}
 
-template <typename T>
+template <typename T, bool RACE>
 __global__ void __launch_bounds__(LT) sample_logits_kernel(const T* __restrict__ logits, long long ld, int V,
                                                            float temp_div, int top_k, const float* __restrict__ noise,
                                                            unsigned long long seed, unsigned long long offset,
@@ -272,6 +268,99 @@ __global__ void __launch_bounds__(LT) sample_logits_kernel(const T* __restrict__
     se += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   se = block_sum(se, red);
+
+  if constexpr (!RACE) {
+    // ---- fast mode: inverse-CDF draw.  One Philox uniform per row and a block-wide prefix sum select an id from
+    // exactly the categorical distribution the reference's exponential race samples from, without generating
+    // 16384 Exp(1) variates per row (the race needs 1 Philox round trip + 2 logs per logit; this needs none).
+    __shared__ __align__(16) float wsum[MAX_V4][LT / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i) {
+      const float sacc = warp_sum((v[i].x + v[i].y) + (v[i].z + v[i].w));
+      if (lane == 0) wsum[i][wid] = sacc;
+    }
+    __syncthreads();
+    // warp 0 locates the (chunk, warp) cell holding the target: 128 cell sums, 4 per lane, in vocabulary order
+    __shared__ int sel_cell;
+    __shared__ float sel_resid;
+    if (wid == 0) {
+      const uint4 r = philox4x32(make_uint4(uint32_t(row), uint32_t(row >> 32), uint32_t(offset), uint32_t(offset >> 32)),
+                                 make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+      const float u = (float(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f);     // (0, 1]
+      const float4 part = *reinterpret_cast<const float4*>(&wsum[0][0] + lane * 4);
+      const float own4 = (part.x + part.y) + (part.z + part.w);
+      float inc = own4;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const float target = u * __shfl_sync(0xffffffffu, inc, 31);
+      const unsigned hit = __ballot_sync(0xffffffffu, own4 > 0.f && inc >= target);
+      const unsigned any = __ballot_sync(0xffffffffu, own4 > 0.f);
+      const int sl = hit ? (__ffs(hit) - 1) : (any ? 31 - __clz(any) : 0);
+      if (lane == sl) {
+        const float rr = hit ? target - (inc - own4) : INFINITY;   // INFINITY: rounding pushed the target past the total
+        const float e[4] = {part.x, part.y, part.z, part.w};
+        int j_sel = -1, j_last = 0;
+        float cum = 0.f, before = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (e[j] > 0.f) { j_last = j; if (j_sel < 0 && cum + e[j] >= rr) { j_sel = j; before = cum; } }
+          cum += e[j];
+        }
+        if (j_sel < 0) { j_sel = j_last; before = -INFINITY; }
+        sel_cell = lane * 4 + j_sel;
+        sel_resid = rr - before;
+      }
+    }
+    __syncthreads();
+    const int ci = sel_cell / (LT / 32), wi = sel_cell % (LT / 32);
+    const float resid = sel_resid;
+    if (wid == wi) {
+      float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < MAX_V4; ++i)
+        if (i == ci) mine = v[i];
+      const float my_own = (mine.x + mine.y) + (mine.z + mine.w);
+      float my_incl = my_own;                      // inclusive scan over the lanes of the selected chunk only
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, my_incl, o);
+        if (lane >= o) my_incl += t;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, my_own > 0.f && my_incl >= resid);
+      const unsigned any = __ballot_sync(0xffffffffu, my_own > 0.f);
+      const int sel = hit ? (__ffs(hit) - 1) : (31 - __clz(any));
+      if (lane == sel) {
+        const float rr = resid - (my_incl - my_own);
+        const float e[4] = {mine.x, mine.y, mine.z, mine.w};
+        int j_sel = -1, j_last = 0;
+        float cum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cum += e[j];
+          if (e[j] > 0.f) { j_last = j; if (j_sel < 0 && cum >= rr) j_sel = j; }
+        }
+        if (j_sel < 0) j_sel = j_last;
+        ids[row] = (threadIdx.x + LT * ci) * 4 + j_sel;
+        if (scores != nullptr) scores[row] = __fdiv_rn(e[j_sel], se);
+      }
+    }
+    if (probs_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < MAX_V4; ++i) {
+        const int c = (threadIdx.x + LT * i) * 4;
+        if (c < V)
+          *reinterpret_cast<float4*>(probs_out + row * V + c) =
+              make_float4(__fdiv_rn(v[i].x, se), __fdiv_rn(v[i].y, se), __fdiv_rn(v[i].z, se), __fdiv_rn(v[i].w, se));
+      }
+    }
+    return;
+  }
+
+  // ---- parity mode: the reference's exponential race on caller-supplied Exp(1) noise ----
   // probs = softmax; psum = probs.sum() as gumbel_sort renormalises (transformer.py:834)
   float psum = 0.f;
 #pragma unroll
@@ -289,15 +378,7 @@ __global__ void __launch_bounds__(LT) sample_logits_kernel(const T* __restrict__
     const int c = (threadIdx.x + LT * i) * 4;
     if (c < V) {
       if (probs_out != nullptr) *reinterpret_cast<float4*>(probs_out + row * V + c) = v[i];
-      float4 q;
-      if (noise != nullptr) {
-        q = __ldg(reinterpret_cast<const float4*>(noise + row * V + c));
-      } else {
-        const uint4 r = philox4x32(make_uint4(uint32_t(row), uint32_t(c >> 2) | (uint32_t(row >> 32) << 16),
-                                              uint32_t(offset), uint32_t(offset >> 32)),
-                                   make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
-        q = make_float4(exp1_from_bits(r.x), exp1_from_bits(r.y), exp1_from_bits(r.z), exp1_from_bits(r.w));
-      }
+      const float4 q = __ldg(reinterpret_cast<const float4*>(noise + row * V + c));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float p = (&v[i].x)[j];
@@ -384,11 +465,12 @@ int mebt_sample_logits(const void* logits, long long ld, int dtype, int rows, in
   const double eb = dtype == MEBT_DTYPE_FP32 ? 4.0 : 2.0;
   LaunchScope ls(FAM_SAMPLE, double(rows) * (double(V) * (eb + (noise != nullptr ? 4.0 : 0.0) + (probs != nullptr ? 4.0 : 0.0)) + 12.0), st);
   if (dtype == MEBT_DTYPE_FP32)
-    sample_logits_kernel<float><<<rows, LT, 0, st>>>(static_cast<const float*>(logits), ld, V, temp_div, top_k, noise,
-                                                     seed, offset, ids, scores, probs);
+    (noise != nullptr ? sample_logits_kernel<float, true> : sample_logits_kernel<float, false>)<<<rows, LT, 0, st>>>(
+        static_cast<const float*>(logits), ld, V, temp_div, top_k, noise, seed, offset, ids, scores, probs);
   else if (dtype == MEBT_DTYPE_BF16)
-    sample_logits_kernel<__nv_bfloat16><<<rows, LT, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, V,
-                                                             temp_div, top_k, noise, seed, offset, ids, scores, probs);
+    (noise != nullptr ? sample_logits_kernel<__nv_bfloat16, true> : sample_logits_kernel<__nv_bfloat16, false>)
+        <<<rows, LT, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, V, temp_div, top_k, noise, seed, offset,
+                              ids, scores, probs);
   else
     MEBT_REQUIRE(false, MEBT_ERR_DTYPE, "sample_logits: unsupported dtype %d", dtype);
   MEBT_LAUNCH_OK("sample_logits_kernel");
