@@ -54,6 +54,7 @@ enum {
   MEBT_GEMM_GELU = 1,         /* exact erf GELU after bias (gpt.py:152 nn.GELU) */
   MEBT_GEMM_OUT_FP32 = 2,     /* C is float (logits, weight gradients); default bf16 */
   MEBT_GEMM_ACCUMULATE = 4,   /* C += result (fp32 C only; gradient accumulation) */
+  MEBT_GEMM_DGELU = 8,        /* result *= gelu'(aux): the backward of the fused fc1+GELU epilogue */
   MEBT_GEMM_FORCE_BN256 = 16, /* tile-width overrides, for tests and tuning */
   MEBT_GEMM_FORCE_BN128 = 32,
   MEBT_GEMM_FORCE_BN64 = 64
@@ -69,6 +70,12 @@ enum {
  */
 int mebt_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
                    int M, int N, int K, const float* bias, const void* residual, int ldres, int flags, void* stream);
+/* Same with an auxiliary bf16 [M, ldaux] tensor: with MEBT_GEMM_GELU it RECEIVES the pre-activation (saved for
+ * backward); with MEBT_GEMM_DGELU it SUPPLIES the pre-activation and the result is multiplied by gelu'(aux), i.e.
+ * d(pre-activation) = (dY * W) .* gelu'(a) for the MLP of mebt/modules/gpt.py:150-155. */
+int mebt_gemm_bf16_aux(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
+                       int M, int N, int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux,
+                       int flags, void* stream);
 
 
 /* ---- dtypes --------------------------------------------------------------------------------- */
@@ -179,6 +186,38 @@ int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV
                               int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, void* O, int ldo,
                               float* lse, int B, int H, int NQ, int head_dim, void* stream);
 
+/* ---- backward of the memory-bound ops (training step, config #2) -------------------------------- */
+/* out[n] (+)= sum_r X[r,n], X bf16 [rows, ld]: the bias gradients autograd computes for every nn.Linear of
+ * mebt/modules/gpt.py:102-116,150-155.  Two-stage fixed-order reduction (deterministic). */
+size_t mebt_colsum_workspace_bytes(int N);
+int mebt_colsum(const void* X, int ld, int rows, int N, float* out, int accumulate, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* nn.LayerNorm backward (gpt.py:147-148,216).  dy, x, dx: bf16 [rows, D] contiguous; mean/rstd as saved by
+ * mebt_layernorm.  dx (+)= ...; dgamma/dbeta (+)= ... (fp32 [D]). */
+size_t mebt_layernorm_bwd_workspace_bytes(int D);
+int mebt_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                       int accumulate_dx, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of mebt_embed_gather: scatter-adds bf16 stream gradients into the fp32 gradients of tok_emb [V,D],
+ * pos_emb [n_pos,D], mask_emb [D], sos_emb [L,D] (all ACCUMULATED into).  Workspace: mebt_colsum_workspace_bytes(D). */
+int mebt_embed_backward(const int64_t* x_indices, int x_stride, const int64_t* ctx_idx, int ctx_stride,
+                        const int64_t* tgt_idx, int tgt_stride, const void* d_contexts, const void* d_targets,
+                        const void* d_latents, float* d_tok_emb, float* d_pos_emb, float* d_mask_emb, float* d_sos_emb,
+                        int B, int NC, int NT, int L, int D, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of mebt_latent_attention_fwd (what autograd runs for mebt/modules/gpt.py:131-137).  Q/KV1/KV2/O and
+ * their layouts exactly as in the forward call; dO [B*NQ, lddo] (head h at columns 64h); lse from the forward.
+ * Gradients are written with the forward's geometry: dQ into a [B*NQ, lddq] buffer at column dq_col0 + 64h, dK/dV of
+ * source s into a [B*NKs, ldds] buffer at dks_col0 / dvs_col0 + 64h (buffers may alias, e.g. one [rows,3D] dQKV).
+ * Workspace: mebt_latent_attention_bwd_workspace_bytes (the per-row delta = rowsum(dO .* O)). */
+size_t mebt_latent_attention_bwd_workspace_bytes(int B, int H, int NQ);
+int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0,
+                              int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, const void* O,
+                              int ldo, const void* dO, int lddo, const float* lse, void* dQ, int lddq, int dq_col0,
+                              void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2, int ldd2, int dk2_col0,
+                              int dv2_col0, int B, int H, int NQ, int head_dim, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 /* ---- the layer stack in one call ---------------------------------------------------------------- */
 enum {
   MEBT_MODE_LATENT_ENC = 0,  /* q = latents, kv = contexts            -> latents   (gpt.py:167-169) */
@@ -209,6 +248,40 @@ size_t mebt_stack_forward_workspace_bytes(int B, int L, int NC, int NT, int D);
 int mebt_stack_forward(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
                        const void* w_head, int B, int L, int NC, int NT, int D, int H, int V, void* lat, void* ctx,
                        void* tgt, void* logits, int logits_dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- training step: forward that saves activations + full backward -------------------------------------- */
+/* fp32 gradient destinations of one Block, same geometry as mebt_layer_t (w_qkv = [3D,D] query|key|value rows). */
+typedef struct mebt_layer_grads {
+  float* ln1_w; float* ln1_b; float* ln2_w; float* ln2_b;
+  float* w_qkv; float* b_qkv; float* w_proj; float* b_proj; float* w_fc1; float* b_fc1; float* w_fc2; float* b_fc2;
+} mebt_layer_grads_t;
+
+size_t mebt_stack_train_saved_bytes(const mebt_layer_t* layers, int n_layers, int B, int L, int NC, int NT, int D, int H);
+size_t mebt_stack_backward_workspace_bytes(int B, int L, int NC, int NT, int D, int H);
+/*
+ * GPT.forward (mebt/modules/gpt.py:234-253) as run inside training_step (mebt/transformer.py:734): like
+ * mebt_stack_forward, but the input streams are left untouched and every tensor backward needs (LayerNorm outputs
+ * and statistics, projections, attention output + log-sum-exp, pre-GELU activations, each new stream version) is
+ * kept in the caller's `saved` arena.  Only the four latent modes are supported (dropout p = 0).
+ */
+int mebt_stack_forward_train(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                             const void* w_head, int B, int L, int NC, int NT, int D, int H, int V, const void* lat0,
+                             const void* ctx, const void* tgt0, void* logits, int logits_dtype, void* saved,
+                             size_t saved_bytes, void* stream);
+/*
+ * Backward of the above — what loss.backward() runs through the reference's stack.  dlogits: bf16 [B*NT, V]
+ * (e.g. from mebt_masked_ce).  Weight/bias/LayerNorm gradients are written (grad_accumulate = 0) or added
+ * (grad_accumulate = 1) to the fp32 destinations in `grads`, d_lnf_*, d_w_head.  d_lat/d_ctx/d_tgt: bf16 stream
+ * gradients [B*L,D], [B*NC,D], [B*NT,D]; on return from the call that includes block 0 they hold the gradients
+ * w.r.t. the stem outputs (feed them to mebt_embed_backward).  Blocks are processed in reverse over
+ * [layer_begin, layer_end); the head is processed when layer_end == n_layers, so a data-parallel caller can issue
+ * the backward in chunks and start the gradient all-reduce of a finished chunk while the next one runs.
+ */
+int mebt_stack_backward(const mebt_layer_t* layers, const mebt_layer_grads_t* grads, int n_layers, const float* lnf_w,
+                        float* d_lnf_w, float* d_lnf_b, const void* w_head, float* d_w_head, int B, int L, int NC, int NT,
+                        int D, int H, int V, const void* lat0, const void* ctx, const void* tgt0, const void* dlogits,
+                        void* saved, size_t saved_bytes, void* d_lat, void* d_ctx, void* d_tgt, int layer_begin,
+                        int layer_end, int grad_accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

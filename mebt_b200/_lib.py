@@ -34,6 +34,18 @@ _SIGNATURES: dict[str, list] = {
     "mebt_device_check": [],
     "mebt_gemm_bf16": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                        c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "mebt_gemm_bf16_aux": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                           c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
+    "mebt_colsum": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
+    "mebt_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                           c_int, c_int, c_void_p, c_size_t, c_void_p],
+    "mebt_embed_backward": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                            c_void_p],
+    "mebt_latent_attention_bwd": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                  c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                  c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_void_p, c_size_t, c_void_p],
     "mebt_embed_gather": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_void_p],
@@ -73,10 +85,31 @@ class LayerStruct(ctypes.Structure):
         "ln1_w", "ln1_b", "ln2_w", "ln2_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
 
 
+class LayerGradsStruct(ctypes.Structure):
+    """mebt_layer_grads_t"""
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_w", "ln1_b", "ln2_w", "ln2_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+
+
+_SIGNATURES["mebt_stack_forward_train"] = [ctypes.POINTER(LayerStruct), c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                           c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int, c_void_p, c_size_t, c_void_p]
+_SIGNATURES["mebt_stack_backward"] = [ctypes.POINTER(LayerStruct), ctypes.POINTER(LayerGradsStruct), c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+                                      c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
 _SIGNATURES["mebt_stack_forward"] = [ctypes.POINTER(LayerStruct), c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p, c_size_t, c_void_p]
 _bind()
+for _n, _a in (("mebt_colsum_workspace_bytes", [c_int]), ("mebt_layernorm_bwd_workspace_bytes", [c_int]),
+               ("mebt_latent_attention_bwd_workspace_bytes", [c_int, c_int, c_int])):
+    getattr(_lib, _n).argtypes = _a
+    getattr(_lib, _n).restype = c_size_t
+_lib.mebt_stack_train_saved_bytes.argtypes = [ctypes.POINTER(LayerStruct), c_int, c_int, c_int, c_int, c_int, c_int, c_int]
+_lib.mebt_stack_train_saved_bytes.restype = c_size_t
+_lib.mebt_stack_backward_workspace_bytes.argtypes = [c_int] * 6
+_lib.mebt_stack_backward_workspace_bytes.restype = c_size_t
 _lib.mebt_launch_count.argtypes = []
 _lib.mebt_launch_count.restype = ctypes.c_ulonglong
 _lib.mebt_profile_enable.argtypes = [c_int]

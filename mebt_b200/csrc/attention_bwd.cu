@@ -1,0 +1,438 @@
+// Backward of K3 (latent attention), head_dim 64 — what autograd computes for the bmm/softmax/bmm of
+// CrossAttention.forward (mebt/modules/gpt.py:131-137) in the training step.
+//
+//   P = exp(S * scale - lse),  S = Q K^T          (recomputed from the saved log-sum-exp, nothing [NQ,NK] is stored)
+//   dV = P^T dO          dP = dO V^T          dS = P .* (dP - delta) * scale,  delta = rowsum(dO .* O)
+//   dQ = dS K            dK = dS^T Q
+//
+// Two kernels, both tcgen05/TMEM/TMA like the forward, no atomics (bitwise reproducible):
+//   attn_bwd_dkv_kernel : one CTA per (128-key tile, head, batch, source); loops over query tiles and keeps the
+//                         dV / dK accumulators in TMEM.  P^T and dS^T are never transposed in memory: the P / dS
+//                         tiles written to shared memory as [q][k] are consumed as MN-major A operands.
+//   attn_bwd_dq_kernel  : one CTA per (128-query tile, head, batch); walks the key tiles of both sources and
+//                         keeps dQ in TMEM.
+// S and dP are recomputed in both (7 instead of 5 tile products): attention is ~5 % of the step's FLOPs.
+#include "common.cuh"
+
+namespace mebt {
+
+int attn_delta(const void* dO, int lddo, const void* O, int ldo, float* delta, int B, int H, int NQ, cudaStream_t st);
+
+namespace {
+
+constexpr int AB_THREADS = 192;
+constexpr int TILE = 128 * 64 * 2;    // 16 KiB, a [128 x 64] bf16 tile
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct BwdParams {
+  int NQ, NK, H;             // NK: keys of the source this launch covers (dkv) / unused (dq)
+  int NK1, NK2;              // dq kernel: both sources
+  int q_col0, k_col0, v_col0;
+  int k1_col0, v1_col0, k2_col0, v2_col0;
+  int do_col0;
+  const float* lse;          // [B,H,NQ]
+  const float* delta;        // [B,H,NQ]
+  __nv_bfloat16* dQ; int lddq; int dq_col0;
+  __nv_bfloat16* dKV; int lddkv; int dk_col0, dv_col0;
+  float scale, scale_log2;
+};
+
+// One thread = one query row of the current [128 q x 128 k] tile pair (S and dP in TMEM).  Computes P and dS for
+// 32 keys at a time and stores them as bf16 into the 128B-swizzled [q][k] shared-memory tiles.
+__device__ __forceinline__ void softmax_bwd_row(uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_addr, int row,
+                                                bool row_ok, int valid_keys, float lse_l2, float delta, float scale,
+                                                float scale_log2, uint8_t* sP, uint8_t* sdS) {
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t rs[32], rd[32];
+    tmem_ld_32x32(tmem_s + lane_addr + c * 32, rs);
+    tmem_ld_32x32(tmem_dp + lane_addr + c * 32, rd);
+    tmem_ld_wait();
+    float p[32], ds[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const bool ok = row_ok && (c * 32 + i < valid_keys);
+      const float pv = ok ? exp2f(__uint_as_float(rs[i]) * scale_log2 - lse_l2) : 0.f;
+      p[i] = pv;
+      ds[i] = ok ? pv * (__uint_as_float(rd[i]) - delta) * scale : 0.f;
+    }
+    const int off = (c >> 1) * (2 * TILE) / 2 + row * 128;     // half (64 keys) = one 16 KiB swizzle-atom column
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int chunk = (c & 1) * 4 + g;
+      const int sw = (chunk ^ (row & 7)) << 4;
+      if (sP != nullptr) {
+        uint4 u;
+        u.x = pack_bf16x2(p[8 * g + 0], p[8 * g + 1]); u.y = pack_bf16x2(p[8 * g + 2], p[8 * g + 3]);
+        u.z = pack_bf16x2(p[8 * g + 4], p[8 * g + 5]); u.w = pack_bf16x2(p[8 * g + 6], p[8 * g + 7]);
+        *reinterpret_cast<uint4*>(sP + off + sw) = u;
+      }
+      uint4 w;
+      w.x = pack_bf16x2(ds[8 * g + 0], ds[8 * g + 1]); w.y = pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]);
+      w.z = pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]); w.w = pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]);
+      *reinterpret_cast<uint4*>(sdS + off + sw) = w;
+    }
+  }
+}
+
+// store a [128 rows x 64] fp32 TMEM tile (lanes = rows) as bf16 into global memory
+__device__ __forceinline__ void store_tmem_rows(uint32_t tmem_addr, uint32_t lane_addr, __nv_bfloat16* dst, bool ok) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_addr + lane_addr + c * 32, r);
+    tmem_ld_wait();
+    if (ok) {
+      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
+        u.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+        u.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+        u.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+        d4[g] = u;
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// dK / dV
+// ================================================================================================
+constexpr int DKV_SMEM_K = 0, DKV_SMEM_V = TILE, DKV_SMEM_Q = 2 * TILE /* 2 stages */, DKV_SMEM_DO = 4 * TILE /* 2 stages */,
+              DKV_SMEM_P = 6 * TILE, DKV_SMEM_DS = 8 * TILE, DKV_SMEM_BAR = 10 * TILE, DKV_SMEM_TOTAL = DKV_SMEM_BAR + 128;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                    const __grid_constant__ CUtensorMap tm_kv, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_SMEM_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* q_empty = bars + 3;   // [2]
+  uint64_t* sp_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* dkv_done = bars + 7;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nq = (p.NQ + 127) / 128;
+  const int valid_keys = min(128, p.NK - jt * 128);
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tm_q); prefetch_tensormap(&tm_do); prefetch_tensormap(&tm_kv);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(sp_full, 1); mbar_init(pds_full, 128); mbar_init(dkv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int krow = b * p.NK + jt * 128;
+      mbar_arrive_expect_tx(kv_full, 2 * TILE);
+      tma_load_2d(smem + DKV_SMEM_K, &tm_kv, kv_full, p.k_col0 + h * 64, krow);
+      tma_load_2d(smem + DKV_SMEM_V, &tm_kv, kv_full, p.v_col0 + h * 64, krow);
+      for (int i = 0; i < nq; ++i) {
+        const int s = i & 1;
+        mbar_wait(&q_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[s], 2 * TILE);
+        const int qrow = b * p.NQ + i * 128;
+        tma_load_2d(smem + DKV_SMEM_Q + s * TILE, &tm_q, &q_full[s], p.q_col0 + h * 64, qrow);
+        tma_load_2d(smem + DKV_SMEM_DO + s * TILE, &tm_do, &q_full[s], p.do_col0 + h * 64, qrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);   // [q x d] . [k x d]^T
+      constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);     // (P|dS)^T as MN-major A, (dO|Q) as MN-major B
+      const uint32_t sK = smem_u32(smem + DKV_SMEM_K), sV = smem_u32(smem + DKV_SMEM_V);
+      const uint32_t sP = smem_u32(smem + DKV_SMEM_P), sdS = smem_u32(smem + DKV_SMEM_DS);
+      auto issue_s_dp = [&](int i) {
+        const uint32_t sQ = smem_u32(smem + DKV_SMEM_Q + (i & 1) * TILE), sdO = smem_u32(smem + DKV_SMEM_DO + (i & 1) * TILE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_s, make_smem_desc_sw128(sQ + k * 32, 16, 1024), make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                       idesc_qk, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_dp, make_smem_desc_sw128(sdO + k * 32, 16, 1024), make_smem_desc_sw128(sV + k * 32, 16, 1024),
+                       idesc_qk, k != 0);
+        umma_commit(sp_full);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&q_full[0], 0);
+      tc_fence_after();
+      issue_s_dp(0);
+      for (int i = 0; i < nq; ++i) {
+        if (i + 1 < nq) mbar_wait(&q_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+        if (i + 1 < nq) issue_s_dp(i + 1);
+        const uint32_t sQ = smem_u32(smem + DKV_SMEM_Q + (i & 1) * TILE), sdO = smem_u32(smem + DKV_SMEM_DO + (i & 1) * TILE);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {     // reduction over the 128 queries of this tile, 16 at a time
+          // A: [q rows][k cols] tile read as MN-major (M = keys): two 64-key atoms 16 KiB apart, 8 q-rows per 1 KiB
+          const uint64_t a_p = make_smem_desc_sw128(sP + kk * 2048, TILE, 1024);
+          const uint64_t a_ds = make_smem_desc_sw128(sdS + kk * 2048, TILE, 1024);
+          const uint64_t b_do = make_smem_desc_sw128(sdO + kk * 2048, TILE, 1024);
+          const uint64_t b_q = make_smem_desc_sw128(sQ + kk * 2048, TILE, 1024);
+          umma_bf16_ss(tmem_dv, a_p, b_do, idesc_t, (i | kk) != 0);
+          umma_bf16_ss(tmem_dk, a_ds, b_q, idesc_t, (i | kk) != 0);
+        }
+        umma_commit(&q_empty[i & 1]);
+        umma_commit(dkv_done);
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
+    for (int i = 0; i < nq; ++i) {
+      const int qrow = i * 128 + row;
+      const bool row_ok = qrow < p.NQ;
+      float lse_l2 = 0.f, delta = 0.f;
+      if (row_ok) {
+        const size_t o = (size_t(b) * p.H + h) * p.NQ + qrow;
+        lse_l2 = p.lse[o] * LOG2E;
+        delta = p.delta[o];
+      }
+      mbar_wait(sp_full, i & 1);
+      tc_fence_after();
+      if (i > 0) mbar_wait(dkv_done, (i - 1) & 1);    // the previous tile's P / dS are no longer being read
+      softmax_bwd_row(tmem_s, tmem_dp, lane_addr, row, row_ok, valid_keys, lse_l2, delta, p.scale, p.scale_log2,
+                      smem + DKV_SMEM_P, smem + DKV_SMEM_DS);
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(pds_full);
+    }
+    mbar_wait(dkv_done, (nq - 1) & 1);
+    tc_fence_after();
+    const bool ok = row < valid_keys;            // TMEM lanes are key rows here
+    __nv_bfloat16* base = p.dKV + (size_t(b) * p.NK + jt * 128 + row) * p.lddkv + h * 64;
+    store_tmem_rows(tmem_dv, lane_addr, base + p.dv_col0, ok);
+    store_tmem_rows(tmem_dk, lane_addr, base + p.dk_col0, ok);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ================================================================================================
+// dQ
+// ================================================================================================
+constexpr int DQ_SMEM_Q = 0, DQ_SMEM_DO = TILE, DQ_SMEM_K = 2 * TILE /* 2 stages */, DQ_SMEM_V = 4 * TILE /* 2 stages */,
+              DQ_SMEM_DS = 6 * TILE, DQ_SMEM_BAR = 8 * TILE, DQ_SMEM_TOTAL = DQ_SMEM_BAR + 128;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_kv1, const __grid_constant__ CUtensorMap tm_kv2,
+                   const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_SMEM_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* sp_full = bars + 5;
+  uint64_t* ds_full = bars + 6;
+  uint64_t* dq_done = bars + 7;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tiles1 = (p.NK1 + 127) / 128, tiles2 = (p.NK2 + 127) / 128;
+  const int nt = tiles1 + tiles2;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tm_q); prefetch_tensormap(&tm_do); prefetch_tensormap(&tm_kv1); prefetch_tensormap(&tm_kv2);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(sp_full, 1); mbar_init(ds_full, 128); mbar_init(dq_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0 && nt > 0) {
+      const int qrow = b * p.NQ + qt * 128;
+      mbar_arrive_expect_tx(q_full, 2 * TILE);
+      tma_load_2d(smem + DQ_SMEM_Q, &tm_q, q_full, p.q_col0 + h * 64, qrow);
+      tma_load_2d(smem + DQ_SMEM_DO, &tm_do, q_full, p.do_col0 + h * 64, qrow);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * TILE);
+        if (j < tiles1) {
+          const int r = b * p.NK1 + j * 128;
+          tma_load_2d(smem + DQ_SMEM_K + s * TILE, &tm_kv1, &kv_full[s], p.k1_col0 + h * 64, r);
+          tma_load_2d(smem + DQ_SMEM_V + s * TILE, &tm_kv1, &kv_full[s], p.v1_col0 + h * 64, r);
+        } else {
+          const int r = b * p.NK2 + (j - tiles1) * 128;
+          tma_load_2d(smem + DQ_SMEM_K + s * TILE, &tm_kv2, &kv_full[s], p.k2_col0 + h * 64, r);
+          tma_load_2d(smem + DQ_SMEM_V + s * TILE, &tm_kv2, &kv_full[s], p.v2_col0 + h * 64, r);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nt > 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);    // dS (K-major) x K (MN-major: d contiguous)
+      const uint32_t sQ = smem_u32(smem + DQ_SMEM_Q), sdO = smem_u32(smem + DQ_SMEM_DO), sdS = smem_u32(smem + DQ_SMEM_DS);
+      auto issue_s_dp = [&](int j) {
+        const uint32_t sK = smem_u32(smem + DQ_SMEM_K + (j & 1) * TILE), sV = smem_u32(smem + DQ_SMEM_V + (j & 1) * TILE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_s, make_smem_desc_sw128(sQ + k * 32, 16, 1024), make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                       idesc_qk, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_dp, make_smem_desc_sw128(sdO + k * 32, 16, 1024), make_smem_desc_sw128(sV + k * 32, 16, 1024),
+                       idesc_qk, k != 0);
+        umma_commit(sp_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s_dp(0);
+      for (int j = 0; j < nt; ++j) {
+        if (j + 1 < nt) mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        mbar_wait(ds_full, j & 1);
+        tc_fence_after();
+        if (j + 1 < nt) issue_s_dp(j + 1);
+        const uint32_t sK = smem_u32(smem + DQ_SMEM_K + (j & 1) * TILE);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(sdS + (kk >> 2) * TILE + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sK + kk * 2048, TILE, 1024);
+          umma_bf16_ss(tmem_dq, da, db, idesc_dq, (j | kk) != 0);
+        }
+        umma_commit(&kv_empty[j & 1]);
+        umma_commit(dq_done);
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
+    const int qrow = qt * 128 + row;
+    const bool row_ok = qrow < p.NQ;
+    float lse_l2 = 0.f, delta = 0.f;
+    if (row_ok) {
+      const size_t o = (size_t(b) * p.H + h) * p.NQ + qrow;
+      lse_l2 = p.lse[o] * LOG2E;
+      delta = p.delta[o];
+    }
+    for (int j = 0; j < nt; ++j) {
+      const int valid = j < tiles1 ? min(128, p.NK1 - j * 128) : min(128, p.NK2 - (j - tiles1) * 128);
+      mbar_wait(sp_full, j & 1);
+      tc_fence_after();
+      if (j > 0) mbar_wait(dq_done, (j - 1) & 1);
+      softmax_bwd_row(tmem_s, tmem_dp, lane_addr, row, row_ok, valid, lse_l2, delta, p.scale, p.scale_log2, nullptr,
+                      smem + DQ_SMEM_DS);
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(ds_full);
+    }
+    __nv_bfloat16* dst = p.dQ + (size_t(b) * p.NQ + qrow) * p.lddq + p.dq_col0 + h * 64;
+    if (nt > 0) {
+      mbar_wait(dq_done, (nt - 1) & 1);
+      tc_fence_after();
+      store_tmem_rows(tmem_dq, lane_addr, dst, row_ok);
+    } else if (row_ok) {
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) d4[g] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace
+}  // namespace mebt
+
+extern "C" {
+
+size_t mebt_latent_attention_bwd_workspace_bytes(int B, int H, int NQ) { return size_t(B) * H * NQ * sizeof(float); }
+
+int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0,
+                              int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, const void* O,
+                              int ldo, const void* dO, int lddo, const float* lse, void* dQ, int lddq, int dq_col0,
+                              void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2, int ldd2, int dk2_col0,
+                              int dv2_col0, int B, int H, int NQ, int head_dim, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  using namespace mebt;
+  MEBT_REQUIRE(head_dim == 64, MEBT_ERR_UNSUPPORTED, "attention_bwd: head_dim %d unsupported", head_dim);
+  MEBT_REQUIRE(B > 0 && H > 0 && NQ > 0 && NK1 >= 0 && NK2 >= 0, MEBT_ERR_SHAPE, "attention_bwd: bad shape");
+  MEBT_REQUIRE(workspace != nullptr && workspace_bytes >= size_t(B) * H * NQ * 4, MEBT_ERR_WORKSPACE,
+               "attention_bwd: workspace too small");
+  MEBT_REQUIRE(ldq % 8 == 0 && lddo % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0, MEBT_ERR_SHAPE, "attention_bwd: strides");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* delta = static_cast<float*>(workspace);
+  int rc = attn_delta(dO, lddo, O, ldo, delta, B, H, NQ, st);
+  if (rc) return rc;
+  CUtensorMap tq, tdo, t1, t2;
+  rc = get_tensor_map_2d(&tq, Q, 2, uint64_t(ldq), uint64_t(B) * NQ, uint64_t(ldq) * 2, 64, 128);
+  if (rc) return rc;
+  rc = get_tensor_map_2d(&tdo, dO, 2, uint64_t(lddo), uint64_t(B) * NQ, uint64_t(lddo) * 2, 64, 128);
+  if (rc) return rc;
+  t1 = tq; t2 = tq;
+  if (NK1 > 0) { rc = get_tensor_map_2d(&t1, KV1, 2, uint64_t(ld1), uint64_t(B) * NK1, uint64_t(ld1) * 2, 64, 128); if (rc) return rc; }
+  if (NK2 > 0) { rc = get_tensor_map_2d(&t2, KV2, 2, uint64_t(ld2), uint64_t(B) * NK2, uint64_t(ld2) * 2, 64, 128); if (rc) return rc; }
+  static bool attr = false;
+  if (!attr) {
+    MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM_TOTAL));
+    MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM_TOTAL));
+    attr = true;
+  }
+  BwdParams p;
+  p.NQ = NQ; p.H = H; p.NK1 = NK1; p.NK2 = NK2; p.NK = 0;
+  p.q_col0 = q_col0; p.do_col0 = 0;
+  p.k1_col0 = k1_col0; p.v1_col0 = v1_col0; p.k2_col0 = k2_col0; p.v2_col0 = v2_col0;
+  p.k_col0 = p.v_col0 = 0;
+  p.lse = lse; p.delta = delta;
+  p.dQ = static_cast<__nv_bfloat16*>(dQ); p.lddq = lddq; p.dq_col0 = dq_col0;
+  p.dKV = nullptr; p.lddkv = 0; p.dk_col0 = p.dv_col0 = 0;
+  p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
+  const double flops_tile = 2.0 * 128 * 128 * 64;
+  {
+    const int nqt = (NQ + 127) / 128;
+    LaunchScope ls(FAM_ATTENTION, 3.0 * flops_tile * double(B) * H * nqt * ((NK1 + 127) / 128 + (NK2 + 127) / 128), st);
+    attn_bwd_dq_kernel<<<dim3(nqt, H, B), AB_THREADS, DQ_SMEM_TOTAL, st>>>(tq, tdo, t1, t2, p);
+  }
+  MEBT_LAUNCH_OK("attn_bwd_dq_kernel");
+  for (int src = 0; src < 2; ++src) {
+    const int NK = src == 0 ? NK1 : NK2;
+    if (NK == 0) continue;
+    BwdParams pk = p;
+    pk.NK = NK;
+    pk.k_col0 = src == 0 ? k1_col0 : k2_col0;
+    pk.v_col0 = src == 0 ? v1_col0 : v2_col0;
+    pk.dKV = static_cast<__nv_bfloat16*>(src == 0 ? dKV1 : dKV2);
+    pk.lddkv = src == 0 ? ldd1 : ldd2;
+    pk.dk_col0 = src == 0 ? dk1_col0 : dk2_col0;
+    pk.dv_col0 = src == 0 ? dv1_col0 : dv2_col0;
+    MEBT_REQUIRE(pk.dKV != nullptr && pk.lddkv % 8 == 0, MEBT_ERR_SHAPE, "attention_bwd: bad dKV%d", src + 1);
+    const int nkt = (NK + 127) / 128;
+    LaunchScope ls(FAM_ATTENTION, 4.0 * flops_tile * double(B) * H * nkt * ((NQ + 127) / 128), st);
+    attn_bwd_dkv_kernel<<<dim3(nkt, H, B), AB_THREADS, DKV_SMEM_TOTAL, st>>>(tq, tdo, src == 0 ? t1 : t2, pk);
+    MEBT_LAUNCH_OK("attn_bwd_dkv_kernel");
+  }
+  return MEBT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+// Memory-bound backward kernels of the MeBT training step (what torch autograd runs for the reference's
+// nn.LayerNorm / nn.Linear bias / nn.Embedding / gather on the path of mebt/transformer.py:216-286 and
+// mebt/modules/gpt.py:159-253):
+//   column sums (bias gradients), LayerNorm backward (dx + per-CTA dgamma/dbeta partials), the partial
+//   reducer, and the stem's scatter-add into tok_emb / pos_emb / mask_emb / sos_emb gradients.
+// Reductions over rows are two-stage with a fixed order (deterministic); only the embedding scatter-add uses
+// fp32 atomics (several tokens of a batch may hit the same row), like torch's embedding backward.
+#include "common.cuh"
+
+namespace mebt {
+namespace {
+
+__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---- column sums: partial[r, n] = sum over the r-th row slab of X[:, n] ------------------------------------
+// grid (N / 128, slabs); 256 threads = 32 column-quads x 8 row lanes
+__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ X, int ld, int rows, int N,
+                                      int rows_per_slab, float* __restrict__ partial) {
+  __shared__ float4 red[8][32];
+  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 128 + cq * 4;
+  const int r0 = blockIdx.y * rows_per_slab;
+  const int r1 = min(rows, r0 + rows_per_slab);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N)
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const float4 v = ld_bf16x4(X + size_t(r) * ld + col);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  red[rl][cq] = acc;
+  __syncthreads();
+  if (rl == 0 && col < N) {
+    for (int i = 1; i < 8; ++i) {
+      const float4 v = red[i][cq];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(partial + size_t(blockIdx.y) * N + col) = acc;
+  }
+}
+
+// out[n] (+)= sum_s partial[s, n]   (fixed order)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int slabs, int N, float* __restrict__ out,
+                                       int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int s = 0; s < slabs; ++s) acc += partial[size_t(s) * N + n];
+  out[n] = accumulate ? out[n] + acc : acc;
+}
+
+// ---- LayerNorm backward --------------------------------------------------------------------------------------
+// y = (x - mean) * rstd * gamma + beta
+// dx = rstd * (g - mean_D(g) - xhat * mean_D(g * xhat)),  g = dy * gamma;   dgamma = sum_rows dy * xhat; dbeta = sum_rows dy
+// One warp per row, rows strided over a fixed grid; each lane keeps its dgamma/dbeta slice in registers across rows.
+template <int MAX_VEC>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx, int accumulate_dx,
+                                     int rows, int D, float* __restrict__ partial /* [grid, 2, D] */) {
+  extern __shared__ float sm[];   // [8 warps][2][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 dg[MAX_VEC], db[MAX_VEC], gm[MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = (lane + 32 * i) * 4;
+    gm[i] = c < D ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invD = 1.0f / float(D);
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[MAX_VEC], g[MAX_VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < D) {
+        const float4 xv = ld_bf16x4(x + row * D + c);
+        const float4 dv = ld_bf16x4(dy + row * D + c);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+        dg[i].x += dv.x * xh[i].x; dg[i].y += dv.y * xh[i].y; dg[i].z += dv.z * xh[i].z; dg[i].w += dv.w * xh[i].w;
+        db[i].x += dv.x; db[i].y += dv.y; db[i].z += dv.z; db[i].w += dv.w;
+      }
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < D) {
+        float4 o;
+        o.x = rs * (g[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (g[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (g[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+        if (accumulate_dx) {
+          const float4 old = ld_bf16x4(dx + row * D + c);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        st_bf16x4(dx + row * D + c, o);
+      }
+    }
+  }
+  // block reduction of the per-warp dgamma / dbeta slices, fixed order
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < D) {
+      *reinterpret_cast<float4*>(sm + (warp * 2 + 0) * D + c) = dg[i];
+      *reinterpret_cast<float4*>(sm + (warp * 2 + 1) * D + c) = db[i];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * D; idx += blockDim.x) {
+    const int which = idx / D, c = idx % D;
+    float acc = 0.f;
+    for (int w = 0; w < 8; ++w) acc += sm[(w * 2 + which) * D + c];
+    partial[(size_t(blockIdx.x) * 2 + which) * D + c] = acc;
+  }
+}
+
+// ---- stem backward ---------------------------------------------------------------------------------------------
+// d_tok_emb[x[ctx_idx]] += d_ctx; d_pos_emb[ctx_idx] += d_ctx; d_pos_emb[tgt_idx] += d_tgt   (fp32 atomics)
+__global__ void embed_scatter_add_kernel(const int64_t* __restrict__ x, int x_stride, const int64_t* __restrict__ ctx_idx,
+                                         int ctx_stride, const int64_t* __restrict__ tgt_idx, int tgt_stride,
+                                         const __nv_bfloat16* __restrict__ d_ctx, const __nv_bfloat16* __restrict__ d_tgt,
+                                         float* __restrict__ d_tok, float* __restrict__ d_pos, int B, int NC, int NT,
+                                         int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  const long long n_ctx = (long long)B * NC, n_tgt = (long long)B * NT;
+  if (row >= n_ctx + n_tgt) return;
+  const __nv_bfloat16* src;
+  float* dst_tok = nullptr;
+  float* dst_pos;
+  if (row < n_ctx) {
+    const int b = int(row / NC), i = int(row % NC);
+    const long long pos = ctx_idx[(long long)b * ctx_stride + i];
+    const long long tok = x[(long long)b * x_stride + pos];
+    src = d_ctx + row * D;
+    dst_tok = d_tok + tok * D;
+    dst_pos = d_pos + pos * D;
+  } else {
+    const long long r = row - n_ctx;
+    const int b = int(r / NT), i = int(r % NT);
+    const long long pos = tgt_idx[(long long)b * tgt_stride + i];
+    src = d_tgt + r * D;
+    dst_pos = d_pos + pos * D;
+  }
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = ld_bf16x4(src + c);
+    atomicAdd(dst_pos + c + 0, v.x); atomicAdd(dst_pos + c + 1, v.y);
+    atomicAdd(dst_pos + c + 2, v.z); atomicAdd(dst_pos + c + 3, v.w);
+    if (dst_tok != nullptr) {
+      atomicAdd(dst_tok + c + 0, v.x); atomicAdd(dst_tok + c + 1, v.y);
+      atomicAdd(dst_tok + c + 2, v.z); atomicAdd(dst_tok + c + 3, v.w);
+    }
+  }
+}
+
+// d_sos[l, :] (+)= sum_b d_lat[b, l, :]   (fixed order over b)
+__global__ void batch_sum_kernel(const __nv_bfloat16* __restrict__ d_lat, int B, long long per_batch,
+                                 float* __restrict__ out, int accumulate) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= per_batch) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; ++b) {
+    const float4 v = ld_bf16x4(d_lat + b * per_batch + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float4* o = reinterpret_cast<float4*>(out + i);
+  if (accumulate) { const float4 p = *o; acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w; }
+  *o = acc;
+}
+
+// dgamma[c] (+)= sum_g partial[g][0][c];  dbeta[c] (+)= sum_g partial[g][1][c]   (fixed order)
+__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int grid, int D, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * D) return;
+  const int which = idx / D, c = idx % D;
+  float acc = 0.f;
+  for (int g = 0; g < grid; ++g) acc += partial[(size_t(g) * 2 + which) * D + c];
+  float* out = which == 0 ? dgamma : dbeta;
+  out[c] = accumulate ? out[c] + acc : acc;
+}
+
+// attention backward preprocess: delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloat16* __restrict__ O,
+                                  int ldo, float* __restrict__ delta, int B, int H, int NQ) {
+  // one warp per (b, q) row; lane pair handles one head (64 dims = 2 lanes x 32)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= (long long)B * NQ) return;
+  const int b = int(row / NQ), q = int(row % NQ);
+  for (int h0 = 0; h0 < H; h0 += 16) {
+    const int h = h0 + (lane >> 1);
+    float acc = 0.f;
+    if (h < H) {
+      const int c0 = h * 64 + (lane & 1) * 32;
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        const float4 a = ld_bf16x4(dO + row * lddo + c0 + k);
+        const float4 o = ld_bf16x4(O + row * ldo + c0 + k);
+        acc += (a.x * o.x + a.y * o.y) + (a.z * o.z + a.w * o.w);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (h < H && (lane & 1) == 0) delta[(size_t(b) * H + h) * NQ + q] = acc;
+  }
+}
+
+}  // namespace
+
+int colsum(const void* X, int ld, int rows, int N, float* out, int accumulate, float* workspace, size_t ws_bytes,
+           cudaStream_t st) {
+  MEBT_REQUIRE(rows >= 0 && N > 0 && N % 4 == 0 && ld % 4 == 0, MEBT_ERR_SHAPE, "colsum: bad shape rows=%d N=%d", rows, N);
+  int slabs = (rows + 255) / 256;
+  if (slabs > 64) slabs = 64;
+  if (slabs < 1) slabs = 1;
+  const int rows_per_slab = (rows + slabs - 1) / slabs;
+  MEBT_REQUIRE(workspace != nullptr && ws_bytes >= size_t(slabs) * N * 4, MEBT_ERR_WORKSPACE,
+               "colsum: workspace too small (%zu < %zu)", ws_bytes, size_t(slabs) * N * 4);
+  {
+    LaunchScope ls(FAM_OTHER, double(rows) * N * 2.0, st);
+    dim3 grid((N + 127) / 128, slabs);
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), ld, rows, N, rows_per_slab, workspace);
+  }
+  MEBT_LAUNCH_OK("colsum_partial_kernel");
+  {
+    LaunchScope ls(FAM_OTHER, double(slabs) * N * 4.0, st);
+    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(workspace, slabs, N, out, accumulate);
+  }
+  MEBT_LAUNCH_OK("reduce_partials_kernel");
+  return MEBT_OK;
+}
+
+constexpr int LNB_GRID = 148 * 2;
+
+size_t layernorm_bwd_workspace_bytes(int D) { return size_t(LNB_GRID) * 2 * D * 4; }
+
+int layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                  int accumulate_dx, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
+                  float* workspace, size_t ws_bytes, cudaStream_t st) {
+  MEBT_REQUIRE(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024, MEBT_ERR_SHAPE, "layernorm_bwd: bad shape rows=%d D=%d", rows, D);
+  MEBT_REQUIRE(workspace != nullptr && ws_bytes >= layernorm_bwd_workspace_bytes(D), MEBT_ERR_WORKSPACE,
+               "layernorm_bwd: workspace too small");
+  if (rows == 0) return MEBT_OK;
+  int grid = (rows + 7) / 8;
+  if (grid > LNB_GRID) grid = LNB_GRID;
+  const size_t smem = size_t(8) * 2 * D * 4;
+  static bool attr = false;
+  if (!attr) {
+    MEBT_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    attr = true;
+  }
+  const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx);
+  {
+    LaunchScope ls(FAM_LAYERNORM, double(rows) * D * (accumulate_dx ? 8.0 : 6.0), st);
+    if (D <= 256) layernorm_bwd_kernel<2><<<grid, 256, smem, st>>>(dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace);
+    else if (D <= 512) layernorm_bwd_kernel<4><<<grid, 256, smem, st>>>(dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace);
+    else layernorm_bwd_kernel<8><<<grid, 256, smem, st>>>(dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace);
+  }
+  MEBT_LAUNCH_OK("layernorm_bwd_kernel");
+  {
+    LaunchScope ls(FAM_OTHER, double(grid) * 2 * D * 4.0, st);
+    ln_param_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(workspace, grid, D, dgamma, dbeta, accumulate_params);
+  }
+  MEBT_LAUNCH_OK("ln_param_reduce_kernel");
+  return MEBT_OK;
+}
+
+int embed_backward(const int64_t* x, int x_stride, const int64_t* ctx_idx, int ctx_stride, const int64_t* tgt_idx,
+                   int tgt_stride, const void* d_ctx, const void* d_tgt, const void* d_lat, float* d_tok, float* d_pos,
+                   float* d_mask, float* d_sos, int B, int NC, int NT, int L, int D, float* workspace, size_t ws_bytes,
+                   cudaStream_t st) {
+  MEBT_REQUIRE(B > 0 && NC >= 0 && NT >= 0 && L >= 0 && D % 4 == 0, MEBT_ERR_SHAPE, "embed_backward: bad shape");
+  const long long rows = (long long)B * (NC + NT);
+  if (rows > 0) {
+    LaunchScope ls(FAM_EMBED, double(B) * (NC * (16.0 + 2.0 * D + 16.0 * D) + NT * (8.0 + 2.0 * D + 8.0 * D)), st);
+    embed_scatter_add_kernel<<<int((rows + 7) / 8), 256, 0, st>>>(
+        x, x_stride, ctx_idx, ctx_stride, tgt_idx, tgt_stride, static_cast<const __nv_bfloat16*>(d_ctx),
+        static_cast<const __nv_bfloat16*>(d_tgt), d_tok, d_pos, B, NC, NT, D);
+    MEBT_LAUNCH_OK("embed_scatter_add_kernel");
+  }
+  if (NT > 0) {   // mask_emb is broadcast to every target row (transformer.py:263)
+    int rc = colsum(d_tgt, D, B * NT, D, d_mask, 1, workspace, ws_bytes, st);
+    if (rc) return rc;
+  }
+  if (L > 0) {    // sos_emb is broadcast over the batch (transformer.py:274)
+    const long long per_batch = (long long)L * D;
+    LaunchScope ls(FAM_OTHER, double(B) * per_batch * 2.0, st);
+    batch_sum_kernel<<<int((per_batch / 4 + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(d_lat), B,
+                                                                        per_batch, d_sos, 1);
+    MEBT_LAUNCH_OK("batch_sum_kernel");
+  }
+  return MEBT_OK;
+}
+
+int attn_delta(const void* dO, int lddo, const void* O, int ldo, float* delta, int B, int H, int NQ, cudaStream_t st) {
+  const long long rows = (long long)B * NQ;
+  if (rows == 0) return MEBT_OK;
+  LaunchScope ls(FAM_ATTENTION, 0.0, st);
+  attn_delta_kernel<<<int((rows + 7) / 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dO), lddo,
+                                                         static_cast<const __nv_bfloat16*>(O), ldo, delta, B, H, NQ);
+  MEBT_LAUNCH_OK("attn_delta_kernel");
+  return MEBT_OK;
+}
+
+}  // namespace mebt
+
+extern "C" {
+
+size_t mebt_colsum_workspace_bytes(int N) { return size_t(64) * N * 4; }
+
+int mebt_colsum(const void* X, int ld, int rows, int N, float* out, int accumulate, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  return mebt::colsum(X, ld, rows, N, out, accumulate, static_cast<float*>(workspace), workspace_bytes,
+                      static_cast<cudaStream_t>(stream));
+}
+
+size_t mebt_layernorm_bwd_workspace_bytes(int D) { return mebt::layernorm_bwd_workspace_bytes(D); }
+
+int mebt_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                       int accumulate_dx, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  return mebt::layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta, accumulate_params, rows, D,
+                             static_cast<float*>(workspace), workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int mebt_embed_backward(const int64_t* x_indices, int x_stride, const int64_t* ctx_idx, int ctx_stride,
+                        const int64_t* tgt_idx, int tgt_stride, const void* d_contexts, const void* d_targets,
+                        const void* d_latents, float* d_tok_emb, float* d_pos_emb, float* d_mask_emb, float* d_sos_emb,
+                        int B, int NC, int NT, int L, int D, void* workspace, size_t workspace_bytes, void* stream) {
+  return mebt::embed_backward(x_indices, x_stride, ctx_idx, ctx_stride, tgt_idx, tgt_stride, d_contexts, d_targets,
+                              d_latents, d_tok_emb, d_pos_emb, d_mask_emb, d_sos_emb, B, NC, NT, L, D,
+                              static_cast<float*>(workspace), workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -234,6 +234,10 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 // exact (erf) GELU, as torch.nn.GELU() default
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// d/dx of the erf GELU: Phi(x) + x * phi(x)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
 #endif  // __CUDACC__
 
 }  // namespace mebt

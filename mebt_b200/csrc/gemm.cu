@@ -37,6 +37,9 @@ struct GemmParams {
   int gelu;
   int out_fp32;
   int accumulate;                      // C += result (fp32 output only)
+  __nv_bfloat16* aux;                  // gelu: optional pre-activation output; dgelu: pre-activation input
+  int ldaux;
+  int dgelu;                           // result *= gelu'(aux)
 };
 
 template <int BN, int STAGES>
@@ -183,8 +186,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
         if (p.gelu) {
+          if (p.aux != nullptr && row_ok) {      // keep the pre-activation for the backward pass
+            uint4* a4 = reinterpret_cast<uint4*>(p.aux + size_t(row) * p.ldaux + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              a4[j] = o;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (p.dgelu && row_ok) {
+          const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.ldaux + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = __ldg(a4 + j);
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+            v[8 * j + 0] *= gelu_erf_grad(a.x); v[8 * j + 1] *= gelu_erf_grad(a.y);
+            v[8 * j + 2] *= gelu_erf_grad(b.x); v[8 * j + 3] *= gelu_erf_grad(b.y);
+            v[8 * j + 4] *= gelu_erf_grad(c2.x); v[8 * j + 5] *= gelu_erf_grad(c2.y);
+            v[8 * j + 6] *= gelu_erf_grad(d.x); v[8 * j + 7] *= gelu_erf_grad(d.y);
+          }
         }
         if (row_ok) {
           if (p.residual != nullptr) {
@@ -277,8 +304,18 @@ int dispatch_major(int a_mn, int b_mn, const void* A, const void* B, const GemmP
 
 }  // namespace
 
+int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                  int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
+                  cudaStream_t stream);
+
 int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
               int K, const float* bias, const void* residual, int ldres, int flags, cudaStream_t stream) {
+  return gemm_bf16_aux(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, bias, residual, ldres, nullptr, 0, flags, stream);
+}
+
+int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                  int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
+                  cudaStream_t stream) {
   MEBT_REQUIRE(M > 0 && N > 0 && K > 0, MEBT_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   MEBT_REQUIRE(N % 64 == 0, MEBT_ERR_SHAPE, "gemm: N=%d must be a multiple of 64", N);
   MEBT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, MEBT_ERR_SHAPE, "gemm: lda/ldb must be multiples of 8 elements");
@@ -296,6 +333,11 @@ int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn
   p.gelu = (flags & MEBT_GEMM_GELU) ? 1 : 0;
   p.out_fp32 = out_fp32 ? 1 : 0;
   p.accumulate = (flags & MEBT_GEMM_ACCUMULATE) ? 1 : 0;
+  p.aux = static_cast<__nv_bfloat16*>(aux);
+  p.ldaux = ldaux;
+  p.dgelu = (flags & MEBT_GEMM_DGELU) ? 1 : 0;
+  MEBT_REQUIRE(!p.dgelu || (aux != nullptr && !p.gelu), MEBT_ERR_SHAPE, "gemm: DGELU needs the pre-activation in aux");
+  MEBT_REQUIRE(aux == nullptr || ldaux % 8 == 0, MEBT_ERR_SHAPE, "gemm: ldaux must be a multiple of 8");
   p.num_m_blocks = (M + BM - 1) / BM;
   p.num_k_blocks = (K + BK - 1) / BK;
   // Tile-width choice: the widest BN that still yields at least ~one wave of tiles.
@@ -314,6 +356,13 @@ int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn
 }
 
 }  // namespace mebt
+
+extern "C" int mebt_gemm_bf16_aux(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
+                                  void* C, int ldc, int M, int N, int K, const float* bias, const void* residual,
+                                  int ldres, void* aux, int ldaux, int flags, void* stream) {
+  return mebt::gemm_bf16_aux(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, bias, residual, ldres, aux, ldaux,
+                             flags, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int mebt_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C,
                               int ldc, int M, int N, int K, const float* bias, const void* residual, int ldres,

@@ -244,3 +244,92 @@ def cast_bf16(x):
 
 def check_index_errors():
     call("mebt_check_index_errors", _stream())
+
+
+# ---- backward ops (training step) --------------------------------------------------------------------------------
+GEMM_DGELU = 8
+_ws_cache: dict = {}
+
+
+def _ws(device, nbytes: int, tag: str = "ws") -> torch.Tensor:
+    key = (device, tag)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+        _ws_cache[key] = t
+    return t
+
+
+def gemm_aux(a, b, aux, bias=None, residual=None, gelu=False, dgelu=False, out=None, a_mn_major=False,
+             b_mn_major=False):
+    """gemm with the auxiliary pre-activation tensor: gelu=True stores it, dgelu=True multiplies by gelu'(aux)."""
+    _need_cuda(a, b, aux)
+    ar, ac, lda = _rows2d(a)
+    br, bc, ldb = _rows2d(b)
+    M, K = (ac, ar) if a_mn_major else (ar, ac)
+    N = bc if b_mn_major else br
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    flags = (GEMM_GELU if gelu else 0) | (GEMM_DGELU if dgelu else 0) | (GEMM_OUT_FP32 if out.dtype == torch.float32 else 0)
+    call("mebt_gemm_bf16_aux", a.data_ptr(), lda, int(a_mn_major), b.data_ptr(), ldb, int(b_mn_major), out.data_ptr(),
+         out.stride(0), M, N, K, _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0,
+         aux.data_ptr(), aux.stride(0), flags, _stream())
+    return out
+
+
+def colsum(x, out=None, accumulate=False):
+    """out[n] (+)= sum_rows x[:, n]; x bf16 [rows, N]."""
+    _need_cuda(x)
+    rows, N, ld = _rows2d(x)
+    if out is None:
+        out = torch.zeros(N, device=x.device, dtype=torch.float32)
+        accumulate = False
+    nbytes = _lib.lib.mebt_colsum_workspace_bytes(N)
+    ws = _ws(x.device, nbytes)
+    call("mebt_colsum", x.data_ptr(), ld, rows, N, out.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx=None, accumulate_dx=False, dgamma=None, dbeta=None,
+                  accumulate_params=False):
+    _need_cuda(dy, x)
+    rows, D = x.shape
+    if dx is None:
+        dx = torch.empty_like(x)
+        accumulate_dx = False
+    if dgamma is None:
+        dgamma = torch.empty(D, device=x.device, dtype=torch.float32)
+        dbeta = torch.empty(D, device=x.device, dtype=torch.float32)
+        accumulate_params = False
+    nbytes = _lib.lib.mebt_layernorm_bwd_workspace_bytes(D)
+    ws = _ws(x.device, nbytes)
+    call("mebt_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+         dx.data_ptr(), int(accumulate_dx), dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate_params), rows, D,
+         ws.data_ptr(), ws.numel(), _stream())
+    return dx, dgamma, dbeta
+
+
+def embed_backward(x_indices, ctx_idx, tgt_idx, d_ctx, d_tgt, d_lat, d_tok, d_pos, d_mask, d_sos):
+    """Accumulates into the fp32 gradients of tok_emb / pos_emb / mask_emb / sos_emb."""
+    B = x_indices.shape[0]
+    NC, NT = ctx_idx.shape[1], tgt_idx.shape[1]
+    D = d_tok.shape[-1]
+    L = d_lat.shape[0] // B
+    ws = _ws(x_indices.device, _lib.lib.mebt_colsum_workspace_bytes(D))
+    call("mebt_embed_backward", x_indices.data_ptr(), x_indices.stride(0), ctx_idx.data_ptr(),
+         ctx_idx.stride(0) if NC else 0, tgt_idx.data_ptr(), tgt_idx.stride(0) if NT else 0, d_ctx.data_ptr(),
+         d_tgt.data_ptr(), d_lat.data_ptr(), d_tok.data_ptr(), d_pos.data_ptr(), d_mask.data_ptr(), d_sos.data_ptr(), B,
+         NC, NT, L, D, ws.data_ptr(), ws.numel(), _stream())
+
+
+def attention_bwd(q, q_col0, kv1, k1_col0, v1_col0, nk1, kv2, k2_col0, v2_col0, nk2, o, do, lse, dq, dq_col0, dkv1,
+                  dk1_col0, dv1_col0, dkv2, dk2_col0, dv2_col0, B, H, NQ):
+    nbytes = _lib.lib.mebt_latent_attention_bwd_workspace_bytes(B, H, NQ)
+    ws = _ws(q.device, nbytes, "attn")
+    call("mebt_latent_attention_bwd", q.data_ptr(), q.stride(0), q_col0,
+         _ptr(kv1) if nk1 else None, kv1.stride(0) if nk1 else 0, k1_col0, v1_col0, nk1,
+         _ptr(kv2) if nk2 else None, kv2.stride(0) if nk2 else 0, k2_col0, v2_col0, nk2,
+         o.data_ptr(), o.stride(0), do.data_ptr(), do.stride(0), lse.data_ptr(), dq.data_ptr(), dq.stride(0), dq_col0,
+         _ptr(dkv1) if nk1 else None, dkv1.stride(0) if nk1 else 0, dk1_col0, dv1_col0,
+         _ptr(dkv2) if nk2 else None, dkv2.stride(0) if nk2 else 0, dk2_col0, dv2_col0, B, H, NQ, 64, ws.data_ptr(),
+         ws.numel(), _stream())

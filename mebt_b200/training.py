@@ -1,0 +1,224 @@
+"""Training step of the MeBT stack on the mebt_b200 kernels (BASELINE.json configs[1]).
+
+Step = stem gather -> stack forward (activations saved) -> fused masked-CE (loss, top-1/5, dlogits in one pass) ->
+stack backward (dgrad / wgrad through the MN-major tcgen05 GEMM modes, attention backward, LayerNorm backward) ->
+stem scatter-add -> gradient all-reduce (NCCL, launched per finished chunk of blocks so it overlaps the rest of
+backward) -> AdamW -> bf16 operand refresh.  This is what `training_step` + `loss.backward()` + DDP + `optimizer.step()`
+do in the reference (mebt/transformer.py:717-739, train_transformer.py:39-41).
+
+`TrainState` re-homes every parameter of a `Net2NetTransformer` into ONE flat fp32 buffer (the `nn.Parameter`
+objects stay, their `.data` become views), so that
+  * query|key|value weights of a block are adjacent and form the fused [3D, D] operand without a copy,
+  * the bf16 tensor-core operands are one cast kernel over the whole buffer,
+  * gradients live in one flat fp32 buffer whose contiguous per-block slices are the all-reduce buckets.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import MebtError, call
+from .stack import MODE_IDS
+
+_BLOCK_ORDER = ("ln1.weight", "ln1.bias", "ln2.weight", "ln2.bias", "attn.query.weight", "attn.key.weight",
+                "attn.value.weight", "attn.query.bias", "attn.key.bias", "attn.value.bias", "attn.proj.weight",
+                "attn.proj.bias", "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias")
+_FIELD_OF = {"ln1.weight": "ln1_w", "ln1.bias": "ln1_b", "ln2.weight": "ln2_w", "ln2.bias": "ln2_b",
+             "attn.query.weight": "w_qkv", "attn.query.bias": "b_qkv", "attn.proj.weight": "w_proj",
+             "attn.proj.bias": "b_proj", "mlp.0.weight": "w_fc1", "mlp.0.bias": "b_fc1", "mlp.2.weight": "w_fc2",
+             "mlp.2.bias": "b_fc2"}
+_BF16_FIELDS = ("w_qkv", "w_proj", "w_fc1", "w_fc2")
+
+
+class TrainState:
+    def __init__(self, model, n_buckets: int = 4):
+        p0 = next(model.parameters())
+        if not p0.is_cuda:
+            raise MebtError("TrainState needs the model on a CUDA device (no CPU fallback)")
+        self.model = model
+        self.device = p0.device
+        gpt = model.transformer
+        self.modes = [b.mode for b in gpt.blocks]
+        for m in self.modes:
+            if m not in ("latent_enc", "latent_self", "latent_dec", "lt2l"):
+                raise NotImplementedError(f"training supports the four latent block modes, not {m!r}")
+        cfg = gpt.config
+        for name in ("embd_pdrop", "resid_pdrop", "attn_pdrop"):
+            if getattr(cfg, name, 0.0) > 0:
+                raise NotImplementedError("mebt_b200 training path: dropout > 0 is not implemented (use p = 0)")
+        self.D, self.H, self.V = cfg.n_embd, cfg.n_head, gpt.head.weight.shape[0]
+        self.L = model.sos_emb.shape[1]
+        named = dict(model.named_parameters())
+        order = []
+        self.block_slices = []
+        for i in range(len(self.modes)):
+            start = sum(named[n].numel() for n in order)
+            order += [f"transformer.blocks.{i}.{s}" for s in _BLOCK_ORDER]
+            self.block_slices.append((start, sum(named[n].numel() for n in order)))
+        order += ["transformer.ln_f.weight", "transformer.ln_f.bias", "transformer.head.weight", "mask_emb", "sos_emb",
+                  "pos_emb", "tok_emb.weight"]
+        assert set(order) == set(named), set(named) ^ set(order)
+        total = sum(named[n].numel() for n in order)
+        self.flat = torch.empty(total, device=self.device, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=self.device, dtype=torch.float32)
+        self.flat_bf16 = torch.empty(total, device=self.device, dtype=torch.bfloat16)
+        self.offsets = {}
+        off = 0
+        for n in order:
+            p = named[n]
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.flat_grad[off:off + k].view(p.shape)
+            self.offsets[n] = (off, k)
+            off += k
+        self.order = order
+        self.head_slice = (self.block_slices[-1][1], self.offsets["mask_emb"][0])       # ln_f + head
+        self.emb_slice = (self.offsets["mask_emb"][0], total)
+        # all-reduce buckets: contiguous groups of blocks, in the order backward finishes them (last block first)
+        n_layers = len(self.modes)
+        n_buckets = max(1, min(n_buckets, n_layers))
+        edges = [round(i * n_layers / n_buckets) for i in range(n_buckets + 1)]
+        self.chunks = [(edges[i], edges[i + 1]) for i in range(n_buckets)]
+        self._build_structs()
+        self.refresh_operands()
+        self._saved = None
+        self._bwd_ws = None
+        self.comm_stream = torch.cuda.Stream(device=self.device)
+
+    # ---- pointer tables for the C engine ---------------------------------------------------------------------------
+    def _view(self, buf, name):
+        off, k = self.offsets[name]
+        return buf[off:off + k]
+
+    def _build_structs(self):
+        n = len(self.modes)
+        self.c_layers = (_lib.LayerStruct * n)()
+        self.c_grads = (_lib.LayerGradsStruct * n)()
+        for i, mode in enumerate(self.modes):
+            self.c_layers[i].mode = MODE_IDS[mode]
+            for suffix, field in _FIELD_OF.items():
+                name = f"transformer.blocks.{i}.{suffix}"
+                src = self.flat_bf16 if field in _BF16_FIELDS else self.flat
+                setattr(self.c_layers[i], field, self._view(src, name).data_ptr())
+                setattr(self.c_grads[i], field, self._view(self.flat_grad, name).data_ptr())
+
+    def refresh_operands(self):
+        """fp32 masters -> bf16 tensor-core operands, one kernel over the flat buffer (after every optimizer step)."""
+        call("mebt_cast_f32_to_bf16", self.flat.data_ptr(), self.flat_bf16.data_ptr(), self.flat.numel() // 4 * 4,
+             torch.cuda.current_stream().cuda_stream)
+
+    # ---- one step ---------------------------------------------------------------------------------------------------
+    def _buffers(self, B, NC, NT):
+        saved_bytes = _lib.lib.mebt_stack_train_saved_bytes(self.c_layers, len(self.modes), B, self.L, NC, NT, self.D, self.H)
+        if self._saved is None or self._saved.numel() < saved_bytes:
+            self._saved = torch.empty(int(saved_bytes * 1.1), dtype=torch.uint8, device=self.device)
+        ws_bytes = _lib.lib.mebt_stack_backward_workspace_bytes(B, self.L, NC, NT, self.D, self.H)
+        if self._bwd_ws is None or self._bwd_ws.numel() < ws_bytes:
+            self._bwd_ws = torch.empty(int(ws_bytes * 1.1), dtype=torch.uint8, device=self.device)
+        return self._saved, self._bwd_ws
+
+    def forward(self, x_indices, ctx_idx, tgt_idx, logits_dtype=torch.bfloat16):
+        """Stem + stack forward keeping activations.  -> logits [B*NT, V]."""
+        m = self.model
+        B = x_indices.shape[0]
+        NC, NT = ctx_idx.shape[1], tgt_idx.shape[1]
+        saved, _ = self._buffers(B, NC, NT)
+        ctx, tgt, lat = ops.embed_gather(x_indices, ctx_idx, tgt_idx, m.tok_emb.weight, m.pos_emb, m.mask_emb, m.sos_emb)
+        logits = torch.empty(B * NT, self.V, device=self.device, dtype=logits_dtype)
+        st = torch.cuda.current_stream().cuda_stream
+        call("mebt_stack_forward_train", self.c_layers, len(self.modes), self._view(self.flat, "transformer.ln_f.weight").data_ptr(),
+             self._view(self.flat, "transformer.ln_f.bias").data_ptr(),
+             self._view(self.flat_bf16, "transformer.head.weight").data_ptr(), B, self.L, NC, NT, self.D, self.H, self.V,
+             lat.data_ptr(), ctx.data_ptr(), tgt.data_ptr(), logits.data_ptr(), ops._DT[logits_dtype], saved.data_ptr(),
+             saved.numel(), st)
+        self._ctx = (B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt)
+        return logits
+
+    def backward(self, dlogits, accumulate=False, world_size=1):
+        """Stack + stem backward into the flat gradient buffer; with world_size > 1 each finished chunk of blocks is
+        all-reduced (averaged) on a side stream while the next chunk runs."""
+        B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt = self._ctx
+        if dlogits.dtype != torch.bfloat16 or not dlogits.is_contiguous():
+            raise MebtError("dlogits must be contiguous bf16 [B*NT, V]")
+        m = self.model
+        saved, ws = self._buffers(B, NC, NT)
+        dev = self.device
+        d_lat = torch.empty(B * self.L, self.D, device=dev, dtype=torch.bfloat16)
+        d_ctx = torch.empty(B * NC, self.D, device=dev, dtype=torch.bfloat16)
+        d_tgt = torch.empty(B * NT, self.D, device=dev, dtype=torch.bfloat16)
+        cur = torch.cuda.current_stream()
+        n = len(self.modes)
+        if not accumulate:
+            lo, hi = self.emb_slice
+            self.flat_grad[lo:hi].zero_()                       # embedding gradients are scatter-added
+        works = []
+        for ci in range(len(self.chunks) - 1, -1, -1):
+            lb, le = self.chunks[ci]
+            call("mebt_stack_backward", self.c_layers, self.c_grads, n,
+                 self._view(self.flat, "transformer.ln_f.weight").data_ptr(),
+                 self._view(self.flat_grad, "transformer.ln_f.weight").data_ptr(),
+                 self._view(self.flat_grad, "transformer.ln_f.bias").data_ptr(),
+                 self._view(self.flat_bf16, "transformer.head.weight").data_ptr(),
+                 self._view(self.flat_grad, "transformer.head.weight").data_ptr(), B, self.L, NC, NT, self.D, self.H, self.V,
+                 lat.data_ptr(), ctx.data_ptr(), tgt.data_ptr(), dlogits.data_ptr(), saved.data_ptr(), saved.numel(),
+                 d_lat.data_ptr(), d_ctx.data_ptr(), d_tgt.data_ptr(), lb, le, int(accumulate), ws.data_ptr(), ws.numel(),
+                 cur.cuda_stream)
+            if world_size > 1:
+                lo, hi = self.block_slices[lb][0], self.block_slices[le - 1][1]
+                works.append(self._all_reduce_async(lo, hi, cur))
+                if le == n:
+                    works.append(self._all_reduce_async(*self.head_slice, cur))
+        g = lambda name: self._view(self.flat_grad, name)
+        ops.embed_backward(x_indices, ctx_idx, tgt_idx, d_ctx, d_tgt, d_lat, g("tok_emb.weight").view(-1, self.D),
+                           g("pos_emb").view(-1, self.D), g("mask_emb"), g("sos_emb").view(-1, self.D))
+        if world_size > 1:
+            works.append(self._all_reduce_async(*self.emb_slice, cur))
+            cur.wait_stream(self.comm_stream)
+        return works
+
+    def _all_reduce_async(self, lo, hi, producer_stream):
+        import torch.distributed as dist
+        self.comm_stream.wait_stream(producer_stream)
+        with torch.cuda.stream(self.comm_stream):
+            return dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, async_op=True)
+
+    def loss_and_backward(self, x_indices, indices, t=None, world_size=1):
+        """shared_step + backward fused: -> dict(loss, acc1, acc5, ratio) as device tensors / floats.
+        loss = CE_sum / (B * seq_len * ratio**avg_loss) (mebt/transformer.py:723-730)."""
+        m = self.model
+        B = x_indices.shape[0]
+        x_indices = x_indices.reshape(B, -1)
+        import random
+        if t is None:
+            t = torch.tensor(random.random())
+            t = m.range[0] + t * (m.range[1] - m.range[0])
+        else:
+            t = torch.tensor(t)
+        prior_t = m.t_prior(m.t_lengths, m.global_step)
+        ctx_idx, tgt_idx, seq_len = m.mask_sampler.divide_indices(indices, t, m.t_lengths, prior_t)
+        z_targets = torch.gather(x_indices, 1, tgt_idx)
+        NC, NT = ctx_idx.shape[1], tgt_idx.shape[1]
+        ratio = float(seq_len - NC) / float(seq_len)
+        scale = 1.0 / (B * seq_len * ratio ** m.config.avg_loss)
+        logits = self.forward(x_indices, ctx_idx, tgt_idx)
+        stats, _ = ops.masked_ce(logits, z_targets.reshape(-1), m.label_smoothing, dlogits=logits, grad_scale=scale)
+        self.backward(logits, world_size=world_size)
+        n = float(B * NT)
+        return dict(loss=stats[0] * scale, acc1=stats[1] * (100.0 / n), acc5=stats[2] * (100.0 / n), ratio=ratio)
+
+    def make_optimizer(self, lr=1.08e-5, weight_decay=0.01):
+        self.model.learning_rate, self.model.weight_decay = lr, weight_decay
+        ref = self.model.configure_optimizers()                  # the reference's four groups (transformer.py:790-797)
+        groups = [{"params": g["params"], "weight_decay": g["weight_decay"]} for g in ref.param_groups]
+        return torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.95), fused=True)
+
+    def train_step(self, optimizer, x_indices, indices, t=None, world_size=1):
+        """fwd + loss + bwd (+ all-reduce) + AdamW + operand refresh.  Returns the loss statistics."""
+        out = self.loss_and_backward(x_indices, indices, t, world_size)
+        optimizer.step()
+        self.refresh_operands()
+        return out
