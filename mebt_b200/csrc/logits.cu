@@ -412,6 +412,131 @@ __global__ void __launch_bounds__(LT) sample_logits_kernel(const T* __restrict__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K6 fast path, streaming form: same inverse-CDF draw as sample_logits_kernel<T,false> but the row is NOT held
+// in registers.  Pass 1 (HBM) computes the online-softmax statistics, pass 2 re-reads the 64 KiB row (an L2 hit)
+// to build the 128 cell sums, and the selected warp re-reads one 16-byte vector.  ~40 registers per thread ->
+// 8 CTAs per SM, which is what lets a one-pass, latency-bound reader approach the HBM roof.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LT, 8) sample_stream_kernel(const T* __restrict__ logits, long long ld, int V,
+                                                              float inv_temp, unsigned long long seed,
+                                                              unsigned long long offset, int64_t* __restrict__ ids,
+                                                              float* __restrict__ scores) {
+  __shared__ float red_m[LT / 32], red_s[LT / 32];
+  __shared__ __align__(16) float wsum[MAX_V4][LT / 32];
+  __shared__ int sel_cell;
+  __shared__ float sel_resid;
+  const long long row = blockIdx.x;
+  const T* xr = logits + row * ld;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  auto scaled = [&](float4 t) {
+    t.x *= inv_temp; t.y *= inv_temp; t.z *= inv_temp; t.w *= inv_temp;
+    if (t.x != t.x) t.x = -INFINITY;
+    if (t.y != t.y) t.y = -INFINITY;
+    if (t.z != t.z) t.z = -INFINITY;
+    if (t.w != t.w) t.w = -INFINITY;
+    return t;
+  };
+  float m = -INFINITY, ssum = 0.f;
+  for (int c = threadIdx.x * 4; c < V; c += LT * 4) {
+    const float4 t = scaled(load4<T>(xr + c));
+    const float m4 = fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w));
+    const float mn = fmaxf(m, m4);
+    if (mn > -INFINITY) {
+      ssum = ssum * __expf(m - mn) + (__expf(t.x - mn) + __expf(t.y - mn)) + (__expf(t.z - mn) + __expf(t.w - mn));
+      m = mn;
+    }
+  }
+  // block combine of (m, s)
+  float wm = warp_max(m);
+  float ws = warp_sum(m > -INFINITY ? ssum * __expf(m - wm) : 0.f);
+  if (lane == 0) { red_m[wid] = wm; red_s[wid] = ws; }
+  for (int i = threadIdx.x; i < MAX_V4 * (LT / 32); i += LT) (&wsum[0][0])[i] = 0.f;
+  __syncthreads();
+  float M = red_m[0];
+#pragma unroll
+  for (int w = 1; w < LT / 32; ++w) M = fmaxf(M, red_m[w]);
+  float S = 0.f;
+#pragma unroll
+  for (int w = 0; w < LT / 32; ++w) S += red_m[w] > -INFINITY ? red_s[w] * __expf(red_m[w] - M) : 0.f;
+  // pass 2: cell sums in vocabulary order (cell = 128 consecutive logits = one warp's float4s of one 1024-chunk)
+  for (int c = threadIdx.x * 4, i = 0; c < V; c += LT * 4, ++i) {
+    const float4 t = scaled(load4<T>(xr + c));
+    const float e4 = (__expf(t.x - M) + __expf(t.y - M)) + (__expf(t.z - M) + __expf(t.w - M));
+    const float cs = warp_sum(e4);
+    if (lane == 0) wsum[i][wid] = cs;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    const uint4 r = philox4x32(make_uint4(uint32_t(row), uint32_t(row >> 32), uint32_t(offset), uint32_t(offset >> 32)),
+                               make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+    const float u = (float(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float4 part = *reinterpret_cast<const float4*>(&wsum[0][0] + lane * 4);
+    const float own4 = (part.x + part.y) + (part.z + part.w);
+    float inc = own4;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const float target = u * __shfl_sync(0xffffffffu, inc, 31);
+    const unsigned hit = __ballot_sync(0xffffffffu, own4 > 0.f && inc >= target);
+    const unsigned any = __ballot_sync(0xffffffffu, own4 > 0.f);
+    const int sl = hit ? (__ffs(hit) - 1) : (any ? 31 - __clz(any) : 0);
+    if (lane == sl) {
+      const float rr = hit ? target - (inc - own4) : INFINITY;
+      const float e[4] = {part.x, part.y, part.z, part.w};
+      int j_sel = -1, j_last = 0;
+      float cum = 0.f, before = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (e[j] > 0.f) { j_last = j; if (j_sel < 0 && cum + e[j] >= rr) { j_sel = j; before = cum; } }
+        cum += e[j];
+      }
+      if (j_sel < 0) { j_sel = j_last; before = -INFINITY; }
+      sel_cell = lane * 4 + j_sel;
+      sel_resid = rr - before;
+    }
+  }
+  __syncthreads();
+  const int ci = sel_cell / (LT / 32), wi = sel_cell % (LT / 32);
+  if (wid == wi) {
+    const int c = (threadIdx.x + LT * ci) * 4;
+    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < V) {
+      const float4 t = scaled(load4<T>(xr + c));
+      mine = make_float4(__expf(t.x - M), __expf(t.y - M), __expf(t.z - M), __expf(t.w - M));
+    }
+    const float my_own = (mine.x + mine.y) + (mine.z + mine.w);
+    float my_incl = my_own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, my_incl, o);
+      if (lane >= o) my_incl += t;
+    }
+    const float resid = sel_resid;
+    const unsigned hit = __ballot_sync(0xffffffffu, my_own > 0.f && my_incl >= resid);
+    const unsigned any = __ballot_sync(0xffffffffu, my_own > 0.f);
+    const int sel = hit ? (__ffs(hit) - 1) : (any ? 31 - __clz(any) : 0);
+    if (lane == sel) {
+      const float rr = resid - (my_incl - my_own);
+      const float e[4] = {mine.x, mine.y, mine.z, mine.w};
+      int j_sel = -1, j_last = 0;
+      float cum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cum += e[j];
+        if (e[j] > 0.f) { j_last = j; if (j_sel < 0 && cum >= rr) j_sel = j; }
+      }
+      if (j_sel < 0) j_sel = j_last;
+      ids[row] = c + j_sel;
+      if (scores != nullptr) scores[row] = e[j_sel] / S;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace mebt
 
@@ -464,6 +589,20 @@ int mebt_sample_logits(const void* logits, long long ld, int dtype, int rows, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const double eb = dtype == MEBT_DTYPE_FP32 ? 4.0 : 2.0;
   LaunchScope ls(FAM_SAMPLE, double(rows) * (double(V) * (eb + (noise != nullptr ? 4.0 : 0.0) + (probs != nullptr ? 4.0 : 0.0)) + 12.0), st);
+  if (noise == nullptr && top_k <= 0 && probs == nullptr && V % 128 == 0) {
+    // fast mode without filters: streaming inverse-CDF kernel (multiplies by 1/(T + 1e-8) instead of dividing)
+    const float inv_temp = float(1.0 / (double(temperature) + 1e-8));
+    if (dtype == MEBT_DTYPE_FP32)
+      sample_stream_kernel<float><<<rows, LT, 0, st>>>(static_cast<const float*>(logits), ld, V, inv_temp, seed, offset,
+                                                       ids, scores);
+    else if (dtype == MEBT_DTYPE_BF16)
+      sample_stream_kernel<__nv_bfloat16><<<rows, LT, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, V, inv_temp,
+                                                               seed, offset, ids, scores);
+    else
+      MEBT_REQUIRE(false, MEBT_ERR_DTYPE, "sample_logits: unsupported dtype %d", dtype);
+    MEBT_LAUNCH_OK("sample_stream_kernel");
+    return MEBT_OK;
+  }
   if (dtype == MEBT_DTYPE_FP32)
     (noise != nullptr ? sample_logits_kernel<float, true> : sample_logits_kernel<float, false>)<<<rows, LT, 0, st>>>(
         static_cast<const float*>(logits), ld, V, temp_div, top_k, noise, seed, offset, ids, scores, probs);

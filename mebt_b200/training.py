@@ -19,7 +19,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, parallel
 from ._lib import MebtError, call
 from .stack import MODE_IDS
 
@@ -181,10 +181,11 @@ class TrainState:
         return works
 
     def _all_reduce_async(self, lo, hi, producer_stream):
-        import torch.distributed as dist
+        """One gradient bucket: waits for the kernels that produced it, then averages it over ranks on the side
+        stream so that it overlaps the rest of backward (the reference's DDP bucket all-reduce)."""
         self.comm_stream.wait_stream(producer_stream)
         with torch.cuda.stream(self.comm_stream):
-            return dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.AVG, async_op=True)
+            return parallel.allreduce_mean_(self.flat_grad[lo:hi], async_op=True)
 
     def loss_and_backward(self, x_indices, indices, t=None, world_size=1):
         """shared_step + backward fused: -> dict(loss, acc1, acc5, ratio) as device tensors / floats.

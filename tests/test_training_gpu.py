@@ -37,6 +37,9 @@ def test_gradients_vs_reference_fixture(name):
             assert float(g.abs().max()) == 0.0, n
             continue
         got = float(g.norm())
+        if ref_norm < 1e-7:            # mathematically zero (e.g. key bias: softmax is shift-invariant), fp noise only
+            assert got < 1e-6, (n, got)
+            continue
         rel = abs(got - ref_norm) / (ref_norm + 1e-12)
         worst = max(worst, rel)
         assert rel < 5e-2, (n, got, float(ref_norm))
@@ -45,6 +48,8 @@ def test_gradients_vs_reference_fixture(name):
             n = key[2:]
             ref = torch.from_numpy(z[key])
             got = grads[n].reshape(-1)[::17].cpu()
+            if float(ref.norm()) < 1e-7:
+                continue
             cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
             err = ((got - ref).norm() / (ref.norm() + 1e-12)).item()
             assert cos > 0.998 and err < 6e-2, (n, cos, err)
@@ -67,6 +72,9 @@ def test_gradients_vs_oracle_autograd_nc0():
             continue
         if float(ref.abs().max()) == 0.0:
             assert float(p.grad.abs().max()) == 0.0, n          # exact zeros stay exact zeros
+            continue
+        if float(ref.norm()) < 1e-7:                             # key bias: zero up to rounding noise
+            assert float(p.grad.norm()) < 1e-6, n
             continue
         err = ((p.grad.cpu() - ref).norm() / ref.norm()).item()
         assert err < 6e-2, (n, err)
