@@ -57,7 +57,8 @@ enum {
   MEBT_GEMM_DGELU = 8,        /* result *= gelu'(aux): the backward of the fused fc1+GELU epilogue */
   MEBT_GEMM_FORCE_BN256 = 16, /* tile-width overrides, for tests and tuning */
   MEBT_GEMM_FORCE_BN128 = 32,
-  MEBT_GEMM_FORCE_BN64 = 64
+  MEBT_GEMM_FORCE_BN64 = 64,
+  MEBT_GEMM_NO_SPLITK = 128   /* never split the reduction across CTAs */
 };
 /*
  * C[M,N] = act( A * B^T + bias ) + residual, tcgen05/TMEM/TMA.

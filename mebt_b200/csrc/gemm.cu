@@ -40,6 +40,13 @@ struct GemmParams {
   __nv_bfloat16* aux;                  // gelu: optional pre-activation output; dgelu: pre-activation input
   int ldaux;
   int dgelu;                           // result *= gelu'(aux)
+  // split-K: `splits` CTAs share one output tile; each writes its fp32 partial accumulator to `partials`
+  // ([tile][split][128][BN]) and the last one to arrive (per-tile counter) sums them in split order and runs the
+  // epilogue.  Deterministic: the summation order does not depend on arrival order.
+  int splits;
+  int kb_per_split;
+  float* partials;
+  int* counters;
 };
 
 template <int BN, int STAGES>
@@ -65,7 +72,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_work = p.num_m_blocks * p.num_n_blocks * p.splits;
+  int* split_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);
   constexpr uint32_t TMEM_COLS = 2 * BN;   // 128, 256 or 512 (power of two >= 32)
 
   if (threadIdx.x == 0) {
@@ -95,10 +103,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int tile = work / p.splits, split = work % p.splits;
         const int m0 = (tile % p.num_m_blocks) * BM;
         const int n0 = (tile / p.num_m_blocks) * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * L::STAGE_BYTES;
           uint8_t* sB = sA + A_TILE_BYTES;
@@ -128,13 +139,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const int split = work % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
@@ -147,10 +161,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                                      : make_smem_desc_sw128(sA + k * (UMMA_K * 2), 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(sB + k * (UMMA_K * 128), BK * 128, 1024)
                                      : make_smem_desc_sw128(sB + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
-          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -159,24 +173,68 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ================= epilogue (warps 2..5) =================
     const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int tile = work / p.splits, split = work % p.splits;
       const int m0 = (tile % p.num_m_blocks) * BM;
       const int n0 = (tile / p.num_m_blocks) * BN;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
+      const float* my_partials = nullptr;
+      if (p.splits > 1) {
+        // park the raw accumulator, release TMEM, and find out whether this CTA completes the tile
+        float* part = p.partials + ((size_t(tile) * p.splits + split) * BM + size_t(q * 32 + lane)) * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), r);
+          tmem_ld_wait();
+          float4* o4 = reinterpret_cast<float4*>(part + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(o4 + j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {                               // first epilogue thread
+          const int old = atomicAdd(p.counters + tile, 1);
+          const int last = old == p.splits - 1;
+          if (last) p.counters[tile] = 0;                      // ready for the next launch
+          *split_flag = last;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*split_flag == 0) continue;
+        __threadfence();
+        my_partials = p.partials + (size_t(tile) * p.splits * BM + size_t(q * 32 + lane)) * BN;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), r);
-        tmem_ld_wait();
         const int col = n0 + c * 32;
         float v[32];
+        if (my_partials == nullptr) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          for (int sp = 0; sp < p.splits; ++sp) {              // fixed order: bitwise reproducible
+            const float4* i4 = reinterpret_cast<const float4*>(my_partials + size_t(sp) * BM * BN + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldcg(i4 + j);
+              v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+          }
+        }
         if (p.bias != nullptr) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
@@ -252,8 +310,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      if (p.splits == 1) {
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+      }
     }
   }
 
@@ -283,7 +343,7 @@ int launch_gemm(const void* A, const void* B, const GemmParams& p, int lda, int 
     MEBT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   {
     LaunchScope ls(FAM_GEMM, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
@@ -307,6 +367,24 @@ int dispatch_major(int a_mn, int b_mn, const void* A, const void* B, const GemmP
 int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
                   int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
                   cudaStream_t stream);
+
+// Split-K scratch: the only device memory the library owns (partials are consumed inside the launch that wrote
+// them; the per-tile counters are returned to zero by the CTA that completes the tile).  Launches that use it are
+// ordered by the caller's stream, like every other launch; it is sized once for the largest split-K problem seen.
+struct SplitKWorkspace { float* partials; int* counters; size_t bytes; int n_counters; };
+static SplitKWorkspace* splitk_workspace(size_t need_bytes, int tiles) {
+  static SplitKWorkspace ws = {nullptr, nullptr, 0, 0};
+  constexpr size_t kMax = size_t(96) << 20;
+  if (need_bytes > kMax || tiles > 4096) return nullptr;
+  if (ws.partials == nullptr) {
+    if (cudaMalloc(&ws.partials, kMax) != cudaSuccess) { ws.partials = nullptr; return nullptr; }
+    if (cudaMalloc(&ws.counters, 4096 * sizeof(int)) != cudaSuccess) { ws.counters = nullptr; return nullptr; }
+    cudaMemset(ws.counters, 0, 4096 * sizeof(int));
+    ws.bytes = kMax;
+    ws.n_counters = 4096;
+  }
+  return &ws;
+}
 
 int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
               int K, const float* bias, const void* residual, int ldres, int flags, cudaStream_t stream) {
@@ -340,14 +418,35 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
   MEBT_REQUIRE(aux == nullptr || ldaux % 8 == 0, MEBT_ERR_SHAPE, "gemm: ldaux must be a multiple of 8");
   p.num_m_blocks = (M + BM - 1) / BM;
   p.num_k_blocks = (K + BK - 1) / BK;
-  // Tile-width choice: the widest BN that still yields at least ~one wave of tiles.
-  int bn = 64;
-  if (N % 256 == 0 && int64_t(p.num_m_blocks) * (N / 256) >= sm_count()) bn = 256;
-  else if (N % 128 == 0 && int64_t(p.num_m_blocks) * (N / 128) >= sm_count()) bn = 128;
+  // Tile width: the widest that divides N (measured: BN=256 wins or ties at every shape of the path, because the
+  // per-CTA cost is TMA latency per k-block, not MMA issue).  Problems with fewer tiles than SMs are split along K.
+  int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
   if (flags & MEBT_GEMM_FORCE_BN256) { MEBT_REQUIRE(N % 256 == 0, MEBT_ERR_SHAPE, "BN256 needs N%%256==0"); bn = 256; }
   if (flags & MEBT_GEMM_FORCE_BN128) { MEBT_REQUIRE(N % 128 == 0, MEBT_ERR_SHAPE, "BN128 needs N%%128==0"); bn = 128; }
   if (flags & MEBT_GEMM_FORCE_BN64) bn = 64;
   p.num_n_blocks = N / bn;
+  p.splits = 1;
+  p.kb_per_split = p.num_k_blocks;
+  p.partials = nullptr;
+  p.counters = nullptr;
+  if (!(flags & MEBT_GEMM_NO_SPLITK)) {
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    int want = sm_count() / tiles;                       // CTAs available per tile
+    if (want > p.num_k_blocks / 4) want = p.num_k_blocks / 4;   // keep >= 4 k-blocks (256 of K) per split
+    if (want > 8) want = 8;
+    if (want >= 2) {
+      const int kpb = (p.num_k_blocks + want - 1) / want;
+      const int splits = (p.num_k_blocks + kpb - 1) / kpb;
+      const size_t need = size_t(tiles) * splits * BM * bn * sizeof(float);
+      SplitKWorkspace* ws = splitk_workspace(need, tiles);
+      if (ws != nullptr && splits >= 2) {
+        p.splits = splits;
+        p.kb_per_split = kpb;
+        p.partials = ws->partials;
+        p.counters = ws->counters;
+      }
+    }
+  }
   switch (bn) {
     case 256: return dispatch_major<256>(a_mn, b_mn, A, B, p, lda, ldb, stream);
     case 128: return dispatch_major<128>(a_mn, b_mn, A, B, p, lda, ldb, stream);

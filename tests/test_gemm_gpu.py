@@ -4,7 +4,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-GELU, OUT_FP32, ACC, BN256, BN128, BN64 = 1, 2, 4, 16, 32, 64
+GELU, OUT_FP32, ACC, BN256, BN128, BN64, NO_SPLITK = 1, 2, 4, 16, 32, 64, 128
 
 CASES = [
     # M, N, K, a_mn, b_mn, flags, bias, resid
@@ -27,6 +27,13 @@ CASES = [
     (1024, 1024, 1000, 1, 1, OUT_FP32 | ACC, False, False),  # ragged K + accumulate
     (1536, 1024, 1024, 0, 1, BN256, True, True),
     (1536, 1024, 1024, 1, 0, BN128, True, False),
+    # split-K territory (few tiles, long K) and the same shapes with the split disabled
+    (256, 512, 4096, 0, 0, 0, True, True),
+    (256, 512, 4096, 0, 0, NO_SPLITK, True, True),
+    (1536, 1024, 4096, 0, 0, GELU, True, False),
+    (1536, 1024, 4096, 0, 1, NO_SPLITK, False, False),
+    (100, 256, 1000, 1, 1, OUT_FP32 | ACC, False, False),
+    (1024, 64, 2048, 0, 0, 0, True, False),
 ]
 
 
@@ -47,7 +54,7 @@ def test_gemm(M, N, K, a_mn, b_mn, flags, bias, resid):
         C0 = torch.randn(M, N, device="cuda", generator=g)
         C.copy_(C0)
     ops.gemm(A_st, B_st, bias_t, res_t, gelu=bool(flags & GELU), out=C, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn),
-             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64))
+             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK))
     torch.cuda.synchronize()
     ref = A.float() @ B.float().t()
     if bias:
@@ -62,3 +69,10 @@ def test_gemm(M, N, K, a_mn, b_mn, flags, bias, resid):
     rel = (C.float() - ref).abs().max().item() / (ref.abs().max().item() + 1e-9)
     # bf16 output: half an ulp of bf16 (2^-9) relative to the row scale; fp32 output: accumulation order only
     assert rel < (1e-4 if out_fp32 else 6e-3), rel
+    # bitwise reproducible, split-K included (partials are summed in split order, not arrival order)
+    C2 = torch.full_like(C, float("nan"))
+    if C0 is not None:
+        C2.copy_(C0)
+    ops.gemm(A_st, B_st, bias_t, res_t, gelu=bool(flags & GELU), out=C2, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn),
+             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK))
+    assert torch.equal(C, C2)
