@@ -81,6 +81,7 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0 && nt > 0) {
@@ -292,7 +293,8 @@ extern "C" int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, con
   {
     LaunchScope ls(FAM_ATTENTION, 4.0 * double(B) * H * double(NQ) * double(NK1 + NK2) * AT_HS,
                    static_cast<cudaStream_t>(stream));
-    latent_attention_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(tq, t1, t2, p);
+    MEBT_CUDA_OK(launch_pdl(latent_attention_fwd_kernel, grid, dim3(AT_THREADS), AT_SMEM_TOTAL,
+                            static_cast<cudaStream_t>(stream), tq, t1, t2, p));
   }
   MEBT_LAUNCH_OK("latent_attention_fwd_kernel");
   return MEBT_OK;

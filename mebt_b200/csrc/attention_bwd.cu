@@ -134,6 +134,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -264,6 +265,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0 && nt > 0) {
@@ -412,7 +414,7 @@ int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV
   {
     const int nqt = (NQ + 127) / 128;
     LaunchScope ls(FAM_ATTENTION, 3.0 * flops_tile * double(B) * H * nqt * ((NK1 + 127) / 128 + (NK2 + 127) / 128), st);
-    attn_bwd_dq_kernel<<<dim3(nqt, H, B), AB_THREADS, DQ_SMEM_TOTAL, st>>>(tq, tdo, t1, t2, p);
+    MEBT_CUDA_OK(launch_pdl(attn_bwd_dq_kernel, dim3(nqt, H, B), dim3(AB_THREADS), DQ_SMEM_TOTAL, st, tq, tdo, t1, t2, p));
   }
   MEBT_LAUNCH_OK("attn_bwd_dq_kernel");
   for (int src = 0; src < 2; ++src) {
@@ -429,7 +431,8 @@ int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV
     MEBT_REQUIRE(pk.dKV != nullptr && pk.lddkv % 8 == 0, MEBT_ERR_SHAPE, "attention_bwd: bad dKV%d", src + 1);
     const int nkt = (NK + 127) / 128;
     LaunchScope ls(FAM_ATTENTION, 4.0 * flops_tile * double(B) * H * nkt * ((NQ + 127) / 128), st);
-    attn_bwd_dkv_kernel<<<dim3(nkt, H, B), AB_THREADS, DKV_SMEM_TOTAL, st>>>(tq, tdo, src == 0 ? t1 : t2, pk);
+    MEBT_CUDA_OK(launch_pdl(attn_bwd_dkv_kernel, dim3(nkt, H, B), dim3(AB_THREADS), DKV_SMEM_TOTAL, st, tq, tdo,
+                            src == 0 ? t1 : t2, pk));
     MEBT_LAUNCH_OK("attn_bwd_dkv_kernel");
   }
   return MEBT_OK;

@@ -28,6 +28,7 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ X, int l
                                       int rows_per_slab, float* __restrict__ partial) {
   __shared__ float4 red[8][32];
   const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  griddep_wait();
   const int col = blockIdx.x * 128 + cq * 4;
   const int r0 = blockIdx.y * rows_per_slab;
   const int r1 = min(rows, r0 + rows_per_slab);
@@ -52,6 +53,7 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ X, int l
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int slabs, int N, float* __restrict__ out,
                                        int accumulate) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
   if (n >= N) return;
   float acc = 0.f;
   for (int s = 0; s < slabs; ++s) acc += partial[size_t(s) * N + n];
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                      int rows, int D, float* __restrict__ partial /* [grid, 2, D] */) {
   extern __shared__ float sm[];   // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_wait();
   float4 dg[MAX_VEC], db[MAX_VEC], gm[MAX_VEC];
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i) {
@@ -191,6 +194,7 @@ __global__ void batch_sum_kernel(const __nv_bfloat16* __restrict__ d_lat, int B,
 __global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int grid, int D, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int accumulate) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
   if (idx >= 2 * D) return;
   const int which = idx / D, c = idx % D;
   float acc = 0.f;
@@ -205,6 +209,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, int lddo
   // one warp per (b, q) row; lane pair handles one head (64 dims = 2 lanes x 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
+  griddep_wait();
   if (row >= (long long)B * NQ) return;
   const int b = int(row / NQ), q = int(row % NQ);
   for (int h0 = 0; h0 < H; h0 += 16) {
@@ -238,12 +243,14 @@ int colsum(const void* X, int ld, int rows, int N, float* out, int accumulate, f
   {
     LaunchScope ls(FAM_OTHER, double(rows) * N * 2.0, st);
     dim3 grid((N + 127) / 128, slabs);
-    colsum_partial_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), ld, rows, N, rows_per_slab, workspace);
+    MEBT_CUDA_OK(launch_pdl(colsum_partial_kernel, grid, dim3(256), 0, st, static_cast<const __nv_bfloat16*>(X), ld, rows,
+                            N, rows_per_slab, workspace));
   }
   MEBT_LAUNCH_OK("colsum_partial_kernel");
   {
     LaunchScope ls(FAM_OTHER, double(slabs) * N * 4.0, st);
-    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(workspace, slabs, N, out, accumulate);
+    MEBT_CUDA_OK(launch_pdl(reduce_partials_kernel, dim3((N + 255) / 256), dim3(256), 0, st, workspace, slabs, N, out,
+                            accumulate));
   }
   MEBT_LAUNCH_OK("reduce_partials_kernel");
   return MEBT_OK;
@@ -273,14 +280,15 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
   __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx);
   {
     LaunchScope ls(FAM_LAYERNORM, double(rows) * D * (accumulate_dx ? 8.0 : 6.0), st);
-    if (D <= 256) layernorm_bwd_kernel<2><<<grid, 256, smem, st>>>(dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace);
-    else if (D <= 512) layernorm_bwd_kernel<4><<<grid, 256, smem, st>>>(dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace);
-    else layernorm_bwd_kernel<8><<<grid, 256, smem, st>>>(dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace);
+    if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace));
+    else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<4>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace));
+    else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<8>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace));
   }
   MEBT_LAUNCH_OK("layernorm_bwd_kernel");
   {
     LaunchScope ls(FAM_OTHER, double(grid) * 2 * D * 4.0, st);
-    ln_param_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(workspace, grid, D, dgamma, dbeta, accumulate_params);
+    MEBT_CUDA_OK(launch_pdl(ln_param_reduce_kernel, dim3((2 * D + 255) / 256), dim3(256), 0, st, workspace, grid, D, dgamma,
+                            dbeta, accumulate_params));
   }
   MEBT_LAUNCH_OK("ln_param_reduce_kernel");
   return MEBT_OK;
@@ -317,8 +325,9 @@ int attn_delta(const void* dO, int lddo, const void* O, int ldo, float* delta, i
   const long long rows = (long long)B * NQ;
   if (rows == 0) return MEBT_OK;
   LaunchScope ls(FAM_ATTENTION, 0.0, st);
-  attn_delta_kernel<<<int((rows + 7) / 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dO), lddo,
-                                                         static_cast<const __nv_bfloat16*>(O), ldo, delta, B, H, NQ);
+  MEBT_CUDA_OK(launch_pdl(attn_delta_kernel, dim3(int((rows + 7) / 8)), dim3(256), 0, st,
+                          static_cast<const __nv_bfloat16*>(dO), lddo, static_cast<const __nv_bfloat16*>(O), ldo, delta, B, H,
+                          NQ));
   MEBT_LAUNCH_OK("attn_delta_kernel");
   return MEBT_OK;
 }

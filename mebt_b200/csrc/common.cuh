@@ -61,6 +61,24 @@ struct LaunchScope {
 };
 
 #ifdef __CUDACC__
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining,
+// so its launch latency and prologue (barrier init, TMEM allocation, descriptor prefetch) overlap the predecessor's
+// tail.  Every kernel launched this way calls griddep_wait() before it touches global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------------------------
 // Device helpers
 // ----------------------------------------------------------------------------------------------
@@ -73,6 +91,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// Wait until every grid this launch depends on has completed and its writes are visible, then let the next
+// kernel in the stream start launching (it will block in its own griddep_wait until this grid completes).
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -90,6 +90,7 @@ __global__ void layernorm_kernel(const InT* __restrict__ x, int ldx, const float
                                  float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + warp;
+  griddep_wait();
   if (row >= rows) return;
   const InT* xr = x + row * ldx;
   float4 v[MAX_VEC];
@@ -213,10 +214,10 @@ int launch_ln(const void* x, int ldx, const float* g, const float* b, void* y, i
   LaunchScope ls(FAM_LAYERNORM, double(rows) * D * double(sizeof(InT) + sizeof(OutT)), st);
   const InT* xi = static_cast<const InT*>(x);
   OutT* yo = static_cast<OutT*>(y);
-  if (D <= 256) layernorm_kernel<InT, OutT, 2><<<grid, 256, 0, st>>>(xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd);
-  else if (D <= 512) layernorm_kernel<InT, OutT, 4><<<grid, 256, 0, st>>>(xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd);
-  else if (D <= 1024) layernorm_kernel<InT, OutT, 8><<<grid, 256, 0, st>>>(xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd);
-  else layernorm_kernel<InT, OutT, 16><<<grid, 256, 0, st>>>(xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd);
+  if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_kernel<InT, OutT, 2>, dim3(grid), dim3(256), 0, st, xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd));
+  else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_kernel<InT, OutT, 4>, dim3(grid), dim3(256), 0, st, xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd));
+  else if (D <= 1024) MEBT_CUDA_OK(launch_pdl(layernorm_kernel<InT, OutT, 8>, dim3(grid), dim3(256), 0, st, xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd));
+  else MEBT_CUDA_OK(launch_pdl(layernorm_kernel<InT, OutT, 16>, dim3(grid), dim3(256), 0, st, xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd));
   MEBT_LAUNCH_OK("layernorm_kernel");
   return MEBT_OK;
 }

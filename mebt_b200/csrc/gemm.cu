@@ -97,6 +97,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  griddep_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -186,17 +187,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const float* my_partials = nullptr;
       if (p.splits > 1) {
         // park the raw accumulator, release TMEM, and find out whether this CTA completes the tile
-        float* part = p.partials + ((size_t(tile) * p.splits + split) * BM + size_t(q * 32 + lane)) * BN;
+        // thread-major layout: float4 slot ((c * 8 + j) * 128 + t) -> every warp store / load is 512 contiguous bytes
+        float4* part = reinterpret_cast<float4*>(p.partials + (size_t(tile) * p.splits + split) * BM * BN) + (q * 32 + lane);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), r);
           tmem_ld_wait();
-          float4* o4 = reinterpret_cast<float4*>(part + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            __stcg(o4 + j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+            __stcg(part + (c * 8 + j) * 128, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty_bar[acc]);
@@ -211,7 +212,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (*split_flag == 0) continue;
         __threadfence();
-        my_partials = p.partials + (size_t(tile) * p.splits * BM + size_t(q * 32 + lane)) * BN;
+        my_partials = p.partials + size_t(tile) * p.splits * BM * BN + size_t(q * 32 + lane) * 4;
       }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -227,11 +228,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
           for (int sp = 0; sp < p.splits; ++sp) {              // fixed order: bitwise reproducible
-            const float4* i4 = reinterpret_cast<const float4*>(my_partials + size_t(sp) * BM * BN + c * 32);
+            const float4* i4 = reinterpret_cast<const float4*>(my_partials + size_t(sp) * BM * BN) + c * 8 * 128;
+            float4 t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = __ldcg(i4 + j * 128);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldcg(i4 + j);
-              v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              v[4 * j + 0] += t[j].x; v[4 * j + 1] += t[j].y; v[4 * j + 2] += t[j].z; v[4 * j + 3] += t[j].w;
             }
           }
         }
@@ -347,7 +350,7 @@ int launch_gemm(const void* A, const void* B, const GemmParams& p, int lda, int 
   const int grid = tiles < sm_count() ? tiles : sm_count();
   {
     LaunchScope ls(FAM_GEMM, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+    MEBT_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, p));
   }
   MEBT_LAUNCH_OK("gemm_bf16_kernel");
   return MEBT_OK;
@@ -432,9 +435,11 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
   if (!(flags & MEBT_GEMM_NO_SPLITK)) {
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int want = sm_count() / tiles;                       // CTAs available per tile
-    if (want > p.num_k_blocks / 4) want = p.num_k_blocks / 4;   // keep >= 4 k-blocks (256 of K) per split
+    // measured: the partial round trip + completion handshake costs ~5 us, so splitting pays only for long
+    // reductions (K >= 2048) and with >= 8 k-blocks left per split
+    if (want > p.num_k_blocks / 8) want = p.num_k_blocks / 8;
     if (want > 8) want = 8;
-    if (want >= 2) {
+    if (want >= 2 && p.num_k_blocks >= 32) {
       const int kpb = (p.num_k_blocks + want - 1) / want;
       const int splits = (p.num_k_blocks + kpb - 1) / kpb;
       const size_t need = size_t(tiles) * splits * BM * bn * sizeof(float);

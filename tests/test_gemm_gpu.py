@@ -32,7 +32,7 @@ CASES = [
     (256, 512, 4096, 0, 0, NO_SPLITK, True, True),
     (1536, 1024, 4096, 0, 0, GELU, True, False),
     (1536, 1024, 4096, 0, 1, NO_SPLITK, False, False),
-    (100, 256, 1000, 1, 1, OUT_FP32 | ACC, False, False),
+    (104, 256, 4000, 1, 1, OUT_FP32 | ACC, False, False),
     (1024, 64, 2048, 0, 0, 0, True, False),
 ]
 

@@ -38,7 +38,7 @@ def bench(M, N, K, flag, reps=40):
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "train"
     if which == "train":      # STL-16f, B = 6: latent rows 1536, token rows 3072
-        shapes = [(1536, 1024, 1024), (1536, 3072, 1024), (1536, 4096, 1024), (1536, 1024, 4096), (3072, 2048, 1024),
+        shapes = [(128, 256, 64), (128, 256, 1024), (1536, 1024, 1024), (1536, 3072, 1024), (1536, 4096, 1024), (1536, 1024, 4096), (3072, 2048, 1024),
                   (3072, 1024, 1024), (3072, 4096, 1024), (3072, 1024, 4096), (3072, 16384, 1024)]
     else:                     # 128f sampling, B = 4: latent rows 1024, token rows up to 32768
         shapes = [(1024, 1024, 1024), (1024, 3072, 1024), (1024, 4096, 1024), (1024, 1024, 4096), (16384, 2048, 1024),
