@@ -198,7 +198,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="train16f", choices=sorted(CONFIGS))
-    ap.add_argument("--batch", type=int, default=0, help="per GPU; default 6 (train16f, as configs/stl/mebt_16f.yaml) / 4")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="per GPU; default 6 for train16f (configs/stl/mebt_16f.yaml), 16 videos for sampling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     cfg = CONFIGS[args.workload]
@@ -206,7 +207,7 @@ def main():
         run_reference(args, cfg)
         return
     training = args.workload == "train16f"
-    B = args.batch or (6 if training else 4)
+    B = args.batch or (6 if training else 16)
     warmup = max(args.warmup, 3)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

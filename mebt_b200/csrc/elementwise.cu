@@ -207,11 +207,98 @@ int* device_err_flag() {
   return flag;
 }
 
+// bf16 -> bf16 fast path for D = 256 * NV: 16-byte loads (8 elements per lane per load) and TWO rows per warp with
+// all loads of both rows issued before the first reduction, which doubles the bytes each warp keeps in flight.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta,
+                                                               __nv_bfloat16* __restrict__ y, int ldy, int rows,
+                                                               float eps, float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out) {
+  constexpr int D = 256 * NV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * ROWS_PER_BLOCK + warp) * 2;
+  griddep_wait();
+  if (row0 >= rows) return;
+  const bool two = row0 + 1 < rows;
+  uint4 raw[2][NV];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      raw[r][i] = (r == 0 || two) ? *reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + (lane + 32 * i) * 8)
+                                  : make_uint4(0, 0, 0, 0);
+  float v[2][NV][8];
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        v[r][i][2 * k] = f.x; v[r][i][2 * k + 1] = f.y;
+        sum[r] += f.x + f.y;
+      }
+    }
+  float mu[2], rs[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) mu[r] = warp_sum(sum[r]) * (1.0f / D);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[r][i][k] - mu[r]; sq += d * d; }
+    rs[r] = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+  }
+  if (lane == 0) {
+    if (mean_out != nullptr) { mean_out[row0] = mu[0]; if (two) mean_out[row0 + 1] = mu[1]; }
+    if (rstd_out != nullptr) { rstd_out[row0] = rs[0]; if (two) rstd_out[row0 + 1] = rs[1]; }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r == 1 && !two) break;
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (v[r][i][k] - mu[r]) * rs[r] * gg[k] + bb[k];
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(y + (row0 + r) * ldy + c) = u;
+    }
+  }
+}
+
 template <typename InT, typename OutT>
 int launch_ln(const void* x, int ldx, const float* g, const float* b, void* y, int ldy, int rows, int D, float eps,
               float* mean, float* rstd, cudaStream_t st) {
   const int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
   LaunchScope ls(FAM_LAYERNORM, double(rows) * D * double(sizeof(InT) + sizeof(OutT)), st);
+  if constexpr (sizeof(InT) == 2 && sizeof(OutT) == 2) {
+    if (D % 256 == 0 && D <= 1024 && ldx % 8 == 0 && ldy % 8 == 0) {
+      const int g2 = (rows + 2 * ROWS_PER_BLOCK - 1) / (2 * ROWS_PER_BLOCK);
+      const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+      __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
+      switch (D / 256) {
+        case 1: MEBT_CUDA_OK(launch_pdl(layernorm_bf16x2_kernel<1>, dim3(g2), dim3(256), 0, st, xb, ldx, g, b, yb, ldy, rows, eps, mean, rstd)); break;
+        case 2: MEBT_CUDA_OK(launch_pdl(layernorm_bf16x2_kernel<2>, dim3(g2), dim3(256), 0, st, xb, ldx, g, b, yb, ldy, rows, eps, mean, rstd)); break;
+        case 3: MEBT_CUDA_OK(launch_pdl(layernorm_bf16x2_kernel<3>, dim3(g2), dim3(256), 0, st, xb, ldx, g, b, yb, ldy, rows, eps, mean, rstd)); break;
+        default: MEBT_CUDA_OK(launch_pdl(layernorm_bf16x2_kernel<4>, dim3(g2), dim3(256), 0, st, xb, ldx, g, b, yb, ldy, rows, eps, mean, rstd)); break;
+      }
+      MEBT_LAUNCH_OK("layernorm_bf16x2_kernel");
+      return MEBT_OK;
+    }
+  }
   const InT* xi = static_cast<const InT*>(x);
   OutT* yo = static_cast<OutT*>(y);
   if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_kernel<InT, OutT, 2>, dim3(grid), dim3(256), 0, st, xi, ldx, g, b, yo, ldy, rows, D, eps, mean, rstd));

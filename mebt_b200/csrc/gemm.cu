@@ -423,7 +423,18 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
   p.num_k_blocks = (K + BK - 1) / BK;
   // Tile width: the widest that divides N (measured: BN=256 wins or ties at every shape of the path, because the
   // per-CTA cost is TMA latency per k-block, not MMA issue).  Problems with fewer tiles than SMs are split along K.
-  int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+  // Measured (tools/gemm_probe.py): with >= one wave of 128x256 tiles the widest tile wins (least L2 traffic per
+  // flop); below one wave a CTA's k-loop runs at its MMA rate regardless of how many CTAs run, so the best width is the
+  // narrowest one that still fits a single wave (most SMs busy, no second wave).
+  int bn = 64;
+  {
+    const int widths[3] = {256, 128, 64};
+    bool chosen = false;
+    if (N % 256 == 0 && int64_t(p.num_m_blocks) * (N / 256) >= sm_count()) { bn = 256; chosen = true; }
+    for (int i = 2; i >= 0 && !chosen; --i)
+      if (N % widths[i] == 0 && int64_t(p.num_m_blocks) * (N / widths[i]) <= sm_count()) { bn = widths[i]; chosen = true; }
+    if (!chosen) bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+  }
   if (flags & MEBT_GEMM_FORCE_BN256) { MEBT_REQUIRE(N % 256 == 0, MEBT_ERR_SHAPE, "BN256 needs N%%256==0"); bn = 256; }
   if (flags & MEBT_GEMM_FORCE_BN128) { MEBT_REQUIRE(N % 128 == 0, MEBT_ERR_SHAPE, "BN128 needs N%%128==0"); bn = 128; }
   if (flags & MEBT_GEMM_FORCE_BN64) bn = 64;
