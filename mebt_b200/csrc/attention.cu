@@ -151,18 +151,26 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       const int valid = j < tiles1 ? min(AT_BKV, p.NK1 - j * AT_BKV) : min(AT_BKV, p.NK2 - (j - tiles1) * AT_BKV);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      const bool full = valid == AT_BKV;            // warp-uniform: only a source's last tile can be ragged
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
         tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
       const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f((m - m_new) * p.scale_log2);     // m = -inf on the first tile -> 0
+      const float alpha = ex2_approx((m - m_new) * p.scale_log2);     // m = -inf on the first tile -> 0
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
@@ -175,9 +183,11 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
           for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(r[i]);
         }
       }
+      if (alpha != 1.0f) {                          // the running maximum rarely moves after the first tiles
 #pragma unroll
-      for (int i = 0; i < AT_HS; ++i) o_acc[i] *= alpha;
-      l *= alpha;
+        for (int i = 0; i < AT_HS; ++i) o_acc[i] *= alpha;
+        l *= alpha;
+      }
       const float mb = m_new * p.scale_log2;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -185,12 +195,22 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
         tmem_ld_wait();
         float pv[32];
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - mb);
-          pv[i] = (c * 32 + i < valid) ? e : 0.f;
-          l += pv[i];
+          for (int i = 0; i < 32; ++i) {
+            pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+            l4[i & 3] += pv[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+            pv[i] = (c * 32 + i < valid) ? e : 0.f;
+            l4[i & 3] += pv[i];
+          }
         }
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         // 32 keys = four 16-byte chunks of this row inside one 64-key swizzle atom
         uint8_t* base = sP + (c >> 1) * AT_TILE_BYTES + row * 128;
 #pragma unroll

@@ -52,7 +52,7 @@ __device__ __forceinline__ void softmax_bwd_row(uint32_t tmem_s, uint32_t tmem_d
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const bool ok = row_ok && (c * 32 + i < valid_keys);
-      const float pv = ok ? exp2f(__uint_as_float(rs[i]) * scale_log2 - lse_l2) : 0.f;
+      const float pv = ok ? ex2_approx(fmaf(__uint_as_float(rs[i]), scale_log2, -lse_l2)) : 0.f;
       p[i] = pv;
       ds[i] = ok ? pv * (__uint_as_float(rd[i]) - delta) * scale : 0.f;
     }
