@@ -58,7 +58,9 @@ enum {
   MEBT_GEMM_FORCE_BN256 = 16, /* tile-width overrides, for tests and tuning */
   MEBT_GEMM_FORCE_BN128 = 32,
   MEBT_GEMM_FORCE_BN64 = 64,
-  MEBT_GEMM_NO_SPLITK = 128   /* never split the reduction across CTAs */
+  MEBT_GEMM_NO_SPLITK = 128,  /* never split the reduction across CTAs */
+  MEBT_GEMM_NO_PAIR = 256,    /* never use the 2-CTA cluster variant (B tile shared by TMA multicast) */
+  MEBT_GEMM_FORCE_PAIR = 512
 };
 /*
  * C[M,N] = act( A * B^T + bias ) + residual, tcgen05/TMEM/TMA.

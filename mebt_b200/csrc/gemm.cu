@@ -47,6 +47,7 @@ struct GemmParams {
   int kb_per_split;
   float* partials;
   int* counters;
+  int pair;                            // host-side only: launch the 2-CTA multicast variant
 };
 
 template <int BN, int STAGES>
@@ -57,7 +58,12 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+// PAIR: two CTAs of a cluster work on vertically adjacent 128-row tiles of the same BN columns and SHARE the B
+// (weight) tile: each CTA fetches half of it and TMA-multicasts that half into both CTAs' shared memory, so the
+// L2 -> SM traffic per CTA and k-block drops from A + B to A + B/2 (the large GEMMs of the path are L2-bandwidth
+// bound at 128x256 tiles).  MMAs and TMEM stay per CTA (cta_group::1); a stage is recycled only when BOTH CTAs'
+// MMAs have drained it, because the peer writes into it.
+template <int BN, bool A_MN, bool B_MN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const GemmParams p) {
@@ -72,7 +78,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_work = p.num_m_blocks * p.num_n_blocks * p.splits;
+  // work decomposition: plain = one 128xBN tile (x split) per item, strided by the grid;
+  //                     pair  = one 256xBN tile pair per item, strided by the number of clusters
+  const int pair_rank = PAIR ? int(blockIdx.x & 1) : 0;
+  const int pair_m = (p.num_m_blocks + 1) >> 1;
+  const int num_work = PAIR ? pair_m * p.num_n_blocks : p.num_m_blocks * p.num_n_blocks * p.splits;
+  const int work0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int work_stride = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
+  auto tile_origin = [&](int work, int& m0, int& n0, int& tile) {
+    if (PAIR) {
+      tile = work;
+      m0 = (2 * (work % pair_m) + pair_rank) * BM;
+      n0 = (work / pair_m) * BN;
+    } else {
+      tile = work / p.splits;
+      m0 = (tile % p.num_m_blocks) * BM;
+      n0 = (tile / p.num_m_blocks) * BN;
+    }
+  };
   int* split_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);
   constexpr uint32_t TMEM_COLS = 2 * BN;   // 128, 256 or 512 (power of two >= 32)
 
@@ -81,7 +104,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     prefetch_tensormap(&tma_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], PAIR ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -95,6 +118,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();        // the peer arrives on / multicasts into this CTA: its barriers must exist
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   griddep_wait();
@@ -104,10 +128,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int tile = work / p.splits, split = work % p.splits;
-        const int m0 = (tile % p.num_m_blocks) * BM;
-        const int n0 = (tile / p.num_m_blocks) * BN;
+      for (int work = work0; work < num_work; work += work_stride) {
+        int m0, n0, tile;
+        tile_origin(work, m0, n0, tile);
+        const int split = PAIR ? 0 : work % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -122,7 +146,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int i = 0; i < BM / 64; ++i)                                      // box [64 m][64 k]
               tma_load_2d(sA + i * (BK * 128), &tma_a, &full_bar[stage], m0 + i * 64, kb * BK);
           }
-          if constexpr (!B_MN) {
+          if constexpr (PAIR) {
+            // this CTA's half of the B tile, delivered to both CTAs (same smem offset, same barrier offset)
+            if constexpr (!B_MN) {
+              tma_load_2d_mc(sB + pair_rank * (BN / 2) * 128, &tma_b, &full_bar[stage], kb * BK, n0 + pair_rank * (BN / 2), 3);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) {
+                const int box = pair_rank * (BN / 128) + i;
+                tma_load_2d_mc(sB + box * (BK * 128), &tma_b, &full_bar[stage], n0 + box * 64, kb * BK, 3);
+              }
+            }
+          } else if constexpr (!B_MN) {
             tma_load_2d(sB, &tma_b, &full_bar[stage], kb * BK, n0);               // box [64 k][BN n]
           } else {
 #pragma unroll
@@ -140,10 +175,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+      for (int work = work0; work < num_work; work += work_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const int split = work % p.splits;
+        const int split = PAIR ? 0 : work % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue drained this accumulator
@@ -164,7 +199,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                                      : make_smem_desc_sw128(sB + k * (UMMA_K * 2), 16, 1024);
             umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
+          if constexpr (PAIR) umma_commit_mc(&empty_bar[stage], 3);   // releases the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -174,12 +210,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ================= epilogue (warps 2..5) =================
     const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
     int it = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+    for (int work = work0; work < num_work; work += work_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tile = work / p.splits, split = work % p.splits;
-      const int m0 = (tile % p.num_m_blocks) * BM;
-      const int n0 = (tile / p.num_m_blocks) * BN;
+      int m0, n0, tile;
+      tile_origin(work, m0, n0, tile);
+      const int split = PAIR ? 0 : work % p.splits;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -322,14 +358,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();        // the peer may still be signalling this CTA's barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch_gemm(const void* A, const void* B, const GemmParams& p, int lda, int ldb, cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
+int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda, int ldb, cudaStream_t stream) {
   constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   using L = SmemLayout<BN, STAGES>;
   CUtensorMap ta, tb;
@@ -337,23 +374,37 @@ int launch_gemm(const void* A, const void* B, const GemmParams& p, int lda, int 
   if (!A_MN) rc = get_tensor_map_2d(&ta, A, 2, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, BK, BM);
   else       rc = get_tensor_map_2d(&ta, A, 2, uint64_t(p.M), uint64_t(p.K), uint64_t(lda) * 2, 64, BK);
   if (rc) return rc;
-  if (!B_MN) rc = get_tensor_map_2d(&tb, B, 2, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, BK, BN);
+  // K-major B in pair mode is fetched as two half-height boxes (one per CTA of the cluster)
+  if (!B_MN) rc = get_tensor_map_2d(&tb, B, 2, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, BK, PAIR ? BN / 2 : BN);
   else       rc = get_tensor_map_2d(&tb, B, 2, uint64_t(p.N), uint64_t(p.K), uint64_t(ldb) * 2, 64, BK);
   if (rc) return rc;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  {
-    LaunchScope ls(FAM_GEMM, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
+  LaunchScope ls(FAM_GEMM, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
+  if constexpr (PAIR) {
+    const int pairs = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
+    int clusters = sm_count() / 2;
+    if (clusters > pairs) clusters = pairs;
+    MEBT_CUDA_OK(launch_pdl_cluster2(kern, dim3(2 * clusters), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, p));
+  } else {
+    const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
     MEBT_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, p));
   }
   MEBT_LAUNCH_OK("gemm_bf16_kernel");
   return MEBT_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_gemm(const void* A, const void* B, const GemmParams& p, int lda, int ldb, cudaStream_t stream) {
+  if constexpr (BN >= 128) {
+    if (p.pair) return launch_gemm_impl<BN, A_MN, B_MN, true>(A, B, p, lda, ldb, stream);
+  }
+  return launch_gemm_impl<BN, A_MN, B_MN, false>(A, B, p, lda, ldb, stream);
 }
 
 template <int BN>
@@ -443,7 +494,10 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
   p.kb_per_split = p.num_k_blocks;
   p.partials = nullptr;
   p.counters = nullptr;
-  if (!(flags & MEBT_GEMM_NO_SPLITK)) {
+  // at least two waves of tiles: pair up vertically adjacent tiles and share the B tile by TMA multicast
+  p.pair = (bn >= 128 && !(flags & MEBT_GEMM_NO_PAIR) && p.num_m_blocks >= 2 &&
+            int64_t(p.num_m_blocks) * p.num_n_blocks >= 2 * int64_t(sm_count())) || (flags & MEBT_GEMM_FORCE_PAIR && bn >= 128);
+  if (!p.pair && !(flags & MEBT_GEMM_NO_SPLITK)) {
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int want = sm_count() / tiles;                       // CTAs available per tile
     // measured: the partial round trip + completion handshake costs ~5 us, so splitting pays only for long

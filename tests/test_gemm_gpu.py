@@ -4,7 +4,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-GELU, OUT_FP32, ACC, BN256, BN128, BN64, NO_SPLITK = 1, 2, 4, 16, 32, 64, 128
+GELU, OUT_FP32, ACC, BN256, BN128, BN64, NO_SPLITK, NO_PAIR, PAIR = 1, 2, 4, 16, 32, 64, 128, 256, 512
 
 CASES = [
     # M, N, K, a_mn, b_mn, flags, bias, resid
@@ -34,6 +34,15 @@ CASES = [
     (1536, 1024, 4096, 0, 1, NO_SPLITK, False, False),
     (104, 256, 4000, 1, 1, OUT_FP32 | ACC, False, False),
     (1024, 64, 2048, 0, 0, 0, True, False),
+    # 2-CTA cluster variant (B tile shared by TMA multicast): forced on small shapes, odd tile rows, both B majors
+    (256, 256, 256, 0, 0, PAIR, False, False),
+    (384, 512, 1024, 0, 0, PAIR | GELU, True, False),
+    (1000, 768, 1024, 0, 0, PAIR | BN128, True, True),
+    (1536, 1024, 4096, 0, 1, PAIR, False, False),
+    (640, 256, 520, 1, 1, PAIR | OUT_FP32, False, False),
+    (128, 256, 128, 0, 0, PAIR, True, False),
+    (8192, 4096, 1024, 0, 0, 0, True, False),            # large enough to take the pair path on its own
+    (8192, 4096, 1024, 0, 0, NO_PAIR, True, False),
 ]
 
 
@@ -54,7 +63,7 @@ def test_gemm(M, N, K, a_mn, b_mn, flags, bias, resid):
         C0 = torch.randn(M, N, device="cuda", generator=g)
         C.copy_(C0)
     ops.gemm(A_st, B_st, bias_t, res_t, gelu=bool(flags & GELU), out=C, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn),
-             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK))
+             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK | NO_PAIR | PAIR))
     torch.cuda.synchronize()
     ref = A.float() @ B.float().t()
     if bias:
@@ -74,5 +83,5 @@ def test_gemm(M, N, K, a_mn, b_mn, flags, bias, resid):
     if C0 is not None:
         C2.copy_(C0)
     ops.gemm(A_st, B_st, bias_t, res_t, gelu=bool(flags & GELU), out=C2, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn),
-             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK))
+             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK | NO_PAIR | PAIR))
     assert torch.equal(C, C2)

@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, ".")
 from mebt_b200 import _lib  # noqa: E402
 
-BN = {256: 16, 128: 32, 64: 64, 0: 0}
+BN = {256: 16, 128: 32, 64: 64, 0: 0, 'pair': 512, 'nopair': 256}
 
 
 def bench(M, N, K, flag, reps=40):
@@ -46,8 +46,8 @@ def main():
                   (32768, 4096, 1024)]
     for (M, N, K) in shapes:
         line = f"M={M:6d} N={N:6d} K={K:5d} |"
-        for bn in (0, 256, 128, 64):
-            if bn and N % bn:
+        for bn in (0, 'pair', 'nopair', 128):
+            if isinstance(bn, int) and bn and N % bn:
                 continue
             us = bench(M, N, K, BN[bn])
             if us is None:
