@@ -240,7 +240,20 @@ typedef struct mebt_layer {
   const void* w_fc2;  const float* b_fc2;
 } mebt_layer_t;
 
+/* Optional inference-time hoist of the latent_enc K|V projections (contexts are constant through the stack and
+ * ln1's statistics are block-independent): w_enc_kv bf16 [n_enc*2D, D] = per-block (key|value) weights with ln1's
+ * gamma folded in, b_enc_kv fp32 [n_enc*2D] = bias + W.beta, ones/zeros fp32 [D].  Blocks are matched in order of
+ * appearance of MEBT_MODE_LATENT_ENC. */
+typedef struct mebt_enc_hoist {
+  int n_enc;
+  const void* w_enc_kv;
+  const float* b_enc_kv;
+  const float* ones;
+  const float* zeros;
+} mebt_enc_hoist_t;
+
 size_t mebt_stack_forward_workspace_bytes(int B, int L, int NC, int NT, int D);
+size_t mebt_stack_forward_hoisted_workspace_bytes(int B, int L, int NC, int NT, int D, int n_enc);
 /*
  * GPT.forward (mebt/modules/gpt.py:234-253) in eval mode: n_layers Blocks threaded over the three streams, then
  * logits = head(ln_f(targets)).  `layers` is a HOST array.  lat [B*L,D], ctx [B*NC,D], tgt [B*NT,D]: bf16 streams
@@ -251,6 +264,11 @@ size_t mebt_stack_forward_workspace_bytes(int B, int L, int NC, int NT, int D);
 int mebt_stack_forward(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
                        const void* w_head, int B, int L, int NC, int NT, int D, int H, int V, void* lat, void* ctx,
                        void* tgt, void* logits, int logits_dtype, void* workspace, size_t workspace_bytes, void* stream);
+/* Same with the latent_enc K|V hoist (hoist may be NULL). Workspace: mebt_stack_forward_hoisted_workspace_bytes. */
+int mebt_stack_forward_hoisted(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                               const void* w_head, const mebt_enc_hoist_t* hoist, int B, int L, int NC, int NT, int D,
+                               int H, int V, void* lat, void* ctx, void* tgt, void* logits, int logits_dtype,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- training step: forward that saves activations + full backward -------------------------------------- */
 /* fp32 gradient destinations of one Block, same geometry as mebt_layer_t (w_qkv = [3D,D] query|key|value rows). */

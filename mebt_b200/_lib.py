@@ -98,6 +98,15 @@ _SIGNATURES["mebt_stack_backward"] = [ctypes.POINTER(LayerStruct), ctypes.POINTE
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
                                       c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
+class EncHoistStruct(ctypes.Structure):
+    """mebt_enc_hoist_t"""
+    _fields_ = [("n_enc", c_int), ("w_enc_kv", c_void_p), ("b_enc_kv", c_void_p), ("ones", c_void_p), ("zeros", c_void_p)]
+
+
+_SIGNATURES["mebt_stack_forward_hoisted"] = [ctypes.POINTER(LayerStruct), c_int, c_void_p, c_void_p, c_void_p,
+                                             ctypes.POINTER(EncHoistStruct), c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                             c_void_p]
 _SIGNATURES["mebt_stack_forward"] = [ctypes.POINTER(LayerStruct), c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p, c_size_t, c_void_p]
@@ -118,6 +127,8 @@ _SIGNATURES["mebt_profile_report"] = [c_void_p, c_void_p, c_void_p]
 _lib.mebt_profile_report.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                      ctypes.POINTER(ctypes.c_longlong)]
 _lib.mebt_profile_report.restype = c_int
+_lib.mebt_stack_forward_hoisted_workspace_bytes.argtypes = [c_int] * 6
+_lib.mebt_stack_forward_hoisted_workspace_bytes.restype = c_size_t
 _lib.mebt_stack_forward_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
 _lib.mebt_stack_forward_workspace_bytes.restype = c_size_t
 _lib.mebt_vq_argmin_workspace_bytes.argtypes = [c_longlong]

@@ -26,7 +26,7 @@ struct Workspace {
   }
 };
 
-size_t stack_workspace_bytes(int B, int L, int NC, int NT, int D) {
+size_t stack_workspace_bytes(int B, int L, int NC, int NT, int D, int n_enc_hoisted = 0) {
   const size_t q_rows = size_t(B) * size_t(L > NC + NT ? L : NC + NT);
   const size_t k_rows = q_rows;
   size_t total = 0;
@@ -40,6 +40,7 @@ size_t stack_workspace_bytes(int B, int L, int NC, int NT, int D) {
   add(q_rows, D);        // h
   add(q_rows, 4 * D);    // u
   add(q_rows, D);        // maskgit concat stream
+  add(size_t(B) * NC, size_t(n_enc_hoisted) * 2 * D);   // hoisted K|V of every latent_enc block
   return total + 4096;
 }
 
@@ -52,15 +53,29 @@ size_t mebt_stack_forward_workspace_bytes(int B, int L, int NC, int NT, int D) {
   return mebt::stack_workspace_bytes(B, L, NC, NT, D);
 }
 
+size_t mebt_stack_forward_hoisted_workspace_bytes(int B, int L, int NC, int NT, int D, int n_enc) {
+  return mebt::stack_workspace_bytes(B, L, NC, NT, D, n_enc);
+}
+
 int mebt_stack_forward(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
                        const void* w_head, int B, int L, int NC, int NT, int D, int H, int V, void* lat, void* ctx,
                        void* tgt, void* logits, int logits_dtype, void* workspace, size_t workspace_bytes,
                        void* stream) {
+  return mebt_stack_forward_hoisted(layers, n_layers, lnf_w, lnf_b, w_head, nullptr, B, L, NC, NT, D, H, V, lat, ctx, tgt,
+                                    logits, logits_dtype, workspace, workspace_bytes, stream);
+}
+
+int mebt_stack_forward_hoisted(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                               const void* w_head, const mebt_enc_hoist_t* hoist, int B, int L, int NC, int NT, int D,
+                               int H, int V, void* lat, void* ctx, void* tgt, void* logits, int logits_dtype,
+                               void* workspace, size_t workspace_bytes, void* stream) {
   using namespace mebt;
+  const int n_hoist = (hoist != nullptr && NC > 0) ? hoist->n_enc : 0;
   MEBT_REQUIRE(B > 0 && L > 0 && NC >= 0 && NT > 0 && D > 0 && H > 0 && D == H * 64, MEBT_ERR_SHAPE,
                "stack_forward: bad shape B=%d L=%d NC=%d NT=%d D=%d H=%d (head_dim must be 64)", B, L, NC, NT, D, H);
-  MEBT_REQUIRE(workspace != nullptr && workspace_bytes >= stack_workspace_bytes(B, L, NC, NT, D), MEBT_ERR_WORKSPACE,
-               "stack_forward: workspace too small (%zu < %zu)", workspace_bytes, stack_workspace_bytes(B, L, NC, NT, D));
+  MEBT_REQUIRE(workspace != nullptr && workspace_bytes >= stack_workspace_bytes(B, L, NC, NT, D, n_hoist), MEBT_ERR_WORKSPACE,
+               "stack_forward: workspace too small (%zu < %zu)", workspace_bytes,
+               stack_workspace_bytes(B, L, NC, NT, D, n_hoist));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace ws{static_cast<char*>(workspace), 0, workspace_bytes};
   const int maxq = L > NC + NT ? L : NC + NT;
@@ -74,7 +89,9 @@ int mebt_stack_forward(const mebt_layer_t* layers, int n_layers, const float* ln
   void* h = ws.take(qr * D * 2);
   void* u = ws.take(qr * 4 * D * 2);
   void* cat = ws.take(qr * D * 2);
-  MEBT_REQUIRE(cat != nullptr, MEBT_ERR_WORKSPACE, "stack_forward: workspace exhausted");
+  void* kv_all = n_hoist > 0 ? ws.take(size_t(B) * NC * size_t(n_hoist) * 2 * D * 2) : nullptr;
+  MEBT_REQUIRE(cat != nullptr && (n_hoist == 0 || kv_all != nullptr), MEBT_ERR_WORKSPACE,
+               "stack_forward: workspace exhausted");
 
   // blocks after the last one that writes `targets` cannot influence the logits (gpt.py:247)
   int last = -1;
@@ -91,6 +108,17 @@ int mebt_stack_forward(const mebt_layer_t* layers, int n_layers, const float* ln
   int rc;
 #define TRY(expr) do { rc = (expr); if (rc != MEBT_OK) return rc; } while (0)
 
+  // Contexts never change through the stack (gpt.py:186-195) and ln1's statistics do not depend on the block, so the
+  // K|V projections of ALL latent_enc blocks are one GEMM over the normalised contexts: xhat (no affine) times the
+  // per-block weights with ln1's gamma folded in (bias absorbs W.beta).  Replaces n_enc LayerNorm passes over
+  // [B*NC, D] and n_enc [B*NC,2D,D] GEMMs by one pass and one [B*NC, n_enc*2D, D] GEMM.
+  int enc_seen = 0;
+  const int ld_all = n_hoist * 2 * D;
+  if (n_hoist > 0) {
+    TRY(LN(ctx, hoist->ones, hoist->zeros, kn, B * NC));
+    TRY(gemm_bf16(kn, D, 0, hoist->w_enc_kv, D, 0, kv_all, ld_all, B * NC, ld_all, D, hoist->b_enc_kv, nullptr, 0, 0, st));
+  }
+
   for (int i = 0; i <= last; ++i) {
     const mebt_layer_t& w = layers[i];
     const __nv_bfloat16* wqkv = static_cast<const __nv_bfloat16*>(w.w_qkv);
@@ -106,7 +134,11 @@ int mebt_stack_forward(const mebt_layer_t* layers, int n_layers, const float* ln
         TRY(LN(lat, w.ln1_w, w.ln1_b, qn, B * L));
         TRY(GEMM(qn, wqkv, D, qkv, D, B * L, D, D, w.b_qkv, nullptr, 0));
         Qb = qkv; ldq = D;
-        if (NC > 0) {
+        if (n_hoist > 0) {
+          MEBT_REQUIRE(enc_seen < n_hoist, MEBT_ERR_SHAPE, "stack_forward: more latent_enc blocks than hoisted weights");
+          KV1 = kv_all; ld1 = ld_all; k1c = enc_seen * 2 * D; v1c = k1c + D; nk1 = NC;
+          ++enc_seen;
+        } else if (NC > 0) {
           TRY(LN(ctx, w.ln1_w, w.ln1_b, kn, B * NC));
           TRY(GEMM(kn, w_kv, D, kv, 2 * D, B * NC, 2 * D, D, b_kv, nullptr, 0));
           KV1 = kv; ld1 = 2 * D; k1c = 0; v1c = D; nk1 = NC;

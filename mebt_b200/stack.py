@@ -10,6 +10,7 @@ Reference behaviour reproduced (mebt/modules/gpt.py:159-195, :234-253):
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass
 from typing import Mapping
 
@@ -73,6 +74,25 @@ class WeightPack:
                       "w_fc2", "b_fc2"):
                 setattr(arr[i], f, getattr(w, f).data_ptr())
         self.c_layers = arr
+        # latent_enc K|V hoist: per-block (key|value) weights with ln1's gamma folded in, bias absorbing W.beta
+        enc = [i for i, m in enumerate(self.modes) if m == "latent_enc"]
+        self.hoist = None
+        if enc:
+            D = self.D
+            ws, bs = [], []
+            for i in enc:
+                p = f"{prefix}blocks.{i}."
+                w_kv = torch.cat([params[p + "attn.key.weight"], params[p + "attn.value.weight"]], 0).detach().float()
+                b_kv = torch.cat([params[p + "attn.key.bias"], params[p + "attn.value.bias"]]).detach().float()
+                g, b = params[p + "ln1.weight"].detach().float(), params[p + "ln1.bias"].detach().float()
+                ws.append(w_kv * g[None, :])
+                bs.append(b_kv + w_kv @ b)
+            self._w_enc_kv = ops.cast_bf16(torch.cat(ws, 0).contiguous())
+            self._b_enc_kv = torch.cat(bs).contiguous()
+            self._ones = torch.ones(D, device=self.lnf_w.device)
+            self._zeros = torch.zeros(D, device=self.lnf_w.device)
+            self.hoist = _lib.EncHoistStruct(len(enc), self._w_enc_kv.data_ptr(), self._b_enc_kv.data_ptr(),
+                                             self._ones.data_ptr(), self._zeros.data_ptr())
 
     def last_live_layer(self) -> int:
         """Blocks after the last one writing `targets` cannot reach the logits (gpt.py:247 reads targets only)."""
@@ -155,19 +175,22 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
     return ws
 
 
-def stack_forward(pack: WeightPack, B: int, lat, ctx, tgt, logits_dtype=torch.float32):
-    """GPT.forward (gpt.py:234-253) in eval mode through the one-call C++ engine (`mebt_stack_forward`).
-    lat/tgt are updated in place.  Returns logits [B*NT, V]."""
+def stack_forward(pack: WeightPack, B: int, lat, ctx, tgt, logits_dtype=torch.float32, hoist=True):
+    """GPT.forward (gpt.py:234-253) in eval mode through the one-call C++ engine (`mebt_stack_forward_hoisted`).
+    lat/tgt are updated in place.  Returns logits [B*NT, V].  hoist=True computes the K|V projections of all
+    latent_enc blocks in one GEMM over the once-normalised contexts."""
     D = pack.D
     L, NC, NT = lat.shape[0] // B, ctx.shape[0] // B, tgt.shape[0] // B
     for t in (lat, ctx, tgt):
         if t.dtype != torch.bfloat16 or not t.is_contiguous():
             raise _lib.MebtError("stack_forward streams must be contiguous bf16")
     logits = torch.empty(B * NT, pack.V, device=lat.device, dtype=logits_dtype)
-    nbytes = _lib.lib.mebt_stack_forward_workspace_bytes(B, L, NC, NT, D)
+    h = pack.hoist if (hoist and pack.hoist is not None and NC > 0) else None
+    nbytes = _lib.lib.mebt_stack_forward_hoisted_workspace_bytes(B, L, NC, NT, D, h.n_enc if h is not None else 0)
     ws = _workspace(lat.device, nbytes)
-    _lib.call("mebt_stack_forward", pack.c_layers, len(pack.layers), pack.lnf_w.data_ptr(), pack.lnf_b.data_ptr(),
-              pack.w_head.data_ptr(), B, L, NC, NT, D, pack.n_head, pack.V, lat.data_ptr(), ctx.data_ptr(),
+    _lib.call("mebt_stack_forward_hoisted", pack.c_layers, len(pack.layers), pack.lnf_w.data_ptr(), pack.lnf_b.data_ptr(),
+              pack.w_head.data_ptr(), ctypes.byref(h) if h is not None else None, B, L, NC, NT, D, pack.n_head, pack.V,
+              lat.data_ptr(), ctx.data_ptr(),
               tgt.data_ptr(), logits.data_ptr(), ops._DT[logits_dtype], ws.data_ptr(), ws.numel(),
               torch.cuda.current_stream().cuda_stream)
     return logits
