@@ -44,7 +44,10 @@ CONFIGS = {
     "train16f": dict(_BASE, block_size=1024, shape=[4, 16, 16]),
     "sample16f": dict(_BASE, block_size=1024, shape=[4, 16, 16]),
     "sample128f": dict(_BASE, block_size=8192, shape=[32, 16, 16]),
+    "maskgit16f": dict(_BASE, block_size=1024, shape=[4, 16, 16]),
+    "vq16f": dict(_BASE, block_size=1024, shape=[4, 16, 16]),
 }
+MASKGIT = dict(temperature=1.0, top_k=None, top_p=None, n_steps=128, strategy="maskgit", context_temperature=6.0)
 DNR = dict(n_draft=8, draft_t=1.0, n_revise=8, revise_t=1.0, M=2)
 TRAIN_T = 0.5
 
@@ -52,6 +55,20 @@ TRAIN_T = 0.5
 def masked_tokens_per_video(N: int) -> int:
     d, r, M = DNR["n_draft"], DNR["n_revise"], DNR["M"]
     return sum(N - i * (N // d) for i in range(d)) + M * r * (N // r)
+
+
+def maskgit_masked_tokens(N: int, n_steps: int) -> int:
+    """sum of NT over the forwards of Net2NetTransformer.sample with the cosine schedule (float32 arithmetic, as the
+    sampler evaluates it; steps whose target count is already below the schedule are skipped)."""
+    nt, total = N, 0
+    for t_next in np.linspace(0, 1, n_steps + 1)[1:]:
+        n_masked = int(torch.ceil(torch.cos(0.5 * np.pi * torch.full((1,), fill_value=t_next)) * N)[0])
+        if n_masked > nt:
+            continue
+        total += nt
+        if N - n_masked > N - nt:
+            nt = n_masked
+    return total
 
 
 def peaks():
@@ -135,6 +152,19 @@ def oracle_sampling_step(cfg, state):
     return step, N // 2, desc
 
 
+def oracle_vq_step(B):
+    from oracle import mebt_oracle as O
+    torch.manual_seed(0)
+    E = torch.randn(16384, 256)
+    z = torch.randn(B, 256, 4, 16, 16, generator=torch.Generator().manual_seed(4))
+
+    def step():
+        with torch.no_grad():
+            out = O.codebook_quantise(z, E)
+            O.codebook_decode_gather(out["encodings"], E)
+    return step, B * 1024, f"Codebook.forward + decode gather on {B} videos (fp32 torch-CPU oracle port)"
+
+
 def oracle_train_step(cfg, state, B):
     from oracle import mebt_oracle as O
     P = {k: v.clone().requires_grad_(True) for k, v in state.items()}
@@ -171,6 +201,8 @@ def run_reference(args, cfg):
     state = {k: v.detach() for k, v in model.state_dict().items()}
     if args.workload == "train16f":
         step, tokens, desc = oracle_train_step(cfg, state, args.batch or 6)
+    elif args.workload == "vq16f":
+        step, tokens, desc = oracle_vq_step(8)
     else:
         step, tokens, desc = oracle_sampling_step(cfg, state)
     for _ in range(args.warmup):
@@ -207,7 +239,7 @@ def main():
         run_reference(args, cfg)
         return
     training = args.workload == "train16f"
-    B = args.batch or (6 if training else 16)
+    B = args.batch or {"train16f": 6, "maskgit16f": 32, "vq16f": 64}.get(args.workload, 16)
     warmup = max(args.warmup, 3)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,6 +279,24 @@ def main():
             out = ts.train_step(opt, x, idx, t=TRAIN_T, world_size=world)
             loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
         h2d, d2h = int(x_host.numel() * 8 + idx_host.numel() * 8), 4
+    elif args.workload == "vq16f":
+        # BASELINE.json configs[3]: codebook quantise + decode-side gather, 16x128x128 videos -> latents [256,4,16,16]
+        from mebt_b200.vqgan import VQGAN
+        torch.manual_seed(0)
+        vq = VQGAN(16384, 256).to(dev).eval()
+        z_host = torch.randn(B, 256, 4, 16, 16, generator=torch.Generator().manual_seed(4 + rank)).pin_memory()
+        enc_host = torch.empty(B, 4, 16, 16, dtype=torch.long).pin_memory()
+        z_dev = z_host.to(dev)
+        tokens_per_step = B * 1024
+
+        def step_device():
+            return vq.decode(vq.encode(z_dev))
+
+        def step_e2e():
+            enc = vq.encode(z_host.to(dev, non_blocking=True))
+            vq.decode(enc)
+            enc_host.copy_(enc, non_blocking=True)
+        h2d, d2h = int(z_host.numel() * 4), int(enc_host.numel() * 8)
     else:
         model.eval()
         model.rng_mode, model.rng_seed = "philox", 1000 + rank
@@ -263,6 +313,18 @@ def main():
             x = x_host.to(dev, non_blocking=True)
             out_host.copy_(model.draft_and_revise(x, None, **DNR), non_blocking=True)
         h2d, d2h = int(x_host.numel() * 8), int(out_host.numel() * 8)
+        if args.workload == "maskgit16f":
+            # BASELINE.json configs[4]: the 24-layer model's maskgit loop (UCF recipe: 128 steps, cosine schedule,
+            # context temperature 6) with the 16384-way logit head + confidence re-masking at batch 32
+            model.mask_sampler.schedule = "cosine"
+            tokens_per_step = B * maskgit_masked_tokens(N, MASKGIT["n_steps"])
+
+            def step_device():                                                # noqa: F811
+                return model.sample(x_dev, None, **MASKGIT)[0]
+
+            def step_e2e():                                                   # noqa: F811
+                x = x_host.to(dev, non_blocking=True)
+                out_host.copy_(model.sample(x, None, **MASKGIT)[0], non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -332,6 +394,9 @@ def main():
             if training:
                 step, toks, desc = oracle_train_step(cfg, state, B)
                 dt = time_cpu(step, 1, 2)
+            elif args.workload == "vq16f":
+                step, toks, desc = oracle_vq_step(8)
+                dt = time_cpu(step, 1, 2)
             else:
                 step, toks, desc = oracle_sampling_step(cfg, state)
                 dt = time_cpu(step, 1, 2)
@@ -344,6 +409,12 @@ def main():
             config.update(t=TRAIN_T, NC=N // 2, NT=N // 2, dropout=0.0, optimizer="AdamW fused fp32 master weights",
                           note="STL yaml uses dropout 0.1; the CUDA path implements p = 0 (taichi/ucf setting)",
                           grad_allreduce="fp32, 4 buckets + head + embeddings, overlapped with backward" if world > 1 else "none (1 GPU)")
+        elif args.workload == "vq16f":
+            config = {"workload": "vq16f", "videos_per_gpu": B, "latent": [256, 4, 16, 16], "codebook": [16384, 256],
+                      "unit_note": "a token = one quantised latent vector (fused fp32 distance+argmin, then both gathers)"}
+        elif args.workload == "maskgit16f":
+            config.update(sampler=MASKGIT, schedule="cosine", masked_tokens_per_video=maskgit_masked_tokens(N, 128),
+                          noise="in-kernel philox", generated_tokens_per_s=world * B * N / (ms * 1e-3))
         else:
             config.update(sampler=DNR, masked_tokens_per_video=masked_tokens_per_video(N), noise="in-kernel philox (inverse CDF)",
                           logits="fp32 materialised", generated_tokens_per_s=world * B * N / (ms * 1e-3))

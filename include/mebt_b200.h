@@ -144,8 +144,9 @@ int mebt_ce_reduce(const float* row_loss, const int* row_rank, int rows, float* 
  * inverse-CDF with one in-kernel Philox4x32-10(seed, offset, row) uniform per row, so no noise tensor exists.
  * probs (optional, fp32 [rows, V]) receives the softmax the reference returns with return_probs=True.
  * Replaces sample_from_logits + gumbel_sort + top_k_logits, mebt/transformer.py:843-895 (a full 16384-way sort
- * per row and ~10 passes over [B,NT,V] become one pass).  top_k <= 0 disables the filter; top_p in (0,1) is
- * not implemented (MEBT_ERR_UNSUPPORTED).
+ * per row and ~10 passes over [B,NT,V] become one pass).  top_k <= 0 and top_p outside (0,1) disable the filters.
+ * top_p (nucleus, transformer.py:898-910) keeps, in descending order, every token up to and including the one whose
+ * cumulative mass first reaches top_p, then renormalises; tokens tying with the boundary value are all kept.
  */
 int mebt_sample_logits(const void* logits, long long ld, int dtype, int rows, int V, float temperature, int top_k,
                        float top_p, const float* noise, unsigned long long seed, unsigned long long offset,

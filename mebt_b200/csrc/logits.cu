@@ -184,7 +184,8 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 
 template <typename T, bool RACE>
 __global__ void __launch_bounds__(LT) sample_logits_kernel(const T* __restrict__ logits, long long ld, int V,
-                                                           float temp_div, int top_k, const float* __restrict__ noise,
+                                                           float temp_div, int top_k, float top_p,
+                                                           const float* __restrict__ noise,
                                                            unsigned long long seed, unsigned long long offset,
                                                            int64_t* __restrict__ ids, float* __restrict__ scores,
                                                            float* __restrict__ probs_out) {
@@ -268,6 +269,71 @@ __global__ void __launch_bounds__(LT) sample_logits_kernel(const T* __restrict__
     se += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   se = block_sum(se, red);
+
+  if (top_p > 0.f && top_p < 1.f) {
+    // Nucleus filter (top_p_probs, transformer.py:898-910): in descending order of probability keep every token
+    // up to and including the one whose cumulative mass first reaches top_p, zero the rest, renormalise.  The
+    // boundary probability is found by a 4-pass radix descent over the float bits with per-bin MASS histograms
+    // (no sort); tokens tying with the boundary value are all kept (the reference's sort breaks such ties
+    // arbitrarily).  v[] leaves this block holding the filtered, renormalised probabilities and se = 1.
+    __shared__ float mass[256];
+    __shared__ uint32_t np_prefix;
+    __shared__ float np_above;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i) {
+      v[i].x = __fdiv_rn(v[i].x, se); v[i].y = __fdiv_rn(v[i].y, se);
+      v[i].z = __fdiv_rn(v[i].z, se); v[i].w = __fdiv_rn(v[i].w, se);
+    }
+    if (threadIdx.x == 0) { np_prefix = 0; np_above = 0.f; }
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      mass[threadIdx.x] = 0.f;
+      __syncthreads();
+      const uint32_t prefix = np_prefix;
+      const uint32_t pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+#pragma unroll
+      for (int i = 0; i < MAX_V4; ++i) {
+        const int c = (threadIdx.x + LT * i) * 4;
+        if (c < V) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float pj = (&v[i].x)[j];
+            const uint32_t key = __float_as_uint(pj);            // p >= 0: the bit pattern is order preserving
+            if ((key & pmask) == prefix && pj > 0.f) atomicAdd(&mass[(key >> shift) & 0xFF], pj);
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float above = np_above;
+        int b = 255;
+        for (; b > 0; --b) {
+          if (above + mass[b] >= top_p) break;
+          above += mass[b];
+        }
+        np_prefix = prefix | (uint32_t(b) << shift);
+        np_above = above;
+      }
+      __syncthreads();
+    }
+    const uint32_t boundary = np_prefix;
+    float kept = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float& pj = (&v[i].x)[j];
+        if (__float_as_uint(pj) < boundary) pj = 0.f;
+        kept += pj;
+      }
+    kept = block_sum(kept, red);
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i) {
+      v[i].x = __fdiv_rn(v[i].x, kept); v[i].y = __fdiv_rn(v[i].y, kept);
+      v[i].z = __fdiv_rn(v[i].z, kept); v[i].w = __fdiv_rn(v[i].w, kept);
+    }
+    se = 1.0f;
+  }
 
   if constexpr (!RACE) {
     // ---- fast mode: inverse-CDF draw.  One Philox uniform per row and a block-wide prefix sum select an id from
@@ -581,15 +647,14 @@ int mebt_sample_logits(const void* logits, long long ld, int dtype, int rows, in
   MEBT_REQUIRE(rows >= 0 && V > 0 && V % 4 == 0 && V <= LT * MAX_V4 * 4, MEBT_ERR_SHAPE,
                "sample_logits: V=%d must be a multiple of 4 and <= %d", V, LT * MAX_V4 * 4);
   MEBT_REQUIRE(ld % 4 == 0, MEBT_ERR_SHAPE, "sample_logits: bad row stride");
-  MEBT_REQUIRE(!(top_p > 0.f && top_p < 1.f), MEBT_ERR_UNSUPPORTED,
-               "sample_logits: nucleus (top_p) filtering is not implemented on the device path yet");
   if (rows == 0) return MEBT_OK;
   // python: temperature + 1e-8 in double, then cast to fp32 for the tensor division
   const float temp_div = float(double(temperature) + 1e-8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const double eb = dtype == MEBT_DTYPE_FP32 ? 4.0 : 2.0;
   LaunchScope ls(FAM_SAMPLE, double(rows) * (double(V) * (eb + (noise != nullptr ? 4.0 : 0.0) + (probs != nullptr ? 4.0 : 0.0)) + 12.0), st);
-  if (noise == nullptr && top_k <= 0 && probs == nullptr && V % 128 == 0) {
+  const bool nucleus = top_p > 0.f && top_p < 1.f;
+  if (noise == nullptr && top_k <= 0 && !nucleus && probs == nullptr && V % 128 == 0) {
     // fast mode without filters: streaming inverse-CDF kernel (multiplies by 1/(T + 1e-8) instead of dividing)
     const float inv_temp = float(1.0 / (double(temperature) + 1e-8));
     if (dtype == MEBT_DTYPE_FP32)
@@ -605,11 +670,11 @@ int mebt_sample_logits(const void* logits, long long ld, int dtype, int rows, in
   }
   if (dtype == MEBT_DTYPE_FP32)
     (noise != nullptr ? sample_logits_kernel<float, true> : sample_logits_kernel<float, false>)<<<rows, LT, 0, st>>>(
-        static_cast<const float*>(logits), ld, V, temp_div, top_k, noise, seed, offset, ids, scores, probs);
+        static_cast<const float*>(logits), ld, V, temp_div, top_k, top_p, noise, seed, offset, ids, scores, probs);
   else if (dtype == MEBT_DTYPE_BF16)
     (noise != nullptr ? sample_logits_kernel<__nv_bfloat16, true> : sample_logits_kernel<__nv_bfloat16, false>)
-        <<<rows, LT, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, V, temp_div, top_k, noise, seed, offset,
-                              ids, scores, probs);
+        <<<rows, LT, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, V, temp_div, top_k, top_p, noise, seed,
+                              offset, ids, scores, probs);
   else
     MEBT_REQUIRE(false, MEBT_ERR_DTYPE, "sample_logits: unsupported dtype %d", dtype);
   MEBT_LAUNCH_OK("sample_logits_kernel");

@@ -119,20 +119,29 @@ def test_sample_logits_vs_reference_golden():
     z, _ = load_golden("sample_from_logits")
     g = torch.Generator().manual_seed(int(z["seed"]))
     logits = 3.0 * torch.randn(3, 40, 16384, generator=g)
-    for tag, (T, k) in dict(plain=(1.0, None), temp=(0.7, None), topk=(1.0, 32)).items():
+    for tag, (T, k, tp) in dict(plain=(1.0, None, None), temp=(0.7, None, None), topk=(1.0, 32, None),
+                                topp=(0.9, None, 0.8), both=(0.8, 100, 0.9)).items():
         torch.manual_seed(123)
         q = torch.empty_like(logits).exponential_()
-        ids, scores, probs = ops.sample_logits(logits.view(-1, 16384).cuda(), T, k, None, noise=q.view(-1, 16384).cuda(),
+        ids, scores, probs = ops.sample_logits(logits.view(-1, 16384).cuda(), T, k, tp, noise=q.view(-1, 16384).cuda(),
                                                return_probs=True)
         ids, scores, probs = ids.cpu().view(3, 40), scores.cpu().view(3, 40), probs.cpu().view(3, 40, -1)
+        nnz_diff = np.abs((probs > 0).sum(-1).numpy() - z[f"{tag}_nnz"])
+        same_set = torch.from_numpy(nnz_diff == 0)
+        if tp is None:
+            assert (nnz_diff == 0).all()
+        else:   # nucleus boundary: fp32 summation order may move it by one token in a few rows
+            assert nnz_diff.max() <= 1 and (nnz_diff > 0).mean() < 0.1, (tag, nnz_diff.max(), (nnz_diff > 0).mean())
+            assert torch.allclose(probs.sum(-1), torch.ones(3, 40), atol=1e-5)
         ref_ids = torch.from_numpy(z[f"{tag}_ids"])
-        mism = (ids != ref_ids)
+        mism = (ids != ref_ids) & same_set
         # bit-exact selection; a differing id is only tolerated as a documented float near-tie of the race
         assert mism.float().mean() <= 0.01, (tag, int(mism.sum()))
-        ok = ~mism
-        np.testing.assert_allclose(scores[ok].numpy(), z[f"{tag}_score"][ok.numpy()], rtol=5e-6, atol=1e-12)
-        assert ((probs > 0).sum(-1).numpy() == z[f"{tag}_nnz"]).all()
-        np.testing.assert_allclose(probs[:, ::5, ::211].numpy(), z[f"{tag}_psub"], rtol=5e-6, atol=1e-12)
+        ok = ~(ids != ref_ids) & same_set
+        np.testing.assert_allclose(scores[ok].numpy(), z[f"{tag}_score"][ok.numpy()], rtol=2e-5, atol=1e-12)
+        sub_same = same_set[:, ::5]
+        np.testing.assert_allclose(probs[:, ::5, ::211][sub_same].numpy(), z[f"{tag}_psub"][sub_same.numpy()],
+                                   rtol=2e-5 if tp is not None else 5e-6, atol=1e-12)
 
 
 def test_sample_logits_bf16_and_philox_distribution():

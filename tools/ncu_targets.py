@@ -1,0 +1,73 @@
+"""Launch each hot kernel once or twice at a BASELINE-sized shape so that `ncu --set full` can capture it cheaply:
+
+    ncu --set full --clock-control none --import-source on -o gpurun_out/prof_kernels python tools/ncu_targets.py
+
+(about 25 kernel launches in total; the warm-up launches are also captured and can be ignored)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from mebt_b200 import ops  # noqa: E402
+
+torch.manual_seed(0)
+dev = "cuda"
+bf = torch.bfloat16
+
+
+def r(*s, dtype=bf):
+    return torch.randn(*s, device=dev).to(dtype)
+
+
+def main():
+    # K2/K4 large GEMMs (128f sampling, 16 videos: token rows up to 131072; use 16384 rows)
+    a = r(8192, 1024)
+    for (n, k) in ((4096, 1024), (1024, 4096)):
+        w = r(n, k)
+        x = r(8192, k)
+        for _ in range(2):
+            ops.gemm(x, w, torch.zeros(n, device=dev))
+    head = r(16384, 1024)
+    for _ in range(2):
+        logits = ops.gemm(a, head, out_dtype=torch.float32)                  # head GEMM, fp32 logits
+    # K6 sampling (fast mode) and K5 masked CE over the materialised logits
+    for _ in range(2):
+        ops.sample_logits(logits, 1.0, None, None, noise=None, seed=1, offset=1)
+    tg = torch.randint(0, 16384, (8192,), device=dev)
+    lb = logits.to(bf)
+    for _ in range(2):
+        ops.masked_ce(lb, tg, 0.0, dlogits=lb, grad_scale=1.0)
+    # LayerNorm and the stem gather at token-row scale
+    g, b = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
+    xs = r(32768, 1024)
+    for _ in range(2):
+        ops.layernorm(xs, g, b)
+    B, N = 8, 8192
+    xi = torch.randint(0, 16384, (B, N), device=dev)
+    perm = torch.stack([torch.randperm(N, device=dev) for _ in range(B)])
+    tok, pos = torch.randn(16384, 1024, device=dev), torch.randn(1, N, 1024, device=dev)
+    for _ in range(2):
+        ops.embed_gather(xi, perm[:, :4096], perm[:, 4096:], tok, pos, torch.randn(1, 1, 1024, device=dev),
+                         torch.randn(1, 256, 1024, device=dev))
+    # K3 attention: latent_enc shape (256 latents x 7168 contexts) and latent_dec shape (8192 targets x 256 latents)
+    Bq, H, D = 4, 16, 1024
+    q = r(Bq * 256, D)
+    kv = r(Bq * 7168, 2 * D)
+    for _ in range(2):
+        ops.attention(q, 0, kv, 0, D, 7168, None, 0, 0, 0, Bq, H, 256)
+    q2 = r(Bq * 8192, D)
+    kv2 = r(Bq * 256, 2 * D)
+    for _ in range(2):
+        ops.attention(q2, 0, kv2, 0, D, 256, None, 0, 0, 0, Bq, H, 8192)
+    # K9/K10 codebook
+    E = torch.randn(16384, 256, device=dev)
+    z = torch.randn(8, 256, 4, 16, 16, device=dev)
+    for _ in range(2):
+        enc = ops.vq_argmin(z, E)
+    ops.row_gather(enc, E, channel_first=True)
+    torch.cuda.synchronize()
+    print("done")
+
+
+if __name__ == "__main__":
+    main()
