@@ -47,27 +47,30 @@ struct GemmParams {
   int kb_per_split;
   float* partials;
   int* counters;
-  int pair;                            // host-side only: launch the 2-CTA multicast variant
+  int pair;                            // host-side only: launch the cta_group::2 (SM pair) variant
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 struct SmemLayout {
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // pair mode: each CTA holds half of the B tile
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
-// PAIR: two CTAs of a cluster work on vertically adjacent 128-row tiles of the same BN columns and SHARE the B
-// (weight) tile: each CTA fetches half of it and TMA-multicasts that half into both CTAs' shared memory, so the
-// L2 -> SM traffic per CTA and k-block drops from A + B to A + B/2 (the large GEMMs of the path are L2-bandwidth
-// bound at 128x256 tiles).  MMAs and TMEM stay per CTA (cta_group::1); a stage is recycled only when BOTH CTAs'
-// MMAs have drained it, because the peer writes into it.
+// PAIR: the two CTAs of a cluster (an SM pair) execute ONE tcgen05.mma.cta_group::2 of shape M=256 x N=BN: each CTA
+// stages its own 128 rows of A and HALF of the B tile, the leader CTA's single thread issues the MMAs, and each CTA
+// receives its 128 accumulator rows in its own TMEM.  Per SM and k-block this moves A + B/2 instead of A + B
+// through shared memory — at 128x256 tiles the 1-CTA form needs ~190 B/clk of shared-memory bandwidth (TMA fill +
+// operand reads) against 128 B/clk available, which is what capped it at ~65 % tensor-pipe utilisation.
+// Handshake: both CTAs' TMA loads complete on the LEADER's full barrier; the leader's tcgen05.commit (multicast)
+// releases the stage in both CTAs and publishes the accumulator to both epilogues; both epilogues arrive on the
+// leader's tmem_empty barrier.
 template <int BN, bool A_MN, bool B_MN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const GemmParams p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -104,21 +107,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     prefetch_tensormap(&tma_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], PAIR ? 2 : 1);
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], PAIR ? 256 : 128);   // pair: the leader waits for both CTAs' epilogues
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_ptr_smem, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();        // the peer arrives on / multicasts into this CTA: its barriers must exist
+  if (PAIR) cluster_sync_all();        // the peer signals this CTA's barriers: they must exist first
+  // shared::cluster addresses of the leader's barriers (identity for the leader itself)
+  uint32_t full_bar_leader = 0, tmem_empty_leader = 0;
+  if constexpr (PAIR) {
+    full_bar_leader = mapa_u32(smem_u32(full_bar), 0);
+    tmem_empty_leader = mapa_u32(smem_u32(tmem_empty_bar), 0);
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   griddep_wait();
@@ -138,6 +147,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * L::STAGE_BYTES;
           uint8_t* sB = sA + A_TILE_BYTES;
+          if constexpr (PAIR) {
+            // both CTAs' bytes complete on the leader's barrier; the leader arms it for the pair
+            const uint32_t bar = full_bar_leader + stage * 8;
+            if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_2d_2sm(sA, &tma_a, bar, kb * BK, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i) tma_load_2d_2sm(sA + i * (BK * 128), &tma_a, bar, m0 + i * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {                       // this CTA's half of the B tile: rows n0 + rank * BN/2 ...
+              tma_load_2d_2sm(sB, &tma_b, bar, kb * BK, n0 + pair_rank * (BN / 2));
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i)
+                tma_load_2d_2sm(sB + i * (BK * 128), &tma_b, bar, n0 + (pair_rank * (BN / 128) + i) * 64, kb * BK);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if constexpr (!A_MN) {
             tma_load_2d(sA, &tma_a, &full_bar[stage], kb * BK, m0);               // box [64 k][128 m]
@@ -146,18 +175,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int i = 0; i < BM / 64; ++i)                                      // box [64 m][64 k]
               tma_load_2d(sA + i * (BK * 128), &tma_a, &full_bar[stage], m0 + i * 64, kb * BK);
           }
-          if constexpr (PAIR) {
-            // this CTA's half of the B tile, delivered to both CTAs (same smem offset, same barrier offset)
-            if constexpr (!B_MN) {
-              tma_load_2d_mc(sB + pair_rank * (BN / 2) * 128, &tma_b, &full_bar[stage], kb * BK, n0 + pair_rank * (BN / 2), 3);
-            } else {
-#pragma unroll
-              for (int i = 0; i < BN / 128; ++i) {
-                const int box = pair_rank * (BN / 128) + i;
-                tma_load_2d_mc(sB + box * (BK * 128), &tma_b, &full_bar[stage], n0 + box * 64, kb * BK, 3);
-              }
-            }
-          } else if constexpr (!B_MN) {
+          if constexpr (!B_MN) {
             tma_load_2d(sB, &tma_b, &full_bar[stage], kb * BK, n0);               // box [64 k][BN n]
           } else {
 #pragma unroll
@@ -170,8 +188,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && pair_rank == 0) {       // pair mode: only the leader CTA issues
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -197,11 +215,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                                      : make_smem_desc_sw128(sA + k * (UMMA_K * 2), 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(sB + k * (UMMA_K * 128), BK * 128, 1024)
                                      : make_smem_desc_sw128(sB + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if constexpr (PAIR) umma_commit_mc(&empty_bar[stage], 3);   // releases the stage in both CTAs
-          else umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+          if constexpr (PAIR) {
+            umma_commit_2sm_mc(&empty_bar[stage], 3);                      // frees the stage in both CTAs
+            if (kb == kb1 - 1) umma_commit_2sm_mc(&tmem_full_bar[acc], 3);  // accumulator ready in both CTAs
+          } else {
+            umma_commit(&empty_bar[stage]);                  // smem slot reusable once these MMAs retire
+            if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -351,7 +374,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       if (p.splits == 1) {
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);
+        if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+        else mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
   }
@@ -361,14 +385,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (PAIR) cluster_sync_all();        // the peer may still be signalling this CTA's barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 template <int BN, bool A_MN, bool B_MN, bool PAIR>
 int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda, int ldb, cudaStream_t stream) {
-  constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  using L = SmemLayout<BN, STAGES>;
+  constexpr int STAGES = PAIR ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  using L = SmemLayout<BN, STAGES, PAIR>;
   CUtensorMap ta, tb;
   int rc;
   if (!A_MN) rc = get_tensor_map_2d(&ta, A, 2, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, BK, BM);
