@@ -505,28 +505,19 @@ __global__ void __launch_bounds__(LT, 8) sample_stream_kernel(const T* __restric
     if (t.w != t.w) t.w = -INFINITY;
     return t;
   };
-  float m = -INFINITY, ssum = 0.f;
+  // pass 1 (HBM): row maximum only — no transcendental work, so the pass runs at memory speed
+  float m = -INFINITY;
   for (int c = threadIdx.x * 4; c < V; c += LT * 4) {
     const float4 t = scaled(load4<T>(xr + c));
-    const float m4 = fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w));
-    const float mn = fmaxf(m, m4);
-    if (mn > -INFINITY) {
-      ssum = ssum * __expf(m - mn) + (__expf(t.x - mn) + __expf(t.y - mn)) + (__expf(t.z - mn) + __expf(t.w - mn));
-      m = mn;
-    }
+    m = fmaxf(m, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
   }
-  // block combine of (m, s)
-  float wm = warp_max(m);
-  float ws = warp_sum(m > -INFINITY ? ssum * __expf(m - wm) : 0.f);
-  if (lane == 0) { red_m[wid] = wm; red_s[wid] = ws; }
+  const float wm = warp_max(m);
+  if (lane == 0) red_m[wid] = wm;
   for (int i = threadIdx.x; i < MAX_V4 * (LT / 32); i += LT) (&wsum[0][0])[i] = 0.f;
   __syncthreads();
   float M = red_m[0];
 #pragma unroll
   for (int w = 1; w < LT / 32; ++w) M = fmaxf(M, red_m[w]);
-  float S = 0.f;
-#pragma unroll
-  for (int w = 0; w < LT / 32; ++w) S += red_m[w] > -INFINITY ? red_s[w] * __expf(red_m[w] - M) : 0.f;
   // pass 2: cell sums in vocabulary order (cell = 128 consecutive logits = one warp's float4s of one 1024-chunk)
   for (int c = threadIdx.x * 4, i = 0; c < V; c += LT * 4, ++i) {
     const float4 t = scaled(load4<T>(xr + c));
@@ -547,7 +538,9 @@ __global__ void __launch_bounds__(LT, 8) sample_stream_kernel(const T* __restric
       const float t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
-    const float target = u * __shfl_sync(0xffffffffu, inc, 31);
+    const float row_total = __shfl_sync(0xffffffffu, inc, 31);      // = sum_v exp(x_v - M), the softmax denominator
+    if (lane == 0) red_s[0] = row_total;
+    const float target = u * row_total;
     const unsigned hit = __ballot_sync(0xffffffffu, own4 > 0.f && inc >= target);
     const unsigned any = __ballot_sync(0xffffffffu, own4 > 0.f);
     const int sl = hit ? (__ffs(hit) - 1) : (any ? 31 - __clz(any) : 0);
@@ -598,7 +591,7 @@ __global__ void __launch_bounds__(LT, 8) sample_stream_kernel(const T* __restric
       }
       if (j_sel < 0) j_sel = j_last;
       ids[row] = c + j_sel;
-      if (scores != nullptr) scores[row] = e[j_sel] / S;
+      if (scores != nullptr) scores[row] = e[j_sel] / red_s[0];
     }
   }
 }
