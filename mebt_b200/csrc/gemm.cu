@@ -55,7 +55,8 @@ struct SmemLayout {
   static constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // pair mode: each CTA holds half of the B tile
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;                           // fp32 bias slice of the current tile
+  static constexpr int TOTAL = BIAS_OFFSET + BN * 4 + 1024;                       // + alignment slack
 };
 
 // PAIR: the two CTAs of a cluster (an SM pair) execute ONE tcgen05.mma.cta_group::2 of shape M=256 x N=BN: each CTA
@@ -243,6 +244,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const bool row_ok = row < p.M;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
+      // stage the tile's bias slice in shared memory once (one L2 round trip per tile instead of one per chunk)
+      float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+      if (p.bias != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");            // the previous tile's readers are done
+        const int t = threadIdx.x - 64;
+        for (int cidx = t; cidx < BN; cidx += 128) s_bias[cidx] = __ldg(p.bias + n0 + cidx);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       const float* my_partials = nullptr;
       if (p.splits > 1) {
         // park the raw accumulator, release TMEM, and find out whether this CTA completes the tile
@@ -298,10 +307,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
         if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
+            const float4 b = b4[j];
             v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
         }
