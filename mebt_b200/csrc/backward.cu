@@ -67,7 +67,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int sl
 template <int MAX_VEC>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx, int accumulate_dx,
+                                     const float* __restrict__ gamma, __nv_bfloat16* dx, const __nv_bfloat16* resid,
                                      int rows, int D, float* __restrict__ partial /* [grid, 2, D] */) {
   extern __shared__ float sm[];   // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
         o.y = rs * (g[i].y - s1 - xh[i].y * s2);
         o.z = rs * (g[i].z - s1 - xh[i].z * s2);
         o.w = rs * (g[i].w - s1 - xh[i].w * s2);
-        if (accumulate_dx) {
-          const float4 old = ld_bf16x4(dx + row * D + c);
+        if (resid != nullptr) {                       // dx = resid + ln'(dy); resid may alias dx (in-place accumulate)
+          const float4 old = ld_bf16x4(resid + row * D + c);
           o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
         }
         st_bf16x4(dx + row * D + c, o);
@@ -260,9 +260,22 @@ constexpr int LNB_GRID = 148 * 2;
 
 size_t layernorm_bwd_workspace_bytes(int D) { return size_t(LNB_GRID) * 2 * D * 4; }
 
+int layernorm_bwd_resid(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                        void* dx, const void* resid, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
+                        float* workspace, size_t ws_bytes, cudaStream_t st);
+
 int layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                   int accumulate_dx, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
                   float* workspace, size_t ws_bytes, cudaStream_t st) {
+  return layernorm_bwd_resid(dy, x, mean, rstd, gamma, dx, accumulate_dx ? dx : nullptr, dgamma, dbeta, accumulate_params,
+                             rows, D, workspace, ws_bytes, st);
+}
+
+// dx = (resid != NULL ? resid : 0) + ln'(dy); resid may be dx itself
+int layernorm_bwd_resid(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                        void* dx, const void* resid, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
+                        float* workspace, size_t ws_bytes, cudaStream_t st) {
+  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(resid);
   MEBT_REQUIRE(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024, MEBT_ERR_SHAPE, "layernorm_bwd: bad shape rows=%d D=%d", rows, D);
   MEBT_REQUIRE(workspace != nullptr && ws_bytes >= layernorm_bwd_workspace_bytes(D), MEBT_ERR_WORKSPACE,
                "layernorm_bwd: workspace too small");
@@ -279,10 +292,10 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx);
   {
-    LaunchScope ls(FAM_LAYERNORM, double(rows) * D * (accumulate_dx ? 8.0 : 6.0), st);
-    if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace));
-    else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<4>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace));
-    else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<8>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, accumulate_dx, rows, D, workspace));
+    LaunchScope ls(FAM_LAYERNORM, double(rows) * D * (rp != nullptr ? 8.0 : 6.0), st);
+    if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, workspace));
+    else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<4>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, workspace));
+    else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<8>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, workspace));
   }
   MEBT_LAUNCH_OK("layernorm_bwd_kernel");
   {

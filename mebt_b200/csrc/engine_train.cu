@@ -23,6 +23,9 @@ int layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const fl
 int layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                   int accumulate_dx, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
                   float* workspace, size_t ws_bytes, cudaStream_t st);
+int layernorm_bwd_resid(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                        void* dx, const void* resid, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
+                        float* workspace, size_t ws_bytes, cudaStream_t st);
 size_t layernorm_bwd_workspace_bytes(int D);
 int colsum(const void* X, int ld, int rows, int N, float* out, int accumulate, float* workspace, size_t ws_bytes,
            cudaStream_t st);
@@ -82,6 +85,26 @@ Plan make_plan(const mebt_layer_t* layers, int n_layers, int B, int L, int NC, i
   return p;
 }
 
+// Weight-gradient GEMMs and bias column sums only consume tensors the data-gradient chain has already produced, so
+// they run on a library-owned side stream, concurrently with the next links of the chain (every GEMM of the 16-frame
+// training step is at most one wave of tiles: two of them fit on the 148 SMs side by side).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t join = nullptr;
+  bool ok = false;
+};
+SideStream& side_stream() {
+  static SideStream s;
+  if (!s.ok && s.stream == nullptr) {
+    bool good = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 4 && good; ++i) good = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+    s.ok = good;
+  }
+  return s;
+}
+
 size_t backward_workspace_bytes(int B, int L, int NC, int NT, int D, int H) {
   const size_t rmax = size_t(B) * size_t(L > NT ? L : NT);
   const size_t rk = size_t(B) * size_t(NC > NT ? (NC > L ? NC : L) : (NT > L ? NT : L));
@@ -93,9 +116,10 @@ size_t backward_workspace_bytes(int B, int L, int NC, int NT, int D, int H) {
   t += al(rmax * D * 2);           // dqn
   t += al(rk * D * 2);             // dkn
   t += al(size_t(B) * H * (L > NT ? L : NT) * 4);   // attention delta
+  t += al(rmax * D * 2);           // dx (kept separate from the stream gradient: the side stream still reads d_out)
   size_t red = layernorm_bwd_workspace_bytes(D);
   const size_t cs = size_t(64) * 16384 * 4;         // column-sum partials up to N = 16384
-  t += al(red > cs ? red : cs);
+  t += 2 * al(red > cs ? red : cs);                 // one reduction scratch per stream
   return t + 4096;
 }
 
@@ -201,15 +225,32 @@ int mebt_stack_backward(const mebt_layer_t* layers, const mebt_layer_grads_t* gr
   void* dkn = take(rkmax * D * 2);
   const size_t delta_bytes = size_t(B) * H * (L > NT ? L : NT) * 4;
   void* delta = take(delta_bytes);
-  const size_t red_bytes = workspace_bytes - off - 256;
+  void* dxb = take(rmax * D * 2);
+  const size_t red_each = ((workspace_bytes - off - 512) / 2) & ~size_t(255);
+  const size_t red_bytes = red_each;
   float* red = reinterpret_cast<float*>(W + off);
+  float* red_side = reinterpret_cast<float*>(W + off + red_each);
   const int acc = grad_accumulate ? 1 : 0;
+  SideStream& side = side_stream();
+  MEBT_REQUIRE(side.ok, MEBT_ERR_CUDA, "backward: cannot create the weight-gradient side stream");
+  cudaStream_t sst = side.stream;
 
   // weight gradient dW[N_out, K_in] (+)= dY^T X : A = dY stored [rows, N_out] (MN-major), B = X stored [rows, K_in] (MN-major)
-  auto WGRAD = [&](const void* dY, int ld_dy, const void* X, int ldx, float* dWt, int ldw, int n_out, int k_in, int rows,
-                   int accumulate) {
+  auto WGRAD_ON = [&](cudaStream_t on, const void* dY, int ld_dy, const void* X, int ldx, float* dWt, int ldw, int n_out,
+                      int k_in, int rows, int accumulate) {
     return gemm_bf16_aux(dY, ld_dy, 1, X, ldx, 1, dWt, ldw, n_out, k_in, rows, nullptr, nullptr, 0, nullptr, 0,
-                         MEBT_GEMM_OUT_FP32 | (accumulate ? MEBT_GEMM_ACCUMULATE : 0), st);
+                         MEBT_GEMM_OUT_FP32 | (accumulate ? MEBT_GEMM_ACCUMULATE : 0), on);
+  };
+  auto WGRAD = [&](const void* dY, int ld_dy, const void* X, int ldx, float* dWt, int ldw, int n_out, int k_in, int rows,
+                   int accumulate) { return WGRAD_ON(st, dY, ld_dy, X, ldx, dWt, ldw, n_out, k_in, rows, accumulate); };
+  // weight + bias gradient of one nn.Linear on the side stream, after everything recorded so far on the main stream
+  auto SIDE_LINEAR = [&](int slot, const void* dY, int ld_dy, const void* X, int ldx, float* dWt, int ldw, float* db,
+                         int n_out, int k_in, int rows, int accumulate) -> int {
+    MEBT_CUDA_OK(cudaEventRecord(side.fork[slot], st));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(sst, side.fork[slot], 0));
+    int rc2 = WGRAD_ON(sst, dY, ld_dy, X, ldx, dWt, ldw, n_out, k_in, rows, accumulate);
+    if (rc2) return rc2;
+    return colsum(dY, ld_dy, rows, n_out, db, accumulate, red_side, red_bytes, sst);
   };
   // data gradient dX[rows, K_in] = dY[rows, N_out] W[N_out, K_in] : B = W stored [K_red = N_out, N = K_in] (MN-major)
   auto DGRAD = [&](const void* dY, int ld_dy, const void* Wt, int ldw, void* dX, int rows, int k_in, int n_out,
@@ -271,22 +312,19 @@ int mebt_stack_backward(const mebt_layer_t* layers, const mebt_layer_grads_t* gr
     void* d_k_stream = mode == MEBT_MODE_LATENT_ENC ? d_ctx : mode == MEBT_MODE_LATENT_DEC ? d_lat : mode == MEBT_MODE_LT2L ? d_tgt : nullptr;
     const int rq = s.rq, rk = s.rk;
 
-    // ---- MLP ----
+    // ---- MLP ----  (main stream: the data-gradient chain; side stream: weight and bias gradients)
+    TRY(SIDE_LINEAR(0, d_out, D, S + s.u, 4 * D, g.w_fc2, 4 * D, g.b_fc2, D, 4 * D, rq, acc));
     TRY(DGRAD(d_out, D, w.w_fc2, 4 * D, da, rq, 4 * D, D, nullptr, S + s.a, 4 * D, MEBT_GEMM_DGELU));     // da
-    TRY(WGRAD(d_out, D, S + s.u, 4 * D, g.w_fc2, 4 * D, D, 4 * D, rq, acc));
-    TRY(colsum(d_out, D, rq, D, g.b_fc2, acc, red, red_bytes, st));
+    TRY(SIDE_LINEAR(1, da, 4 * D, S + s.h, D, g.w_fc1, D, g.b_fc1, 4 * D, D, rq, acc));
     TRY(DGRAD(da, 4 * D, w.w_fc1, D, dh, rq, D, 4 * D, nullptr, nullptr, 0, 0));                            // dh
-    TRY(WGRAD(da, 4 * D, S + s.h, D, g.w_fc1, D, 4 * D, D, rq, acc));
-    TRY(colsum(da, 4 * D, rq, 4 * D, g.b_fc1, acc, red, red_bytes, st));
-    // dx = d_out + ln2'(dh), in place in the stream-gradient buffer
-    TRY(layernorm_bwd(dh, S + s.x, reinterpret_cast<float*>(S + s.x_mean), reinterpret_cast<float*>(S + s.x_rstd), w.ln2_w,
-                      d_out, 1, g.ln2_w, g.ln2_b, acc, rq, D, red, red_bytes, st));
-    void* dx = d_out;
+    // dx = d_out + ln2'(dh), written to its own buffer (d_out is still being read by the side stream)
+    void* dx = dxb;
+    TRY(layernorm_bwd_resid(dh, S + s.x, reinterpret_cast<float*>(S + s.x_mean), reinterpret_cast<float*>(S + s.x_rstd),
+                            w.ln2_w, dx, d_out, g.ln2_w, g.ln2_b, acc, rq, D, red, red_bytes, st));
     // ---- attention output projection ----
     void* datt = dh;
+    TRY(SIDE_LINEAR(2, dx, D, S + s.att, D, g.w_proj, D, g.b_proj, D, D, rq, acc));
     TRY(DGRAD(dx, D, w.w_proj, D, datt, rq, D, D, nullptr, nullptr, 0, 0));
-    TRY(WGRAD(dx, D, S + s.att, D, g.w_proj, D, D, D, rq, acc));
-    TRY(colsum(dx, D, rq, D, g.b_proj, acc, red, red_bytes, st));
     // ---- attention ----
     const int nk_sep = rk / B;
     const float* lse = reinterpret_cast<float*>(S + s.lse);
@@ -300,18 +338,20 @@ int mebt_stack_backward(const mebt_layer_t* layers, const mebt_layer_grads_t* gr
                                     0, 0, B, H, s.nq, 64, delta, delta_bytes, stream));
     // ---- q/k/v projections ----
     const int qw = fused ? 3 * D : D;
-    TRY(DGRAD(dqkv, qw, wqkv, D, dqn, rq, D, qw, dx, nullptr, 0, 0));                                       // dqn = dx + dQKV Wqkv
-    TRY(WGRAD(dqkv, qw, S + s.qn, D, g.w_qkv, D, qw, D, rq, acc));
-    TRY(colsum(dqkv, qw, rq, qw, g.b_qkv, acc, red, red_bytes, st));
-    if (rk > 0) {
-      TRY(DGRAD(dkv, 2 * D, w_kv, D, dkn, rk, D, 2 * D, nullptr, nullptr, 0, 0));
-      TRY(WGRAD(dkv, 2 * D, S + s.kn, D, g.w_qkv + size_t(D) * D, D, 2 * D, D, rk, fused ? 1 : acc));
-      TRY(colsum(dkv, 2 * D, rk, 2 * D, g.b_qkv + D, fused ? 1 : acc, red, red_bytes, st));
+    TRY(SIDE_LINEAR(3, dqkv, qw, S + s.qn, D, g.w_qkv, D, g.b_qkv, qw, D, rq, acc));
+    if (rk > 0) {   // same side stream, after the q-side gradients: they may accumulate into the same rows (lt2l)
+      TRY(WGRAD_ON(sst, dkv, 2 * D, S + s.kn, D, g.w_qkv + size_t(D) * D, D, 2 * D, D, rk, fused ? 1 : acc));
+      TRY(colsum(dkv, 2 * D, rk, 2 * D, g.b_qkv + D, fused ? 1 : acc, red_side, red_bytes, sst));
     } else if (!fused && !acc) {
       // latent_enc with no context: key/value projections receive exact-zero gradients
-      MEBT_CUDA_OK(cudaMemsetAsync(g.w_qkv + size_t(D) * D, 0, size_t(2) * D * D * 4, st));
-      MEBT_CUDA_OK(cudaMemsetAsync(g.b_qkv + D, 0, size_t(2) * D * 4, st));
+      MEBT_CUDA_OK(cudaMemsetAsync(g.w_qkv + size_t(D) * D, 0, size_t(2) * D * D * 4, sst));
+      MEBT_CUDA_OK(cudaMemsetAsync(g.b_qkv + D, 0, size_t(2) * D * 4, sst));
     }
+    TRY(DGRAD(dqkv, qw, wqkv, D, dqn, rq, D, qw, dx, nullptr, 0, 0));                                       // dqn = dx + dQKV Wqkv
+    if (rk > 0) TRY(DGRAD(dkv, 2 * D, w_kv, D, dkn, rk, D, 2 * D, nullptr, nullptr, 0, 0));
+    // the side stream must be done with d_out / da / dx / dqkv / dkv before they are overwritten
+    MEBT_CUDA_OK(cudaEventRecord(side.join, sst));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0));
     // ---- ln1 on both streams ----
     TRY(layernorm_bwd(dqn, q_in, reinterpret_cast<float*>(S + s.q_mean), reinterpret_cast<float*>(S + s.q_rstd), w.ln1_w,
                       d_out, 0, g.ln1_w, g.ln1_b, acc, rq, D, red, red_bytes, st));                        // assigns d(q stream)

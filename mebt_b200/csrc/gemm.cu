@@ -459,18 +459,22 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
 // Split-K scratch: the only device memory the library owns (partials are consumed inside the launch that wrote
 // them; the per-tile counters are returned to zero by the CTA that completes the tile).  Launches that use it are
 // ordered by the caller's stream, like every other launch; it is sized once for the largest split-K problem seen.
-struct SplitKWorkspace { float* partials; int* counters; size_t bytes; int n_counters; };
-static SplitKWorkspace* splitk_workspace(size_t need_bytes, int tiles) {
-  static SplitKWorkspace ws = {nullptr, nullptr, 0, 0};
+struct SplitKWorkspace { float* partials; int* counters; cudaStream_t stream; };
+// one scratch area per stream (the training engine overlaps weight-gradient GEMMs on a side stream)
+static SplitKWorkspace* splitk_workspace(size_t need_bytes, int tiles, cudaStream_t stream) {
+  static SplitKWorkspace pool[4] = {};
+  static int used = 0;
   constexpr size_t kMax = size_t(96) << 20;
   if (need_bytes > kMax || tiles > 4096) return nullptr;
-  if (ws.partials == nullptr) {
-    if (cudaMalloc(&ws.partials, kMax) != cudaSuccess) { ws.partials = nullptr; return nullptr; }
-    if (cudaMalloc(&ws.counters, 4096 * sizeof(int)) != cudaSuccess) { ws.counters = nullptr; return nullptr; }
-    cudaMemset(ws.counters, 0, 4096 * sizeof(int));
-    ws.bytes = kMax;
-    ws.n_counters = 4096;
-  }
+  for (int i = 0; i < used; ++i)
+    if (pool[i].stream == stream) return &pool[i];
+  if (used == 4) return nullptr;
+  SplitKWorkspace& ws = pool[used];
+  if (cudaMalloc(&ws.partials, kMax) != cudaSuccess) { ws.partials = nullptr; return nullptr; }
+  if (cudaMalloc(&ws.counters, 4096 * sizeof(int)) != cudaSuccess) { ws.counters = nullptr; return nullptr; }
+  cudaMemset(ws.counters, 0, 4096 * sizeof(int));
+  ws.stream = stream;
+  ++used;
   return &ws;
 }
 
@@ -542,7 +546,7 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
       const int kpb = (p.num_k_blocks + want - 1) / want;
       const int splits = (p.num_k_blocks + kpb - 1) / kpb;
       const size_t need = size_t(tiles) * splits * BM * bn * sizeof(float);
-      SplitKWorkspace* ws = splitk_workspace(need, tiles);
+      SplitKWorkspace* ws = splitk_workspace(need, tiles, stream);
       if (ws != nullptr && splits >= 2) {
         p.splits = splits;
         p.kb_per_split = kpb;
