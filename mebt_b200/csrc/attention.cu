@@ -152,27 +152,68 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const bool full = valid == AT_BKV;            // warp-uniform: only a source's last tile can be ragged
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
-        tmem_ld_wait();
+      // One pass over the S row: p = 2^(s*c - m*c) with the CURRENT running maximum m (no separate max pass), the row
+      // maximum of this tile as a by-product.  m is only advanced when a score exceeds it by more than 8 in the log2
+      // domain (p would exceed 256): the exact result does not depend on the stabiliser, only overflow safety does,
+      // so the usual per-tile max pass, and the rescale of O that follows every small increase of the maximum, are
+      // skipped.  The first tile takes its maximum explicitly.
+      auto row_pass = [&](float mb, float& l_tile, float& mx_tile) {
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (full) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
+          tmem_ld_wait();
+          float pv[32];
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
-        } else {
+            for (int i = 0; i < 32; ++i) {
+              const float sv = __uint_as_float(r[i]);
+              m4[i & 3] = fmaxf(m4[i & 3], sv);
+              pv[i] = ex2_approx(fmaf(sv, p.scale_log2, -mb));
+              l4[i & 3] += pv[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float sv = __uint_as_float(r[i]);
+              const bool ok = c * 32 + i < valid;
+              if (ok) m4[i & 3] = fmaxf(m4[i & 3], sv);
+              pv[i] = ok ? ex2_approx(fmaf(sv, p.scale_log2, -mb)) : 0.f;
+              l4[i & 3] += pv[i];
+            }
+          }
+          // 32 keys = four 16-byte chunks of this row inside one 64-key swizzle atom
+          uint8_t* base = sP + (c >> 1) * AT_TILE_BYTES + row * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(pv[8 * g + 0], pv[8 * g + 1]);
+            u.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
+            u.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
+            u.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
+            const int chunk = (c & 1) * 4 + g;
+            *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = u;
+          }
+        }
+        l_tile = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        mx_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      };
+      if (j == 0) {                                 // explicit maximum of the first tile
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+            if (full || c * 32 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
         }
-        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-      }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = ex2_approx((m - m_new) * p.scale_log2);     // m = -inf on the first tile -> 0
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+        mbar_wait(o_full, (j - 1) & 1);             // PV_{j-1} done: O_{j-1} readable, P buffer reusable
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -183,48 +224,17 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
           for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(r[i]);
         }
       }
-      if (alpha != 1.0f) {                          // the running maximum rarely moves after the first tiles
+      float l_tile, mx_tile;
+      row_pass(m * p.scale_log2, l_tile, mx_tile);
+      if ((mx_tile - m) * p.scale_log2 > 8.0f) {    // rare: re-base on the new maximum and redo this row
+        const float alpha = ex2_approx((m - mx_tile) * p.scale_log2);
 #pragma unroll
         for (int i = 0; i < AT_HS; ++i) o_acc[i] *= alpha;
         l *= alpha;
+        m = mx_tile;
+        row_pass(m * p.scale_log2, l_tile, mx_tile);
       }
-      const float mb = m_new * p.scale_log2;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
-            l4[i & 3] += pv[i];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
-            pv[i] = (c * 32 + i < valid) ? e : 0.f;
-            l4[i & 3] += pv[i];
-          }
-        }
-        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        // 32 keys = four 16-byte chunks of this row inside one 64-key swizzle atom
-        uint8_t* base = sP + (c >> 1) * AT_TILE_BYTES + row * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(pv[8 * g + 0], pv[8 * g + 1]);
-          u.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
-          u.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
-          u.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
-          const int chunk = (c & 1) * 4 + g;
-          *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = u;
-        }
-      }
-      m = m_new;
+      l += l_tile;
       tc_fence_before();
       fence_proxy_async_smem();       // make the st.shared P tile visible to the tensor-core (async) proxy
       mbar_arrive(p_full);
