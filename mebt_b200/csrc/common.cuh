@@ -45,6 +45,10 @@ int cuda_fail(cudaError_t e, const char* what);
 int get_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
+// 3-D slab view: one box = `slabs` adjacent 128-byte-wide column slabs of `box_outer` rows (see runtime.cu)
+int get_tensor_map_slabs(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                         uint64_t row_stride_bytes, uint32_t box_outer, uint32_t slabs);
+
 int sm_count();
 
 // ---- lightweight in-library accounting (bench.py's gpu_launches and per-kernel roofline numbers) ----------
@@ -181,6 +185,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D (slab view) tile load: c0 = element inside the 128-byte slab (0), c1 = row, c2 = slab index
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // multicast tile load: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each
 // destination CTA's mbarrier (same offset) receives the complete_tx for the bytes it got
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -246,6 +257,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
+}
+// C (global, through the tensor map's dtype) += tile in shared memory
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// at most N of this thread's most recent bulk groups may still be reading their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -327,6 +349,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but naming the registers an earlier (still in flight) tcgen05.ld targets as read-write operands, so the
+// compiler cannot schedule a use of them above the wait when other work sits between the load and the wait.
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // ---- small numeric helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
@@ -358,6 +391,59 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // d/dx of the erf GELU: Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
+// ---- packed (f32x2) GELU for the GEMM epilogues ----
+// erf(x / sqrt(2)) = x * P(x^2) / Q(x^2) on |x| <= 4 sqrt(2) (the rational minimax form used by Eigen/XLA for float
+// erf, rescaled so that it takes x rather than x / sqrt(2)); |erf error| < 5e-7, |gelu error| < 2e-6 over all x — the
+// result is rounded to bf16 (2^-9 relative) right after.  Two elements per FFMA2: 11 issue slots per element against
+// ~28 for the erff() path, which made the fc1 epilogue as long as its main loop.
+namespace gelu_detail {
+constexpr double kS = 0.70710678118654752440;
+constexpr float kA6 = float(-2.72614225801306e-10 * kS / 64.0), kA5 = float(2.77068142495902e-08 * kS / 32.0),
+                kA4 = float(-2.10102402082508e-06 * kS / 16.0), kA3 = float(-5.69250639462346e-05 * kS / 8.0),
+                kA2 = float(-7.34990630326855e-04 * kS / 4.0), kA1 = float(-2.95459980854025e-03 * kS / 2.0),
+                kA0 = float(-1.60960333262415e-02 * kS);
+constexpr float kB4 = float(-1.45660718464996e-05 / 16.0), kB3 = float(-2.13374055278905e-04 / 8.0),
+                kB2 = float(-1.68282697438203e-03 / 4.0), kB1 = float(-7.37332916720468e-03 / 2.0),
+                kB0 = float(-1.42647390514189e-02);
+constexpr float kClamp = 5.65685424949238f;   // 4 sqrt(2)
+}  // namespace gelu_detail
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// erf(x / sqrt(2)) for two values
+__device__ __forceinline__ float2 erf_rsqrt2_x2(float2 x) {
+  using namespace gelu_detail;
+  x.x = fminf(fmaxf(x.x, -kClamp), kClamp);
+  x.y = fminf(fmaxf(x.y, -kClamp), kClamp);
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 p = __ffma2_rn(splat2(kA6), x2, splat2(kA5));
+  p = __ffma2_rn(p, x2, splat2(kA4));
+  p = __ffma2_rn(p, x2, splat2(kA3));
+  p = __ffma2_rn(p, x2, splat2(kA2));
+  p = __ffma2_rn(p, x2, splat2(kA1));
+  p = __ffma2_rn(p, x2, splat2(kA0));
+  p = __fmul2_rn(p, x);
+  float2 q = __ffma2_rn(splat2(kB4), x2, splat2(kB3));
+  q = __ffma2_rn(q, x2, splat2(kB2));
+  q = __ffma2_rn(q, x2, splat2(kB1));
+  q = __ffma2_rn(q, x2, splat2(kB0));
+  float2 rq;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq.x) : "f"(q.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq.y) : "f"(q.y));
+  return __fmul2_rn(p, rq);
+}
+__device__ __forceinline__ float2 gelu_erf_x2(float2 x) {
+  const float2 h = __fmul2_rn(x, splat2(0.5f));
+  return __ffma2_rn(h, erf_rsqrt2_x2(x), h);              // 0.5 x (1 + erf)
+}
+// d/dx of the erf GELU for two values: Phi(x) + x phi(x)
+__device__ __forceinline__ float2 gelu_erf_grad_x2(float2 x) {
+  const float2 e = erf_rsqrt2_x2(x);
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 g;                                                // exp(-x^2 / 2) = 2^(-x^2 * log2(e) / 2)
+  g.x = ex2_approx(x2.x * -0.72134752044448170368f);
+  g.y = ex2_approx(x2.y * -0.72134752044448170368f);
+  const float2 phi = __fmul2_rn(__fmul2_rn(x, splat2(0.39894228040143267794f)), g);
+  return __fadd2_rn(__ffma2_rn(e, splat2(0.5f), splat2(0.5f)), phi);
 }
 #endif  // __CUDACC__
 

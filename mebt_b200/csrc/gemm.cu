@@ -26,6 +26,15 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 
+// Epilogue staging: a ring of EPI_SLOTS slots of [128 rows x 128 bytes] (64 bf16 or 32 fp32 columns of the tile's
+// 128 accumulator rows, 128B-swizzled; each epilogue warp fills its 32 rows).  Results leave through ONE TMA store per
+// slot (full 128-byte lines instead of 32 scattered 16-byte pieces per store instruction; the TMA unit costs ~190 clk
+// per box on top of ~1 clk per row, so few large boxes) and a residual / saved pre-activation operand arrives through
+// TMA loads issued up to three slots ahead; both were what the MMA issuer ended up waiting for before.
+constexpr int RASTER_M = 16;           // row blocks (pair mode: row-block pairs) per rasterisation band
+constexpr int EPI_SLOTS = 4;
+constexpr int EPI_SLOT_BYTES = 128 * 128;
+
 struct GemmParams {
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_k_blocks;
@@ -40,6 +49,7 @@ struct GemmParams {
   __nv_bfloat16* aux;                  // gelu: optional pre-activation output; dgelu: pre-activation input
   int ldaux;
   int dgelu;                           // result *= gelu'(aux)
+  int in_kind;                         // operand read by the epilogue through TMA: 0 none, 1 residual, 2 dgelu aux
   // split-K: `splits` CTAs share one output tile; each writes its fp32 partial accumulator to `partials`
   // ([tile][split][128][BN]) and the last one to arrive (per-tile counter) sums them in split order and runs the
   // epilogue.  Deterministic: the summation order does not depend on arrival order.
@@ -48,15 +58,40 @@ struct GemmParams {
   float* partials;
   int* counters;
   int pair;                            // host-side only: launch the cta_group::2 (SM pair) variant
+#ifdef MEBT_GEMM_TRACE
+  long long* trace;                    // [grid][8] cycle counters (tools/gemm_bench.cu)
+#endif
 };
+
+// Role-level cycle accounting for tools/gemm_bench.cu (compiled out of the library build).
+#ifdef MEBT_GEMM_TRACE
+#define TR_DECL long long tr_t = 0, tr_start = clock64(), tr_acc[6] = {0, 0, 0, 0, 0, 0}
+#define TR_BEGIN tr_t = clock64()
+#define TR_END(i) tr_acc[i] += clock64() - tr_t
+#define TR_FLUSH(base, n)                                                                  \
+  do {                                                                                     \
+    if (p.trace != nullptr) {                                                              \
+      for (int _i = 0; _i < (n); ++_i) p.trace[blockIdx.x * 8 + (base) + _i] = tr_acc[_i]; \
+      p.trace[blockIdx.x * 8 + (base) + (n)] = clock64() - tr_start;                       \
+    }                                                                                      \
+  } while (0)
+long long* g_gemm_trace = nullptr;
+#else
+#define TR_DECL
+#define TR_BEGIN
+#define TR_END(i)
+#define TR_FLUSH(base, n)
+#endif
 
 template <int BN, int STAGES, bool PAIR = false>
 struct SmemLayout {
   static constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // pair mode: each CTA holds half of the B tile
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;                           // fp32 bias slice of the current tile
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;                         // epilogue staging (TMA store / load)
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_SLOTS * EPI_SLOT_BYTES;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;                           // fp32 bias slice of the current tile
   static constexpr int TOTAL = BIAS_OFFSET + BN * 4 + 1024;                       // + alignment slack
+  static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
 // PAIR: the two CTAs of a cluster (an SM pair) execute ONE tcgen05.mma.cta_group::2 of shape M=256 x N=BN: each CTA
@@ -70,7 +105,8 @@ struct SmemLayout {
 template <int BN, bool A_MN, bool B_MN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_aux,
+                 const __grid_constant__ CUtensorMap tma_in, const GemmParams p) {
   using L = SmemLayout<BN, STAGES, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,7 +114,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* epi_bar = tmem_empty_bar + 2;                       // [EPI_SLOTS]: staged input operand landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_bar + EPI_SLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,16 +126,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int num_work = PAIR ? pair_m * p.num_n_blocks : p.num_m_blocks * p.num_n_blocks * p.splits;
   const int work0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
   const int work_stride = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
+  // Rasterisation: bands of RASTER_M row blocks (2048 rows), inside a band the row block runs fastest, then the
+  // column block.  The tiles in flight at any time then touch one or two bands of A (<= 16 MiB at K = 4096) and the
+  // whole of B, which stay in L2; sweeping all of M per column block streamed A from HBM once per column block
+  // (16x at 131072 x 4096 x 1024, which made that GEMM HBM-bound).
+  auto raster = [&](int t, int rows_m, int& mi, int& ni) {
+    const int band_tiles = RASTER_M * p.num_n_blocks;
+    const int band = t / band_tiles;
+    const int in_band = t - band * band_tiles;
+    const int band_rows = min(RASTER_M, rows_m - band * RASTER_M);
+    ni = in_band / band_rows;
+    mi = band * RASTER_M + (in_band - ni * band_rows);
+  };
   auto tile_origin = [&](int work, int& m0, int& n0, int& tile) {
+    int mi, ni;
     if (PAIR) {
       tile = work;
-      m0 = (2 * (work % pair_m) + pair_rank) * BM;
-      n0 = (work / pair_m) * BN;
+      raster(work, pair_m, mi, ni);
+      m0 = (2 * mi + pair_rank) * BM;
     } else {
       tile = work / p.splits;
-      m0 = (tile % p.num_m_blocks) * BM;
-      n0 = (tile / p.num_m_blocks) * BN;
+      raster(tile, p.num_m_blocks, mi, ni);
+      m0 = mi * BM;
     }
+    n0 = ni * BN;
   };
   int* split_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);
   constexpr uint32_t TMEM_COLS = 2 * BN;   // 128, 256 or 512 (power of two >= 32)
@@ -106,6 +157,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tma_a);
     prefetch_tensormap(&tma_b);
+    prefetch_tensormap(&tma_c);
+    for (int s = 0; s < EPI_SLOTS; ++s) mbar_init(&epi_bar[s], 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -138,6 +191,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      TR_DECL;
       for (int work = work0; work < num_work; work += work_stride) {
         int m0, n0, tile;
         tile_origin(work, m0, n0, tile);
@@ -145,7 +199,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
+          TR_BEGIN;
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          TR_END(0);
           uint8_t* sA = smem + stage * L::STAGE_BYTES;
           uint8_t* sB = sA + A_TILE_BYTES;
           if constexpr (PAIR) {
@@ -186,6 +242,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      TR_FLUSH(0, 1);
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -194,17 +251,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      TR_DECL;
       for (int work = work0; work < num_work; work += work_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const int split = PAIR ? 0 : work % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        TR_BEGIN;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue drained this accumulator
+        TR_END(1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
+          TR_BEGIN;
           mbar_wait(&full_bar[stage], phase);
+          TR_END(0);
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sB = sA + A_TILE_BYTES;
@@ -229,10 +291,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      TR_FLUSH(2, 2);
     }
   } else {
     // ================= epilogue (warps 2..5) =================
+    TR_DECL;
     const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
+    uint8_t* slots = smem + L::EPI_OFFSET;
+    uint64_t* in_full = epi_bar;
+    const bool epi_t0 = threadIdx.x == 64;                    // issues the epilogue's TMA traffic
+    const bool tma_epi = p.splits == 1;
+    const bool f32 = p.out_fp32 != 0;
+    const bool aux_out = p.gelu && p.aux != nullptr;
+    const bool k_gelu = p.gelu != 0;
+    const int k_in = p.in_kind;
+    const int och_per_tile = f32 ? BN / 32 : BN / 64;         // 128-byte output chunks per tile row
+    const int my_tiles = work0 < num_work ? (num_work - work0 + work_stride - 1) / work_stride : 0;
+    const int total_och = my_tiles * och_per_tile;
+    // global coordinates of output chunk g (chunks are numbered across the CTA's tiles)
+    auto och_coords = [&](int g, int& r0, int& c0) {
+      int m0, n0, tile;
+      tile_origin(work0 + (g / och_per_tile) * work_stride, m0, n0, tile);
+      r0 = m0;
+      c0 = n0 + (g % och_per_tile) * (f32 ? 32 : 64);
+    };
+    auto issue_in = [&](int g) {                              // epi_t0: fetch the input operand of chunk g into its slot
+      int r0, c0;
+      och_coords(g, r0, c0);
+      mbar_arrive_expect_tx(&in_full[g & 3], EPI_SLOT_BYTES);
+      tma_load_2d(slots + (g & 3) * EPI_SLOT_BYTES, &tma_in, &in_full[g & 3], c0, r0);
+    };
+    if (tma_epi && k_in != 0 && epi_t0)
+      for (int g = 0; g < 3 && g < total_och; ++g) issue_in(g);
     int it = 0;
     for (int work = work0; work < num_work; work += work_stride, ++it) {
       const int acc = it & 1;
@@ -242,16 +332,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int split = PAIR ? 0 : work % p.splits;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
       // stage the tile's bias slice in shared memory once (one L2 round trip per tile instead of one per chunk)
       float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+      TR_BEGIN;
       if (p.bias != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");            // the previous tile's readers are done
         const int t = threadIdx.x - 64;
         for (int cidx = t; cidx < BN; cidx += 128) s_bias[cidx] = __ldg(p.bias + n0 + cidx);
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      TR_END(5);
+      TR_BEGIN;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      TR_END(0);
+      tc_fence_after();
       const float* my_partials = nullptr;
       if (p.splits > 1) {
         // park the raw accumulator, release TMEM, and find out whether this CTA completes the tile
@@ -282,30 +376,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         __threadfence();
         my_partials = p.partials + size_t(tile) * p.splits * BM * BN + size_t(q * 32 + lane) * 4;
       }
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      // One 32-column chunk of this thread's row: bias, GELU / GELU', residual, store.
+      auto finish_chunk = [&](float (&v)[32], int c) {
         const int col = n0 + c * 32;
-        float v[32];
-        if (my_partials == nullptr) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          for (int sp = 0; sp < p.splits; ++sp) {              // fixed order: bitwise reproducible
-            const float4* i4 = reinterpret_cast<const float4*>(my_partials + size_t(sp) * BM * BN) + c * 8 * 128;
-            float4 t[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) t[j] = __ldcg(i4 + j * 128);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[4 * j + 0] += t[j].x; v[4 * j + 1] += t[j].y; v[4 * j + 2] += t[j].z; v[4 * j + 3] += t[j].w;
-            }
-          }
-        }
         if (p.bias != nullptr) {
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
@@ -328,18 +401,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 16; ++j) {
+            const float2 g = gelu_erf_x2(make_float2(v[2 * j], v[2 * j + 1]));
+            v[2 * j] = g.x; v[2 * j + 1] = g.y;
+          }
         }
         if (p.dgelu && row_ok) {
           const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.ldaux + col);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 u = __ldg(a4 + j);
-            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-            v[8 * j + 0] *= gelu_erf_grad(a.x); v[8 * j + 1] *= gelu_erf_grad(a.y);
-            v[8 * j + 2] *= gelu_erf_grad(b.x); v[8 * j + 3] *= gelu_erf_grad(b.y);
-            v[8 * j + 4] *= gelu_erf_grad(c2.x); v[8 * j + 5] *= gelu_erf_grad(c2.y);
-            v[8 * j + 6] *= gelu_erf_grad(d.x); v[8 * j + 7] *= gelu_erf_grad(d.y);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 g = gelu_erf_grad_x2(unpack_bf16x2(w[t]));
+              v[8 * j + 2 * t] *= g.x; v[8 * j + 2 * t + 1] *= g.y;
+            }
           }
         }
         if (row_ok) {
@@ -380,13 +457,154 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         }
-      }
-      if (p.splits == 1) {
-        tc_fence_before();
-        if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
-        else mbar_arrive(&tmem_empty_bar[acc]);
+      };
+      // One 32-column unit of this thread's row through the staging ring (TMA epilogue).
+      auto staged_unit = [&](const uint32_t (&r)[32], int u) {
+        const int gu = it * (BN / 32) + u;                     // unit counter across this CTA's tiles
+        const int g = f32 ? gu : gu >> 1;                      // output chunk it belongs to
+        const int half = f32 ? 0 : (u & 1);
+        const int s_c = aux_out ? (2 * g) & 3 : g & 3;
+        const int sw = lane & 7;
+        uint8_t* row_c = slots + s_c * EPI_SLOT_BYTES + (q * 32 + lane) * 128;
+        if ((f32 || half == 0) && k_in != 0) {
+          TR_BEGIN;
+          mbar_wait(&in_full[s_c], (g >> 2) & 1);              // this chunk's residual / pre-activation has landed
+          TR_END(1);
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + u * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (k_gelu) {
+          if (aux_out) {                                       // keep the pre-activation for the backward pass
+            uint8_t* row_a = slots + ((2 * g + 1) & 3) * EPI_SLOT_BYTES + (q * 32 + lane) * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(row_a + (((half * 4 + j) ^ sw) << 4)) = o;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 gl = gelu_erf_x2(make_float2(v[2 * j], v[2 * j + 1]));
+            v[2 * j] = gl.x; v[2 * j + 1] = gl.y;
+          }
+        }
+        if (k_in != 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 w4 = *reinterpret_cast<const uint4*>(row_c + (((half * 4 + j) ^ sw) << 4));
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x = unpack_bf16x2(w[t]);
+              if (k_in == 2) {
+                const float2 gg = gelu_erf_grad_x2(x);
+                v[8 * j + 2 * t] *= gg.x; v[8 * j + 2 * t + 1] *= gg.y;
+              } else {
+                v[8 * j + 2 * t] += x.x; v[8 * j + 2 * t + 1] += x.y;
+              }
+            }
+          }
+        }
+        if (f32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(row_c + ((j ^ sw) << 4)) = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(row_c + (((half * 4 + j) ^ sw) << 4)) = o;
+          }
+        }
+        if (f32 || half == 1) {
+          // One barrier per chunk: behind it every row of the slot is written (and fenced towards the async proxy), and
+          // the slot the NEXT chunk writes has been read out by its previous store (epi_t0 checks before arriving).
+          TR_BEGIN;
+          fence_proxy_async_smem();
+          if (epi_t0 && k_in == 0) { if (aux_out) tma_store_wait_read<0>(); else tma_store_wait_read<2>(); }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          TR_END(2);
+          TR_BEGIN;
+          if (epi_t0) {
+            int r0, c0;
+            och_coords(g, r0, c0);
+            if (p.accumulate) tma_reduce_add_2d(&tma_c, slots + s_c * EPI_SLOT_BYTES, c0, r0);
+            else tma_store_2d(&tma_c, slots + s_c * EPI_SLOT_BYTES, c0, r0);
+            if (aux_out) tma_store_2d(&tma_aux, slots + ((2 * g + 1) & 3) * EPI_SLOT_BYTES, c0, r0);
+            tma_store_commit();
+            if (k_in != 0 && g + 3 < total_och) {
+              tma_store_wait_read<1>();                        // chunk g-1's store has released the slot chunk g+3 reuses
+              issue_in(g + 3);
+            }
+          }
+          TR_END(3);
+        }
+      };
+      if (my_partials == nullptr) {
+        // software pipeline over the accumulator: the TMEM load of unit u+1 is in flight while unit u is finished
+        const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(t_acc, ra);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c += 2) {
+          TR_BEGIN;
+          tmem_ld_wait_regs(ra);
+          TR_END(4);
+          tmem_ld_32x32(t_acc + uint32_t((c + 1) * 32), rb);
+          staged_unit(ra, c);
+          TR_BEGIN;
+          tmem_ld_wait_regs(rb);
+          TR_END(4);
+          if (c + 2 < BN / 32) tmem_ld_32x32(t_acc + uint32_t((c + 2) * 32), ra);
+          else {                                   // accumulator fully read: hand it back before the last stores
+            tc_fence_before();
+            if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          staged_unit(rb, c + 1);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          for (int sp = 0; sp < p.splits; ++sp) {              // fixed order: bitwise reproducible
+            const float4* i4 = reinterpret_cast<const float4*>(my_partials + size_t(sp) * BM * BN) + c * 8 * 128;
+            float4 t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = __ldcg(i4 + j * 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j + 0] += t[j].x; v[4 * j + 1] += t[j].y; v[4 * j + 2] += t[j].z; v[4 * j + 3] += t[j].w;
+            }
+          }
+          finish_chunk(v, c);
+        }
       }
     }
+    if (tma_epi && epi_t0) tma_store_wait0();                  // all of the CTA's stores have been written
+    if (threadIdx.x == 64) TR_FLUSH(5, 1);
+#ifdef MEBT_GEMM_TRACE
+    if (threadIdx.x == 64 && p.trace != nullptr) for (int _i = 1; _i < 6; ++_i) p.trace[148 * 8 + blockIdx.x * 5 + _i - 1] = tr_acc[_i];
+#endif
   }
 
   tc_fence_before();
@@ -401,7 +619,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
 template <int BN, bool A_MN, bool B_MN, bool PAIR>
 int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda, int ldb, cudaStream_t stream) {
-  constexpr int STAGES = PAIR ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  // 64 KiB of the 227 KiB go to the epilogue staging ring; the rest is the operand ring
+  constexpr int STAGES = PAIR ? (BN == 256 ? 5 : 6) : ((BN == 256) ? 3 : (BN == 128 ? 5 : 6));
   using L = SmemLayout<BN, STAGES, PAIR>;
   CUtensorMap ta, tb;
   int rc;
@@ -412,6 +631,20 @@ int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda,
   if (!B_MN) rc = get_tensor_map_2d(&tb, B, 2, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, BK, PAIR ? BN / 2 : BN);
   else       rc = get_tensor_map_2d(&tb, B, 2, uint64_t(p.N), uint64_t(p.K), uint64_t(ldb) * 2, 64, BK);
   if (rc) return rc;
+  // epilogue operands: 128-byte-wide boxes of the tile's 128 rows (one per chunk)
+  CUtensorMap tc = ta, taux = ta, tin = ta;
+  if (p.splits == 1) {
+    if (p.out_fp32) rc = get_tensor_map_2d(&tc, p.C, 4, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldc) * 4, 32, 128);
+    else            rc = get_tensor_map_2d(&tc, p.C, 2, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldc) * 2, 64, 128);
+    if (rc) return rc;
+    if (p.gelu && p.aux != nullptr) {
+      rc = get_tensor_map_2d(&taux, p.aux, 2, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldaux) * 2, 64, 128);
+      if (rc) return rc;
+    }
+    if (p.in_kind == 1) rc = get_tensor_map_2d(&tin, p.residual, 2, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldres) * 2, 64, 128);
+    if (p.in_kind == 2) rc = get_tensor_map_2d(&tin, p.aux, 2, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldaux) * 2, 64, 128);
+    if (rc) return rc;
+  }
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -423,11 +656,11 @@ int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda,
     const int pairs = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
     int clusters = sm_count() / 2;
     if (clusters > pairs) clusters = pairs;
-    MEBT_CUDA_OK(launch_pdl_cluster2(kern, dim3(2 * clusters), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, p));
+    MEBT_CUDA_OK(launch_pdl_cluster2(kern, dim3(2 * clusters), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, tc, taux, tin, p));
   } else {
     const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    MEBT_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, p));
+    MEBT_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, tc, taux, tin, p));
   }
   MEBT_LAUNCH_OK("gemm_bf16_kernel");
   return MEBT_OK;
@@ -508,6 +741,12 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
   p.dgelu = (flags & MEBT_GEMM_DGELU) ? 1 : 0;
   MEBT_REQUIRE(!p.dgelu || (aux != nullptr && !p.gelu), MEBT_ERR_SHAPE, "gemm: DGELU needs the pre-activation in aux");
   MEBT_REQUIRE(aux == nullptr || ldaux % 8 == 0, MEBT_ERR_SHAPE, "gemm: ldaux must be a multiple of 8");
+  MEBT_REQUIRE(!(p.dgelu && residual != nullptr) && !(out_fp32 && (p.dgelu || residual != nullptr)), MEBT_ERR_UNSUPPORTED,
+               "gemm: the epilogue reads one bf16 operand (residual or gelu' input) and only with bf16 output");
+  p.in_kind = residual != nullptr ? 1 : (p.dgelu ? 2 : 0);
+#ifdef MEBT_GEMM_TRACE
+  p.trace = g_gemm_trace;
+#endif
   p.num_m_blocks = (M + BM - 1) / BM;
   p.num_k_blocks = (K + BK - 1) / BK;
   // Tile width: the widest that divides N (measured: BN=256 wins or ties at every shape of the path, because the
@@ -563,6 +802,10 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
 }
 
 }  // namespace mebt
+
+#ifdef MEBT_GEMM_TRACE
+extern "C" void mebt_gemm_set_trace(long long* buf) { mebt::g_gemm_trace = buf; }
+#endif
 
 extern "C" int mebt_gemm_bf16_aux(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
                                   void* C, int ldc, int M, int N, int K, const float* bias, const void* residual,

@@ -87,7 +87,7 @@ static EncodeTiledFn encode_fn() {
 struct MapKey {
   const void* ptr;
   uint64_t inner, outer, stride;
-  uint32_t box_inner, box_outer, elem;
+  uint32_t box_inner, box_outer, elem, slabs;
   bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -98,6 +98,50 @@ struct MapKeyHash {
     return size_t(h);
   }
 };
+
+// 3-D view of a row-major [outer, inner] matrix as [inner / w][outer][w] with w = 128 bytes of elements, so that ONE
+// box {w, box_outer, slabs} brings `slabs` adjacent 128-byte-wide column slabs of `box_outer` rows, laid out in shared
+// memory slab after slab (each slab = box_outer rows of 128 B, 128B-swizzled).  `inner` must be a multiple of w.
+int get_tensor_map_slabs(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                         uint64_t row_stride_bytes, uint32_t box_outer, uint32_t slabs) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const uint32_t w = 128u / uint32_t(elem_bytes);
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.inner = inner; key.outer = outer; key.stride = row_stride_bytes;
+  key.box_inner = w; key.box_outer = box_outer; key.elem = uint32_t(elem_bytes); key.slabs = slabs;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return MEBT_OK; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  MEBT_REQUIRE(fn != nullptr, MEBT_ERR_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  MEBT_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (row_stride_bytes & 15) == 0, MEBT_ERR_SHAPE,
+               "TMA operand must be 16-byte aligned (ptr=%p stride=%llu)", ptr, (unsigned long long)row_stride_bytes);
+  MEBT_REQUIRE(inner % w == 0 && box_outer >= 1 && box_outer <= 256 && slabs >= 1 && slabs <= 256, MEBT_ERR_SHAPE,
+               "TMA slab view needs inner %% %u == 0 (inner=%llu box_outer=%u slabs=%u)", w, (unsigned long long)inner,
+               box_outer, slabs);
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t dims[3] = {w, outer, inner / w};
+  cuuint64_t strides[2] = {row_stride_bytes, 128};
+  cuuint32_t box[3] = {w, box_outer, slabs};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MEBT_REQUIRE(r == CUDA_SUCCESS, MEBT_ERR_CUDA,
+               "cuTensorMapEncodeTiled(3d) failed (%d) ptr=%p inner=%llu outer=%llu stride=%llu box=%ux%ux%u", int(r), ptr,
+               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, w, box_outer, slabs);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, m);
+  }
+  *out = m;
+  return MEBT_OK;
+}
 
 int get_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
