@@ -6,12 +6,23 @@
 // lt2l's torch.cat([sos_emb, targets]) is never materialised: the kernel walks two K/V sources.
 // NK == 0 (first draft step: no context) yields O = 0, like the empty softmax in the reference.
 //
-// One CTA per (128-query tile, head, batch element), 192 threads:
-//   warp 0    : TMA producer (Q once, then K/V tiles of 128 keys through a 2-deep ring)
-//   warp 1    : tcgen05.mma issuer: S = Q K^T (M128 N128 K64) and O_j = P_j V_j (M128 N64 K128) into TMEM
-//   warps 2-5 : online softmax; one query row per thread, S read from TMEM twice (max pass, exp pass),
-//               P written to shared memory in the 128B-swizzled K-major layout the PV MMA consumes,
-//               O_j folded into a register accumulator with the usual running-max rescale.
+// Persistent CTAs (one per SM, 320 threads) walk a list of work items (batch element, head, PAIR of 128-query tiles):
+//   warp 0    : TMA producer (the item's two Q tiles into a double buffer, K/V tiles of 128 keys through a 3-deep ring)
+//   warp 1    : tcgen05.mma issuer: S_t = Q_t K^T (M128 N128 K64) and O_t = P_t V (M128 N64 K128) into TMEM
+//   warps 2-5 : softmax warpgroup 0 (query tile 2i)      warps 6-9 : softmax warpgroup 1 (query tile 2i+1)
+// Both warpgroups walk the SAME K/V tiles (each tile is loaded once and feeds four MMAs), each with its own
+// S / P / O buffers and running (max, sum, O) state; nothing is merged.  Each softmax thread owns one query row: it
+// reads S from TMEM (the next 32-column chunk is in flight while the current one is exponentiated), writes P (bf16)
+// into the 128B-swizzled K-major shared-memory layout the PV MMA consumes, and folds O_j into a register
+// accumulator.  The exponentials (one per score, 16 / clk / SM on the MUFU pipe) bound the kernel, not the tensor
+// pipe: 128 x 128 scores cost 1024 clk of MUFU against 512 clk of MMA at head_dim 64.  Two measures keep the MUFU
+// pipe busy:
+//   * the warpgroups take TURNS at the row pass (mbarrier hand-off): one exponentiates while the other waits for
+//     its S / PV round trip through the tensor pipe (about 1000 clk), instead of both contending and then both
+//     waiting;
+//   * one exponential in four is evaluated on the FMA pipe (Cody-Waite split + degree-3 polynomial, relative error
+//     7.5e-5, far below the bf16 rounding of P).
+#include <type_traits>
 #include "common.cuh"
 
 namespace mebt {
@@ -20,55 +31,100 @@ namespace {
 constexpr int AT_BQ = 128;
 constexpr int AT_BKV = 128;
 constexpr int AT_HS = 64;
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;      // 16 KiB: a [128 x 64] bf16 tile (Q, K or V)
-constexpr int AT_SMEM_Q = 0;
-constexpr int AT_SMEM_K = AT_TILE_BYTES;                         // 2 stages
-constexpr int AT_SMEM_V = AT_SMEM_K + 2 * AT_TILE_BYTES;         // 2 stages
-constexpr int AT_SMEM_P = AT_SMEM_V + 2 * AT_TILE_BYTES;         // 32 KiB: [128 x 128] bf16
-constexpr int AT_SMEM_BAR = AT_SMEM_P + 2 * AT_TILE_BYTES;
-constexpr int AT_SMEM_TOTAL = AT_SMEM_BAR + 128;
-constexpr uint32_t AT_TMEM_COLS = 256;           // S: [0,128)  O: [128,192)
+constexpr int AT_KV_STAGES = 3;
+constexpr int AT_SMEM_Q = 0;                                     // 2 buffers x 2 query tiles
+constexpr int AT_SMEM_K = AT_SMEM_Q + 4 * AT_TILE_BYTES;
+constexpr int AT_SMEM_V = AT_SMEM_K + AT_KV_STAGES * AT_TILE_BYTES;
+constexpr int AT_SMEM_P = AT_SMEM_V + AT_KV_STAGES * AT_TILE_BYTES;   // 2 warpgroups x [128 x 128] bf16
+constexpr int AT_SMEM_BAR = AT_SMEM_P + 4 * AT_TILE_BYTES;
+constexpr int AT_SMEM_TOTAL = AT_SMEM_BAR + 256;
+constexpr uint32_t AT_TMEM_COLS = 512;           // S_0: [0,128)  S_1: [128,256)  O_0: [256,320)  O_1: [320,384)
+static_assert(AT_SMEM_TOTAL <= 232448, "shared memory budget");
+
+#ifndef MEBT_ATTN_TURN
+#define MEBT_ATTN_TURN -1     // hand the row-pass turn over after this 32-column chunk (0..3); -1: no turn taking
+#endif
+#ifndef MEBT_ATTN_POLY
+#define MEBT_ATTN_POLY 1      // 1: every fourth exponential on the FMA pipe
+#endif
+
+#ifdef MEBT_ATTN_TRACE
+long long* g_attn_trace = nullptr;
+#define ATR_BEGIN tr_t = clock64()
+#define ATR_END(i) tr_acc[i] += clock64() - tr_t
+#else
+#define ATR_BEGIN
+#define ATR_END(i)
+#endif
 
 struct AttnParams {
-  int NQ, NK1, NK2, H;
+  int NQ, NK1, NK2, H, B;
   int q_col0, k1_col0, v1_col0, k2_col0, v2_col0;
   __nv_bfloat16* O;
   int ldo;
   float* lse;              // optional [B, H, NQ]
   float scale_log2;        // log2(e) / sqrt(hs)
   float scale;             // 1 / sqrt(hs)
+  long long* trace;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// 2^x for x <= ~8 on the FMA pipe: n = round(x), f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial, the
+// exponent added as an integer.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float xf = x + 12582912.f;               // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (xf - 12582912.f);
+  float pl = fmaf(0.0551716685f, f, 0.2426111251f);
+  pl = fmaf(pl, f, 0.6932609677f);
+  pl = fmaf(pl, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(xf) << 23));
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
 latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv1,
                             const __grid_constant__ CUtensorMap tm_kv2, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_SMEM_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* q_full = bars + 0;     // [2] Q buffers (a pair of query tiles each)
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;    // [AT_KV_STAGES]
+  uint64_t* kv_empty = bars + 8;   // [AT_KV_STAGES]
+  uint64_t* s_full = bars + 12;    // [2] per warpgroup
+  uint64_t* p_full = bars + 14;    // [2]
+  uint64_t* o_full = bars + 16;    // [2]
+  uint64_t* rp_done = bars + 18;   // [2] row-pass turn hand-off
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tiles1 = (p.NK1 + AT_BKV - 1) / AT_BKV;
   const int tiles2 = (p.NK2 + AT_BKV - 1) / AT_BKV;
   const int nt = tiles1 + tiles2;
+  const int q_tiles = (p.NQ + AT_BQ - 1) / AT_BQ;
+  const int q_pairs = (q_tiles + 1) >> 1;
+  const int n_items = p.B * p.H * q_pairs;
+  const int my_items = int(blockIdx.x) < n_items ? (n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+  // item -> (b, h, query-tile pair); the pair runs fastest so that consecutive CTAs share a (b, h)'s K/V in L2
+  auto item_coords = [&](int n, int& b, int& h, int& qp) {
+    const int item = int(blockIdx.x) + n * int(gridDim.x);
+    qp = item % q_pairs;
+    const int bh = item / q_pairs;
+    h = bh % p.H;
+    b = bh / p.H;
+  };
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tm_q);
     prefetch_tensormap(&tm_kv1);
     prefetch_tensormap(&tm_kv2);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_full[s], 1);
+      mbar_init(&rp_done[s], 128);
+    }
+    for (int s = 0; s < AT_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -79,26 +135,36 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_o = tmem_base + 128;
   griddep_wait();
 
   if (warp == 0) {
     if (lane == 0 && nt > 0) {
-      mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
-      tma_load_2d(smem + AT_SMEM_Q, &tm_q, q_full, p.q_col0 + h * AT_HS, b * p.NQ + qt * AT_BQ);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * AT_TILE_BYTES);
-        if (j < tiles1) {
-          const int r = b * p.NK1 + j * AT_BKV;
-          tma_load_2d(smem + AT_SMEM_K + s * AT_TILE_BYTES, &tm_kv1, &kv_full[s], p.k1_col0 + h * AT_HS, r);
-          tma_load_2d(smem + AT_SMEM_V + s * AT_TILE_BYTES, &tm_kv1, &kv_full[s], p.v1_col0 + h * AT_HS, r);
-        } else {
-          const int r = b * p.NK2 + (j - tiles1) * AT_BKV;
-          tma_load_2d(smem + AT_SMEM_K + s * AT_TILE_BYTES, &tm_kv2, &kv_full[s], p.k2_col0 + h * AT_HS, r);
-          tma_load_2d(smem + AT_SMEM_V + s * AT_TILE_BYTES, &tm_kv2, &kv_full[s], p.v2_col0 + h * AT_HS, r);
+      int gj = 0;                    // K/V tiles loaded by this CTA
+      for (int n = 0; n < my_items; ++n) {
+        int b, h, qp;
+        item_coords(n, b, h, qp);
+        const int qb = n & 1;
+        mbar_wait_backoff(&q_empty[qb], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qb], 2 * AT_TILE_BYTES);
+        // a pair's second tile may lie past the last query row: the rows it reads instead (the next batch element's,
+        // or TMA zero fill past the tensor) are computed and never stored
+        tma_load_2d(smem + AT_SMEM_Q + (2 * qb) * AT_TILE_BYTES, &tm_q, &q_full[qb], p.q_col0 + h * AT_HS,
+                    b * p.NQ + (2 * qp) * AT_BQ);
+        tma_load_2d(smem + AT_SMEM_Q + (2 * qb + 1) * AT_TILE_BYTES, &tm_q, &q_full[qb], p.q_col0 + h * AT_HS,
+                    b * p.NQ + (2 * qp + 1) * AT_BQ);
+        for (int j = 0; j < nt; ++j, ++gj) {
+          const int s = gj % AT_KV_STAGES;
+          mbar_wait_backoff(&kv_empty[s], ((gj / AT_KV_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * AT_TILE_BYTES);
+          if (j < tiles1) {
+            const int r = b * p.NK1 + j * AT_BKV;
+            tma_load_2d(smem + AT_SMEM_K + s * AT_TILE_BYTES, &tm_kv1, &kv_full[s], p.k1_col0 + h * AT_HS, r);
+            tma_load_2d(smem + AT_SMEM_V + s * AT_TILE_BYTES, &tm_kv1, &kv_full[s], p.v1_col0 + h * AT_HS, r);
+          } else {
+            const int r = b * p.NK2 + (j - tiles1) * AT_BKV;
+            tma_load_2d(smem + AT_SMEM_K + s * AT_TILE_BYTES, &tm_kv2, &kv_full[s], p.k2_col0 + h * AT_HS, r);
+            tma_load_2d(smem + AT_SMEM_V + s * AT_TILE_BYTES, &tm_kv2, &kv_full[s], p.v2_col0 + h * AT_HS, r);
+          }
         }
       }
     }
@@ -106,167 +172,212 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     if (lane == 0 && nt > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // P (K-major) x V (MN-major: hs contiguous)
-      const uint32_t sQ = smem_u32(smem + AT_SMEM_Q);
-      const uint32_t sP = smem_u32(smem + AT_SMEM_P);
-      auto issue_s = [&](int j) {
-        const uint32_t sK = smem_u32(smem + AT_SMEM_K + (j & 1) * AT_TILE_BYTES);
+      // step g = 2 * (K/V tile counter) + warpgroup: the two warpgroups' MMAs on one K/V tile are adjacent
+      const int total = my_items * nt * 2;
+      // S_t of step g into warpgroup t's S buffer: legal once that warpgroup has consumed the S of step g-2
+      auto issue_s = [&](int g) {
+        const int gj = g >> 1, t = g & 1;
+        const int n = gj / nt, j = gj - n * nt;
+        if (t == 0) {
+          if (j == 0) mbar_wait(&q_full[n & 1], (n >> 1) & 1);
+          mbar_wait(&kv_full[gj % AT_KV_STAGES], (gj / AT_KV_STAGES) & 1);
+          tc_fence_after();
+        }
+        const uint32_t sQ = smem_u32(smem + AT_SMEM_Q + (2 * (n & 1) + t) * AT_TILE_BYTES);
+        const uint32_t sK = smem_u32(smem + AT_SMEM_K + (gj % AT_KV_STAGES) * AT_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < AT_HS / 16; ++k)
-          umma_bf16_ss(tmem_s, make_smem_desc_sw128(sQ + k * 32, 16, 1024), make_smem_desc_sw128(sK + k * 32, 16, 1024),
-                       idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(s_full);
+          umma_bf16_ss(tmem_base + t * 128, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
+                       make_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
+        if (t == 1 && j == nt - 1) umma_commit(&q_empty[n & 1]);      // the item's last S: its Q buffer is free
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-        mbar_wait(p_full, j & 1);               // softmax(j) done: S consumed, P_j in smem, O_{j-1} consumed
+      if (total > 0) { issue_s(0); issue_s(1); }
+      for (int g = 0; g < total; ++g) {
+        const int t = g & 1, gj = g >> 1;
+        mbar_wait(&p_full[t], gj & 1);   // warpgroup t done with this tile: S_t consumed, P_t in smem, O_t read
         tc_fence_after();
-        if (j + 1 < nt) issue_s(j + 1);         // overlaps softmax(j+1) with PV_j
-        const uint32_t sV = smem_u32(smem + AT_SMEM_V + (j & 1) * AT_TILE_BYTES);
+        if (g + 2 < total) issue_s(g + 2);       // overlaps the warpgroup's next softmax with this tile's PV
+        const uint32_t sV = smem_u32(smem + AT_SMEM_V + (gj % AT_KV_STAGES) * AT_TILE_BYTES);
+        const uint32_t sP = smem_u32(smem + AT_SMEM_P + t * 2 * AT_TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < AT_BKV / 16; ++kk) {
           const uint64_t da = make_smem_desc_sw128(sP + (kk >> 2) * AT_TILE_BYTES + (kk & 3) * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sV + kk * 2048, 64 * 128, 1024);
-          umma_bf16_ss(tmem_o, da, db, idesc_o, kk != 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_base + 256 + t * 64, da, db, idesc_o, kk != 0 ? 1u : 0u);
         }
-        umma_commit(&kv_empty[j & 1]);
-        umma_commit(o_full);
+        umma_commit(&o_full[t]);
+        if (t == 1) umma_commit(&kv_empty[gj % AT_KV_STAGES]);   // both warpgroups' S and PV of this K/V stage are done
       }
     }
   } else {
-    // ===== softmax warps =====
-    const int q = warp & 3;
+    // ===== softmax warpgroups =====
+    const int t = (warp - 2) >> 2;                // warpgroup: query tile 2 * pair + t
+    const int q = warp & 3;                       // TMEM lane quarter
     const int row = q * 32 + lane;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    float m = -INFINITY, l = 0.f;
-    float o_acc[AT_HS];
+    const uint32_t tmem_s = tmem_base + t * 128 + lane_addr;
+    const uint32_t tmem_o = tmem_base + 256 + t * 64 + lane_addr;
+    uint8_t* sP = smem + AT_SMEM_P + t * 2 * AT_TILE_BYTES;
+    int k = 0;                                    // K/V tiles this warpgroup has processed (across items)
+#ifdef MEBT_ATTN_TRACE
+    long long tr_t = 0, tr_acc[4] = {0, 0, 0, 0};
+    const long long tr_start = clock64();
+#endif
+    for (int n = 0; n < my_items; ++n) {
+      int b, h, qp;
+      item_coords(n, b, h, qp);
+      const int qt = 2 * qp + t;
+      const bool active = qt < q_tiles;            // an odd tile count leaves warpgroup 1 without a tile in the last pair
+      float m = 0.f, l = 0.f;
+      float o_acc[AT_HS];
 #pragma unroll
-    for (int i = 0; i < AT_HS; ++i) o_acc[i] = 0.f;
-    uint8_t* sP = smem + AT_SMEM_P;
-
-    for (int j = 0; j < nt; ++j) {
-      const int valid = j < tiles1 ? min(AT_BKV, p.NK1 - j * AT_BKV) : min(AT_BKV, p.NK2 - (j - tiles1) * AT_BKV);
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const bool full = valid == AT_BKV;            // warp-uniform: only a source's last tile can be ragged
-      // One pass over the S row: p = 2^(s*c - m*c) with the CURRENT running maximum m (no separate max pass), the row
-      // maximum of this tile as a by-product.  m is only advanced when a score exceeds it by more than 8 in the log2
-      // domain (p would exceed 256): the exact result does not depend on the stabiliser, only overflow safety does,
-      // so the usual per-tile max pass, and the rescale of O that follows every small increase of the maximum, are
-      // skipped.  The first tile takes its maximum explicitly.
-      auto row_pass = [&](float mb, float& l_tile, float& mx_tile) {
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
-          tmem_ld_wait();
-          float pv[32];
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float sv = __uint_as_float(r[i]);
-              m4[i & 3] = fmaxf(m4[i & 3], sv);
-              pv[i] = ex2_approx(fmaf(sv, p.scale_log2, -mb));
-              l4[i & 3] += pv[i];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float sv = __uint_as_float(r[i]);
-              const bool ok = c * 32 + i < valid;
-              if (ok) m4[i & 3] = fmaxf(m4[i & 3], sv);
-              pv[i] = ok ? ex2_approx(fmaf(sv, p.scale_log2, -mb)) : 0.f;
-              l4[i & 3] += pv[i];
-            }
-          }
-          // 32 keys = four 16-byte chunks of this row inside one 64-key swizzle atom
-          uint8_t* base = sP + (c >> 1) * AT_TILE_BYTES + row * 128;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(pv[8 * g + 0], pv[8 * g + 1]);
-            u.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
-            u.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
-            u.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
-            const int chunk = (c & 1) * 4 + g;
-            *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = u;
-          }
-        }
-        l_tile = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        mx_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      };
-      if (j == 0) {                                 // explicit maximum of the first tile
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (full || c * 32 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
-        }
-        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      } else {
-        mbar_wait(o_full, (j - 1) & 1);             // PV_{j-1} done: O_{j-1} readable, P buffer reusable
+      for (int i = 0; i < AT_HS; ++i) o_acc[i] = 0.f;
+      auto fold_o = [&](int kprev) {                // O of this warpgroup's tile kprev: readable once its PV has retired
+        ATR_BEGIN;
+        mbar_wait(&o_full[t], kprev & 1);
+        ATR_END(1);
+        if (!active) return;
         tc_fence_after();
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(tmem_o, r0);
+        tmem_ld_32x32(tmem_o + 32, r1);
+        tmem_ld_wait_regs(r0);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_o + lane_addr + c * 32, r);
-          tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) o_acc[i] += __uint_as_float(r0[i]);
+        tmem_ld_wait_regs(r1);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) o_acc[32 + i] += __uint_as_float(r1[i]);
+      };
+      for (int j = 0; j < nt; ++j, ++k) {
+        const int valid = j < tiles1 ? min(AT_BKV, p.NK1 - j * AT_BKV) : min(AT_BKV, p.NK2 - (j - tiles1) * AT_BKV);
+        ATR_BEGIN;
+        mbar_wait(&s_full[t], k & 1);
+        ATR_END(0);
+        tc_fence_after();
+        const bool full = valid == AT_BKV;            // warp-uniform: only a source's last tile can be ragged
+        // One pass over the S row: p = 2^(s*c - m*c) with the CURRENT running maximum m (no separate max pass), the row
+        // maximum of this tile as a by-product.  m is only advanced when a score exceeds it by more than 8 in the log2
+        // domain (p would exceed 256): the exact result does not depend on the stabiliser, only overflow safety does,
+        // so the usual per-tile max pass, and the rescale of O that follows every small increase of the maximum, are
+        // skipped.  The first tile of an item seeds m from its first 32 scores.
+        auto chunk = [&](auto full_tag, const uint32_t (&r)[32], int c, float mb, float (&l4)[4], float (&m4)[4]) {
+          constexpr bool FULL = decltype(full_tag)::value;
+          uint8_t* base = sP + (c >> 1) * AT_TILE_BYTES + row * 128;   // 32 keys = four 16-byte chunks of this row
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            float pv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int i = 8 * gq + e;
+              const float sv = __uint_as_float(r[i]);
+              const bool ok = FULL || c * 32 + i < valid;
+              if (ok) m4[e & 3] = fmaxf(m4[e & 3], sv);
+              const float x = fmaf(sv, p.scale_log2, -mb);
+              float pe;
+              if (MEBT_ATTN_POLY && (e & 3) == 3) pe = ex2_poly(x); else pe = ex2_approx(x);
+              pv[e] = ok ? pe : 0.f;
+              l4[e & 3] += pv[e];
+            }
+            uint4 u;
+            u.x = pack_bf16x2(pv[0], pv[1]);
+            u.y = pack_bf16x2(pv[2], pv[3]);
+            u.z = pack_bf16x2(pv[4], pv[5]);
+            u.w = pack_bf16x2(pv[6], pv[7]);
+            const int ch = (c & 1) * 4 + gq;
+            *reinterpret_cast<uint4*>(base + ((ch ^ (row & 7)) << 4)) = u;
+          }
+        };
+        auto row_pass_t = [&](auto full_tag, float mb, float& l_tile, float& mx_tile, bool hand_over) {
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32(tmem_s, ra);
+          tmem_ld_wait_regs(ra);
+          tmem_ld_32x32(tmem_s + 32, rb);
+          chunk(full_tag, ra, 0, mb, l4, m4);
+          if (hand_over && MEBT_ATTN_TURN == 0) mbar_arrive(&rp_done[t]);
+          tmem_ld_wait_regs(rb);
+          tmem_ld_32x32(tmem_s + 64, ra);
+          chunk(full_tag, rb, 1, mb, l4, m4);
+          if (hand_over && MEBT_ATTN_TURN == 1) mbar_arrive(&rp_done[t]);
+          tmem_ld_wait_regs(ra);
+          tmem_ld_32x32(tmem_s + 96, rb);
+          chunk(full_tag, ra, 2, mb, l4, m4);
+          if (hand_over && MEBT_ATTN_TURN == 2) mbar_arrive(&rp_done[t]);
+          tmem_ld_wait_regs(rb);
+          chunk(full_tag, rb, 3, mb, l4, m4);
+          if (hand_over && MEBT_ATTN_TURN == 3) mbar_arrive(&rp_done[t]);
+          l_tile = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+          mx_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        };
+        auto row_pass = [&](float mb, float& l_tile, float& mx_tile, bool hand_over) {
+          if (full) row_pass_t(std::true_type{}, mb, l_tile, mx_tile, hand_over);
+          else row_pass_t(std::false_type{}, mb, l_tile, mx_tile, hand_over);
+        };
+        if (j > 0) fold_o(k - 1);                     // PV of the previous tile done: O readable, P buffer reusable
+        // turn taking: warpgroup 0's tile k follows warpgroup 1's tile k-1, warpgroup 1's tile k follows warpgroup 0's
+        if (MEBT_ATTN_TURN >= 0) {
+          ATR_BEGIN;
+          if (t == 1) mbar_wait(&rp_done[0], k & 1);
+          else if (k > 0) mbar_wait(&rp_done[1], (k - 1) & 1);
+          ATR_END(1);
         }
-      }
-      float l_tile, mx_tile;
-      row_pass(m * p.scale_log2, l_tile, mx_tile);
-      if ((mx_tile - m) * p.scale_log2 > 8.0f) {    // rare: re-base on the new maximum and redo this row
-        const float alpha = ex2_approx((m - mx_tile) * p.scale_log2);
+        if (active) {
+          if (j == 0) {                               // seed the running maximum from the first 32 scores
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_s, r);
+            tmem_ld_wait_regs(r);
+            float mx = __uint_as_float(r[0]);
 #pragma unroll
-        for (int i = 0; i < AT_HS; ++i) o_acc[i] *= alpha;
-        l *= alpha;
-        m = mx_tile;
-        row_pass(m * p.scale_log2, l_tile, mx_tile);
+            for (int i = 1; i < 32; ++i)
+              if (i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+            m = mx;
+          }
+          float l_tile, mx_tile;
+          ATR_BEGIN;
+          row_pass(m * p.scale_log2, l_tile, mx_tile, true);
+          ATR_END(2);
+          if ((mx_tile - m) * p.scale_log2 > 8.0f) {  // rare: re-base on the new maximum and redo this row
+            const float alpha = ex2_approx((m - mx_tile) * p.scale_log2);
+#pragma unroll
+            for (int i = 0; i < AT_HS; ++i) o_acc[i] *= alpha;
+            l *= alpha;
+            m = mx_tile;
+            row_pass(m * p.scale_log2, l_tile, mx_tile, false);
+          }
+          l += l_tile;
+        } else if (MEBT_ATTN_TURN >= 0) {
+          mbar_arrive(&rp_done[t]);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();       // make the st.shared P tile visible to the tensor-core (async) proxy
+        mbar_arrive(&p_full[t]);
       }
-      l += l_tile;
-      tc_fence_before();
-      fence_proxy_async_smem();       // make the st.shared P tile visible to the tensor-core (async) proxy
-      mbar_arrive(p_full);
+      if (nt > 0) fold_o(k - 1);        // the last PV of this item
+      const int qrow = qt * AT_BQ + row;
+      if (active && qrow < p.NQ) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(p.O + (size_t(b) * p.NQ + qrow) * p.ldo + h * AT_HS);
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq) {
+          uint4 u;
+          u.x = pack_bf16x2(o_acc[8 * gq + 0] * inv, o_acc[8 * gq + 1] * inv);
+          u.y = pack_bf16x2(o_acc[8 * gq + 2] * inv, o_acc[8 * gq + 3] * inv);
+          u.z = pack_bf16x2(o_acc[8 * gq + 4] * inv, o_acc[8 * gq + 5] * inv);
+          u.w = pack_bf16x2(o_acc[8 * gq + 6] * inv, o_acc[8 * gq + 7] * inv);
+          dst[gq] = u;
+        }
+        if (p.lse != nullptr)
+          p.lse[(size_t(b) * p.H + h) * p.NQ + qrow] = l > 0.f ? m * p.scale + logf(l) : -INFINITY;
+      }
     }
-    if (nt > 0) {
-      mbar_wait(o_full, (nt - 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_o + lane_addr + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(r[i]);
-      }
+#ifdef MEBT_ATTN_TRACE
+    if (p.trace != nullptr && lane == 0 && q == 0) {
+      long long* o = p.trace + (blockIdx.x * 2 + t) * 4;
+      o[0] = tr_acc[0]; o[1] = tr_acc[1]; o[2] = tr_acc[2]; o[3] = clock64() - tr_start;
     }
-    const int qrow = qt * AT_BQ + row;
-    if (qrow < p.NQ) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(p.O + (size_t(b) * p.NQ + qrow) * p.ldo + h * AT_HS);
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(o_acc[8 * g + 0] * inv, o_acc[8 * g + 1] * inv);
-        u.y = pack_bf16x2(o_acc[8 * g + 2] * inv, o_acc[8 * g + 3] * inv);
-        u.z = pack_bf16x2(o_acc[8 * g + 4] * inv, o_acc[8 * g + 5] * inv);
-        u.w = pack_bf16x2(o_acc[8 * g + 6] * inv, o_acc[8 * g + 7] * inv);
-        dst[g] = u;
-      }
-      if (p.lse != nullptr)
-        p.lse[(size_t(b) * p.H + h) * p.NQ + qrow] = l > 0.f ? m * p.scale + logf(l) : -INFINITY;
-    }
+#endif
   }
 
   tc_fence_before();
@@ -279,6 +390,10 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 
 }  // namespace
 }  // namespace mebt
+
+#ifdef MEBT_ATTN_TRACE
+extern "C" void mebt_attn_set_trace(long long* buf) { mebt::g_attn_trace = buf; }
+#endif
 
 extern "C" int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
                                          int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0,
@@ -306,20 +421,26 @@ extern "C" int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, con
     if (rc) return rc;
   }
   AttnParams p;
-  p.NQ = NQ; p.NK1 = NK1; p.NK2 = NK2; p.H = H;
+  p.NQ = NQ; p.NK1 = NK1; p.NK2 = NK2; p.H = H; p.B = B;
   p.q_col0 = q_col0; p.k1_col0 = k1_col0; p.v1_col0 = v1_col0; p.k2_col0 = k2_col0; p.v2_col0 = v2_col0;
   p.O = static_cast<__nv_bfloat16*>(O);
   p.ldo = ldo;
   p.lse = lse;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+#ifdef MEBT_ATTN_TRACE
+  p.trace = g_attn_trace;
+#else
+  p.trace = nullptr;
+#endif
   static bool attr = false;
   if (!attr) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(latent_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       AT_SMEM_TOTAL));
     attr = true;
   }
-  dim3 grid((NQ + AT_BQ - 1) / AT_BQ, H, B);
+  const int n_items = B * H * (((NQ + AT_BQ - 1) / AT_BQ + 1) / 2);
+  dim3 grid(n_items < sm_count() ? n_items : sm_count());
   {
     LaunchScope ls(FAM_ATTENTION, 4.0 * double(B) * H * double(NQ) * double(NK1 + NK2) * AT_HS,
                    static_cast<cudaStream_t>(stream));

@@ -107,6 +107,9 @@ inline cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3
 // ----------------------------------------------------------------------------------------------
 // Device helpers
 // ----------------------------------------------------------------------------------------------
+#ifndef MEBT_WAIT_BACKOFF_NS
+#define MEBT_WAIT_BACKOFF_NS 40
+#endif
 #ifndef MEBT_SPIN_LIMIT
 #define MEBT_SPIN_LIMIT (1u << 26)   // a stuck pipeline traps instead of hanging the GPU
 #endif
@@ -170,6 +173,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > MEBT_SPIN_LIMIT) __trap();
+  }
+}
+
+// Same for the single-thread producer / MMA-issuer roles: back off between polls so that the spinning warp does not
+// take issue slots from the compute warps that share its SM sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (MEBT_WAIT_BACKOFF_NS > 0) __nanosleep(MEBT_WAIT_BACKOFF_NS);
     if (++spins > MEBT_SPIN_LIMIT) __trap();
   }
 }

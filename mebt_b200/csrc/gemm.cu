@@ -600,7 +600,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
-    if (tma_epi && epi_t0) tma_store_wait0();                  // all of the CTA's stores have been written
+    if (tma_epi && epi_t0) tma_store_wait_read<0>();          // the stores have read their slots (the writes drain with the grid)
     if (threadIdx.x == 64) TR_FLUSH(5, 1);
 #ifdef MEBT_GEMM_TRACE
     if (threadIdx.x == 64 && p.trace != nullptr) for (int _i = 1; _i < 6; ++_i) p.trace[148 * 8 + blockIdx.x * 5 + _i - 1] = tr_acc[_i];
