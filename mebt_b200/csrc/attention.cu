@@ -7,21 +7,24 @@
 // NK == 0 (first draft step: no context) yields O = 0, like the empty softmax in the reference.
 //
 // Persistent CTAs (one per SM, 320 threads) walk a list of work items (batch element, head, PAIR of 128-query tiles):
-//   warp 0    : TMA producer (the item's two Q tiles into a double buffer, K/V tiles of 128 keys through a 3-deep ring)
-//   warp 1    : tcgen05.mma issuer: S_t = Q_t K^T (M128 N128 K64) and O_t = P_t V (M128 N64 K128) into TMEM
-//   warps 2-5 : softmax warpgroup 0 (query tile 2i)      warps 6-9 : softmax warpgroup 1 (query tile 2i+1)
-// Both warpgroups walk the SAME K/V tiles (each tile is loaded once and feeds four MMAs), each with its own
-// S / P / O buffers and running (max, sum, O) state; nothing is merged.  Each softmax thread owns one query row: it
-// reads S from TMEM (the next 32-column chunk is in flight while the current one is exponentiated), writes P (bf16)
-// into the 128B-swizzled K-major shared-memory layout the PV MMA consumes, and folds O_j into a register
-// accumulator.  The exponentials (one per score, 16 / clk / SM on the MUFU pipe) bound the kernel, not the tensor
-// pipe: 128 x 128 scores cost 1024 clk of MUFU against 512 clk of MMA at head_dim 64.  Two measures keep the MUFU
-// pipe busy:
-//   * the warpgroups take TURNS at the row pass (mbarrier hand-off): one exponentiates while the other waits for
-//     its S / PV round trip through the tensor pipe (about 1000 clk), instead of both contending and then both
-//     waiting;
-//   * one exponential in four is evaluated on the FMA pipe (Cody-Waite split + degree-3 polynomial, relative error
-//     7.5e-5, far below the bf16 rounding of P).
+//   warps 0-3 : softmax warpgroup 0 (query tile 2i)      warps 4-7 : softmax warpgroup 1 (query tile 2i+1)
+//   warp 8    : TMA producer (the item's two Q tiles into a double buffer, K/V tiles of 128 keys through a 5-deep ring)
+//   warp 9    : tcgen05.mma issuer: S_t = Q_t K^T (M128 N128 K64, both operands in smem) and
+//               O_t += P_t V (M128 N64 K128, P read from TENSOR MEMORY, V from smem)
+// (the two single-thread roles carry the HIGHEST warp ids: the sub-partition arbiter favours the highest eligible warp
+// id, so the MMA issuer is never queued behind the two softmax warps it shares its scheduler with)
+// Both warpgroups walk the SAME K/V tiles (each tile is loaded once and feeds four MMAs), each with its own S, P and O
+// regions of tensor memory (128 + 64 + 64 columns); while one exponentiates, the other's S / PV round trip runs.
+// Each softmax thread owns one query row (= its TMEM lane): it reads S with tcgen05.ld, forms P = 2^(s c - m c) in
+// bf16 and writes it back with tcgen05.st in the packed layout the PV MMA takes its A operand in, so P never touches
+// shared memory: at head_dim 64 the kernel would otherwise be bound by shared-memory bandwidth (per 128 x 128 tile
+// 80 KB of MMA operand reads + 32 KB of P writes against 128 B/clk).  O accumulates in TMEM across K/V tiles.
+// The stabiliser m is LAZY: it is seeded from the first 32 scores of the row and only advanced when a score exceeds
+// it by more than 8 in the log2 domain (P would exceed 256) - the exact result does not depend on the stabiliser,
+// only overflow safety does - and only then is O rescaled in TMEM (warp-uniform branch, tcgen05.ld / st).
+// What is left is bound by the exponentials (one per score, 16 / clk / SM on the MUFU pipe: 1024 clk per tile
+// against 512 clk of MMA), so one exponential in four is evaluated on the FMA pipe (Cody-Waite split + degree-3
+// polynomial, relative error 7.5e-5, far below the bf16 rounding of P).
 #include <type_traits>
 #include "common.cuh"
 
@@ -33,19 +36,15 @@ constexpr int AT_BKV = 128;
 constexpr int AT_HS = 64;
 constexpr int AT_THREADS = 320;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;      // 16 KiB: a [128 x 64] bf16 tile (Q, K or V)
-constexpr int AT_KV_STAGES = 3;
+constexpr int AT_KV_STAGES = 5;
 constexpr int AT_SMEM_Q = 0;                                     // 2 buffers x 2 query tiles
 constexpr int AT_SMEM_K = AT_SMEM_Q + 4 * AT_TILE_BYTES;
 constexpr int AT_SMEM_V = AT_SMEM_K + AT_KV_STAGES * AT_TILE_BYTES;
-constexpr int AT_SMEM_P = AT_SMEM_V + AT_KV_STAGES * AT_TILE_BYTES;   // 2 warpgroups x [128 x 128] bf16
-constexpr int AT_SMEM_BAR = AT_SMEM_P + 4 * AT_TILE_BYTES;
-constexpr int AT_SMEM_TOTAL = AT_SMEM_BAR + 256;
-constexpr uint32_t AT_TMEM_COLS = 512;           // S_0: [0,128)  S_1: [128,256)  O_0: [256,320)  O_1: [320,384)
+constexpr int AT_SMEM_BAR = AT_SMEM_V + AT_KV_STAGES * AT_TILE_BYTES;
+constexpr int AT_SMEM_TOTAL = AT_SMEM_BAR + 512;
+constexpr uint32_t AT_TMEM_COLS = 512;           // S_t: 128 t    O_t: 256 + 64 t    P_t: 384 + 64 t
 static_assert(AT_SMEM_TOTAL <= 232448, "shared memory budget");
 
-#ifndef MEBT_ATTN_TURN
-#define MEBT_ATTN_TURN -1     // hand the row-pass turn over after this 32-column chunk (0..3); -1: no turn taking
-#endif
 #ifndef MEBT_ATTN_POLY
 #define MEBT_ATTN_POLY 1      // 1: every fourth exponential on the FMA pipe
 #endif
@@ -91,12 +90,11 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   uint64_t* q_full = bars + 0;     // [2] Q buffers (a pair of query tiles each)
   uint64_t* q_empty = bars + 2;    // [2]
   uint64_t* kv_full = bars + 4;    // [AT_KV_STAGES]
-  uint64_t* kv_empty = bars + 8;   // [AT_KV_STAGES]
-  uint64_t* s_full = bars + 12;    // [2] per warpgroup
-  uint64_t* p_full = bars + 14;    // [2]
-  uint64_t* o_full = bars + 16;    // [2]
-  uint64_t* rp_done = bars + 18;   // [2] row-pass turn hand-off
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* kv_empty = bars + 12;  // [AT_KV_STAGES]
+  uint64_t* s_full = bars + 20;    // [2] per warpgroup
+  uint64_t* p_full = bars + 22;    // [2]
+  uint64_t* pv_done = bars + 24;   // [2] the warpgroup's latest PV has retired: O includes it, P may be overwritten
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles1 = (p.NK1 + AT_BKV - 1) / AT_BKV;
@@ -121,13 +119,12 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     prefetch_tensormap(&tm_kv2);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_full[s], 1);
-      mbar_init(&rp_done[s], 128);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1);
     }
     for (int s = 0; s < AT_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 8) {
     tmem_alloc(tmem_ptr_smem, AT_TMEM_COLS);
     tmem_relinquish();
   }
@@ -136,8 +133,9 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   griddep_wait();
+  // the softmax warpgroups take the registers the single-thread roles do not need (S row + P row live per thread)
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0 && nt > 0) {
       int gj = 0;                    // K/V tiles loaded by this CTA
       for (int n = 0; n < my_items; ++n) {
@@ -168,19 +166,30 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0 && nt > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // P (K-major) x V (MN-major: hs contiguous)
-      // step g = 2 * (K/V tile counter) + warpgroup: the two warpgroups' MMAs on one K/V tile are adjacent
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // P (TMEM, K-major) x V (MN-major: hs contiguous)
+#ifdef MEBT_ATTN_TRACE
+      long long mt[3] = {0, 0, 0}, mt0 = 0;
+      const long long mstart = clock64();
+#define MTR_BEGIN mt0 = clock64()
+#define MTR_END(i) mt[i] += clock64() - mt0
+#else
+#define MTR_BEGIN
+#define MTR_END(i)
+#endif
+      // step g = 2 * (K/V tile counter gj) + warpgroup t
       const int total = my_items * nt * 2;
-      // S_t of step g into warpgroup t's S buffer: legal once that warpgroup has consumed the S of step g-2
+      // S_t of tile gj: legal once warpgroup t has consumed the S of tile gj-1
       auto issue_s = [&](int g) {
         const int gj = g >> 1, t = g & 1;
         const int n = gj / nt, j = gj - n * nt;
         if (t == 0) {
+          MTR_BEGIN;
           if (j == 0) mbar_wait(&q_full[n & 1], (n >> 1) & 1);
           mbar_wait(&kv_full[gj % AT_KV_STAGES], (gj / AT_KV_STAGES) & 1);
+          MTR_END(1);
           tc_fence_after();
         }
         const uint32_t sQ = smem_u32(smem + AT_SMEM_Q + (2 * (n & 1) + t) * AT_TILE_BYTES);
@@ -195,30 +204,34 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       if (total > 0) { issue_s(0); issue_s(1); }
       for (int g = 0; g < total; ++g) {
         const int t = g & 1, gj = g >> 1;
-        mbar_wait(&p_full[t], gj & 1);   // warpgroup t done with this tile: S_t consumed, P_t in smem, O_t read
+        const int j = gj % nt;
+        // warpgroup t is done with tile gj: S consumed, P in TMEM (and, at j == 0, the previous item's O read)
+        MTR_BEGIN;
+        mbar_wait(&p_full[t], gj & 1);
+        MTR_END(0);
         tc_fence_after();
-        if (g + 2 < total) issue_s(g + 2);       // overlaps the warpgroup's next softmax with this tile's PV
+        if (g + 2 < total) issue_s(g + 2);       // the warpgroup's next S first: it is what the warpgroup waits for
         const uint32_t sV = smem_u32(smem + AT_SMEM_V + (gj % AT_KV_STAGES) * AT_TILE_BYTES);
-        const uint32_t sP = smem_u32(smem + AT_SMEM_P + t * 2 * AT_TILE_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < AT_BKV / 16; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(sP + (kk >> 2) * AT_TILE_BYTES + (kk & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sV + kk * 2048, 64 * 128, 1024);
-          umma_bf16_ss(tmem_base + 256 + t * 64, da, db, idesc_o, kk != 0 ? 1u : 0u);
-        }
-        umma_commit(&o_full[t]);
+        for (int kk = 0; kk < AT_BKV / 16; ++kk)
+          umma_bf16_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + kk * 8,
+                       make_smem_desc_sw128(sV + kk * 2048, 64 * 128, 1024), idesc_o, (j != 0 || kk != 0) ? 1u : 0u);
+        umma_commit(&pv_done[t]);
         if (t == 1) umma_commit(&kv_empty[gj % AT_KV_STAGES]);   // both warpgroups' S and PV of this K/V stage are done
       }
+#ifdef MEBT_ATTN_TRACE
+      if (p.trace != nullptr) { long long* o = p.trace + 148 * 8 + blockIdx.x * 4; o[0] = mt[0]; o[1] = mt[1]; o[2] = mt[2]; o[3] = clock64() - mstart; }
+#endif
     }
   } else {
     // ===== softmax warpgroups =====
-    const int t = (warp - 2) >> 2;                // warpgroup: query tile 2 * pair + t
+    const int t = warp >> 2;                      // warpgroup: query tile 2 * pair + t
     const int q = warp & 3;                       // TMEM lane quarter
     const int row = q * 32 + lane;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const uint32_t tmem_s = tmem_base + t * 128 + lane_addr;
     const uint32_t tmem_o = tmem_base + 256 + t * 64 + lane_addr;
-    uint8_t* sP = smem + AT_SMEM_P + t * 2 * AT_TILE_BYTES;
+    const uint32_t tmem_p = tmem_base + 384 + t * 64 + lane_addr;
     int k = 0;                                    // K/V tiles this warpgroup has processed (across items)
 #ifdef MEBT_ATTN_TRACE
     long long tr_t = 0, tr_acc[4] = {0, 0, 0, 0};
@@ -230,145 +243,138 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       const int qt = 2 * qp + t;
       const bool active = qt < q_tiles;            // an odd tile count leaves warpgroup 1 without a tile in the last pair
       float m = 0.f, l = 0.f;
-      float o_acc[AT_HS];
-#pragma unroll
-      for (int i = 0; i < AT_HS; ++i) o_acc[i] = 0.f;
-      auto fold_o = [&](int kprev) {                // O of this warpgroup's tile kprev: readable once its PV has retired
-        ATR_BEGIN;
-        mbar_wait(&o_full[t], kprev & 1);
-        ATR_END(1);
-        if (!active) return;
-        tc_fence_after();
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32(tmem_o, r0);
-        tmem_ld_32x32(tmem_o + 32, r1);
-        tmem_ld_wait_regs(r0);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[i] += __uint_as_float(r0[i]);
-        tmem_ld_wait_regs(r1);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[32 + i] += __uint_as_float(r1[i]);
-      };
       for (int j = 0; j < nt; ++j, ++k) {
-        const int valid = j < tiles1 ? min(AT_BKV, p.NK1 - j * AT_BKV) : min(AT_BKV, p.NK2 - (j - tiles1) * AT_BKV);
+        const int rem = j < tiles1 ? p.NK1 - j * AT_BKV : p.NK2 - (j - tiles1) * AT_BKV;
+        const int valid = min(AT_BKV, rem);
+        const bool full = valid == AT_BKV;            // warp-uniform: only a source's last tile can be ragged
         ATR_BEGIN;
         mbar_wait(&s_full[t], k & 1);
         ATR_END(0);
         tc_fence_after();
-        const bool full = valid == AT_BKV;            // warp-uniform: only a source's last tile can be ragged
-        // One pass over the S row: p = 2^(s*c - m*c) with the CURRENT running maximum m (no separate max pass), the row
-        // maximum of this tile as a by-product.  m is only advanced when a score exceeds it by more than 8 in the log2
-        // domain (p would exceed 256): the exact result does not depend on the stabiliser, only overflow safety does,
-        // so the usual per-tile max pass, and the rescale of O that follows every small increase of the maximum, are
-        // skipped.  The first tile of an item seeds m from its first 32 scores.
-        auto chunk = [&](auto full_tag, const uint32_t (&r)[32], int c, float mb, float (&l4)[4], float (&m4)[4]) {
-          constexpr bool FULL = decltype(full_tag)::value;
-          uint8_t* base = sP + (c >> 1) * AT_TILE_BYTES + row * 128;   // 32 keys = four 16-byte chunks of this row
-#pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            float pv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int i = 8 * gq + e;
-              const float sv = __uint_as_float(r[i]);
-              const bool ok = FULL || c * 32 + i < valid;
-              if (ok) m4[e & 3] = fmaxf(m4[e & 3], sv);
-              const float x = fmaf(sv, p.scale_log2, -mb);
-              float pe;
-              if (MEBT_ATTN_POLY && (e & 3) == 3) pe = ex2_poly(x); else pe = ex2_approx(x);
-              pv[e] = ok ? pe : 0.f;
-              l4[e & 3] += pv[e];
-            }
-            uint4 u;
-            u.x = pack_bf16x2(pv[0], pv[1]);
-            u.y = pack_bf16x2(pv[2], pv[3]);
-            u.z = pack_bf16x2(pv[4], pv[5]);
-            u.w = pack_bf16x2(pv[6], pv[7]);
-            const int ch = (c & 1) * 4 + gq;
-            *reinterpret_cast<uint4*>(base + ((ch ^ (row & 7)) << 4)) = u;
-          }
-        };
-        auto row_pass_t = [&](auto full_tag, float mb, float& l_tile, float& mx_tile, bool hand_over) {
-          float l4[4] = {0.f, 0.f, 0.f, 0.f};
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          uint32_t ra[32], rb[32];
-          tmem_ld_32x32(tmem_s, ra);
-          tmem_ld_wait_regs(ra);
-          tmem_ld_32x32(tmem_s + 32, rb);
-          chunk(full_tag, ra, 0, mb, l4, m4);
-          if (hand_over && MEBT_ATTN_TURN == 0) mbar_arrive(&rp_done[t]);
-          tmem_ld_wait_regs(rb);
-          tmem_ld_32x32(tmem_s + 64, ra);
-          chunk(full_tag, rb, 1, mb, l4, m4);
-          if (hand_over && MEBT_ATTN_TURN == 1) mbar_arrive(&rp_done[t]);
-          tmem_ld_wait_regs(ra);
-          tmem_ld_32x32(tmem_s + 96, rb);
-          chunk(full_tag, ra, 2, mb, l4, m4);
-          if (hand_over && MEBT_ATTN_TURN == 2) mbar_arrive(&rp_done[t]);
-          tmem_ld_wait_regs(rb);
-          chunk(full_tag, rb, 3, mb, l4, m4);
-          if (hand_over && MEBT_ATTN_TURN == 3) mbar_arrive(&rp_done[t]);
-          l_tile = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-          mx_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        };
-        auto row_pass = [&](float mb, float& l_tile, float& mx_tile, bool hand_over) {
-          if (full) row_pass_t(std::true_type{}, mb, l_tile, mx_tile, hand_over);
-          else row_pass_t(std::false_type{}, mb, l_tile, mx_tile, hand_over);
-        };
-        if (j > 0) fold_o(k - 1);                     // PV of the previous tile done: O readable, P buffer reusable
-        // turn taking: warpgroup 0's tile k follows warpgroup 1's tile k-1, warpgroup 1's tile k follows warpgroup 0's
-        if (MEBT_ATTN_TURN >= 0) {
-          ATR_BEGIN;
-          if (t == 1) mbar_wait(&rp_done[0], k & 1);
-          else if (k > 0) mbar_wait(&rp_done[1], (k - 1) & 1);
-          ATR_END(1);
-        }
         if (active) {
-          if (j == 0) {                               // seed the running maximum from the first 32 scores
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_s, r);
-            tmem_ld_wait_regs(r);
-            float mx = __uint_as_float(r[0]);
+          // 32 scores -> 16 columns of packed bf16 P
+          auto chunk = [&](auto full_tag, const uint32_t (&r)[32], int c, float mb, float (&l4)[4], float (&m4)[4]) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            uint32_t pk[16];
 #pragma unroll
-            for (int i = 1; i < 32; ++i)
-              if (i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-            m = mx;
-          }
+            for (int i = 0; i < 32; i += 2) {
+              float pe[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float sv = __uint_as_float(r[i + e]);
+                const bool ok = FULL || c * 32 + i + e < valid;
+                if (ok) m4[(i + e) & 3] = fmaxf(m4[(i + e) & 3], sv);
+                const float x = fmaf(sv, p.scale_log2, -mb);
+                float v;
+                if (MEBT_ATTN_POLY && ((i + e) & 3) == 3) v = ex2_poly(x); else v = ex2_approx(x);
+                pe[e] = ok ? v : 0.f;
+                l4[(i + e) & 3] += pe[e];
+              }
+              pk[i >> 1] = pack_bf16x2(pe[0], pe[1]);
+            }
+            tmem_st_32x16(tmem_p + c * 16, pk);
+          };
+          // One pass over the S row (the next 32 columns are in flight while the current ones are exponentiated); the
+          // first P store waits for the previous tile's PV (it reads P).
+          auto row_pass = [&](auto full_tag, float mb, float& l_tile, float& mx_tile, bool seed) {
+            float l4[4] = {0.f, 0.f, 0.f, 0.f};
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(tmem_s, ra);
+            tmem_ld_32x32(tmem_s + 32, rb);
+            tmem_ld_wait_regs(ra);
+            if (seed) {                               // seed the stabiliser from the first 32 scores
+              float mx = __uint_as_float(ra[0]);
+#pragma unroll
+              for (int i = 1; i < 32; ++i)
+                if (i < valid) mx = fmaxf(mx, __uint_as_float(ra[i]));
+              m = mx;
+              mb = mx * p.scale_log2;
+            }
+            if (k > 0) {
+              ATR_BEGIN;
+              mbar_wait(&pv_done[t], (k - 1) & 1);
+              ATR_END(1);
+              tc_fence_after();
+            }
+            chunk(full_tag, ra, 0, mb, l4, m4);
+            tmem_ld_wait_regs(rb);
+            tmem_ld_32x32(tmem_s + 64, ra);
+            chunk(full_tag, rb, 1, mb, l4, m4);
+            tmem_ld_wait_regs(ra);
+            tmem_ld_32x32(tmem_s + 96, rb);
+            chunk(full_tag, ra, 2, mb, l4, m4);
+            tmem_ld_wait_regs(rb);
+            chunk(full_tag, rb, 3, mb, l4, m4);
+            l_tile = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+            mx_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          };
           float l_tile, mx_tile;
-          ATR_BEGIN;
-          row_pass(m * p.scale_log2, l_tile, mx_tile, true);
-          ATR_END(2);
-          if ((mx_tile - m) * p.scale_log2 > 8.0f) {  // rare: re-base on the new maximum and redo this row
-            const float alpha = ex2_approx((m - mx_tile) * p.scale_log2);
+#ifdef MEBT_ATTN_TRACE
+          const long long rp0 = clock64(), w0 = tr_acc[1];
+#endif
+          if (full) row_pass(std::true_type{}, m * p.scale_log2, l_tile, mx_tile, j == 0);
+          else row_pass(std::false_type{}, m * p.scale_log2, l_tile, mx_tile, j == 0);
+#ifdef MEBT_ATTN_TRACE
+          tr_acc[2] += (clock64() - rp0) - (tr_acc[1] - w0);
+#endif
+          const bool grow = (mx_tile - m) * p.scale_log2 > 8.0f;
+          if (__any_sync(0xffffffffu, grow)) {        // rare: re-base on the new maximum, rescale O, redo this tile
+            const float alpha = grow ? ex2_approx((m - mx_tile) * p.scale_log2) : 1.f;
+            if (grow) { l *= alpha; m = mx_tile; }
+            if (j > 0) {                              // (the PV of tile k-1 has retired: row_pass waited for it)
 #pragma unroll
-            for (int i = 0; i < AT_HS; ++i) o_acc[i] *= alpha;
-            l *= alpha;
-            m = mx_tile;
-            row_pass(m * p.scale_log2, l_tile, mx_tile, false);
+              for (int c = 0; c < 2; ++c) {
+                uint32_t ro[32];
+                tmem_ld_32x32(tmem_o + c * 32, ro);
+                tmem_ld_wait_regs(ro);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+                tmem_st_32x32(tmem_o + c * 32, ro);
+              }
+            }
+            if (full) row_pass(std::true_type{}, m * p.scale_log2, l_tile, mx_tile, false);
+            else row_pass(std::false_type{}, m * p.scale_log2, l_tile, mx_tile, false);
           }
           l += l_tile;
-        } else if (MEBT_ATTN_TURN >= 0) {
-          mbar_arrive(&rp_done[t]);
+          tmem_st_wait();
         }
         tc_fence_before();
-        fence_proxy_async_smem();       // make the st.shared P tile visible to the tensor-core (async) proxy
         mbar_arrive(&p_full[t]);
       }
-      if (nt > 0) fold_o(k - 1);        // the last PV of this item
       const int qrow = qt * AT_BQ + row;
-      if (active && qrow < p.NQ) {
+      if (nt > 0) {                     // the item's last PV: O complete
+        ATR_BEGIN;
+        mbar_wait(&pv_done[t], (k - 1) & 1);
+        ATR_END(1);
+        tc_fence_after();
+      }
+      if (active) {
         const float inv = l > 0.f ? 1.f / l : 0.f;
         uint4* dst = reinterpret_cast<uint4*>(p.O + (size_t(b) * p.NQ + qrow) * p.ldo + h * AT_HS);
 #pragma unroll
-        for (int gq = 0; gq < 8; ++gq) {
-          uint4 u;
-          u.x = pack_bf16x2(o_acc[8 * gq + 0] * inv, o_acc[8 * gq + 1] * inv);
-          u.y = pack_bf16x2(o_acc[8 * gq + 2] * inv, o_acc[8 * gq + 3] * inv);
-          u.z = pack_bf16x2(o_acc[8 * gq + 4] * inv, o_acc[8 * gq + 5] * inv);
-          u.w = pack_bf16x2(o_acc[8 * gq + 6] * inv, o_acc[8 * gq + 7] * inv);
-          dst[gq] = u;
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ro[32];
+          if (nt > 0) {
+            tmem_ld_32x32(tmem_o + c * 32, ro);
+            tmem_ld_wait_regs(ro);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ro[i] = 0u;
+          }
+          if (qrow < p.NQ) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(ro[8 * gq + 0]) * inv, __uint_as_float(ro[8 * gq + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(ro[8 * gq + 2]) * inv, __uint_as_float(ro[8 * gq + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(ro[8 * gq + 4]) * inv, __uint_as_float(ro[8 * gq + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(ro[8 * gq + 6]) * inv, __uint_as_float(ro[8 * gq + 7]) * inv);
+              dst[c * 4 + gq] = u;
+            }
+          }
         }
-        if (p.lse != nullptr)
+        if (qrow < p.NQ && p.lse != nullptr)
           p.lse[(size_t(b) * p.H + h) * p.NQ + qrow] = l > 0.f ? m * p.scale + logf(l) : -INFINITY;
       }
     }
@@ -382,7 +388,7 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, AT_TMEM_COLS);
   }
@@ -413,11 +419,11 @@ extern "C" int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, con
   t1 = tq;
   t2 = tq;
   if (NK1 > 0) {
-    rc = get_tensor_map_2d(&t1, KV1, 2, uint64_t(ld1), uint64_t(B) * NK1, uint64_t(ld1) * 2, 64, 128);
+    rc = get_tensor_map_2d(&t1, KV1, 2, uint64_t(ld1), uint64_t(B) * NK1, uint64_t(ld1) * 2, 64, AT_BKV);
     if (rc) return rc;
   }
   if (NK2 > 0) {
-    rc = get_tensor_map_2d(&t2, KV2, 2, uint64_t(ld2), uint64_t(B) * NK2, uint64_t(ld2) * 2, 64, 128);
+    rc = get_tensor_map_2d(&t2, KV2, 2, uint64_t(ld2), uint64_t(B) * NK2, uint64_t(ld2) * 2, 64, AT_BKV);
     if (rc) return rc;
   }
   AttnParams p;
