@@ -222,6 +222,28 @@ int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV
                               int dv2_col0, int B, int H, int NQ, int head_dim, void* workspace, size_t workspace_bytes,
                               void* stream);
 
+/* ---- dropout (training mode; nn.Dropout at mebt/modules/gpt.py:112-113,140,150-155,216,239-242) ------------- */
+/* Keep decisions are counter-based: a pure function of (seed, site, row, column), regenerated by the backward
+ * kernels instead of being stored.  p is quantised to 1/65536 and kept elements are scaled by 65536/(65536-round(p*65536)).
+ * y[r,:] = resid[r,:] + x[r,:] .* keep / (1-p)   (bf16 [rows, D]; resid may be NULL; y may alias x).
+ * Calling it on dy with the same (p, seed, site) and resid = NULL is the backward. */
+int mebt_dropout_rows(const void* x, int ldx, const void* resid, int ldres, void* y, int ldy, int rows, int D, float p,
+                      unsigned long long seed, unsigned long long site, void* stream);
+/* mebt_latent_attention_fwd / _bwd with attn_drop applied to the softmax output (gpt.py:136): O = (P .* keep/(1-p)) V. */
+int mebt_latent_attention_fwd_dropout(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
+                                      int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2,
+                                      void* O, int ldo, float* lse, int B, int H, int NQ, int head_dim, float p,
+                                      unsigned long long seed, void* stream);
+int mebt_latent_attention_bwd_dropout(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
+                                      int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2,
+                                      const void* O, int ldo, const void* dO, int lddo, const float* lse, void* dQ,
+                                      int lddq, int dq_col0, void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2,
+                                      int ldd2, int dk2_col0, int dv2_col0, int B, int H, int NQ, int head_dim, float p,
+                                      unsigned long long seed, void* workspace, size_t workspace_bytes, void* stream);
+/* The keep factors (0 or 1/(1-p)) those two kernels apply, as fp32 [B, H, NQ, NK1+NK2] (test support). */
+int mebt_attention_dropout_mask(float* out, int B, int H, int NQ, int NK1, int NK2, float p, unsigned long long seed,
+                                void* stream);
+
 /* ---- the layer stack in one call ---------------------------------------------------------------- */
 enum {
   MEBT_MODE_LATENT_ENC = 0,  /* q = latents, kv = contexts            -> latents   (gpt.py:167-169) */
@@ -304,6 +326,27 @@ int mebt_stack_backward(const mebt_layer_t* layers, const mebt_layer_grads_t* gr
                         int D, int H, int V, const void* lat0, const void* ctx, const void* tgt0, const void* dlogits,
                         void* saved, size_t saved_bytes, void* d_lat, void* d_ctx, void* d_tgt, int layer_begin,
                         int layer_end, int grad_accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same two calls in training mode with dropout.  attn_p: on the attention probabilities (attn_drop, gpt.py:136);
+ * resid_p: on the proj and MLP outputs before their residual adds (resid_drop gpt.py:140, mlp[3] gpt.py:154).  The
+ * stem dropout (embd_pdrop, gpt.py:239-242) is applied by the caller on the input streams (mebt_dropout_rows).
+ * Block i draws its masks from sites (seed, 4*i + {0: attention, 1: proj, 2: mlp}); a NULL `drop` or p = 0 is the
+ * deterministic path above.  Forward and backward must be given the same values. */
+typedef struct mebt_dropout {
+  float attn_p;
+  float resid_p;
+  unsigned long long seed;
+} mebt_dropout_t;
+int mebt_stack_forward_train_dropout(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                                     const void* w_head, int B, int L, int NC, int NT, int D, int H, int V,
+                                     const void* lat0, const void* ctx, const void* tgt0, void* logits, int logits_dtype,
+                                     void* saved, size_t saved_bytes, const mebt_dropout_t* drop, void* stream);
+int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_grads_t* grads, int n_layers,
+                                const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const void* w_head, float* d_w_head,
+                                int B, int L, int NC, int NT, int D, int H, int V, const void* lat0, const void* ctx,
+                                const void* tgt0, const void* dlogits, void* saved, size_t saved_bytes, void* d_lat,
+                                void* d_ctx, void* d_tgt, int layer_begin, int layer_end, int grad_accumulate,
+                                const mebt_dropout_t* drop, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,24 @@ _SIGNATURES["mebt_stack_backward"] = [ctypes.POINTER(LayerStruct), ctypes.POINTE
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
                                       c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
+class DropoutStruct(ctypes.Structure):
+    """mebt_dropout_t"""
+    _fields_ = [("attn_p", c_float), ("resid_p", c_float), ("seed", c_uint64)]
+
+
+_SIGNATURES["mebt_stack_forward_train_dropout"] = _SIGNATURES["mebt_stack_forward_train"][:-1] + [
+    ctypes.POINTER(DropoutStruct), c_void_p]
+_SIGNATURES["mebt_stack_backward_dropout"] = _SIGNATURES["mebt_stack_backward"][:-3] + [
+    ctypes.POINTER(DropoutStruct), c_void_p, c_size_t, c_void_p]
+_SIGNATURES["mebt_dropout_rows"] = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_uint64,
+                                    c_uint64, c_void_p]
+_SIGNATURES["mebt_latent_attention_fwd_dropout"] = _SIGNATURES["mebt_latent_attention_fwd"][:-1] + [c_float, c_uint64,
+                                                                                                    c_void_p]
+_SIGNATURES["mebt_latent_attention_bwd_dropout"] = _SIGNATURES["mebt_latent_attention_bwd"][:-3] + [
+    c_float, c_uint64, c_void_p, c_size_t, c_void_p]
+_SIGNATURES["mebt_attention_dropout_mask"] = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_void_p]
+
+
 class EncHoistStruct(ctypes.Structure):
     """mebt_enc_hoist_t"""
     _fields_ = [("n_enc", c_int), ("w_enc_kv", c_void_p), ("b_enc_kv", c_void_p), ("ones", c_void_p), ("zeros", c_void_p)]

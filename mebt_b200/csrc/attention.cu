@@ -67,6 +67,7 @@ struct AttnParams {
   float scale_log2;        // log2(e) / sqrt(hs)
   float scale;             // 1 / sqrt(hs)
   long long* trace;
+  DropKey drop;            // attention-probability dropout (training); thr == 0: off
 };
 
 // 2^x for x <= ~8 on the FMA pipe: n = round(x), f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial, the
@@ -81,6 +82,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(pl) + (__float_as_int(xf) << 23));
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv1,
                             const __grid_constant__ CUtensorMap tm_kv2, const AttnParams p) {
@@ -243,9 +245,11 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       const int qt = 2 * qp + t;
       const bool active = qt < q_tiles;            // an odd tile count leaves warpgroup 1 without a tile in the last pair
       float m = 0.f, l = 0.f;
+      const uint32_t drop_rk = DROP ? drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qt * AT_BQ + row)) : 0u;
       for (int j = 0; j < nt; ++j, ++k) {
         const int rem = j < tiles1 ? p.NK1 - j * AT_BKV : p.NK2 - (j - tiles1) * AT_BKV;
         const int valid = min(AT_BKV, rem);
+        const uint32_t pair0 = j < tiles1 ? uint32_t(j * (AT_BKV / 2)) : (1u << 19) | uint32_t((j - tiles1) * (AT_BKV / 2));
         const bool full = valid == AT_BKV;            // warp-uniform: only a source's last tile can be ragged
         ATR_BEGIN;
         mbar_wait(&s_full[t], k & 1);
@@ -269,6 +273,11 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
                 if (MEBT_ATTN_POLY && ((i + e) & 3) == 3) v = ex2_poly(x); else v = ex2_approx(x);
                 pe[e] = ok ? v : 0.f;
                 l4[(i + e) & 3] += pe[e];
+              }
+              if (DROP) {              // the row sum keeps the undropped probabilities (dropout follows the softmax)
+                float f0, f1;
+                drop_pair(p.drop, drop_rk, pair0 + uint32_t(c * 16 + (i >> 1)), f0, f1);
+                pe[0] *= f0; pe[1] *= f1;
               }
               pk[i >> 1] = pack_bf16x2(pe[0], pe[1]);
             }
@@ -401,17 +410,18 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 extern "C" void mebt_attn_set_trace(long long* buf) { mebt::g_attn_trace = buf; }
 #endif
 
-extern "C" int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
-                                         int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0,
-                                         int NK2, void* O, int ldo, float* lse, int B, int H, int NQ, int head_dim,
-                                         void* stream) {
-  using namespace mebt;
+namespace mebt {
+int latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0, int NK1,
+                         const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, void* O, int ldo, float* lse, int B,
+                         int H, int NQ, int head_dim, float drop_p, unsigned long long drop_seed, void* stream) {
   MEBT_REQUIRE(head_dim == AT_HS, MEBT_ERR_UNSUPPORTED, "attention: head_dim %d unsupported (every MeBT config uses 64)",
                head_dim);
   MEBT_REQUIRE(B > 0 && H > 0 && NQ > 0 && NK1 >= 0 && NK2 >= 0, MEBT_ERR_SHAPE, "attention: bad shape");
   MEBT_REQUIRE(ldq % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0, MEBT_ERR_SHAPE, "attention: Q/O strides must be 16B aligned");
   MEBT_REQUIRE(NK1 == 0 || (KV1 != nullptr && ld1 % 8 == 0), MEBT_ERR_SHAPE, "attention: bad KV1");
   MEBT_REQUIRE(NK2 == 0 || (KV2 != nullptr && ld2 % 8 == 0), MEBT_ERR_SHAPE, "attention: bad KV2");
+  MEBT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MEBT_ERR_SHAPE, "attention: dropout p = %f outside [0, 1)", drop_p);
+  MEBT_REQUIRE(NK1 < (1 << 20) && NK2 < (1 << 20), MEBT_ERR_SHAPE, "attention: more than 2^20 keys per source");
   CUtensorMap tq, t1, t2;
   int rc = get_tensor_map_2d(&tq, Q, 2, uint64_t(ldq), uint64_t(B) * NQ, uint64_t(ldq) * 2, 64, 128);
   if (rc) return rc;
@@ -434,25 +444,68 @@ extern "C" int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, con
   p.lse = lse;
   p.scale = 0.125f;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.drop = make_drop_key(drop_p, drop_seed, 0);
 #ifdef MEBT_ATTN_TRACE
   p.trace = g_attn_trace;
 #else
   p.trace = nullptr;
 #endif
-  static bool attr = false;
-  if (!attr) {
-    MEBT_CUDA_OK(cudaFuncSetAttribute(latent_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      AT_SMEM_TOTAL));
-    attr = true;
+  const bool drop = p.drop.thr != 0;
+  auto kernel = drop ? latent_attention_fwd_kernel<true> : latent_attention_fwd_kernel<false>;
+  static bool attr[2] = {false, false};
+  if (!attr[drop]) {
+    MEBT_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_TOTAL));
+    attr[drop] = true;
   }
   const int n_items = B * H * (((NQ + AT_BQ - 1) / AT_BQ + 1) / 2);
   dim3 grid(n_items < sm_count() ? n_items : sm_count());
   {
     LaunchScope ls(FAM_ATTENTION, 4.0 * double(B) * H * double(NQ) * double(NK1 + NK2) * AT_HS,
                    static_cast<cudaStream_t>(stream));
-    MEBT_CUDA_OK(launch_pdl(latent_attention_fwd_kernel, grid, dim3(AT_THREADS), AT_SMEM_TOTAL,
-                            static_cast<cudaStream_t>(stream), tq, t1, t2, p));
+    MEBT_CUDA_OK(launch_pdl(kernel, grid, dim3(AT_THREADS), AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream), tq, t1, t2, p));
   }
   MEBT_LAUNCH_OK("latent_attention_fwd_kernel");
+  return MEBT_OK;
+}
+
+// The keep factors (0 or 1/(1-p)) the kernels above/below apply, materialised as fp32 [B, H, NQ, NK1 + NK2]: test
+// support (the oracle replays the same mask), not used on the product path.
+__global__ void attention_dropout_mask_kernel(float* __restrict__ out, int B, int H, int NQ, int NK1, int NK2, DropKey key) {
+  const long long total = (long long)B * H * NQ * (NK1 + NK2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kk = int(i % (NK1 + NK2));
+    const uint32_t row_id = uint32_t(i / (NK1 + NK2));       // (b * H + h) * NQ + q
+    const uint32_t kl = kk < NK1 ? uint32_t(kk) : (1u << 20) | uint32_t(kk - NK1);
+    float f0, f1;
+    drop_pair(key, drop_row_key(key, row_id), kl >> 1, f0, f1);
+    out[i] = key.thr == 0 ? 1.f : ((kl & 1u) ? f1 : f0);
+  }
+}
+}  // namespace mebt
+
+extern "C" int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
+                                         int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0,
+                                         int NK2, void* O, int ldo, float* lse, int B, int H, int NQ, int head_dim,
+                                         void* stream) {
+  return mebt::latent_attention_fwd(Q, ldq, q_col0, KV1, ld1, k1_col0, v1_col0, NK1, KV2, ld2, k2_col0, v2_col0, NK2, O, ldo,
+                                    lse, B, H, NQ, head_dim, 0.f, 0ull, stream);
+}
+
+extern "C" int mebt_latent_attention_fwd_dropout(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
+                                                 int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0,
+                                                 int v2_col0, int NK2, void* O, int ldo, float* lse, int B, int H, int NQ,
+                                                 int head_dim, float p, unsigned long long seed, void* stream) {
+  return mebt::latent_attention_fwd(Q, ldq, q_col0, KV1, ld1, k1_col0, v1_col0, NK1, KV2, ld2, k2_col0, v2_col0, NK2, O, ldo,
+                                    lse, B, H, NQ, head_dim, p, seed, stream);
+}
+
+extern "C" int mebt_attention_dropout_mask(float* out, int B, int H, int NQ, int NK1, int NK2, float p,
+                                           unsigned long long seed, void* stream) {
+  using namespace mebt;
+  MEBT_REQUIRE(out != nullptr && B > 0 && H > 0 && NQ > 0 && NK1 >= 0 && NK2 >= 0 && NK1 + NK2 > 0, MEBT_ERR_SHAPE,
+               "attention_dropout_mask: bad shape");
+  const DropKey key = make_drop_key(p, seed, 0);
+  attention_dropout_mask_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, B, H, NQ, NK1, NK2, key);
+  MEBT_LAUNCH_OK("attention_dropout_mask_kernel");
   return MEBT_OK;
 }

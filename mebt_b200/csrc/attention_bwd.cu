@@ -35,26 +35,38 @@ struct BwdParams {
   __nv_bfloat16* dQ; int lddq; int dq_col0;
   __nv_bfloat16* dKV; int lddkv; int dk_col0, dv_col0;
   float scale, scale_log2;
+  DropKey drop;              // attention-probability dropout of the forward (thr == 0: none)
+  int src;                   // dkv kernel: which key source this launch covers (0 / 1)
 };
 
 // One thread = one query row of the current [128 q x 128 k] tile pair (S and dP in TMEM).  Computes P and dS for
 // 32 keys at a time and stores them as bf16 into the 128B-swizzled [q][k] shared-memory tiles.
 __device__ __forceinline__ void softmax_bwd_row(uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_addr, int row,
                                                 bool row_ok, int valid_keys, float lse_l2, float delta, float scale,
-                                                float scale_log2, uint8_t* sP, uint8_t* sdS) {
+                                                float scale_log2, uint8_t* sP, uint8_t* sdS, const DropKey& dk,
+                                                uint32_t row_key, uint32_t pair0) {
+  // With dropout (keep factor f = 0 or 1/(1-p) per score): O = (P.f) V, so dV takes P.f, and dP = (dO V^T).f
+  const bool drop = dk.thr != 0;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     uint32_t rs[32], rd[32];
     tmem_ld_32x32(tmem_s + lane_addr + c * 32, rs);
     tmem_ld_32x32(tmem_dp + lane_addr + c * 32, rd);
     tmem_ld_wait();
-    float p[32], ds[32];
+    float p[32], ds[32], f[32];
+    if (drop) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) drop_pair(dk, row_key, pair0 + uint32_t(c * 16 + (i >> 1)), f[i], f[i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = 1.f;
+    }
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const bool ok = row_ok && (c * 32 + i < valid_keys);
       const float pv = ok ? ex2_approx(fmaf(__uint_as_float(rs[i]), scale_log2, -lse_l2)) : 0.f;
-      p[i] = pv;
-      ds[i] = ok ? pv * (__uint_as_float(rd[i]) - delta) * scale : 0.f;
+      p[i] = pv * f[i];
+      ds[i] = ok ? pv * (__uint_as_float(rd[i]) * f[i] - delta) * scale : 0.f;
     }
     const int off = (c >> 1) * (2 * TILE) / 2 + row * 128;     // half (64 keys) = one 16 KiB swizzle-atom column
 #pragma unroll
@@ -210,7 +222,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_fence_after();
       if (i > 0) mbar_wait(dkv_done, (i - 1) & 1);    // the previous tile's P / dS are no longer being read
       softmax_bwd_row(tmem_s, tmem_dp, lane_addr, row, row_ok, valid_keys, lse_l2, delta, p.scale, p.scale_log2,
-                      smem + DKV_SMEM_P, smem + DKV_SMEM_DS);
+                      smem + DKV_SMEM_P, smem + DKV_SMEM_DS, p.drop,
+                      drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qrow)), (uint32_t(p.src) << 19) | uint32_t(jt * 64));
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(pds_full);
@@ -343,7 +356,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_after();
       if (j > 0) mbar_wait(dq_done, (j - 1) & 1);
       softmax_bwd_row(tmem_s, tmem_dp, lane_addr, row, row_ok, valid, lse_l2, delta, p.scale, p.scale_log2, nullptr,
-                      smem + DQ_SMEM_DS);
+                      smem + DQ_SMEM_DS, p.drop, drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qrow)),
+                      j < tiles1 ? uint32_t(j * 64) : (1u << 19) | uint32_t((j - tiles1) * 64));
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(ds_full);
@@ -377,7 +391,20 @@ int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV
                               void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2, int ldd2, int dk2_col0,
                               int dv2_col0, int B, int H, int NQ, int head_dim, void* workspace, size_t workspace_bytes,
                               void* stream) {
+  return mebt_latent_attention_bwd_dropout(Q, ldq, q_col0, KV1, ld1, k1_col0, v1_col0, NK1, KV2, ld2, k2_col0, v2_col0, NK2,
+                                           O, ldo, dO, lddo, lse, dQ, lddq, dq_col0, dKV1, ldd1, dk1_col0, dv1_col0, dKV2,
+                                           ldd2, dk2_col0, dv2_col0, B, H, NQ, head_dim, 0.f, 0ull, workspace,
+                                           workspace_bytes, stream);
+}
+
+int mebt_latent_attention_bwd_dropout(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
+                                      int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2,
+                                      const void* O, int ldo, const void* dO, int lddo, const float* lse, void* dQ,
+                                      int lddq, int dq_col0, void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2,
+                                      int ldd2, int dk2_col0, int dv2_col0, int B, int H, int NQ, int head_dim, float drop_p,
+                                      unsigned long long drop_seed, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace mebt;
+  MEBT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MEBT_ERR_SHAPE, "attention_bwd: dropout p = %f outside [0, 1)", drop_p);
   MEBT_REQUIRE(head_dim == 64, MEBT_ERR_UNSUPPORTED, "attention_bwd: head_dim %d unsupported", head_dim);
   MEBT_REQUIRE(B > 0 && H > 0 && NQ > 0 && NK1 >= 0 && NK2 >= 0, MEBT_ERR_SHAPE, "attention_bwd: bad shape");
   MEBT_REQUIRE(workspace != nullptr && workspace_bytes >= size_t(B) * H * NQ * 4, MEBT_ERR_WORKSPACE,
@@ -410,6 +437,8 @@ int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV
   p.dQ = static_cast<__nv_bfloat16*>(dQ); p.lddq = lddq; p.dq_col0 = dq_col0;
   p.dKV = nullptr; p.lddkv = 0; p.dk_col0 = p.dv_col0 = 0;
   p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
+  p.drop = make_drop_key(drop_p, drop_seed, 0);
+  p.src = 0;
   const double flops_tile = 2.0 * 128 * 128 * 64;
   {
     const int nqt = (NQ + 127) / 128;
@@ -422,6 +451,7 @@ int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV
     if (NK == 0) continue;
     BwdParams pk = p;
     pk.NK = NK;
+    pk.src = src;
     pk.k_col0 = src == 0 ? k1_col0 : k2_col0;
     pk.v_col0 = src == 0 ? v1_col0 : v2_col0;
     pk.dKV = static_cast<__nv_bfloat16*>(src == 0 ? dKV1 : dKV2);

@@ -411,6 +411,40 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// ---- dropout (training): counter-based keep decisions, identical in forward and backward ----
+// One 32-bit hash per PAIR of adjacent elements (16 bits each); keep iff bits >= thr.  The hash is the "lowbias32"
+// integer finaliser applied to (row key + pair index * golden ratio); the row key mixes the 64-bit site seed with the
+// row id.  Reference: nn.Dropout / F.dropout (mebt/modules/gpt.py:112-113,140,150-155,239-242): y = x * keep / (1-p).
+struct DropKey {
+  uint32_t k0, k1;     // site seed
+  uint32_t thr;        // round(p * 65536); 0 = dropout off
+  float inv_keep;      // 65536 / (65536 - thr)
+};
+inline DropKey make_drop_key(float p, unsigned long long seed, unsigned long long site) {
+  DropKey k;
+  unsigned long long s = seed + (site + 1) * 0x9E3779B97F4A7C15ull;
+  s ^= s >> 30; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 27; s *= 0x94D049BB133111EBull; s ^= s >> 31;   // splitmix64
+  k.k0 = uint32_t(s);
+  k.k1 = uint32_t(s >> 32);
+  long t = lrintf(p * 65536.f);
+  k.thr = uint32_t(t < 0 ? 0 : (t > 65535 ? 65535 : t));
+  k.inv_keep = 65536.f / float(65536u - k.thr);
+  return k;
+}
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_row_key(const DropKey& k, uint32_t row_id) {
+  return mix32(k.k0 ^ mix32(row_id + k.k1));
+}
+// keep factors (inv_keep or 0) of elements 2*pair and 2*pair+1 of the row
+__host__ __device__ __forceinline__ void drop_pair(const DropKey& k, uint32_t row_key, uint32_t pair, float& f0, float& f1) {
+  const uint32_t h = mix32(row_key + pair * 0x9E3779B9u);
+  f0 = (h & 0xffffu) >= k.thr ? k.inv_keep : 0.f;
+  f1 = (h >> 16) >= k.thr ? k.inv_keep : 0.f;
+}
+
 // ---- small numeric helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -360,9 +360,61 @@ int layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const fl
   return MEBT_OK;
 }
 
+// ---- dropout on [rows, D] bf16 activations (training) ----
+// forward : y = resid + x * keep / (1-p)   (resid optional; in place when y == x)
+// backward: dx = dy * keep / (1-p)
+// 8 elements (16 bytes) per thread; the keep decisions are regenerated from (seed, site, row, column).
+__global__ void dropout_rows_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ resid,
+                                    int ldres, __nv_bfloat16* __restrict__ y, int ldy, int rows, int D, DropKey key) {
+  const int per_row = D >> 3;
+  const long long total = (long long)rows * per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = int(i / per_row), c8 = int(i - (long long)row * per_row) * 8;
+    const uint32_t rk = drop_row_key(key, uint32_t(row));
+    uint4 v = *reinterpret_cast<const uint4*>(x + (size_t)row * ldx + c8);
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (resid != nullptr) r = *reinterpret_cast<const uint4*>(resid + (size_t)row * ldres + c8);
+    uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
+    const uint32_t* rr = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f0, f1;
+      drop_pair(key, rk, uint32_t(c8 / 2 + j), f0, f1);
+      const float2 a = unpack_bf16x2(vv[j]);
+      const float2 b = unpack_bf16x2(rr[j]);
+      vv[j] = pack_bf16x2(fmaf(a.x, f0, b.x), fmaf(a.y, f1, b.y));
+    }
+    *reinterpret_cast<uint4*>(y + (size_t)row * ldy + c8) = v;
+  }
+}
+
+int dropout_rows(const void* x, int ldx, const void* resid, int ldres, void* y, int ldy, int rows, int D, float p,
+                 unsigned long long seed, unsigned long long site, cudaStream_t st) {
+  MEBT_REQUIRE(rows >= 0 && D > 0 && D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (resid == nullptr || ldres % 8 == 0),
+               MEBT_ERR_SHAPE, "dropout: D and the row strides must be multiples of 8");
+  MEBT_REQUIRE(p >= 0.f && p < 1.f, MEBT_ERR_SHAPE, "dropout: p = %f outside [0, 1)", p);
+  if (rows == 0) return MEBT_OK;
+  const DropKey key = make_drop_key(p, seed, site);
+  const long long total = (long long)rows * (D / 8);
+  const int blocks = int(std::min<long long>((total + 255) / 256, 148 * 8));
+  {
+    LaunchScope ls(FAM_OTHER, 0.0, st);
+    dropout_rows_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+                                                static_cast<const __nv_bfloat16*>(resid), ldres,
+                                                static_cast<__nv_bfloat16*>(y), ldy, rows, D, key);
+  }
+  MEBT_LAUNCH_OK("dropout_rows_kernel");
+  return MEBT_OK;
+}
+
 }  // namespace mebt
 
 extern "C" {
+
+int mebt_dropout_rows(const void* x, int ldx, const void* resid, int ldres, void* y, int ldy, int rows, int D, float p,
+                      unsigned long long seed, unsigned long long site, void* stream) {
+  return mebt::dropout_rows(x, ldx, resid, ldres, y, ldy, rows, D, p, seed, site, static_cast<cudaStream_t>(stream));
+}
 
 int mebt_embed_gather(const int64_t* x_indices, int x_stride, const int64_t* ctx_idx, int ctx_stride,
                       const int64_t* tgt_idx, int tgt_stride, const float* tok_emb, const float* pos_emb,

@@ -29,6 +29,8 @@ int layernorm_bwd_resid(const void* dy, const void* x, const float* mean, const 
 size_t layernorm_bwd_workspace_bytes(int D);
 int colsum(const void* X, int ld, int rows, int N, float* out, int accumulate, float* workspace, size_t ws_bytes,
            cudaStream_t st);
+int dropout_rows(const void* x, int ldx, const void* resid, int ldres, void* y, int ldy, int rows, int D, float p,
+                 unsigned long long seed, unsigned long long site, cudaStream_t st);
 
 namespace {
 
@@ -117,6 +119,7 @@ size_t backward_workspace_bytes(int B, int L, int NC, int NT, int D, int H) {
   t += al(rk * D * 2);             // dkn
   t += al(size_t(B) * H * (L > NT ? L : NT) * 4);   // attention delta
   t += al(rmax * D * 2);           // dx (kept separate from the stream gradient: the side stream still reads d_out)
+  t += 2 * al(rmax * D * 2);       // dropout: gradients w.r.t. the pre-dropout MLP / proj outputs
   size_t red = layernorm_bwd_workspace_bytes(D);
   const size_t cs = size_t(64) * 16384 * 4;         // column-sum partials up to N = 16384
   t += 2 * al(red > cs ? red : cs);                 // one reduction scratch per stream
@@ -142,7 +145,18 @@ int mebt_stack_forward_train(const mebt_layer_t* layers, int n_layers, const flo
                              const void* w_head, int B, int L, int NC, int NT, int D, int H, int V, const void* lat0,
                              const void* ctx, const void* tgt0, void* logits, int logits_dtype, void* saved,
                              size_t saved_bytes, void* stream) {
+  return mebt_stack_forward_train_dropout(layers, n_layers, lnf_w, lnf_b, w_head, B, L, NC, NT, D, H, V, lat0, ctx, tgt0,
+                                          logits, logits_dtype, saved, saved_bytes, nullptr, stream);
+}
+
+int mebt_stack_forward_train_dropout(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                                     const void* w_head, int B, int L, int NC, int NT, int D, int H, int V,
+                                     const void* lat0, const void* ctx, const void* tgt0, void* logits, int logits_dtype,
+                                     void* saved, size_t saved_bytes, const mebt_dropout_t* drop, void* stream) {
   using namespace mebt;
+  const float attn_p = drop != nullptr ? drop->attn_p : 0.f, resid_p = drop != nullptr ? drop->resid_p : 0.f;
+  const unsigned long long seed = drop != nullptr ? drop->seed : 0ull;
+  MEBT_REQUIRE(attn_p >= 0.f && attn_p < 1.f && resid_p >= 0.f && resid_p < 1.f, MEBT_ERR_SHAPE, "forward_train: bad dropout p");
   MEBT_REQUIRE(B > 0 && L > 0 && NC >= 0 && NT > 0 && D == H * 64, MEBT_ERR_SHAPE, "forward_train: bad shape");
   for (int i = 0; i < n_layers; ++i)
     MEBT_REQUIRE(layers[i].mode >= MEBT_MODE_LATENT_ENC && layers[i].mode <= MEBT_MODE_LT2L, MEBT_ERR_UNSUPPORTED,
@@ -178,17 +192,28 @@ int mebt_stack_forward_train(const mebt_layer_t* layers, int n_layers, const flo
       TRY(gemm_bf16_aux(kn, D, 0, w_kv, D, 0, kv, 2 * D, s.rk, 2 * D, D, b_kv, nullptr, 0, nullptr, 0, 0, st));
     }
     const int nk_sep = s.rk / B;
+    const unsigned long long site = 4ull * i;      // + 0: attention, + 1: proj, + 2: mlp
     if (fused)
-      TRY(mebt_latent_attention_fwd(qkv, 3 * D, 0, qkv, 3 * D, D, 2 * D, L, s.rk > 0 ? kv : nullptr, 2 * D, 0, D, nk_sep,
-                                    att, D, lse, B, H, s.nq, 64, stream));
+      TRY(mebt_latent_attention_fwd_dropout(qkv, 3 * D, 0, qkv, 3 * D, D, 2 * D, L, s.rk > 0 ? kv : nullptr, 2 * D, 0, D,
+                                            nk_sep, att, D, lse, B, H, s.nq, 64, attn_p, seed + site, stream));
     else
-      TRY(mebt_latent_attention_fwd(qkv, D, 0, s.rk > 0 ? kv : nullptr, 2 * D, 0, D, nk_sep, nullptr, 0, 0, 0, 0, att, D,
-                                    lse, B, H, s.nq, 64, stream));
-    TRY(gemm_bf16_aux(att, D, 0, w.w_proj, D, 0, x, D, s.rq, D, D, w.b_proj, qn, D, nullptr, 0, 0, st));
+      TRY(mebt_latent_attention_fwd_dropout(qkv, D, 0, s.rk > 0 ? kv : nullptr, 2 * D, 0, D, nk_sep, nullptr, 0, 0, 0, 0,
+                                            att, D, lse, B, H, s.nq, 64, attn_p, seed + site, stream));
+    if (resid_p > 0.f) {     // x = qn + drop(att Wp + b): the GEMM leaves the pre-dropout value, the dropout kernel adds qn
+      TRY(gemm_bf16_aux(att, D, 0, w.w_proj, D, 0, x, D, s.rq, D, D, w.b_proj, nullptr, 0, nullptr, 0, 0, st));
+      TRY(dropout_rows(x, D, qn, D, x, D, s.rq, D, resid_p, seed, site + 1, st));
+    } else {
+      TRY(gemm_bf16_aux(att, D, 0, w.w_proj, D, 0, x, D, s.rq, D, D, w.b_proj, qn, D, nullptr, 0, 0, st));
+    }
     TRY(layernorm(x, D, MEBT_DTYPE_BF16, w.ln2_w, w.ln2_b, h, D, MEBT_DTYPE_BF16, s.rq, D, 1e-5f,
                   reinterpret_cast<float*>(S + s.x_mean), reinterpret_cast<float*>(S + s.x_rstd), st));
     TRY(gemm_bf16_aux(h, D, 0, w.w_fc1, D, 0, u, 4 * D, s.rq, 4 * D, D, w.b_fc1, nullptr, 0, a, 4 * D, MEBT_GEMM_GELU, st));
-    TRY(gemm_bf16_aux(u, 4 * D, 0, w.w_fc2, 4 * D, 0, out, D, s.rq, D, 4 * D, w.b_fc2, x, D, nullptr, 0, 0, st));
+    if (resid_p > 0.f) {     // out = x + drop(u W2 + b)
+      TRY(gemm_bf16_aux(u, 4 * D, 0, w.w_fc2, 4 * D, 0, out, D, s.rq, D, 4 * D, w.b_fc2, nullptr, 0, nullptr, 0, 0, st));
+      TRY(dropout_rows(out, D, x, D, out, D, s.rq, D, resid_p, seed, site + 2, st));
+    } else {
+      TRY(gemm_bf16_aux(u, 4 * D, 0, w.w_fc2, 4 * D, 0, out, D, s.rq, D, 4 * D, w.b_fc2, x, D, nullptr, 0, 0, st));
+    }
     if (w.mode == MEBT_MODE_LATENT_DEC) tgt = out; else lat = out;
   }
   TRY(layernorm(tgt, D, MEBT_DTYPE_BF16, lnf_w, lnf_b, S + plan.xf, D, MEBT_DTYPE_BF16, B * NT, D, 1e-5f,
@@ -203,7 +228,21 @@ int mebt_stack_backward(const mebt_layer_t* layers, const mebt_layer_grads_t* gr
                         int D, int H, int V, const void* lat0, const void* ctx, const void* tgt0, const void* dlogits,
                         void* saved, size_t saved_bytes, void* d_lat, void* d_ctx, void* d_tgt, int layer_begin,
                         int layer_end, int grad_accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  return mebt_stack_backward_dropout(layers, grads, n_layers, lnf_w, d_lnf_w, d_lnf_b, w_head, d_w_head, B, L, NC, NT, D, H, V,
+                                     lat0, ctx, tgt0, dlogits, saved, saved_bytes, d_lat, d_ctx, d_tgt, layer_begin,
+                                     layer_end, grad_accumulate, nullptr, workspace, workspace_bytes, stream);
+}
+
+int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_grads_t* grads, int n_layers,
+                                const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const void* w_head, float* d_w_head,
+                                int B, int L, int NC, int NT, int D, int H, int V, const void* lat0, const void* ctx,
+                                const void* tgt0, const void* dlogits, void* saved, size_t saved_bytes, void* d_lat,
+                                void* d_ctx, void* d_tgt, int layer_begin, int layer_end, int grad_accumulate,
+                                const mebt_dropout_t* drop, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace mebt;
+  const float attn_p = drop != nullptr ? drop->attn_p : 0.f, resid_p = drop != nullptr ? drop->resid_p : 0.f;
+  const unsigned long long seed = drop != nullptr ? drop->seed : 0ull;
+  MEBT_REQUIRE(attn_p >= 0.f && attn_p < 1.f && resid_p >= 0.f && resid_p < 1.f, MEBT_ERR_SHAPE, "backward: bad dropout p");
   MEBT_REQUIRE(B > 0 && L > 0 && NC >= 0 && NT > 0 && D == H * 64, MEBT_ERR_SHAPE, "backward: bad shape");
   MEBT_REQUIRE(0 <= layer_begin && layer_begin <= layer_end && layer_end <= n_layers, MEBT_ERR_SHAPE, "backward: bad layer range");
   const Plan plan = make_plan(layers, n_layers, B, L, NC, NT, D, H);
@@ -226,6 +265,8 @@ int mebt_stack_backward(const mebt_layer_t* layers, const mebt_layer_grads_t* gr
   const size_t delta_bytes = size_t(B) * H * (L > NT ? L : NT) * 4;
   void* delta = take(delta_bytes);
   void* dxb = take(rmax * D * 2);
+  void* dy_mlp = take(rmax * D * 2);     // d_out .* keep/(1-p): gradient w.r.t. the pre-dropout MLP output
+  void* dy_proj = take(rmax * D * 2);    // dx .* keep/(1-p): gradient w.r.t. the pre-dropout proj output
   const size_t red_each = ((workspace_bytes - off - 512) / 2) & ~size_t(255);
   const size_t red_bytes = red_each;
   float* red = reinterpret_cast<float*>(W + off);
@@ -312,9 +353,15 @@ int mebt_stack_backward(const mebt_layer_t* layers, const mebt_layer_grads_t* gr
     void* d_k_stream = mode == MEBT_MODE_LATENT_ENC ? d_ctx : mode == MEBT_MODE_LATENT_DEC ? d_lat : mode == MEBT_MODE_LT2L ? d_tgt : nullptr;
     const int rq = s.rq, rk = s.rk;
 
+    const unsigned long long site = 4ull * i;
     // ---- MLP ----  (main stream: the data-gradient chain; side stream: weight and bias gradients)
-    TRY(SIDE_LINEAR(0, d_out, D, S + s.u, 4 * D, g.w_fc2, 4 * D, g.b_fc2, D, 4 * D, rq, acc));
-    TRY(DGRAD(d_out, D, w.w_fc2, 4 * D, da, rq, 4 * D, D, nullptr, S + s.a, 4 * D, MEBT_GEMM_DGELU));     // da
+    const void* d_mlp = d_out;                      // gradient w.r.t. (u W2 + b): d_out through the dropout mask
+    if (resid_p > 0.f) {
+      TRY(dropout_rows(d_out, D, nullptr, 0, dy_mlp, D, rq, D, resid_p, seed, site + 2, st));
+      d_mlp = dy_mlp;
+    }
+    TRY(SIDE_LINEAR(0, d_mlp, D, S + s.u, 4 * D, g.w_fc2, 4 * D, g.b_fc2, D, 4 * D, rq, acc));
+    TRY(DGRAD(d_mlp, D, w.w_fc2, 4 * D, da, rq, 4 * D, D, nullptr, S + s.a, 4 * D, MEBT_GEMM_DGELU));     // da
     TRY(SIDE_LINEAR(1, da, 4 * D, S + s.h, D, g.w_fc1, D, g.b_fc1, 4 * D, D, rq, acc));
     TRY(DGRAD(da, 4 * D, w.w_fc1, D, dh, rq, D, 4 * D, nullptr, nullptr, 0, 0));                            // dh
     // dx = d_out + ln2'(dh), written to its own buffer (d_out is still being read by the side stream)
@@ -323,19 +370,26 @@ int mebt_stack_backward(const mebt_layer_t* layers, const mebt_layer_grads_t* gr
                             w.ln2_w, dx, d_out, g.ln2_w, g.ln2_b, acc, rq, D, red, red_bytes, st));
     // ---- attention output projection ----
     void* datt = dh;
-    TRY(SIDE_LINEAR(2, dx, D, S + s.att, D, g.w_proj, D, g.b_proj, D, D, rq, acc));
-    TRY(DGRAD(dx, D, w.w_proj, D, datt, rq, D, D, nullptr, nullptr, 0, 0));
+    const void* d_proj = dx;                        // gradient w.r.t. (att Wp + b)
+    if (resid_p > 0.f) {
+      TRY(dropout_rows(dx, D, nullptr, 0, dy_proj, D, rq, D, resid_p, seed, site + 1, st));
+      d_proj = dy_proj;
+    }
+    TRY(SIDE_LINEAR(2, d_proj, D, S + s.att, D, g.w_proj, D, g.b_proj, D, D, rq, acc));
+    TRY(DGRAD(d_proj, D, w.w_proj, D, datt, rq, D, D, nullptr, nullptr, 0, 0));
     // ---- attention ----
     const int nk_sep = rk / B;
     const float* lse = reinterpret_cast<float*>(S + s.lse);
     if (fused)
-      TRY(mebt_latent_attention_bwd(S + s.qkv, 3 * D, 0, S + s.qkv, 3 * D, D, 2 * D, L, rk > 0 ? S + s.kv : nullptr, 2 * D, 0, D,
-                                    nk_sep, S + s.att, D, datt, D, lse, dqkv, 3 * D, 0, dqkv, 3 * D, D, 2 * D,
-                                    rk > 0 ? dkv : nullptr, 2 * D, 0, D, B, H, s.nq, 64, delta, delta_bytes, stream));
+      TRY(mebt_latent_attention_bwd_dropout(S + s.qkv, 3 * D, 0, S + s.qkv, 3 * D, D, 2 * D, L, rk > 0 ? S + s.kv : nullptr,
+                                            2 * D, 0, D, nk_sep, S + s.att, D, datt, D, lse, dqkv, 3 * D, 0, dqkv, 3 * D, D,
+                                            2 * D, rk > 0 ? dkv : nullptr, 2 * D, 0, D, B, H, s.nq, 64, attn_p, seed + site,
+                                            delta, delta_bytes, stream));
     else
-      TRY(mebt_latent_attention_bwd(S + s.qkv, D, 0, rk > 0 ? S + s.kv : nullptr, 2 * D, 0, D, nk_sep, nullptr, 0, 0, 0, 0,
-                                    S + s.att, D, datt, D, lse, dqkv, D, 0, rk > 0 ? dkv : nullptr, 2 * D, 0, D, nullptr, 0,
-                                    0, 0, B, H, s.nq, 64, delta, delta_bytes, stream));
+      TRY(mebt_latent_attention_bwd_dropout(S + s.qkv, D, 0, rk > 0 ? S + s.kv : nullptr, 2 * D, 0, D, nk_sep, nullptr, 0, 0,
+                                            0, 0, S + s.att, D, datt, D, lse, dqkv, D, 0, rk > 0 ? dkv : nullptr, 2 * D, 0,
+                                            D, nullptr, 0, 0, 0, B, H, s.nq, 64, attn_p, seed + site, delta, delta_bytes,
+                                            stream));
     // ---- q/k/v projections ----
     const int qw = fused ? 3 * D : D;
     TRY(SIDE_LINEAR(3, dqkv, qw, S + s.qn, D, g.w_qkv, D, g.b_qkv, qw, D, rq, acc));

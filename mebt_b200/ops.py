@@ -116,16 +116,18 @@ def layernorm(x, gamma, beta, out=None, out_dtype=None, eps=1e-5, save_stats=Fal
     return (out, mean, rstd) if save_stats else out
 
 
-def attention(q, q_col0, kv1, k1_col0, v1_col0, nk1, kv2, k2_col0, v2_col0, nk2, B, H, NQ, out=None, lse=None):
-    """q: [B*NQ, ldq] bf16 buffer; kv1/kv2: [B*NK, ld] buffers (or None).  Returns O [B*NQ, H*64] bf16."""
+def attention(q, q_col0, kv1, k1_col0, v1_col0, nk1, kv2, k2_col0, v2_col0, nk2, B, H, NQ, out=None, lse=None,
+              drop_p=0.0, drop_seed=0):
+    """q: [B*NQ, ldq] bf16 buffer; kv1/kv2: [B*NK, ld] buffers (or None).  Returns O [B*NQ, H*64] bf16.
+    drop_p > 0: attn_drop on the softmax output (training mode, gpt.py:136)."""
     _need_cuda(q, kv1, kv2)
     D = H * 64
     if out is None:
         out = torch.empty(B * NQ, D, device=q.device, dtype=torch.bfloat16)
-    call("mebt_latent_attention_fwd", q.data_ptr(), q.stride(0), q_col0,
+    call("mebt_latent_attention_fwd_dropout", q.data_ptr(), q.stride(0), q_col0,
          _ptr(kv1) if nk1 > 0 else None, kv1.stride(0) if nk1 > 0 else 0, k1_col0, v1_col0, nk1,
          _ptr(kv2) if nk2 > 0 else None, kv2.stride(0) if nk2 > 0 else 0, k2_col0, v2_col0, nk2,
-         out.data_ptr(), out.stride(0), _ptr(lse), B, H, NQ, 64, _stream())
+         out.data_ptr(), out.stride(0), _ptr(lse), B, H, NQ, 64, float(drop_p), int(drop_seed), _stream())
     return out
 
 
@@ -323,13 +325,34 @@ def embed_backward(x_indices, ctx_idx, tgt_idx, d_ctx, d_tgt, d_lat, d_tok, d_po
 
 
 def attention_bwd(q, q_col0, kv1, k1_col0, v1_col0, nk1, kv2, k2_col0, v2_col0, nk2, o, do, lse, dq, dq_col0, dkv1,
-                  dk1_col0, dv1_col0, dkv2, dk2_col0, dv2_col0, B, H, NQ):
+                  dk1_col0, dv1_col0, dkv2, dk2_col0, dv2_col0, B, H, NQ, drop_p=0.0, drop_seed=0):
     nbytes = _lib.lib.mebt_latent_attention_bwd_workspace_bytes(B, H, NQ)
     ws = _ws(q.device, nbytes, "attn")
-    call("mebt_latent_attention_bwd", q.data_ptr(), q.stride(0), q_col0,
+    call("mebt_latent_attention_bwd_dropout", q.data_ptr(), q.stride(0), q_col0,
          _ptr(kv1) if nk1 else None, kv1.stride(0) if nk1 else 0, k1_col0, v1_col0, nk1,
          _ptr(kv2) if nk2 else None, kv2.stride(0) if nk2 else 0, k2_col0, v2_col0, nk2,
          o.data_ptr(), o.stride(0), do.data_ptr(), do.stride(0), lse.data_ptr(), dq.data_ptr(), dq.stride(0), dq_col0,
          _ptr(dkv1) if nk1 else None, dkv1.stride(0) if nk1 else 0, dk1_col0, dv1_col0,
-         _ptr(dkv2) if nk2 else None, dkv2.stride(0) if nk2 else 0, dk2_col0, dv2_col0, B, H, NQ, 64, ws.data_ptr(),
-         ws.numel(), _stream())
+         _ptr(dkv2) if nk2 else None, dkv2.stride(0) if nk2 else 0, dk2_col0, dv2_col0, B, H, NQ, 64, float(drop_p),
+         int(drop_seed), ws.data_ptr(), ws.numel(), _stream())
+
+
+def dropout_rows_(x, p: float, seed: int, site: int, resid=None):
+    """In-place training-mode dropout of a bf16 [rows, D] activation: x <- (resid +) x * keep / (1-p), keep a pure
+    function of (seed, site, row, column) (nn.Dropout, mebt/modules/gpt.py:216,239-241).  Backward = the same call on dy."""
+    _need_cuda(x)
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.stride(1) != 1:
+        raise MebtError("dropout_rows_: bf16 [rows, D] with unit column stride expected")
+    if x.shape[0] == 0:
+        return x
+    call("mebt_dropout_rows", x.data_ptr(), x.stride(0), resid.data_ptr() if resid is not None else None,
+         resid.stride(0) if resid is not None else 0, x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], float(p),
+         int(seed), int(site), _stream())
+    return x
+
+
+def attention_dropout_mask(B, H, NQ, NK1, NK2, p: float, seed: int, device="cuda"):
+    """Keep factors (0 or 1/(1-p)) the attention kernels apply for (p, seed): fp32 [B, H, NQ, NK1+NK2] (test support)."""
+    out = torch.empty(B, H, NQ, NK1 + NK2, device=device, dtype=torch.float32)
+    call("mebt_attention_dropout_mask", out.data_ptr(), B, H, NQ, NK1, NK2, float(p), int(seed), _stream())
+    return out

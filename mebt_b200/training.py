@@ -46,9 +46,11 @@ class TrainState:
             if m not in ("latent_enc", "latent_self", "latent_dec", "lt2l"):
                 raise NotImplementedError(f"training supports the four latent block modes, not {m!r}")
         cfg = gpt.config
-        for name in ("embd_pdrop", "resid_pdrop", "attn_pdrop"):
-            if getattr(cfg, name, 0.0) > 0:
-                raise NotImplementedError("mebt_b200 training path: dropout > 0 is not implemented (use p = 0)")
+        # nn.Dropout probabilities of the reference (gpt.py:112-113,154,216); applied only while model.training
+        self.embd_pdrop = float(getattr(cfg, "embd_pdrop", 0.0))
+        self.resid_pdrop = float(getattr(cfg, "resid_pdrop", 0.0))
+        self.attn_pdrop = float(getattr(cfg, "attn_pdrop", 0.0))
+        self.dropout_seed = None          # set to an int to pin the masks (tests); default: drawn from torch's RNG per step
         self.D, self.H, self.V = cfg.n_embd, cfg.n_head, gpt.head.weight.shape[0]
         self.L = model.sos_emb.shape[1]
         named = dict(model.named_parameters())
@@ -121,6 +123,20 @@ class TrainState:
             self._bwd_ws = torch.empty(int(ws_bytes * 1.1), dtype=torch.uint8, device=self.device)
         return self._saved, self._bwd_ws
 
+    # stem dropout sites (GPT.forward drops sos_emb, contexts, targets before the blocks, gpt.py:239-241; the fourth
+    # dropout, on mask_emb, feeds nothing in the latent modes)
+    STEM_SITES = {"lat": 1 << 20, "ctx": (1 << 20) + 1, "tgt": (1 << 20) + 2}
+
+    def _dropout(self):
+        """-> (DropoutStruct or None, embd_p, seed) for this step: active only in training mode, like nn.Dropout."""
+        if not self.model.transformer.training or max(self.embd_pdrop, self.resid_pdrop, self.attn_pdrop) <= 0.0:
+            return None, 0.0, 0
+        seed = self.dropout_seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # CPU generator: follows torch.manual_seed
+        d = _lib.DropoutStruct(self.attn_pdrop, self.resid_pdrop, seed)
+        return d, self.embd_pdrop, seed
+
     def forward(self, x_indices, ctx_idx, tgt_idx, logits_dtype=torch.bfloat16):
         """Stem + stack forward keeping activations.  -> logits [B*NT, V]."""
         m = self.model
@@ -128,20 +144,25 @@ class TrainState:
         NC, NT = ctx_idx.shape[1], tgt_idx.shape[1]
         saved, _ = self._buffers(B, NC, NT)
         ctx, tgt, lat = ops.embed_gather(x_indices, ctx_idx, tgt_idx, m.tok_emb.weight, m.pos_emb, m.mask_emb, m.sos_emb)
+        drop, embd_p, seed = self._dropout()
+        if embd_p > 0.0:
+            for name, stream_t in (("lat", lat), ("ctx", ctx), ("tgt", tgt)):
+                ops.dropout_rows_(stream_t, embd_p, seed, self.STEM_SITES[name])
         logits = torch.empty(B * NT, self.V, device=self.device, dtype=logits_dtype)
         st = torch.cuda.current_stream().cuda_stream
-        call("mebt_stack_forward_train", self.c_layers, len(self.modes), self._view(self.flat, "transformer.ln_f.weight").data_ptr(),
+        call("mebt_stack_forward_train_dropout", self.c_layers, len(self.modes),
+             self._view(self.flat, "transformer.ln_f.weight").data_ptr(),
              self._view(self.flat, "transformer.ln_f.bias").data_ptr(),
              self._view(self.flat_bf16, "transformer.head.weight").data_ptr(), B, self.L, NC, NT, self.D, self.H, self.V,
              lat.data_ptr(), ctx.data_ptr(), tgt.data_ptr(), logits.data_ptr(), ops._DT[logits_dtype], saved.data_ptr(),
-             saved.numel(), st)
-        self._ctx = (B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt)
+             saved.numel(), ctypes.byref(drop) if drop is not None else None, st)
+        self._ctx = (B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt, drop, embd_p, seed)
         return logits
 
     def backward(self, dlogits, accumulate=False, world_size=1):
         """Stack + stem backward into the flat gradient buffer; with world_size > 1 each finished chunk of blocks is
         all-reduced (averaged) on a side stream while the next chunk runs."""
-        B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt = self._ctx
+        B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt, drop, embd_p, seed = self._ctx
         if dlogits.dtype != torch.bfloat16 or not dlogits.is_contiguous():
             raise MebtError("dlogits must be contiguous bf16 [B*NT, V]")
         m = self.model
@@ -158,20 +179,23 @@ class TrainState:
         works = []
         for ci in range(len(self.chunks) - 1, -1, -1):
             lb, le = self.chunks[ci]
-            call("mebt_stack_backward", self.c_layers, self.c_grads, n,
+            call("mebt_stack_backward_dropout", self.c_layers, self.c_grads, n,
                  self._view(self.flat, "transformer.ln_f.weight").data_ptr(),
                  self._view(self.flat_grad, "transformer.ln_f.weight").data_ptr(),
                  self._view(self.flat_grad, "transformer.ln_f.bias").data_ptr(),
                  self._view(self.flat_bf16, "transformer.head.weight").data_ptr(),
                  self._view(self.flat_grad, "transformer.head.weight").data_ptr(), B, self.L, NC, NT, self.D, self.H, self.V,
                  lat.data_ptr(), ctx.data_ptr(), tgt.data_ptr(), dlogits.data_ptr(), saved.data_ptr(), saved.numel(),
-                 d_lat.data_ptr(), d_ctx.data_ptr(), d_tgt.data_ptr(), lb, le, int(accumulate), ws.data_ptr(), ws.numel(),
-                 cur.cuda_stream)
+                 d_lat.data_ptr(), d_ctx.data_ptr(), d_tgt.data_ptr(), lb, le, int(accumulate),
+                 ctypes.byref(drop) if drop is not None else None, ws.data_ptr(), ws.numel(), cur.cuda_stream)
             if world_size > 1:
                 lo, hi = self.block_slices[lb][0], self.block_slices[le - 1][1]
                 works.append(self._all_reduce_async(lo, hi, cur))
                 if le == n:
                     works.append(self._all_reduce_async(*self.head_slice, cur))
+        if embd_p > 0.0:                                        # backward of the stem dropout: the same masks
+            for name, grad_t in (("lat", d_lat), ("ctx", d_ctx), ("tgt", d_tgt)):
+                ops.dropout_rows_(grad_t, embd_p, seed, self.STEM_SITES[name])
         g = lambda name: self._view(self.flat_grad, name)
         ops.embed_backward(x_indices, ctx_idx, tgt_idx, d_ctx, d_tgt, d_lat, g("tok_emb.weight").view(-1, self.D),
                            g("pos_emb").view(-1, self.D), g("mask_emb"), g("sos_emb").view(-1, self.D))

@@ -79,8 +79,10 @@ def layer_norm(x, w, b):
     return F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
 
 
-def cross_attention(P: dict, pre: str, q_in, k_in, n_head: int):
-    """CrossAttention.forward, gpt.py:119-141 (dropout = identity, attn_bias = 0.)."""
+def cross_attention(P: dict, pre: str, q_in, k_in, n_head: int, attn_keep=None, resid_keep=None):
+    """CrossAttention.forward, gpt.py:119-141 (attn_bias = 0.).  Dropout: eval mode / p = 0 when the keep tensors are
+    None; otherwise `attn_keep` [B,h,NQ,NK] and `resid_keep` [B,NQ,C] hold nn.Dropout's factors (0 or 1/(1-p)) for
+    attn_drop (gpt.py:136) and resid_drop (gpt.py:140), so that a recorded or replayed mask gives the training-mode result."""
     B, NQ, C = q_in.shape
     NK = k_in.shape[1]
     hs = C // n_head
@@ -89,12 +91,19 @@ def cross_attention(P: dict, pre: str, q_in, k_in, n_head: int):
     v = F.linear(k_in, P[pre + "value.weight"], P[pre + "value.bias"]).view(B, NK, n_head, hs).transpose(1, 2)
     att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(hs))
     att = F.softmax(att, dim=-1)          # NK == 0 -> empty softmax -> y == 0
+    if attn_keep is not None:
+        att = att * attn_keep
     y = (att @ v).transpose(1, 2).contiguous().view(B, NQ, C)
-    return F.linear(y, P[pre + "proj.weight"], P[pre + "proj.bias"])
+    y = F.linear(y, P[pre + "proj.weight"], P[pre + "proj.bias"])
+    if resid_keep is not None:
+        y = y * resid_keep
+    return y
 
 
-def block_forward(P: dict, i: int, mode: str, n_head: int, lat, ctx, tgt):
-    """Block.forward, gpt.py:159-195: shared ln1 on query and key; residual on the NORMALISED query."""
+def block_forward(P: dict, i: int, mode: str, n_head: int, lat, ctx, tgt, drop=None):
+    """Block.forward, gpt.py:159-195: shared ln1 on query and key; residual on the NORMALISED query.
+    `drop`: optional dict of dropout keep factors {(i,"attn"), (i,"proj"), (i,"mlp")} (training mode, gpt.py:136,140,154)."""
+    drop = drop or {}
     pre = f"transformer.blocks.{i}."
     if mode == "latent_self":
         q, k = lat, lat
@@ -111,11 +120,14 @@ def block_forward(P: dict, i: int, mode: str, n_head: int, lat, ctx, tgt):
         raise ValueError(mode)
     qn = layer_norm(q, P[pre + "ln1.weight"], P[pre + "ln1.bias"])
     kn = layer_norm(k, P[pre + "ln1.weight"], P[pre + "ln1.bias"])
-    x = qn + cross_attention(P, pre + "attn.", qn, kn, n_head)
+    x = qn + cross_attention(P, pre + "attn.", qn, kn, n_head, drop.get((i, "attn")), drop.get((i, "proj")))
     h = layer_norm(x, P[pre + "ln2.weight"], P[pre + "ln2.bias"])
     h = F.linear(h, P[pre + "mlp.0.weight"], P[pre + "mlp.0.bias"])
     h = F.gelu(h)                          # nn.GELU() = exact erf form (gpt.py:152)
-    x = x + F.linear(h, P[pre + "mlp.2.weight"], P[pre + "mlp.2.bias"])
+    h = F.linear(h, P[pre + "mlp.2.weight"], P[pre + "mlp.2.bias"])
+    if (i, "mlp") in drop:
+        h = h * drop[(i, "mlp")]
+    x = x + h
     if mode in ("latent_enc", "latent_self", "lt2l"):
         lat = x
     elif mode == "latent_dec":
@@ -144,10 +156,15 @@ def stem(P: dict, cfg: dict, x_indices, ctx_idx, tgt_idx):
     return lat, ctx, tgt
 
 
-def gpt_forward(P: dict, cfg: dict, lat, ctx, tgt, return_hidden: bool = False):
-    """GPT.forward, gpt.py:234-253 (eval mode / p=0: the four stem dropouts are identity)."""
+def gpt_forward(P: dict, cfg: dict, lat, ctx, tgt, return_hidden: bool = False, drop=None):
+    """GPT.forward, gpt.py:234-253.  Eval mode / p=0 when `drop` is None (the stem dropouts are identity); otherwise
+    `drop` maps ("stem","lat"|"ctx"|"tgt") and (i,"attn"|"proj"|"mlp") to keep factors (gpt.py:239-241 and the blocks)."""
+    if drop:
+        lat = lat * drop[("stem", "lat")] if ("stem", "lat") in drop else lat
+        ctx = ctx * drop[("stem", "ctx")] if ("stem", "ctx") in drop else ctx
+        tgt = tgt * drop[("stem", "tgt")] if ("stem", "tgt") in drop else tgt
     for i, mode in enumerate(stack_modes(cfg)):
-        lat, ctx, tgt = block_forward(P, i, mode, cfg["n_head"], lat, ctx, tgt)
+        lat, ctx, tgt = block_forward(P, i, mode, cfg["n_head"], lat, ctx, tgt, drop)
     x = layer_norm(tgt, P["transformer.ln_f.weight"], P["transformer.ln_f.bias"])
     logits = F.linear(x, P["transformer.head.weight"])
     if return_hidden:
@@ -155,12 +172,12 @@ def gpt_forward(P: dict, cfg: dict, lat, ctx, tgt, return_hidden: bool = False):
     return logits
 
 
-def reconstruct_mask(P: dict, cfg: dict, x_indices, ctx_idx, tgt_idx):
+def reconstruct_mask(P: dict, cfg: dict, x_indices, ctx_idx, tgt_idx, drop=None):
     """Net2NetTransformer.reconstruct_mask, transformer.py:288-324 -> logits [B,NT,V] fp32."""
     B = x_indices.shape[0]
     x_indices = x_indices.reshape(B, -1)
     lat, ctx, tgt = stem(P, cfg, x_indices, ctx_idx, tgt_idx)
-    return gpt_forward(P, cfg, lat, ctx, tgt)
+    return gpt_forward(P, cfg, lat, ctx, tgt, drop=drop)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -315,7 +332,7 @@ def masked_ce(logits, targets, label_smoothing: float = 0.0):
     return ce, int(hit[:, :1].sum()), int(hit.sum())
 
 
-def shared_step(P, cfg, x_indices, indices, t: float, schedule_name: str, label_smoothing=0.0):
+def shared_step(P, cfg, x_indices, indices, t: float, schedule_name: str, label_smoothing=0.0, drop=None):
     """forward + shared_step for a full-length clip (T == max_T, budget >= N), transformer.py:216-286,
     :717-732.  Returns dict(loss, acc1, acc5, ce_sum, logits, z_targets, ratio)."""
     B = x_indices.shape[0]
@@ -325,7 +342,7 @@ def shared_step(P, cfg, x_indices, indices, t: float, schedule_name: str, label_
     n_tgt = min(budget, tgt_idx.shape[1])
     tgt_idx = tgt_idx[:, -n_tgt:] if n_tgt > 0 else tgt_idx
     z_t = torch.gather(x_indices, 1, tgt_idx)
-    logits = reconstruct_mask(P, cfg, x_indices, ctx_idx, tgt_idx)
+    logits = reconstruct_mask(P, cfg, x_indices, ctx_idx, tgt_idx, drop=drop)
     NT_weight = float(seq_len - ctx_idx.shape[1])
     ratio = NT_weight / float(seq_len)
     ce, n1, n5 = masked_ce(logits, z_t, label_smoothing)

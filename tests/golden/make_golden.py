@@ -96,7 +96,7 @@ CONFIGS = {
 }
 
 
-def build_reference(cfg: dict, schedule: str, seed: int):
+def build_reference(cfg: dict, schedule: str, seed: int, pdrop: float = 0.0):
     from mebt.transformer import Net2NetTransformer  # the reference's class
 
     from oracle.mebt_oracle import make_weights
@@ -104,7 +104,7 @@ def build_reference(cfg: dict, schedule: str, seed: int):
     params = to_attr(dict(
         unconditional=True, vocab_size=cfg["vocab_size"], first_stage_vocab_size=cfg["vocab_size"],
         block_size=cfg["block_size"], n_layer=cfg["n_layer"], n_head=cfg["n_head"], n_embd=cfg["n_embd"],
-        n_unmasked=0, embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, sample_every_n_latent_frames=0,
+        n_unmasked=0, embd_pdrop=pdrop, resid_pdrop=pdrop, attn_pdrop=pdrop, sample_every_n_latent_frames=0,
         first_stage_key="video", cond_stage_key="label", vtokens=True, vtokens_pos=False, vis_epoch=100,
         sos_emb=cfg["sos_emb"], avg_loss=bool(cfg.get("avg_loss", 1.0)), mode=list(cfg["mode"]), class_cond_dim=None))
     mask = to_attr(dict(target="mebt.mask_sampler.MaskGen",
@@ -322,6 +322,53 @@ def gen_codebook():
          gap=(top2[:, 1] - top2[:, 0]))
 
 
+def gen_grads_dropout(cfg_name, B, wseed, dseed, t, p, mseed):
+    """Training-mode (dropout p) loss and gradients of the reference with RECORDED dropout masks: nn.Dropout.forward is
+    replaced by `x * keep / (1-p)` with keep drawn from a seeded generator, and every keep tensor is stored (bit-packed)
+    under the name of the module that drew it, in call order.  Replaying them pins where the oracle applies dropout."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    cfg = CONFIGS[cfg_name]
+    model, _ = build_reference(cfg, "linear", wseed, pdrop=p)
+    model.transformer.train()                     # the dropouts live in GPT; the mask sampler stays in eval mode
+    names = {id(m): n for n, m in model.named_modules()}
+    g = torch.Generator().manual_seed(mseed)
+    record = []
+    orig = nn.Dropout.forward
+
+    def recorded(self, x):
+        assert self.training and abs(self.p - p) < 1e-12
+        keep = torch.rand(x.shape, generator=g) >= p
+        record.append((names[id(self)], keep))
+        return x * keep.to(x.dtype) / (1.0 - p)
+
+    nn.Dropout.forward = recorded
+    try:
+        x, indices = synth_tokens(cfg, B, dseed)
+        logits, target, NT_weight, seq_len = model(x, None, t=t, indices=indices)
+        ratio = NT_weight / float(seq_len)
+        ce = F.cross_entropy(logits.reshape(-1, logits.size(-1)), target.reshape(-1), reduction="sum")
+        loss = ce / (B * seq_len * ratio ** model.config.avg_loss)
+        loss.backward()
+    finally:
+        nn.Dropout.forward = orig
+    arrays = dict(x=x, indices=indices, wseed=wseed, t=t, p=p, loss=float(loss), logits_sample=logits.detach().reshape(-1)[::997])
+    arrays["mask_names"] = np.array([n for n, _ in record])
+    for i, (n, keep) in enumerate(record):
+        arrays[f"mask_shape:{i}"] = np.array(keep.shape)
+        arrays[f"mask_bits:{i}"] = np.packbits(keep.numpy().reshape(-1))
+    gnames, norms = [], []
+    for n, prm in model.named_parameters():
+        gnames.append(n)
+        norms.append(float(prm.grad.norm()) if prm.grad is not None else -1.0)
+        if prm.grad is not None and ("blocks.0." in n or "blocks.3." in n or "_emb" in n or "ln_f" in n):
+            arrays["g:" + n] = prm.grad.reshape(-1)[::17].contiguous()
+    arrays["grad_names"] = np.array(gnames)
+    arrays["grad_norms"] = np.array(norms)
+    save(f"grads_dropout_{cfg_name}", cfg, **arrays)
+
+
 def main():
     install_stubs()
     sys.path.insert(0, REF)          # `import mebt` resolves to the reference; also its top-level utils.py
@@ -337,9 +384,17 @@ def main():
     gen_shared_step("micro", 3, wseed=5, dseed=6, ts=[0.5, 0.3], label_smoothing=0.1)
     gen_grads("tiny5", 2, wseed=3, dseed=4, t=0.5)
     gen_grads("micro", 2, wseed=1, dseed=2, t=0.4)
+    gen_grads_dropout("micro", 2, wseed=1, dseed=2, t=0.4, p=0.1, mseed=11)
     gen_sampling("micro", 2, wseed=1, seed=9)
     gen_sampling("tiny", 2, wseed=1, seed=9)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "dropout":     # only the fixture added after the first generation
+        install_stubs()
+        sys.path.insert(0, REF)
+        sys.path.insert(1, str(REPO))
+        torch.set_num_threads(8)
+        gen_grads_dropout("micro", 2, wseed=1, dseed=2, t=0.4, p=0.1, mseed=11)
+    else:
+        main()

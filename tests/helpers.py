@@ -56,3 +56,20 @@ def synth_tokens(cfg, B, seed):
     x = torch.randint(0, cfg["vocab_size"], (B, *cfg["shape"]), generator=g)
     indices = torch.stack([torch.randperm(N, generator=g) for _ in range(B)])
     return x, indices
+
+
+def reference_dropout_masks(z, p):
+    """Keep factors recorded from the reference's nn.Dropout calls (tests/golden/make_golden.py::gen_grads_dropout),
+    keyed the way oracle.mebt_oracle.gpt_forward(drop=...) expects them."""
+    site = {"attn.attn_drop": "attn", "attn.resid_drop": "proj", "mlp.3": "mlp"}
+    drop, stem = {}, iter(("lat", "ctx", "tgt", "mask_emb"))
+    for i, name in enumerate(str(n) for n in z["mask_names"]):
+        shape = tuple(int(v) for v in z[f"mask_shape:{i}"])
+        keep = np.unpackbits(z[f"mask_bits:{i}"])[:int(np.prod(shape))].reshape(shape)
+        factor = torch.from_numpy(keep.astype(np.float32)) / (1.0 - p)
+        if name == "transformer.drop":                 # GPT.forward drops sos_emb, contexts, targets, mask_emb in this order
+            drop[("stem", next(stem))] = factor
+        else:
+            layer, sub = name[len("transformer.blocks."):].split(".", 1)
+            drop[(int(layer), site[sub])] = factor
+    return drop

@@ -50,6 +50,32 @@ def test_shared_step(name):
         np.testing.assert_allclose(torch.logsumexp(r["logits"], -1).numpy(), z[f"t{i}_lse"], atol=2e-5)
 
 
+def test_training_mode_dropout_replayed_from_reference():
+    """The reference run in training mode (p = 0.1) with its nn.Dropout masks recorded: replaying the masks through the
+    oracle must give the reference's loss and gradients, i.e. the oracle applies dropout where the reference does."""
+    from helpers import reference_dropout_masks
+    z, cfg = load_golden("grads_dropout_micro")
+    p = float(z["p"])
+    drop = reference_dropout_masks(z, p)
+    P = {k: v.clone().requires_grad_(True) for k, v in O.make_weights(cfg, int(z["wseed"])).items()}
+    r = O.shared_step(P, cfg, torch.from_numpy(z["x"]), torch.from_numpy(z["indices"]), float(z["t"]), "linear", drop=drop)
+    assert abs(float(r["loss"]) - float(z["loss"])) < 2e-6 * float(z["loss"])
+    np.testing.assert_allclose(r["logits"].detach().reshape(-1)[::997].numpy(), z["logits_sample"], atol=2e-5, rtol=0)
+    r["loss"].backward()
+    for n, ref_norm in zip((str(n) for n in z["grad_names"]), z["grad_norms"]):
+        g = P[n].grad
+        if ref_norm < 0:
+            assert g is None or float(g.abs().max()) == 0.0, n
+            continue
+        assert abs(float(g.norm()) - ref_norm) <= 1e-4 * ref_norm + 1e-9, (n, float(g.norm()), float(ref_norm))
+    for key in z.files:
+        if key.startswith("g:"):
+            np.testing.assert_allclose(P[key[2:]].grad.reshape(-1)[::17].numpy(), z[key], atol=1e-7, rtol=1e-3)
+    # and dropout really changed the result
+    r0 = O.shared_step(P, cfg, torch.from_numpy(z["x"]), torch.from_numpy(z["indices"]), float(z["t"]), "linear")
+    assert float((r0["logits"] - r["logits"]).abs().max()) > 1e-2
+
+
 def test_sample_from_logits_bit_exact():
     z, _ = load_golden("sample_from_logits")
     g = torch.Generator().manual_seed(int(z["seed"]))
