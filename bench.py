@@ -117,13 +117,14 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def build_cpu_model(cfg, seed=0):
+def build_cpu_model(cfg, seed=0, pdrop=0.0):
     """Random-init weights in the reference's distribution (N(0,0.02), zero biases, unit LayerNorm), built on the
-    CPU so that the same values feed the GPU model and the CPU oracle."""
+    CPU so that the same values feed the GPU model and the CPU oracle.  pdrop: embd/resid/attn dropout (STL yaml: 0.1)."""
     from helpers import model_configs
     from mebt_b200.transformer import Net2NetTransformer
     torch.manual_seed(seed)
     params, vq, mask = model_configs(cfg, schedule="linear")
+    params.embd_pdrop = params.resid_pdrop = params.attn_pdrop = pdrop
     return Net2NetTransformer(params, vq, mask)
 
 
@@ -165,19 +166,34 @@ def oracle_vq_step(B):
     return step, B * 1024, f"Codebook.forward + decode gather on {B} videos (fp32 torch-CPU oracle port)"
 
 
-def oracle_train_step(cfg, state, B):
+def oracle_dropout_masks(cfg, B, NC, NT, p):
+    """Fresh nn.Dropout keep factors for every dropout call of one training-mode forward (gpt.py:136,140,154,239-241)."""
+    from oracle import mebt_oracle as O
+    D, H, L = cfg["n_embd"], cfg["n_head"], cfg["sos_emb"]
+    keep = lambda *shape: (torch.rand(*shape) >= p).float() / (1.0 - p)
+    drop = {("stem", "lat"): keep(B, L, D), ("stem", "ctx"): keep(B, NC, D), ("stem", "tgt"): keep(B, NT, D)}
+    for i, mode in enumerate(O.stack_modes(cfg)):
+        nq = NT if mode == "latent_dec" else L
+        nk = {"latent_enc": NC, "latent_self": L, "latent_dec": L, "lt2l": L + NT}[mode]
+        drop[(i, "attn")], drop[(i, "proj")], drop[(i, "mlp")] = keep(B, H, nq, nk), keep(B, nq, D), keep(B, nq, D)
+    return drop
+
+
+def oracle_train_step(cfg, state, B, pdrop=0.0):
     from oracle import mebt_oracle as O
     P = {k: v.clone().requires_grad_(True) for k, v in state.items()}
     opt = torch.optim.AdamW(list(P.values()), lr=1.08e-5, betas=(0.9, 0.95), weight_decay=0.01)
     x, indices = synth_batch(cfg, B, 1)
+    N = int(np.prod(cfg["shape"]))
 
     def step():
         opt.zero_grad(set_to_none=True)
-        r = O.shared_step(P, cfg, x, indices, TRAIN_T, "linear")
+        drop = oracle_dropout_masks(cfg, B, N // 2, N // 2, pdrop) if pdrop > 0 else None
+        r = O.shared_step(P, cfg, x, indices, TRAIN_T, "linear", drop=drop)
         r["loss"].backward()
         opt.step()
-    N = int(np.prod(cfg["shape"]))
-    desc = f"full training step (fwd + CE + autograd bwd + AdamW), B={B}, t={TRAIN_T}, fp32 torch-CPU oracle port"
+    desc = (f"full training step (fwd + CE + autograd bwd + AdamW), B={B}, t={TRAIN_T}, dropout {pdrop}, "
+            "fp32 torch-CPU oracle port")
     return step, B * (N // 2), desc
 
 
@@ -200,7 +216,7 @@ def run_reference(args, cfg):
     model = build_cpu_model(cfg)
     state = {k: v.detach() for k, v in model.state_dict().items()}
     if args.workload == "train16f":
-        step, tokens, desc = oracle_train_step(cfg, state, args.batch or 6)
+        step, tokens, desc = oracle_train_step(cfg, state, args.batch or 6, args.dropout)
     elif args.workload == "vq16f":
         step, tokens, desc = oracle_vq_step(8)
     else:
@@ -233,6 +249,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0,
                     help="per GPU; default 6 for train16f (configs/stl/mebt_16f.yaml), 16 videos for sampling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="train16f: embd/resid/attn dropout (configs/stl/mebt_16f.yaml uses 0.1)")
     args = ap.parse_args()
     cfg = CONFIGS[args.workload]
     if args.impl == "reference":
@@ -253,7 +271,7 @@ def main():
 
     from mebt_b200 import _lib
     _lib.check(_lib.lib.mebt_device_check(), "mebt_device_check")
-    cpu_model = build_cpu_model(cfg)                      # same weights on every rank (seed 0)
+    cpu_model = build_cpu_model(cfg, pdrop=args.dropout if args.workload == "train16f" else 0.0)   # same weights on every rank (seed 0)
     state = {k: v.detach().clone() for k, v in cpu_model.state_dict().items()} if rank == 0 else None
     model = cpu_model.to(dev)
     N = int(np.prod(cfg["shape"]))
@@ -392,7 +410,7 @@ def main():
             threads = os.cpu_count() or 1
             torch.set_num_threads(threads)
             if training:
-                step, toks, desc = oracle_train_step(cfg, state, B)
+                step, toks, desc = oracle_train_step(cfg, state, B, args.dropout)
                 dt = time_cpu(step, 1, 2)
             elif args.workload == "vq16f":
                 step, toks, desc = oracle_vq_step(8)
@@ -406,8 +424,8 @@ def main():
                   "weights": "random init, reference distribution (337 M parameters)",
                   "l2": "working set (0.67 GB bf16 weights + activations/logits) exceeds the 126 MB L2; no flush needed"}
         if training:
-            config.update(t=TRAIN_T, NC=N // 2, NT=N // 2, dropout=0.0, optimizer="AdamW fused fp32 master weights",
-                          note="STL yaml uses dropout 0.1; the CUDA path implements p = 0 (taichi/ucf setting)",
+            config.update(t=TRAIN_T, NC=N // 2, NT=N // 2, dropout=args.dropout, optimizer="AdamW fused fp32 master weights",
+                          note="embd/attn/resid dropout as in configs/stl/mebt_16f.yaml; masks regenerated in backward",
                           grad_allreduce="fp32, 4 buckets + head + embeddings, overlapped with backward" if world > 1 else "none (1 GPU)")
         elif args.workload == "vq16f":
             config = {"workload": "vq16f", "videos_per_gpu": B, "latent": [256, 4, 16, 16], "codebook": [16384, 256],

@@ -222,6 +222,14 @@ int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV
                               int dv2_col0, int B, int H, int NQ, int head_dim, void* workspace, size_t workspace_bytes,
                               void* stream);
 
+/* ---- optimizer step (mebt/transformer.py:749-798 configure_optimizers -> torch.optim.AdamW, betas (0.9, 0.95)) ---- */
+/* One AdamW step over flat fp32 buffers p / g / m / v [n] with torch's fused-AdamW arithmetic, plus p_bf16 = bf16(p) (the
+ * tensor-core operand copy).  decay_blocks[i >> block_shift] != 0 marks elements of weight-decayed tensors; `step` counts
+ * from 1 (bias correction). */
+int mebt_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, const unsigned char* decay_blocks,
+                    int block_shift, long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    void* stream);
+
 /* ---- dropout (training mode; nn.Dropout at mebt/modules/gpt.py:112-113,140,150-155,216,239-242) ------------- */
 /* Keep decisions are counter-based: a pure function of (seed, site, row, column), regenerated by the backward
  * kernels instead of being stored.  p is quantised to 1/65536 and kept elements are scaled by 65536/(65536-round(p*65536)).

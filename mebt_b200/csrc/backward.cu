@@ -5,6 +5,9 @@
 //   reducer, and the stem's scatter-add into tok_emb / pos_emb / mask_emb / sos_emb gradients.
 // Reductions over rows are two-stage with a fixed order (deterministic); only the embedding scatter-add uses
 // fp32 atomics (several tokens of a batch may hit the same row), like torch's embedding backward.
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mebt {
@@ -22,11 +25,14 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
-// ---- column sums: partial[r, n] = sum over the r-th row slab of X[:, n] ------------------------------------
-// grid (N / 128, slabs); 256 threads = 32 column-quads x 8 row lanes
-__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ X, int ld, int rows, int N,
-                                      int rows_per_slab, float* __restrict__ partial) {
+// ---- column sums: out[n] (+)= sum_r X[r, n] ----------------------------------------------------------------
+// grid (N / 128, slabs); 256 threads = 32 column-quads x 8 row lanes.  Each CTA writes the partial sums of its row slab;
+// the LAST CTA of a column block to finish (ticket counter) adds the slabs in slab order, so the result does not depend
+// on which CTA that is (bitwise reproducible) and no second launch is needed.
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, int ld, int rows, int N, int rows_per_slab,
+                              float* __restrict__ partial, float* __restrict__ out, int accumulate, int* __restrict__ counters) {
   __shared__ float4 red[8][32];
+  __shared__ int s_last;
   const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
   griddep_wait();
   const int col = blockIdx.x * 128 + cq * 4;
@@ -45,94 +51,170 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ X, int l
       const float4 v = red[i][cq];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    *reinterpret_cast<float4*>(partial + size_t(blockIdx.y) * N + col) = acc;
+    __stcg(reinterpret_cast<float4*>(partial + size_t(blockIdx.y) * N + col), acc);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(counters + blockIdx.x, 1);
+    s_last = ticket == int(gridDim.y) - 1;
+    if (s_last) counters[blockIdx.x] = 0;            // ready for the next launch on this stream
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // slab sums: row lane rl adds slabs rl, rl+8, ... in order, then lane 0 adds the eight lane sums in order
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N)
+    for (int sl = rl; sl < int(gridDim.y); sl += 8) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + size_t(sl) * N + col));
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+  red[rl][cq] = t;
+  __syncthreads();
+  if (rl == 0 && col < N) {
+    for (int i = 1; i < 8; ++i) {
+      const float4 v = red[i][cq];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out + col);
+    if (accumulate) { const float4 v = *o; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    *o = t;
   }
 }
 
-// out[n] (+)= sum_s partial[s, n]   (fixed order)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int slabs, int N, float* __restrict__ out,
-                                       int accumulate) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  griddep_wait();
-  if (n >= N) return;
-  float acc = 0.f;
-  for (int s = 0; s < slabs; ++s) acc += partial[size_t(s) * N + n];
-  out[n] = accumulate ? out[n] + acc : acc;
+// Ticket counters of the fused two-stage reductions: one zero-initialised block per stream that uses them (the kernels
+// of one stream are serialised; the training backward runs its bias-gradient sums on a second stream).
+int* reduce_counters(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<cudaStream_t, int*> table;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = table.find(st);
+  if (it != table.end()) return it->second;
+  int* p = nullptr;
+  if (cudaMalloc(&p, 1024 * sizeof(int)) != cudaSuccess) return nullptr;
+  if (cudaMemset(p, 0, 1024 * sizeof(int)) != cudaSuccess) return nullptr;
+  cudaDeviceSynchronize();
+  table[st] = p;
+  return p;
 }
 
 // ---- LayerNorm backward --------------------------------------------------------------------------------------
 // y = (x - mean) * rstd * gamma + beta
 // dx = rstd * (g - mean_D(g) - xhat * mean_D(g * xhat)),  g = dy * gamma;   dgamma = sum_rows dy * xhat; dbeta = sum_rows dy
-// One warp per row, rows strided over a fixed grid; each lane keeps its dgamma/dbeta slice in registers across rows.
+// Two kernels with opposite parallelism: dx is row-parallel (one warp per row), the parameter gradients are column sums
+// (128 columns x a slab of rows per CTA, finished by the last CTA of a column block in slab order: reproducible).
 template <int MAX_VEC>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ gamma, __nv_bfloat16* dx, const __nv_bfloat16* resid,
-                                     int rows, int D, float* __restrict__ partial /* [grid, 2, D] */) {
-  extern __shared__ float sm[];   // [8 warps][2][D]
+                                     int rows, int D) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   griddep_wait();
-  float4 dg[MAX_VEC], db[MAX_VEC], gm[MAX_VEC];
+  float4 gm[MAX_VEC];
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i) {
-    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int c = (lane + 32 * i) * 4;
     gm[i] = c < D ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invD = 1.0f / float(D);
-  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
-    const float mu = mean[row], rs = rstd[row];
-    float4 xh[MAX_VEC], g[MAX_VEC];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAX_VEC; ++i) {
-      const int c = (lane + 32 * i) * 4;
-      if (c < D) {
-        const float4 xv = ld_bf16x4(x + row * D + c);
-        const float4 dv = ld_bf16x4(dy + row * D + c);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
-        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-        dg[i].x += dv.x * xh[i].x; dg[i].y += dv.y * xh[i].y; dg[i].z += dv.z * xh[i].z; dg[i].w += dv.w * xh[i].w;
-        db[i].x += dv.x; db[i].y += dv.y; db[i].z += dv.z; db[i].w += dv.w;
-      }
-    }
-    s1 = warp_sum(s1) * invD;
-    s2 = warp_sum(s2) * invD;
-#pragma unroll
-    for (int i = 0; i < MAX_VEC; ++i) {
-      const int c = (lane + 32 * i) * 4;
-      if (c < D) {
-        float4 o;
-        o.x = rs * (g[i].x - s1 - xh[i].x * s2);
-        o.y = rs * (g[i].y - s1 - xh[i].y * s2);
-        o.z = rs * (g[i].z - s1 - xh[i].z * s2);
-        o.w = rs * (g[i].w - s1 - xh[i].w * s2);
-        if (resid != nullptr) {                       // dx = resid + ln'(dy); resid may alias dx (in-place accumulate)
-          const float4 old = ld_bf16x4(resid + row * D + c);
-          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-        }
-        st_bf16x4(dx + row * D + c, o);
-      }
-    }
-  }
-  // block reduction of the per-warp dgamma / dbeta slices, fixed order
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const float mu = mean[row], rs = rstd[row];
+  float4 xh[MAX_VEC], g[MAX_VEC], old[MAX_VEC];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i) {
     const int c = (lane + 32 * i) * 4;
     if (c < D) {
-      *reinterpret_cast<float4*>(sm + (warp * 2 + 0) * D + c) = dg[i];
-      *reinterpret_cast<float4*>(sm + (warp * 2 + 1) * D + c) = db[i];
+      const float4 xv = ld_bf16x4(x + row * D + c);
+      const float4 dv = ld_bf16x4(dy + row * D + c);
+      if (resid != nullptr) old[i] = ld_bf16x4(resid + row * D + c);      // dx = resid + ln'(dy); resid may alias dx
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
     }
   }
+  s1 = warp_sum(s1) * invD;
+  s2 = warp_sum(s2) * invD;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < D) {
+      float4 o;
+      o.x = rs * (g[i].x - s1 - xh[i].x * s2);
+      o.y = rs * (g[i].y - s1 - xh[i].y * s2);
+      o.z = rs * (g[i].z - s1 - xh[i].z * s2);
+      o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+      if (resid != nullptr) { o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w; }
+      st_bf16x4(dx + row * D + c, o);
+    }
+  }
+}
+
+// dgamma[c] (+)= sum_r dy[r,c] * xhat[r,c],  dbeta[c] (+)= sum_r dy[r,c].  grid (D / 128, slabs), 256 threads =
+// 32 column-quads x 8 row lanes; partial: [slabs][2][D].
+__global__ void __launch_bounds__(256) layernorm_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd, int rows, int D,
+                                       int rows_per_slab, float* __restrict__ partial, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate, int* __restrict__ counters) {
+  __shared__ float4 red[2][8][32];
+  __shared__ int s_last;
+  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  griddep_wait();
+  const int col = blockIdx.x * 128 + cq * 4;
+  const int r0 = blockIdx.y * rows_per_slab;
+  const int r1 = min(rows, r0 + rows_per_slab);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < D)
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const float4 dv = ld_bf16x4(dy + size_t(r) * D + col);
+      const float4 xv = ld_bf16x4(x + size_t(r) * D + col);
+      const float mu = mean[r], rs = rstd[r];
+      ag.x += dv.x * ((xv.x - mu) * rs); ag.y += dv.y * ((xv.y - mu) * rs);
+      ag.z += dv.z * ((xv.z - mu) * rs); ag.w += dv.w * ((xv.w - mu) * rs);
+      ab.x += dv.x; ab.y += dv.y; ab.z += dv.z; ab.w += dv.w;
+    }
+  red[0][rl][cq] = ag;
+  red[1][rl][cq] = ab;
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 2 * D; idx += blockDim.x) {
-    const int which = idx / D, c = idx % D;
-    float acc = 0.f;
-    for (int w = 0; w < 8; ++w) acc += sm[(w * 2 + which) * D + c];
-    partial[(size_t(blockIdx.x) * 2 + which) * D + c] = acc;
+  if (rl < 2 && col < D) {                           // row lane 0 finishes dgamma, row lane 1 dbeta
+    float4 t = red[rl][0][cq];
+    for (int i = 1; i < 8; ++i) {
+      const float4 v = red[rl][i][cq];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    __stcg(reinterpret_cast<float4*>(partial + (size_t(blockIdx.y) * 2 + rl) * D + col), t);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(counters + blockIdx.x, 1);
+    s_last = ticket == int(gridDim.y) - 1;
+    if (s_last) counters[blockIdx.x] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last CTA of the column block: row lanes 0-3 add the dgamma slabs (lane j: slabs j, j+4, ...), 4-7 the dbeta slabs
+  const int which = rl >> 2, j = rl & 3;
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < D)
+    for (int sl = j; sl < int(gridDim.y); sl += 4) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (size_t(sl) * 2 + which) * D + col));
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+  red[which][j][cq] = t;
+  __syncthreads();
+  if (j == 0 && col < D) {
+    for (int i = 1; i < 4; ++i) {
+      const float4 v = red[which][i][cq];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>((which == 0 ? dgamma : dbeta) + col);
+    if (accumulate) { const float4 v = *o; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    *o = t;
   }
 }
 
@@ -190,19 +272,6 @@ __global__ void batch_sum_kernel(const __nv_bfloat16* __restrict__ d_lat, int B,
   *o = acc;
 }
 
-// dgamma[c] (+)= sum_g partial[g][0][c];  dbeta[c] (+)= sum_g partial[g][1][c]   (fixed order)
-__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int grid, int D, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  griddep_wait();
-  if (idx >= 2 * D) return;
-  const int which = idx / D, c = idx % D;
-  float acc = 0.f;
-  for (int g = 0; g < grid; ++g) acc += partial[(size_t(g) * 2 + which) * D + c];
-  float* out = which == 0 ? dgamma : dbeta;
-  out[c] = accumulate ? out[c] + acc : acc;
-}
-
 // attention backward preprocess: delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloat16* __restrict__ O,
                                   int ldo, float* __restrict__ delta, int B, int H, int NQ) {
@@ -233,32 +302,29 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, int lddo
 
 int colsum(const void* X, int ld, int rows, int N, float* out, int accumulate, float* workspace, size_t ws_bytes,
            cudaStream_t st) {
-  MEBT_REQUIRE(rows >= 0 && N > 0 && N % 4 == 0 && ld % 4 == 0, MEBT_ERR_SHAPE, "colsum: bad shape rows=%d N=%d", rows, N);
-  int slabs = (rows + 255) / 256;
+  MEBT_REQUIRE(rows >= 0 && N > 0 && N % 4 == 0 && ld % 4 == 0 && N <= 128 * 1000, MEBT_ERR_SHAPE,
+               "colsum: bad shape rows=%d N=%d", rows, N);
+  int slabs = (rows + 31) / 32;             // 4 rows per thread: enough CTAs in flight to hide the load latency
   if (slabs > 64) slabs = 64;
   if (slabs < 1) slabs = 1;
   const int rows_per_slab = (rows + slabs - 1) / slabs;
   MEBT_REQUIRE(workspace != nullptr && ws_bytes >= size_t(slabs) * N * 4, MEBT_ERR_WORKSPACE,
                "colsum: workspace too small (%zu < %zu)", ws_bytes, size_t(slabs) * N * 4);
+  int* counters = reduce_counters(st);
+  MEBT_REQUIRE(counters != nullptr, MEBT_ERR_CUDA, "colsum: cannot allocate the ticket counters");
   {
     LaunchScope ls(FAM_OTHER, double(rows) * N * 2.0, st);
     dim3 grid((N + 127) / 128, slabs);
-    MEBT_CUDA_OK(launch_pdl(colsum_partial_kernel, grid, dim3(256), 0, st, static_cast<const __nv_bfloat16*>(X), ld, rows,
-                            N, rows_per_slab, workspace));
+    MEBT_CUDA_OK(launch_pdl(colsum_kernel, grid, dim3(256), 0, st, static_cast<const __nv_bfloat16*>(X), ld, rows, N,
+                            rows_per_slab, workspace, out, accumulate, counters));
   }
-  MEBT_LAUNCH_OK("colsum_partial_kernel");
-  {
-    LaunchScope ls(FAM_OTHER, double(slabs) * N * 4.0, st);
-    MEBT_CUDA_OK(launch_pdl(reduce_partials_kernel, dim3((N + 255) / 256), dim3(256), 0, st, workspace, slabs, N, out,
-                            accumulate));
-  }
-  MEBT_LAUNCH_OK("reduce_partials_kernel");
+  MEBT_LAUNCH_OK("colsum_kernel");
   return MEBT_OK;
 }
 
-constexpr int LNB_GRID = 148 * 2;
+constexpr int LNB_MAX_SLABS = 64;
 
-size_t layernorm_bwd_workspace_bytes(int D) { return size_t(LNB_GRID) * 2 * D * 4; }
+size_t layernorm_bwd_workspace_bytes(int D) { return size_t(LNB_MAX_SLABS) * 2 * D * 4; }
 
 int layernorm_bwd_resid(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                         void* dx, const void* resid, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
@@ -280,30 +346,29 @@ int layernorm_bwd_resid(const void* dy, const void* x, const float* mean, const 
   MEBT_REQUIRE(workspace != nullptr && ws_bytes >= layernorm_bwd_workspace_bytes(D), MEBT_ERR_WORKSPACE,
                "layernorm_bwd: workspace too small");
   if (rows == 0) return MEBT_OK;
-  int grid = (rows + 7) / 8;
-  if (grid > LNB_GRID) grid = LNB_GRID;
-  const size_t smem = size_t(8) * 2 * D * 4;
-  static bool attr = false;
-  if (!attr) {
-    MEBT_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
-    attr = true;
-  }
   const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx);
+  int* counters = reduce_counters(st);
+  MEBT_REQUIRE(counters != nullptr, MEBT_ERR_CUDA, "layernorm_bwd: cannot allocate the ticket counters");
   {
+    // parameter gradients first: they read dy, which dx may overwrite when the caller accumulates in place
+    int slabs = (rows + 31) / 32;
+    if (slabs > LNB_MAX_SLABS) slabs = LNB_MAX_SLABS;
+    const int rows_per_slab = (rows + slabs - 1) / slabs;
+    LaunchScope ls(FAM_LAYERNORM, double(rows) * D * 4.0, st);
+    MEBT_CUDA_OK(launch_pdl(layernorm_bwd_param_kernel, dim3((D + 127) / 128, slabs), dim3(256), 0, st, dyp, xp, mean, rstd,
+                            rows, D, rows_per_slab, workspace, dgamma, dbeta, accumulate_params, counters + 1000));
+  }
+  MEBT_LAUNCH_OK("layernorm_bwd_param_kernel");
+  {
+    const dim3 grid((rows + 7) / 8);
     LaunchScope ls(FAM_LAYERNORM, double(rows) * D * (rp != nullptr ? 8.0 : 6.0), st);
-    if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, workspace));
-    else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<4>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, workspace));
-    else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_kernel<8>, dim3(grid), dim3(256), smem, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, workspace));
+    if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<2>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D));
+    else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<4>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D));
+    else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<8>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D));
   }
-  MEBT_LAUNCH_OK("layernorm_bwd_kernel");
-  {
-    LaunchScope ls(FAM_OTHER, double(grid) * 2 * D * 4.0, st);
-    MEBT_CUDA_OK(launch_pdl(ln_param_reduce_kernel, dim3((2 * D + 255) / 256), dim3(256), 0, st, workspace, grid, D, dgamma,
-                            dbeta, accumulate_params));
-  }
-  MEBT_LAUNCH_OK("ln_param_reduce_kernel");
+  MEBT_LAUNCH_OK("layernorm_bwd_dx_kernel");
   return MEBT_OK;
 }
 

@@ -360,6 +360,59 @@ int layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const fl
   return MEBT_OK;
 }
 
+// ---- AdamW over the flat parameter buffer, fused with the bf16 operand refresh ----
+// torch.optim.AdamW(fused=True) arithmetic (decoupled decay, bias-corrected moments) on fp32 masters p, moments m / v and
+// gradients g, all [n]; additionally writes bf16(p) for the tensor-core operands, which saves the separate cast pass.
+// decay[i >> shift] != 0 marks the blocks of 2^shift elements that belong to a weight-decayed tensor
+// (configure_optimizers, mebt/transformer.py:749-798: only the transformer's Linear weights decay).
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, __nv_bfloat16* __restrict__ p16,
+                                                         const unsigned char* __restrict__ decay, int shift, long long n4,
+                                                         float lr, float beta1, float beta2, float eps, float wd,
+                                                         float step_size, float inv_bc2_sqrt) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<const float4*>(p)[i];
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<const float4*>(m)[i];
+    float4 vv = reinterpret_cast<const float4*>(v)[i];
+    const float keep = decay[(i * 4) >> shift] ? 1.f - lr * wd : 1.f;
+    float* pp = reinterpret_cast<float*>(&pv);
+    const float* gg = reinterpret_cast<const float*>(&gv);
+    float* mm = reinterpret_cast<float*>(&mv);
+    float* vq = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pp[k] *= keep;
+      mm[k] = mm[k] + (1.f - beta1) * (gg[k] - mm[k]);
+      vq[k] = beta2 * vq[k] + (1.f - beta2) * gg[k] * gg[k];
+      const float denom = sqrtf(vq[k]) * inv_bc2_sqrt + eps;
+      pp[k] -= step_size * (mm[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    uint2 o;
+    o.x = pack_bf16x2(pp[0], pp[1]);
+    o.y = pack_bf16x2(pp[2], pp[3]);
+    reinterpret_cast<uint2*>(p16)[i] = o;
+  }
+}
+
+int adamw_flat(float* p, const float* g, float* m, float* v, void* p16, const unsigned char* decay, int shift, long long n,
+               float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st) {
+  MEBT_REQUIRE(n >= 0 && n % 4 == 0 && shift >= 2 && step >= 1, MEBT_ERR_SHAPE, "adamw: n %% 4 != 0, shift < 2 or step < 1");
+  if (n == 0) return MEBT_OK;
+  const double bc1 = 1.0 - pow(double(beta1), double(step));
+  const double bc2 = 1.0 - pow(double(beta2), double(step));
+  {
+    LaunchScope ls(FAM_OTHER, double(n) * 30.0, st);
+    adamw_flat_kernel<<<148 * 8, 256, 0, st>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p16), decay, shift, n / 4, lr, beta1,
+                                               beta2, eps, wd, float(double(lr) / bc1), float(1.0 / sqrt(bc2)));
+  }
+  MEBT_LAUNCH_OK("adamw_flat_kernel");
+  return MEBT_OK;
+}
+
 // ---- dropout on [rows, D] bf16 activations (training) ----
 // forward : y = resid + x * keep / (1-p)   (resid optional; in place when y == x)
 // backward: dx = dy * keep / (1-p)
@@ -410,6 +463,13 @@ int dropout_rows(const void* x, int ldx, const void* resid, int ldres, void* y, 
 }  // namespace mebt
 
 extern "C" {
+
+int mebt_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, const unsigned char* decay_blocks,
+                    int block_shift, long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    void* stream) {
+  return mebt::adamw_flat(p, g, m, v, p_bf16, decay_blocks, block_shift, n, lr, beta1, beta2, eps, weight_decay, step,
+                          static_cast<cudaStream_t>(stream));
+}
 
 int mebt_dropout_rows(const void* x, int ldx, const void* resid, int ldres, void* y, int ldy, int rows, int D, float p,
                       unsigned long long seed, unsigned long long site, void* stream) {

@@ -235,15 +235,72 @@ class TrainState:
         n = float(B * NT)
         return dict(loss=stats[0] * scale, acc1=stats[1] * (100.0 / n), acc5=stats[2] * (100.0 / n), ratio=ratio)
 
-    def make_optimizer(self, lr=1.08e-5, weight_decay=0.01):
+    def make_optimizer(self, lr=1.08e-5, weight_decay=0.01, flat=True):
+        """The reference's AdamW (configure_optimizers, transformer.py:749-798: betas (0.9, 0.95), decay only on the
+        transformer's Linear weights).  flat=True: one fused kernel over the flat buffers that also refreshes the bf16
+        operands (FlatAdamW); flat=False: torch.optim.AdamW(fused=True) on the same parameter groups."""
         self.model.learning_rate, self.model.weight_decay = lr, weight_decay
         ref = self.model.configure_optimizers()                  # the reference's four groups (transformer.py:790-797)
         groups = [{"params": g["params"], "weight_decay": g["weight_decay"]} for g in ref.param_groups]
-        return torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.95), fused=True)
+        if not flat:
+            return torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.95), fused=True)
+        return FlatAdamW(self, groups, lr=lr, betas=(0.9, 0.95), weight_decay=weight_decay)
 
     def train_step(self, optimizer, x_indices, indices, t=None, world_size=1):
         """fwd + loss + bwd (+ all-reduce) + AdamW + operand refresh.  Returns the loss statistics."""
         out = self.loss_and_backward(x_indices, indices, t, world_size)
         optimizer.step()
-        self.refresh_operands()
+        if not isinstance(optimizer, FlatAdamW):
+            self.refresh_operands()
         return out
+
+
+class FlatAdamW:
+    """AdamW over TrainState's flat fp32 parameter / gradient buffers in ONE kernel (`mebt_adamw_flat`): torch's fused
+    AdamW arithmetic, the reference's decay / no-decay split as a per-block flag table, and the bf16 operand copy written
+    in the same pass (30 B per parameter instead of 28 + 6 for optimizer + cast).  Exposes `param_groups[i]["lr"]` so
+    that the reference's warm-up code (optimizer_step, transformer.py:665-681) can drive it."""
+
+    def __init__(self, ts: TrainState, groups, lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.01):
+        self.ts = ts
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.param_groups = [dict(g, lr=lr) for g in groups]
+        self.m = torch.zeros_like(ts.flat)
+        self.v = torch.zeros_like(ts.flat)
+        self.steps = 0
+        name_of = {id(p): n for n, p in ts.model.named_parameters()}
+        decayed = {name_of[id(p)] for g in groups if g["weight_decay"] > 0 for p in g["params"]}
+        edges = sorted({o for o, _ in ts.offsets.values()} | {o + k for o, k in ts.offsets.values()})
+        shift = 2
+        while all(e % (1 << (shift + 1)) == 0 for e in edges) and shift < 20:
+            shift += 1
+        self.shift = shift
+        n = ts.flat.numel()
+        flags = np.zeros((n + (1 << shift) - 1) >> shift, dtype=np.uint8)
+        for name in decayed:
+            o, k = ts.offsets[name]
+            flags[o >> shift:(o + k) >> shift] = 1
+        self.flags = torch.from_numpy(flags).to(ts.device)
+        if n % 4:
+            raise MebtError("FlatAdamW: the flat parameter buffer must hold a multiple of 4 elements")
+
+    def zero_grad(self, set_to_none=False):
+        self.ts.flat_grad.zero_()
+
+    def step(self):
+        ts = self.ts
+        self.steps += 1
+        lr = float(self.param_groups[0]["lr"])
+        call("mebt_adamw_flat", ts.flat.data_ptr(), ts.flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+             ts.flat_bf16.data_ptr(), self.flags.data_ptr(), self.shift, ts.flat.numel(), lr, self.betas[0], self.betas[1],
+             self.eps, self.weight_decay, self.steps, torch.cuda.current_stream().cuda_stream)
+
+    def state_dict(self):
+        return dict(m=self.m, v=self.v, steps=self.steps, lr=[g["lr"] for g in self.param_groups])
+
+    def load_state_dict(self, sd):
+        self.m.copy_(sd["m"])
+        self.v.copy_(sd["v"])
+        self.steps = int(sd["steps"])
+        for g, lr in zip(self.param_groups, sd["lr"]):
+            g["lr"] = lr
