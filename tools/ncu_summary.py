@@ -1,5 +1,5 @@
-"""Compact per-kernel summary of an ncu --set full report.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [out.md]"""
+"""Compact per-kernel summary of an ncu --set full report (or of its exported raw CSV page).
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep|prof_raw.csv [out.md]"""
 import csv
 import subprocess
 import sys
@@ -14,7 +14,10 @@ WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
 
 def main():
     rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):          # already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv > x.csv
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}

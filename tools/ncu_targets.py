@@ -25,44 +25,58 @@ def main():
     for (n, k) in ((4096, 1024), (1024, 4096)):
         w = r(n, k)
         x = r(8192, k)
-        for _ in range(2):
+        for _ in range(1):
             ops.gemm(x, w, torch.zeros(n, device=dev))
     head = r(16384, 1024)
-    for _ in range(2):
+    for _ in range(1):
         logits = ops.gemm(a, head, out_dtype=torch.float32)                  # head GEMM, fp32 logits
     # K6 sampling (fast mode) and K5 masked CE over the materialised logits
-    for _ in range(2):
+    for _ in range(1):
         ops.sample_logits(logits, 1.0, None, None, noise=None, seed=1, offset=1)
     tg = torch.randint(0, 16384, (8192,), device=dev)
     lb = logits.to(bf)
-    for _ in range(2):
+    for _ in range(1):
         ops.masked_ce(lb, tg, 0.0, dlogits=lb, grad_scale=1.0)
     # LayerNorm and the stem gather at token-row scale
     g, b = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
     xs = r(32768, 1024)
-    for _ in range(2):
+    for _ in range(1):
         ops.layernorm(xs, g, b)
     B, N = 8, 8192
     xi = torch.randint(0, 16384, (B, N), device=dev)
     perm = torch.stack([torch.randperm(N, device=dev) for _ in range(B)])
     tok, pos = torch.randn(16384, 1024, device=dev), torch.randn(1, N, 1024, device=dev)
-    for _ in range(2):
+    for _ in range(1):
         ops.embed_gather(xi, perm[:, :4096], perm[:, 4096:], tok, pos, torch.randn(1, 1, 1024, device=dev),
                          torch.randn(1, 256, 1024, device=dev))
     # K3 attention: latent_enc shape (256 latents x 7168 contexts) and latent_dec shape (8192 targets x 256 latents)
     Bq, H, D = 4, 16, 1024
     q = r(Bq * 256, D)
     kv = r(Bq * 7168, 2 * D)
-    for _ in range(2):
+    for _ in range(1):
         ops.attention(q, 0, kv, 0, D, 7168, None, 0, 0, 0, Bq, H, 256)
     q2 = r(Bq * 8192, D)
     kv2 = r(Bq * 256, 2 * D)
-    for _ in range(2):
+    for _ in range(1):
         ops.attention(q2, 0, kv2, 0, D, 256, None, 0, 0, 0, Bq, H, 8192)
+    # training-step kernels at the 16-frame shapes (B = 6: 1536 latent rows, 3072 token rows)
+    rows = 3072
+    xs2, dy2 = r(rows, 1024), r(rows, 1024)
+    _, mean, rstd = ops.layernorm(xs2, g, b, save_stats=True)
+    for _ in range(1):
+        ops.layernorm_bwd(dy2, xs2, mean, rstd, g)
+        ops.colsum(r(rows, 4096))
+        ops.dropout_rows_(dy2, 0.1, 1, 1)
+    qb, kvb, dob = r(6 * 256, 3 * D), r(6 * 512, 2 * D), r(6 * 256, D)
+    lse = torch.empty(6, H, 256, device=dev)
+    for _ in range(1):
+        ob = ops.attention(qb, D, kvb, 0, D, 512, None, 0, 0, 0, 6, H, 256, lse=lse, drop_p=0.1, drop_seed=3)
+        ops.attention_bwd(qb, D, kvb, 0, D, 512, None, 0, 0, 0, ob, dob, lse, torch.zeros_like(qb), D, torch.zeros_like(kvb),
+                          0, D, None, 0, 0, 6, H, 256, drop_p=0.1, drop_seed=3)
     # K9/K10 codebook
     E = torch.randn(16384, 256, device=dev)
     z = torch.randn(8, 256, 4, 16, 16, device=dev)
-    for _ in range(2):
+    for _ in range(1):
         enc = ops.vq_argmin(z, E)
     ops.row_gather(enc, E, channel_first=True)
     torch.cuda.synchronize()
