@@ -222,6 +222,16 @@ int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV
                               int dv2_col0, int B, int H, int NQ, int head_dim, void* workspace, size_t workspace_bytes,
                               void* stream);
 
+/* ---- fp32-accurate mode (logits within 1e-4 of the fp32 reference; configs[0]) ---------------------------- */
+/* x (fp32 [rows, K], row stride ld) -> bf16 [rows, 3K] = hi | lo | hi (weight_side = 0) or hi | hi | lo (weight_side = 1),
+ * hi = bf16(x), lo = bf16(x - hi).  mebt_gemm_bf16 on the two splits (K' = 3K, fp32 output) then evaluates the
+ * nn.Linear of mebt/modules/gpt.py:126-128,140,150-155,248 with a relative error of 2^-16 per product. */
+int mebt_split_f32_bf16x3(const float* x, int ld, int rows, int K, void* out, int weight_side, void* stream);
+/* mebt_latent_attention_fwd on fp32 buffers in plain fp32 arithmetic (same geometry; no LSE, no dropout). */
+int mebt_latent_attention_fwd_f32(const float* Q, int ldq, int q_col0, const float* KV1, int ld1, int k1_col0, int v1_col0,
+                                  int NK1, const float* KV2, int ld2, int k2_col0, int v2_col0, int NK2, float* O, int ldo,
+                                  int B, int H, int NQ, int head_dim, void* stream);
+
 /* ---- optimizer step (mebt/transformer.py:749-798 configure_optimizers -> torch.optim.AdamW, betas (0.9, 0.95)) ---- */
 /* One AdamW step over flat fp32 buffers p / g / m / v [n] with torch's fused-AdamW arithmetic, plus p_bf16 = bf16(p) (the
  * tensor-core operand copy).  decay_blocks[i >> block_shift] != 0 marks elements of weight-decayed tensors; `step` counts

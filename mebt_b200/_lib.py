@@ -107,6 +107,10 @@ _SIGNATURES["mebt_stack_forward_train_dropout"] = _SIGNATURES["mebt_stack_forwar
     ctypes.POINTER(DropoutStruct), c_void_p]
 _SIGNATURES["mebt_stack_backward_dropout"] = _SIGNATURES["mebt_stack_backward"][:-3] + [
     ctypes.POINTER(DropoutStruct), c_void_p, c_size_t, c_void_p]
+_SIGNATURES["mebt_split_f32_bf16x3"] = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+_SIGNATURES["mebt_latent_attention_fwd_f32"] = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                                c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                                c_void_p]
 _SIGNATURES["mebt_adamw_flat"] = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_float,
                                   c_float, c_float, c_float, c_float, c_int, c_void_p]
 _SIGNATURES["mebt_dropout_rows"] = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_uint64,

@@ -11,7 +11,8 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..stack import LayerWeights, WeightPack, attention_core, block_forward, stack_forward
+from ..stack import (LayerWeights, PreciseWeightPack, WeightPack, attention_core, block_forward, stack_forward,
+                     stack_forward_f32)
 
 
 class GPTConfig:
@@ -170,9 +171,19 @@ class GPT(nn.Module):
             self._pack = (key, WeightPack(params, [b.mode for b in self.blocks], self.config.n_head))
         return self._pack[1]
 
+    def precise_pack(self) -> PreciseWeightPack:
+        key = _versions(self)
+        if getattr(self, "_ppack", None) is None or self._ppack[0] != key:
+            params = {"transformer." + n: p for n, p in self.named_parameters()}
+            self._ppack = (key, PreciseWeightPack(params, [b.mode for b in self.blocks], self.config.n_head))
+        return self._ppack[1]
+
     def forward_rows(self, B, lat, ctx, tgt, logits_dtype=torch.float32):
-        """Stack on 2-D bf16 streams -> logits [B*NT, V] (no reshapes / dtype round trips)."""
+        """Stack on 2-D streams -> logits [B*NT, V] (no reshapes / dtype round trips).  bf16 streams take the tcgen05
+        engine (1e-2 tolerance); fp32 streams take the fp32-accurate path (1e-4 tolerance, `precision = "fp32"`)."""
         _check_no_dropout(self, self.config.embd_pdrop, self.config.resid_pdrop, self.config.attn_pdrop)
+        if lat.dtype == torch.float32:
+            return stack_forward_f32(self.precise_pack(), B, lat, ctx, tgt).to(logits_dtype)
         return stack_forward(self.weight_pack(), B, lat, ctx, tgt, logits_dtype)
 
     def forward(self, sos_emb, contexts, targets, mask_emb, attn_bias=None, debug=False):

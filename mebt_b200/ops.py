@@ -356,3 +356,36 @@ def attention_dropout_mask(B, H, NQ, NK1, NK2, p: float, seed: int, device="cuda
     out = torch.empty(B, H, NQ, NK1 + NK2, device=device, dtype=torch.float32)
     call("mebt_attention_dropout_mask", out.data_ptr(), B, H, NQ, NK1, NK2, float(p), int(seed), _stream())
     return out
+
+
+# ---- fp32-accurate mode (bf16x3 split GEMM + fp32 attention); see csrc/precise.cu -------------------------------------
+def split3(x, weight_side: bool):
+    """fp32 [rows, K] -> bf16 [rows, 3K] = hi|lo|hi (activations) or hi|hi|lo (weights)."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise MebtError("split3: fp32 [rows, K] with unit column stride expected")
+    rows, K = x.shape
+    out = torch.empty(rows, 3 * K, device=x.device, dtype=torch.bfloat16)
+    call("mebt_split_f32_bf16x3", x.data_ptr(), x.stride(0), rows, K, out.data_ptr(), int(weight_side), _stream())
+    return out
+
+
+def gemm_f32(a, w_split, bias=None, residual=None, gelu=False):
+    """out[M,N] (fp32) = act(a @ W^T + bias) (+ residual) to fp32 accuracy: a fp32 [M,K]; w_split = split3(W, True)."""
+    if residual is not None and gelu:
+        raise MebtError("gemm_f32: residual and gelu are exclusive")
+    out = residual.clone() if residual is not None else None          # C += A W^T + bias on top of the residual
+    if out is None:
+        out = torch.empty(a.shape[0], w_split.shape[0], device=a.device, dtype=torch.float32)
+    return gemm(split3(a, False), w_split, bias, gelu=gelu, out=out, accumulate=residual is not None)
+
+
+def attention_f32(q, q_col0, kv1, k1_col0, v1_col0, nk1, kv2, k2_col0, v2_col0, nk2, B, H, NQ):
+    """mebt_latent_attention_fwd on fp32 buffers in fp32 arithmetic.  Returns O [B*NQ, H*64] fp32."""
+    _need_cuda(q, kv1, kv2)
+    out = torch.empty(B * NQ, H * 64, device=q.device, dtype=torch.float32)
+    call("mebt_latent_attention_fwd_f32", q.data_ptr(), q.stride(0), q_col0,
+         _ptr(kv1) if nk1 > 0 else None, kv1.stride(0) if nk1 > 0 else 0, k1_col0, v1_col0, nk1,
+         _ptr(kv2) if nk2 > 0 else None, kv2.stride(0) if nk2 > 0 else 0, k2_col0, v2_col0, nk2,
+         out.data_ptr(), out.stride(0), B, H, NQ, 64, _stream())
+    return out

@@ -206,3 +206,96 @@ def stack_forward_ops(pack: WeightPack, B: int, lat, ctx, tgt, logits_dtype=torc
         lat, ctx, tgt = block_forward(w, pack.n_head, B, lat, ctx, tgt)
     xf = ops.layernorm(tgt, pack.lnf_w, pack.lnf_b)
     return ops.gemm(xf, pack.w_head, out_dtype=logits_dtype)
+
+
+# ---- fp32-accurate mode -----------------------------------------------------------------------------------------------
+class PreciseWeightPack:
+    """Weights of the stack as bf16 (hi | hi | lo) splits for the fp32-accurate GEMM (csrc/precise.cu); LayerNorm
+    parameters and biases stay fp32."""
+
+    def __init__(self, params: Mapping[str, torch.Tensor], modes, n_head: int, prefix: str = "transformer."):
+        self.modes = list(modes)
+        self.n_head = n_head
+        f32 = lambda t: t.detach().float().contiguous()
+        sp = lambda t: ops.split3(f32(t), True)
+        self.layers = []
+        for i, mode in enumerate(self.modes):
+            p = f"{prefix}blocks.{i}."
+            wq, wk, wv = (params[p + f"attn.{n}.weight"].detach().float() for n in ("query", "key", "value"))
+            bq, bk, bv = (params[p + f"attn.{n}.bias"].detach().float() for n in ("query", "key", "value"))
+            self.layers.append(LayerWeights(
+                mode=mode,
+                ln1_w=f32(params[p + "ln1.weight"]), ln1_b=f32(params[p + "ln1.bias"]),
+                ln2_w=f32(params[p + "ln2.weight"]), ln2_b=f32(params[p + "ln2.bias"]),
+                w_qkv=sp(torch.cat([wq, wk, wv], 0)), b_qkv=torch.cat([bq, bk, bv]).contiguous(),
+                w_proj=sp(params[p + "attn.proj.weight"]), b_proj=f32(params[p + "attn.proj.bias"]),
+                w_fc1=sp(params[p + "mlp.0.weight"]), b_fc1=f32(params[p + "mlp.0.bias"]),
+                w_fc2=sp(params[p + "mlp.2.weight"]), b_fc2=f32(params[p + "mlp.2.bias"])))
+        self.lnf_w = f32(params[prefix + "ln_f.weight"])
+        self.lnf_b = f32(params[prefix + "ln_f.bias"])
+        self.w_head = sp(params[prefix + "head.weight"])
+        self.D = self.lnf_w.numel()
+        self.V = self.w_head.shape[0]
+
+
+def _attention_core_f32(w: LayerWeights, n_head: int, B: int, qn, kn1, nk1: int, kn2=None, nk2: int = 0, q_is_k1=False):
+    D = qn.shape[1]
+    NQ = qn.shape[0] // B
+    if q_is_k1:
+        qkv = ops.gemm_f32(qn, w.w_qkv, w.b_qkv)                  # [B*NQ, 3D]
+        q_buf, kv1, k1c, v1c = qkv, qkv, D, 2 * D
+    else:
+        q_buf = ops.gemm_f32(qn, w.w_qkv[:D], w.b_qkv[:D])
+        kv1, k1c, v1c = None, 0, 0
+        if nk1 > 0:
+            kv1 = ops.gemm_f32(kn1, w.w_qkv[D:], w.b_qkv[D:])
+            k1c, v1c = 0, D
+    kv2 = ops.gemm_f32(kn2, w.w_qkv[D:], w.b_qkv[D:]) if nk2 > 0 else None
+    return ops.attention_f32(q_buf, 0, kv1, k1c, v1c, nk1, kv2, 0, D, nk2, B, n_head, NQ)
+
+
+def stack_forward_f32(pack: PreciseWeightPack, B: int, lat, ctx, tgt):
+    """GPT.forward (gpt.py:234-253, eval mode) on fp32 streams [B*rows, D] with fp32-accurate GEMMs and attention:
+    the path behind the 1e-4 tolerance of BASELINE.json's configs[0].  Returns fp32 logits [B*NT, V]."""
+    D = pack.D
+    L, NC, NT = lat.shape[0] // B, ctx.shape[0] // B, tgt.shape[0] // B
+    last = -1
+    for i, m in enumerate(pack.modes):
+        if m in ("latent_dec", "maskgit"):
+            last = i
+    for i, w in enumerate(pack.layers):
+        if i > last:
+            break
+        ln1 = lambda t: ops.layernorm(t, w.ln1_w, w.ln1_b)
+        mode = w.mode
+        if mode == "latent_enc":
+            qn = ln1(lat)
+            att = _attention_core_f32(w, pack.n_head, B, qn, ln1(ctx) if NC > 0 else None, NC)
+        elif mode == "latent_self":
+            qn = ln1(lat)
+            att = _attention_core_f32(w, pack.n_head, B, qn, None, L, q_is_k1=True)
+        elif mode == "latent_dec":
+            qn = ln1(tgt)
+            att = _attention_core_f32(w, pack.n_head, B, qn, ln1(lat), L)
+        elif mode == "lt2l":
+            qn = ln1(lat)
+            att = _attention_core_f32(w, pack.n_head, B, qn, None, L, ln1(tgt) if NT > 0 else None, NT, q_is_k1=True)
+        elif mode == "maskgit":
+            both = torch.cat([ctx.view(B, NC, D), tgt.view(B, NT, D)], 1).reshape(B * (NC + NT), D)
+            qn = ln1(both)
+            att = _attention_core_f32(w, pack.n_head, B, qn, None, NC + NT, q_is_k1=True)
+        else:
+            raise ValueError(f"unknown block mode {mode!r}")
+        x = ops.gemm_f32(att, w.w_proj, w.b_proj, residual=qn)
+        h = ops.layernorm(x, w.ln2_w, w.ln2_b)
+        u = ops.gemm_f32(h, w.w_fc1, w.b_fc1, gelu=True)
+        x = ops.gemm_f32(u, w.w_fc2, w.b_fc2, residual=x)
+        if mode in ("latent_enc", "latent_self", "lt2l"):
+            lat = x
+        elif mode == "latent_dec":
+            tgt = x
+        else:
+            x3 = x.view(B, NC + NT, D)
+            ctx, tgt = x3[:, :NC].reshape(B * NC, D), x3[:, NC:].reshape(B * NT, D)
+    xf = ops.layernorm(tgt, pack.lnf_w, pack.lnf_b)
+    return ops.gemm_f32(xf, pack.w_head)

@@ -169,6 +169,9 @@ class Net2NetTransformer(_Base):
         self._rng_offset = 0
         # dtype of the logits the head writes for the internal sampling / loss paths
         self.logits_dtype = torch.float32
+        # "bf16": tcgen05 engine, logits within 1e-2 of the fp32 reference; "fp32": split-GEMM + fp32 attention path,
+        # within 1e-4 (north_star tolerances).  Also settable from the config (`precision: fp32`).
+        self.precision = str(getattr(transformer_config, "precision", "bf16"))
         self.save_hyperparameters()
 
     # ---- checkpoint / stage plumbing (transformer.py:170-214) ---------------------------------------------------
@@ -202,8 +205,11 @@ class Net2NetTransformer(_Base):
         if not x_indices.is_cuda:
             raise MebtError("mebt_b200 runs on CUDA tensors only (no CPU fallback); move the model and inputs to cuda")
         B = x_indices.shape[0]
+        if self.precision not in ("bf16", "fp32"):
+            raise MebtError(f"precision must be 'bf16' or 'fp32', not {self.precision!r}")
+        stream_dtype = torch.float32 if self.precision == "fp32" else torch.bfloat16
         ctx, tgt, lat = ops.embed_gather(x_indices, context_indices, target_indices, self.tok_emb.weight, self.pos_emb,
-                                         self.mask_emb, self.sos_emb)
+                                         self.mask_emb, self.sos_emb, out_dtype=stream_dtype)
         return self.transformer.forward_rows(B, lat, ctx, tgt, logits_dtype or self.logits_dtype)
 
     def _sample_rows(self, logits_rows, temperature, top_k, top_p, return_probs=False):

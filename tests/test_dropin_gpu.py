@@ -196,3 +196,28 @@ def test_codebook_and_vqgan_boundary():
     assert (enc.cpu() != ref["encodings"]).sum() <= 2
     dec = vq.decode(ref["encodings"].cuda())
     assert torch.equal(dec.cpu(), O.codebook_decode_gather(ref["encodings"], E))
+
+
+def test_fp32_precision_forward_and_loss_vs_reference_fixture():
+    """BASELINE configs[0] (MeBT tiny, fwd + masked CE) with `precision = "fp32"`: logits' log-sum-exp and the
+    loss within 1e-4 of what the unmodified reference produced; targets and mask split bit-exact."""
+    from oracle import mebt_oracle as O
+    z, cfg = load_golden("shared_step_tiny")
+    P = O.make_weights(cfg, int(z["wseed"]))
+    model = build_model(cfg, P)
+    model.precision = "fp32"
+    x, indices = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["indices"]).cuda()
+    B = x.shape[0]
+    for i, t in enumerate(z["ts"]):
+        logits, target, NT_weight, seq_len = model(x, None, t=float(t), indices=indices)
+        ce, loss, acc1, acc5, ratio, sl, ntw = z[f"t{i}_scalars"]
+        assert (target.cpu().numpy() == z[f"t{i}_target"]).all()
+        lse = torch.logsumexp(logits, -1).cpu().numpy()
+        assert np.abs(lse - z[f"t{i}_lse"]).max() < 1e-4 * np.abs(z[f"t{i}_lse"]).max()
+        ce_gpu = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), target.reshape(-1), reduction="sum")
+        assert abs(float(ce_gpu) - ce) < 1e-4 * ce
+        from mebt_b200 import ops
+        stats, _ = ops.masked_ce(logits.reshape(-1, logits.shape[-1]), target.reshape(-1), 0.0)
+        assert abs(float(stats[0]) - ce) < 1e-4 * ce                           # the K5 kernel on the fp32 logits
+        loss_gpu = float(stats[0]) / (B * sl * ratio ** 1.0)
+        assert abs(loss_gpu - loss) < 1e-4 * loss
