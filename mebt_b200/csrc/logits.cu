@@ -129,6 +129,104 @@ __global__ void __launch_bounds__(LT) masked_ce_kernel(const T* __restrict__ log
   }
 }
 
+// K5, bf16 logits (the training path): 256 threads per row, the row kept PACKED in registers (8 x 16 bytes = 64 logits per
+// thread, 32 registers) so that four rows are in flight per SM and their load / reduce / store phases overlap; one
+// combined block reduction for (max, sum), exponentials on MUFU ex2 (the fp32 kernel above stays the generic path).
+constexpr int CE_T = 256;
+__global__ void __launch_bounds__(CE_T, 3) masked_ce_bf16_kernel(const __nv_bfloat16* __restrict__ logits, long long ld,
+                                                              const int64_t* __restrict__ targets, int V, float smoothing,
+                                                              float* __restrict__ row_loss, int* __restrict__ row_rank,
+                                                              __nv_bfloat16* dlogits, long long ldd, float grad_scale) {
+  __shared__ float red_a[CE_T / 32], red_b[CE_T / 32];
+  __shared__ int red_i[CE_T / 32];
+  const long long row = blockIdx.x;
+  const __nv_bfloat16* xr = logits + row * ld;
+  const int tgt = int(targets[row]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4 v[8];
+  float m = -INFINITY, total = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = (threadIdx.x + CE_T * i) * 8;
+    if (c < V) {
+      v[i] = *reinterpret_cast<const uint4*>(xr + c);
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        m = fmaxf(m, fmaxf(f.x, f.y));
+        total += f.x + f.y;
+      }
+    }
+  }
+  m = warp_max(m);
+  total = warp_sum(total);
+  if (lane == 0) { red_a[warp] = m; red_b[warp] = total; }
+  __syncthreads();
+  m = red_a[0];
+  total = red_b[0];
+#pragma unroll
+  for (int i = 1; i < CE_T / 32; ++i) { m = fmaxf(m, red_a[i]); total += red_b[i]; }
+  __syncthreads();
+  const float xt = (tgt >= 0 && tgt < V) ? __bfloat162float(xr[tgt]) : 0.f;
+  const float ml2 = m * 1.4426950408889634f;
+  float se = 0.f;
+  int rank = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = (threadIdx.x + CE_T * i) * 8;
+    if (c < V) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        se += ex2_approx(fmaf(f.x, 1.4426950408889634f, -ml2)) + ex2_approx(fmaf(f.y, 1.4426950408889634f, -ml2));
+        rank += (f.x > xt) + (f.y > xt);
+      }
+    }
+  }
+  se = warp_sum(se);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+  if (lane == 0) { red_a[warp] = se; red_i[warp] = rank; }
+  __syncthreads();
+  se = 0.f;
+  rank = 0;
+#pragma unroll
+  for (int i = 0; i < CE_T / 32; ++i) { se += red_a[i]; rank += red_i[i]; }     // fixed order: deterministic
+  const float lse = m + logf(se);
+  if (threadIdx.x == 0) {
+    const float nll = lse - xt;
+    const float smooth = lse - total / float(V);
+    row_loss[row] = (1.f - smoothing) * nll + smoothing * smooth;
+    if (row_rank != nullptr) row_rank[row] = rank;
+  }
+  if (dlogits != nullptr) {
+    // d(sum CE)/dlogit_v = softmax_v - (1-eps) [v == t] - eps / V, times the upstream scale (may overwrite the logits)
+    __nv_bfloat16* dr = dlogits + row * ldd;
+    const float inv = grad_scale / se, u = grad_scale * smoothing / float(V), hot = grad_scale * (1.f - smoothing);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = (threadIdx.x + CE_T * i) * 8;
+      if (c < V) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16x2(w[k]);
+          float g0 = fmaf(ex2_approx(fmaf(f.x, 1.4426950408889634f, -ml2)), inv, -u);
+          float g1 = fmaf(ex2_approx(fmaf(f.y, 1.4426950408889634f, -ml2)), inv, -u);
+          if (tgt == c + 2 * k) g0 -= hot;
+          if (tgt == c + 2 * k + 1) g1 -= hot;
+          ow[k] = pack_bf16x2(g0, g1);
+        }
+        *reinterpret_cast<uint4*>(dr + c) = o;
+      }
+    }
+  }
+}
+
 // deterministic single-CTA reduction of the per-row results: out = {ce_sum, n_top1, n_top5}
 __global__ void ce_reduce_kernel(const float* __restrict__ row_loss, const int* __restrict__ row_rank, int rows,
                                  float* __restrict__ out) {
@@ -615,6 +713,9 @@ int mebt_masked_ce(const void* logits, long long ld, int dtype, const int64_t* t
   if (dtype == MEBT_DTYPE_FP32)
     masked_ce_kernel<float><<<rows, LT, 0, st>>>(static_cast<const float*>(logits), ld, targets, V, label_smoothing,
                                                  row_loss, row_rank, static_cast<float*>(dlogits), ld_d, grad_scale);
+  else if (dtype == MEBT_DTYPE_BF16 && V % 8 == 0 && V <= CE_T * 64 && ld % 8 == 0 && (dlogits == nullptr || ld_d % 8 == 0))
+    masked_ce_bf16_kernel<<<rows, CE_T, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, targets, V, label_smoothing,
+                                                 row_loss, row_rank, static_cast<__nv_bfloat16*>(dlogits), ld_d, grad_scale);
   else if (dtype == MEBT_DTYPE_BF16)
     masked_ce_kernel<__nv_bfloat16><<<rows, LT, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, targets, V,
                                                          label_smoothing, row_loss, row_rank,
