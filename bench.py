@@ -400,6 +400,13 @@ def main():
                     "share_of_step": gemm["ms"] / total_ms if total_ms else None,
                     "families_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]},
                     "families_launches": {k: v["launches"] for k, v in prof.items() if v["launches"]}}
+        tr = REPO / "profiles" / "r01_kernel_traffic.json"        # ncu --set full capture of one representative launch
+        if tr.exists():
+            t = json.loads(tr.read_text()).get("gemm_bf16_kernel")
+            if t:
+                roofline["traffic"] = t["dram_bytes"]
+                roofline["traffic_note"] = (f"dram read+write of one launch at {t['shape']} (ncu, profiles/r01_ncu_kernels.md); "
+                                            f"algorithmic bytes of that launch {t['algorithmic_bytes']}")
         for fam in ("sample", "ce", "layernorm"):
             f = prof[fam]
             if f["ms"] > 0:
