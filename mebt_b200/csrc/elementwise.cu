@@ -210,7 +210,7 @@ int* device_err_flag() {
 // bf16 -> bf16 fast path for D = 256 * NV: 16-byte loads (8 elements per lane per load) and TWO rows per warp with
 // all loads of both rows issued before the first reduction, which doubles the bytes each warp keeps in flight.
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+__global__ void __launch_bounds__(256, 3) layernorm_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta,
                                                                __nv_bfloat16* __restrict__ y, int ldy, int rows,
@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(256) layernorm_bf16x2_kernel(const __nv_bfloat
     for (int i = 0; i < NV; ++i)
       raw[r][i] = (r == 0 || two) ? *reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + (lane + 32 * i) * 8)
                                   : make_uint4(0, 0, 0, 0);
-  float v[2][NV][8];
+  // the rows stay PACKED in registers (16 per row at D = 1024) and are unpacked on the fly in each of the three passes:
+  // half the registers of an fp32 copy, so that twice as many rows are in flight per SM
   float sum[2] = {0.f, 0.f};
 #pragma unroll
   for (int r = 0; r < 2; ++r)
@@ -239,7 +240,6 @@ __global__ void __launch_bounds__(256) layernorm_bf16x2_kernel(const __nv_bfloat
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = unpack_bf16x2(w[k]);
-        v[r][i][2 * k] = f.x; v[r][i][2 * k + 1] = f.y;
         sum[r] += f.x + f.y;
       }
     }
@@ -250,9 +250,16 @@ __global__ void __launch_bounds__(256) layernorm_bf16x2_kernel(const __nv_bfloat
   for (int r = 0; r < 2; ++r) {
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { const float d = v[r][i][k] - mu[r]; sq += d * d; }
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        const float d0 = f.x - mu[r], d1 = f.y - mu[r];
+        sq += d0 * d0;
+        sq += d1 * d1;
+      }
+    }
     rs[r] = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
   }
   if (lane == 0) {
@@ -269,9 +276,14 @@ __global__ void __launch_bounds__(256) layernorm_bf16x2_kernel(const __nv_bfloat
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       if (r == 1 && !two) break;
+      const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
       float o[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = (v[r][i][k] - mu[r]) * rs[r] * gg[k] + bb[k];
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        o[2 * k] = (f.x - mu[r]) * rs[r] * gg[2 * k] + bb[2 * k];
+        o[2 * k + 1] = (f.y - mu[r]) * rs[r] * gg[2 * k + 1] + bb[2 * k + 1];
+      }
       uint4 u;
       u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
       *reinterpret_cast<uint4*>(y + (row0 + r) * ldy + c) = u;
