@@ -369,6 +369,55 @@ def gen_grads_dropout(cfg_name, B, wseed, dseed, t, p, mseed):
     save(f"grads_dropout_{cfg_name}", cfg, **arrays)
 
 
+def _reference_script_functions():
+    """bidirect_sample / extrapolate exactly as written in the reference's sample_vqgan_transformer_videos.py: the two
+    FunctionDefs are compiled out of the script's source (the module itself imports lightning, omegaconf, matplotlib...)."""
+    import ast
+
+    from einops import rearrange, repeat
+    src = open(os.path.join(REF, "sample_vqgan_transformer_videos.py")).read()
+    tree = ast.parse(src)
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("bidirect_sample", "extrapolate")]
+    ns = dict(torch=torch, np=np, repeat=repeat, rearrange=rearrange)
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "sample_vqgan_transformer_videos.py", "exec"), ns)
+    return ns["bidirect_sample"], ns["extrapolate"]
+
+
+def gen_pipelines():
+    """Sliding-window pipelines of the sampling script driven by tests/helpers.py::FakeSampler (deterministic tokens,
+    recorded calls): the reference's code maps, scores and the arguments of every model.sample call."""
+    sys.path.insert(0, str(REPO / "tests"))
+    from helpers import FakeSampler
+    bidirect, extrapolate = _reference_script_functions()
+    arrays = {}
+
+    def record(tag, model, log):
+        arrays[f"{tag}_code_maps"] = log["code_maps"]
+        arrays[f"{tag}_samples"] = log["samples"]
+        if "score" in log:
+            arrays[f"{tag}_score"] = log["score"]
+        arrays[f"{tag}_n_calls"] = len(model.calls)
+        for i, c in enumerate(model.calls):
+            arrays[f"{tag}_call{i}_x"], arrays[f"{tag}_call{i}_ctx"], arrays[f"{tag}_call{i}_tgt"] = c["x"], c["ctx"], c["tgt"]
+            arrays[f"{tag}_call{i}_meta"] = np.array(json.dumps({k: (list(v) if isinstance(v, tuple) else v) for k, v in c.items()
+                                                                 if k not in ("x", "ctx", "tgt")}))
+
+    m = FakeSampler((4, 4, 4))
+    record("bi_one", m, bidirect(m, 2, total_length=16, step_size=16, context_size=12, temperature=0.9, top_k=5,
+                                 vid_n_steps=6, vid_c_temp=2.0, ctemp_schedule="cosine", strategy="maskgit", bootstrap=3))
+    m = FakeSampler((4, 4, 4))
+    record("bi_one_nb", m, bidirect(m, 3, total_length=16, step_size=16, context_size=8, vid_n_steps=4, strategy="random"))
+    m = FakeSampler((4, 4, 4))
+    torch.manual_seed(5)
+    vq = torch.randint(0, FakeSampler.V, (2, 4, 4, 4))
+    arrays["ex_input"] = vq
+    record("ex", m, extrapolate(m, vq, total_length=40, step_size=16, context_size=8, temperature=0.8, top_p=0.9,
+                                vid_n_steps=5, vid_c_temp=3.0))
+    m = FakeSampler((4, 4, 4))
+    record("ex_odd", m, extrapolate(m, vq, total_length=30, step_size=16, context_size=12, vid_n_steps=7))
+    save("pipelines", dict(note="FakeSampler"), **arrays)
+
+
 def main():
     install_stubs()
     sys.path.insert(0, REF)          # `import mebt` resolves to the reference; also its top-level utils.py
@@ -387,10 +436,14 @@ def main():
     gen_grads_dropout("micro", 2, wseed=1, dseed=2, t=0.4, p=0.1, mseed=11)
     gen_sampling("micro", 2, wseed=1, seed=9)
     gen_sampling("tiny", 2, wseed=1, seed=9)
+    gen_pipelines()
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "dropout":     # only the fixture added after the first generation
+    if len(sys.argv) > 1 and sys.argv[1] == "pipelines":
+        sys.path.insert(1, str(REPO))
+        gen_pipelines()
+    elif len(sys.argv) > 1 and sys.argv[1] == "dropout":     # only the fixture added after the first generation
         install_stubs()
         sys.path.insert(0, REF)
         sys.path.insert(1, str(REPO))

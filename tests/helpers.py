@@ -73,3 +73,62 @@ def reference_dropout_masks(z, p):
             layer, sub = name[len("transformer.blocks."):].split(".", 1)
             drop[(int(layer), site[sub])] = factor
     return drop
+
+
+class FakeSampler:
+    """Stands in for Net2NetTransformer in the pipeline tests (bidirect_sample / extrapolate are host orchestration over
+    `model.sample`): deterministic tokens, every call recorded.  Used both by tests/golden/make_golden.py (driving the
+    REFERENCE's functions) and by tests/test_pipelines_cpu.py (driving mebt_b200.pipelines)."""
+
+    V = 32
+
+    class _MS:
+        def __init__(self, shape):
+            self.shape = shape
+
+    class _FS:
+        @staticmethod
+        def decode(code_map):
+            B, T, H, W = code_map.shape
+            return (code_map.float().view(B, 1, T, H, W).repeat(1, 3, 4, 1, 1) / 16.0) - 1.0
+
+    def __init__(self, shape):
+        self.mask_sampler = self._MS(shape)
+        self.first_stage_model = self._FS()
+        self.device = torch.device("cpu")
+        self.calls = []
+
+    def sample(self, x, c, temperature=1.0, top_k=None, top_p=None, n_steps=8, context_indices=None, target_indices=None,
+               strategy="maskgit", context_temperature=4.5, phase_history=None, refine_steps=1, forget_pivot=False,
+               skips=(False, False, False), debug=False, ctemp_schedule="linear", edit=False):
+        B = x.shape[0]
+        x = x.reshape(B, -1).clone()
+        N = x.shape[1]
+        k = len(self.calls)
+        if target_indices is None:
+            g = torch.Generator().manual_seed(100 + k)
+            perm = torch.stack([torch.randperm(N, generator=g) for _ in range(B)])
+            context_indices, target_indices = perm[:, :0], perm
+        self.calls.append(dict(temperature=temperature, top_k=top_k, top_p=top_p, n_steps=n_steps, strategy=strategy,
+                               context_temperature=context_temperature, skips=skips, debug=debug,
+                               ctemp_schedule=ctemp_schedule, edit=edit, x=x.clone(),
+                               ctx=context_indices.clone(), tgt=target_indices.clone()))
+        vals = (target_indices * 7 + 3 * k + 1) % self.V
+        if strategy == "bootstrap":                       # reveals n_steps tokens, the rest stays masked
+            n_new = min(n_steps, target_indices.shape[1])
+            x.scatter_(1, target_indices[:, :n_new], vals[:, :n_new])
+            ctx_out = torch.cat([context_indices, target_indices[:, :n_new]], 1)
+            tgt_out = target_indices[:, n_new:]
+            filled = target_indices[:, :n_new]
+        else:
+            x.scatter_(1, target_indices, vals)
+            ctx_out = torch.cat([context_indices, target_indices], 1)
+            tgt_out = target_indices[:, :0]
+            filled = target_indices
+        if not debug:
+            return x, ctx_out, tgt_out
+        probs = -torch.ones(B, N, self.V)
+        g = torch.Generator().manual_seed(200 + k)
+        p = torch.rand(B, filled.shape[1], self.V, generator=g) + 0.05
+        probs.scatter_(1, filled.unsqueeze(-1).expand(-1, -1, self.V), p / p.sum(-1, keepdim=True))
+        return x, ctx_out, tgt_out, [], [], probs

@@ -221,3 +221,25 @@ def test_fp32_precision_forward_and_loss_vs_reference_fixture():
         assert abs(float(stats[0]) - ce) < 1e-4 * ce                           # the K5 kernel on the fp32 logits
         loss_gpu = float(stats[0]) / (B * sl * ratio ** 1.0)
         assert abs(loss_gpu - loss) < 1e-4 * loss
+
+
+def test_sampling_script_pipelines_on_the_cuda_model():
+    """bidirect_sample / extrapolate (sample_vqgan_transformer_videos.py:22-157) over the CUDA sampler: window
+    bookkeeping on real `model.sample` outputs (the call-by-call parity with the reference's functions is the CPU test
+    tests/test_pipelines_cpu.py)."""
+    from oracle import mebt_oracle as O
+    from mebt_b200.pipelines import bidirect_sample, extrapolate
+    z, cfg = load_golden("forward_tiny")
+    model = build_model(cfg, O.make_weights(cfg, int(z["wseed"])), schedule="cosine")
+    B, hw = 2, 256
+    log = bidirect_sample(model, B, total_length=16, step_size=16, context_size=8, vid_n_steps=4, vid_c_temp=1.0, bootstrap=2)
+    cm = log["code_maps"]
+    assert cm.shape == (B, 4, 16, 16) and cm.dtype == torch.long and int(cm.min()) >= 0 and int(cm.max()) < 16384
+    assert log["score"].shape == (B,) and torch.isfinite(log["score"]).all() and (log["score"] < 0).all()
+    start = cm.clone()
+    log = extrapolate(model, start, total_length=32, step_size=16, context_size=8, vid_n_steps=3, vid_c_temp=1.0)
+    cm2 = log["code_maps"]
+    assert cm2.shape == (B, 8, 16, 16)                       # 4 given frames + 2 jumps of 2 new frames
+    assert torch.equal(cm2[:, :4], start)                    # the given tokens are kept
+    assert int(cm2.min()) >= 0 and int(cm2.max()) < 16384
+    assert not torch.equal(cm2[:, 4:6], cm2[:, 6:8])
