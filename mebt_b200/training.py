@@ -68,6 +68,7 @@ class TrainState:
         self.flat_grad = torch.zeros(total, device=self.device, dtype=torch.float32)
         self.flat_bf16 = torch.empty(total, device=self.device, dtype=torch.bfloat16)
         self.offsets = {}
+        self._grad_views = []             # (parameter, its view of the flat gradient buffer)
         off = 0
         for n in order:
             p = named[n]
@@ -75,6 +76,7 @@ class TrainState:
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.flat_grad[off:off + k].view(p.shape)
+            self._grad_views.append((p, p.grad))
             self.offsets[n] = (off, k)
             off += k
         self.order = order
@@ -90,6 +92,7 @@ class TrainState:
         self._saved = None
         self._bwd_ws = None
         self.comm_stream = torch.cuda.Stream(device=self.device)
+        model.__dict__["_train_state"] = self          # found again by Net2NetTransformer.training_step
 
     # ---- pointer tables for the C engine ---------------------------------------------------------------------------
     def _view(self, buf, name):
@@ -108,10 +111,21 @@ class TrainState:
                 setattr(self.c_layers[i], field, self._view(src, name).data_ptr())
                 setattr(self.c_grads[i], field, self._view(self.flat_grad, name).data_ptr())
 
+    def _param_versions(self):
+        return tuple(p._version for p, _ in self._grad_views)
+
     def refresh_operands(self):
         """fp32 masters -> bf16 tensor-core operands, one kernel over the flat buffer (after every optimizer step)."""
         call("mebt_cast_f32_to_bf16", self.flat.data_ptr(), self.flat_bf16.data_ptr(), self.flat.numel() // 4 * 4,
              torch.cuda.current_stream().cuda_stream)
+        self._op_version = self._param_versions()
+
+    def relink_grads(self):
+        """`optimizer.zero_grad(set_to_none=True)` (torch's default) drops the `.grad` views of the flat gradient buffer;
+        put them back so that any torch optimizer sees what backward wrote."""
+        for p, g in self._grad_views:
+            if p.grad is not g:
+                p.grad = g
 
     # ---- one step ---------------------------------------------------------------------------------------------------
     def _buffers(self, B, NC, NT):
@@ -143,6 +157,8 @@ class TrainState:
         B = x_indices.shape[0]
         NC, NT = ctx_idx.shape[1], tgt_idx.shape[1]
         saved, _ = self._buffers(B, NC, NT)
+        if self._param_versions() != self._op_version:          # a torch optimizer (or the user) updated the masters in place
+            self.refresh_operands()
         ctx, tgt, lat = ops.embed_gather(x_indices, ctx_idx, tgt_idx, m.tok_emb.weight, m.pos_emb, m.mask_emb, m.sos_emb)
         drop, embd_p, seed = self._dropout()
         if embd_p > 0.0:
@@ -202,6 +218,7 @@ class TrainState:
         if world_size > 1:
             works.append(self._all_reduce_async(*self.emb_slice, cur))
             cur.wait_stream(self.comm_stream)
+        self.relink_grads()
         return works
 
     def _all_reduce_async(self, lo, hi, producer_stream):
@@ -211,9 +228,11 @@ class TrainState:
         with torch.cuda.stream(self.comm_stream):
             return parallel.allreduce_mean_(self.flat_grad[lo:hi], async_op=True)
 
-    def loss_and_backward(self, x_indices, indices, t=None, world_size=1):
+    def loss_and_backward(self, x_indices, indices, t=None, world_size=1, defer_backward=False):
         """shared_step + backward fused: -> dict(loss, acc1, acc5, ratio) as device tensors / floats.
-        loss = CE_sum / (B * seq_len * ratio**avg_loss) (mebt/transformer.py:723-730)."""
+        loss = CE_sum / (B * seq_len * ratio**avg_loss) (mebt/transformer.py:723-730).
+        defer_backward=True stops after the loss and returns (dict, dlogits) for a later `backward(dlogits)`
+        (the autograd bridge behind Net2NetTransformer.training_step)."""
         m = self.model
         B = x_indices.shape[0]
         x_indices = x_indices.reshape(B, -1)
@@ -231,9 +250,12 @@ class TrainState:
         scale = 1.0 / (B * seq_len * ratio ** m.config.avg_loss)
         logits = self.forward(x_indices, ctx_idx, tgt_idx)
         stats, _ = ops.masked_ce(logits, z_targets.reshape(-1), m.label_smoothing, dlogits=logits, grad_scale=scale)
-        self.backward(logits, world_size=world_size)
         n = float(B * NT)
-        return dict(loss=stats[0] * scale, acc1=stats[1] * (100.0 / n), acc5=stats[2] * (100.0 / n), ratio=ratio)
+        out = dict(loss=stats[0] * scale, acc1=stats[1] * (100.0 / n), acc5=stats[2] * (100.0 / n), ratio=ratio)
+        if defer_backward:
+            return out, logits                                  # logits now hold d(loss)/d(logits)
+        self.backward(logits, world_size=world_size)
+        return out
 
     def make_optimizer(self, lr=1.08e-5, weight_decay=0.01, flat=True):
         """The reference's AdamW (configure_optimizers, transformer.py:749-798: betas (0.9, 0.95), decay only on the
@@ -304,3 +326,27 @@ class FlatAdamW:
         self.steps = int(sd["steps"])
         for g, lr in zip(self.param_groups, sd["lr"]):
             g["lr"] = lr
+
+
+class TrainStepFunction(torch.autograd.Function):
+    """Autograd bridge for the drop-in `training_step`: forward runs stem + stack + fused masked CE on the CUDA engine
+    and returns the loss; `loss.backward()` runs the engine's backward, which writes every parameter gradient straight
+    into `p.grad` (views of the flat gradient buffer) and, under torch.distributed, averages them over ranks the way
+    the reference's DDP does (train_transformer.py:39-41).  Gradients are overwritten, not accumulated, per call."""
+
+    @staticmethod
+    def forward(ctx, anchor, ts, x_indices, indices, world_size):
+        out, dlogits = ts.loss_and_backward(x_indices, indices, world_size=world_size, defer_backward=True)
+        ctx.ts, ctx.dlogits, ctx.world_size = ts, dlogits, world_size
+        ctx.mark_non_differentiable(out["acc1"], out["acc5"])
+        return out["loss"].reshape(()), out["acc1"], out["acc5"]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc1, g_acc5):
+        dlogits = ctx.dlogits
+        if dlogits is None:
+            raise MebtError("training_step: backward through the same step twice")
+        dlogits.mul_(g_loss.to(dlogits.dtype))                   # 1.0 unless the caller scaled the loss
+        ctx.ts.backward(dlogits, world_size=ctx.world_size)
+        ctx.dlogits = None
+        return None, None, None, None, None

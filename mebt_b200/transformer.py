@@ -482,7 +482,18 @@ class Net2NetTransformer(_Base):
         return stats[1:2] * (100.0 / n), stats[2:3] * (100.0 / n), loss, ratio
 
     def training_step(self, batch, batch_idx):
-        acc1, acc5, loss, ratio = self.shared_step(batch, batch_idx)
+        """-> loss with an autograd edge into the CUDA backward (transformer.py:734-739): `loss.backward()` fills every
+        `p.grad`; any optimizer over `self.parameters()` then applies (the bf16 operand copies follow the masters)."""
+        if next(self.parameters()).is_cuda and torch.is_grad_enabled():
+            from .training import TrainState, TrainStepFunction
+            ts = self.__dict__.get("_train_state") or TrainState(self)
+            x, c = self.get_xc(batch)
+            indices = self.get_input("indices", batch)
+            import torch.distributed as dist
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            loss, acc1, acc5 = TrainStepFunction.apply(self.mask_emb, ts, x.reshape(x.shape[0], -1), indices, world)
+        else:
+            acc1, acc5, loss, ratio = self.shared_step(batch, batch_idx)
         for name, v in (("train/loss", loss), ("train/acc1", acc1), ("train/acc5", acc5)):
             self.log(name, v, prog_bar=True, logger=True, on_step=True, on_epoch=True, sync_dist=True)
         return loss

@@ -127,3 +127,38 @@ def test_flat_adamw_matches_torch_fused_adamw():
             assert torch.allclose(p.detach(), ref_params[n].detach(), rtol=2e-5 * (step + 1), atol=2e-7 * (step + 1)), (n, step)
     w = "transformer.blocks.1.attn.proj.weight"
     assert torch.equal(ts._view(ts.flat_bf16, w), ts._view(ts.flat, w).bfloat16())
+
+
+def test_training_step_autograd_bridge_with_a_torch_optimizer():
+    """The drop-in `training_step` (transformer.py:734-739) used the reference's way: loss.backward() + any optimizer over
+    model.parameters(), zero_grad(set_to_none=True) included; gradients equal the direct TrainState path bit for bit."""
+    import random
+    z, cfg, P, model, ts = _state("micro")
+    x, indices = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["indices"]).cuda()
+    batch = dict(video=x, label=x, indices=indices)
+    lo = ts.emb_slice[0]
+    random.seed(1)
+    loss = model.training_step(batch, 0)
+    assert loss.requires_grad and loss.dim() == 0
+    loss.backward()
+    g = ts.flat_grad.clone()
+    random.seed(1)
+    out = ts.loss_and_backward(x, indices)
+    assert float(out["loss"]) == float(loss) and torch.equal(g[:lo], ts.flat_grad[:lo])
+    random.seed(1)
+    (0.5 * model.training_step(batch, 0)).backward()            # a scaled loss scales the gradients
+    assert torch.allclose(ts.flat_grad[:lo], 0.5 * g[:lo], rtol=1e-3, atol=1e-9)
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-3, betas=(0.9, 0.95), weight_decay=0.0)
+    random.seed(0)
+    losses = []
+    for i in range(8):
+        opt.zero_grad()                                         # set_to_none=True: the .grad views are re-linked by backward
+        loss = model.training_step(batch, i)
+        loss.backward()
+        assert all(p.grad is not None for p in model.parameters())
+        opt.step()                                              # in-place update of the fp32 masters; operands refresh lazily
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] - 0.3, losses
+    with torch.no_grad():
+        val = model.validation_step(batch, 0)
+    assert not val.requires_grad and torch.isfinite(val)
