@@ -257,7 +257,7 @@ def main():
         run_reference(args, cfg)
         return
     training = args.workload == "train16f"
-    B = args.batch or {"train16f": 6, "maskgit16f": 32, "vq16f": 64}.get(args.workload, 16)
+    B = args.batch or {"train16f": 6, "maskgit16f": 32, "vq16f": 64}.get(args.workload, 32)
     warmup = max(args.warmup, 3)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
