@@ -291,6 +291,19 @@ def main():
         def step_device():
             return ts.train_step(opt, x_dev, idx_dev, t=TRAIN_T, world_size=world)
 
+        def replicas_in_sync():
+            """Data-parallel invariant: after any number of steps every rank holds the same parameters (checked once,
+            outside the timed region)."""
+            try:
+                import torch.distributed as dist
+                chk = torch.stack([ts.flat.sum(dtype=torch.float64), ts.flat.abs().sum(dtype=torch.float64)])
+                lo, hi = chk.clone(), chk.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                return bool(torch.equal(lo, hi))
+            except Exception as exc:  # noqa: BLE001  (a diagnostic must never cost the bench line)
+                return f"check failed: {type(exc).__name__}"
+
         def step_e2e():
             x = x_host.to(dev, non_blocking=True)
             idx = idx_host.to(dev, non_blocking=True)
@@ -382,6 +395,7 @@ def main():
         torch.cuda.synchronize()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    in_sync = replicas_in_sync() if (training and world > 1) else None
 
     # per-kernel-family timing of one more step (events on the launch stream, recorded by the library)
     _lib.profile_enable(True)
@@ -434,6 +448,8 @@ def main():
             config.update(t=TRAIN_T, NC=N // 2, NT=N // 2, dropout=args.dropout, optimizer="AdamW fused fp32 master weights",
                           note="embd/attn/resid dropout as in configs/stl/mebt_16f.yaml; masks regenerated in backward",
                           grad_allreduce="fp32, 4 buckets + head + embeddings, overlapped with backward" if world > 1 else "none (1 GPU)")
+            if in_sync is not None:
+                config["replicas_in_sync"] = in_sync
         elif args.workload == "vq16f":
             config = {"workload": "vq16f", "videos_per_gpu": B, "latent": [256, 4, 16, 16], "codebook": [16384, 256],
                       "unit_note": "a token = one quantised latent vector (fused fp32 distance+argmin, then both gathers)"}

@@ -162,3 +162,25 @@ def test_training_step_autograd_bridge_with_a_torch_optimizer():
     with torch.no_grad():
         val = model.validation_step(batch, 0)
     assert not val.requires_grad and torch.isfinite(val)
+
+
+def test_overlapped_optimizer_update_matches_sequential():
+    """train_step(overlap_update=True): per-chunk AdamW on the side stream gives the same parameters as backward followed
+    by one whole-buffer step."""
+    z, cfg, P, model, ts = _state("micro")
+    x, indices = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["indices"]).cuda()
+    opt = ts.make_optimizer(lr=1e-3, weight_decay=0.05)
+    start = ts.flat.clone()
+    for _ in range(3):
+        ts.train_step(opt, x, indices, t=0.5, overlap_update=True)
+    torch.cuda.synchronize()
+    got = ts.flat.clone()
+    ts.flat.copy_(start)
+    ts.refresh_operands()
+    opt2 = ts.make_optimizer(lr=1e-3, weight_decay=0.05)
+    for _ in range(3):
+        ts.train_step(opt2, x, indices, t=0.5)
+    torch.cuda.synchronize()
+    lo = ts.emb_slice[0]
+    assert torch.equal(got[:lo], ts.flat[:lo])
+    assert torch.allclose(got[lo:], ts.flat[lo:], rtol=1e-5, atol=1e-7)        # embedding grads: fp32 atomics
