@@ -173,3 +173,19 @@ def test_config_yaml_shape_parses():
     assert modes.count("latent_enc") == 7 and modes.count("latent_self") == 6
     assert modes.count("latent_dec") == 6 and modes.count("lt2l") == 5 and modes[-1] == "latent_dec"
     assert m.mask_sampler.schedule == "linear" and m.t_prior.__name__ == "longest"
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/mebt_b200.h must compile as C99 (no torch / C++ types in signatures)."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = Path(__file__).resolve().parent.parent / "include" / "mebt_b200.h"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", str(hdr)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import re
+    code = re.sub(r"/\*.*?\*/", "", hdr.read_text(), flags=re.S)          # declarations only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "std::" not in code and "#include <c" not in code.replace("#include <cuda", "")
