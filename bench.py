@@ -280,7 +280,7 @@ def main():
     if training:
         from mebt_b200.training import TrainState
         model.train()
-        ts = TrainState(model, n_buckets=4)
+        ts = TrainState(model, n_buckets=8 if world > 1 else 4)   # finer buckets shorten the exposed tail of the last all-reduce
         opt = ts.make_optimizer(lr=1.08e-5, weight_decay=0.01)
         x_cpu, idx_cpu = synth_batch(cfg, B, 100 + rank)  # each rank its own batch (DistributedSampler)
         x_host, idx_host = x_cpu.pin_memory(), idx_cpu.pin_memory()
@@ -447,7 +447,7 @@ def main():
         if training:
             config.update(t=TRAIN_T, NC=N // 2, NT=N // 2, dropout=args.dropout, optimizer="AdamW fused fp32 master weights",
                           note="embd/attn/resid dropout as in configs/stl/mebt_16f.yaml; masks regenerated in backward",
-                          grad_allreduce="fp32, 4 buckets + head + embeddings, overlapped with backward" if world > 1 else "none (1 GPU)")
+                          grad_allreduce="fp32, 8 block buckets + head + embeddings, overlapped with backward" if world > 1 else "none (1 GPU)")
             if in_sync is not None:
                 config["replicas_in_sync"] = in_sync
         elif args.workload == "vq16f":
