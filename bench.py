@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the MeBT hot path on B200 (contract: the task statement; summary in DESIGN.md §5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train16f|sample128f|sample16f] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ...] [--impl reference]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic input:
 
-  train16f    (default; BASELINE.json configs[1]) STL 16-frame model — 24 blocks, D=1024, 16 heads, 256 latents,
+  train16f    (headline; BASELINE.json configs[1]) STL 16-frame model — 24 blocks, D=1024, 16 heads, 256 latents,
               N = 1024 tokens, 337 M parameters — bf16 training step at batch 6 per GPU: stem -> stack forward ->
-              fused masked CE -> full backward -> NCCL gradient all-reduce (N > 1) -> AdamW -> bf16 operand refresh.
+              fused masked CE -> full backward -> NCCL gradient exchange (N > 1) -> AdamW -> bf16 operand refresh.
               metric = masked tokens/s = all ranks' B * NT / step time, with t = 0.5 (NC = NT = 512).
   sample128f  (configs[2]) 128-frame draft-and-revise sampling, token grid [32,16,16] = 8192 tokens, script defaults
               n_draft=8, n_revise=8, M=2 -> 24 forwards and 53 248 masked-token predictions per video; videos sharded
               by batch over the ranks, no collective on the data path.
-  sample16f   the same on the 16-frame model.
+  sample16f / maskgit16f / vq16f   configs[2] on the 16-frame model, configs[4], configs[3].
+
+With no --workload the line is the train16f record AND carries the 128-frame half of BASELINE.json's metric
+("16f & 128f") under `workloads.sample128f` (8 videos per GPU, its own value / e2e / ms_per_step / roofline /
+cpu_baseline), so that the driver's 1 -> 8 GPU runs record both curves.
 
 `value`: inputs resident in HBM, CUDA events, max over ranks.  `e2e`: through the public API with the batch coming
 from pinned host memory and the result (loss / sampled ids) copied back to the host inside the timed region.
-`--impl reference` times the CPU oracle (a torch-CPU restatement of the reference; /root/reference does not exist on
-the GPU box) on the same workload (train) or a bounded sample of it (sampling) with all host threads.
+`--impl reference` times the reference's CPU implementation of the same workload on the host cores: the UNMODIFIED
+reference when a source tree is reachable ($MEBT_REF, baseline/_ref, /root/reference; `kind: "reference"`), else
+the torch-CPU oracle port (`kind: "port"`; /root/reference does not exist on the GPU box).  That arm imports neither
+`mebt_b200` nor its shared library.
 """
 from __future__ import annotations
 
@@ -29,7 +35,9 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 from pathlib import Path
+from types import SimpleNamespace
 
 import numpy as np
 import torch
@@ -47,6 +55,8 @@ CONFIGS = {
     "maskgit16f": dict(_BASE, block_size=1024, shape=[4, 16, 16]),
     "vq16f": dict(_BASE, block_size=1024, shape=[4, 16, 16]),
 }
+DEFAULT_BATCH = {"train16f": 6, "maskgit16f": 32, "vq16f": 64, "sample128f": 32, "sample16f": 32}
+SECONDARY_BATCH = {"sample128f": 8}      # videos per GPU when sample128f rides along with the default line
 MASKGIT = dict(temperature=1.0, top_k=None, top_p=None, n_steps=128, strategy="maskgit", context_temperature=6.0)
 DNR = dict(n_draft=8, draft_t=1.0, n_revise=8, revise_t=1.0, M=2)
 TRAIN_T = 0.5
@@ -117,15 +127,36 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def build_cpu_model(cfg, seed=0, pdrop=0.0):
-    """Random-init weights in the reference's distribution (N(0,0.02), zero biases, unit LayerNorm), built on the
-    CPU so that the same values feed the GPU model and the CPU oracle.  pdrop: embd/resid/attn dropout (STL yaml: 0.1)."""
-    from helpers import model_configs
-    from mebt_b200.transformer import Net2NetTransformer
-    torch.manual_seed(seed)
-    params, vq, mask = model_configs(cfg, schedule="linear")
-    params.embd_pdrop = params.resid_pdrop = params.attn_pdrop = pdrop
-    return Net2NetTransformer(params, vq, mask)
+# ---- synthetic inputs shared by both arms (no package import: the reference arm must not load the native library) ----
+def synth_weights(cfg: dict, seed: int = 0) -> dict:
+    """Random-init weights in the reference's distribution (gpt.py:225-232, transformer.py:126-140: N(0, 0.02)
+    Linear / embedding weights, zero biases, unit LayerNorm), one seeded generator per tensor, keyed by the
+    reference's state_dict names.  The same values feed the GPU model, the CPU oracle and the unmodified reference."""
+    D, V, L, N = cfg["n_embd"], cfg["vocab_size"], cfg["sos_emb"], cfg["block_size"]
+    shapes = {"mask_emb": (1, 1, D), "sos_emb": (1, L, D), "pos_emb": (1, N, D), "tok_emb.weight": (V, D)}
+    for i in range(cfg["n_layer"]):
+        p = f"transformer.blocks.{i}."
+        for ln in ("ln1", "ln2"):
+            shapes[p + ln + ".weight"] = (D,)
+            shapes[p + ln + ".bias"] = (D,)
+        for lin in ("key", "query", "value", "proj"):
+            shapes[p + f"attn.{lin}.weight"] = (D, D)
+            shapes[p + f"attn.{lin}.bias"] = (D,)
+        shapes[p + "mlp.0.weight"], shapes[p + "mlp.0.bias"] = (4 * D, D), (4 * D,)
+        shapes[p + "mlp.2.weight"], shapes[p + "mlp.2.bias"] = (D, 4 * D), (D,)
+    shapes["transformer.ln_f.weight"] = shapes["transformer.ln_f.bias"] = (D,)
+    shapes["transformer.head.weight"] = (V, D)
+    out = {}
+    for name, shape in shapes.items():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
+        is_ln = ".ln1." in name or ".ln2." in name or ".ln_f." in name
+        if is_ln and name.endswith("weight"):
+            out[name] = torch.ones(shape)
+        elif name.endswith("bias"):
+            out[name] = torch.zeros(shape)
+        else:
+            out[name] = 0.02 * torch.randn(shape, generator=g)
+    return out
 
 
 def synth_batch(cfg, B, seed):
@@ -136,65 +167,187 @@ def synth_batch(cfg, B, seed):
     return x, indices
 
 
-# ---- CPU oracle legs --------------------------------------------------------------------------------------------------
-def oracle_sampling_step(cfg, state):
-    from oracle import mebt_oracle as O
+def workload_config(workload, cfg, B, dropout, world):
+    """The `config` object of the JSON line — identical for the native and the reference arm."""
     N = int(np.prod(cfg["shape"]))
+    config = {"workload": workload, "tokens": N, "batch_per_gpu": B,
+              "weights": "random init, reference distribution (337 M parameters)",
+              "l2": "working set (0.67 GB bf16 weights + activations/logits) exceeds the 126 MB L2; no flush needed"}
+    if workload == "train16f":
+        config.update(t=TRAIN_T, NC=N // 2, NT=N // 2, dropout=dropout, optimizer="AdamW, fp32 master weights",
+                      note="embd/attn/resid dropout as in configs/stl/mebt_16f.yaml")
+    elif workload == "vq16f":
+        config = {"workload": "vq16f", "videos_per_gpu": B, "latent": [256, 4, 16, 16], "codebook": [16384, 256],
+                  "unit_note": "a token = one quantised latent vector (distance + argmin, then both gathers)"}
+    elif workload == "maskgit16f":
+        config.update(sampler=MASKGIT, schedule="cosine", masked_tokens_per_video=maskgit_masked_tokens(N, 128))
+    else:
+        config.update(sampler=DNR, masked_tokens_per_video=masked_tokens_per_video(N))
+    return config
+
+
+# ---- CPU legs: the oracle port, or the unmodified reference when its source tree is reachable -----------------------
+def find_reference():
+    for p in (os.environ.get("MEBT_REF"), str(REPO / "baseline" / "_ref"), "/root/reference"):
+        if p and (Path(p) / "mebt" / "transformer.py").exists():
+            return p
+    return None
+
+
+def import_reference(path):
+    """The reference needs pytorch_lightning / h5py / imageio / skvideo, absent from the image; nothing on the hot
+    path touches them, so they are stubbed (same stubs as tests/golden/make_golden.py)."""
+    import types
+    pl = types.ModuleType("pytorch_lightning")
+
+    class LightningModule(torch.nn.Module):
+        global_step = 0
+        current_epoch = 0
+
+        def save_hyperparameters(self, *a, **k):
+            pass
+
+        def log(self, *a, **k):
+            pass
+
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+    pl.LightningModule = LightningModule
+    pl.LightningDataModule = type("LightningDataModule", (), {})
+    pl.Trainer = type("Trainer", (), {})
+    cb = types.ModuleType("pytorch_lightning.callbacks")
+    cb.ModelCheckpoint = type("ModelCheckpoint", (), {})
+    cb.Callback = type("Callback", (), {})
+    pl.callbacks = cb
+    sys.modules["pytorch_lightning"] = pl
+    sys.modules["pytorch_lightning.callbacks"] = cb
+    for name in ("h5py", "imageio", "skvideo", "skvideo.io"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["skvideo"].io = sys.modules["skvideo.io"]
+    for k in [k for k in sys.modules if k == "mebt" or k.startswith("mebt.") or k == "utils"]:
+        del sys.modules[k]
+    sys.path[:] = [p for p in sys.path if Path(p).resolve() not in (REPO, REPO / "tests")]
+    sys.path.insert(0, path)
+    from mebt.transformer import Net2NetTransformer   # the reference's class
+    return Net2NetTransformer
+
+
+class AttrDict(dict):
+    """Stands in for OmegaConf nodes: attribute access, hasattr, `in`, .get."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _attr(d):
+    return AttrDict({k: _attr(v) for k, v in d.items()}) if isinstance(d, dict) else d
+
+
+def model_configs(cfg: dict, schedule="linear"):
+    """(transformer_config, first_stage_config, mask_config) of Net2NetTransformer for one of CONFIGS, the keys the
+    shipped yaml files set (configs/stl/mebt_16f.yaml), `vtokens: True` so that no VQGAN checkpoint is needed."""
+    params = _attr(dict(
+        unconditional=True, vocab_size=cfg["vocab_size"], first_stage_vocab_size=cfg["vocab_size"],
+        block_size=cfg["block_size"], n_layer=cfg["n_layer"], n_head=cfg["n_head"], n_embd=cfg["n_embd"], n_unmasked=0,
+        embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, sample_every_n_latent_frames=0, first_stage_key="video",
+        cond_stage_key="label", vtokens=True, vtokens_pos=False, vis_epoch=100, sos_emb=cfg["sos_emb"],
+        avg_loss=bool(cfg.get("avg_loss", 1.0)), mode=list(cfg["mode"]), class_cond_dim=None))
+    mask = _attr(dict(target="mebt.mask_sampler.MaskGen",
+                      params=dict(iid=False, schedule=schedule, max_token=cfg["block_size"], method="mlm",
+                                  shape=cfg["shape"], t_range=[0.0, 1.0], budget=cfg["block_size"])))
+    vq = _attr(dict(params=dict(ckpt_path="unused", ignore_keys=["loss"])))
+    return params, vq, mask
+
+
+def reference_model(cfg, state, pdrop, schedule="linear"):
+    Net = import_reference(find_reference())
+    params, vq, mask = model_configs(cfg, schedule)
+    params.embd_pdrop = params.resid_pdrop = params.attn_pdrop = pdrop
+    model = Net(params, vq, mask)
+    model.load_state_dict(state, strict=True)
+    return model
+
+
+def cpu_leg(workload, cfg, B, dropout, state, use_reference):
+    """-> (step, units per step, description, kind).  A bounded sample of the workload (a few seconds per step)."""
+    N = int(np.prod(cfg["shape"]))
+    if workload == "vq16f":
+        from oracle import mebt_oracle as O
+        torch.manual_seed(0)
+        E = torch.randn(16384, 256)
+        z = torch.randn(8, 256, 4, 16, 16, generator=torch.Generator().manual_seed(4))
+
+        def step():
+            with torch.no_grad():
+                out = O.codebook_quantise(z, E)
+                O.codebook_decode_gather(out["encodings"], E)
+        return step, 8 * 1024, "Codebook.forward + decode gather on 8 videos (fp32 torch-CPU oracle port)", "port"
+    if workload == "train16f":
+        x, indices = synth_batch(cfg, B, 1)
+        what = f"full training step (fwd + CE + autograd bwd + AdamW), B={B}, t={TRAIN_T}, dropout {dropout}"
+        if use_reference:
+            import torch.nn.functional as F
+            model = reference_model(cfg, state, dropout).train()
+            opt = torch.optim.AdamW(model.parameters(), lr=1.08e-5, betas=(0.9, 0.95), weight_decay=0.01)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                logits, target, nt_weight, seq_len = model(x, None, t=TRAIN_T, indices=indices)
+                loss = F.cross_entropy(logits.reshape(-1, logits.size(-1)), target.reshape(-1), reduction="sum")
+                (loss / (x.shape[0] * seq_len * (nt_weight / float(seq_len)))).backward()
+                opt.step()
+            return step, B * (N // 2), what + ", unmodified reference modules (fp32 torch CPU)", "reference"
+        from oracle import mebt_oracle as O
+        P = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+        opt = torch.optim.AdamW(list(P.values()), lr=1.08e-5, betas=(0.9, 0.95), weight_decay=0.01)
+        D, H, L = cfg["n_embd"], cfg["n_head"], cfg["sos_emb"]
+        keep = lambda *shape: (torch.rand(*shape) >= dropout).float() / (1.0 - dropout)
+
+        def masks(NC, NT):
+            """fresh nn.Dropout keep factors for every dropout call of one training-mode forward (gpt.py:136,140,154,239-241)"""
+            drop = {("stem", "lat"): keep(B, L, D), ("stem", "ctx"): keep(B, NC, D), ("stem", "tgt"): keep(B, NT, D)}
+            for i, mode in enumerate(O.stack_modes(cfg)):
+                nq = NT if mode == "latent_dec" else L
+                nk = {"latent_enc": NC, "latent_self": L, "latent_dec": L, "lt2l": L + NT}[mode]
+                drop[(i, "attn")], drop[(i, "proj")], drop[(i, "mlp")] = keep(B, H, nq, nk), keep(B, nq, D), keep(B, nq, D)
+            return drop
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            r = O.shared_step(P, cfg, x, indices, TRAIN_T, "linear", drop=masks(N // 2, N // 2) if dropout > 0 else None)
+            r["loss"].backward()
+            opt.step()
+        return step, B * (N // 2), what + ", fp32 torch-CPU oracle port", "port"
+    # sampling workloads: one forward + sample step of one video at NC = NT = N/2
     g = torch.Generator().manual_seed(1)
     x = torch.randint(0, cfg["vocab_size"], (1, N), generator=g)
     perm = torch.randperm(N, generator=g).view(1, N)
     ctx, tgt = perm[:, : N // 2], perm[:, N // 2:]
+    what = f"1 forward+sample step of one video (NC=NT={N // 2}, B=1; a video takes 24 such forwards)"
+    if use_reference:
+        model = reference_model(cfg, state, 0.0).eval()
+        from mebt.transformer import sample_from_logits
+
+        def step():
+            with torch.no_grad():
+                logits, _ = model.reconstruct_mask(x, ctx, tgt)
+                sample_from_logits(logits, temperature=1.0, top_k=None, top_p=None)
+        return step, N // 2, what + ", unmodified reference modules (fp32 torch CPU)", "reference"
+    from oracle import mebt_oracle as O
 
     def step():
         with torch.no_grad():
             logits = O.reconstruct_mask(state, cfg, x, ctx, tgt)
             O.sample_from_logits(logits, 1.0, None, None, torch.empty_like(logits).exponential_())
-    desc = f"1 of the 24 forward+sample steps of one video (NC=NT={N // 2}, B=1, fp32 torch-CPU oracle port)"
-    return step, N // 2, desc
-
-
-def oracle_vq_step(B):
-    from oracle import mebt_oracle as O
-    torch.manual_seed(0)
-    E = torch.randn(16384, 256)
-    z = torch.randn(B, 256, 4, 16, 16, generator=torch.Generator().manual_seed(4))
-
-    def step():
-        with torch.no_grad():
-            out = O.codebook_quantise(z, E)
-            O.codebook_decode_gather(out["encodings"], E)
-    return step, B * 1024, f"Codebook.forward + decode gather on {B} videos (fp32 torch-CPU oracle port)"
-
-
-def oracle_dropout_masks(cfg, B, NC, NT, p):
-    """Fresh nn.Dropout keep factors for every dropout call of one training-mode forward (gpt.py:136,140,154,239-241)."""
-    from oracle import mebt_oracle as O
-    D, H, L = cfg["n_embd"], cfg["n_head"], cfg["sos_emb"]
-    keep = lambda *shape: (torch.rand(*shape) >= p).float() / (1.0 - p)
-    drop = {("stem", "lat"): keep(B, L, D), ("stem", "ctx"): keep(B, NC, D), ("stem", "tgt"): keep(B, NT, D)}
-    for i, mode in enumerate(O.stack_modes(cfg)):
-        nq = NT if mode == "latent_dec" else L
-        nk = {"latent_enc": NC, "latent_self": L, "latent_dec": L, "lt2l": L + NT}[mode]
-        drop[(i, "attn")], drop[(i, "proj")], drop[(i, "mlp")] = keep(B, H, nq, nk), keep(B, nq, D), keep(B, nq, D)
-    return drop
-
-
-def oracle_train_step(cfg, state, B, pdrop=0.0):
-    from oracle import mebt_oracle as O
-    P = {k: v.clone().requires_grad_(True) for k, v in state.items()}
-    opt = torch.optim.AdamW(list(P.values()), lr=1.08e-5, betas=(0.9, 0.95), weight_decay=0.01)
-    x, indices = synth_batch(cfg, B, 1)
-    N = int(np.prod(cfg["shape"]))
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        drop = oracle_dropout_masks(cfg, B, N // 2, N // 2, pdrop) if pdrop > 0 else None
-        r = O.shared_step(P, cfg, x, indices, TRAIN_T, "linear", drop=drop)
-        r["loss"].backward()
-        opt.step()
-    desc = (f"full training step (fwd + CE + autograd bwd + AdamW), B={B}, t={TRAIN_T}, dropout {pdrop}, "
-            "fp32 torch-CPU oracle port")
-    return step, B * (N // 2), desc
+    return step, N // 2, what + ", fp32 torch-CPU oracle port", "port"
 
 
 def time_cpu(step, warm, reps):
@@ -208,88 +361,109 @@ def time_cpu(step, warm, reps):
     return float(np.median(ts))
 
 
-def run_reference(args, cfg):
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
+def cpu_baseline_record(workload, cfg, B, dropout, state):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    model = build_cpu_model(cfg)
-    state = {k: v.detach() for k, v in model.state_dict().items()}
-    if args.workload == "train16f":
-        step, tokens, desc = oracle_train_step(cfg, state, args.batch or 6, args.dropout)
-    elif args.workload == "vq16f":
-        step, tokens, desc = oracle_vq_step(8)
-    else:
-        step, tokens, desc = oracle_sampling_step(cfg, state)
+    step, units, desc, kind = cpu_leg(workload, cfg, B, dropout, state, use_reference=False)
+    dt = time_cpu(step, 1, 2)
+    return {"value": units / dt, "unit": "tokens/s", "cores": threads, "kind": kind,
+            "sample": desc + ", median of 2 after 1 warm-up"}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    workload = args.workload or "train16f"
+    cfg = CONFIGS[workload]
+    B = args.batch or DEFAULT_BATCH[workload]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    state = synth_weights(cfg)
+    use_ref = find_reference() is not None and workload != "vq16f" and not args.port
+    try:
+        step, units, desc, kind = cpu_leg(workload, cfg, B, args.dropout, state, use_ref)
+    except Exception as exc:  # noqa: BLE001  (an unimportable reference tree must not cost the line)
+        if not use_ref:
+            raise
+        sys.stderr.write(f"reference tree unusable ({type(exc).__name__}: {exc}); timing the oracle port\n")
+        sys.path.insert(0, str(REPO))
+        step, units, desc, kind = cpu_leg(workload, cfg, B, args.dropout, state, False)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    value = tokens / dt
+    value = units / dt
     print(json.dumps({
         "impl": "reference", "metric": "masked video tokens/sec", "value": value, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "tokens": int(np.prod(cfg["shape"]))},
-        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": "each step = " + desc},
+        "config": workload_config(workload, cfg, B, args.dropout, 1),
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": kind, "sample": "each step = " + desc},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
 # ---- native arm -------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="train16f", choices=sorted(CONFIGS))
-    ap.add_argument("--batch", type=int, default=0,
-                    help="per GPU; default 6 for train16f (configs/stl/mebt_16f.yaml), 16 videos for sampling")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dropout", type=float, default=0.1,
-                    help="train16f: embd/resid/attn dropout (configs/stl/mebt_16f.yaml uses 0.1)")
-    args = ap.parse_args()
-    cfg = CONFIGS[args.workload]
-    if args.impl == "reference":
-        run_reference(args, cfg)
-        return
-    training = args.workload == "train16f"
-    B = args.batch or {"train16f": 6, "maskgit16f": 32, "vq16f": 64}.get(args.workload, 32)
-    warmup = max(args.warmup, 3)
+def build_native_model(cfg, state, pdrop, dev):
+    from mebt_b200.transformer import Net2NetTransformer
+    params, vq, mask = model_configs(cfg, schedule="linear")
+    params.embd_pdrop = params.resid_pdrop = params.attn_pdrop = pdrop
+    model = Net2NetTransformer(params, vq, mask)
+    model.load_state_dict(state, strict=True)
+    return model.to(dev)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
 
-    from mebt_b200 import _lib
-    _lib.check(_lib.lib.mebt_device_check(), "mebt_device_check")
-    cpu_model = build_cpu_model(cfg, pdrop=args.dropout if args.workload == "train16f" else 0.0)   # same weights on every rank (seed 0)
-    state = {k: v.detach().clone() for k, v in cpu_model.state_dict().items()} if rank == 0 else None
-    model = cpu_model.to(dev)
+def make_step(workload, cfg, B, dropout, dev, rank, world):
+    """Builds the workload on `dev` and returns its two step closures (device-resident / end-to-end) and bookkeeping."""
+    B = B or DEFAULT_BATCH[workload]
     N = int(np.prod(cfg["shape"]))
+    w = SimpleNamespace(workload=workload, cfg=cfg, B=B, N=N, in_sync=None, extra={}, state=None, comm=None)
     random.seed(42)                                       # python RNG identical on every rank, as pl.seed_everything(42)
+    if workload == "vq16f":
+        # BASELINE.json configs[3]: codebook quantise + decode-side gather, 16x128x128 videos -> latents [256,4,16,16]
+        from mebt_b200.vqgan import VQGAN
+        torch.manual_seed(0)
+        vq = VQGAN(16384, 256).to(dev).eval()
+        z_host = torch.randn(B, 256, 4, 16, 16, generator=torch.Generator().manual_seed(4 + rank)).pin_memory()
+        enc_host = torch.empty(B, 4, 16, 16, dtype=torch.long).pin_memory()
+        z_dev = z_host.to(dev)
+        w.tokens_per_step = B * 1024
 
-    if training:
+        def step_device():
+            return vq.decode(vq.encode(z_dev))
+
+        def step_e2e():
+            enc = vq.encode(z_host.to(dev, non_blocking=True))
+            vq.decode(enc)
+            enc_host.copy_(enc, non_blocking=True)
+        w.device, w.e2e = step_device, step_e2e
+        w.h2d, w.d2h = int(z_host.numel() * 4), int(enc_host.numel() * 8)
+        return w
+    w.state = synth_weights(cfg)                          # same weights on every rank (seed 0)
+    model = build_native_model(cfg, w.state, dropout if workload == "train16f" else 0.0, dev)
+    w.model = model
+    if workload == "train16f":
         from mebt_b200.training import TrainState
         model.train()
-        ts = TrainState(model, n_buckets=8 if world > 1 else 4)   # finer buckets shorten the exposed tail of the last all-reduce
+        ts = TrainState(model, n_buckets=8 if world > 1 else 4)
         opt = ts.make_optimizer(lr=1.08e-5, weight_decay=0.01)
+        w.ts = ts
         x_cpu, idx_cpu = synth_batch(cfg, B, 100 + rank)  # each rank its own batch (DistributedSampler)
         x_host, idx_host = x_cpu.pin_memory(), idx_cpu.pin_memory()
         loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
         x_dev, idx_dev = x_host.to(dev), idx_host.to(dev)
-        tokens_per_step = B * (N // 2)
+        w.tokens_per_step = B * (N // 2)
 
         def step_device():
             return ts.train_step(opt, x_dev, idx_dev, t=TRAIN_T, world_size=world)
+
+        def step_e2e():
+            x = x_host.to(dev, non_blocking=True)
+            idx = idx_host.to(dev, non_blocking=True)
+            out = ts.train_step(opt, x, idx, t=TRAIN_T, world_size=world)
+            loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
 
         def replicas_in_sync():
             """Data-parallel invariant: after any number of steps every rank holds the same parameters (checked once,
@@ -303,39 +477,35 @@ def main():
                 return bool(torch.equal(lo, hi))
             except Exception as exc:  # noqa: BLE001  (a diagnostic must never cost the bench line)
                 return f"check failed: {type(exc).__name__}"
+        w.device, w.e2e = step_device, step_e2e
+        w.in_sync = replicas_in_sync if world > 1 else None
+        w.comm = getattr(ts, "comm_report", None)
+        w.h2d, w.d2h = int(x_host.numel() * 8 + idx_host.numel() * 8), 4
+        w.extra = dict(grad_exchange=getattr(ts, "exchange_desc", lambda ws: "none (1 GPU)")(world) if world > 1 else "none (1 GPU)",
+                       note="embd/attn/resid dropout as in configs/stl/mebt_16f.yaml; masks regenerated in backward")
+        return w
+    model.eval()
+    model.rng_mode, model.rng_seed = "philox", 1000 + rank
+    x_host = torch.zeros(B, *cfg["shape"], dtype=torch.long).pin_memory()
+    out_host = torch.empty(B, N, dtype=torch.long).pin_memory()
+    x_dev = x_host.to(dev)
+    torch.manual_seed(1234 + rank)                        # CPU generator: the randperm draws of the gibbs masks
+    w.h2d, w.d2h = int(x_host.numel() * 8), int(out_host.numel() * 8)
+    if workload == "maskgit16f":
+        # BASELINE.json configs[4]: the 24-layer model's maskgit loop (UCF recipe: 128 steps, cosine schedule,
+        # context temperature 6) with the 16384-way logit head + confidence re-masking at batch 32
+        model.mask_sampler.schedule = "cosine"
+        w.tokens_per_step = B * maskgit_masked_tokens(N, MASKGIT["n_steps"])
+
+        def step_device():
+            return model.sample(x_dev, None, **MASKGIT)[0]
 
         def step_e2e():
             x = x_host.to(dev, non_blocking=True)
-            idx = idx_host.to(dev, non_blocking=True)
-            out = ts.train_step(opt, x, idx, t=TRAIN_T, world_size=world)
-            loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
-        h2d, d2h = int(x_host.numel() * 8 + idx_host.numel() * 8), 4
-    elif args.workload == "vq16f":
-        # BASELINE.json configs[3]: codebook quantise + decode-side gather, 16x128x128 videos -> latents [256,4,16,16]
-        from mebt_b200.vqgan import VQGAN
-        torch.manual_seed(0)
-        vq = VQGAN(16384, 256).to(dev).eval()
-        z_host = torch.randn(B, 256, 4, 16, 16, generator=torch.Generator().manual_seed(4 + rank)).pin_memory()
-        enc_host = torch.empty(B, 4, 16, 16, dtype=torch.long).pin_memory()
-        z_dev = z_host.to(dev)
-        tokens_per_step = B * 1024
-
-        def step_device():
-            return vq.decode(vq.encode(z_dev))
-
-        def step_e2e():
-            enc = vq.encode(z_host.to(dev, non_blocking=True))
-            vq.decode(enc)
-            enc_host.copy_(enc, non_blocking=True)
-        h2d, d2h = int(z_host.numel() * 4), int(enc_host.numel() * 8)
+            out_host.copy_(model.sample(x, None, **MASKGIT)[0], non_blocking=True)
+        w.extra = dict(noise="in-kernel philox")
     else:
-        model.eval()
-        model.rng_mode, model.rng_seed = "philox", 1000 + rank
-        tokens_per_step = B * masked_tokens_per_video(N)
-        x_host = torch.zeros(B, *cfg["shape"], dtype=torch.long).pin_memory()
-        out_host = torch.empty(B, N, dtype=torch.long).pin_memory()
-        x_dev = x_host.to(dev)
-        torch.manual_seed(1234 + rank)                    # CPU generator: the randperm draws of the gibbs masks
+        w.tokens_per_step = B * masked_tokens_per_video(N)
 
         def step_device():
             return model.draft_and_revise(x_dev, None, **DNR)
@@ -343,19 +513,29 @@ def main():
         def step_e2e():
             x = x_host.to(dev, non_blocking=True)
             out_host.copy_(model.draft_and_revise(x, None, **DNR), non_blocking=True)
-        h2d, d2h = int(x_host.numel() * 8), int(out_host.numel() * 8)
-        if args.workload == "maskgit16f":
-            # BASELINE.json configs[4]: the 24-layer model's maskgit loop (UCF recipe: 128 steps, cosine schedule,
-            # context temperature 6) with the 16384-way logit head + confidence re-masking at batch 32
-            model.mask_sampler.schedule = "cosine"
-            tokens_per_step = B * maskgit_masked_tokens(N, MASKGIT["n_steps"])
+        w.extra = dict(noise="in-kernel philox (inverse CDF)", logits=getattr(model, "sampler_logits_desc", "fp32 materialised"))
+    w.device, w.e2e = step_device, step_e2e
+    return w
 
-            def step_device():                                                # noqa: F811
-                return model.sample(x_dev, None, **MASKGIT)[0]
 
-            def step_e2e():                                                   # noqa: F811
-                x = x_host.to(dev, non_blocking=True)
-                out_host.copy_(model.sample(x, None, **MASKGIT)[0], non_blocking=True)
+def kernel_traffic(workload):
+    """DRAM read+write bytes per launch of the workload's dominant kernel family, from the committed ncu pass of the
+    SAME bench command (profiles/r02_kernel_traffic.json, written by tools/summarize_launches.py --traffic); None
+    when this workload has no capture."""
+    tr = REPO / "profiles" / "r02_kernel_traffic.json"
+    if not tr.exists():
+        return None, None
+    t = json.loads(tr.read_text()).get(workload)
+    if not t:
+        return None, None
+    return t.get("dram_bytes_per_launch"), t.get("note")
+
+
+def measure(w, steps, warmup, world, rank, dev, with_cpu_baseline):
+    """warm-up, the device-timed region, the end-to-end region, the per-family profile; -> the record (rank 0) or None"""
+    from mebt_b200 import _lib
+    if world > 1:
+        import torch.distributed as dist
 
     def barrier():
         if world > 1:
@@ -370,102 +550,143 @@ def main():
         return float(t)
 
     for _ in range(warmup):
-        step_device()
+        w.device()
     barrier()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(dev.index or 0)
     if rank == 0:
         clocks.start()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        step_device()
+    for _ in range(steps):
+        w.device()
     e1.record()
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    launches = (_lib.launch_count() - launches0) // args.steps
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    launches = (_lib.launch_count() - launches0) // steps
     clock_info = clocks.stop() if rank == 0 else None
 
-    step_e2e()
+    w.e2e()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    for _ in range(steps):
+        w.e2e()
         torch.cuda.synchronize()
     barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
-    in_sync = replicas_in_sync() if (training and world > 1) else None
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / steps
+    in_sync = w.in_sync() if w.in_sync is not None else None
+    comm = w.comm() if w.comm is not None and world > 1 else None
 
     # per-kernel-family timing of one more step (events on the launch stream, recorded by the library)
     _lib.profile_enable(True)
-    step_device()
+    w.device()
     prof = _lib.profile_report()
     _lib.profile_enable(False)
-
-    if rank == 0:
-        pk = peaks()
-        gemm = prof["gemm"]
-        total_ms = sum(f["ms"] for f in prof.values())
-        achieved = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    if rank != 0:
+        return None
+    pk = peaks()
+    fam = "vq" if w.workload == "vq16f" else "gemm"
+    dom = prof[fam]
+    total_ms = sum(f["ms"] for f in prof.values())
+    achieved = dom["work"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
+    if fam == "gemm":
         roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / pk["tf_sustained"], "traffic": None, "kernel": "gemm_bf16_kernel (tcgen05)",
-                    "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
-                    "share_of_step": gemm["ms"] / total_ms if total_ms else None,
-                    "families_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]},
-                    "families_launches": {k: v["launches"] for k, v in prof.items() if v["launches"]}}
-        tr = REPO / "profiles" / "r01_kernel_traffic.json"        # ncu --set full capture of one representative launch
-        if tr.exists():
-            t = json.loads(tr.read_text()).get("gemm_bf16_kernel")
-            if t:
-                roofline["traffic"] = t["dram_bytes"]
-                roofline["traffic_note"] = (f"dram read+write of one launch at {t['shape']} (ncu, profiles/r01_ncu_kernels.md); "
-                                            f"algorithmic bytes of that launch {t['algorithmic_bytes']}")
-        for fam in ("sample", "ce", "layernorm"):
-            f = prof[fam]
-            if f["ms"] > 0:
-                gbs = f["work"] / (f["ms"] * 1e-3) / 1e9
-                roofline[f"{fam}_kernel_hbm"] = {"achieved_gbs": gbs, "peak_gbs": pk["hbm"], "frac": gbs / pk["hbm"]}
-        cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            torch.set_num_threads(threads)
-            if training:
-                step, toks, desc = oracle_train_step(cfg, state, B, args.dropout)
-                dt = time_cpu(step, 1, 2)
-            elif args.workload == "vq16f":
-                step, toks, desc = oracle_vq_step(8)
-                dt = time_cpu(step, 1, 2)
-            else:
-                step, toks, desc = oracle_sampling_step(cfg, state)
-                dt = time_cpu(step, 1, 2)
-            cpu_baseline = {"value": toks / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
-                            "sample": desc + ", median of 2 after 1 warm-up"}
-        config = {"workload": args.workload, "tokens": N, "batch_per_gpu": B,
-                  "weights": "random init, reference distribution (337 M parameters)",
-                  "l2": "working set (0.67 GB bf16 weights + activations/logits) exceeds the 126 MB L2; no flush needed"}
-        if training:
-            config.update(t=TRAIN_T, NC=N // 2, NT=N // 2, dropout=args.dropout, optimizer="AdamW fused fp32 master weights",
-                          note="embd/attn/resid dropout as in configs/stl/mebt_16f.yaml; masks regenerated in backward",
-                          grad_allreduce="fp32, 8 block buckets + head + embeddings, overlapped with backward" if world > 1 else "none (1 GPU)")
-            if in_sync is not None:
-                config["replicas_in_sync"] = in_sync
-        elif args.workload == "vq16f":
-            config = {"workload": "vq16f", "videos_per_gpu": B, "latent": [256, 4, 16, 16], "codebook": [16384, 256],
-                      "unit_note": "a token = one quantised latent vector (fused fp32 distance+argmin, then both gathers)"}
-        elif args.workload == "maskgit16f":
-            config.update(sampler=MASKGIT, schedule="cosine", masked_tokens_per_video=maskgit_masked_tokens(N, 128),
-                          noise="in-kernel philox", generated_tokens_per_s=world * B * N / (ms * 1e-3))
-        else:
-            config.update(sampler=DNR, masked_tokens_per_video=masked_tokens_per_video(N), noise="in-kernel philox (inverse CDF)",
-                          logits="fp32 materialised", generated_tokens_per_s=world * B * N / (ms * 1e-3))
-        print(json.dumps({
-            "metric": "masked video tokens/sec", "value": world * tokens_per_step / (ms * 1e-3), "unit": "tokens/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
-            "e2e": {"value": world * tokens_per_step / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info}))
+                    "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step)"}
+    else:
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["tf_sustained"], "traffic": None, "kernel": "vq_argmin (fused distance + argmin)",
+                    "peak_source": f"{pk['src']} bf16 sustained; the fused form is compute-bound (SURVEY.md §8(d))"}
+    roofline["share_of_step"] = dom["ms"] / total_ms if total_ms else None
+    roofline["families_ms"] = {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}
+    roofline["families_launches"] = {k: v["launches"] for k, v in prof.items() if v["launches"]}
+    traffic, note = kernel_traffic(w.workload)
+    if traffic is not None:
+        roofline["traffic"] = traffic
+        roofline["traffic_note"] = note
+    for f in ("sample", "ce", "layernorm"):
+        r = prof[f]
+        if r["ms"] > 0:
+            gbs = r["work"] / (r["ms"] * 1e-3) / 1e9
+            roofline[f"{f}_kernel_hbm"] = {"achieved_gbs": gbs, "peak_gbs": pk["hbm"], "frac": gbs / pk["hbm"]}
+    config = workload_config(w.workload, w.cfg, w.B, getattr(w, "dropout", 0.0), world)
+    detail = dict(w.extra)                 # native-arm facts; `config` stays identical to the reference arm's
+    if w.workload in ("sample128f", "sample16f", "maskgit16f"):
+        detail["generated_tokens_per_s"] = world * w.B * w.N / (ms * 1e-3)
+    if in_sync is not None:
+        detail["replicas_in_sync"] = in_sync
+    if comm is not None:
+        detail["comm"] = comm
+    rec = {"metric": "masked video tokens/sec", "value": world * w.tokens_per_step / (ms * 1e-3), "unit": "tokens/s",
+           "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+           "e2e": {"value": world * w.tokens_per_step / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": w.h2d,
+                   "d2h_bytes_per_step": w.d2h},
+           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None, "clocks": clock_info,
+           "detail": detail}
+    if with_cpu_baseline and world == 1:
+        rec["cpu_baseline"] = cpu_baseline_record(w.workload, w.cfg, w.B, getattr(w, "dropout", 0.0), w.state)
+    return rec
+
+
+def release(w):
+    for k in list(vars(w)):
+        setattr(w, k, None)
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(CONFIGS),
+                    help="default: train16f headline + workloads.sample128f in the same line")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="per GPU; default 6 for train16f (configs/stl/mebt_16f.yaml), 32 videos for sampling")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="default line without workloads.sample128f")
+    ap.add_argument("--port", action="store_true", help="--impl reference: time the oracle port even if a reference tree exists")
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="train16f: embd/resid/attn dropout (configs/stl/mebt_16f.yaml uses 0.1)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    primary = args.workload or "train16f"
+    secondary = [] if (args.workload or args.no_secondary) else ["sample128f"]
+    warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from mebt_b200 import _lib
+    _lib.check(_lib.lib.mebt_device_check(), "mebt_device_check")
+
+    w = make_step(primary, CONFIGS[primary], args.batch, args.dropout, dev, rank, world)
+    w.dropout = args.dropout if primary == "train16f" else 0.0
+    rec = measure(w, args.steps, warmup, world, rank, dev, not args.no_cpu_baseline)
+    release(w)
+    for name in secondary:
+        # the 128-frame half of the metric: fewer videos and steps than its stand-alone run so that the default
+        # invocation stays within minutes; same code path, same per-video work
+        w2 = make_step(name, CONFIGS[name], SECONDARY_BATCH[name], 0.0, dev, rank, world)
+        sub = measure(w2, max(1, min(args.steps, 2)), 3, world, rank, dev, not args.no_cpu_baseline)
+        release(w2)
+        if rec is not None:
+            rec.setdefault("workloads", {})[name] = sub
+    if rank == 0:
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
 

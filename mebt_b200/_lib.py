@@ -176,6 +176,20 @@ def call(name: str, *args) -> None:
     check(getattr(_lib, name)(*args), name)
 
 
+# Parameters are also written through raw device pointers (FlatAdamW's kernel updates the fp32 masters in place), which
+# torch's per-tensor version counters do not see.  Every such writer bumps this epoch; the caches of derived operands
+# (bf16 casts, folded weights) key on it next to (data_ptr, _version).
+_WRITE_EPOCH = [0]
+
+
+def bump_write_epoch() -> None:
+    _WRITE_EPOCH[0] += 1
+
+
+def write_epoch() -> int:
+    return _WRITE_EPOCH[0]
+
+
 FAMILIES = ("gemm", "attention", "layernorm", "embed", "sample", "ce", "remask", "scatter", "vq", "other")
 
 

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import _lib, ops
 from ..stack import (LayerWeights, PreciseWeightPack, WeightPack, attention_core, block_forward, stack_forward,
                      stack_forward_f32)
 
@@ -41,7 +41,9 @@ def _as_rows(t: torch.Tensor) -> torch.Tensor:
 
 
 def _versions(module: nn.Module):
-    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+    """Cache key of the operands derived from a module's parameters: storage + torch's version counters + the epoch of
+    raw-pointer writers (FlatAdamW updates the masters in place without touching `_version`)."""
+    return (_lib.write_epoch(),) + tuple((p.data_ptr(), p._version) for p in module.parameters())
 
 
 def _check_no_dropout(module: nn.Module, *ps):

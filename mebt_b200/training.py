@@ -91,6 +91,10 @@ class TrainState:
         self.refresh_operands()
         self._saved = None
         self._bwd_ws = None
+        self._ctx = None
+        self._step_id = 0                 # stamps the saved activations: one forward owns them until its backward ran
+        self._grads_dirty = False         # the flat gradient buffer holds a gradient no optimizer step / zero_grad consumed
+        self._grad_torch_version = self.flat_grad._version
         self.comm_stream = torch.cuda.Stream(device=self.device)
         model.__dict__["_train_state"] = self          # found again by Net2NetTransformer.training_step
 
@@ -172,14 +176,28 @@ class TrainState:
              self._view(self.flat_bf16, "transformer.head.weight").data_ptr(), B, self.L, NC, NT, self.D, self.H, self.V,
              lat.data_ptr(), ctx.data_ptr(), tgt.data_ptr(), logits.data_ptr(), ops._DT[logits_dtype], saved.data_ptr(),
              saved.numel(), ctypes.byref(drop) if drop is not None else None, st)
+        self._step_id += 1
         self._ctx = (B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt, drop, embd_p, seed)
         return logits
+
+    def grads_pending(self) -> bool:
+        """True when the flat gradient buffer still holds a gradient that no `zero_grad` / optimizer step consumed, i.e.
+        the next backward must ADD to it (torch autograd semantics, the reference's `accumulate_grad_batches`,
+        train_transformer.py:47-50).  zero_grad(set_to_none=True) shows as dropped `.grad` views, an in-place zero as
+        a bump of the buffer's torch version counter; FlatAdamW clears the flag itself."""
+        if not self._grads_dirty:
+            return False
+        if any(p.grad is None for p, _ in self._grad_views) or self.flat_grad._version != self._grad_torch_version:
+            self._grads_dirty = False
+        return self._grads_dirty
 
     def backward(self, dlogits, accumulate=False, world_size=1, optimizer=None):
         """Stack + stem backward into the flat gradient buffer; with world_size > 1 each finished chunk of blocks is
         all-reduced (averaged) on a side stream while the next chunk runs.  With a `FlatAdamW` passed as `optimizer` the
         parameter update of a finished chunk is issued on that side stream too, right behind its all-reduce: blocks
         that backward has left are never read again in this step, so their AdamW overlaps the rest of backward."""
+        if self._ctx is None:
+            raise MebtError("backward: no forward is pending (each forward's activations serve exactly one backward)")
         B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt, drop, embd_p, seed = self._ctx
         if dlogits.dtype != torch.bfloat16 or not dlogits.is_contiguous():
             raise MebtError("dlogits must be contiguous bf16 [B*NT, V]")
@@ -228,6 +246,9 @@ class TrainState:
         if world_size > 1 or optimizer is not None:
             cur.wait_stream(self.comm_stream)
         self.relink_grads()
+        self._ctx = None
+        self._grads_dirty = True
+        self._grad_torch_version = self.flat_grad._version
         return works
 
     def _update_async(self, optimizer, lo, hi, producer_stream):
@@ -254,12 +275,7 @@ class TrainState:
         m = self.model
         B = x_indices.shape[0]
         x_indices = x_indices.reshape(B, -1)
-        import random
-        if t is None:
-            t = torch.tensor(random.random())
-            t = m.range[0] + t * (m.range[1] - m.range[0])
-        else:
-            t = torch.tensor(t)
+        t = m._draw_t(t, training=True)                        # uniform over t_range, or the annealed Beta(a, b) of beta configs
         prior_t = m.t_prior(m.t_lengths, m.global_step)
         ctx_idx, tgt_idx, seq_len = m.mask_sampler.divide_indices(indices, t, m.t_lengths, prior_t)
         z_targets = torch.gather(x_indices, 1, tgt_idx)
@@ -296,6 +312,7 @@ class TrainState:
             return self.loss_and_backward(x_indices, indices, t, world_size, optimizer=optimizer)
         out = self.loss_and_backward(x_indices, indices, t, world_size)
         optimizer.step()
+        self._grads_dirty = False                               # train_step owns the whole step: the gradient is consumed
         if not isinstance(optimizer, FlatAdamW):
             self.refresh_operands()
         return out
@@ -332,6 +349,7 @@ class FlatAdamW:
 
     def zero_grad(self, set_to_none=False):
         self.ts.flat_grad.zero_()
+        self.ts._grads_dirty = False
 
     def begin_step(self):
         self.steps += 1
@@ -347,6 +365,8 @@ class FlatAdamW:
              self.v.data_ptr() + 4 * lo, ts.flat_bf16.data_ptr() + 2 * lo, self.flags.data_ptr() + (lo >> self.shift),
              self.shift, hi - lo, lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.steps,
              torch.cuda.current_stream().cuda_stream)
+        _lib.bump_write_epoch()                # the masters changed behind torch's version counters: derived operands are stale
+        ts._grads_dirty = False
 
     def step(self):
         self.begin_step()
@@ -367,12 +387,13 @@ class TrainStepFunction(torch.autograd.Function):
     """Autograd bridge for the drop-in `training_step`: forward runs stem + stack + fused masked CE on the CUDA engine
     and returns the loss; `loss.backward()` runs the engine's backward, which writes every parameter gradient straight
     into `p.grad` (views of the flat gradient buffer) and, under torch.distributed, averages them over ranks the way
-    the reference's DDP does (train_transformer.py:39-41).  Gradients are overwritten, not accumulated, per call."""
+    the reference's DDP does (train_transformer.py:39-41).  Like autograd, a backward ADDS to gradients that no
+    `zero_grad()` / optimizer step has consumed since the previous backward (gradient accumulation)."""
 
     @staticmethod
     def forward(ctx, anchor, ts, x_indices, indices, world_size):
         out, dlogits = ts.loss_and_backward(x_indices, indices, world_size=world_size, defer_backward=True)
-        ctx.ts, ctx.dlogits, ctx.world_size = ts, dlogits, world_size
+        ctx.ts, ctx.dlogits, ctx.world_size, ctx.step_id = ts, dlogits, world_size, ts._step_id
         ctx.mark_non_differentiable(out["acc1"], out["acc5"])
         return out["loss"].reshape(()), out["acc1"], out["acc5"]
 
@@ -381,7 +402,11 @@ class TrainStepFunction(torch.autograd.Function):
         dlogits = ctx.dlogits
         if dlogits is None:
             raise MebtError("training_step: backward through the same step twice")
+        ts = ctx.ts
+        if ts._step_id != ctx.step_id or ts._ctx is None:
+            raise MebtError("training_step: another forward ran before this loss's backward; the saved activations belong "
+                            "to the later step (call loss.backward() before the next training_step)")
         dlogits.mul_(g_loss.to(dlogits.dtype))                   # 1.0 unless the caller scaled the loss
-        ctx.ts.backward(dlogits, world_size=ctx.world_size)
+        ts.backward(dlogits, accumulate=ts.grads_pending(), world_size=ctx.world_size)
         ctx.dlogits = None
         return None, None, None, None, None

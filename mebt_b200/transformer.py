@@ -99,6 +99,21 @@ def _instantiate(config):
     return get_obj_from_str(target)(**config.get("params", dict()))
 
 
+def _refuse_ddp_wrapper(module):
+    """The CUDA backward writes parameter gradients straight into `p.grad` and averages them over ranks itself, so no
+    autograd hook of a DistributedDataParallel wrapper ever fires: a wrapped module would stop at DDP's 'Expected to
+    have finished reduction in the prior iteration' on the second step (or reduce twice with find_unused_parameters).
+    The reference's Lightning `DDPStrategy` (train_transformer.py:41) wraps the module - detect it and say what to
+    use instead: one process per GPU with torch.distributed initialised and a non-wrapping strategy."""
+    trainer = getattr(module, "_trainer", None) or module.__dict__.get("trainer")
+    wrapped = getattr(getattr(trainer, "strategy", None), "model", None) if trainer is not None else None
+    if isinstance(wrapped, torch.nn.parallel.DistributedDataParallel):
+        raise MebtError(
+            "mebt_b200.training_step: the module is wrapped in DistributedDataParallel (Lightning DDPStrategy). The CUDA "
+            "backward all-reduces its own gradient buckets over torch.distributed; run one process per GPU with "
+            "init_process_group('nccl') and a single-device strategy (see INTEGRATION.md, 'Data-parallel training')")
+
+
 class Net2NetTransformer(_Base):
     def __init__(self, transformer_config, first_stage_config, mask_config, ckpt_path=None, ignore_keys=[],
                  first_stage_key="video", cond_stage_key="label", pkeep=1.0, sos_token=0):
@@ -223,26 +238,30 @@ class Net2NetTransformer(_Base):
         return ops.sample_logits(logits_rows, temperature, top_k, top_p, noise=noise, seed=seed, offset=offset,
                                  return_probs=return_probs)
 
+    def _draw_t(self, t, training):
+        """The masking time of one step (transformer.py:225-242): given, or uniform over `t_range`, or - for configs
+        with `beta_params` - Beta(a, b) annealed towards Beta(1, 1) over `beta_iter` steps."""
+        if t is not None:
+            return torch.tensor(t)
+        if training and self.beta:
+            if self.global_step > self.beta_iter:
+                a, b = 1., 1.
+            else:
+                a0, b0 = self.beta_params
+                a = a0 - (a0 - 1.) * (self.global_step / self.beta_iter)
+                b = b0 - (b0 - 1.) * (self.global_step / self.beta_iter)
+            return torch.distributions.beta.Beta(a, b).sample()
+        t = torch.tensor(random.random())                          # python RNG: identical on every DDP rank
+        if training:
+            t = self.range[0] + t * (self.range[1] - self.range[0])
+        return t
+
     def forward(self, x, c, t=None, indices=None, vid_t=None, debug=False):
         """One masked-prediction step -> (logits [B,NT,V] fp32, z_targets, NT_weight, seq_len) (transformer.py:216-286)."""
         assert indices is not None
         _, x_indices = self.encode_to_z(x)
         B = x_indices.shape[0]
-        if t is None:
-            if (self.training or debug) and self.beta:
-                if self.global_step > self.beta_iter:
-                    a, b = 1., 1.
-                else:
-                    a0, b0 = self.beta_params
-                    a = a0 - (a0 - 1.) * (self.global_step / self.beta_iter)
-                    b = b0 - (b0 - 1.) * (self.global_step / self.beta_iter)
-                t = torch.distributions.beta.Beta(a, b).sample()
-            else:
-                t = torch.tensor(random.random())                  # python RNG: identical on every DDP rank
-                if self.training or debug:
-                    t = self.range[0] + t * (self.range[1] - self.range[0])
-        else:
-            t = torch.tensor(t)
+        t = self._draw_t(t, self.training or debug)
         if vid_t is None:
             prior_t = self.t_prior(self.t_lengths, self.global_step)
             vid_t = self.t_lengths
@@ -491,6 +510,7 @@ class Net2NetTransformer(_Base):
             indices = self.get_input("indices", batch)
             import torch.distributed as dist
             world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            _refuse_ddp_wrapper(self)
             loss, acc1, acc5 = TrainStepFunction.apply(self.mask_emb, ts, x.reshape(x.shape[0], -1), indices, world)
         else:
             acc1, acc5, loss, ratio = self.shared_step(batch, batch_idx)

@@ -146,6 +146,7 @@ def test_training_step_autograd_bridge_with_a_torch_optimizer():
     out = ts.loss_and_backward(x, indices)
     assert float(out["loss"]) == float(loss) and torch.equal(g[:lo], ts.flat_grad[:lo])
     random.seed(1)
+    model.zero_grad()                                           # consume the pending gradient: the next backward assigns
     (0.5 * model.training_step(batch, 0)).backward()            # a scaled loss scales the gradients
     assert torch.allclose(ts.flat_grad[:lo], 0.5 * g[:lo], rtol=1e-3, atol=1e-9)
     opt = torch.optim.AdamW(model.parameters(), lr=3e-3, betas=(0.9, 0.95), weight_decay=0.0)
@@ -184,3 +185,72 @@ def test_overlapped_optimizer_update_matches_sequential():
     lo = ts.emb_slice[0]
     assert torch.equal(got[:lo], ts.flat[:lo])
     assert torch.allclose(got[lo:], ts.flat[lo:], rtol=1e-5, atol=1e-7)        # embedding grads: fp32 atomics
+
+
+def test_eval_sees_flat_adamw_updates():
+    """ADVICE r1 (high): FlatAdamW writes the masters through raw pointers, which torch's version counters do not see;
+    the inference operand caches (GPT.weight_pack, Block.layer_weights, CrossAttention._weights) must still follow."""
+    from mebt_b200.stack import WeightPack
+    z, cfg, P, model, ts = _state("micro")
+    x, indices = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["indices"]).cuda()
+    ctx, tgt = indices[:, :100], indices[:, 100:]
+    model.eval()
+    before, _ = model.reconstruct_mask(x, ctx, tgt)               # builds the packs
+    lat = model.sos_emb.expand(x.shape[0], -1, -1)
+    blk = model.transformer.blocks[1]
+    blk_before = blk(lat, lat[:, :0], lat[:, :0])[0].clone()
+    model.train()
+    opt = ts.make_optimizer(lr=3e-3, weight_decay=0.0)
+    for _ in range(4):
+        ts.train_step(opt, x, indices, t=0.5)
+    model.eval()
+    after, _ = model.reconstruct_mask(x, ctx, tgt)
+    assert float((after - before).abs().max()) > 1e-2            # the update is visible ...
+    gpt = model.transformer
+    params = {"transformer." + n: p for n, p in gpt.named_parameters()}
+    fresh = WeightPack(params, [b.mode for b in gpt.blocks], gpt.config.n_head)
+    gpt._pack = (gpt._pack[0], fresh)
+    again, _ = model.reconstruct_mask(x, ctx, tgt)
+    assert torch.equal(after, again)                              # ... and equals a pack built from scratch
+    assert float((blk(lat, lat[:, :0], lat[:, :0])[0] - blk_before).abs().max()) > 1e-3   # module path too
+
+
+def test_training_step_accumulates_like_autograd():
+    """two loss.backward() calls without zero_grad add up (accumulate_grad_batches,
+    train_transformer.py:47-50); zero_grad in either form makes the next backward assign."""
+    import random
+    z, cfg, P, model, ts = _state("micro")
+    x, indices = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["indices"]).cuda()
+    batch = dict(video=x, label=x, indices=indices)
+    batch2 = dict(video=x.flip(0), label=x, indices=indices.flip(0))
+    lo = ts.emb_slice[0]
+    grads = []
+    for b, seed in ((batch, 3), (batch2, 4)):
+        model.zero_grad()
+        random.seed(seed)
+        model.training_step(b, 0).backward()
+        grads.append(ts.flat_grad.clone())
+    model.zero_grad()
+    for b, seed in ((batch, 3), (batch2, 4)):
+        random.seed(seed)
+        model.training_step(b, 0).backward()
+    want = grads[0] + grads[1]
+    err = ((ts.flat_grad[:lo] - want[:lo]).norm() / want[:lo].norm()).item()
+    assert err < 2e-3, err                                        # bf16 attention / LN paths re-round; fp32 accumulation
+    for p in model.parameters():                                  # zero_grad(set_to_none=False): in-place zero
+        p.grad.zero_()
+    random.seed(3)
+    model.training_step(batch, 0).backward()
+    assert torch.allclose(ts.flat_grad[:lo], grads[0][:lo], rtol=1e-4, atol=1e-8)
+
+
+def test_training_step_refuses_a_stale_backward():
+    from mebt_b200._lib import MebtError
+    z, cfg, P, model, ts = _state("micro")
+    x, indices = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["indices"]).cuda()
+    batch = dict(video=x, label=x, indices=indices)
+    first = model.training_step(batch, 0)
+    second = model.training_step(batch, 1)
+    with pytest.raises(MebtError, match="another forward"):
+        first.backward()
+    second.backward()

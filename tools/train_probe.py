@@ -14,7 +14,7 @@ from mebt_b200.training import TrainState  # noqa: E402
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 6
     cfg = bench.CONFIGS["train16f"]
-    model = bench.build_cpu_model(cfg).cuda().train()
+    model = bench.build_native_model(cfg, bench.synth_weights(cfg), float(sys.argv[2]) if len(sys.argv) > 2 else 0.1, torch.device("cuda", 0)).train()
     ts = TrainState(model)
     opt = ts.make_optimizer()
     x, idx = bench.synth_batch(cfg, B, 1)
