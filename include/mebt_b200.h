@@ -80,6 +80,19 @@ int mebt_gemm_bf16_aux(const void* A, int lda, int a_mn_major, const void* B, in
                        int M, int N, int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux,
                        int flags, void* stream);
 
+/* Up to 6 independent weight-gradient problems  dW[n_out, k_in] (+)= dY[rows, n_out]^T X[rows, k_in]  (bf16 operands,
+ * fp32 dW) in ONE persistent launch: the nn.Linear weight gradients autograd computes for one Block
+ * (mebt/modules/gpt.py:126-128,140,150-155 in the backward of :159-195).  Each alone is a fraction of a wave of tiles at
+ * the training shapes; together they fill the machine.  The outputs must not overlap (the problems run concurrently).
+ * Shapes the grouped tile does not fit (k_in % 256 != 0) are run as separate mebt_gemm_bf16 launches. */
+typedef struct mebt_wgrad_desc {
+  const void* dY; int ld_dy;      /* bf16 [rows, n_out], row stride in elements */
+  const void* X;  int ldx;        /* bf16 [rows, k_in] */
+  float* dW;      int ldw;        /* fp32 [n_out, k_in] */
+  int n_out, k_in, rows;
+  int accumulate;                 /* dW += result instead of dW = result */
+} mebt_wgrad_desc_t;
+int mebt_gemm_grouped_wgrad(const mebt_wgrad_desc_t* problems, int n_problems, void* stream);
 
 /* ---- dtypes --------------------------------------------------------------------------------- */
 enum { MEBT_DTYPE_BF16 = 0, MEBT_DTYPE_FP32 = 1 };
@@ -239,6 +252,12 @@ int mebt_latent_attention_fwd_f32(const float* Q, int ldq, int q_col0, const flo
 int mebt_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, const unsigned char* decay_blocks,
                     int block_shift, long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     void* stream);
+/* The same update as a background kernel of at most `max_ctas` CTAs (0 = the full grid): it trickles through HBM at a
+ * fraction of the bandwidth, for a caller that overlaps the update of finished parameter ranges with the rest of the
+ * backward pass on another stream (the latency-bound kernels there keep their SMs and their L2). */
+int mebt_adamw_flat_bg(float* p, const float* g, float* m, float* v, void* p_bf16, const unsigned char* decay_blocks,
+                       int block_shift, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       int step, int max_ctas, void* stream);
 
 /* ---- dropout (training mode; nn.Dropout at mebt/modules/gpt.py:112-113,140,150-155,216,239-242) ------------- */
 /* Keep decisions are counter-based: a pure function of (seed, site, row, column), regenerated by the backward

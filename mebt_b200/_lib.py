@@ -113,6 +113,7 @@ _SIGNATURES["mebt_latent_attention_fwd_f32"] = [c_void_p, c_int, c_int, c_void_p
                                                 c_void_p]
 _SIGNATURES["mebt_adamw_flat"] = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_float,
                                   c_float, c_float, c_float, c_float, c_int, c_void_p]
+_SIGNATURES["mebt_adamw_flat_bg"] = _SIGNATURES["mebt_adamw_flat"][:-1] + [c_int, c_void_p]
 _SIGNATURES["mebt_dropout_rows"] = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_uint64,
                                     c_uint64, c_void_p]
 _SIGNATURES["mebt_latent_attention_fwd_dropout"] = _SIGNATURES["mebt_latent_attention_fwd"][:-1] + [c_float, c_uint64,
@@ -120,6 +121,15 @@ _SIGNATURES["mebt_latent_attention_fwd_dropout"] = _SIGNATURES["mebt_latent_atte
 _SIGNATURES["mebt_latent_attention_bwd_dropout"] = _SIGNATURES["mebt_latent_attention_bwd"][:-3] + [
     c_float, c_uint64, c_void_p, c_size_t, c_void_p]
 _SIGNATURES["mebt_attention_dropout_mask"] = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_void_p]
+
+
+class WgradDesc(ctypes.Structure):
+    """mebt_wgrad_desc_t"""
+    _fields_ = [("dY", c_void_p), ("ld_dy", c_int), ("X", c_void_p), ("ldx", c_int), ("dW", c_void_p), ("ldw", c_int),
+                ("n_out", c_int), ("k_in", c_int), ("rows", c_int), ("accumulate", c_int)]
+
+
+_SIGNATURES["mebt_gemm_grouped_wgrad"] = [ctypes.POINTER(WgradDesc), c_int, c_void_p]
 
 
 class EncHoistStruct(ctypes.Structure):

@@ -5,13 +5,16 @@
 //   dV = P^T dO          dP = dO V^T          dS = P .* (dP - delta) * scale,  delta = rowsum(dO .* O)
 //   dQ = dS K            dK = dS^T Q
 //
-// Two kernels, both tcgen05/TMEM/TMA like the forward, no atomics (bitwise reproducible):
-//   attn_bwd_dkv_kernel : one CTA per (128-key tile, head, batch, source); loops over query tiles and keeps the
-//                         dV / dK accumulators in TMEM.  P^T and dS^T are never transposed in memory: the P / dS
-//                         tiles written to shared memory as [q][k] are consumed as MN-major A operands.
-//   attn_bwd_dq_kernel  : one CTA per (128-query tile, head, batch); walks the key tiles of both sources and
-//                         keeps dQ in TMEM.
-// S and dP are recomputed in both (7 instead of 5 tile products): attention is ~5 % of the step's FLOPs.
+// ONE launch (attn_bwd_kernel) with two kinds of CTA, both tcgen05/TMEM/TMA like the forward, no atomics (bitwise
+// reproducible):
+//   dkv CTA : one per (128-key tile, head, batch, source); loops over query tiles and keeps the dV / dK accumulators
+//             in TMEM.  P^T and dS^T are never transposed in memory: the P / dS tiles written to shared memory as
+//             [q][k] are consumed as MN-major A operands.
+//   dq CTA  : one per (128-query tile, head, batch); walks the key tiles of both sources and keeps dQ in TMEM.
+// S and dP are recomputed in both (7 instead of 5 tile products): attention is ~5 % of the step's FLOPs.  The kinds
+// used to be separate launches (dq, dkv of source 1, dkv of source 2): at the training shapes each was less than two
+// waves of short CTAs, so three launch boundaries cost more than the work; now the heavier kind is scheduled first
+// and the lighter one fills the tail.
 #include "common.cuh"
 
 namespace mebt {
@@ -25,18 +28,19 @@ constexpr int TILE = 128 * 64 * 2;    // 16 KiB, a [128 x 64] bf16 tile
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct BwdParams {
-  int NQ, NK, H;             // NK: keys of the source this launch covers (dkv) / unused (dq)
-  int NK1, NK2;              // dq kernel: both sources
-  int q_col0, k_col0, v_col0;
-  int k1_col0, v1_col0, k2_col0, v2_col0;
+  int NQ, H;
+  int NK[2];                 // keys of the two sources
+  int q_col0;
+  int k_col0[2], v_col0[2];
   int do_col0;
   const float* lse;          // [B,H,NQ]
   const float* delta;        // [B,H,NQ]
   __nv_bfloat16* dQ; int lddq; int dq_col0;
-  __nv_bfloat16* dKV; int lddkv; int dk_col0, dv_col0;
+  __nv_bfloat16* dKV[2]; int lddkv[2]; int dk_col0[2], dv_col0[2];
   float scale, scale_log2;
   DropKey drop;              // attention-probability dropout of the forward (thr == 0: none)
-  int src;                   // dkv kernel: which key source this launch covers (0 / 1)
+  int n_dq, n_dkv0;          // CTAs (per head and batch element) of each kind: query tiles, key tiles of source 0
+  int dq_first;              // blockIdx.x order: 1 = dq tiles, then dkv source 0, then source 1; 0 = dkv tiles first
 };
 
 // One thread = one query row of the current [128 q x 128 k] tile pair (S and dP in TMEM).  Computes P and dS for
@@ -115,11 +119,9 @@ __device__ __forceinline__ void store_tmem_rows(uint32_t tmem_addr, uint32_t lan
 constexpr int DKV_SMEM_K = 0, DKV_SMEM_V = TILE, DKV_SMEM_Q = 2 * TILE /* 2 stages */, DKV_SMEM_DO = 4 * TILE /* 2 stages */,
               DKV_SMEM_P = 6 * TILE, DKV_SMEM_DS = 8 * TILE, DKV_SMEM_BAR = 10 * TILE, DKV_SMEM_TOTAL = DKV_SMEM_BAR + 128;
 
-__global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
-                    const __grid_constant__ CUtensorMap tm_kv, const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+__device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorMap& tm_q, const CUtensorMap& tm_do,
+                                                  const CUtensorMap& tm_kv, const BwdParams& p, const int src,
+                                                  const int jt, const int h, const int b) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_SMEM_BAR);
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;    // [2]
@@ -129,9 +131,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* dkv_done = bars + 7;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nq = (p.NQ + 127) / 128;
-  const int valid_keys = min(128, p.NK - jt * 128);
+  const int NK = p.NK[src];
+  const int valid_keys = min(128, NK - jt * 128);
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tm_q); prefetch_tensormap(&tm_do); prefetch_tensormap(&tm_kv);
@@ -150,10 +152,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      const int krow = b * p.NK + jt * 128;
+      const int krow = b * NK + jt * 128;
       mbar_arrive_expect_tx(kv_full, 2 * TILE);
-      tma_load_2d(smem + DKV_SMEM_K, &tm_kv, kv_full, p.k_col0 + h * 64, krow);
-      tma_load_2d(smem + DKV_SMEM_V, &tm_kv, kv_full, p.v_col0 + h * 64, krow);
+      tma_load_2d(smem + DKV_SMEM_K, &tm_kv, kv_full, p.k_col0[src] + h * 64, krow);
+      tma_load_2d(smem + DKV_SMEM_V, &tm_kv, kv_full, p.v_col0[src] + h * 64, krow);
       for (int i = 0; i < nq; ++i) {
         const int s = i & 1;
         mbar_wait(&q_empty[s], ((i >> 1) & 1) ^ 1);
@@ -223,7 +225,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (i > 0) mbar_wait(dkv_done, (i - 1) & 1);    // the previous tile's P / dS are no longer being read
       softmax_bwd_row(tmem_s, tmem_dp, lane_addr, row, row_ok, valid_keys, lse_l2, delta, p.scale, p.scale_log2,
                       smem + DKV_SMEM_P, smem + DKV_SMEM_DS, p.drop,
-                      drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qrow)), (uint32_t(p.src) << 19) | uint32_t(jt * 64));
+                      drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qrow)), (uint32_t(src) << 19) | uint32_t(jt * 64));
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(pds_full);
@@ -231,9 +233,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     mbar_wait(dkv_done, (nq - 1) & 1);
     tc_fence_after();
     const bool ok = row < valid_keys;            // TMEM lanes are key rows here
-    __nv_bfloat16* base = p.dKV + (size_t(b) * p.NK + jt * 128 + row) * p.lddkv + h * 64;
-    store_tmem_rows(tmem_dv, lane_addr, base + p.dv_col0, ok);
-    store_tmem_rows(tmem_dk, lane_addr, base + p.dk_col0, ok);
+    __nv_bfloat16* base = p.dKV[src] + (size_t(b) * NK + jt * 128 + row) * p.lddkv[src] + h * 64;
+    store_tmem_rows(tmem_dv, lane_addr, base + p.dv_col0[src], ok);
+    store_tmem_rows(tmem_dk, lane_addr, base + p.dk_col0[src], ok);
   }
   tc_fence_before();
   __syncthreads();
@@ -246,12 +248,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 constexpr int DQ_SMEM_Q = 0, DQ_SMEM_DO = TILE, DQ_SMEM_K = 2 * TILE /* 2 stages */, DQ_SMEM_V = 4 * TILE /* 2 stages */,
               DQ_SMEM_DS = 6 * TILE, DQ_SMEM_BAR = 8 * TILE, DQ_SMEM_TOTAL = DQ_SMEM_BAR + 128;
 
-__global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
-                   const __grid_constant__ CUtensorMap tm_kv1, const __grid_constant__ CUtensorMap tm_kv2,
-                   const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+__device__ __forceinline__ void attn_bwd_dq_body(uint8_t* smem, const CUtensorMap& tm_q, const CUtensorMap& tm_do,
+                                                 const CUtensorMap& tm_kv1, const CUtensorMap& tm_kv2,
+                                                 const BwdParams& p, const int qt, const int h, const int b) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_SMEM_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
@@ -261,8 +260,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* dq_done = bars + 7;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tiles1 = (p.NK1 + 127) / 128, tiles2 = (p.NK2 + 127) / 128;
+  const int NK1 = p.NK[0], NK2 = p.NK[1];
+  const int tiles1 = (NK1 + 127) / 128, tiles2 = (NK2 + 127) / 128;
   const int nt = tiles1 + tiles2;
 
   if (threadIdx.x == 0) {
@@ -291,13 +290,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], 2 * TILE);
         if (j < tiles1) {
-          const int r = b * p.NK1 + j * 128;
-          tma_load_2d(smem + DQ_SMEM_K + s * TILE, &tm_kv1, &kv_full[s], p.k1_col0 + h * 64, r);
-          tma_load_2d(smem + DQ_SMEM_V + s * TILE, &tm_kv1, &kv_full[s], p.v1_col0 + h * 64, r);
+          const int r = b * NK1 + j * 128;
+          tma_load_2d(smem + DQ_SMEM_K + s * TILE, &tm_kv1, &kv_full[s], p.k_col0[0] + h * 64, r);
+          tma_load_2d(smem + DQ_SMEM_V + s * TILE, &tm_kv1, &kv_full[s], p.v_col0[0] + h * 64, r);
         } else {
-          const int r = b * p.NK2 + (j - tiles1) * 128;
-          tma_load_2d(smem + DQ_SMEM_K + s * TILE, &tm_kv2, &kv_full[s], p.k2_col0 + h * 64, r);
-          tma_load_2d(smem + DQ_SMEM_V + s * TILE, &tm_kv2, &kv_full[s], p.v2_col0 + h * 64, r);
+          const int r = b * NK2 + (j - tiles1) * 128;
+          tma_load_2d(smem + DQ_SMEM_K + s * TILE, &tm_kv2, &kv_full[s], p.k_col0[1] + h * 64, r);
+          tma_load_2d(smem + DQ_SMEM_V + s * TILE, &tm_kv2, &kv_full[s], p.v_col0[1] + h * 64, r);
         }
       }
     }
@@ -351,7 +350,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       delta = p.delta[o];
     }
     for (int j = 0; j < nt; ++j) {
-      const int valid = j < tiles1 ? min(128, p.NK1 - j * 128) : min(128, p.NK2 - (j - tiles1) * 128);
+      const int valid = j < tiles1 ? min(128, NK1 - j * 128) : min(128, NK2 - (j - tiles1) * 128);
       mbar_wait(sp_full, j & 1);
       tc_fence_after();
       if (j > 0) mbar_wait(dq_done, (j - 1) & 1);
@@ -376,6 +375,29 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+constexpr int AB_SMEM_TOTAL = DKV_SMEM_TOTAL > DQ_SMEM_TOTAL ? DKV_SMEM_TOTAL : DQ_SMEM_TOTAL;
+
+// grid (n_dq + n_dkv0 + n_dkv1, H, B): the kind of a CTA is a function of blockIdx.x alone (block-uniform branch)
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                const __grid_constant__ CUtensorMap tm_kv1, const __grid_constant__ CUtensorMap tm_kv2, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_dkv = int(gridDim.x) - p.n_dq;
+  int x = blockIdx.x;
+  bool is_dq;
+  if (p.dq_first) { is_dq = x < p.n_dq; if (!is_dq) x -= p.n_dq; }
+  else { is_dq = x >= n_dkv; if (is_dq) x -= n_dkv; }
+  if (is_dq) {
+    attn_bwd_dq_body(smem, tm_q, tm_do, tm_kv1, tm_kv2, p, x, h, b);
+  } else if (x < p.n_dkv0) {
+    attn_bwd_dkv_body(smem, tm_q, tm_do, tm_kv1, p, 0, x, h, b);
+  } else {
+    attn_bwd_dkv_body(smem, tm_q, tm_do, tm_kv2, p, 1, x - p.n_dkv0, h, b);
+  }
 }
 
 }  // namespace
@@ -424,47 +446,33 @@ int mebt_latent_attention_bwd_dropout(const void* Q, int ldq, int q_col0, const 
   if (NK2 > 0) { rc = get_tensor_map_2d(&t2, KV2, 2, uint64_t(ld2), uint64_t(B) * NK2, uint64_t(ld2) * 2, 64, 128); if (rc) return rc; }
   static bool attr = false;
   if (!attr) {
-    MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM_TOTAL));
-    MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM_TOTAL));
+    MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_TOTAL));
     attr = true;
   }
   BwdParams p;
-  p.NQ = NQ; p.H = H; p.NK1 = NK1; p.NK2 = NK2; p.NK = 0;
+  p.NQ = NQ; p.H = H; p.NK[0] = NK1; p.NK[1] = NK2;
   p.q_col0 = q_col0; p.do_col0 = 0;
-  p.k1_col0 = k1_col0; p.v1_col0 = v1_col0; p.k2_col0 = k2_col0; p.v2_col0 = v2_col0;
-  p.k_col0 = p.v_col0 = 0;
+  p.k_col0[0] = k1_col0; p.v_col0[0] = v1_col0; p.k_col0[1] = k2_col0; p.v_col0[1] = v2_col0;
   p.lse = lse; p.delta = delta;
   p.dQ = static_cast<__nv_bfloat16*>(dQ); p.lddq = lddq; p.dq_col0 = dq_col0;
-  p.dKV = nullptr; p.lddkv = 0; p.dk_col0 = p.dv_col0 = 0;
+  p.dKV[0] = static_cast<__nv_bfloat16*>(dKV1); p.lddkv[0] = ldd1; p.dk_col0[0] = dk1_col0; p.dv_col0[0] = dv1_col0;
+  p.dKV[1] = static_cast<__nv_bfloat16*>(dKV2); p.lddkv[1] = ldd2; p.dk_col0[1] = dk2_col0; p.dv_col0[1] = dv2_col0;
   p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
   p.drop = make_drop_key(drop_p, drop_seed, 0);
-  p.src = 0;
+  for (int src = 0; src < 2; ++src)
+    MEBT_REQUIRE(p.NK[src] == 0 || (p.dKV[src] != nullptr && p.lddkv[src] % 8 == 0), MEBT_ERR_SHAPE,
+                 "attention_bwd: bad dKV%d", src + 1);
+  const int nqt = (NQ + 127) / 128, nkt0 = (NK1 + 127) / 128, nkt1 = (NK2 + 127) / 128;
+  p.n_dq = nqt; p.n_dkv0 = nkt0;
+  // per-CTA work: a dq CTA runs 3 tile products per key tile, a dkv CTA 4 per query tile; the longer kind goes first
+  p.dq_first = 3 * (nkt0 + nkt1) >= 4 * nqt ? 1 : 0;
   const double flops_tile = 2.0 * 128 * 128 * 64;
   {
-    const int nqt = (NQ + 127) / 128;
-    LaunchScope ls(FAM_ATTENTION, 3.0 * flops_tile * double(B) * H * nqt * ((NK1 + 127) / 128 + (NK2 + 127) / 128), st);
-    MEBT_CUDA_OK(launch_pdl(attn_bwd_dq_kernel, dim3(nqt, H, B), dim3(AB_THREADS), DQ_SMEM_TOTAL, st, tq, tdo, t1, t2, p));
+    LaunchScope ls(FAM_ATTENTION, 7.0 * flops_tile * double(B) * H * nqt * (nkt0 + nkt1), st);
+    MEBT_CUDA_OK(launch_pdl(attn_bwd_kernel, dim3(nqt + nkt0 + nkt1, H, B), dim3(AB_THREADS), AB_SMEM_TOTAL, st, tq, tdo,
+                            t1, t2, p));
   }
-  MEBT_LAUNCH_OK("attn_bwd_dq_kernel");
-  for (int src = 0; src < 2; ++src) {
-    const int NK = src == 0 ? NK1 : NK2;
-    if (NK == 0) continue;
-    BwdParams pk = p;
-    pk.NK = NK;
-    pk.src = src;
-    pk.k_col0 = src == 0 ? k1_col0 : k2_col0;
-    pk.v_col0 = src == 0 ? v1_col0 : v2_col0;
-    pk.dKV = static_cast<__nv_bfloat16*>(src == 0 ? dKV1 : dKV2);
-    pk.lddkv = src == 0 ? ldd1 : ldd2;
-    pk.dk_col0 = src == 0 ? dk1_col0 : dk2_col0;
-    pk.dv_col0 = src == 0 ? dv1_col0 : dv2_col0;
-    MEBT_REQUIRE(pk.dKV != nullptr && pk.lddkv % 8 == 0, MEBT_ERR_SHAPE, "attention_bwd: bad dKV%d", src + 1);
-    const int nkt = (NK + 127) / 128;
-    LaunchScope ls(FAM_ATTENTION, 4.0 * flops_tile * double(B) * H * nkt * ((NQ + 127) / 128), st);
-    MEBT_CUDA_OK(launch_pdl(attn_bwd_dkv_kernel, dim3(nkt, H, B), dim3(AB_THREADS), DKV_SMEM_TOTAL, st, tq, tdo,
-                            src == 0 ? t1 : t2, pk));
-    MEBT_LAUNCH_OK("attn_bwd_dkv_kernel");
-  }
+  MEBT_LAUNCH_OK("attn_bwd_kernel");
   return MEBT_OK;
 }
 

@@ -18,6 +18,10 @@ __device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
   return make_float4(a.x, a.y, b.x, b.y);
 }
+__device__ __forceinline__ float4 ld_round_bf16x4(float4 v) {      // v rounded to bf16 and back
+  const float2 a = unpack_bf16x2(pack_bf16x2(v.x, v.y)), b = unpack_bf16x2(pack_bf16x2(v.z, v.w));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
   uint2 u;
   u.x = pack_bf16x2(v.x, v.y);
@@ -108,7 +112,10 @@ template <int MAX_VEC>
 __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ gamma, __nv_bfloat16* dx, const __nv_bfloat16* resid,
-                                     int rows, int D) {
+                                     int rows, int D, __nv_bfloat16* dx_drop, DropKey drop) {
+  // dx_drop (optional): a second copy of the result multiplied by the keep factors of `drop` - the gradient w.r.t. the
+  // pre-dropout output of the Linear that produced this stream (proj / mlp.2), which its dgrad and wgrad GEMMs consume;
+  // saves the separate dropout_rows launch between this kernel and those GEMMs.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   griddep_wait();
   float4 gm[MAX_VEC];
@@ -149,6 +156,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat
       o.w = rs * (g[i].w - s1 - xh[i].w * s2);
       if (resid != nullptr) { o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w; }
       st_bf16x4(dx + row * D + c, o);
+      if (dx_drop != nullptr) {
+        // the standalone kernel masks the bf16-rounded gradient: round first so that both forms agree bit for bit
+        const float4 r = ld_round_bf16x4(o);
+        const uint32_t rk = drop_row_key(drop, uint32_t(row));
+        float f0, f1, f2, f3;
+        drop_pair(drop, rk, uint32_t(c >> 1), f0, f1);
+        drop_pair(drop, rk, uint32_t(c >> 1) + 1u, f2, f3);
+        st_bf16x4(dx_drop + row * D + c, make_float4(r.x * f0, r.y * f1, r.z * f2, r.w * f3));
+      }
     }
   }
 }
@@ -326,50 +342,60 @@ constexpr int LNB_MAX_SLABS = 64;
 
 size_t layernorm_bwd_workspace_bytes(int D) { return size_t(LNB_MAX_SLABS) * 2 * D * 4; }
 
+// Parameter gradients of a LayerNorm: dgamma (+)= sum_r dy * xhat, dbeta (+)= sum_r dy.
+int layernorm_bwd_params(const void* dy, const void* x, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                         int accumulate_params, int rows, int D, float* workspace, size_t ws_bytes, cudaStream_t st) {
+  MEBT_REQUIRE(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024, MEBT_ERR_SHAPE, "layernorm_bwd: bad shape rows=%d D=%d", rows, D);
+  MEBT_REQUIRE(workspace != nullptr && ws_bytes >= layernorm_bwd_workspace_bytes(D), MEBT_ERR_WORKSPACE,
+               "layernorm_bwd: workspace too small");
+  if (rows == 0) return MEBT_OK;
+  int* counters = reduce_counters(st);
+  MEBT_REQUIRE(counters != nullptr, MEBT_ERR_CUDA, "layernorm_bwd: cannot allocate the ticket counters");
+  int slabs = (rows + 31) / 32;
+  if (slabs > LNB_MAX_SLABS) slabs = LNB_MAX_SLABS;
+  const int rows_per_slab = (rows + slabs - 1) / slabs;
+  LaunchScope ls(FAM_LAYERNORM, double(rows) * D * 4.0, st);
+  MEBT_CUDA_OK(launch_pdl(layernorm_bwd_param_kernel, dim3((D + 127) / 128, slabs), dim3(256), 0, st,
+                          static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), mean, rstd, rows, D,
+                          rows_per_slab, workspace, dgamma, dbeta, accumulate_params, counters + 1000));
+  MEBT_LAUNCH_OK("layernorm_bwd_param_kernel");
+  return MEBT_OK;
+}
+
+// dx = (resid != NULL ? resid : 0) + ln'(dy); resid may be dx itself.  dx_drop / drop: see the kernel.
+int layernorm_bwd_dx(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                     const void* resid, int rows, int D, void* dx_drop, const DropKey* drop, cudaStream_t st) {
+  MEBT_REQUIRE(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024, MEBT_ERR_SHAPE, "layernorm_bwd: bad shape rows=%d D=%d", rows, D);
+  if (rows == 0) return MEBT_OK;
+  const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(resid);
+  __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx);
+  __nv_bfloat16* ddp = static_cast<__nv_bfloat16*>(dx_drop);      // with thr == 0 the second output is a plain copy
+  const DropKey dk = drop != nullptr ? *drop : DropKey{0u, 0u, 0u, 1.f};
+  const dim3 grid((rows + 7) / 8);
+  LaunchScope ls(FAM_LAYERNORM, double(rows) * D * (rp != nullptr ? 8.0 : 6.0), st);
+  if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<2>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, ddp, dk));
+  else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<4>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, ddp, dk));
+  else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<8>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, ddp, dk));
+  MEBT_LAUNCH_OK("layernorm_bwd_dx_kernel");
+  return MEBT_OK;
+}
+
 int layernorm_bwd_resid(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                         void* dx, const void* resid, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
-                        float* workspace, size_t ws_bytes, cudaStream_t st);
+                        float* workspace, size_t ws_bytes, cudaStream_t st) {
+  // parameter gradients first: they read dy, which dx may overwrite when the caller accumulates in place
+  int rc = layernorm_bwd_params(dy, x, mean, rstd, dgamma, dbeta, accumulate_params, rows, D, workspace, ws_bytes, st);
+  if (rc) return rc;
+  return layernorm_bwd_dx(dy, x, mean, rstd, gamma, dx, resid, rows, D, nullptr, nullptr, st);
+}
 
 int layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                   int accumulate_dx, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
                   float* workspace, size_t ws_bytes, cudaStream_t st) {
   return layernorm_bwd_resid(dy, x, mean, rstd, gamma, dx, accumulate_dx ? dx : nullptr, dgamma, dbeta, accumulate_params,
                              rows, D, workspace, ws_bytes, st);
-}
-
-// dx = (resid != NULL ? resid : 0) + ln'(dy); resid may be dx itself
-int layernorm_bwd_resid(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
-                        void* dx, const void* resid, float* dgamma, float* dbeta, int accumulate_params, int rows, int D,
-                        float* workspace, size_t ws_bytes, cudaStream_t st) {
-  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(resid);
-  MEBT_REQUIRE(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024, MEBT_ERR_SHAPE, "layernorm_bwd: bad shape rows=%d D=%d", rows, D);
-  MEBT_REQUIRE(workspace != nullptr && ws_bytes >= layernorm_bwd_workspace_bytes(D), MEBT_ERR_WORKSPACE,
-               "layernorm_bwd: workspace too small");
-  if (rows == 0) return MEBT_OK;
-  const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
-  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
-  __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx);
-  int* counters = reduce_counters(st);
-  MEBT_REQUIRE(counters != nullptr, MEBT_ERR_CUDA, "layernorm_bwd: cannot allocate the ticket counters");
-  {
-    // parameter gradients first: they read dy, which dx may overwrite when the caller accumulates in place
-    int slabs = (rows + 31) / 32;
-    if (slabs > LNB_MAX_SLABS) slabs = LNB_MAX_SLABS;
-    const int rows_per_slab = (rows + slabs - 1) / slabs;
-    LaunchScope ls(FAM_LAYERNORM, double(rows) * D * 4.0, st);
-    MEBT_CUDA_OK(launch_pdl(layernorm_bwd_param_kernel, dim3((D + 127) / 128, slabs), dim3(256), 0, st, dyp, xp, mean, rstd,
-                            rows, D, rows_per_slab, workspace, dgamma, dbeta, accumulate_params, counters + 1000));
-  }
-  MEBT_LAUNCH_OK("layernorm_bwd_param_kernel");
-  {
-    const dim3 grid((rows + 7) / 8);
-    LaunchScope ls(FAM_LAYERNORM, double(rows) * D * (rp != nullptr ? 8.0 : 6.0), st);
-    if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<2>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D));
-    else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<4>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D));
-    else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<8>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D));
-  }
-  MEBT_LAUNCH_OK("layernorm_bwd_dx_kernel");
-  return MEBT_OK;
 }
 
 int embed_backward(const int64_t* x, int x_stride, const int64_t* ctx_idx, int ctx_stride, const int64_t* tgt_idx,

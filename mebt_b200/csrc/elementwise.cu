@@ -411,14 +411,17 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
 }
 
 int adamw_flat(float* p, const float* g, float* m, float* v, void* p16, const unsigned char* decay, int shift, long long n,
-               float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st) {
+               float lr, float beta1, float beta2, float eps, float wd, int step, int max_ctas, cudaStream_t st) {
   MEBT_REQUIRE(n >= 0 && n % 4 == 0 && shift >= 2 && step >= 1, MEBT_ERR_SHAPE, "adamw: n %% 4 != 0, shift < 2 or step < 1");
   if (n == 0) return MEBT_OK;
   const double bc1 = 1.0 - pow(double(beta1), double(step));
   const double bc2 = 1.0 - pow(double(beta2), double(step));
   {
     LaunchScope ls(FAM_OTHER, double(n) * 30.0, st);
-    adamw_flat_kernel<<<148 * 8, 256, 0, st>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p16), decay, shift, n / 4, lr, beta1,
+    // max_ctas > 0: a background update - few CTAs trickle through the buffers while latency-bound kernels of another
+    // stream (the rest of backward) keep the SMs; the full grid saturates HBM and is for an update nothing overlaps
+    const int grid = max_ctas > 0 && max_ctas < 148 * 8 ? max_ctas : 148 * 8;
+    adamw_flat_kernel<<<grid, 256, 0, st>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p16), decay, shift, n / 4, lr, beta1,
                                                beta2, eps, wd, float(double(lr) / bc1), float(1.0 / sqrt(bc2)));
   }
   MEBT_LAUNCH_OK("adamw_flat_kernel");
@@ -479,8 +482,15 @@ extern "C" {
 int mebt_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, const unsigned char* decay_blocks,
                     int block_shift, long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     void* stream) {
-  return mebt::adamw_flat(p, g, m, v, p_bf16, decay_blocks, block_shift, n, lr, beta1, beta2, eps, weight_decay, step,
+  return mebt::adamw_flat(p, g, m, v, p_bf16, decay_blocks, block_shift, n, lr, beta1, beta2, eps, weight_decay, step, 0,
                           static_cast<cudaStream_t>(stream));
+}
+
+int mebt_adamw_flat_bg(float* p, const float* g, float* m, float* v, void* p_bf16, const unsigned char* decay_blocks,
+                       int block_shift, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       int step, int max_ctas, void* stream) {
+  return mebt::adamw_flat(p, g, m, v, p_bf16, decay_blocks, block_shift, n, lr, beta1, beta2, eps, weight_decay, step,
+                          max_ctas, static_cast<cudaStream_t>(stream));
 }
 
 int mebt_dropout_rows(const void* x, int ldx, const void* resid, int ldres, void* y, int ldy, int rows, int D, float p,

@@ -31,6 +31,20 @@ int colsum(const void* X, int ld, int rows, int N, float* out, int accumulate, f
            cudaStream_t st);
 int dropout_rows(const void* x, int ldx, const void* resid, int ldres, void* y, int ldy, int rows, int D, float p,
                  unsigned long long seed, unsigned long long site, cudaStream_t st);
+int gemm_bf16_drop(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                   int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
+                   const DropKey* drop, cudaStream_t stream);
+struct WgradDesc {           // csrc/gemm_grouped.cu
+  const void* dY; int ld_dy;
+  const void* X; int ldx;
+  float* dW; int ldw;
+  int n_out, k_in, rows, accumulate;
+};
+int gemm_grouped_wgrad(const WgradDesc* d, int n, cudaStream_t stream);
+int layernorm_bwd_params(const void* dy, const void* x, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                         int accumulate_params, int rows, int D, float* workspace, size_t ws_bytes, cudaStream_t st);
+int layernorm_bwd_dx(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                     const void* resid, int rows, int D, void* dx_drop, const DropKey* drop, cudaStream_t st);
 
 namespace {
 
@@ -87,43 +101,97 @@ Plan make_plan(const mebt_layer_t* layers, int n_layers, int B, int L, int NC, i
   return p;
 }
 
-// Weight-gradient GEMMs and bias column sums only consume tensors the data-gradient chain has already produced, so
-// they run on a library-owned side stream, concurrently with the next links of the chain (every GEMM of the 16-frame
-// training step is at most one wave of tiles: two of them fit on the 148 SMs side by side).
-struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t join = nullptr;
+// Weight-gradient GEMMs, bias column sums and LayerNorm parameter gradients only consume tensors the data-gradient
+// chain has already produced, so they run on two library-owned side streams (A: the tcgen05 weight-gradient GEMMs,
+// B: the small reductions), concurrently with the next links of the chain: every kernel of the 16-frame training step
+// is at most about one wave of CTAs, so the chain is bound by per-kernel latency, not by SM time.
+struct SideStreams {
+  cudaStream_t a = nullptr, b = nullptr;
+  cudaEvent_t fork[8] = {};
+  cudaEvent_t join_a = nullptr, join_b = nullptr;
+  // per block parity: the block's readers of its masked stream gradient are done (A: the grouped weight gradients,
+  // B: the mlp.2 bias gradient) / all of the block's side work is done (it reads the scratch buffers the block after
+  // next reuses)
+  cudaEvent_t fc2_a[2] = {}, fc2_b[2] = {}, end_a[2] = {}, end_b[2] = {};
   bool ok = false;
 };
-SideStream& side_stream() {
-  static SideStream s;
-  if (!s.ok && s.stream == nullptr) {
-    bool good = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 4 && good; ++i) good = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess;
-    good = good && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+SideStreams& side_streams() {
+  static SideStreams s;
+  if (!s.ok && s.a == nullptr) {
+    bool good = cudaStreamCreateWithFlags(&s.a, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&s.b, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && good; ++i) good = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&s.join_a, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.join_b, cudaEventDisableTiming) == cudaSuccess;
+    for (cudaEvent_t* e : {s.fc2_a, s.fc2_b, s.end_a, s.end_b})
+      for (int i = 0; i < 2 && good; ++i) good = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) == cudaSuccess;
     s.ok = good;
   }
   return s;
 }
 
-size_t backward_workspace_bytes(int B, int L, int NC, int NT, int D, int H) {
+// Which LayerNorm backward finishes the gradient w.r.t. block i's output stream (the last accumulation before block i
+// reads it): the first later block that reads that stream, through its query side (0) or key side (1), or ln_f (2)
+// for the last latent_dec block; -1 when nothing reads it.  That kernel also writes the gradient multiplied by block
+// i's mlp-dropout mask, which is what block i's first two GEMMs consume.
+struct FinalWriter { int block; int side; };
+FinalWriter final_writer(const mebt_layer_t* layers, int last, int i) {
+  const bool tgt_stream = layers[i].mode == MEBT_MODE_LATENT_DEC;
+  for (int j = i + 1; j <= last; ++j) {
+    const int m = layers[j].mode;
+    if (tgt_stream) {
+      if (m == MEBT_MODE_LATENT_DEC) return {j, 0};
+      if (m == MEBT_MODE_LT2L) return {j, 1};
+    } else {
+      if (m == MEBT_MODE_LATENT_DEC) return {j, 1};
+      return {j, 0};                       // latent_enc / latent_self / lt2l read the latents as queries
+    }
+  }
+  if (i == last) return {last + 1, 2};
+  return {-1, -1};
+}
+
+// Every scratch tensor of a block's backward exists twice (by block parity): the side streams may still be reading
+// block i's buffers while the main stream runs block i-1, and block i-2 only starts after block i's side work.
+struct BwdWorkspace {
+  void *da[2], *dh[2], *datt[2], *dqkv[2], *dkv[2], *dqn[2], *dkn[2], *dxb[2], *dy_proj[2], *delta, *dy_mlp[2][2];
+  float *red, *red_b;
+  size_t red_bytes, delta_bytes, total;
+};
+BwdWorkspace carve_backward_workspace(char* W, int B, int L, int NC, int NT, int D, int H) {
   const size_t rmax = size_t(B) * size_t(L > NT ? L : NT);
   const size_t rk = size_t(B) * size_t(NC > NT ? (NC > L ? NC : L) : (NT > L ? NT : L));
-  size_t t = 0;
-  t += al(rmax * 4 * D * 2);       // da
-  t += al(rmax * D * 2);           // dh / datt
-  t += al(rmax * 3 * D * 2);       // dqkv
-  t += al(rk * 2 * D * 2);         // dkv
-  t += al(rmax * D * 2);           // dqn
-  t += al(rk * D * 2);             // dkn
-  t += al(size_t(B) * H * (L > NT ? L : NT) * 4);   // attention delta
-  t += al(rmax * D * 2);           // dx (kept separate from the stream gradient: the side stream still reads d_out)
-  t += 2 * al(rmax * D * 2);       // dropout: gradients w.r.t. the pre-dropout MLP / proj outputs
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = W + off; off += al(bytes); return static_cast<void*>(p); };
+  BwdWorkspace w;
+  for (int i = 0; i < 2; ++i) {
+    w.da[i] = take(rmax * 4 * D * 2);
+    w.dh[i] = take(rmax * D * 2);
+    w.datt[i] = take(rmax * D * 2);        // separate from dh: side stream B still reads dh (ln2 parameter gradients)
+    w.dqkv[i] = take(rmax * 3 * D * 2);
+    w.dkv[i] = take(rk * 2 * D * 2);
+    w.dqn[i] = take(rmax * D * 2);
+    w.dkn[i] = take(rk * D * 2);
+    w.dxb[i] = take(rmax * D * 2);         // dx, separate from the stream gradient (the side streams still read d_out)
+    w.dy_proj[i] = take(rmax * D * 2);     // dx .* keep/(1-p): gradient w.r.t. the pre-dropout proj output
+  }
+  w.delta_bytes = size_t(B) * H * (L > NT ? L : NT) * 4;
+  w.delta = take(w.delta_bytes);
+  for (int i = 0; i < 2; ++i) {                  // [stream][parity of the consuming block]
+    w.dy_mlp[0][i] = take(size_t(B) * L * D * 2);     // d(latents) .* keep/(1-p): gradient w.r.t. the pre-dropout MLP output
+    w.dy_mlp[1][i] = take(size_t(B) * NT * D * 2);    // the same for the targets stream
+  }
   size_t red = layernorm_bwd_workspace_bytes(D);
   const size_t cs = size_t(64) * 16384 * 4;         // column-sum partials up to N = 16384
-  t += 2 * al(red > cs ? red : cs);                 // one reduction scratch per stream
-  return t + 4096;
+  w.red_bytes = al(red > cs ? red : cs);
+  w.red = static_cast<float*>(take(w.red_bytes));
+  w.red_b = static_cast<float*>(take(w.red_bytes));
+  w.total = off + 4096;
+  return w;
+}
+
+size_t backward_workspace_bytes(int B, int L, int NC, int NT, int D, int H) {
+  return carve_backward_workspace(nullptr, B, L, NC, NT, D, H).total;
 }
 
 }  // namespace
@@ -199,21 +267,15 @@ int mebt_stack_forward_train_dropout(const mebt_layer_t* layers, int n_layers, c
     else
       TRY(mebt_latent_attention_fwd_dropout(qkv, D, 0, s.rk > 0 ? kv : nullptr, 2 * D, 0, D, nk_sep, nullptr, 0, 0, 0, 0,
                                             att, D, lse, B, H, s.nq, 64, attn_p, seed + site, stream));
-    if (resid_p > 0.f) {     // x = qn + drop(att Wp + b): the GEMM leaves the pre-dropout value, the dropout kernel adds qn
-      TRY(gemm_bf16_aux(att, D, 0, w.w_proj, D, 0, x, D, s.rq, D, D, w.b_proj, nullptr, 0, nullptr, 0, 0, st));
-      TRY(dropout_rows(x, D, qn, D, x, D, s.rq, D, resid_p, seed, site + 1, st));
-    } else {
-      TRY(gemm_bf16_aux(att, D, 0, w.w_proj, D, 0, x, D, s.rq, D, D, w.b_proj, qn, D, nullptr, 0, 0, st));
-    }
+    // x = qn + drop(att Wp + b): the keep factors are applied in the GEMM epilogue, between the bias and the residual
+    const DropKey k_proj = make_drop_key(resid_p, seed, site + 1), k_mlp = make_drop_key(resid_p, seed, site + 2);
+    TRY(gemm_bf16_drop(att, D, 0, w.w_proj, D, 0, x, D, s.rq, D, D, w.b_proj, qn, D, nullptr, 0, 0,
+                       resid_p > 0.f ? &k_proj : nullptr, st));
     TRY(layernorm(x, D, MEBT_DTYPE_BF16, w.ln2_w, w.ln2_b, h, D, MEBT_DTYPE_BF16, s.rq, D, 1e-5f,
                   reinterpret_cast<float*>(S + s.x_mean), reinterpret_cast<float*>(S + s.x_rstd), st));
     TRY(gemm_bf16_aux(h, D, 0, w.w_fc1, D, 0, u, 4 * D, s.rq, 4 * D, D, w.b_fc1, nullptr, 0, a, 4 * D, MEBT_GEMM_GELU, st));
-    if (resid_p > 0.f) {     // out = x + drop(u W2 + b)
-      TRY(gemm_bf16_aux(u, 4 * D, 0, w.w_fc2, 4 * D, 0, out, D, s.rq, D, 4 * D, w.b_fc2, nullptr, 0, nullptr, 0, 0, st));
-      TRY(dropout_rows(out, D, x, D, out, D, s.rq, D, resid_p, seed, site + 2, st));
-    } else {
-      TRY(gemm_bf16_aux(u, 4 * D, 0, w.w_fc2, 4 * D, 0, out, D, s.rq, D, 4 * D, w.b_fc2, x, D, nullptr, 0, 0, st));
-    }
+    TRY(gemm_bf16_drop(u, 4 * D, 0, w.w_fc2, 4 * D, 0, out, D, s.rq, D, 4 * D, w.b_fc2, x, D, nullptr, 0, 0,
+                       resid_p > 0.f ? &k_mlp : nullptr, st));               // out = x + drop(u W2 + b)
     if (w.mode == MEBT_MODE_LATENT_DEC) tgt = out; else lat = out;
   }
   TRY(layernorm(tgt, D, MEBT_DTYPE_BF16, lnf_w, lnf_b, S + plan.xf, D, MEBT_DTYPE_BF16, B * NT, D, 1e-5f,
@@ -251,30 +313,43 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
                "backward: workspace too small (%zu < %zu)", workspace_bytes, backward_workspace_bytes(B, L, NC, NT, D, H));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* S = static_cast<char*>(saved);
-  char* W = static_cast<char*>(workspace);
-  const size_t rmax = size_t(B) * size_t(L > NT ? L : NT);
-  const size_t rkmax = size_t(B) * size_t(NC > NT ? (NC > L ? NC : L) : (NT > L ? NT : L));
-  size_t off = 0;
-  auto take = [&](size_t bytes) { char* p = W + off; off += al(bytes); return p; };
-  void* da = take(rmax * 4 * D * 2);
-  void* dh = take(rmax * D * 2);
-  void* dqkv = take(rmax * 3 * D * 2);
-  void* dkv = take(rkmax * 2 * D * 2);
-  void* dqn = take(rmax * D * 2);
-  void* dkn = take(rkmax * D * 2);
-  const size_t delta_bytes = size_t(B) * H * (L > NT ? L : NT) * 4;
-  void* delta = take(delta_bytes);
-  void* dxb = take(rmax * D * 2);
-  void* dy_mlp = take(rmax * D * 2);     // d_out .* keep/(1-p): gradient w.r.t. the pre-dropout MLP output
-  void* dy_proj = take(rmax * D * 2);    // dx .* keep/(1-p): gradient w.r.t. the pre-dropout proj output
-  const size_t red_each = ((workspace_bytes - off - 512) / 2) & ~size_t(255);
-  const size_t red_bytes = red_each;
-  float* red = reinterpret_cast<float*>(W + off);
-  float* red_side = reinterpret_cast<float*>(W + off + red_each);
+  const BwdWorkspace ws = carve_backward_workspace(static_cast<char*>(workspace), B, L, NC, NT, D, H);
+  void* delta = ws.delta;
+  const size_t delta_bytes = ws.delta_bytes, red_bytes = ws.red_bytes;
+  float* red_b = ws.red_b;            // reduction scratch of side stream B (ws.red: main stream, unused by this engine now)
   const int acc = grad_accumulate ? 1 : 0;
-  SideStream& side = side_stream();
-  MEBT_REQUIRE(side.ok, MEBT_ERR_CUDA, "backward: cannot create the weight-gradient side stream");
-  cudaStream_t sst = side.stream;
+  SideStreams& side = side_streams();
+  MEBT_REQUIRE(side.ok, MEBT_ERR_CUDA, "backward: cannot create the weight-gradient side streams");
+  cudaStream_t sa = side.a, sb = side.b;
+  int fork_slot = 0;
+  // everything issued so far on the main stream happens before whatever is issued next on the two side streams
+  auto FORK = [&]() -> int {
+    cudaEvent_t e = side.fork[fork_slot];
+    fork_slot = (fork_slot + 1) & 7;
+    MEBT_CUDA_OK(cudaEventRecord(e, st));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(sa, e, 0));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(sb, e, 0));
+    return MEBT_OK;
+  };
+  // the side streams' work so far is marked by (ea on A, eb on B) ... / ... and the main stream waits for such a mark
+  auto MARK = [&](cudaEvent_t ea, cudaEvent_t eb) -> int {
+    MEBT_CUDA_OK(cudaEventRecord(ea, sa));
+    MEBT_CUDA_OK(cudaEventRecord(eb, sb));
+    return MEBT_OK;
+  };
+  auto AWAIT = [&](cudaEvent_t ea, cudaEvent_t eb) -> int {
+    MEBT_CUDA_OK(cudaStreamWaitEvent(st, ea, 0));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(st, eb, 0));
+    return MEBT_OK;
+  };
+  // ... and everything issued so far on the side streams happens before whatever is issued next on the main stream
+  auto JOIN = [&]() -> int {
+    MEBT_CUDA_OK(cudaEventRecord(side.join_a, sa));
+    MEBT_CUDA_OK(cudaEventRecord(side.join_b, sb));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.join_a, 0));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.join_b, 0));
+    return MEBT_OK;
+  };
 
   // weight gradient dW[N_out, K_in] (+)= dY^T X : A = dY stored [rows, N_out] (MN-major), B = X stored [rows, K_in] (MN-major)
   auto WGRAD_ON = [&](cudaStream_t on, const void* dY, int ld_dy, const void* X, int ldx, float* dWt, int ldw, int n_out,
@@ -282,33 +357,50 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
     return gemm_bf16_aux(dY, ld_dy, 1, X, ldx, 1, dWt, ldw, n_out, k_in, rows, nullptr, nullptr, 0, nullptr, 0,
                          MEBT_GEMM_OUT_FP32 | (accumulate ? MEBT_GEMM_ACCUMULATE : 0), on);
   };
-  auto WGRAD = [&](const void* dY, int ld_dy, const void* X, int ldx, float* dWt, int ldw, int n_out, int k_in, int rows,
-                   int accumulate) { return WGRAD_ON(st, dY, ld_dy, X, ldx, dWt, ldw, n_out, k_in, rows, accumulate); };
-  // weight + bias gradient of one nn.Linear on the side stream, after everything recorded so far on the main stream
-  auto SIDE_LINEAR = [&](int slot, const void* dY, int ld_dy, const void* X, int ldx, float* dWt, int ldw, float* db,
-                         int n_out, int k_in, int rows, int accumulate) -> int {
-    MEBT_CUDA_OK(cudaEventRecord(side.fork[slot], st));
-    MEBT_CUDA_OK(cudaStreamWaitEvent(sst, side.fork[slot], 0));
-    int rc2 = WGRAD_ON(sst, dY, ld_dy, X, ldx, dWt, ldw, n_out, k_in, rows, accumulate);
-    if (rc2) return rc2;
-    return colsum(dY, ld_dy, rows, n_out, db, accumulate, red_side, red_bytes, sst);
-  };
   // data gradient dX[rows, K_in] = dY[rows, N_out] W[N_out, K_in] : B = W stored [K_red = N_out, N = K_in] (MN-major)
   auto DGRAD = [&](const void* dY, int ld_dy, const void* Wt, int ldw, void* dX, int rows, int k_in, int n_out,
                    const void* residual, void* aux, int ldaux, int flags) {
     return gemm_bf16_aux(dY, ld_dy, 0, Wt, ldw, 1, dX, k_in, rows, k_in, n_out, nullptr, residual, k_in, aux, ldaux, flags, st);
   };
+  // the masked copy the LayerNorm backward `side` (0 query / 1 key / 2 ln_f) of block `j` owes to an earlier block
+  // (with resid_p = 0 the copy is unmasked: block i's GEMMs then read a buffer nobody overwrites behind their back)
+  struct Owed { void* dst; DropKey key; int consumer; };
+  auto owed_by = [&](int j, int which) {
+    Owed o{nullptr, make_drop_key(0.f, 0ull, 0ull), -1};
+    for (int i = 0; i <= plan.last && i < j; ++i) {
+      const FinalWriter fw = final_writer(layers, plan.last, i);
+      if (fw.block == j && fw.side == which) {
+        o.dst = ws.dy_mlp[layers[i].mode == MEBT_MODE_LATENT_DEC ? 1 : 0][i & 1];
+        o.key = make_drop_key(resid_p, seed, 4ull * i + 2);
+        o.consumer = i;
+      }
+    }
+    return o;
+  };
+  // before the copy owed to block `consumer` is written: the previous readers of that buffer (side work of the last
+  // processed block of the same parity) must be done
+  auto AWAIT_OWED = [&](const Owed& o) -> int {
+    if (o.consumer < 0) return MEBT_OK;
+    return AWAIT(side.fc2_a[o.consumer & 1], side.fc2_b[o.consumer & 1]);
+  };
 
   if (layer_end == n_layers) {
     // ---- head + ln_f (gpt.py:247-248) ----
     const int rows = B * NT;
-    void* d_xf = dh;
+    const int hp = (plan.last + 1) & 1;           // the head takes the scratch parity of a block behind the last one
+    void* d_xf = ws.dh[hp];
     TRY(DGRAD(dlogits, V, w_head, D, d_xf, rows, D, V, nullptr, nullptr, 0, 0));
-    TRY(WGRAD(dlogits, V, S + plan.xf, D, d_w_head, D, V, D, rows, acc));
+    TRY(FORK());
+    TRY(WGRAD_ON(sa, dlogits, V, S + plan.xf, D, d_w_head, D, V, D, rows, acc));
     // the final targets stream is the `out` of the last latent_dec block
     const void* tgt_final = S + plan.layers[plan.last].out;
-    TRY(layernorm_bwd(d_xf, tgt_final, reinterpret_cast<float*>(S + plan.f_mean), reinterpret_cast<float*>(S + plan.f_rstd),
-                      lnf_w, d_tgt, 0, d_lnf_w, d_lnf_b, acc, rows, D, red, red_bytes, st));
+    TRY(layernorm_bwd_params(d_xf, tgt_final, reinterpret_cast<float*>(S + plan.f_mean), reinterpret_cast<float*>(S + plan.f_rstd),
+                             d_lnf_w, d_lnf_b, acc, rows, D, red_b, red_bytes, sb));
+    const Owed o = owed_by(plan.last + 1, 2);
+    TRY(AWAIT_OWED(o));
+    TRY(layernorm_bwd_dx(d_xf, tgt_final, reinterpret_cast<float*>(S + plan.f_mean), reinterpret_cast<float*>(S + plan.f_rstd),
+                         lnf_w, d_tgt, nullptr, rows, D, o.dst, &o.key, st));
+    TRY(MARK(side.end_a[hp], side.end_b[hp]));
     MEBT_CUDA_OK(cudaMemsetAsync(d_lat, 0, size_t(B) * L * D * 2, st));
     if (NC > 0) MEBT_CUDA_OK(cudaMemsetAsync(d_ctx, 0, size_t(B) * NC * D * 2, st));
     if (!acc) {
@@ -352,30 +444,45 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
     const void* k_in = mode == MEBT_MODE_LATENT_ENC ? ctx : mode == MEBT_MODE_LATENT_DEC ? lat_in[i] : mode == MEBT_MODE_LT2L ? tgt_in[i] : nullptr;
     void* d_k_stream = mode == MEBT_MODE_LATENT_ENC ? d_ctx : mode == MEBT_MODE_LATENT_DEC ? d_lat : mode == MEBT_MODE_LT2L ? d_tgt : nullptr;
     const int rq = s.rq, rk = s.rk;
+    const int par = i & 1;
+    void *da = ws.da[par], *dh = ws.dh[par], *datt = ws.datt[par], *dqkv = ws.dqkv[par], *dkv = ws.dkv[par],
+         *dqn = ws.dqn[par], *dkn = ws.dkn[par], *dxb = ws.dxb[par], *dy_proj = ws.dy_proj[par];
+    // this block reuses the scratch buffers of block i + 2: that block's side work (issued two blocks ago) must be done
+    TRY(AWAIT(side.end_a[par], side.end_b[par]));
 
     const unsigned long long site = 4ull * i;
-    // ---- MLP ----  (main stream: the data-gradient chain; side stream: weight and bias gradients)
-    const void* d_mlp = d_out;                      // gradient w.r.t. (u W2 + b): d_out through the dropout mask
-    if (resid_p > 0.f) {
-      TRY(dropout_rows(d_out, D, nullptr, 0, dy_mlp, D, rq, D, resid_p, seed, site + 2, st));
-      d_mlp = dy_mlp;
+    // ---- MLP ----  (main stream: the data-gradient chain; side stream A: ONE grouped launch of the block's weight
+    // gradients once its last operand exists; side stream B: bias and LayerNorm parameter gradients as they become ready)
+    // d_mlp = d_out through the mlp-dropout mask = gradient w.r.t. (u W2 + b): a copy written by the LayerNorm backward
+    // that finished d_out (see final_writer), so that this block's last kernels may overwrite d_out while the side
+    // streams still read d_mlp; made here when no such kernel exists
+    void* d_mlp = ws.dy_mlp[mode == MEBT_MODE_LATENT_DEC ? 1 : 0][par];
+    if (final_writer(layers, plan.last, i).block < 0) {
+      TRY(AWAIT(side.fc2_a[par], side.fc2_b[par]));
+      TRY(dropout_rows(d_out, D, nullptr, 0, d_mlp, D, rq, D, resid_p, seed, site + 2, st));
     }
-    TRY(SIDE_LINEAR(0, d_mlp, D, S + s.u, 4 * D, g.w_fc2, 4 * D, g.b_fc2, D, 4 * D, rq, acc));
+    auto SIDE_COLSUM = [&](const void* dY, int ld_dy, int rows, int n_out, float* db, int accumulate) -> int {
+      int rc2 = FORK();
+      if (rc2) return rc2;
+      return colsum(dY, ld_dy, rows, n_out, db, accumulate, red_b, red_bytes, sb);
+    };
+    TRY(SIDE_COLSUM(d_mlp, D, rq, D, g.b_fc2, acc));
+    MEBT_CUDA_OK(cudaEventRecord(side.fc2_b[par], sb));
     TRY(DGRAD(d_mlp, D, w.w_fc2, 4 * D, da, rq, 4 * D, D, nullptr, S + s.a, 4 * D, MEBT_GEMM_DGELU));     // da
-    TRY(SIDE_LINEAR(1, da, 4 * D, S + s.h, D, g.w_fc1, D, g.b_fc1, 4 * D, D, rq, acc));
+    TRY(SIDE_COLSUM(da, 4 * D, rq, 4 * D, g.b_fc1, acc));
     TRY(DGRAD(da, 4 * D, w.w_fc1, D, dh, rq, D, 4 * D, nullptr, nullptr, 0, 0));                            // dh
-    // dx = d_out + ln2'(dh), written to its own buffer (d_out is still being read by the side stream)
+    // dx = d_out + ln2'(dh), in its own buffer; the same kernel writes dx through the proj-dropout mask = the gradient
+    // w.r.t. (att Wp + b)
     void* dx = dxb;
-    TRY(layernorm_bwd_resid(dh, S + s.x, reinterpret_cast<float*>(S + s.x_mean), reinterpret_cast<float*>(S + s.x_rstd),
-                            w.ln2_w, dx, d_out, g.ln2_w, g.ln2_b, acc, rq, D, red, red_bytes, st));
+    TRY(FORK());
+    TRY(layernorm_bwd_params(dh, S + s.x, reinterpret_cast<float*>(S + s.x_mean), reinterpret_cast<float*>(S + s.x_rstd),
+                             g.ln2_w, g.ln2_b, acc, rq, D, red_b, red_bytes, sb));
+    const DropKey k_proj = make_drop_key(resid_p, seed, site + 1);
+    TRY(layernorm_bwd_dx(dh, S + s.x, reinterpret_cast<float*>(S + s.x_mean), reinterpret_cast<float*>(S + s.x_rstd),
+                         w.ln2_w, dx, d_out, rq, D, resid_p > 0.f ? dy_proj : nullptr, &k_proj, st));
     // ---- attention output projection ----
-    void* datt = dh;
-    const void* d_proj = dx;                        // gradient w.r.t. (att Wp + b)
-    if (resid_p > 0.f) {
-      TRY(dropout_rows(dx, D, nullptr, 0, dy_proj, D, rq, D, resid_p, seed, site + 1, st));
-      d_proj = dy_proj;
-    }
-    TRY(SIDE_LINEAR(2, d_proj, D, S + s.att, D, g.w_proj, D, g.b_proj, D, D, rq, acc));
+    const void* d_proj = resid_p > 0.f ? dy_proj : dx;
+    TRY(SIDE_COLSUM(d_proj, D, rq, D, g.b_proj, acc));
     TRY(DGRAD(d_proj, D, w.w_proj, D, datt, rq, D, D, nullptr, nullptr, 0, 0));
     // ---- attention ----
     const int nk_sep = rk / B;
@@ -390,29 +497,59 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
                                             0, 0, S + s.att, D, datt, D, lse, dqkv, D, 0, rk > 0 ? dkv : nullptr, 2 * D, 0,
                                             D, nullptr, 0, 0, 0, B, H, s.nq, 64, attn_p, seed + site, delta, delta_bytes,
                                             stream));
-    // ---- q/k/v projections ----
+    // ---- weight gradients of the whole block: one grouped launch on side stream A ----
     const int qw = fused ? 3 * D : D;
-    TRY(SIDE_LINEAR(3, dqkv, qw, S + s.qn, D, g.w_qkv, D, g.b_qkv, qw, D, rq, acc));
-    if (rk > 0) {   // same side stream, after the q-side gradients: they may accumulate into the same rows (lt2l)
-      TRY(WGRAD_ON(sst, dkv, 2 * D, S + s.kn, D, g.w_qkv + size_t(D) * D, D, 2 * D, D, rk, fused ? 1 : acc));
-      TRY(colsum(dkv, 2 * D, rk, 2 * D, g.b_qkv + D, fused ? 1 : acc, red_side, red_bytes, sst));
-    } else if (!fused && !acc) {
-      // latent_enc with no context: key/value projections receive exact-zero gradients
-      MEBT_CUDA_OK(cudaMemsetAsync(g.w_qkv + size_t(D) * D, 0, size_t(2) * D * D * 4, sst));
-      MEBT_CUDA_OK(cudaMemsetAsync(g.b_qkv + D, 0, size_t(2) * D * 4, sst));
+    {
+      WgradDesc wd[5];
+      int n = 0;
+      wd[n++] = WgradDesc{d_mlp, D, S + s.u, 4 * D, g.w_fc2, 4 * D, D, 4 * D, rq, acc};
+      wd[n++] = WgradDesc{da, 4 * D, S + s.h, D, g.w_fc1, D, 4 * D, D, rq, acc};
+      wd[n++] = WgradDesc{d_proj, D, S + s.att, D, g.w_proj, D, D, D, rq, acc};
+      wd[n++] = WgradDesc{dqkv, qw, S + s.qn, D, g.w_qkv, D, qw, D, rq, acc};
+      // key|value rows of a separately projected key source: disjoint from the query rows unless the block also
+      // projected keys / values from its own stream (lt2l), in which case they are added by a second launch
+      if (rk > 0 && !fused) wd[n++] = WgradDesc{dkv, 2 * D, S + s.kn, D, g.w_qkv + size_t(D) * D, D, 2 * D, D, rk, acc};
+      TRY(FORK());
+      TRY(gemm_grouped_wgrad(wd, n, sa));
+      if (rk > 0 && fused) {
+        const WgradDesc kv{dkv, 2 * D, S + s.kn, D, g.w_qkv + size_t(D) * D, D, 2 * D, D, rk, 1};
+        TRY(gemm_grouped_wgrad(&kv, 1, sa));
+      }
+      MEBT_CUDA_OK(cudaEventRecord(side.fc2_a[par], sa));
+      TRY(colsum(dqkv, qw, rq, qw, g.b_qkv, acc, red_b, red_bytes, sb));
+      if (rk > 0) {
+        TRY(colsum(dkv, 2 * D, rk, 2 * D, g.b_qkv + D, fused ? 1 : acc, red_b, red_bytes, sb));
+      } else if (!fused && !acc) {
+        // latent_enc with no context: key/value projections receive exact-zero gradients
+        MEBT_CUDA_OK(cudaMemsetAsync(g.w_qkv + size_t(D) * D, 0, size_t(2) * D * D * 4, sa));
+        MEBT_CUDA_OK(cudaMemsetAsync(g.b_qkv + D, 0, size_t(2) * D * 4, sb));
+      }
     }
     TRY(DGRAD(dqkv, qw, wqkv, D, dqn, rq, D, qw, dx, nullptr, 0, 0));                                       // dqn = dx + dQKV Wqkv
     if (rk > 0) TRY(DGRAD(dkv, 2 * D, w_kv, D, dkn, rk, D, 2 * D, nullptr, nullptr, 0, 0));
-    // the side stream must be done with d_out / da / dx / dqkv / dkv before they are overwritten
-    MEBT_CUDA_OK(cudaEventRecord(side.join, sst));
-    MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0));
-    // ---- ln1 on both streams ----
-    TRY(layernorm_bwd(dqn, q_in, reinterpret_cast<float*>(S + s.q_mean), reinterpret_cast<float*>(S + s.q_rstd), w.ln1_w,
-                      d_out, 0, g.ln1_w, g.ln1_b, acc, rq, D, red, red_bytes, st));                        // assigns d(q stream)
-    if (rk > 0)
-      TRY(layernorm_bwd(dkn, k_in, reinterpret_cast<float*>(S + s.k_mean), reinterpret_cast<float*>(S + s.k_rstd), w.ln1_w,
-                        d_k_stream, 1, g.ln1_w, g.ln1_b, 1, rk, D, red, red_bytes, st));                   // accumulates
+    // ---- ln1 on both streams ----  parameter gradients on side stream B; the dx kernels also write the masked copy
+    // an earlier block's GEMMs will read (nothing on the side streams reads d_out itself)
+    TRY(FORK());
+    TRY(layernorm_bwd_params(dqn, q_in, reinterpret_cast<float*>(S + s.q_mean), reinterpret_cast<float*>(S + s.q_rstd),
+                             g.ln1_w, g.ln1_b, acc, rq, D, red_b, red_bytes, sb));
+    {
+      const Owed o = owed_by(i, 0);
+      TRY(AWAIT_OWED(o));
+      TRY(layernorm_bwd_dx(dqn, q_in, reinterpret_cast<float*>(S + s.q_mean), reinterpret_cast<float*>(S + s.q_rstd), w.ln1_w,
+                           d_out, nullptr, rq, D, o.dst, &o.key, st));                                     // assigns d(q stream)
+    }
+    if (rk > 0) {
+      TRY(layernorm_bwd_params(dkn, k_in, reinterpret_cast<float*>(S + s.k_mean), reinterpret_cast<float*>(S + s.k_rstd),
+                               g.ln1_w, g.ln1_b, 1, rk, D, red_b, red_bytes, sb));
+      const Owed o = owed_by(i, 1);
+      TRY(AWAIT_OWED(o));
+      TRY(layernorm_bwd_dx(dkn, k_in, reinterpret_cast<float*>(S + s.k_mean), reinterpret_cast<float*>(S + s.k_rstd), w.ln1_w,
+                           d_k_stream, d_k_stream, rk, D, o.dst, &o.key, st));                             // accumulates
+    }
+    TRY(MARK(side.end_a[par], side.end_b[par]));
   }
+  // the caller's stream sees every gradient of this call (the all-reduce / optimizer is ordered after it)
+  TRY(JOIN());
   return MEBT_OK;
 }
 

@@ -58,6 +58,7 @@ struct GemmParams {
   float* partials;
   int* counters;
   int pair;                            // host-side only: launch the cta_group::2 (SM pair) variant
+  DropKey drop;                        // residual-site dropout applied to (acc + bias) before the residual add (thr 0: off)
 #ifdef MEBT_GEMM_TRACE
   long long* trace;                    // [grid][8] cycle counters (tools/gemm_bench.cu)
 #endif
@@ -332,6 +333,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int split = PAIR ? 0 : work % p.splits;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
+      const bool k_drop = p.drop.thr != 0;
+      const uint32_t drop_rk = drop_row_key(p.drop, uint32_t(row));
+      // keep factors of one 32-column unit of this thread's row (same (seed, site, row, column) function as
+      // dropout_rows_kernel, so that backward regenerates the mask the fused forward used)
+      auto apply_drop = [&](float (&v)[32], int col0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float f0, f1;
+          drop_pair(p.drop, drop_rk, uint32_t((col0 >> 1) + j), f0, f1);
+          v[2 * j] *= f0; v[2 * j + 1] *= f1;
+        }
+      };
       // stage the tile's bias slice in shared memory once (one L2 round trip per tile instead of one per chunk)
       float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
       TR_BEGIN;
@@ -387,6 +400,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
         }
+        if (k_drop) apply_drop(v, col);
         if (p.gelu) {
           if (p.aux != nullptr && row_ok) {      // keep the pre-activation for the backward pass
             uint4* a4 = reinterpret_cast<uint4*>(p.aux + size_t(row) * p.ldaux + col);
@@ -482,6 +496,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
         }
+        if (k_drop) apply_drop(v, n0 + u * 32);
         if (k_gelu) {
           if (aux_out) {                                       // keep the pre-activation for the backward pass
             uint8_t* row_a = slots + ((2 * g + 1) & 3) * EPI_SLOT_BYTES + (q * 32 + lane) * 128;
@@ -688,6 +703,9 @@ int dispatch_major(int a_mn, int b_mn, const void* A, const void* B, const GemmP
 int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
                   int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
                   cudaStream_t stream);
+int gemm_bf16_drop(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                   int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
+                   const DropKey* drop, cudaStream_t stream);
 
 // Split-K scratch: the only device memory the library owns (partials are consumed inside the launch that wrote
 // them; the per-tile counters are returned to zero by the CTA that completes the tile).  Launches that use it are
@@ -719,6 +737,15 @@ int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn
 int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
                   int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
                   cudaStream_t stream) {
+  return gemm_bf16_drop(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, bias, residual, ldres, aux, ldaux, flags, nullptr,
+                        stream);
+}
+
+// C = drop(A B^T + bias) + residual: the epilogue multiplies (acc + bias) by the keep factors of `drop` (nullptr or
+// thr == 0: none) before the residual add - nn.Dropout on the proj / mlp outputs (gpt.py:140,154) without a launch.
+int gemm_bf16_drop(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                   int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
+                   const DropKey* drop, cudaStream_t stream) {
   MEBT_REQUIRE(M > 0 && N > 0 && K > 0, MEBT_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   MEBT_REQUIRE(N % 64 == 0, MEBT_ERR_SHAPE, "gemm: N=%d must be a multiple of 64", N);
   MEBT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, MEBT_ERR_SHAPE, "gemm: lda/ldb must be multiples of 8 elements");
@@ -744,6 +771,11 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
   MEBT_REQUIRE(!(p.dgelu && residual != nullptr) && !(out_fp32 && (p.dgelu || residual != nullptr)), MEBT_ERR_UNSUPPORTED,
                "gemm: the epilogue reads one bf16 operand (residual or gelu' input) and only with bf16 output");
   p.in_kind = residual != nullptr ? 1 : (p.dgelu ? 2 : 0);
+  p.drop = DropKey{0u, 0u, 0u, 1.f};
+  if (drop != nullptr && drop->thr != 0) {
+    MEBT_REQUIRE(!p.gelu && !p.dgelu && !out_fp32, MEBT_ERR_UNSUPPORTED, "gemm: dropout epilogue only on plain bf16 outputs");
+    p.drop = *drop;
+  }
 #ifdef MEBT_GEMM_TRACE
   p.trace = g_gemm_trace;
 #endif

@@ -46,11 +46,16 @@ def _versions(module: nn.Module):
     return (_lib.write_epoch(),) + tuple((p.data_ptr(), p._version) for p in module.parameters())
 
 
-def _check_no_dropout(module: nn.Module, *ps):
-    if module.training and any(p > 0 for p in ps):
-        raise NotImplementedError(
-            "mebt_b200: dropout in training mode is not implemented on the CUDA path; use p = 0 "
-            "(taichi / ucf configs) or eval mode")
+def _dropout_seed(module: nn.Module, *ps):
+    """None in eval mode / with p = 0; else a fresh 62-bit seed for the counter-based masks of this call, drawn from
+    torch's CPU generator (so `torch.manual_seed` pins the masks the way it pins nn.Dropout's)."""
+    if not module.training or not any(p > 0 for p in ps):
+        return None
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+# stem sites of GPT.forward's embd dropout (sos_emb, contexts, targets; gpt.py:239-241) - the training engine's values
+STEM_SITES = {"lat": 1 << 20, "ctx": (1 << 20) + 1, "tgt": (1 << 20) + 2}
 
 
 class CrossAttention(nn.Module):
@@ -82,13 +87,16 @@ class CrossAttention(nn.Module):
         reference path, transformer.py:281,321)."""
         if torch.is_tensor(attn_bias) or attn_bias not in (0, 0.0, None):
             raise NotImplementedError("mebt_b200: a non-zero attn_bias is dead code in the reference and unsupported")
-        _check_no_dropout(self, self.attn_drop.p, self.resid_drop.p)
+        seed = _dropout_seed(self, self.attn_drop.p, self.resid_drop.p)
         B, NQ, D = query.shape
         NK = key.shape[1]
         w_qkv, b_qkv, w_proj, b_proj = self._weights()
         lw = LayerWeights("none", None, None, None, None, w_qkv, b_qkv, w_proj, b_proj, None, None, None, None)
-        att = attention_core(lw, self.n_head, B, _as_rows(query), _as_rows(key) if NK > 0 else None, NK)
+        att = attention_core(lw, self.n_head, B, _as_rows(query), _as_rows(key) if NK > 0 else None, NK,
+                             attn_p=self.attn_drop.p if seed is not None else 0.0, attn_seed=seed or 0)
         y = ops.gemm(att, w_proj, b_proj)
+        if seed is not None and self.resid_drop.p > 0:           # attn_drop on the probabilities, resid_drop on the output
+            ops.dropout_rows_(y, self.resid_drop.p, seed, 1)
         return y.view(B, NQ, D).to(query.dtype), None, None, None
 
 
@@ -124,11 +132,12 @@ class Block(nn.Module):
         return lw
 
     def forward(self, sos_emb, contexts, targets, mask_emb=None, attn_bias=None):
-        _check_no_dropout(self, self.attn.attn_drop.p, self.attn.resid_drop.p, self.mlp[3].p)
+        seed = _dropout_seed(self, self.attn.attn_drop.p, self.attn.resid_drop.p, self.mlp[3].p)
+        drop = (self.attn.attn_drop.p, self.attn.resid_drop.p, seed, 0) if seed is not None else None
         B, NS, C = sos_emb.size()
         NC, NT = contexts.size(1), targets.size(1)
         lat, ctx, tgt = block_forward(self.layer_weights(), self.attn.n_head, B, _as_rows(sos_emb), _as_rows(contexts),
-                                      _as_rows(targets))
+                                      _as_rows(targets), drop=drop)
         dt = sos_emb.dtype
         return (lat.view(B, NS, C).to(dt), ctx.view(B, NC, C).to(dt), tgt.view(B, NT, C).to(dt), attn_bias, None)
 
@@ -183,10 +192,31 @@ class GPT(nn.Module):
     def forward_rows(self, B, lat, ctx, tgt, logits_dtype=torch.float32):
         """Stack on 2-D streams -> logits [B*NT, V] (no reshapes / dtype round trips).  bf16 streams take the tcgen05
         engine (1e-2 tolerance); fp32 streams take the fp32-accurate path (1e-4 tolerance, `precision = "fp32"`)."""
-        _check_no_dropout(self, self.config.embd_pdrop, self.config.resid_pdrop, self.config.attn_pdrop)
+        seed = _dropout_seed(self, self.config.embd_pdrop, self.config.resid_pdrop, self.config.attn_pdrop)
+        if seed is not None:
+            return self._forward_rows_dropout(B, lat, ctx, tgt, logits_dtype, seed)
         if lat.dtype == torch.float32:
             return stack_forward_f32(self.precise_pack(), B, lat, ctx, tgt).to(logits_dtype)
         return stack_forward(self.weight_pack(), B, lat, ctx, tgt, logits_dtype)
+
+    def _forward_rows_dropout(self, B, lat, ctx, tgt, logits_dtype, seed):
+        """Training-mode forward with the configured dropout (`model.train(); model(x, c, indices=...)` with the STL
+        yaml's p = 0.1, gpt.py:238-248): embd dropout on the three streams, attention / proj / mlp dropout inside
+        every block, block by block on the kernels (same sites as the one-call training engine, so one seed gives one
+        set of masks on both paths).  Inference-only output (no autograd graph): training runs through
+        `training_step` / `TrainState`."""
+        cfg = self.config
+        if lat.dtype != torch.bfloat16:
+            raise NotImplementedError('mebt_b200: training-mode dropout runs on the bf16 path (precision = "bf16")')
+        if cfg.embd_pdrop > 0:
+            for name, t in (("lat", lat), ("ctx", ctx), ("tgt", tgt)):
+                ops.dropout_rows_(t, cfg.embd_pdrop, seed, STEM_SITES[name])
+        for i, blk in enumerate(self.blocks):
+            lat, ctx, tgt = block_forward(blk.layer_weights(), cfg.n_head, B, lat, ctx, tgt,
+                                          drop=(cfg.attn_pdrop, cfg.resid_pdrop, seed, 4 * i))
+        xf = ops.layernorm(tgt, self.ln_f.weight.detach().float().contiguous(), self.ln_f.bias.detach().float().contiguous())
+        w_head = self.weight_pack().w_head
+        return ops.gemm(xf, w_head, out_dtype=logits_dtype)
 
     def forward(self, sos_emb, contexts, targets, mask_emb, attn_bias=None, debug=False):
         B, NT = targets.shape[0], targets.shape[1]

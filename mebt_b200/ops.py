@@ -279,6 +279,24 @@ def gemm_aux(a, b, aux, bias=None, residual=None, gelu=False, dgelu=False, out=N
     return out
 
 
+def grouped_wgrad(problems):
+    """problems: list of (dY [rows, n_out] bf16, X [rows, k_in] bf16, dW [n_out, k_in] fp32, accumulate) -> one launch
+    computing every dW (+)= dY^T X (disjoint outputs)."""
+    n = len(problems)
+    descs = (_lib.WgradDesc * n)()
+    for d, (dy, x, dw, acc) in zip(descs, problems):
+        _need_cuda(dy, x, dw)
+        if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dw.dtype != torch.float32:
+            raise MebtError("grouped_wgrad: dY / X must be bf16 and dW fp32")
+        rows, n_out, ld_dy = _rows2d(dy)
+        rows_x, k_in, ldx = _rows2d(x)
+        if rows != rows_x or tuple(dw.shape) != (n_out, k_in):
+            raise MebtError("grouped_wgrad: shape mismatch")
+        d.dY, d.ld_dy, d.X, d.ldx, d.dW, d.ldw = dy.data_ptr(), ld_dy, x.data_ptr(), ldx, dw.data_ptr(), dw.stride(0)
+        d.n_out, d.k_in, d.rows, d.accumulate = n_out, k_in, rows, int(bool(acc))
+    call("mebt_gemm_grouped_wgrad", descs, n, _stream())
+
+
 def colsum(x, out=None, accumulate=False):
     """out[n] (+)= sum_rows x[:, n]; x bf16 [rows, N]."""
     _need_cuda(x)

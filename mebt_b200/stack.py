@@ -103,9 +103,11 @@ class WeightPack:
         return live
 
 
-def attention_core(w: LayerWeights, n_head: int, B: int, qn, kn1, nk1: int, kn2=None, nk2: int = 0, q_is_k1=False):
+def attention_core(w: LayerWeights, n_head: int, B: int, qn, kn1, nk1: int, kn2=None, nk2: int = 0, q_is_k1=False,
+                   attn_p: float = 0.0, attn_seed: int = 0):
     """q/k/v projections + attention for one block.  qn: ln1(query) [B*NQ, D]; kn1/kn2: ln1(key sources).
-    q_is_k1: the first key source is the query stream itself (latent_self, lt2l, maskgit) -> one fused QKV GEMM."""
+    q_is_k1: the first key source is the query stream itself (latent_self, lt2l, maskgit) -> one fused QKV GEMM.
+    attn_p > 0: training-mode dropout on the attention probabilities (attn_drop, gpt.py:136)."""
     D = qn.shape[1]
     NQ = qn.shape[0] // B
     if q_is_k1:
@@ -120,39 +122,51 @@ def attention_core(w: LayerWeights, n_head: int, B: int, qn, kn1, nk1: int, kn2=
     kv2 = None
     if nk2 > 0:
         kv2 = ops.gemm(kn2, w.w_qkv[D:], w.b_qkv[D:])
-    return ops.attention(q_buf, q_col, kv1, k1c, v1c, nk1, kv2, 0, D, nk2, B, n_head, NQ)
+    return ops.attention(q_buf, q_col, kv1, k1c, v1c, nk1, kv2, 0, D, nk2, B, n_head, NQ, drop_p=attn_p,
+                         drop_seed=attn_seed)
 
 
-def block_forward(w: LayerWeights, n_head: int, B: int, lat, ctx, tgt):
-    """One Block (gpt.py:159-195) on 2-D bf16 streams; returns the updated (lat, ctx, tgt)."""
+def block_forward(w: LayerWeights, n_head: int, B: int, lat, ctx, tgt, drop=None):
+    """One Block (gpt.py:159-195) on 2-D bf16 streams; returns the updated (lat, ctx, tgt).
+    drop = (attn_p, resid_p, seed, site): training-mode dropout with the training engine's sites (site + 0 attention
+    probabilities, + 1 proj output, + 2 mlp output; csrc/engine_train.cu), so that for the same seed the op-by-op
+    module path and `mebt_stack_forward_train_dropout` draw the same masks."""
     mode = w.mode
+    attn_p, resid_p, seed, site = drop if drop is not None else (0.0, 0.0, 0, 0)
+    att_kw = dict(attn_p=attn_p, attn_seed=seed + site)
     L = lat.shape[0] // B
     NC = ctx.shape[0] // B
     NT = tgt.shape[0] // B
     ln1 = lambda t: ops.layernorm(t, w.ln1_w, w.ln1_b)
     if mode == "latent_enc":
         qn = ln1(lat)
-        att = attention_core(w, n_head, B, qn, ln1(ctx) if NC > 0 else None, NC)
+        att = attention_core(w, n_head, B, qn, ln1(ctx) if NC > 0 else None, NC, **att_kw)
     elif mode == "latent_self":
         qn = ln1(lat)
-        att = attention_core(w, n_head, B, qn, None, L, q_is_k1=True)
+        att = attention_core(w, n_head, B, qn, None, L, q_is_k1=True, **att_kw)
     elif mode == "latent_dec":
         qn = ln1(tgt)
-        att = attention_core(w, n_head, B, qn, ln1(lat), L)
+        att = attention_core(w, n_head, B, qn, ln1(lat), L, **att_kw)
     elif mode == "lt2l":
         qn = ln1(lat)
-        att = attention_core(w, n_head, B, qn, None, L, ln1(tgt) if NT > 0 else None, NT, q_is_k1=True)
+        att = attention_core(w, n_head, B, qn, None, L, ln1(tgt) if NT > 0 else None, NT, q_is_k1=True, **att_kw)
     elif mode == "maskgit":
         D = lat.shape[1]
         both = torch.cat([ctx.view(B, NC, D), tgt.view(B, NT, D)], 1).reshape(B * (NC + NT), D)
         qn = ln1(both)
-        att = attention_core(w, n_head, B, qn, None, NC + NT, q_is_k1=True)
+        att = attention_core(w, n_head, B, qn, None, NC + NT, q_is_k1=True, **att_kw)
     else:
         raise ValueError(f"unknown block mode {mode!r}")
-    x = ops.gemm(att, w.w_proj, w.b_proj, residual=qn)            # x = ln1(q) + proj(attn)
-    h = ops.layernorm(x, w.ln2_w, w.ln2_b)
-    u = ops.gemm(h, w.w_fc1, w.b_fc1, gelu=True)
-    x = ops.gemm(u, w.w_fc2, w.b_fc2, residual=x)                 # x + mlp(ln2(x))
+    if resid_p > 0.0:                                             # x = ln1(q) + drop(proj(attn)), x + drop(mlp(ln2(x)))
+        x = ops.dropout_rows_(ops.gemm(att, w.w_proj, w.b_proj), resid_p, seed, site + 1, resid=qn)
+        h = ops.layernorm(x, w.ln2_w, w.ln2_b)
+        u = ops.gemm(h, w.w_fc1, w.b_fc1, gelu=True)
+        x = ops.dropout_rows_(ops.gemm(u, w.w_fc2, w.b_fc2), resid_p, seed, site + 2, resid=x)
+    else:
+        x = ops.gemm(att, w.w_proj, w.b_proj, residual=qn)        # x = ln1(q) + proj(attn)
+        h = ops.layernorm(x, w.ln2_w, w.ln2_b)
+        u = ops.gemm(h, w.w_fc1, w.b_fc1, gelu=True)
+        x = ops.gemm(u, w.w_fc2, w.b_fc2, residual=x)             # x + mlp(ln2(x))
     if mode in ("latent_enc", "latent_self", "lt2l"):
         lat = x
     elif mode == "latent_dec":

@@ -92,10 +92,12 @@ class TrainState:
         self._saved = None
         self._bwd_ws = None
         self._ctx = None
+        self._pending = False             # a forward whose backward has not run yet
         self._step_id = 0                 # stamps the saved activations: one forward owns them until its backward ran
         self._grads_dirty = False         # the flat gradient buffer holds a gradient no optimizer step / zero_grad consumed
         self._grad_torch_version = self.flat_grad._version
         self.comm_stream = torch.cuda.Stream(device=self.device)
+        self.update_ctas = 48             # grid of the background AdamW kernels (train_step(overlap_update=True))
         model.__dict__["_train_state"] = self          # found again by Net2NetTransformer.training_step
 
     # ---- pointer tables for the C engine ---------------------------------------------------------------------------
@@ -177,6 +179,7 @@ class TrainState:
              lat.data_ptr(), ctx.data_ptr(), tgt.data_ptr(), logits.data_ptr(), ops._DT[logits_dtype], saved.data_ptr(),
              saved.numel(), ctypes.byref(drop) if drop is not None else None, st)
         self._step_id += 1
+        self._pending = True
         self._ctx = (B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt, drop, embd_p, seed)
         return logits
 
@@ -196,7 +199,7 @@ class TrainState:
         all-reduced (averaged) on a side stream while the next chunk runs.  With a `FlatAdamW` passed as `optimizer` the
         parameter update of a finished chunk is issued on that side stream too, right behind its all-reduce: blocks
         that backward has left are never read again in this step, so their AdamW overlaps the rest of backward."""
-        if self._ctx is None:
+        if not self._pending:
             raise MebtError("backward: no forward is pending (each forward's activations serve exactly one backward)")
         B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt, drop, embd_p, seed = self._ctx
         if dlogits.dtype != torch.bfloat16 or not dlogits.is_contiguous():
@@ -230,7 +233,7 @@ class TrainState:
                 if le == n:
                     works.append(self._all_reduce_async(*self.head_slice, cur))
             if optimizer is not None:
-                self._update_async(optimizer, lo, hi, cur)
+                self._update_async(optimizer, lo, hi, cur, background=ci > 0)
                 if le == n:
                     self._update_async(optimizer, *self.head_slice, cur)
         if embd_p > 0.0:                                        # backward of the stem dropout: the same masks
@@ -242,21 +245,23 @@ class TrainState:
         if world_size > 1:
             works.append(self._all_reduce_async(*self.emb_slice, cur))
         if optimizer is not None:
-            self._update_async(optimizer, *self.emb_slice, cur)
+            self._update_async(optimizer, *self.emb_slice, cur, background=False)
         if world_size > 1 or optimizer is not None:
             cur.wait_stream(self.comm_stream)
         self.relink_grads()
-        self._ctx = None
+        self._pending = False
         self._grads_dirty = True
         self._grad_torch_version = self.flat_grad._version
         return works
 
-    def _update_async(self, optimizer, lo, hi, producer_stream):
+    def _update_async(self, optimizer, lo, hi, producer_stream, background=True):
         """AdamW + operand refresh of parameters [lo, hi) on the side stream, after the kernels (and the all-reduce,
-        which runs on the same stream) that produced their gradients."""
+        which runs on the same stream) that produced their gradients.  background: as a few-CTA kernel that leaves the
+        SMs and the L2 to the backward kernels it overlaps (`self.update_ctas`); the last ranges of a step, which
+        nothing overlaps, take the full grid."""
         self.comm_stream.wait_stream(producer_stream)
         with torch.cuda.stream(self.comm_stream):
-            optimizer.step_range(lo, hi)
+            optimizer.step_range(lo, hi, self.update_ctas if background else 0)
 
     def _all_reduce_async(self, lo, hi, producer_stream):
         """One gradient bucket: waits for the kernels that produced it, then averages it over ranks on the side
@@ -354,17 +359,17 @@ class FlatAdamW:
     def begin_step(self):
         self.steps += 1
 
-    def step_range(self, lo, hi):
+    def step_range(self, lo, hi, max_ctas=0):
         """The update of parameters [lo, hi) of the flat buffer (tensor-aligned bounds) for the step opened by
-        `begin_step`, on the current stream."""
+        `begin_step`, on the current stream.  max_ctas > 0: as a background kernel of that many CTAs."""
         ts = self.ts
         if lo % (1 << self.shift) or (hi - lo) % 4:
             raise MebtError("FlatAdamW.step_range: bounds must be tensor boundaries of the flat buffer")
         lr = float(self.param_groups[0]["lr"])
-        call("mebt_adamw_flat", ts.flat.data_ptr() + 4 * lo, ts.flat_grad.data_ptr() + 4 * lo, self.m.data_ptr() + 4 * lo,
+        call("mebt_adamw_flat_bg", ts.flat.data_ptr() + 4 * lo, ts.flat_grad.data_ptr() + 4 * lo, self.m.data_ptr() + 4 * lo,
              self.v.data_ptr() + 4 * lo, ts.flat_bf16.data_ptr() + 2 * lo, self.flags.data_ptr() + (lo >> self.shift),
              self.shift, hi - lo, lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.steps,
-             torch.cuda.current_stream().cuda_stream)
+             int(max_ctas), torch.cuda.current_stream().cuda_stream)
         _lib.bump_write_epoch()                # the masters changed behind torch's version counters: derived operands are stale
         ts._grads_dirty = False
 
@@ -403,7 +408,7 @@ class TrainStepFunction(torch.autograd.Function):
         if dlogits is None:
             raise MebtError("training_step: backward through the same step twice")
         ts = ctx.ts
-        if ts._step_id != ctx.step_id or ts._ctx is None:
+        if ts._step_id != ctx.step_id or not ts._pending:
             raise MebtError("training_step: another forward ran before this loss's backward; the saved activations belong "
                             "to the later step (call loss.backward() before the next training_step)")
         dlogits.mul_(g_loss.to(dlogits.dtype))                   # 1.0 unless the caller scaled the loss

@@ -456,6 +456,47 @@ def sample_maskgit(P, cfg, x, rng, temperature=1.0, top_k=None, top_p=None, n_st
     return x, ctx_idx, tgt_idx
 
 
+def entropy_scores(probs: torch.Tensor) -> torch.Tensor:
+    """The reveal score of entp_sample, transformer.py:499-500: sum_v (p - log(p + 1e-8)), subtracted from its row
+    maximum (so the most peaked distribution scores highest... and the flattest one exactly 0)."""
+    s = -(-probs + torch.log(probs + 1e-8)).sum(-1)
+    return s.max(-1, keepdim=True)[0] - s
+
+
+def sample_entp(P, cfg, x, rng, temperature=1.0, top_k=None, top_p=None, n_steps=8, strategy="maskgit",
+                schedule_name="cosine"):
+    """Net2NetTransformer.entp_sample, transformer.py:449-542, with MaskGen.generate_next_mask_entp
+    (mask_sampler.py:248-303): like `sample`, but tokens are revealed in the order of `entropy_scores`, the re-masking
+    temperature is 0 (the Exp(1) draw is still consumed), the mask size is re-derived from the schedule inside
+    generate_next_mask_entp (no n_masked_toks argument), and only 'random' replaces the scores by randn ('bootstrap'
+    keeps them and reveals one token per step)."""
+    B = x.shape[0]
+    x = x.reshape(B, -1)
+    N = x.shape[1]
+    ctx_idx = torch.empty(B, 0, dtype=torch.long)
+    tgt_idx = torch.arange(N).repeat(B, 1)
+    for t_next in np.linspace(0, 1, n_steps + 1)[1:]:
+        t = torch.full((B,), fill_value=t_next)
+        n_masked_t = torch.ceil(schedule(schedule_name, t) * N)
+        if int((n_masked_t > tgt_idx.shape[-1]).sum()) == B:
+            continue
+        logits = reconstruct_mask(P, cfg, x, ctx_idx, tgt_idx)
+        ids, probs = sample_from_logits(logits, temperature, top_k, top_p, rng.exponential(logits.shape))
+        scores = entropy_scores(probs)
+        x = _write_back(x, tgt_idx, ids)
+        NC, NT = ctx_idx.shape[1], tgt_idx.shape[1]
+        randn = rng.randn(scores.shape) if strategy == "random" else None        # mask_sampler.py:267-269
+        n_masked = int(torch.ceil(schedule(schedule_name, t)[0] * (NC + NT)).to(torch.long))   # :273-275
+        if strategy == "bootstrap":
+            n_masked = NT - 1
+        if NC + NT - n_masked <= NC:
+            continue
+        q = rng.exponential(scores.shape)
+        ctx_idx, tgt_idx = generate_next_mask(ctx_idx, tgt_idx, scores, n_masked, 0.0, q,
+                                              "random" if strategy == "random" else "maskgit", randn)
+    return x, ctx_idx, tgt_idx
+
+
 # ------------------------------------------------------------------------------------------------
 # VQGAN codebook (eval path)
 # ------------------------------------------------------------------------------------------------

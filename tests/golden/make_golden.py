@@ -229,6 +229,27 @@ def gen_sampling(cfg_name, B, wseed, seed):
     save(f"sampling_{cfg_name}", cfg, **arrays)
 
 
+def gen_entp(cfg_name, B, wseed, seed):
+    """Net2NetTransformer.entp_sample (transformer.py:449-542) in its three strategies, and `sample(debug=True)`'s
+    probability bookkeeping (transformer.py:396,428-437): the per-position top-8 of the dense [B,N,16384] tensor."""
+    cfg = CONFIGS[cfg_name]
+    model, _ = build_reference(cfg, "cosine", wseed)
+    x0 = torch.zeros((B, *cfg["shape"]), dtype=torch.long)
+    arrays = dict(wseed=wseed, seed=seed, B=B)
+    for strat, steps in (("maskgit", 5), ("random", 4), ("bootstrap", 3)):
+        torch.manual_seed(seed)
+        ids, ctx, tgt = model.entp_sample(x0, None, temperature=1.0, top_k=None, top_p=None, n_steps=steps, strategy=strat)
+        arrays[f"entp_{strat}_ids"], arrays[f"entp_{strat}_ctx"], arrays[f"entp_{strat}_tgt"] = ids, ctx, tgt
+    torch.manual_seed(seed + 1)
+    out = model.sample(x0, None, temperature=0.9, top_k=64, top_p=None, n_steps=4, strategy="maskgit",
+                       context_temperature=4.5, debug=True)
+    probs = out[5]
+    top = probs.topk(8, -1)
+    arrays.update(debug_ids=out[0], debug_ctx=out[1], debug_tgt=out[2], debug_top_p=top.values, debug_top_i=top.indices,
+                  debug_chosen_p=probs.gather(-1, out[0].unsqueeze(-1)).squeeze(-1))
+    save(f"entp_{cfg_name}", cfg, **arrays)
+
+
 def gen_sample_from_logits():
     """sample_from_logits / top-k / top-p / gumbel on random logits: ids + probs digests."""
     from mebt.transformer import sample_from_logits
@@ -436,6 +457,7 @@ def main():
     gen_grads_dropout("micro", 2, wseed=1, dseed=2, t=0.4, p=0.1, mseed=11)
     gen_sampling("micro", 2, wseed=1, seed=9)
     gen_sampling("tiny", 2, wseed=1, seed=9)
+    gen_entp("micro", 2, wseed=1, seed=13)
     gen_pipelines()
 
 
@@ -443,6 +465,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pipelines":
         sys.path.insert(1, str(REPO))
         gen_pipelines()
+    elif len(sys.argv) > 1 and sys.argv[1] == "entp":        # only the fixture added in round 2
+        install_stubs()
+        sys.path.insert(0, REF)
+        sys.path.insert(1, str(REPO))
+        torch.set_num_threads(8)
+        gen_entp("micro", 2, wseed=1, seed=13)
     elif len(sys.argv) > 1 and sys.argv[1] == "dropout":     # only the fixture added after the first generation
         install_stubs()
         sys.path.insert(0, REF)

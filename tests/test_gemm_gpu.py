@@ -85,3 +85,36 @@ def test_gemm(M, N, K, a_mn, b_mn, flags, bias, resid):
     ops.gemm(A_st, B_st, bias_t, res_t, gelu=bool(flags & GELU), out=C2, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn),
              accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK | NO_PAIR | PAIR))
     assert torch.equal(C, C2)
+
+
+@pytest.mark.parametrize("rows_q,rows_k,D", [(1536, 3072, 1024), (3072, 1536, 1024), (200, 72, 256)])
+def test_grouped_wgrad(rows_q, rows_k, D):
+    """One launch for the five weight gradients of a Block (csrc/gemm_grouped.cu) against torch fp32 matmuls of the same
+    bf16 operands; strided operands (dqkv inside a [rows, 3D] buffer), accumulation, ragged reductions, and the fused
+    dropout epilogue's companion: bit-identical results to the five separate mebt_gemm_bf16 launches."""
+    from mebt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows_q + rows_k)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    d_mlp, u = rnd(rows_q, D), rnd(rows_q, 4 * D)
+    da, h = rnd(rows_q, 4 * D), rnd(rows_q, D)
+    d_proj, att = rnd(rows_q, D), rnd(rows_q, D)
+    dqkv_buf, qn = rnd(rows_q, 3 * D), rnd(rows_q, D)
+    dq = dqkv_buf[:, :D]                                        # a column slice: row stride 3D
+    dkv, kn = rnd(rows_k, 2 * D), rnd(rows_k, D)
+    w_qkv = torch.full((3 * D, D), float("nan"), device="cuda")
+    outs = [torch.full((D, 4 * D), float("nan"), device="cuda"), torch.full((4 * D, D), float("nan"), device="cuda"),
+            torch.randn(D, D, device="cuda", generator=g), w_qkv[:D], w_qkv[D:]]
+    prev_proj = outs[2].clone()
+    problems = [(d_mlp, u, outs[0], False), (da, h, outs[1], False), (d_proj, att, outs[2], True), (dq, qn, outs[3], False),
+                (dkv, kn, outs[4], False)]
+    ops.grouped_wgrad(problems)
+    torch.cuda.synchronize()
+    for i, (dy, x, dw, acc) in enumerate(problems):
+        ref = dy.float().t() @ x.float()
+        if acc:
+            ref = ref + prev_proj
+        err = (dw - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 2e-3, (i, err)
+    # same arithmetic as the stand-alone GEMM (fp32 accumulation in TMEM over the same k-blocks in the same order)
+    single = ops.gemm(d_mlp, u, out_dtype=torch.float32, a_mn_major=True, b_mn_major=True, flags_extra=16 | 128)
+    assert torch.equal(single, outs[0])

@@ -135,7 +135,16 @@ def test_sample_logits_vs_reference_golden():
             assert torch.allclose(probs.sum(-1), torch.ones(3, 40), atol=1e-5)
         ref_ids = torch.from_numpy(z[f"{tag}_ids"])
         mism = (ids != ref_ids) & same_set
-        # bit-exact selection; a differing id is only tolerated as a documented float near-tie of the race
+        # bit-exact selection; a differing id is admitted only as a float near-tie of the race, proven in float64: the
+        # two candidates' keys p_i / q_i (p = softmax of the scaled logits) agree to NEAR_TIE relative - what separates
+        # the GPU's expf from the CPU's is a few fp32 ulps (1.2e-7 each)
+        NEAR_TIE = 1e-5
+        if mism.any():
+            p64 = torch.softmax(logits.double() / (T + 1e-8), -1)
+            k64 = p64 / q.double()
+            kg = k64.gather(-1, ids.unsqueeze(-1)).squeeze(-1)[mism]
+            kr = k64.gather(-1, ref_ids.unsqueeze(-1)).squeeze(-1)[mism]
+            assert ((kg / kr - 1).abs() < NEAR_TIE).all(), (tag, (kg / kr - 1).abs().max())
         assert mism.float().mean() <= 0.01, (tag, int(mism.sum()))
         ok = ~(ids != ref_ids) & same_set
         np.testing.assert_allclose(scores[ok].numpy(), z[f"{tag}_score"][ok.numpy()], rtol=2e-5, atol=1e-12)
@@ -175,8 +184,19 @@ def test_remask_sort_vs_reference_golden():
     n_new = z["gnm_next_ctx"].shape[1] - ctx.shape[1]
     nc, nt, order = ops.remask_sort(score.cuda(), ctx.cuda(), tgt.cuda(), n_new, 2.25, noise=q.cuda(), want_order=True)
     nc, nt = nc.cpu().numpy(), nt.cpu().numpy()
-    # powf on the GPU vs torch.pow on the CPU differ by ulps: adjacent near-equal keys may swap
-    assert (nc == z["gnm_next_ctx"]).mean() > 0.995 and (nt == z["gnm_next_tgt"]).mean() > 0.995
+    # powf on the GPU vs torch.pow on the CPU differ by ulps: near-equal keys may swap.  Every position where the
+    # selection differs from the reference's is proven a near-tie in float64: the keys (s / sum s) / q^ctemp of the two
+    # tokens agree to NEAR_TIE relative.
+    NEAR_TIE = 1e-5
+    key64 = (score.double() / score.double().sum(-1, keepdim=True)) / q.double() ** 2.25
+    n_ctx0 = ctx.shape[1]
+    for got, ref in ((nc[:, n_ctx0:], z["gnm_next_ctx"][:, n_ctx0:]), (nt, z["gnm_next_tgt"])):
+        for b in range(got.shape[0]):
+            of = {int(t): float(k) for t, k in zip(tgt[b].tolist(), key64[b].tolist())}
+            for a, r in zip(got[b][got[b] != ref[b]].tolist(), ref[b][got[b] != ref[b]].tolist()):
+                assert abs(of[a] / of[r] - 1.0) < NEAR_TIE, (a, r, of[a], of[r])
+    assert np.array_equal(nc[:, :n_ctx0], z["gnm_next_ctx"][:, :n_ctx0])
+    assert (nc == z["gnm_next_ctx"]).mean() > 0.99 and (nt == z["gnm_next_tgt"]).mean() > 0.99
     assert sorted(np.concatenate([nc[0], nt[0]]).tolist()) == list(range(1024))
 
 
@@ -199,6 +219,12 @@ def test_remask_sort_order_property(NT, ctemp):
     assert (sorted_keys[:, 1:] <= sorted_keys[:, :-1] * (1 + 1e-5)).all()       # descending up to pow ulps
     assert (order.sort(1).values == torch.arange(NT)).all()                      # a permutation
     assert (order == ref).float().mean() > 0.99
+    # every differing position holds two tokens whose float64 keys agree to 1e-5 relative (a documented near-tie)
+    key64 = (score.double() / score.double().sum(-1, keepdim=True)) / q.double() ** ctemp
+    diff = order != ref
+    if diff.any():
+        kg, kr = key64.gather(1, order)[diff], key64.gather(1, ref)[diff]
+        assert ((kg / kr - 1).abs() < 1e-5).all(), (kg / kr - 1).abs().max()
     if ctemp == 0.0:
         assert torch.equal(order, ref)                                            # no pow involved: bit-exact
     assert torch.equal(nc.cpu(), torch.cat([ctx, tgt.gather(1, order[:, :n_new])], 1))

@@ -160,6 +160,19 @@ def test_samplers_bit_exact(name):
         assert (tgt.numpy() == z[f"sample_{strat}_tgt"]).all(), strat
 
 
+def test_entp_sampler_bit_exact():
+    """oracle.sample_entp against the unmodified reference's entp_sample (fixture entp_micro.npz), all three strategies."""
+    z, cfg = load_golden("entp_micro")
+    P = O.make_weights(cfg, int(z["wseed"]))
+    B, seed = int(z["B"]), int(z["seed"])
+    x0 = torch.zeros(B, *cfg["shape"], dtype=torch.long)
+    for strat, steps in (("maskgit", 5), ("random", 4), ("bootstrap", 3)):
+        ids, ctx, tgt = O.sample_entp(P, cfg, x0, O.TorchRng(seed), n_steps=steps, strategy=strat, schedule_name="cosine")
+        assert (ids.numpy() == z[f"entp_{strat}_ids"]).all(), strat
+        assert (ctx.numpy() == z[f"entp_{strat}_ctx"]).all(), strat
+        assert (tgt.numpy() == z[f"entp_{strat}_tgt"]).all(), strat
+
+
 def test_codebook_bit_exact():
     z, _ = load_golden("codebook")
     torch.manual_seed(int(z["cb_seed"]))

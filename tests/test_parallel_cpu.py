@@ -35,6 +35,25 @@ def _worker(rank, world, port, ret):
     ref = flat.clone()
     dist.broadcast(ref, 0)
     assert torch.equal(ref, flat)
+    # sharded exchange (fused flat AdamW): reduce-scatter -> update of the own shard -> all-gather of the result
+    g2 = torch.Generator().manual_seed(200 + rank)
+    grads = torch.randn(64, generator=g2)
+    other_g = torch.randn(64, generator=torch.Generator().manual_seed(200 + (1 - rank)))
+    params = torch.arange(64, dtype=torch.float32)
+    for lo, hi in [(40, 60), (60, 64), (20, 40), (0, 20)]:
+        a, b = P.shard_bounds(lo, hi, rank, world)
+        shard = P.reduce_scatter_mean_(grads[lo:hi])
+        assert shard.data_ptr() == grads[a:b].data_ptr()
+        assert torch.allclose(grads[a:b], (grads.new_tensor(0) + (other_g[a:b] + torch.randn(64, generator=torch.Generator().manual_seed(200 + rank))[a:b]) / 2))
+        params[a:b] -= 0.5 * grads[a:b]                       # "optimizer" on the shard only
+        P.all_gather_shards_(params[lo:hi])
+    mean = (torch.randn(64, generator=torch.Generator().manual_seed(200)) + torch.randn(64, generator=torch.Generator().manual_seed(201))) / 2
+    assert torch.allclose(params, torch.arange(64, dtype=torch.float32) - 0.5 * mean)
+    chk = params.clone()
+    dist.broadcast(chk, 0)
+    assert torch.equal(chk, params)                           # every rank ends with the same parameters
+    with pytest.raises(ValueError):
+        P.shard_bounds(0, 7, rank, world)
     # sampling: videos sharded by batch, per-rank RNG streams, results gathered on rank 0 for output only
     shard = P.shard_range(7, rank, world)
     ids = torch.full((len(shard), 4), rank, dtype=torch.long)
