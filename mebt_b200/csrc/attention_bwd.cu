@@ -403,29 +403,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }  // namespace
 }  // namespace mebt
 
-extern "C" {
-
-size_t mebt_latent_attention_bwd_workspace_bytes(int B, int H, int NQ) { return size_t(B) * H * NQ * sizeof(float); }
-
-int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0,
-                              int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, const void* O,
-                              int ldo, const void* dO, int lddo, const float* lse, void* dQ, int lddq, int dq_col0,
-                              void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2, int ldd2, int dk2_col0,
-                              int dv2_col0, int B, int H, int NQ, int head_dim, void* workspace, size_t workspace_bytes,
-                              void* stream) {
-  return mebt_latent_attention_bwd_dropout(Q, ldq, q_col0, KV1, ld1, k1_col0, v1_col0, NK1, KV2, ld2, k2_col0, v2_col0, NK2,
-                                           O, ldo, dO, lddo, lse, dQ, lddq, dq_col0, dKV1, ldd1, dk1_col0, dv1_col0, dKV2,
-                                           ldd2, dk2_col0, dv2_col0, B, H, NQ, head_dim, 0.f, 0ull, workspace,
-                                           workspace_bytes, stream);
-}
-
-int mebt_latent_attention_bwd_dropout(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
-                                      int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2,
-                                      const void* O, int ldo, const void* dO, int lddo, const float* lse, void* dQ,
-                                      int lddq, int dq_col0, void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2,
-                                      int ldd2, int dk2_col0, int dv2_col0, int B, int H, int NQ, int head_dim, float drop_p,
-                                      unsigned long long drop_seed, void* workspace, size_t workspace_bytes, void* stream) {
-  using namespace mebt;
+namespace mebt {
+// delta_ready: `workspace` already holds delta[b,h,q] = rowsum(dO .* O) (written by the epilogue of the GEMM that
+// produced dO, csrc/gemm.cu in_kind 3); otherwise the preprocess kernel computes it here.
+int latent_attention_bwd_launch(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
+                                int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2,
+                                const void* O, int ldo, const void* dO, int lddo, const float* lse, void* dQ,
+                                int lddq, int dq_col0, void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2,
+                                int ldd2, int dk2_col0, int dv2_col0, int B, int H, int NQ, int head_dim, float drop_p,
+                                unsigned long long drop_seed, void* workspace, size_t workspace_bytes, int delta_ready,
+                                void* stream) {
   MEBT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MEBT_ERR_SHAPE, "attention_bwd: dropout p = %f outside [0, 1)", drop_p);
   MEBT_REQUIRE(head_dim == 64, MEBT_ERR_UNSUPPORTED, "attention_bwd: head_dim %d unsupported", head_dim);
   MEBT_REQUIRE(B > 0 && H > 0 && NQ > 0 && NK1 >= 0 && NK2 >= 0, MEBT_ERR_SHAPE, "attention_bwd: bad shape");
@@ -434,8 +421,11 @@ int mebt_latent_attention_bwd_dropout(const void* Q, int ldq, int q_col0, const 
   MEBT_REQUIRE(ldq % 8 == 0 && lddo % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0, MEBT_ERR_SHAPE, "attention_bwd: strides");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* delta = static_cast<float*>(workspace);
-  int rc = attn_delta(dO, lddo, O, ldo, delta, B, H, NQ, st);
-  if (rc) return rc;
+  int rc = MEBT_OK;
+  if (!delta_ready) {
+    rc = attn_delta(dO, lddo, O, ldo, delta, B, H, NQ, st);
+    if (rc) return rc;
+  }
   CUtensorMap tq, tdo, t1, t2;
   rc = get_tensor_map_2d(&tq, Q, 2, uint64_t(ldq), uint64_t(B) * NQ, uint64_t(ldq) * 2, 64, 128);
   if (rc) return rc;
@@ -474,6 +464,35 @@ int mebt_latent_attention_bwd_dropout(const void* Q, int ldq, int q_col0, const 
   }
   MEBT_LAUNCH_OK("attn_bwd_kernel");
   return MEBT_OK;
+}
+}  // namespace mebt
+
+extern "C" {
+
+size_t mebt_latent_attention_bwd_workspace_bytes(int B, int H, int NQ) { return size_t(B) * H * NQ * sizeof(float); }
+
+int mebt_latent_attention_bwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0,
+                              int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, const void* O,
+                              int ldo, const void* dO, int lddo, const float* lse, void* dQ, int lddq, int dq_col0,
+                              void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2, int ldd2, int dk2_col0,
+                              int dv2_col0, int B, int H, int NQ, int head_dim, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  return mebt_latent_attention_bwd_dropout(Q, ldq, q_col0, KV1, ld1, k1_col0, v1_col0, NK1, KV2, ld2, k2_col0, v2_col0, NK2,
+                                           O, ldo, dO, lddo, lse, dQ, lddq, dq_col0, dKV1, ldd1, dk1_col0, dv1_col0, dKV2,
+                                           ldd2, dk2_col0, dv2_col0, B, H, NQ, head_dim, 0.f, 0ull, workspace,
+                                           workspace_bytes, stream);
+}
+
+int mebt_latent_attention_bwd_dropout(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
+                                      int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2,
+                                      const void* O, int ldo, const void* dO, int lddo, const float* lse, void* dQ,
+                                      int lddq, int dq_col0, void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2,
+                                      int ldd2, int dk2_col0, int dv2_col0, int B, int H, int NQ, int head_dim, float drop_p,
+                                      unsigned long long drop_seed, void* workspace, size_t workspace_bytes, void* stream) {
+  return mebt::latent_attention_bwd_launch(Q, ldq, q_col0, KV1, ld1, k1_col0, v1_col0, NK1, KV2, ld2, k2_col0, v2_col0, NK2, O,
+                                           ldo, dO, lddo, lse, dQ, lddq, dq_col0, dKV1, ldd1, dk1_col0, dv1_col0, dKV2, ldd2,
+                                           dk2_col0, dv2_col0, B, H, NQ, head_dim, drop_p, drop_seed, workspace,
+                                           workspace_bytes, 0, stream);
 }
 
 }  // extern "C"

@@ -108,26 +108,46 @@ int* reduce_counters(cudaStream_t st) {
 // dx = rstd * (g - mean_D(g) - xhat * mean_D(g * xhat)),  g = dy * gamma;   dgamma = sum_rows dy * xhat; dbeta = sum_rows dy
 // Two kernels with opposite parallelism: dx is row-parallel (one warp per row), the parameter gradients are column sums
 // (128 columns x a slab of rows per CTA, finished by the last CTA of a column block in slab order: reproducible).
+// One row-parallel LayerNorm-backward problem: dx = (resid ? resid : 0) + ln'(dy [+ dy_add]) over `rows` rows.
+struct LnDxProblem {
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* dy_add;     // optional second addend of the incoming gradient (a residual branch), or nullptr
+  const __nv_bfloat16* x;
+  const float* mean;
+  const float* rstd;
+  __nv_bfloat16* dx;
+  const __nv_bfloat16* resid;      // may alias dx
+  __nv_bfloat16* dx_drop;          // optional masked copy (see below)
+  DropKey drop;
+  int rows;
+};
+
+// Up to two problems that share gamma (ln1 applied to the query stream and to the key stream of one Block,
+// gpt.py:180-181) in ONE launch: CTAs [0, blocks0) take problem 0, the rest problem 1.
 template <int MAX_VEC>
-__global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     const float* __restrict__ gamma, __nv_bfloat16* dx, const __nv_bfloat16* resid,
-                                     int rows, int D, __nv_bfloat16* dx_drop, DropKey drop) {
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const LnDxProblem p0, const LnDxProblem p1, int blocks0,
+                                                               const float* __restrict__ gamma, int D) {
   // dx_drop (optional): a second copy of the result multiplied by the keep factors of `drop` - the gradient w.r.t. the
   // pre-dropout output of the Linear that produced this stream (proj / mlp.2), which its dgrad and wgrad GEMMs consume;
   // saves the separate dropout_rows launch between this kernel and those GEMMs.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  griddep_wait();
+  const bool second = int(blockIdx.x) >= blocks0;
+  const LnDxProblem& q = second ? p1 : p0;
+  // gamma is a parameter, not a product of the preceding kernels: fetch it before the dependency wait
   float4 gm[MAX_VEC];
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i) {
     const int c = (lane + 32 * i) * 4;
     gm[i] = c < D ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  griddep_wait();
   const float invD = 1.0f / float(D);
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  if (row >= rows) return;
-  const float mu = mean[row], rs = rstd[row];
+  const long long row = (long long)(int(blockIdx.x) - (second ? blocks0 : 0)) * 8 + warp;
+  if (row >= q.rows) return;
+  const __nv_bfloat16* dy = q.dy;
+  const __nv_bfloat16* x = q.x;
+  const __nv_bfloat16* resid = q.resid;
+  const float mu = q.mean[row], rs = q.rstd[row];
   float4 xh[MAX_VEC], g[MAX_VEC], old[MAX_VEC];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -135,7 +155,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat
     const int c = (lane + 32 * i) * 4;
     if (c < D) {
       const float4 xv = ld_bf16x4(x + row * D + c);
-      const float4 dv = ld_bf16x4(dy + row * D + c);
+      float4 dv = ld_bf16x4(dy + row * D + c);
+      if (q.dy_add != nullptr) {
+        const float4 d2 = ld_bf16x4(q.dy_add + row * D + c);
+        dv.x += d2.x; dv.y += d2.y; dv.z += d2.z; dv.w += d2.w;
+      }
       if (resid != nullptr) old[i] = ld_bf16x4(resid + row * D + c);      // dx = resid + ln'(dy); resid may alias dx
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
@@ -155,15 +179,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat
       o.z = rs * (g[i].z - s1 - xh[i].z * s2);
       o.w = rs * (g[i].w - s1 - xh[i].w * s2);
       if (resid != nullptr) { o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w; }
-      st_bf16x4(dx + row * D + c, o);
-      if (dx_drop != nullptr) {
+      st_bf16x4(q.dx + row * D + c, o);
+      if (q.dx_drop != nullptr) {
         // the standalone kernel masks the bf16-rounded gradient: round first so that both forms agree bit for bit
         const float4 r = ld_round_bf16x4(o);
-        const uint32_t rk = drop_row_key(drop, uint32_t(row));
+        const uint32_t rk = drop_row_key(q.drop, uint32_t(row));
         float f0, f1, f2, f3;
-        drop_pair(drop, rk, uint32_t(c >> 1), f0, f1);
-        drop_pair(drop, rk, uint32_t(c >> 1) + 1u, f2, f3);
-        st_bf16x4(dx_drop + row * D + c, make_float4(r.x * f0, r.y * f1, r.z * f2, r.w * f3));
+        drop_pair(q.drop, rk, uint32_t(c >> 1), f0, f1);
+        drop_pair(q.drop, rk, uint32_t(c >> 1) + 1u, f2, f3);
+        st_bf16x4(q.dx_drop + row * D + c, make_float4(r.x * f0, r.y * f1, r.z * f2, r.w * f3));
       }
     }
   }
@@ -362,24 +386,49 @@ int layernorm_bwd_params(const void* dy, const void* x, const float* mean, const
   return MEBT_OK;
 }
 
-// dx = (resid != NULL ? resid : 0) + ln'(dy); resid may be dx itself.  dx_drop / drop: see the kernel.
-int layernorm_bwd_dx(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
-                     const void* resid, int rows, int D, void* dx_drop, const DropKey* drop, cudaStream_t st) {
-  MEBT_REQUIRE(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024, MEBT_ERR_SHAPE, "layernorm_bwd: bad shape rows=%d D=%d", rows, D);
-  if (rows == 0) return MEBT_OK;
-  const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
-  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
-  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(resid);
-  __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx);
-  __nv_bfloat16* ddp = static_cast<__nv_bfloat16*>(dx_drop);      // with thr == 0 the second output is a plain copy
-  const DropKey dk = drop != nullptr ? *drop : DropKey{0u, 0u, 0u, 1.f};
-  const dim3 grid((rows + 7) / 8);
-  LaunchScope ls(FAM_LAYERNORM, double(rows) * D * (rp != nullptr ? 8.0 : 6.0), st);
-  if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<2>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, ddp, dk));
-  else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<4>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, ddp, dk));
-  else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<8>, grid, dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, rp, rows, D, ddp, dk));
+// dx = (resid != NULL ? resid : 0) + ln'(dy [+ dy_add]); resid may be dx itself.  dx_drop / drop: see the kernel.
+// One or two problems (n = 1, 2) sharing gamma, in one launch.
+struct LnDxDesc {
+  const void* dy; const void* dy_add; const void* x; const float* mean; const float* rstd; void* dx; const void* resid;
+  int rows; void* dx_drop; const DropKey* drop;
+};
+int layernorm_bwd_dx_multi(const LnDxDesc* d, int n, const float* gamma, int D, cudaStream_t st) {
+  MEBT_REQUIRE(n >= 1 && n <= 2 && D > 0 && D % 4 == 0 && D <= 1024, MEBT_ERR_SHAPE, "layernorm_bwd: bad shape n=%d D=%d", n, D);
+  LnDxProblem p[2];
+  int blocks[2] = {0, 0};
+  double bytes = 0.0;
+  for (int i = 0; i < 2; ++i) {
+    const LnDxDesc& s = d[i < n ? i : 0];
+    p[i].dy = static_cast<const __nv_bfloat16*>(s.dy);
+    p[i].dy_add = static_cast<const __nv_bfloat16*>(s.dy_add);
+    p[i].x = static_cast<const __nv_bfloat16*>(s.x);
+    p[i].mean = s.mean; p[i].rstd = s.rstd;
+    p[i].dx = static_cast<__nv_bfloat16*>(s.dx);
+    p[i].resid = static_cast<const __nv_bfloat16*>(s.resid);
+    p[i].dx_drop = static_cast<__nv_bfloat16*>(s.dx_drop);          // with thr == 0 the second output is a plain copy
+    p[i].drop = s.drop != nullptr ? *s.drop : DropKey{0u, 0u, 0u, 1.f};
+    p[i].rows = i < n ? s.rows : 0;
+    MEBT_REQUIRE(p[i].rows >= 0, MEBT_ERR_SHAPE, "layernorm_bwd: negative row count");
+    blocks[i] = (p[i].rows + 7) / 8;
+    bytes += double(p[i].rows) * D * (6.0 + (p[i].resid != nullptr ? 2.0 : 0.0) + (p[i].dy_add != nullptr ? 2.0 : 0.0) +
+                                      (p[i].dx_drop != nullptr ? 2.0 : 0.0));
+  }
+  if (blocks[0] + blocks[1] == 0) return MEBT_OK;
+  const dim3 grid(blocks[0] + blocks[1]);
+  LaunchScope ls(FAM_LAYERNORM, bytes, st);
+  if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<2>, grid, dim3(256), 0, st, p[0], p[1], blocks[0], gamma, D));
+  else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<4>, grid, dim3(256), 0, st, p[0], p[1], blocks[0], gamma, D));
+  else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<8>, grid, dim3(256), 0, st, p[0], p[1], blocks[0], gamma, D));
   MEBT_LAUNCH_OK("layernorm_bwd_dx_kernel");
   return MEBT_OK;
+}
+
+int layernorm_bwd_dx(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                     const void* resid, int rows, int D, void* dx_drop, const DropKey* drop, cudaStream_t st) {
+  MEBT_REQUIRE(rows >= 0, MEBT_ERR_SHAPE, "layernorm_bwd: bad shape rows=%d D=%d", rows, D);
+  if (rows == 0) return MEBT_OK;
+  const LnDxDesc d{dy, nullptr, x, mean, rstd, dx, resid, rows, dx_drop, drop};
+  return layernorm_bwd_dx_multi(&d, 1, gamma, D, st);
 }
 
 int layernorm_bwd_resid(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,

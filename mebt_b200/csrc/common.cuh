@@ -68,6 +68,18 @@ struct LaunchScope {
 // Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining,
 // so its launch latency and prologue (barrier init, TMEM allocation, descriptor prefetch) overlap the predecessor's
 // tail.  Every kernel launched this way calls griddep_wait() before it touches global memory.
+// An event recorded between a kernel and its programmatic dependent is not signalled until the dependent has been
+// scheduled behind it; a stream that forks work to other streams through such an event therefore asks for its NEXT
+// launch to be an ordinary (fully serialised) one: pdl_fence(stream).
+struct PdlFence { cudaStream_t stream; bool armed; };
+inline PdlFence& pdl_fence_state() { static thread_local PdlFence f{nullptr, false}; return f; }
+inline void pdl_fence(cudaStream_t st) { pdl_fence_state() = PdlFence{st, true}; }
+inline int pdl_allowed(cudaStream_t st) {
+  PdlFence& f = pdl_fence_state();
+  if (f.armed && f.stream == st) { f.armed = false; return 0; }
+  return 1;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -77,7 +89,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_allowed(st);
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
@@ -94,7 +106,7 @@ inline cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_allowed(st);
   attr[1].id = cudaLaunchAttributeClusterDimension;
   attr[1].val.clusterDim.x = 2;
   attr[1].val.clusterDim.y = 1;
@@ -116,6 +128,15 @@ inline cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// 16-byte shared-memory accesses by 32-bit shared-window address (LDS/STS instead of generic LD/ST)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

@@ -9,6 +9,7 @@
 //             (dQ, dK, dV) = attention'(datt);  dqn = dx + dQKV Wqkv;  dkn = dKV Wkv;
 //             d_q = ln1'(dqn) (assigned),  d_k += ln1'(dkn) (accumulated: a stream version may feed several blocks);
 //             weight grads = (dY)^T X through the MN-major GEMM modes, bias grads = column sums.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -34,6 +35,16 @@ int dropout_rows(const void* x, int ldx, const void* resid, int ldres, void* y, 
 int gemm_bf16_drop(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
                    int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
                    const DropKey* drop, cudaStream_t stream);
+int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                 int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
+                 const DropKey* drop, float* delta_out, int delta_nq, int delta_h, cudaStream_t stream);
+int latent_attention_bwd_launch(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
+                                int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2,
+                                const void* O, int ldo, const void* dO, int lddo, const float* lse, void* dQ,
+                                int lddq, int dq_col0, void* dKV1, int ldd1, int dk1_col0, int dv1_col0, void* dKV2,
+                                int ldd2, int dk2_col0, int dv2_col0, int B, int H, int NQ, int head_dim, float drop_p,
+                                unsigned long long drop_seed, void* workspace, size_t workspace_bytes, int delta_ready,
+                                void* stream);
 struct WgradDesc {           // csrc/gemm_grouped.cu
   const void* dY; int ld_dy;
   const void* X; int ldx;
@@ -105,29 +116,42 @@ Plan make_plan(const mebt_layer_t* layers, int n_layers, int B, int L, int NC, i
 // chain has already produced, so they run on two library-owned side streams (A: the tcgen05 weight-gradient GEMMs,
 // B: the small reductions), concurrently with the next links of the chain: every kernel of the 16-frame training step
 // is at most about one wave of CTAs, so the chain is bound by per-kernel latency, not by SM time.
+constexpr int OWED_RING = 4;          // depth of the masked-copy ring (dy_mlp): writers never wait for recent readers
 struct SideStreams {
-  cudaStream_t a = nullptr, b = nullptr;
+  cudaStream_t a = nullptr, b = nullptr, c = nullptr;
   cudaEvent_t fork[8] = {};
-  cudaEvent_t join_a = nullptr, join_b = nullptr;
-  // per block parity: the block's readers of its masked stream gradient are done (A: the grouped weight gradients,
-  // B: the mlp.2 bias gradient) / all of the block's side work is done (it reads the scratch buffers the block after
-  // next reuses)
-  cudaEvent_t fc2_a[2] = {}, fc2_b[2] = {}, end_a[2] = {}, end_b[2] = {};
+  cudaEvent_t join_a = nullptr, join_b = nullptr, join_c = nullptr;
+  // fc2_*[ring slot]: the readers of a block's masked stream gradient are done (A: the grouped weight gradients,
+  // B: the mlp.2 bias gradient).  end_*[block parity]: all of the block's side work is done (it reads the scratch
+  // buffers the block after next reuses).  kdgrad_c[parity]: the key-side data gradient (stream C) exists.
+  cudaEvent_t fc2_a[OWED_RING] = {}, fc2_b[OWED_RING] = {}, end_a[2] = {}, end_b[2] = {}, end_c[2] = {}, kdgrad_c[2] = {};
+  std::vector<cudaEvent_t> fwd_k;       // forward: block i's key/value projection (stream C) is ready
   bool ok = false;
 };
 SideStreams& side_streams() {
   static SideStreams s;
   if (!s.ok && s.a == nullptr) {
     bool good = cudaStreamCreateWithFlags(&s.a, cudaStreamNonBlocking) == cudaSuccess &&
-                cudaStreamCreateWithFlags(&s.b, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 8 && good; ++i) good = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess;
-    good = good && cudaEventCreateWithFlags(&s.join_a, cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&s.join_b, cudaEventDisableTiming) == cudaSuccess;
-    for (cudaEvent_t* e : {s.fc2_a, s.fc2_b, s.end_a, s.end_b})
-      for (int i = 0; i < 2 && good; ++i) good = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) == cudaSuccess;
+                cudaStreamCreateWithFlags(&s.b, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&s.c, cudaStreamNonBlocking) == cudaSuccess;
+    auto make = [&](cudaEvent_t* e, int n) {
+      for (int i = 0; i < n && good; ++i) good = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) == cudaSuccess;
+    };
+    make(s.fork, 8);
+    make(&s.join_a, 1); make(&s.join_b, 1); make(&s.join_c, 1);
+    make(s.fc2_a, OWED_RING); make(s.fc2_b, OWED_RING);
+    make(s.end_a, 2); make(s.end_b, 2); make(s.end_c, 2); make(s.kdgrad_c, 2);
     s.ok = good;
   }
   return s;
+}
+bool ensure_fwd_events(SideStreams& s, int n) {
+  while (int(s.fwd_k.size()) < n) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+    s.fwd_k.push_back(e);
+  }
+  return true;
 }
 
 // Which LayerNorm backward finishes the gradient w.r.t. block i's output stream (the last accumulation before block i
@@ -154,7 +178,7 @@ FinalWriter final_writer(const mebt_layer_t* layers, int last, int i) {
 // Every scratch tensor of a block's backward exists twice (by block parity): the side streams may still be reading
 // block i's buffers while the main stream runs block i-1, and block i-2 only starts after block i's side work.
 struct BwdWorkspace {
-  void *da[2], *dh[2], *datt[2], *dqkv[2], *dkv[2], *dqn[2], *dkn[2], *dxb[2], *dy_proj[2], *delta, *dy_mlp[2][2];
+  void *da[2], *dh[2], *datt[2], *dqkv[2], *dkv[2], *dqn[2], *dkn[2], *dxb[2], *dy_proj[2], *delta, *dy_mlp[2][OWED_RING];
   float *red, *red_b;
   size_t red_bytes, delta_bytes, total;
 };
@@ -177,7 +201,7 @@ BwdWorkspace carve_backward_workspace(char* W, int B, int L, int NC, int NT, int
   }
   w.delta_bytes = size_t(B) * H * (L > NT ? L : NT) * 4;
   w.delta = take(w.delta_bytes);
-  for (int i = 0; i < 2; ++i) {                  // [stream][parity of the consuming block]
+  for (int i = 0; i < OWED_RING; ++i) {          // [stream][ring slot of the consuming block]
     w.dy_mlp[0][i] = take(size_t(B) * L * D * 2);     // d(latents) .* keep/(1-p): gradient w.r.t. the pre-dropout MLP output
     w.dy_mlp[1][i] = take(size_t(B) * NT * D * 2);    // the same for the targets stream
   }
@@ -236,29 +260,59 @@ int mebt_stack_forward_train_dropout(const mebt_layer_t* layers, int n_layers, c
   MEBT_REQUIRE(plan.last >= 0, MEBT_ERR_UNSUPPORTED, "forward_train: no latent_dec block, the logits do not depend on the stack");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* S = static_cast<char*>(saved);
+  // The key side of a block (ln1 of the key stream + its K|V projection) does not depend on the query side: it runs
+  // on library stream C, next to the query side on the caller's stream, and the attention kernel waits for both.  The
+  // contexts never change through the stack (gpt.py:243-245), so the key sides of ALL latent_enc blocks are issued
+  // up front and are off the critical path altogether.
+  SideStreams& side = side_streams();
+  MEBT_REQUIRE(side.ok && ensure_fwd_events(side, n_layers), MEBT_ERR_CUDA, "forward_train: cannot create the side streams");
+  cudaStream_t sc = side.c;
+  int fork_slot = 0;
+  auto FORK_C = [&]() -> int {
+    cudaEvent_t e = side.fork[fork_slot];
+    fork_slot = (fork_slot + 1) & 7;
+    MEBT_CUDA_OK(cudaEventRecord(e, st));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(sc, e, 0));
+    return MEBT_OK;
+  };
+  auto KEY_SIDE = [&](int i, const void* k_in) -> int {
+    const mebt_layer_t& w = layers[i];
+    const LayerSaved& s = plan.layers[i];
+    const __nv_bfloat16* w_kv = static_cast<const __nv_bfloat16*>(w.w_qkv) + size_t(D) * D;
+    int rc2 = layernorm(k_in, D, MEBT_DTYPE_BF16, w.ln1_w, w.ln1_b, S + s.kn, D, MEBT_DTYPE_BF16, s.rk, D, 1e-5f,
+                        reinterpret_cast<float*>(S + s.k_mean), reinterpret_cast<float*>(S + s.k_rstd), sc);
+    if (rc2) return rc2;
+    rc2 = gemm_bf16_aux(S + s.kn, D, 0, w_kv, D, 0, S + s.kv, 2 * D, s.rk, 2 * D, D, w.b_qkv + D, nullptr, 0, nullptr, 0, 0, sc);
+    if (rc2) return rc2;
+    MEBT_CUDA_OK(cudaEventRecord(side.fwd_k[i], sc));
+    return MEBT_OK;
+  };
+  if (NC > 0) {
+    TRY(FORK_C());
+    for (int i = 0; i <= plan.last; ++i)
+      if (layers[i].mode == MEBT_MODE_LATENT_ENC) TRY(KEY_SIDE(i, ctx));
+  }
   const void* lat = lat0;
   const void* tgt = tgt0;
   for (int i = 0; i <= plan.last; ++i) {
     const mebt_layer_t& w = layers[i];
     const LayerSaved& s = plan.layers[i];
     const __nv_bfloat16* wqkv = static_cast<const __nv_bfloat16*>(w.w_qkv);
-    const __nv_bfloat16* w_kv = wqkv + size_t(D) * D;
-    const float* b_kv = w.b_qkv + D;
     const void* q_in = w.mode == MEBT_MODE_LATENT_DEC ? tgt : lat;
     const void* k_in = w.mode == MEBT_MODE_LATENT_ENC ? ctx : w.mode == MEBT_MODE_LATENT_DEC ? lat : w.mode == MEBT_MODE_LT2L ? tgt : nullptr;
-    void *qn = S + s.qn, *kn = S + s.kn, *qkv = S + s.qkv, *kv = S + s.kv, *att = S + s.att, *x = S + s.x, *h = S + s.h,
+    void *qn = S + s.qn, *qkv = S + s.qkv, *kv = S + s.kv, *att = S + s.att, *x = S + s.x, *h = S + s.h,
          *a = S + s.a, *u = S + s.u, *out = S + s.out;
     float* lse = reinterpret_cast<float*>(S + s.lse);
     const bool fused = w.mode == MEBT_MODE_LATENT_SELF || w.mode == MEBT_MODE_LT2L;
+    if (s.rk > 0 && w.mode != MEBT_MODE_LATENT_ENC) {
+      TRY(FORK_C());
+      TRY(KEY_SIDE(i, k_in));
+    }
     TRY(layernorm(q_in, D, MEBT_DTYPE_BF16, w.ln1_w, w.ln1_b, qn, D, MEBT_DTYPE_BF16, s.rq, D, 1e-5f,
                   reinterpret_cast<float*>(S + s.q_mean), reinterpret_cast<float*>(S + s.q_rstd), st));
     const int qw = fused ? 3 * D : D;
     TRY(gemm_bf16_aux(qn, D, 0, wqkv, D, 0, qkv, qw, s.rq, qw, D, w.b_qkv, nullptr, 0, nullptr, 0, 0, st));
-    if (s.rk > 0) {
-      TRY(layernorm(k_in, D, MEBT_DTYPE_BF16, w.ln1_w, w.ln1_b, kn, D, MEBT_DTYPE_BF16, s.rk, D, 1e-5f,
-                    reinterpret_cast<float*>(S + s.k_mean), reinterpret_cast<float*>(S + s.k_rstd), st));
-      TRY(gemm_bf16_aux(kn, D, 0, w_kv, D, 0, kv, 2 * D, s.rk, 2 * D, D, b_kv, nullptr, 0, nullptr, 0, 0, st));
-    }
+    if (s.rk > 0) MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.fwd_k[i], 0));
     const int nk_sep = s.rk / B;
     const unsigned long long site = 4ull * i;      // + 0: attention, + 1: proj, + 2: mlp
     if (fused)
@@ -320,15 +374,24 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
   const int acc = grad_accumulate ? 1 : 0;
   SideStreams& side = side_streams();
   MEBT_REQUIRE(side.ok, MEBT_ERR_CUDA, "backward: cannot create the weight-gradient side streams");
-  cudaStream_t sa = side.a, sb = side.b;
+  cudaStream_t sa = side.a, sb = side.b, sc = side.c;
   int fork_slot = 0;
+  static const bool fence_forks = getenv("MEBT_FORK_NOPDL") != nullptr;
   // everything issued so far on the main stream happens before whatever is issued next on the two side streams
   auto FORK = [&]() -> int {
     cudaEvent_t e = side.fork[fork_slot];
     fork_slot = (fork_slot + 1) & 7;
     MEBT_CUDA_OK(cudaEventRecord(e, st));
+    if (fence_forks) pdl_fence(st);
     MEBT_CUDA_OK(cudaStreamWaitEvent(sa, e, 0));
     MEBT_CUDA_OK(cudaStreamWaitEvent(sb, e, 0));
+    return MEBT_OK;
+  };
+  auto FORK_C = [&]() -> int {
+    cudaEvent_t e = side.fork[fork_slot];
+    fork_slot = (fork_slot + 1) & 7;
+    MEBT_CUDA_OK(cudaEventRecord(e, st));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(sc, e, 0));
     return MEBT_OK;
   };
   // the side streams' work so far is marked by (ea on A, eb on B) ... / ... and the main stream waits for such a mark
@@ -346,8 +409,10 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
   auto JOIN = [&]() -> int {
     MEBT_CUDA_OK(cudaEventRecord(side.join_a, sa));
     MEBT_CUDA_OK(cudaEventRecord(side.join_b, sb));
+    MEBT_CUDA_OK(cudaEventRecord(side.join_c, sc));
     MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.join_a, 0));
     MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.join_b, 0));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.join_c, 0));
     return MEBT_OK;
   };
 
@@ -370,18 +435,20 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
     for (int i = 0; i <= plan.last && i < j; ++i) {
       const FinalWriter fw = final_writer(layers, plan.last, i);
       if (fw.block == j && fw.side == which) {
-        o.dst = ws.dy_mlp[layers[i].mode == MEBT_MODE_LATENT_DEC ? 1 : 0][i & 1];
+        o.dst = ws.dy_mlp[layers[i].mode == MEBT_MODE_LATENT_DEC ? 1 : 0][i % OWED_RING];
         o.key = make_drop_key(resid_p, seed, 4ull * i + 2);
         o.consumer = i;
       }
     }
     return o;
   };
-  // before the copy owed to block `consumer` is written: the previous readers of that buffer (side work of the last
-  // processed block of the same parity) must be done
-  auto AWAIT_OWED = [&](const Owed& o) -> int {
+  // before the copy owed to block `consumer` is written (on stream `on`): the previous readers of that ring slot
+  // (side work of block consumer + OWED_RING, issued long ago) must be done
+  auto AWAIT_OWED = [&](const Owed& o, cudaStream_t on) -> int {
     if (o.consumer < 0) return MEBT_OK;
-    return AWAIT(side.fc2_a[o.consumer & 1], side.fc2_b[o.consumer & 1]);
+    MEBT_CUDA_OK(cudaStreamWaitEvent(on, side.fc2_a[o.consumer % OWED_RING], 0));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(on, side.fc2_b[o.consumer % OWED_RING], 0));
+    return MEBT_OK;
   };
 
   if (layer_end == n_layers) {
@@ -397,7 +464,7 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
     TRY(layernorm_bwd_params(d_xf, tgt_final, reinterpret_cast<float*>(S + plan.f_mean), reinterpret_cast<float*>(S + plan.f_rstd),
                              d_lnf_w, d_lnf_b, acc, rows, D, red_b, red_bytes, sb));
     const Owed o = owed_by(plan.last + 1, 2);
-    TRY(AWAIT_OWED(o));
+    TRY(AWAIT_OWED(o, st));
     TRY(layernorm_bwd_dx(d_xf, tgt_final, reinterpret_cast<float*>(S + plan.f_mean), reinterpret_cast<float*>(S + plan.f_rstd),
                          lnf_w, d_tgt, nullptr, rows, D, o.dst, &o.key, st));
     TRY(MARK(side.end_a[hp], side.end_b[hp]));
@@ -447,8 +514,10 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
     const int par = i & 1;
     void *da = ws.da[par], *dh = ws.dh[par], *datt = ws.datt[par], *dqkv = ws.dqkv[par], *dkv = ws.dkv[par],
          *dqn = ws.dqn[par], *dkn = ws.dkn[par], *dxb = ws.dxb[par], *dy_proj = ws.dy_proj[par];
+    const int ring = i % OWED_RING;
     // this block reuses the scratch buffers of block i + 2: that block's side work (issued two blocks ago) must be done
     TRY(AWAIT(side.end_a[par], side.end_b[par]));
+    MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.end_c[par], 0));
 
     const unsigned long long site = 4ull * i;
     // ---- MLP ----  (main stream: the data-gradient chain; side stream A: ONE grouped launch of the block's weight
@@ -456,9 +525,9 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
     // d_mlp = d_out through the mlp-dropout mask = gradient w.r.t. (u W2 + b): a copy written by the LayerNorm backward
     // that finished d_out (see final_writer), so that this block's last kernels may overwrite d_out while the side
     // streams still read d_mlp; made here when no such kernel exists
-    void* d_mlp = ws.dy_mlp[mode == MEBT_MODE_LATENT_DEC ? 1 : 0][par];
+    void* d_mlp = ws.dy_mlp[mode == MEBT_MODE_LATENT_DEC ? 1 : 0][ring];
     if (final_writer(layers, plan.last, i).block < 0) {
-      TRY(AWAIT(side.fc2_a[par], side.fc2_b[par]));
+      TRY(AWAIT(side.fc2_a[ring], side.fc2_b[ring]));
       TRY(dropout_rows(d_out, D, nullptr, 0, d_mlp, D, rq, D, resid_p, seed, site + 2, st));
     }
     auto SIDE_COLSUM = [&](const void* dY, int ld_dy, int rows, int n_out, float* db, int accumulate) -> int {
@@ -467,7 +536,7 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
       return colsum(dY, ld_dy, rows, n_out, db, accumulate, red_b, red_bytes, sb);
     };
     TRY(SIDE_COLSUM(d_mlp, D, rq, D, g.b_fc2, acc));
-    MEBT_CUDA_OK(cudaEventRecord(side.fc2_b[par], sb));
+    MEBT_CUDA_OK(cudaEventRecord(side.fc2_b[ring], sb));
     TRY(DGRAD(d_mlp, D, w.w_fc2, 4 * D, da, rq, 4 * D, D, nullptr, S + s.a, 4 * D, MEBT_GEMM_DGELU));     // da
     TRY(SIDE_COLSUM(da, 4 * D, rq, 4 * D, g.b_fc1, acc));
     TRY(DGRAD(da, 4 * D, w.w_fc1, D, dh, rq, D, 4 * D, nullptr, nullptr, 0, 0));                            // dh
@@ -483,20 +552,22 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
     // ---- attention output projection ----
     const void* d_proj = resid_p > 0.f ? dy_proj : dx;
     TRY(SIDE_COLSUM(d_proj, D, rq, D, g.b_proj, acc));
-    TRY(DGRAD(d_proj, D, w.w_proj, D, datt, rq, D, D, nullptr, nullptr, 0, 0));
+    // datt = d_proj Wp; the same epilogue emits delta = rowsum_head(datt .* att) for the attention backward
+    TRY(gemm_bf16_ex(d_proj, D, 0, w.w_proj, D, 1, datt, D, rq, D, D, nullptr, nullptr, 0, S + s.att, D, 0, nullptr,
+                     static_cast<float*>(delta), s.nq, H, st));
     // ---- attention ----
     const int nk_sep = rk / B;
     const float* lse = reinterpret_cast<float*>(S + s.lse);
     if (fused)
-      TRY(mebt_latent_attention_bwd_dropout(S + s.qkv, 3 * D, 0, S + s.qkv, 3 * D, D, 2 * D, L, rk > 0 ? S + s.kv : nullptr,
-                                            2 * D, 0, D, nk_sep, S + s.att, D, datt, D, lse, dqkv, 3 * D, 0, dqkv, 3 * D, D,
-                                            2 * D, rk > 0 ? dkv : nullptr, 2 * D, 0, D, B, H, s.nq, 64, attn_p, seed + site,
-                                            delta, delta_bytes, stream));
+      TRY(latent_attention_bwd_launch(S + s.qkv, 3 * D, 0, S + s.qkv, 3 * D, D, 2 * D, L, rk > 0 ? S + s.kv : nullptr,
+                                      2 * D, 0, D, nk_sep, S + s.att, D, datt, D, lse, dqkv, 3 * D, 0, dqkv, 3 * D, D,
+                                      2 * D, rk > 0 ? dkv : nullptr, 2 * D, 0, D, B, H, s.nq, 64, attn_p, seed + site,
+                                      delta, delta_bytes, 1, stream));
     else
-      TRY(mebt_latent_attention_bwd_dropout(S + s.qkv, D, 0, rk > 0 ? S + s.kv : nullptr, 2 * D, 0, D, nk_sep, nullptr, 0, 0,
-                                            0, 0, S + s.att, D, datt, D, lse, dqkv, D, 0, rk > 0 ? dkv : nullptr, 2 * D, 0,
-                                            D, nullptr, 0, 0, 0, B, H, s.nq, 64, attn_p, seed + site, delta, delta_bytes,
-                                            stream));
+      TRY(latent_attention_bwd_launch(S + s.qkv, D, 0, rk > 0 ? S + s.kv : nullptr, 2 * D, 0, D, nk_sep, nullptr, 0, 0,
+                                      0, 0, S + s.att, D, datt, D, lse, dqkv, D, 0, rk > 0 ? dkv : nullptr, 2 * D, 0,
+                                      D, nullptr, 0, 0, 0, B, H, s.nq, 64, attn_p, seed + site, delta, delta_bytes, 1,
+                                      stream));
     // ---- weight gradients of the whole block: one grouped launch on side stream A ----
     const int qw = fused ? 3 * D : D;
     {
@@ -510,12 +581,13 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
       // projected keys / values from its own stream (lt2l), in which case they are added by a second launch
       if (rk > 0 && !fused) wd[n++] = WgradDesc{dkv, 2 * D, S + s.kn, D, g.w_qkv + size_t(D) * D, D, 2 * D, D, rk, acc};
       TRY(FORK());
+      if (rk > 0) MEBT_CUDA_OK(cudaStreamWaitEvent(sc, side.fork[(fork_slot + 7) & 7], 0));   // stream C forks here too
       TRY(gemm_grouped_wgrad(wd, n, sa));
       if (rk > 0 && fused) {
         const WgradDesc kv{dkv, 2 * D, S + s.kn, D, g.w_qkv + size_t(D) * D, D, 2 * D, D, rk, 1};
         TRY(gemm_grouped_wgrad(&kv, 1, sa));
       }
-      MEBT_CUDA_OK(cudaEventRecord(side.fc2_a[par], sa));
+      MEBT_CUDA_OK(cudaEventRecord(side.fc2_a[ring], sa));
       TRY(colsum(dqkv, qw, rq, qw, g.b_qkv, acc, red_b, red_bytes, sb));
       if (rk > 0) {
         TRY(colsum(dkv, 2 * D, rk, 2 * D, g.b_qkv + D, fused ? 1 : acc, red_b, red_bytes, sb));
@@ -525,27 +597,37 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
         MEBT_CUDA_OK(cudaMemsetAsync(g.b_qkv + D, 0, size_t(2) * D * 4, sb));
       }
     }
+    // ---- key side, on stream C next to the query side: data gradient of the K|V projection, then ln1 backward into
+    // the key stream's gradient (and the masked copy an earlier block's GEMMs will read).  For latent_enc the key
+    // stream is the contexts, whose gradient only the embedding backward reads: never joined before the end.
+    if (rk > 0) {
+      TRY(gemm_bf16_aux(dkv, 2 * D, 0, w_kv, D, 1, dkn, D, rk, D, 2 * D, nullptr, nullptr, 0, nullptr, 0, 0, sc));   // dkn
+      MEBT_CUDA_OK(cudaEventRecord(side.kdgrad_c[par], sc));
+      const Owed o = owed_by(i, 1);
+      TRY(AWAIT_OWED(o, sc));
+      TRY(layernorm_bwd_dx(dkn, k_in, reinterpret_cast<float*>(S + s.k_mean), reinterpret_cast<float*>(S + s.k_rstd), w.ln1_w,
+                           d_k_stream, d_k_stream, rk, D, o.dst, &o.key, sc));                             // accumulates
+      MEBT_CUDA_OK(cudaEventRecord(side.end_c[par], sc));
+    }
     TRY(DGRAD(dqkv, qw, wqkv, D, dqn, rq, D, qw, dx, nullptr, 0, 0));                                       // dqn = dx + dQKV Wqkv
-    if (rk > 0) TRY(DGRAD(dkv, 2 * D, w_kv, D, dkn, rk, D, 2 * D, nullptr, nullptr, 0, 0));
-    // ---- ln1 on both streams ----  parameter gradients on side stream B; the dx kernels also write the masked copy
-    // an earlier block's GEMMs will read (nothing on the side streams reads d_out itself)
+    // ---- ln1, query side ----  parameter gradients on side stream B (query side, then key side: they add into the
+    // same vectors); the dx kernel also writes the masked copy an earlier block's GEMMs will read
     TRY(FORK());
     TRY(layernorm_bwd_params(dqn, q_in, reinterpret_cast<float*>(S + s.q_mean), reinterpret_cast<float*>(S + s.q_rstd),
                              g.ln1_w, g.ln1_b, acc, rq, D, red_b, red_bytes, sb));
+    if (rk > 0) {
+      MEBT_CUDA_OK(cudaStreamWaitEvent(sb, side.kdgrad_c[par], 0));
+      TRY(layernorm_bwd_params(dkn, k_in, reinterpret_cast<float*>(S + s.k_mean), reinterpret_cast<float*>(S + s.k_rstd),
+                               g.ln1_w, g.ln1_b, 1, rk, D, red_b, red_bytes, sb));
+    }
     {
       const Owed o = owed_by(i, 0);
-      TRY(AWAIT_OWED(o));
+      TRY(AWAIT_OWED(o, st));
       TRY(layernorm_bwd_dx(dqn, q_in, reinterpret_cast<float*>(S + s.q_mean), reinterpret_cast<float*>(S + s.q_rstd), w.ln1_w,
                            d_out, nullptr, rq, D, o.dst, &o.key, st));                                     // assigns d(q stream)
     }
-    if (rk > 0) {
-      TRY(layernorm_bwd_params(dkn, k_in, reinterpret_cast<float*>(S + s.k_mean), reinterpret_cast<float*>(S + s.k_rstd),
-                               g.ln1_w, g.ln1_b, 1, rk, D, red_b, red_bytes, sb));
-      const Owed o = owed_by(i, 1);
-      TRY(AWAIT_OWED(o));
-      TRY(layernorm_bwd_dx(dkn, k_in, reinterpret_cast<float*>(S + s.k_mean), reinterpret_cast<float*>(S + s.k_rstd), w.ln1_w,
-                           d_k_stream, d_k_stream, rk, D, o.dst, &o.key, st));                             // accumulates
-    }
+    // the next block (backward order) consumes the key stream's gradient unless that stream is the contexts
+    if (rk > 0 && mode != MEBT_MODE_LATENT_ENC) MEBT_CUDA_OK(cudaStreamWaitEvent(st, side.end_c[par], 0));
     TRY(MARK(side.end_a[par], side.end_b[par]));
   }
   // the caller's stream sees every gradient of this call (the all-reduce / optimizer is ordered after it)

@@ -49,7 +49,10 @@ struct GemmParams {
   __nv_bfloat16* aux;                  // gelu: optional pre-activation output; dgelu: pre-activation input
   int ldaux;
   int dgelu;                           // result *= gelu'(aux)
-  int in_kind;                         // operand read by the epilogue through TMA: 0 none, 1 residual, 2 dgelu aux
+  int in_kind;                         // operand read by the epilogue through TMA: 0 none, 1 residual, 2 dgelu aux,
+                                       // 3 attention output O (the epilogue also emits delta = rowsum_head(C .* O))
+  float* delta_out;                    // in_kind 3: [B, H, NQ] fp32, rows of C are (b, q), 64-column groups are heads
+  int delta_nq, delta_h;
   // split-K: `splits` CTAs share one output tile; each writes its fp32 partial accumulator to `partials`
   // ([tile][split][128][BN]) and the last one to arrive (per-tile counter) sums them in split order and runs the
   // epilogue.  Deterministic: the summation order does not depend on arrival order.
@@ -77,7 +80,10 @@ struct GemmParams {
     }                                                                                      \
   } while (0)
 long long* g_gemm_trace = nullptr;
+// absolute timestamps (SM clock) of one CTA's milestones: trace[148 * 13 + blockIdx.x * 8 + i]
+#define TS(i) do { if (p.trace != nullptr) p.trace[148 * 13 + blockIdx.x * 16 + (i)] = clock64(); } while (0)
 #else
+#define TS(i)
 #define TR_DECL
 #define TR_BEGIN
 #define TR_END(i)
@@ -118,6 +124,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* epi_bar = tmem_empty_bar + 2;                       // [EPI_SLOTS]: staged input operand landed
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_bar + EPI_SLOTS);
 
+  if (threadIdx.x == 0) TS(0);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // work decomposition: plain = one 128xBN tile (x split) per item, strided by the grid;
@@ -185,7 +192,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) TS(1);
   griddep_wait();
+  if (threadIdx.x == 0) TS(2);
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -268,6 +277,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           TR_BEGIN;
           mbar_wait(&full_bar[stage], phase);
           TR_END(0);
+          if (it == 0 && kb == kb0) TS(3);
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sB = sA + A_TILE_BYTES;
@@ -292,6 +302,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      TS(4);
       TR_FLUSH(2, 2);
     }
   } else {
@@ -358,6 +369,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       TR_BEGIN;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       TR_END(0);
+      if (threadIdx.x == 64 && it == 0) TS(5);
       tc_fence_after();
       const float* my_partials = nullptr;
       if (p.splits > 1) {
@@ -473,6 +485,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       };
       // One 32-column unit of this thread's row through the staging ring (TMA epilogue).
+      float dacc = 0.f;                                        // in_kind 3: running dot product of the current head
       auto staged_unit = [&](const uint32_t (&r)[32], int u) {
         const int gu = it * (BN / 32) + u;                     // unit counter across this CTA's tiles
         const int g = f32 ? gu : gu >> 1;                      // output chunk it belongs to
@@ -480,26 +493,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int s_c = aux_out ? (2 * g) & 3 : g & 3;
         const int sw = lane & 7;
         uint8_t* row_c = slots + s_c * EPI_SLOT_BYTES + (q * 32 + lane) * 128;
+        if (threadIdx.x == 64 && it == 0 && u < 2) TS(8 + 4 * u);
         if ((f32 || half == 0) && k_in != 0) {
           TR_BEGIN;
           mbar_wait(&in_full[s_c], (g >> 2) & 1);              // this chunk's residual / pre-activation has landed
           TR_END(1);
         }
+        if (threadIdx.x == 64 && it == 0 && u < 2) TS(9 + 4 * u);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        // every shared-memory operand of the unit is fetched up front (LDS, all in flight together); the option
+        // switches sit outside the element loops so that each variant is straight-line code
+        const uint32_t row_c_s = smem_u32(row_c);
+        uint4 in4[4];
+        if (k_in != 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) in4[j] = lds128(row_c_s + uint32_t(((half * 4 + j) ^ sw) << 4));
+        }
         if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + u * 32);
+          const uint32_t b_s = smem_u32(s_bias + u * 32);
+          uint4 b4[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b4[j] = lds128(b_s + j * 16);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = b4[j];
-            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            v[4 * j + 0] += __uint_as_float(b4[j].x); v[4 * j + 1] += __uint_as_float(b4[j].y);
+            v[4 * j + 2] += __uint_as_float(b4[j].z); v[4 * j + 3] += __uint_as_float(b4[j].w);
           }
         }
         if (k_drop) apply_drop(v, n0 + u * 32);
         if (k_gelu) {
           if (aux_out) {                                       // keep the pre-activation for the backward pass
-            uint8_t* row_a = slots + ((2 * g + 1) & 3) * EPI_SLOT_BYTES + (q * 32 + lane) * 128;
+            const uint32_t row_a_s = smem_u32(slots + ((2 * g + 1) & 3) * EPI_SLOT_BYTES + (q * 32 + lane) * 128);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -507,7 +533,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
               o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
               o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              *reinterpret_cast<uint4*>(row_a + (((half * 4 + j) ^ sw) << 4)) = o;
+              sts128(row_a_s + uint32_t(((half * 4 + j) ^ sw) << 4), o);
             }
           }
 #pragma unroll
@@ -516,27 +542,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             v[2 * j] = gl.x; v[2 * j + 1] = gl.y;
           }
         }
-        if (k_in != 0) {
+        if (k_in == 1) {                                       // residual
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 w4 = *reinterpret_cast<const uint4*>(row_c + (((half * 4 + j) ^ sw) << 4));
-            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const uint32_t w[4] = {in4[j].x, in4[j].y, in4[j].z, in4[j].w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const float2 x = unpack_bf16x2(w[t]);
-              if (k_in == 2) {
-                const float2 gg = gelu_erf_grad_x2(x);
-                v[8 * j + 2 * t] *= gg.x; v[8 * j + 2 * t + 1] *= gg.y;
-              } else {
-                v[8 * j + 2 * t] += x.x; v[8 * j + 2 * t + 1] += x.y;
-              }
+              v[8 * j + 2 * t] += x.x; v[8 * j + 2 * t + 1] += x.y;
             }
+          }
+        } else if (k_in == 2) {                                // gelu'(pre-activation)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w[4] = {in4[j].x, in4[j].y, in4[j].z, in4[j].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 gg = gelu_erf_grad_x2(unpack_bf16x2(w[t]));
+              v[8 * j + 2 * t] *= gg.x; v[8 * j + 2 * t + 1] *= gg.y;
+            }
+          }
+        } else if (k_in == 3) {                                // delta = rowsum_head(C .* O)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w[4] = {in4[j].x, in4[j].y, in4[j].z, in4[j].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x = unpack_bf16x2(w[t]);
+              dacc = fmaf(v[8 * j + 2 * t], x.x, dacc);
+              dacc = fmaf(v[8 * j + 2 * t + 1], x.y, dacc);
+            }
+          }
+          if (half == 1) {                                     // one 64-column chunk = one head of this row
+            if (row_ok) {
+              const int bq = row / p.delta_nq;
+              const int hd = (n0 + u * 32) >> 6;
+              p.delta_out[(size_t(bq) * p.delta_h + hd) * p.delta_nq + (row - bq * p.delta_nq)] = dacc;
+            }
+            dacc = 0.f;
           }
         }
         if (f32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(row_c + ((j ^ sw) << 4)) = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            sts128(row_c_s + uint32_t((j ^ sw) << 4), make_uint4(__float_as_uint(v[4 * j + 0]), __float_as_uint(v[4 * j + 1]),
+                                                                 __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -545,9 +595,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
             o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
             o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(row_c + (((half * 4 + j) ^ sw) << 4)) = o;
+            sts128(row_c_s + uint32_t(((half * 4 + j) ^ sw) << 4), o);
           }
         }
+        if (threadIdx.x == 64 && it == 0 && u < 2) TS(10 + 4 * u);
         if (f32 || half == 1) {
           // One barrier per chunk: behind it every row of the slot is written (and fenced towards the async proxy), and
           // the slot the NEXT chunk writes has been read out by its previous store (epi_t0 checks before arriving).
@@ -571,6 +622,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           TR_END(3);
         }
+        if (threadIdx.x == 64 && it == 0 && u < 2) TS(11 + 4 * u);
       };
       if (my_partials == nullptr) {
         // software pipeline over the accumulator: the TMEM load of unit u+1 is in flight while unit u is finished
@@ -615,6 +667,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
+    if (threadIdx.x == 64) TS(6);
     if (tma_epi && epi_t0) tma_store_wait_read<0>();          // the stores have read their slots (the writes drain with the grid)
     if (threadIdx.x == 64) TR_FLUSH(5, 1);
 #ifdef MEBT_GEMM_TRACE
@@ -629,6 +682,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
+    if (lane == 0) TS(7);
   }
 }
 
@@ -658,6 +712,7 @@ int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda,
     }
     if (p.in_kind == 1) rc = get_tensor_map_2d(&tin, p.residual, 2, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldres) * 2, 64, 128);
     if (p.in_kind == 2) rc = get_tensor_map_2d(&tin, p.aux, 2, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldaux) * 2, 64, 128);
+    if (p.in_kind == 3) rc = get_tensor_map_2d(&tin, p.aux, 2, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldaux) * 2, 64, 128);
     if (rc) return rc;
   }
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, PAIR>;
@@ -706,6 +761,9 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
 int gemm_bf16_drop(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
                    int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
                    const DropKey* drop, cudaStream_t stream);
+int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                 int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
+                 const DropKey* drop, float* delta_out, int delta_nq, int delta_h, cudaStream_t stream);
 
 // Split-K scratch: the only device memory the library owns (partials are consumed inside the launch that wrote
 // them; the per-tile counters are returned to zero by the CTA that completes the tile).  Launches that use it are
@@ -746,6 +804,16 @@ int gemm_bf16_aux(const void* A, int lda, int a_mn, const void* B, int ldb, int 
 int gemm_bf16_drop(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
                    int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
                    const DropKey* drop, cudaStream_t stream) {
+  return gemm_bf16_ex(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, bias, residual, ldres, aux, ldaux, flags, drop, nullptr, 0,
+                      0, stream);
+}
+
+// + delta: C = A B^T as bf16 and, from the same fp32 accumulators, delta[b, h, q] = sum over the 64 columns of head h
+// of C[(b, q), :] * O[(b, q), :] with O passed in `aux` - the row sums the attention backward needs (dO = C), without
+// the separate pass over dO and O.
+int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                 int K, const float* bias, const void* residual, int ldres, void* aux, int ldaux, int flags,
+                 const DropKey* drop, float* delta_out, int delta_nq, int delta_h, cudaStream_t stream) {
   MEBT_REQUIRE(M > 0 && N > 0 && K > 0, MEBT_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   MEBT_REQUIRE(N % 64 == 0, MEBT_ERR_SHAPE, "gemm: N=%d must be a multiple of 64", N);
   MEBT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, MEBT_ERR_SHAPE, "gemm: lda/ldb must be multiples of 8 elements");
@@ -771,6 +839,14 @@ int gemm_bf16_drop(const void* A, int lda, int a_mn, const void* B, int ldb, int
   MEBT_REQUIRE(!(p.dgelu && residual != nullptr) && !(out_fp32 && (p.dgelu || residual != nullptr)), MEBT_ERR_UNSUPPORTED,
                "gemm: the epilogue reads one bf16 operand (residual or gelu' input) and only with bf16 output");
   p.in_kind = residual != nullptr ? 1 : (p.dgelu ? 2 : 0);
+  p.delta_out = delta_out; p.delta_nq = delta_nq; p.delta_h = delta_h;
+  if (delta_out != nullptr) {
+    MEBT_REQUIRE(aux != nullptr && residual == nullptr && !p.gelu && !p.dgelu && !out_fp32 && bias == nullptr &&
+                 delta_nq > 0 && M % delta_nq == 0 && N == 64 * delta_h, MEBT_ERR_UNSUPPORTED,
+                 "gemm: the delta epilogue needs O in aux, a plain bf16 output of width 64 * H and whole batches of rows");
+    p.in_kind = 3;
+    flags |= MEBT_GEMM_NO_SPLITK;
+  }
   p.drop = DropKey{0u, 0u, 0u, 1.f};
   if (drop != nullptr && drop->thr != 0) {
     MEBT_REQUIRE(!p.gelu && !p.dgelu && !out_fp32, MEBT_ERR_UNSUPPORTED, "gemm: dropout epilogue only on plain bf16 outputs");

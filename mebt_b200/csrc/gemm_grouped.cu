@@ -11,6 +11,7 @@
 // Structure = csrc/gemm.cu without its options (192 threads: TMA producer warp, single-thread MMA issuer, 4 epilogue
 // warps; 3-stage 128B-swizzled operand ring; two TMEM accumulators; epilogue through a 4-slot staging ring and TMA
 // store / reduce-add).  Tiles are numbered problem after problem; inside a problem in bands of 16 row blocks.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -299,7 +300,9 @@ int gemm_grouped_wgrad(const WgradDesc* d, int n, cudaStream_t stream) {
     attr_set = true;
   }
   LaunchScope ls(FAM_GEMM, flops, stream);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  static const int cta_cap = getenv("MEBT_WGRAD_CTAS") != nullptr ? atoi(getenv("MEBT_WGRAD_CTAS")) : 0;   // experiment knob
+  const int cap = cta_cap > 0 ? cta_cap : sm_count();
+  const int grid = tiles < cap ? tiles : cap;
   MEBT_CUDA_OK(launch_pdl(gemm_grouped_wgrad_kernel, dim3(grid), dim3(GG_THREADS), SMEM_TOTAL, stream, maps, p));
   MEBT_LAUNCH_OK("gemm_grouped_wgrad_kernel");
   return MEBT_OK;

@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
   cudaStream_t st;
   cudaStreamCreate(&st);
   long long* trace;
-  cudaMalloc(&trace, 148 * 13 * sizeof(long long));
+  cudaMalloc(&trace, 148 * 29 * sizeof(long long));
   for (const Shape& s : shapes) {
     const size_t pool = 8;   // rotate weights so that they come from HBM, as inside the model
     __nv_bfloat16 *A, *W, *R;
@@ -67,11 +67,11 @@ int main(int argc, char** argv) {
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
     const double us = ms * 1e3 / reps;
-    cudaMemset(trace, 0, 148 * 13 * sizeof(long long));
+    cudaMemset(trace, 0, 148 * 29 * sizeof(long long));
     mebt_gemm_set_trace(trace);
     run(0);
     cudaStreamSynchronize(st);
-    long long h[148 * 13];
+    static long long h[148 * 29];
     cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
     double avg[8] = {0};
     int n = 0;
@@ -87,6 +87,22 @@ int main(int argc, char** argv) {
     for (int b = 0; b < 148; ++b) for (int i = 0; i < 5; ++i) ex[i] += double(h[148 * 8 + b * 5 + i]) / (n2 ? n2 : 1);
     printf("%-16s M=%6d N=%6d K=%5d | %8.1f us %7.1f TF | ctas %3d | prod wait_empty %7.0f / %7.0f | mma wait_full %7.0f wait_acc %7.0f / %7.0f | epi wait_full %7.0f / %7.0f [slot %6.0f fence %6.0f store %6.0f tmem %6.0f bias %6.0f]\n",
            s.name, s.M, s.N, s.K, us, 2.0 * s.M * s.N * s.K / us / 1e6, n, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], ex[0], ex[1], ex[2], ex[3], ex[4]);
+    {   // milestones of the CTAs (SM clocks after kernel entry): prologue done, dependency wait passed, first operands landed,
+        // last MMA issued, accumulator complete, last unit staged, CTA end
+      double t[16] = {0};
+      int m = 0;
+      for (int b = 0; b < 148; ++b) {
+        const long long* q = h + 148 * 13 + b * 16;
+        if (q[0] == 0) continue;
+        ++m;
+        for (int i = 1; i < 16; ++i) t[i] += double(q[i] - q[0]);
+      }
+      for (int i = 1; i < 16; ++i) t[i] /= (m ? m : 1);
+      printf("    milestones (clk): prologue %6.0f | dep %6.0f | first-full %6.0f | last-mma %6.0f | acc-ready %6.0f | staged %6.0f | end %6.0f\n",
+             t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+      printf("    epilogue unit 0: enter %6.0f in-ready %6.0f computed %6.0f done %6.0f | unit 1: enter %6.0f in-ready %6.0f computed %6.0f done %6.0f\n",
+             t[8], t[9], t[10], t[11], t[12], t[13], t[14], t[15]);
+    }
     fflush(stdout);
     cudaFree(A); cudaFree(W); cudaFree(C); cudaFree(bias); cudaFree(R);
   }

@@ -32,7 +32,10 @@ def main():
     x, idx = bench.synth_batch(cfg, 6, 1)
     x, idx = x.to(dev), idx.to(dev)
     n = len(ts.modes)
-    print("sequential update            : %.3f ms" % timed(lambda: ts.train_step(opt, x, idx, t=0.5)))
+    print("sequential update            : %.3f ms" % timed(lambda: ts.train_step(opt, x, idx, t=0.5), reps=20))
+    if "--base" in sys.argv:
+        print("sequential update (repeat)   : %.3f ms" % timed(lambda: ts.train_step(opt, x, idx, t=0.5), reps=20))
+        return
     for nb in (4, 8, 12):
         edges = [round(i * n / nb) for i in range(nb + 1)]
         ts.chunks = [(edges[i], edges[i + 1]) for i in range(nb)]
