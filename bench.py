@@ -470,6 +470,7 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
             outside the timed region)."""
             try:
                 import torch.distributed as dist
+                ts.sync_masters()                         # sharded exchange: gather every rank's fp32 master shards first
                 chk = torch.stack([ts.flat.sum(dtype=torch.float64), ts.flat.abs().sum(dtype=torch.float64)])
                 lo, hi = chk.clone(), chk.clone()
                 dist.all_reduce(lo, op=dist.ReduceOp.MIN)

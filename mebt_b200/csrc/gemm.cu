@@ -730,7 +730,15 @@ int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda,
   } else {
     const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    MEBT_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, tc, taux, tin, p));
+    const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, tc, taux, tin, p);
+    if (le != cudaSuccess) {
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, kern);
+      set_last_error("gemm launch failed: %s (regs %d, max threads %d, static smem %zu, dynamic smem %d, max dynamic %d)",
+                     cudaGetErrorString(le), fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, L::TOTAL,
+                     fa.maxDynamicSharedSizeBytes);
+      return MEBT_ERR_CUDA;
+    }
   }
   MEBT_LAUNCH_OK("gemm_bf16_kernel");
   return MEBT_OK;

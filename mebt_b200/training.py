@@ -54,39 +54,65 @@ class TrainState:
         self.D, self.H, self.V = cfg.n_embd, cfg.n_head, gpt.head.weight.shape[0]
         self.L = model.sos_emb.shape[1]
         named = dict(model.named_parameters())
-        order = []
+        # Flat layout: block 0 | pad | block 1 | pad | ... | ln_f + head | pad | embeddings | pad.  Every bucket (any run of
+        # blocks, the head bucket, the embedding bucket) is padded to a multiple of 8 x the natural alignment of the
+        # tensors inside it, so that it splits into 1, 2, 4 or 8 equal shards whose bounds are also bounds of the
+        # optimizer's decay-flag blocks (reduce-scatter / sharded AdamW / all-gather, `_exchange_sharded`).  The padding
+        # belongs to no parameter and stays zero.
+        natural = 1 << 20
+        for p_ in named.values():
+            while p_.numel() % natural:
+                natural >>= 1
+        self.align = 8 * max(natural, 4)
+        pad_to = lambda n: -(-n // self.align) * self.align
+        order, placed = [], {}
         self.block_slices = []
+        off = 0
         for i in range(len(self.modes)):
-            start = sum(named[n].numel() for n in order)
-            order += [f"transformer.blocks.{i}.{s}" for s in _BLOCK_ORDER]
-            self.block_slices.append((start, sum(named[n].numel() for n in order)))
-        order += ["transformer.ln_f.weight", "transformer.ln_f.bias", "transformer.head.weight", "mask_emb", "sos_emb",
-                  "pos_emb", "tok_emb.weight"]
+            start = off
+            for s_ in _BLOCK_ORDER:
+                n_ = f"transformer.blocks.{i}.{s_}"
+                order.append(n_)
+                placed[n_] = off
+                off += named[n_].numel()
+            off = pad_to(off)
+            self.block_slices.append((start, off))
+        head_start = off
+        for n_ in ("transformer.ln_f.weight", "transformer.ln_f.bias", "transformer.head.weight"):
+            order.append(n_)
+            placed[n_] = off
+            off += named[n_].numel()
+        off = pad_to(off)
+        emb_start = off
+        for n_ in ("mask_emb", "sos_emb", "pos_emb", "tok_emb.weight"):
+            order.append(n_)
+            placed[n_] = off
+            off += named[n_].numel()
+        total = pad_to(off)
         assert set(order) == set(named), set(named) ^ set(order)
-        total = sum(named[n].numel() for n in order)
-        self.flat = torch.empty(total, device=self.device, dtype=torch.float32)
+        self.flat = torch.zeros(total, device=self.device, dtype=torch.float32)
         self.flat_grad = torch.zeros(total, device=self.device, dtype=torch.float32)
-        self.flat_bf16 = torch.empty(total, device=self.device, dtype=torch.bfloat16)
+        self.flat_bf16 = torch.zeros(total, device=self.device, dtype=torch.bfloat16)
         self.offsets = {}
         self._grad_views = []             # (parameter, its view of the flat gradient buffer)
-        off = 0
         for n in order:
             p = named[n]
             k = p.numel()
+            off = placed[n]
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.flat_grad[off:off + k].view(p.shape)
             self._grad_views.append((p, p.grad))
             self.offsets[n] = (off, k)
-            off += k
         self.order = order
-        self.head_slice = (self.block_slices[-1][1], self.offsets["mask_emb"][0])       # ln_f + head
-        self.emb_slice = (self.offsets["mask_emb"][0], total)
+        self.head_slice = (head_start, emb_start)                                       # ln_f + head (+ pad)
+        self.emb_slice = (emb_start, total)
         # all-reduce buckets: contiguous groups of blocks, in the order backward finishes them (last block first)
         n_layers = len(self.modes)
         n_buckets = max(1, min(n_buckets, n_layers))
         edges = [round(i * n_layers / n_buckets) for i in range(n_buckets + 1)]
         self.chunks = [(edges[i], edges[i + 1]) for i in range(n_buckets)]
+        self.masters_dirty = False        # sharded exchange: other ranks' shards of the fp32 masters are stale here
         self._build_structs()
         self.refresh_operands()
         self._saved = None
@@ -98,6 +124,8 @@ class TrainState:
         self._grad_torch_version = self.flat_grad._version
         self.comm_stream = torch.cuda.Stream(device=self.device)
         self.update_ctas = 48             # grid of the background AdamW kernels (train_step(overlap_update=True))
+        self._comm_ev = None              # (before, after) events around the main stream's wait for the exchange stream
+        self._sharded_last = False
         model.__dict__["_train_state"] = self          # found again by Net2NetTransformer.training_step
 
     # ---- pointer tables for the C engine ---------------------------------------------------------------------------
@@ -122,6 +150,7 @@ class TrainState:
 
     def refresh_operands(self):
         """fp32 masters -> bf16 tensor-core operands, one kernel over the flat buffer (after every optimizer step)."""
+        self.sync_masters()
         call("mebt_cast_f32_to_bf16", self.flat.data_ptr(), self.flat_bf16.data_ptr(), self.flat.numel() // 4 * 4,
              torch.cuda.current_stream().cuda_stream)
         self._op_version = self._param_versions()
@@ -194,7 +223,7 @@ class TrainState:
             self._grads_dirty = False
         return self._grads_dirty
 
-    def backward(self, dlogits, accumulate=False, world_size=1, optimizer=None):
+    def backward(self, dlogits, accumulate=False, world_size=1, optimizer=None, sharded=False):
         """Stack + stem backward into the flat gradient buffer; with world_size > 1 each finished chunk of blocks is
         all-reduced (averaged) on a side stream while the next chunk runs.  With a `FlatAdamW` passed as `optimizer` the
         parameter update of a finished chunk is issued on that side stream too, right behind its all-reduce: blocks
@@ -228,6 +257,11 @@ class TrainState:
                  d_lat.data_ptr(), d_ctx.data_ptr(), d_tgt.data_ptr(), lb, le, int(accumulate),
                  ctypes.byref(drop) if drop is not None else None, ws.data_ptr(), ws.numel(), cur.cuda_stream)
             lo, hi = self.block_slices[lb][0], self.block_slices[le - 1][1]
+            if sharded:
+                self._exchange_sharded(optimizer, lo, hi, cur)
+                if le == n:
+                    self._exchange_sharded(optimizer, *self.head_slice, cur)
+                continue
             if world_size > 1:
                 works.append(self._all_reduce_async(lo, hi, cur))
                 if le == n:
@@ -242,12 +276,20 @@ class TrainState:
         g = lambda name: self._view(self.flat_grad, name)
         ops.embed_backward(x_indices, ctx_idx, tgt_idx, d_ctx, d_tgt, d_lat, g("tok_emb.weight").view(-1, self.D),
                            g("pos_emb").view(-1, self.D), g("mask_emb"), g("sos_emb").view(-1, self.D))
-        if world_size > 1:
-            works.append(self._all_reduce_async(*self.emb_slice, cur))
-        if optimizer is not None:
-            self._update_async(optimizer, *self.emb_slice, cur, background=False)
+        if sharded:
+            self._exchange_sharded(optimizer, *self.emb_slice, cur)
+        else:
+            if world_size > 1:
+                works.append(self._all_reduce_async(*self.emb_slice, cur))
+            if optimizer is not None:
+                self._update_async(optimizer, *self.emb_slice, cur, background=False)
         if world_size > 1 or optimizer is not None:
+            if self._comm_ev is None:
+                self._comm_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self._comm_ev[0].record(cur)
             cur.wait_stream(self.comm_stream)
+            self._comm_ev[1].record(cur)
+        self._sharded_last = bool(sharded)
         self.relink_grads()
         self._pending = False
         self._grads_dirty = True
@@ -263,6 +305,49 @@ class TrainState:
         with torch.cuda.stream(self.comm_stream):
             optimizer.step_range(lo, hi, self.update_ctas if background else 0)
 
+    def _exchange_sharded(self, optimizer, lo, hi, producer_stream):
+        """One bucket of the sharded exchange, on the side stream behind the kernels that produced its gradients:
+        reduce-scatter (mean over ranks, fp32) -> AdamW + bf16 operand refresh of THIS rank's 1/world shard ->
+        all-gather of the bucket's bf16 operands.  What the reference's DDP all-reduce + replicated optimizer.step()
+        compute (train_transformer.py:39-41, transformer.py:749-798), with the optimizer's HBM traffic divided by the
+        world size and 3/4 of the bytes on the wire.  The fp32 masters of the other ranks' shards go stale here until
+        `sync_masters()`; the bf16 operands, which are all the forward / backward read, are complete on every rank."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        a, b = parallel.shard_bounds(lo, hi, rank, world)
+        self.comm_stream.wait_stream(producer_stream)
+        with torch.cuda.stream(self.comm_stream):
+            parallel.reduce_scatter_mean_(self.flat_grad[lo:hi])
+            optimizer.step_range(a, b, 0)
+            parallel.all_gather_shards_(self.flat_bf16[lo:hi])
+        self.masters_dirty = True
+
+    def sync_masters(self):
+        """After sharded steps: all-gather the fp32 masters so that `model.parameters()` / `state_dict()` / a rebuilt
+        inference pack see every rank's updates (a no-op otherwise).  Collective: every rank must call it."""
+        if not self.masters_dirty:
+            return
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.comm_stream)
+        for lo, hi in parallel.bucket_slices(self.block_slices, self.chunks, self.head_slice, self.emb_slice):
+            parallel.all_gather_shards_(self.flat[lo:hi])
+        self.masters_dirty = False
+        _lib.bump_write_epoch()
+
+    def comm_report(self):
+        """Exposed exchange time of the last step: how long the compute stream waited for the exchange stream at the end
+        of backward (ms), and the exchange used."""
+        if self._comm_ev is None:
+            return None
+        torch.cuda.synchronize()
+        return dict(exposed_ms=self._comm_ev[0].elapsed_time(self._comm_ev[1]),
+                    exchange="reduce-scatter / sharded AdamW / bf16 all-gather" if self._sharded_last else "all-reduce")
+
+    def exchange_desc(self, world):
+        nb = len(self.chunks) + 2
+        return (f"{nb} buckets ({len(self.chunks)} block chunks + head + embeddings): fp32 NCCL reduce-scatter (AVG) -> fused AdamW "
+                f"on the 1/{world} shard -> bf16 all-gather of the operands, per bucket on a side stream behind backward")
+
     def _all_reduce_async(self, lo, hi, producer_stream):
         """One gradient bucket: waits for the kernels that produced it, then averages it over ranks on the side
         stream so that it overlaps the rest of backward (the reference's DDP bucket all-reduce)."""
@@ -272,7 +357,7 @@ class TrainState:
             # for the collective, so that later work on it (the chunk's AdamW) and `wait_stream` see averaged gradients
             return parallel.allreduce_mean_(self.flat_grad[lo:hi], async_op=False)
 
-    def loss_and_backward(self, x_indices, indices, t=None, world_size=1, defer_backward=False, optimizer=None):
+    def loss_and_backward(self, x_indices, indices, t=None, world_size=1, defer_backward=False, optimizer=None, sharded=False):
         """shared_step + backward fused: -> dict(loss, acc1, acc5, ratio) as device tensors / floats.
         loss = CE_sum / (B * seq_len * ratio**avg_loss) (mebt/transformer.py:723-730).
         defer_backward=True stops after the loss and returns (dict, dlogits) for a later `backward(dlogits)`
@@ -293,7 +378,7 @@ class TrainState:
         out = dict(loss=stats[0] * scale, acc1=stats[1] * (100.0 / n), acc5=stats[2] * (100.0 / n), ratio=ratio)
         if defer_backward:
             return out, logits                                  # logits now hold d(loss)/d(logits)
-        self.backward(logits, world_size=world_size, optimizer=optimizer)
+        self.backward(logits, world_size=world_size, optimizer=optimizer, sharded=sharded)
         return out
 
     def make_optimizer(self, lr=1.08e-5, weight_decay=0.01, flat=True):
@@ -307,11 +392,17 @@ class TrainState:
             return torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.95), fused=True)
         return FlatAdamW(self, groups, lr=lr, betas=(0.9, 0.95), weight_decay=weight_decay)
 
-    def train_step(self, optimizer, x_indices, indices, t=None, world_size=1, overlap_update=False):
+    def train_step(self, optimizer, x_indices, indices, t=None, world_size=1, overlap_update=False, sharded=True):
         """fwd + loss + bwd (+ all-reduce) + AdamW + operand refresh.  Returns the loss statistics.
         overlap_update=True (FlatAdamW only) issues the update of each finished chunk of blocks on the side stream while
         backward continues; measured on B200 at the 16-frame shapes it gains 0.8 % per step (13.81 -> 13.70 ms) because the
         HBM-bound update slows the latency-bound backward kernels it overlaps, so it is off by default."""
+        if isinstance(optimizer, FlatAdamW) and world_size > 1 and sharded:
+            # data parallel with the fused optimizer: reduce-scatter -> AdamW on this rank's shard -> bf16 all-gather
+            optimizer.begin_step()
+            out = self.loss_and_backward(x_indices, indices, t, world_size, optimizer=optimizer, sharded=True)
+            self._grads_dirty = False
+            return out
         if isinstance(optimizer, FlatAdamW) and overlap_update:
             optimizer.begin_step()
             return self.loss_and_backward(x_indices, indices, t, world_size, optimizer=optimizer)
@@ -340,7 +431,7 @@ class FlatAdamW:
         decayed = {name_of[id(p)] for g in groups if g["weight_decay"] > 0 for p in g["params"]}
         edges = sorted({o for o, _ in ts.offsets.values()} | {o + k for o, k in ts.offsets.values()})
         shift = 2
-        while all(e % (1 << (shift + 1)) == 0 for e in edges) and shift < 20:
+        while all(e % (1 << (shift + 1)) == 0 for e in edges) and shift < 20 and (1 << (shift + 1)) <= ts.align // 8:
             shift += 1
         self.shift = shift
         n = ts.flat.numel()
