@@ -518,6 +518,23 @@ class Net2NetTransformer(_Base):
             self.log(name, v, prog_bar=True, logger=True, on_step=True, on_epoch=True, sync_dist=True)
         return loss
 
+    # After data-parallel steps with the sharded exchange (TrainState.train_step, world > 1) each rank holds fresh fp32
+    # masters only for its own shard; anything that reads the parameters themselves first gathers them (collective:
+    # like the reference's DDP, every rank enters eval / state_dict together).
+    def _sync_masters(self):
+        ts = self.__dict__.get("_train_state")
+        if ts is not None and ts.masters_dirty:
+            ts.sync_masters()
+
+    def train(self, mode: bool = True):
+        if not mode:
+            self._sync_masters()
+        return super().train(mode)
+
+    def state_dict(self, *args, **kwargs):
+        self._sync_masters()
+        return super().state_dict(*args, **kwargs)
+
     def validation_step(self, batch, batch_idx):
         acc1, acc5, loss, ratio = self.shared_step(batch, batch_idx)
         for name, v in (("val/loss", loss), ("val/acc1", acc1), ("val/acc5", acc5)):

@@ -254,3 +254,15 @@ def test_training_step_refuses_a_stale_backward():
     with pytest.raises(MebtError, match="another forward"):
         first.backward()
     second.backward()
+
+
+def test_maskgit_block_mode_training_is_refused():
+    """The `maskgit` Block mode (gpt.py:176-178,191-192: one self-attending stream over cat[contexts, targets]) runs on the
+    inference engine only; no shipped config of the reference uses it (configs/*/*.yaml list the four latent modes).
+    Training such a stack must fail loudly and at construction, never fall back to another path."""
+    from mebt_b200.training import TrainState
+    cfg = dict(n_embd=128, n_head=2, sos_emb=16, block_size=64, shape=[1, 8, 8], n_layer=2, vocab_size=256, avg_loss=1.0,
+               mode=["maskgit", "maskgit"])
+    model = build_model(cfg).train()
+    with pytest.raises(NotImplementedError, match="four latent block modes"):
+        TrainState(model)
