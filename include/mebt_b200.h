@@ -187,6 +187,18 @@ size_t mebt_vq_argmin_workspace_bytes(long long M);
  */
 int mebt_vq_argmin(const float* z_channel_first, int batch, int C, int S, const float* E, const float* e_sqnorm, int K,
                    int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * The same search on the tensor cores (the default of Codebook.forward): z.E^T as ONE fp16 tcgen05 GEMM over operands split
+ * into fp16 (hi, lo) halves, reduction dimension 3C ([z_hi|z_lo|z_hi].[e_hi|e_hi|e_lo]^T, fp32 accumulation, relative
+ * 2^-21 per product), with the distance (|z|^2 - 2 z.e) + |e|^2 and the running argmin as the GEMM epilogue; lowest index
+ * on exact ties.  e_split: the codebook in that form, fp16 [K, 3C], made once per codebook by mebt_vq_split_codebook
+ * (mebt_vq_codebook_split_bytes bytes).  C and K multiples of 64.
+ */
+size_t mebt_vq_codebook_split_bytes(int K, int C);
+int mebt_vq_split_codebook(const float* E, int K, int C, void* e_split, void* stream);
+size_t mebt_vq_argmin_tc_workspace_bytes(long long M, int C);
+int mebt_vq_argmin_tc(const float* z_channel_first, int batch, int C, int S, const void* e_split, const float* e_sqnorm,
+                      int K, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K3 : latent attention --------------------------------------------------------------------- */
 /*

@@ -65,6 +65,9 @@ _SIGNATURES: dict[str, list] = {
     "mebt_row_sqnorm": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "mebt_vq_argmin": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
                        c_void_p],
+    "mebt_vq_split_codebook": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "mebt_vq_argmin_tc": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                          c_void_p],
     "mebt_latent_attention_fwd": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                   c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
@@ -167,6 +170,10 @@ _lib.mebt_stack_forward_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, 
 _lib.mebt_stack_forward_workspace_bytes.restype = c_size_t
 _lib.mebt_vq_argmin_workspace_bytes.argtypes = [c_longlong]
 _lib.mebt_vq_argmin_workspace_bytes.restype = c_size_t
+_lib.mebt_vq_argmin_tc_workspace_bytes.argtypes = [c_longlong, c_int]
+_lib.mebt_vq_argmin_tc_workspace_bytes.restype = c_size_t
+_lib.mebt_vq_codebook_split_bytes.argtypes = [c_int, c_int]
+_lib.mebt_vq_codebook_split_bytes.restype = c_size_t
 
 
 def version() -> str:

@@ -20,6 +20,7 @@ namespace mebt {
 
 namespace {
 
+constexpr int MEBT_GEMM_INTERNAL_ARGMIN = 1 << 30;   // not part of the C ABI
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
@@ -53,6 +54,11 @@ struct GemmParams {
                                        // 3 attention output O (the epilogue also emits delta = rowsum_head(C .* O))
   float* delta_out;                    // in_kind 3: [B, H, NQ] fp32, rows of C are (b, q), 64-column groups are heads
   int delta_nq, delta_h;
+  int fp16_in;                         // operands are fp16 (kind::f16 A/B format 0) instead of bf16
+  // nearest-code search (K9): no C; per row the running minimum of d = (row_sq[row] - 2 acc) + bias[col] over all
+  // columns, merged across tiles by a 64-bit atomicMin on (orderable d bits << 32 | col)
+  unsigned long long* argmin_out;
+  const float* row_sq;
   // split-K: `splits` CTAs share one output tile; each writes its fp32 partial accumulator to `partials`
   // ([tile][split][128][BN]) and the last one to arrive (per-tile counter) sums them in split order and runs the
   // epilogue.  Deterministic: the summation order does not depend on arrival order.
@@ -257,7 +263,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0 && pair_rank == 0) {       // pair mode: only the leader CTA issues
-      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0) &
+                             (p.fp16_in ? ~((1u << 7) | (1u << 10)) : ~0u);            // A/B format: 1 = bf16, 0 = fp16
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -400,6 +407,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (*split_flag == 0) continue;
         __threadfence();
         my_partials = p.partials + size_t(tile) * p.splits * BM * BN + size_t(q * 32 + lane) * 4;
+      }
+      if (p.argmin_out != nullptr) {
+        // K9 epilogue: nothing is stored but each row's best (distance, code) over this tile's columns
+        const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+        const float zq = row_ok ? __ldg(p.row_sq + row) : 0.f;
+        float bestd = INFINITY;
+        int besti = 0x7fffffff;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_acc + uint32_t(c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            // the reference's expression order: (|z|^2 - 2 z.e) + |e|^2  (codebook.py:53-55)
+            const float d = (zq - 2.0f * __uint_as_float(r[j])) + s_bias[c * 32 + j];
+            if (d < bestd) { bestd = d; besti = n0 + c * 32 + j; }      // columns ascending: the first minimum wins
+          }
+        }
+        tc_fence_before();
+        if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+        if (row_ok && besti != 0x7fffffff) {
+          const uint32_t u = __float_as_uint(bestd);
+          const uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+          atomicMin(p.argmin_out + row, (static_cast<unsigned long long>(key) << 32) | uint32_t(besti));
+        }
+        continue;
       }
       // One 32-column chunk of this thread's row: bias, GELU / GELU', residual, store.
       auto finish_chunk = [&](float (&v)[32], int c) {
@@ -702,7 +737,7 @@ int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda,
   if (rc) return rc;
   // epilogue operands: 128-byte-wide boxes of the tile's 128 rows (one per chunk)
   CUtensorMap tc = ta, taux = ta, tin = ta;
-  if (p.splits == 1) {
+  if (p.splits == 1 && p.argmin_out == nullptr) {
     if (p.out_fp32) rc = get_tensor_map_2d(&tc, p.C, 4, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldc) * 4, 32, 128);
     else            rc = get_tensor_map_2d(&tc, p.C, 2, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldc) * 2, 64, 128);
     if (rc) return rc;
@@ -846,8 +881,17 @@ int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b
   MEBT_REQUIRE(aux == nullptr || ldaux % 8 == 0, MEBT_ERR_SHAPE, "gemm: ldaux must be a multiple of 8");
   MEBT_REQUIRE(!(p.dgelu && residual != nullptr) && !(out_fp32 && (p.dgelu || residual != nullptr)), MEBT_ERR_UNSUPPORTED,
                "gemm: the epilogue reads one bf16 operand (residual or gelu' input) and only with bf16 output");
-  p.in_kind = residual != nullptr ? 1 : (p.dgelu ? 2 : 0);
+  p.in_kind = (residual != nullptr && !(flags & MEBT_GEMM_INTERNAL_ARGMIN)) ? 1 : (p.dgelu ? 2 : 0);
   p.delta_out = delta_out; p.delta_nq = delta_nq; p.delta_h = delta_h;
+  p.fp16_in = 0; p.argmin_out = nullptr; p.row_sq = nullptr;
+  if (flags & MEBT_GEMM_INTERNAL_ARGMIN) {          // gemm_f16_argmin below: C carries the packed output, residual the row norms
+    p.fp16_in = 1;
+    p.argmin_out = static_cast<unsigned long long*>(C);
+    p.row_sq = reinterpret_cast<const float*>(residual);
+    p.residual = nullptr;
+    p.C = nullptr;
+    flags |= MEBT_GEMM_NO_SPLITK;
+  }
   if (delta_out != nullptr) {
     MEBT_REQUIRE(aux != nullptr && residual == nullptr && !p.gelu && !p.dgelu && !out_fp32 && bias == nullptr &&
                  delta_nq > 0 && M % delta_nq == 0 && N == 64 * delta_h, MEBT_ERR_UNSUPPORTED,
@@ -915,6 +959,15 @@ int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b
     case 128: return dispatch_major<128>(a_mn, b_mn, A, B, p, lda, ldb, stream);
     default: return dispatch_major<64>(a_mn, b_mn, A, B, p, lda, ldb, stream);
   }
+}
+
+// K9 on the tensor cores: packed[row] = min over codes n of (order(d) << 32 | n), d = (row_sq[row] - 2 A[row].B[n]) + col_sq[n],
+// with fp16 operands (A [M, K] and B [N, K] K-major; see csrc/vq.cu for the split that makes the products fp32-accurate).
+int gemm_f16_argmin(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* col_sq,
+                    const float* row_sq, unsigned long long* packed, cudaStream_t stream) {
+  MEBT_REQUIRE(col_sq != nullptr && row_sq != nullptr && packed != nullptr, MEBT_ERR_SHAPE, "gemm_f16_argmin: null operand");
+  return gemm_bf16_ex(A, lda, 0, B, ldb, 0, packed, 8, M, N, K, col_sq, row_sq, 8, nullptr, 0, MEBT_GEMM_INTERNAL_ARGMIN, nullptr,
+                      nullptr, 0, 0, stream);
 }
 
 }  // namespace mebt

@@ -4,6 +4,8 @@
 //      reference: F.cross_entropy(sum) at mebt/transformer.py:726 and accuracy() at mebt/utils.py:80-94
 //   K6 temperature / top-k / softmax / Exp-race ("Gumbel") argmax / confidence score
 //      reference: sample_from_logits + gumbel_sort, mebt/transformer.py:843-889 / :826-841
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mebt {
@@ -224,6 +226,143 @@ __global__ void __launch_bounds__(CE_T, 3) masked_ce_bf16_kernel(const __nv_bflo
         *reinterpret_cast<uint4*>(dr + c) = o;
       }
     }
+  }
+}
+
+// K5, bf16 logits, V <= 16384: PERSISTENT CTAs (two per SM) that stream rows through a two-deep shared-memory ring filled
+// by 1-D bulk copies, so that the load of row r+1 is in flight during the whole of row r's arithmetic and stores (the
+// one-row-per-CTA kernel above has no load outstanding while it reduces, exponentiates and stores: 0.41 of the HBM
+// peak).  Each exponential is computed once and kept as packed fp16 (the gradient is stored as bf16: 8 mantissa bits).
+constexpr int CE_ROW_BYTES = 16384 * 2;
+constexpr int CE_STAGES = 3;          // rows in flight per CTA (two CTAs per SM: 192 KiB of the 227)
+__global__ void __launch_bounds__(CE_T, 2) masked_ce_bf16_stream_kernel(const __nv_bfloat16* __restrict__ logits, long long ld,
+                                                                     const int64_t* __restrict__ targets, int V, int rows,
+                                                                     float smoothing, float* __restrict__ row_loss,
+                                                                     int* __restrict__ row_rank, __nv_bfloat16* dlogits,
+                                                                     long long ldd, float grad_scale) {
+  extern __shared__ __align__(128) uint8_t ce_smem[];
+  __shared__ float red_a[CE_T / 32], red_b[CE_T / 32];
+  __shared__ int red_i[CE_T / 32];
+  __shared__ __align__(8) uint64_t bar[CE_STAGES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t row_bytes = uint32_t(V) * 2u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < CE_STAGES; ++i) mbar_init(&bar[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  griddep_wait();
+  long long row = blockIdx.x;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < CE_STAGES - 1; ++i) {
+      const long long r = row + (long long)i * gridDim.x;
+      if (r < rows) {
+        mbar_arrive_expect_tx(&bar[i], row_bytes);
+        bulk_load_1d(ce_smem + i * CE_ROW_BYTES, logits + r * ld, row_bytes, &bar[i]);
+      }
+    }
+  }
+  for (int it = 0; row < rows; row += gridDim.x, ++it) {
+    const int buf = it % CE_STAGES;
+    const long long ahead = row + (long long)(CE_STAGES - 1) * gridDim.x;
+    const int abuf = (it + CE_STAGES - 1) % CE_STAGES;
+    // buffer abuf was last read in iteration it-1, which copied its row into registers before that iteration's barriers
+    if (threadIdx.x == 0 && ahead < rows) {
+      mbar_arrive_expect_tx(&bar[abuf], row_bytes);
+      bulk_load_1d(ce_smem + abuf * CE_ROW_BYTES, logits + ahead * ld, row_bytes, &bar[abuf]);
+    }
+    const int tgt = int(targets[row]);
+    mbar_wait(&bar[buf], uint32_t(it / CE_STAGES) & 1u);
+    const uint8_t* sr = ce_smem + buf * CE_ROW_BYTES;
+    uint4 v[8];
+    float m = -INFINITY, total = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = (threadIdx.x + CE_T * i) * 8;
+      if (c < V) {
+        v[i] = *reinterpret_cast<const uint4*>(sr + size_t(c) * 2);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16x2(w[k]);
+          m = fmaxf(m, fmaxf(f.x, f.y));
+          total += f.x + f.y;
+        }
+      }
+    }
+    const float xt = (tgt >= 0 && tgt < V) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(sr)[tgt]) : 0.f;
+    m = warp_max(m);
+    total = warp_sum(total);
+    if (lane == 0) { red_a[warp] = m; red_b[warp] = total; }
+    __syncthreads();
+    m = red_a[0];
+    total = red_b[0];
+#pragma unroll
+    for (int i = 1; i < CE_T / 32; ++i) { m = fmaxf(m, red_a[i]); total += red_b[i]; }
+    __syncthreads();
+    const float ml2 = m * 1.4426950408889634f;
+    float se = 0.f;
+    int rank = 0;
+    uint32_t e16[32];                                         // exp(x - max) as packed fp16 pairs
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = (threadIdx.x + CE_T * i) * 8;
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float e0 = 0.f, e1 = 0.f;
+        if (c < V) {
+          const float2 f = unpack_bf16x2(w[k]);
+          e0 = ex2_approx(fmaf(f.x, 1.4426950408889634f, -ml2));
+          e1 = ex2_approx(fmaf(f.y, 1.4426950408889634f, -ml2));
+          se += e0 + e1;
+          rank += (f.x > xt) + (f.y > xt);
+        }
+        const __half2 h = __floats2half2_rn(e0, e1);
+        e16[4 * i + k] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    se = warp_sum(se);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (lane == 0) { red_a[warp] = se; red_i[warp] = rank; }
+    __syncthreads();
+    se = 0.f;
+    rank = 0;
+#pragma unroll
+    for (int i = 0; i < CE_T / 32; ++i) { se += red_a[i]; rank += red_i[i]; }     // fixed order: deterministic
+    if (threadIdx.x == 0) {
+      const float lse = m + logf(se);
+      const float nll = lse - xt;
+      const float smooth = lse - total / float(V);
+      row_loss[row] = (1.f - smoothing) * nll + smoothing * smooth;
+      if (row_rank != nullptr) row_rank[row] = rank;
+    }
+    if (dlogits != nullptr) {
+      // d(sum CE)/dlogit_v = softmax_v - (1-eps) [v == t] - eps / V, times the upstream scale (may overwrite the logits:
+      // the row was read completely, into shared memory, before its first store)
+      __nv_bfloat16* dr = dlogits + row * ldd;
+      const float inv = grad_scale / se, u = grad_scale * smoothing / float(V), hot = grad_scale * (1.f - smoothing);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = (threadIdx.x + CE_T * i) * 8;
+        if (c < V) {
+          uint4 o;
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&e16[4 * i + k]));
+            float g0 = fmaf(e.x, inv, -u);
+            float g1 = fmaf(e.y, inv, -u);
+            if (tgt == c + 2 * k) g0 -= hot;
+            if (tgt == c + 2 * k + 1) g1 -= hot;
+            ow[k] = pack_bf16x2(g0, g1);
+          }
+          *reinterpret_cast<uint4*>(dr + c) = o;
+        }
+      }
+    }
+    __syncthreads();                                          // red_* are reused by the next row
   }
 }
 
@@ -713,7 +852,18 @@ int mebt_masked_ce(const void* logits, long long ld, int dtype, const int64_t* t
   if (dtype == MEBT_DTYPE_FP32)
     masked_ce_kernel<float><<<rows, LT, 0, st>>>(static_cast<const float*>(logits), ld, targets, V, label_smoothing,
                                                  row_loss, row_rank, static_cast<float*>(dlogits), ld_d, grad_scale);
-  else if (dtype == MEBT_DTYPE_BF16 && V % 8 == 0 && V <= CE_T * 64 && ld % 8 == 0 && (dlogits == nullptr || ld_d % 8 == 0))
+  else if (dtype == MEBT_DTYPE_BF16 && V % 8 == 0 && V <= CE_T * 64 && ld % 8 == 0 && (dlogits == nullptr || ld_d % 8 == 0) &&
+           rows >= 2 * sm_count()) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      MEBT_CUDA_OK(cudaFuncSetAttribute(masked_ce_bf16_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_STAGES * CE_ROW_BYTES));
+      attr_set = true;
+    }
+    const int grid = rows < 2 * sm_count() ? rows : 2 * sm_count();
+    masked_ce_bf16_stream_kernel<<<grid, CE_T, CE_STAGES * CE_ROW_BYTES, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, targets,
+                                                                      V, rows, label_smoothing, row_loss, row_rank,
+                                                                      static_cast<__nv_bfloat16*>(dlogits), ld_d, grad_scale);
+  } else if (dtype == MEBT_DTYPE_BF16 && V % 8 == 0 && V <= CE_T * 64 && ld % 8 == 0 && (dlogits == nullptr || ld_d % 8 == 0))
     masked_ce_bf16_kernel<<<rows, CE_T, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, targets, V, label_smoothing,
                                                  row_loss, row_rank, static_cast<__nv_bfloat16*>(dlogits), ld_d, grad_scale);
   else if (dtype == MEBT_DTYPE_BF16)

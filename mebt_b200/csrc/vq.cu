@@ -10,9 +10,15 @@
 // Tiling: CTA = 64 latent vectors x CODES_PER_CTA codes, 256 threads, 4x4 register micro-tiles, the
 // z tile (64 x C) resident in shared memory, code tiles (64 x 16) streamed.  Partial winners are merged
 // across CTAs with a 64-bit atomicMin on (orderable distance bits << 32 | index).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mebt {
+
+int gemm_f16_argmin(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* col_sq,
+                    const float* row_sq, unsigned long long* packed, cudaStream_t stream);
+
 namespace {
 
 constexpr int VQ_BM = 64;        // latent vectors per CTA
@@ -146,6 +152,61 @@ __global__ void __launch_bounds__(VQ_THREADS) vq_argmin_kernel(const float* __re
   }
 }
 
+
+// ---- K9 on the tensor cores ------------------------------------------------------------------------------------
+// fp32 x = hi + lo + r with hi = fp16(x), lo = fp16(x - hi), |r| <= 2^-22 |x|: the dot product z.e becomes ONE fp16
+// GEMM with the reduction dimension tripled,
+//     [z_hi | z_lo | z_hi] . [e_hi | e_hi | e_lo]^T = z_hi e_hi + z_lo e_hi + z_hi e_lo        (fp32 accumulation in TMEM)
+// which drops lo.lo and the residuals: relative 2^-21 per product, 8 ulp of an fp32 product - far below the 1e-3 gap
+// under which tests accept a flipped near-tie (bf16 halves would give 2^-15 and do flip them).  The distance and the
+// running argmin are the GEMM's epilogue (csrc/gemm.cu, argmin_out), in the reference's expression order.
+
+// z [b, C, S] fp32 channel-first -> A [b*S, 3C] fp16 rows (hi | lo | hi) and |z|^2 per row (fp32, channels in order).
+// One CTA transposes a [C x 32] slab through shared memory: coalesced along s on the way in, along c on the way out.
+__global__ void __launch_bounds__(256) vq_split_z_kernel(const float* __restrict__ z, int C, int S, __half* __restrict__ A,
+                                                         float* __restrict__ zsq) {
+  extern __shared__ float tile[];                    // [C][33]
+  const int b = blockIdx.y, s0 = blockIdx.x * 32;
+  const float* zb = z + (size_t)b * C * S;
+  for (int i = threadIdx.x; i < C * 32; i += 256) {
+    const int c = i >> 5, s = i & 31;
+    tile[c * 33 + s] = (s0 + s < S) ? zb[(size_t)c * S + s0 + s] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int s = warp; s < 32 && s0 + s < S; s += 8) {
+    __half* row = A + ((size_t)b * S + s0 + s) * 3 * C;
+    for (int c = lane; c < C; c += 32) {
+      const float x = tile[c * 33 + s];
+      const __half hi = __float2half_rn(x);
+      const __half lo = __float2half_rn(x - __half2float(hi));
+      row[c] = hi;
+      row[C + c] = lo;
+      row[2 * C + c] = hi;
+    }
+  }
+  if (threadIdx.x < 32 && s0 + threadIdx.x < S) {    // |z|^2: sequential over channels, like the FFMA kernel
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) { const float v = tile[c * 33 + threadIdx.x]; a += v * v; }
+    zsq[(size_t)b * S + s0 + threadIdx.x] = a;
+  }
+}
+
+// E [K, C] fp32 -> B [K, 3C] fp16 rows (hi | hi | lo)
+__global__ void vq_split_e_kernel(const float* __restrict__ E, long long n, int C, __half* __restrict__ B) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = int(i - r * C);
+    const float x = E[i];
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn(x - __half2float(hi));
+    __half* row = B + r * 3 * C;
+    row[c] = hi;
+    row[C + c] = hi;
+    row[2 * C + c] = lo;
+  }
+}
+
 }  // namespace
 }  // namespace mebt
 
@@ -188,6 +249,57 @@ int mebt_vq_argmin(const float* z_channel_first, int batch, int C, int S, const 
   LaunchScope ls(FAM_VQ, 2.0 * double(M) * double(K) * double(C), st);
   vq_argmin_kernel<<<grid, VQ_THREADS, smem, st>>>(z_channel_first, S, C, E, e_sqnorm, K, M, codes_per_cta, packed);
   MEBT_LAUNCH_OK("vq_argmin_kernel");
+  vq_unpack_kernel<<<int((M + 255) / 256), 256, 0, st>>>(packed, out_idx, M);
+  MEBT_LAUNCH_OK("vq_unpack_kernel");
+  return MEBT_OK;
+}
+
+
+/* ---- tensor-core path ---- */
+size_t mebt_vq_codebook_split_bytes(int K, int C) { return size_t(K) * 3 * C * 2; }
+
+int mebt_vq_split_codebook(const float* E, int K, int C, void* e_split, void* stream) {
+  MEBT_REQUIRE(K > 0 && C > 0, MEBT_ERR_SHAPE, "vq_split_codebook: bad shape");
+  const long long n = (long long)K * C;
+  mebt::vq_split_e_kernel<<<int((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      E, n, C, static_cast<__half*>(e_split));
+  MEBT_LAUNCH_OK("vq_split_e_kernel");
+  return MEBT_OK;
+}
+
+size_t mebt_vq_argmin_tc_workspace_bytes(long long M, int C) {
+  return ((size_t(M) * 3 * C * 2 + 255) & ~size_t(255)) + ((size_t(M) * 4 + 255) & ~size_t(255)) + size_t(M) * 8;
+}
+
+int mebt_vq_argmin_tc(const float* z_channel_first, int batch, int C, int S, const void* e_split, const float* e_sqnorm,
+                      int K, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace mebt;
+  const long long M = (long long)batch * S;
+  MEBT_REQUIRE(batch >= 0 && S >= 0 && C > 0 && C % 64 == 0 && C <= 1024 && K > 0 && K % 64 == 0, MEBT_ERR_SHAPE,
+               "vq_argmin_tc: bad shape batch=%d C=%d S=%d K=%d (C and K must be multiples of 64)", batch, C, S, K);
+  if (M == 0) return MEBT_OK;
+  MEBT_REQUIRE(M < (1ll << 31), MEBT_ERR_SHAPE, "vq_argmin_tc: too many vectors");
+  MEBT_REQUIRE(workspace != nullptr && workspace_bytes >= mebt_vq_argmin_tc_workspace_bytes(M, C), MEBT_ERR_WORKSPACE,
+               "vq_argmin_tc: workspace too small (%zu < %zu)", workspace_bytes, mebt_vq_argmin_tc_workspace_bytes(M, C));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* W = static_cast<char*>(workspace);
+  __half* A = reinterpret_cast<__half*>(W);
+  float* zsq = reinterpret_cast<float*>(W + ((size_t(M) * 3 * C * 2 + 255) & ~size_t(255)));
+  unsigned long long* packed = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(zsq) + ((size_t(M) * 4 + 255) & ~size_t(255)));
+  const size_t smem = size_t(C) * 33 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    MEBT_CUDA_OK(cudaFuncSetAttribute(vq_split_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+    attr = true;
+  }
+  {
+    LaunchScope ls(FAM_VQ, 0.0, st);
+    vq_split_z_kernel<<<dim3((S + 31) / 32, batch), 256, smem, st>>>(z_channel_first, C, S, A, zsq);
+    MEBT_LAUNCH_OK("vq_split_z_kernel");
+    vq_init_kernel<<<int((M + 255) / 256), 256, 0, st>>>(packed, M);
+  }
+  int rc = gemm_f16_argmin(A, 3 * C, e_split, 3 * C, int(M), K, 3 * C, e_sqnorm, zsq, packed, st);
+  if (rc) return rc;
   vq_unpack_kernel<<<int((M + 255) / 256), 256, 0, st>>>(packed, out_idx, M);
   MEBT_LAUNCH_OK("vq_unpack_kernel");
   return MEBT_OK;

@@ -26,17 +26,20 @@ class Codebook(nn.Module):
         self._sq = None
 
     def _sqnorm(self):
+        """(|E|^2 per code, the codebook's fp16 (hi | hi | lo) form for the tensor-core search), per codebook version."""
         key = (self.embeddings.data_ptr(), self.embeddings._version)
         if self._sq is None or self._sq[0] != key:
-            self._sq = (key, ops.row_sqnorm(self.embeddings))
-        return self._sq[1]
+            tc = self.embedding_dim % 64 == 0 and self.n_codes % 64 == 0 and self.embedding_dim <= 1024
+            self._sq = (key, ops.row_sqnorm(self.embeddings), ops.vq_split_codebook(self.embeddings) if tc else None)
+        return self._sq[1], self._sq[2]
 
     def forward(self, z):
         """z [b, c, t, h, w] fp32 -> dict(embeddings, encodings, commitment_loss, perplexity) (codebook.py:48-97)."""
         if self.training:
             raise NotImplementedError("mebt_b200.Codebook: EMA codebook training is out of scope; call .eval()")
         z = z.float().contiguous()
-        enc = ops.vq_argmin(z, self.embeddings, self._sqnorm())                  # [b, t, h, w] int64
+        sq, split = self._sqnorm()
+        enc = ops.vq_argmin(z, self.embeddings, sq, split)                      # [b, t, h, w] int64
         emb = ops.row_gather(enc, self.embeddings, channel_first=True)           # [b, c, t, h, w]
         commitment_loss = 0.25 * torch.mean((z - emb) ** 2)
         emb_st = (emb - z).detach() + z                                           # straight-through value

@@ -204,8 +204,19 @@ def row_sqnorm(E):
     return out
 
 
-def vq_argmin(z, E, e_sqnorm=None):
-    """z: [b, C, ...] fp32 channel-first; E: [K, C] fp32 -> encodings int64 [b, ...]."""
+def vq_split_codebook(E):
+    """E [K, C] fp32 -> the fp16 (hi | hi | lo) form [K, 3C] the tensor-core search multiplies by (once per codebook)."""
+    _need_cuda(E)
+    K, C = E.shape
+    out = torch.empty(K, 3 * C, device=E.device, dtype=torch.float16)
+    call("mebt_vq_split_codebook", E.contiguous().data_ptr(), K, C, out.data_ptr(), _stream())
+    return out
+
+
+def vq_argmin(z, E, e_sqnorm=None, e_split=None, tensor_cores=None):
+    """z: [b, C, ...] fp32 channel-first; E: [K, C] fp32 -> encodings int64 [b, ...].
+    tensor_cores (default: whenever C and K are multiples of 64): the fp16-split tcgen05 GEMM with the argmin epilogue;
+    False: the fp32 FFMA kernel (kept as the cross-check of the split arithmetic)."""
     _need_cuda(z, E)
     z = z.contiguous()
     b, C = z.shape[:2]
@@ -213,6 +224,17 @@ def vq_argmin(z, E, e_sqnorm=None):
     K = E.shape[0]
     if e_sqnorm is None:
         e_sqnorm = row_sqnorm(E)
+    if tensor_cores is None:
+        tensor_cores = C % 64 == 0 and K % 64 == 0 and C <= 1024
+    if tensor_cores:
+        if e_split is None:
+            e_split = vq_split_codebook(E)
+        out = torch.empty(b * S, device=z.device, dtype=torch.int64)
+        ws_bytes = _lib.lib.mebt_vq_argmin_tc_workspace_bytes(b * S, C)
+        ws = torch.empty(ws_bytes, device=z.device, dtype=torch.uint8)
+        call("mebt_vq_argmin_tc", z.data_ptr(), b, C, S, e_split.data_ptr(), e_sqnorm.data_ptr(), K, out.data_ptr(),
+             ws.data_ptr(), ws_bytes, _stream())
+        return out.view(b, *z.shape[2:])
     out = torch.empty(b * S, device=z.device, dtype=torch.int64)
     ws_bytes = _lib.lib.mebt_vq_argmin_workspace_bytes(b * S)
     ws = torch.empty(ws_bytes, device=z.device, dtype=torch.uint8)

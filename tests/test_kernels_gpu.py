@@ -231,14 +231,17 @@ def test_remask_sort_order_property(NT, ctemp):
     assert torch.equal(nt.cpu(), tgt.gather(1, order[:, n_new:]))
 
 
-def test_vq_argmin_and_gather_vs_reference_golden():
+@pytest.mark.parametrize("tensor_cores", [True, False])
+def test_vq_argmin_and_gather_vs_reference_golden(tensor_cores):
+    """Both search kernels against the reference's recorded encodings: the fp16-split tcgen05 GEMM with the argmin epilogue
+    (the default) and the fp32 FFMA kernel, under the same near-tie rule."""
     ops = _ops()
     z, _ = load_golden("codebook")
     torch.manual_seed(int(z["cb_seed"]))
     E = torch.randn(16384, 256)
     g = torch.Generator().manual_seed(int(z["z_seed"]))
     zz = torch.randn(2, 256, 4, 16, 16, generator=g)
-    enc = ops.vq_argmin(zz.cuda(), E.cuda())
+    enc = ops.vq_argmin(zz.cuda(), E.cuda(), tensor_cores=tensor_cores)
     ref = torch.from_numpy(z["encodings"])
     mism = (enc.cpu() != ref)
     gap = torch.from_numpy(z["gap"]).view_as(ref)
@@ -251,6 +254,27 @@ def test_vq_argmin_and_gather_vs_reference_golden():
     emb2 = ops.row_gather(ref.cuda(), E.cuda(), channel_first=False)
     assert torch.equal(emb2.cpu(), F.embedding(ref, E))
     ops.check_index_errors()
+
+
+def test_vq_argmin_tensor_cores_vs_float64():
+    """The split arithmetic on its own bar: against float64 distances every chosen code is the true nearest one or within
+    1e-4 of it (the fp32 rounding of d ~ 370 alone is 3e-5), on ragged sizes (rows not a multiple of the tile, a batch
+    boundary inside a tile) and with exact duplicates in the codebook (lowest index wins)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    E = torch.randn(4096, 128, generator=g)
+    E[77] = E[5]                                              # exact tie: index 5 must win over 77
+    z = torch.randn(3, 128, 1, 7, 13, generator=g)           # 91 vectors per batch element
+    z[0, :, 0, 0, 0] = E[77]                                  # a vector that sits exactly on the duplicated code
+    enc = ops.vq_argmin(z.cuda(), E.cuda(), tensor_cores=True).cpu()
+    flat = z.permute(0, 2, 3, 4, 1).reshape(-1, 128).double()
+    d = (flat ** 2).sum(1, keepdim=True) - 2 * flat @ E.double().t() + (E.double() ** 2).sum(1)[None]
+    best = d.min(1).values
+    chosen = d.gather(1, enc.reshape(-1, 1)).squeeze(1)
+    assert (chosen - best).max() < 1e-4, (chosen - best).max()
+    assert enc.reshape(-1)[0] == 5
+    enc_f = ops.vq_argmin(z.cuda(), E.cuda(), tensor_cores=False).cpu()
+    assert (enc != enc_f).sum() <= 1
 
 
 def _attn_ref(q, k, v):

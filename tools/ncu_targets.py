@@ -59,6 +59,12 @@ def main():
     kv2 = r(Bq * 256, 2 * D)
     for _ in range(1):
         ops.attention(q2, 0, kv2, 0, D, 256, None, 0, 0, 0, Bq, H, 8192)
+    # enc at the full 128-frame context (256 x 8192) and lt2l (256 latents x [256 latents + 8192 targets])
+    kv3 = r(Bq * 8192, 2 * D)
+    qkv3 = r(Bq * 256, 3 * D)
+    for _ in range(1):
+        ops.attention(q, 0, kv3, 0, D, 8192, None, 0, 0, 0, Bq, H, 256)
+        ops.attention(qkv3, 0, qkv3, D, 2 * D, 256, kv3, 0, D, 8192, Bq, H, 256)
     # training-step kernels at the 16-frame shapes (B = 6: 1536 latent rows, 3072 token rows)
     rows = 3072
     xs2, dy2 = r(rows, 1024), r(rows, 1024)
@@ -73,11 +79,21 @@ def main():
         ob = ops.attention(qb, D, kvb, 0, D, 512, None, 0, 0, 0, 6, H, 256, lse=lse, drop_p=0.1, drop_seed=3)
         ops.attention_bwd(qb, D, kvb, 0, D, 512, None, 0, 0, 0, ob, dob, lse, torch.zeros_like(qb), D, torch.zeros_like(kvb),
                           0, D, None, 0, 0, 6, H, 256, drop_p=0.1, drop_seed=3)
-    # K9/K10 codebook
+    # masked CE at the training shape (3072 rows: the streaming kernel) and the grouped weight-gradient launch of a block
+    lt = r(3072, 16384)
+    ops.masked_ce(lt, torch.randint(0, 16384, (3072,), device=dev), 0.0, dlogits=lt, grad_scale=1.0)
+    from mebt_b200 import _lib
+    if hasattr(ops, "grouped_wgrad"):
+        R = 1536
+        probs = [(r(R, 1024), r(R, 4096), torch.empty(1024, 4096, device=dev), False), (r(R, 4096), r(R, 1024), torch.empty(4096, 1024, device=dev), False),
+                 (r(R, 1024), r(R, 1024), torch.empty(1024, 1024, device=dev), False), (r(R, 3072), r(R, 1024), torch.empty(3072, 1024, device=dev), False)]
+        ops.grouped_wgrad(probs)
+    # K9/K10 codebook: tensor-core search (default) and the fp32 FFMA kernel
     E = torch.randn(16384, 256, device=dev)
-    z = torch.randn(8, 256, 4, 16, 16, device=dev)
+    z = torch.randn(64, 256, 4, 16, 16, device=dev)
     for _ in range(1):
         enc = ops.vq_argmin(z, E)
+        ops.vq_argmin(z[:8], E, tensor_cores=False)
     ops.row_gather(enc, E, channel_first=True)
     torch.cuda.synchronize()
     print("done")
