@@ -514,7 +514,7 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
         def step_e2e():
             x = x_host.to(dev, non_blocking=True)
             out_host.copy_(model.draft_and_revise(x, None, **DNR), non_blocking=True)
-        w.extra = dict(noise="in-kernel philox (inverse CDF)", logits=getattr(model, "sampler_logits_desc", "fp32 materialised"))
+        w.extra = dict(noise="in-kernel philox (inverse CDF)", logits="bf16 materialised between the head GEMM and the sampling kernel (model.sampler_logits_dtype)")
     w.device, w.e2e = step_device, step_e2e
     return w
 

@@ -356,6 +356,54 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
       : "memory");
 }
 
+// The four K = 16 steps of one 64-wide k-block as ONE instruction sequence.  The single issuing thread is what bounds small
+// tiles (measured: ~157 clk per tcgen05.mma when every descriptor is rebuilt from a byte address - shift, mask, or, two
+// 32-bit moves per operand - and every instruction sits in its own elect / branch wrapper, against 64 clk of tensor
+// time for M128 N128 K16), so the descriptors are split into a loop-invariant high word and a low word that advances
+// by a constant per step: (address >> 4) | (LBO >> 4) << 16, + a_step / b_step.
+__host__ __device__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+template <bool TWO_SM>
+__device__ __forceinline__ void umma_bf16_ss_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_step,
+                                                uint32_t b_step, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate_first) {
+#define MEBT_MMA4(CG)                                                                     \
+  asm volatile(                                                                           \
+      "{\n"                                                                               \
+      ".reg .pred p, t;\n"                                                                \
+      ".reg .b64 da, db;\n"                                                               \
+      ".reg .b32 al, bl;\n"                                                               \
+      "setp.ne.b32 p, %8, 0;\n"                                                           \
+      "setp.eq.b32 t, 0, 0;\n"                                                            \
+      "mov.b64 da, {%1, %5};\n"                                                           \
+      "mov.b64 db, {%2, %6};\n"                                                           \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %7, p;\n"                    \
+      "add.u32 al, %1, %3;\n"                                                             \
+      "add.u32 bl, %2, %4;\n"                                                             \
+      "mov.b64 da, {al, %5};\n"                                                           \
+      "mov.b64 db, {bl, %6};\n"                                                           \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %7, t;\n"                    \
+      "add.u32 al, al, %3;\n"                                                             \
+      "add.u32 bl, bl, %4;\n"                                                             \
+      "mov.b64 da, {al, %5};\n"                                                           \
+      "mov.b64 db, {bl, %6};\n"                                                           \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %7, t;\n"                    \
+      "add.u32 al, al, %3;\n"                                                             \
+      "add.u32 bl, bl, %4;\n"                                                             \
+      "mov.b64 da, {al, %5};\n"                                                           \
+      "mov.b64 db, {bl, %6};\n"                                                           \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %7, t;\n"                    \
+      "}\n" ::"r"(tmem_d),                                                                \
+      "r"(a_lo), "r"(b_lo), "r"(a_step), "r"(b_step), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate_first) \
+      : "memory")
+  if constexpr (TWO_SM) MEBT_MMA4("2"); else MEBT_MMA4("1");
+#undef MEBT_MMA4
+}
+
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M x K, K-major) is read from tensor memory - row m in lane m,
 // two bf16 per 32-bit column, element k in column k / 2 (low half = even k).  A K = 16 step consumes 8 columns.
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,

@@ -269,6 +269,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       int it = 0;
       TR_DECL;
+      static_assert(BK / UMMA_K == 4, "umma_bf16_ss_x4 issues the four K = 16 steps of a 64-wide k-block");
+      constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), A_MN ? BK * 128 : 16);
+      // B tile: A_TILE_BYTES behind A in the stage; its LBO field may differ from A's
+      const uint32_t b_off = uint32_t(A_TILE_BYTES >> 4) + ((uint32_t((B_MN ? BK * 128 : 16) >> 4) - uint32_t((A_MN ? BK * 128 : 16) >> 4)) << 16);
       for (int work = work0; work < num_work; work += work_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -286,19 +291,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           TR_END(0);
           if (it == 0 && kb == kb0) TS(3);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sB = sA + A_TILE_BYTES;
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major : advance 16 elements (32 B) inside the 128 B swizzle row; SBO = 8 rows * 128 B
-            // MN-major: advance 16 k-rows (2048 B); LBO = next 64-wide MN atom (BK rows * 128 B), SBO = 8 k-rows
-            const uint64_t da = A_MN ? make_smem_desc_sw128(sA + k * (UMMA_K * 128), BK * 128, 1024)
-                                     : make_smem_desc_sw128(sA + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(sB + k * (UMMA_K * 128), BK * 128, 1024)
-                                     : make_smem_desc_sw128(sB + k * (UMMA_K * 2), 16, 1024);
-            if constexpr (PAIR) umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          // descriptor low words of the stage's first K = 16 step (see umma_bf16_ss_x4); per step:
+          // K-major : advance 16 elements (32 B) inside the 128 B swizzle row; LBO field 1, SBO = 8 rows * 128 B
+          // MN-major: advance 16 k-rows (2048 B); LBO = next 64-wide MN atom (BK rows * 128 B), SBO = 8 k-rows
+          const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(L::STAGE_BYTES >> 4);
+          umma_bf16_ss_x4<PAIR>(tmem_d, a_lo, a_lo + b_off, A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4,
+                                B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4, desc_hi, desc_hi, idesc,
+                                kb > kb0 ? 1u : 0u);
           if constexpr (PAIR) {
             umma_commit_2sm_mc(&empty_bar[stage], 3);                      // frees the stage in both CTAs
             if (kb == kb1 - 1) umma_commit_2sm_mc(&tmem_full_bar[acc], 3);  // accumulator ready in both CTAs

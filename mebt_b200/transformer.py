@@ -184,6 +184,10 @@ class Net2NetTransformer(_Base):
         self._rng_offset = 0
         # dtype of the logits the head writes for the internal sampling / loss paths
         self.logits_dtype = torch.float32
+        # ... and for the samplers' own forward -> sample steps (draft / revise / sample / entp_sample), whose logits never
+        # leave the library: None = bf16 under precision "bf16" (half the head GEMM's store and the sampling kernel's read;
+        # the rounding, 2^-9 relative, is below the bf16 forward's own 1e-2), fp32 under precision "fp32"
+        self.sampler_logits_dtype = None
         # "bf16": tcgen05 engine, logits within 1e-2 of the fp32 reference; "fp32": split-GEMM + fp32 attention path,
         # within 1e-4 (north_star tolerances).  Also settable from the config (`precision: fp32`).
         self.precision = str(getattr(transformer_config, "precision", "bf16"))
@@ -314,7 +318,8 @@ class Net2NetTransformer(_Base):
     def _predict_and_write(self, partial, ctx_idx, tgt_idx, temperature, top_k, top_p, want_probs=False):
         """One sampler step: forward, sample every target, write the ids back.  -> (ids, scores, probs)"""
         B = partial.shape[0]
-        logits = self._logits_rows(partial, ctx_idx, tgt_idx)
+        dt = self.sampler_logits_dtype or (torch.bfloat16 if self.precision == "bf16" else torch.float32)
+        logits = self._logits_rows(partial, ctx_idx, tgt_idx, dt)
         ids, scores, probs = self._sample_rows(logits, temperature, top_k, top_p, return_probs=want_probs)
         NT = tgt_idx.shape[1]
         ops.scatter_ids(partial, tgt_idx, ids.view(B, NT))
