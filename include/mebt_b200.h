@@ -214,6 +214,14 @@ int mebt_vq_argmin_tc(const float* z_channel_first, int batch, int C, int S, con
 int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0,
                               int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, void* O, int ldo,
                               float* lse, int B, int H, int NQ, int head_dim, void* stream);
+/* The same with caller-provided scratch (mebt_latent_attention_fwd_workspace_bytes): launches with few work items and
+ * long key lists (small-batch 128-frame sampling: B*H*ceil(NQ/256) <= 74, >= 1024 keys) split each item's keys over
+ * up to 8 CTAs and merge the partial rows in a second kernel; otherwise identical. */
+size_t mebt_latent_attention_fwd_workspace_bytes(int B, int H, int NQ);
+int mebt_latent_attention_fwd_ws(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0,
+                                 int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, void* O, int ldo,
+                                 float* lse, int B, int H, int NQ, int head_dim, void* workspace, size_t workspace_bytes,
+                                 void* stream);
 
 /* ---- backward of the memory-bound ops (training step, config #2) -------------------------------- */
 /* out[n] (+)= sum_r X[r,n], X bf16 [rows, ld]: the bias gradients autograd computes for every nn.Linear of

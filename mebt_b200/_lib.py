@@ -70,6 +70,9 @@ _SIGNATURES: dict[str, list] = {
                           c_void_p],
     "mebt_latent_attention_fwd": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                   c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "mebt_latent_attention_fwd_ws": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                     c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                                     c_void_p],
 }
 
 
@@ -168,6 +171,8 @@ _lib.mebt_stack_forward_hoisted_workspace_bytes.argtypes = [c_int] * 6
 _lib.mebt_stack_forward_hoisted_workspace_bytes.restype = c_size_t
 _lib.mebt_stack_forward_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
 _lib.mebt_stack_forward_workspace_bytes.restype = c_size_t
+_lib.mebt_latent_attention_fwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
+_lib.mebt_latent_attention_fwd_workspace_bytes.restype = c_size_t
 _lib.mebt_vq_argmin_workspace_bytes.argtypes = [c_longlong]
 _lib.mebt_vq_argmin_workspace_bytes.restype = c_size_t
 _lib.mebt_vq_argmin_tc_workspace_bytes.argtypes = [c_longlong, c_int]

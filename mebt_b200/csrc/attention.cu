@@ -39,6 +39,7 @@ constexpr int AT_HS = 64;
 constexpr int AT_THREADS = 320;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;      // 16 KiB: a [128 x 64] bf16 tile (Q, K or V)
 constexpr int AT_KV_STAGES = 5;
+constexpr int AT_MAX_SPLITS = 8;                 // split-KV fan-out (workspace = AT_MAX_SPLITS partial outputs)
 constexpr int AT_SMEM_Q = 0;                                     // 2 buffers x 2 query tiles
 constexpr int AT_SMEM_K = AT_SMEM_Q + 4 * AT_TILE_BYTES;
 constexpr int AT_SMEM_V = AT_SMEM_K + AT_KV_STAGES * AT_TILE_BYTES;
@@ -70,6 +71,12 @@ struct AttnParams {
   float scale;             // 1 / sqrt(hs)
   long long* trace;
   DropKey drop;            // attention-probability dropout (training); thr == 0: off
+  // split-KV (few work items, long key lists: small-batch sampling): `splits` CTAs share an item, each walks `nts` of
+  // its K/V tiles and leaves an UNNORMALISED fp32 O row plus its (stabiliser m, row sum l); attention_combine_kernel
+  // merges them.  splits == 1: nts = all tiles, O is final.
+  int splits, nts;
+  float* part_o;           // [splits, B, H, NQ, 64]
+  float* part_ml;          // [splits, B, H, NQ, 2]
 };
 
 // 2^x for x <= ~8 on the FMA pipe: n = round(x), f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial, the
@@ -106,13 +113,16 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   const int nt = tiles1 + tiles2;
   const int q_tiles = (p.NQ + AT_BQ - 1) / AT_BQ;
   const int q_pairs = (q_tiles + 1) >> 1;
-  const int n_items = p.B * p.H * q_pairs;
+  const int n_items = p.B * p.H * q_pairs * p.splits;
   const int my_items = int(blockIdx.x) < n_items ? (n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
-  // item -> (b, h, query-tile pair); the pair runs fastest so that consecutive CTAs share a (b, h)'s K/V in L2
-  auto item_coords = [&](int n, int& b, int& h, int& qp) {
+  const int nts = p.nts;           // K/V tiles per item (= nt without split-KV)
+  // item -> (b, h, K/V split, query-tile pair); the pair runs fastest so that consecutive CTAs share a (b, h)'s K/V in L2
+  auto item_coords = [&](int n, int& b, int& h, int& qp, int& sp) {
     const int item = int(blockIdx.x) + n * int(gridDim.x);
     qp = item % q_pairs;
-    const int bh = item / q_pairs;
+    const int rest = item / q_pairs;
+    sp = rest % p.splits;
+    const int bh = rest / p.splits;
     h = bh % p.H;
     b = bh / p.H;
   };
@@ -143,8 +153,8 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     if (lane == 0 && nt > 0) {
       int gj = 0;                    // K/V tiles loaded by this CTA
       for (int n = 0; n < my_items; ++n) {
-        int b, h, qp;
-        item_coords(n, b, h, qp);
+        int b, h, qp, sp;
+        item_coords(n, b, h, qp, sp);
         const int qb = n & 1;
         mbar_wait_backoff(&q_empty[qb], ((n >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[qb], 2 * AT_TILE_BYTES);
@@ -154,7 +164,8 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
                     b * p.NQ + (2 * qp) * AT_BQ);
         tma_load_2d(smem + AT_SMEM_Q + (2 * qb + 1) * AT_TILE_BYTES, &tm_q, &q_full[qb], p.q_col0 + h * AT_HS,
                     b * p.NQ + (2 * qp + 1) * AT_BQ);
-        for (int j = 0; j < nt; ++j, ++gj) {
+        for (int jl = 0; jl < nts; ++jl, ++gj) {
+          const int j = sp * nts + jl;                 // tile of the item's whole key list
           const int s = gj % AT_KV_STAGES;
           mbar_wait_backoff(&kv_empty[s], ((gj / AT_KV_STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&kv_full[s], 2 * AT_TILE_BYTES);
@@ -184,11 +195,11 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 #define MTR_END(i)
 #endif
       // step g = 2 * (K/V tile counter gj) + warpgroup t
-      const int total = my_items * nt * 2;
+      const int total = my_items * nts * 2;
       // S_t of tile gj: legal once warpgroup t has consumed the S of tile gj-1
       auto issue_s = [&](int g) {
         const int gj = g >> 1, t = g & 1;
-        const int n = gj / nt, j = gj - n * nt;
+        const int n = gj / nts, j = gj - n * nts;
         if (t == 0) {
           MTR_BEGIN;
           if (j == 0) mbar_wait(&q_full[n & 1], (n >> 1) & 1);
@@ -203,12 +214,12 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
           umma_bf16_ss(tmem_base + t * 128, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
                        make_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[t]);
-        if (t == 1 && j == nt - 1) umma_commit(&q_empty[n & 1]);      // the item's last S: its Q buffer is free
+        if (t == 1 && j == nts - 1) umma_commit(&q_empty[n & 1]);     // the item's last S: its Q buffer is free
       };
       if (total > 0) { issue_s(0); issue_s(1); }
       for (int g = 0; g < total; ++g) {
         const int t = g & 1, gj = g >> 1;
-        const int j = gj % nt;
+        const int j = gj % nts;
         // warpgroup t is done with tile gj: S consumed, P in TMEM (and, at j == 0, the previous item's O read)
         MTR_BEGIN;
         mbar_wait(&p_full[t], gj & 1);
@@ -242,16 +253,17 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     const long long tr_start = clock64();
 #endif
     for (int n = 0; n < my_items; ++n) {
-      int b, h, qp;
-      item_coords(n, b, h, qp);
+      int b, h, qp, sp;
+      item_coords(n, b, h, qp, sp);
       const int qt = 2 * qp + t;
       const bool active = qt < q_tiles;            // an odd tile count leaves warpgroup 1 without a tile in the last pair
       float m = 0.f, l = 0.f;
       const uint32_t drop_rk = DROP ? drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qt * AT_BQ + row)) : 0u;
-      for (int j = 0; j < nt; ++j, ++k) {
-        const int rem = j < tiles1 ? p.NK1 - j * AT_BKV : p.NK2 - (j - tiles1) * AT_BKV;
+      for (int j = 0; j < nts; ++j, ++k) {
+        const int jg = sp * nts + j;                   // tile of the item's whole key list
+        const int rem = jg < tiles1 ? p.NK1 - jg * AT_BKV : p.NK2 - (jg - tiles1) * AT_BKV;
         const int valid = min(AT_BKV, rem);
-        const uint32_t pair0 = j < tiles1 ? uint32_t(j * (AT_BKV / 2)) : (1u << 19) | uint32_t((j - tiles1) * (AT_BKV / 2));
+        const uint32_t pair0 = jg < tiles1 ? uint32_t(jg * (AT_BKV / 2)) : (1u << 19) | uint32_t((jg - tiles1) * (AT_BKV / 2));
         const bool full = valid == AT_BKV;            // warp-uniform: only a source's last tile can be ragged
         ATR_BEGIN;
         mbar_wait(&s_full[t], k & 1);
@@ -360,7 +372,24 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         ATR_END(1);
         tc_fence_after();
       }
-      if (active) {
+      if (active && p.splits > 1) {
+        // split-KV: leave the unnormalised row and its (m, l) for the combine kernel
+        const size_t prow = ((size_t(sp) * p.B + b) * p.H + h) * p.NQ + qrow;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ro[32];
+          tmem_ld_32x32(tmem_o + c * 32, ro);
+          tmem_ld_wait_regs(ro);
+          if (qrow < p.NQ) {
+            float4* d4 = reinterpret_cast<float4*>(p.part_o + prow * AT_HS + c * 32);
+#pragma unroll
+            for (int gq = 0; gq < 8; ++gq)
+              d4[gq] = make_float4(__uint_as_float(ro[4 * gq]), __uint_as_float(ro[4 * gq + 1]), __uint_as_float(ro[4 * gq + 2]),
+                                   __uint_as_float(ro[4 * gq + 3]));
+          }
+        }
+        if (qrow < p.NQ) *reinterpret_cast<float2*>(p.part_ml + prow * 2) = make_float2(m, l);
+      } else if (active) {
         const float inv = l > 0.f ? 1.f / l : 0.f;
         uint4* dst = reinterpret_cast<uint4*>(p.O + (size_t(b) * p.NQ + qrow) * p.ldo + h * AT_HS);
 #pragma unroll
@@ -405,6 +434,38 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   }
 }
 
+// Merge of the split-KV partials: one warp per (b, h, q) row, lane = two of the 64 head dimensions.
+//   M = max_s m_s,  w_s = 2^((m_s - M) c),  O = sum_s w_s O_s / sum_s w_s l_s        (c = log2(e) / sqrt(hs))
+__global__ void __launch_bounds__(256) attention_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                                                                int splits, int B, int H, int NQ, float scale_log2,
+                                                                __nv_bfloat16* __restrict__ O, int ldo) {
+  griddep_wait();
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * H * NQ;
+  if (row >= rows) return;
+  float M = -INFINITY;
+  for (int sidx = 0; sidx < splits; ++sidx) {
+    const float2 ml = *reinterpret_cast<const float2*>(part_ml + (sidx * rows + row) * 2);
+    if (ml.y > 0.f) M = fmaxf(M, ml.x);
+  }
+  float o0 = 0.f, o1 = 0.f, L = 0.f;
+  for (int sidx = 0; sidx < splits; ++sidx) {
+    const float2 ml = *reinterpret_cast<const float2*>(part_ml + (sidx * rows + row) * 2);
+    if (!(ml.y > 0.f)) continue;
+    const float w = ex2_approx((ml.x - M) * scale_log2);
+    const float2 v = *reinterpret_cast<const float2*>(part_o + (sidx * rows + row) * AT_HS + lane * 2);
+    o0 = fmaf(w, v.x, o0);
+    o1 = fmaf(w, v.y, o1);
+    L = fmaf(w, ml.y, L);
+  }
+  const float inv = L > 0.f ? 1.f / L : 0.f;
+  const int q = int(row % NQ);
+  const long long bh = row / NQ;
+  const int h = int(bh % H), b = int(bh / H);
+  *reinterpret_cast<uint32_t*>(O + (size_t(b) * NQ + q) * ldo + h * AT_HS + lane * 2) = pack_bf16x2(o0 * inv, o1 * inv);
+}
+
 }  // namespace
 }  // namespace mebt
 
@@ -413,9 +474,14 @@ extern "C" void mebt_attn_set_trace(long long* buf) { mebt::g_attn_trace = buf; 
 #endif
 
 namespace mebt {
+size_t latent_attention_fwd_workspace_bytes(int B, int H, int NQ) {
+  return size_t(AT_MAX_SPLITS) * B * H * NQ * (AT_HS + 2) * sizeof(float);
+}
+
 int latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0, int NK1,
                          const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, void* O, int ldo, float* lse, int B,
-                         int H, int NQ, int head_dim, float drop_p, unsigned long long drop_seed, void* stream) {
+                         int H, int NQ, int head_dim, float drop_p, unsigned long long drop_seed, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   MEBT_REQUIRE(head_dim == AT_HS, MEBT_ERR_UNSUPPORTED, "attention: head_dim %d unsupported (every MeBT config uses 64)",
                head_dim);
   MEBT_REQUIRE(B > 0 && H > 0 && NQ > 0 && NK1 >= 0 && NK2 >= 0, MEBT_ERR_SHAPE, "attention: bad shape");
@@ -459,7 +525,21 @@ int latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, in
     MEBT_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_TOTAL));
     attr[drop] = true;
   }
-  const int n_items = B * H * (((NQ + AT_BQ - 1) / AT_BQ + 1) / 2);
+  const int base_items = B * H * (((NQ + AT_BQ - 1) / AT_BQ + 1) / 2);
+  const int nt = (NK1 + AT_BKV - 1) / AT_BKV + (NK2 + AT_BKV - 1) / AT_BKV;
+  // split-KV: with fewer items than half the SMs and a long key list (small-batch sampling: B <= 2 at 8192 keys), the
+  // largest divisor of the tile count that still fits one wave and leaves >= 4 tiles per CTA
+  int splits = 1;
+  if (!drop && lse == nullptr && workspace != nullptr && 2 * base_items <= sm_count() && nt >= 8)
+    for (int c = 2; c <= AT_MAX_SPLITS; ++c)
+      if (nt % c == 0 && base_items * c <= sm_count() && nt / c >= 4 &&
+          workspace_bytes >= size_t(c) * B * H * NQ * (AT_HS + 2) * sizeof(float))
+        splits = c;
+  p.splits = splits;
+  p.nts = nt / splits;
+  p.part_o = static_cast<float*>(workspace);
+  p.part_ml = p.part_o != nullptr ? p.part_o + size_t(splits) * B * H * NQ * AT_HS : nullptr;
+  const int n_items = base_items * splits;
   dim3 grid(n_items < sm_count() ? n_items : sm_count());
   {
     LaunchScope ls(FAM_ATTENTION, 4.0 * double(B) * H * double(NQ) * double(NK1 + NK2) * AT_HS,
@@ -467,6 +547,14 @@ int latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, in
     MEBT_CUDA_OK(launch_pdl(kernel, grid, dim3(AT_THREADS), AT_SMEM_TOTAL, static_cast<cudaStream_t>(stream), tq, t1, t2, p));
   }
   MEBT_LAUNCH_OK("latent_attention_fwd_kernel");
+  if (splits > 1) {
+    const long long rows = (long long)B * H * NQ;
+    LaunchScope ls(FAM_ATTENTION, 0.0, static_cast<cudaStream_t>(stream));
+    MEBT_CUDA_OK(launch_pdl(attention_combine_kernel, dim3(int((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                            static_cast<const float*>(p.part_o), static_cast<const float*>(p.part_ml), splits, B, H, NQ,
+                            p.scale_log2, p.O, ldo));
+    MEBT_LAUNCH_OK("attention_combine_kernel");
+  }
   return MEBT_OK;
 }
 
@@ -490,7 +578,19 @@ extern "C" int mebt_latent_attention_fwd(const void* Q, int ldq, int q_col0, con
                                          int NK2, void* O, int ldo, float* lse, int B, int H, int NQ, int head_dim,
                                          void* stream) {
   return mebt::latent_attention_fwd(Q, ldq, q_col0, KV1, ld1, k1_col0, v1_col0, NK1, KV2, ld2, k2_col0, v2_col0, NK2, O, ldo,
-                                    lse, B, H, NQ, head_dim, 0.f, 0ull, stream);
+                                    lse, B, H, NQ, head_dim, 0.f, 0ull, nullptr, 0, stream);
+}
+
+extern "C" size_t mebt_latent_attention_fwd_workspace_bytes(int B, int H, int NQ) {
+  return mebt::latent_attention_fwd_workspace_bytes(B, H, NQ);
+}
+
+extern "C" int mebt_latent_attention_fwd_ws(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
+                                            int v1_col0, int NK1, const void* KV2, int ld2, int k2_col0, int v2_col0,
+                                            int NK2, void* O, int ldo, float* lse, int B, int H, int NQ, int head_dim,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+  return mebt::latent_attention_fwd(Q, ldq, q_col0, KV1, ld1, k1_col0, v1_col0, NK1, KV2, ld2, k2_col0, v2_col0, NK2, O, ldo,
+                                    lse, B, H, NQ, head_dim, 0.f, 0ull, workspace, workspace_bytes, stream);
 }
 
 extern "C" int mebt_latent_attention_fwd_dropout(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0,
@@ -498,7 +598,7 @@ extern "C" int mebt_latent_attention_fwd_dropout(const void* Q, int ldq, int q_c
                                                  int v2_col0, int NK2, void* O, int ldo, float* lse, int B, int H, int NQ,
                                                  int head_dim, float p, unsigned long long seed, void* stream) {
   return mebt::latent_attention_fwd(Q, ldq, q_col0, KV1, ld1, k1_col0, v1_col0, NK1, KV2, ld2, k2_col0, v2_col0, NK2, O, ldo,
-                                    lse, B, H, NQ, head_dim, p, seed, stream);
+                                    lse, B, H, NQ, head_dim, p, seed, nullptr, 0, stream);
 }
 
 extern "C" int mebt_attention_dropout_mask(float* out, int B, int H, int NQ, int NK1, int NK2, float p,

@@ -10,6 +10,11 @@ namespace mebt {
 
 int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
               int K, const float* bias, const void* residual, int ldres, int flags, cudaStream_t stream);
+size_t latent_attention_fwd_workspace_bytes(int B, int H, int NQ);
+int latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0, int NK1,
+                         const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, void* O, int ldo, float* lse, int B,
+                         int H, int NQ, int head_dim, float drop_p, unsigned long long drop_seed, void* workspace,
+                         size_t workspace_bytes, void* stream);
 int layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const float* beta, void* y, int ldy,
               int out_dtype, int rows, int D, float eps, float* mean, float* rstd, cudaStream_t st);
 
@@ -26,6 +31,21 @@ struct Workspace {
   }
 };
 
+// Scratch of the split-KV attention (csrc/attention.cu): only launches with at most half an SM count of work items
+// split, i.e. small batches; sized for the largest query count such a launch of this stack can have.
+size_t attention_split_bytes(int B, int L, int NC, int NT, int D) {
+  const int H = D / 64;
+  size_t need = 0;
+  for (int nq : {L, NT, NC + NT}) {
+    const int pairs = ((nq + 127) / 128 + 1) / 2;
+    if (nq > 0 && 2 * B * H * pairs <= sm_count()) {
+      const size_t b = latent_attention_fwd_workspace_bytes(B, H, nq);
+      need = b > need ? b : need;
+    }
+  }
+  return (need + 255) & ~size_t(255);
+}
+
 size_t stack_workspace_bytes(int B, int L, int NC, int NT, int D, int n_enc_hoisted = 0) {
   const size_t q_rows = size_t(B) * size_t(L > NC + NT ? L : NC + NT);
   const size_t k_rows = q_rows;
@@ -41,6 +61,7 @@ size_t stack_workspace_bytes(int B, int L, int NC, int NT, int D, int n_enc_hois
   add(q_rows, 4 * D);    // u
   add(q_rows, D);        // maskgit concat stream
   add(size_t(B) * NC, size_t(n_enc_hoisted) * 2 * D);   // hoisted K|V of every latent_enc block
+  total += attention_split_bytes(B, L, NC, NT, D);     // split-KV partials (small batches only)
   return total + 4096;
 }
 
@@ -90,6 +111,8 @@ int mebt_stack_forward_hoisted(const mebt_layer_t* layers, int n_layers, const f
   void* u = ws.take(qr * 4 * D * 2);
   void* cat = ws.take(qr * D * 2);
   void* kv_all = n_hoist > 0 ? ws.take(size_t(B) * NC * size_t(n_hoist) * 2 * D * 2) : nullptr;
+  const size_t attn_ws_bytes = attention_split_bytes(B, L, NC, NT, D);
+  void* attn_ws = attn_ws_bytes > 0 ? ws.take(attn_ws_bytes) : nullptr;
   MEBT_REQUIRE(cat != nullptr && (n_hoist == 0 || kv_all != nullptr), MEBT_ERR_WORKSPACE,
                "stack_forward: workspace exhausted");
 
@@ -188,8 +211,8 @@ int mebt_stack_forward_hoisted(const mebt_layer_t* layers, int n_layers, const f
       default:
         MEBT_REQUIRE(false, MEBT_ERR_UNSUPPORTED, "stack_forward: unknown block mode %d", w.mode);
     }
-    TRY(mebt_latent_attention_fwd(Qb, ldq, 0, KV1, ld1, k1c, v1c, nk1, KV2, ld2, 0, D, nk2, att, D, nullptr, B, H, nq,
-                                  64, stream));
+    TRY(latent_attention_fwd(Qb, ldq, 0, KV1, ld1, k1c, v1c, nk1, KV2, ld2, 0, D, nk2, att, D, nullptr, B, H, nq, 64, 0.f, 0ull,
+                             attn_ws, attn_ws_bytes, stream));
     const int rows = B * nq;
     TRY(GEMM(att, w.w_proj, D, x, D, rows, D, D, w.b_proj, qn, 0));                    // x = ln1(q) + proj(att)
     TRY(LN(x, w.ln2_w, w.ln2_b, h, rows));

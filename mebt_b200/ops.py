@@ -124,6 +124,16 @@ def attention(q, q_col0, kv1, k1_col0, v1_col0, nk1, kv2, k2_col0, v2_col0, nk2,
     D = H * 64
     if out is None:
         out = torch.empty(B * NQ, D, device=q.device, dtype=torch.bfloat16)
+    if drop_p == 0.0 and lse is None and 2 * B * H * (((NQ + 127) // 128 + 1) // 2) <= 148:          # B200: 148 SMs (the library targets sm_100a only)
+        # few work items: hand the library scratch for the split-KV form (it splits when the key list is long enough;
+        # the same rule as the one-call engine, so both paths produce the same bits)
+        nbytes = _lib.lib.mebt_latent_attention_fwd_workspace_bytes(B, H, NQ)
+        ws = _ws(q.device, nbytes, "attn_fwd")
+        call("mebt_latent_attention_fwd_ws", q.data_ptr(), q.stride(0), q_col0,
+             _ptr(kv1) if nk1 > 0 else None, kv1.stride(0) if nk1 > 0 else 0, k1_col0, v1_col0, nk1,
+             _ptr(kv2) if nk2 > 0 else None, kv2.stride(0) if nk2 > 0 else 0, k2_col0, v2_col0, nk2,
+             out.data_ptr(), out.stride(0), None, B, H, NQ, 64, ws.data_ptr(), ws.numel(), _stream())
+        return out
     call("mebt_latent_attention_fwd_dropout", q.data_ptr(), q.stride(0), q_col0,
          _ptr(kv1) if nk1 > 0 else None, kv1.stride(0) if nk1 > 0 else 0, k1_col0, v1_col0, nk1,
          _ptr(kv2) if nk2 > 0 else None, kv2.stride(0) if nk2 > 0 else 0, k2_col0, v2_col0, nk2,
