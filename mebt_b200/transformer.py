@@ -346,7 +346,9 @@ class Net2NetTransformer(_Base):
         self.mask_sampler.rng_mode, self.mask_sampler.rng_seed = self.rng_mode, self.rng_seed + 1
         for t_next in np.linspace(0, 1, n_steps + 1)[1:]:
             t = torch.full((B,), fill_value=t_next, device=x.device)              # float32
-            n_masked_toks = torch.ceil(self.mask_sampler.schedule_fn(t) * edit_N)
+            # computed on the device like the reference, then read back ONCE per step (the skip test and the re-mask size
+            # below both use the host copy: one sync per step instead of two)
+            n_masked_toks = torch.ceil(self.mask_sampler.schedule_fn(t) * edit_N).cpu()
             if int((n_masked_toks > target_indices.shape[-1]).sum()) == B:
                 continue                                                           # context already larger than asked
             target_indices = target_indices.view(B, -1)
@@ -385,7 +387,7 @@ class Net2NetTransformer(_Base):
             partial_probs = -torch.ones(B, N, 16384, device=x.device)
         for t_next in np.linspace(0, 1, n_steps + 1)[1:]:
             t = torch.full((B,), fill_value=t_next, device=x.device)
-            n_masked_toks = torch.ceil(self.mask_sampler.schedule_fn(t) * N)
+            n_masked_toks = torch.ceil(self.mask_sampler.schedule_fn(t) * N).cpu()
             if int((n_masked_toks > target_indices.shape[-1]).sum()) == B:
                 continue
             target_indices = target_indices.view(B, -1)
