@@ -931,8 +931,12 @@ int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b
   p.partials = nullptr;
   p.counters = nullptr;
   // at least two waves of tiles: pair up vertically adjacent tiles and share the B tile by TMA multicast
+  // ... and 256-wide tiles already from 96 tiles up (measured, tools/gemm_probe.py: 1536 x 3072/4096 x 1024, 3072 x 2048 x 1024,
+  // 3072 x 1024 x 4096 gain 3-10 % as pairs - each CTA stages half of B -; below that the 48-tile problems lose)
+  const int64_t n_tiles = int64_t(p.num_m_blocks) * p.num_n_blocks;
   p.pair = (bn >= 128 && !(flags & MEBT_GEMM_NO_PAIR) && p.num_m_blocks >= 2 &&
-            int64_t(p.num_m_blocks) * p.num_n_blocks >= 2 * int64_t(sm_count())) || (flags & MEBT_GEMM_FORCE_PAIR && bn >= 128);
+            (n_tiles >= 2 * int64_t(sm_count()) || (bn == 256 && p.num_m_blocks % 2 == 0 && n_tiles >= 96))) ||
+           (flags & MEBT_GEMM_FORCE_PAIR && bn >= 128);
   if (!p.pair && !(flags & MEBT_GEMM_NO_SPLITK)) {
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int want = sm_count() / tiles;                       // CTAs available per tile
