@@ -274,24 +274,34 @@ __global__ void __launch_bounds__(CE_T, 2) masked_ce_bf16_stream_kernel(const __
     const int tgt = int(targets[row]);
     mbar_wait(&bar[buf], uint32_t(it / CE_STAGES) & 1u);
     const uint8_t* sr = ce_smem + buf * CE_ROW_BYTES;
+    // Packed arithmetic throughout (the kernel is issue-bound next to the HBM stream): the maximum and the rank count in
+    // bf16x2 (exact: a maximum of bf16 values; counts <= 64 per lane half), the exponent argument and the sums in f32x2,
+    // the label-smoothing sum only when smoothing is on, the one-hot correction as a single store after the row.
     uint4 v[8];
-    float m = -INFINITY, total = 0.f;
+    __nv_bfloat162 m2 = __float2bfloat162_rn(-INFINITY);
+    float total = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = (threadIdx.x + CE_T * i) * 8;
       if (c < V) {
         v[i] = *reinterpret_cast<const uint4*>(sr + size_t(c) * 2);
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+        const __nv_bfloat162* w = reinterpret_cast<const __nv_bfloat162*>(&v[i]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = unpack_bf16x2(w[k]);
-          m = fmaxf(m, fmaxf(f.x, f.y));
-          total += f.x + f.y;
+        for (int k = 0; k < 4; ++k) m2 = __hmax2(m2, w[k]);
+        if (smoothing != 0.f) {
+          const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = unpack_bf16x2(u[k]);
+            total += f.x + f.y;
+          }
         }
       }
     }
-    const float xt = (tgt >= 0 && tgt < V) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(sr)[tgt]) : 0.f;
-    m = warp_max(m);
+    const bool tgt_ok = tgt >= 0 && tgt < V;
+    const __nv_bfloat16 xt_b = tgt_ok ? reinterpret_cast<const __nv_bfloat16*>(sr)[tgt] : __float2bfloat16(0.f);
+    const float xt = __bfloat162float(xt_b);
+    float m = warp_max(fmaxf(__low2float(m2), __high2float(m2)));
     total = warp_sum(total);
     if (lane == 0) { red_a[warp] = m; red_b[warp] = total; }
     __syncthreads();
@@ -300,29 +310,33 @@ __global__ void __launch_bounds__(CE_T, 2) masked_ce_bf16_stream_kernel(const __
 #pragma unroll
     for (int i = 1; i < CE_T / 32; ++i) { m = fmaxf(m, red_a[i]); total += red_b[i]; }
     __syncthreads();
-    const float ml2 = m * 1.4426950408889634f;
-    float se = 0.f;
-    int rank = 0;
+    const float2 nml2 = make_float2(-m * 1.4426950408889634f, -m * 1.4426950408889634f);
+    const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+    const __nv_bfloat162 xt2 = __bfloat162bfloat162(xt_b);
+    float2 se2 = make_float2(0.f, 0.f);
+    __nv_bfloat162 cnt2 = __float2bfloat162_rn(0.f);
     uint32_t e16[32];                                         // exp(x - max) as packed fp16 pairs
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = (threadIdx.x + CE_T * i) * 8;
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[i]);
+      const __nv_bfloat162* w = reinterpret_cast<const __nv_bfloat162*>(&v[i]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float e0 = 0.f, e1 = 0.f;
+        float2 e = make_float2(0.f, 0.f);
         if (c < V) {
-          const float2 f = unpack_bf16x2(w[k]);
-          e0 = ex2_approx(fmaf(f.x, 1.4426950408889634f, -ml2));
-          e1 = ex2_approx(fmaf(f.y, 1.4426950408889634f, -ml2));
-          se += e0 + e1;
-          rank += (f.x > xt) + (f.y > xt);
+          const float2 x = __ffma2_rn(unpack_bf16x2(u[k]), l2e, nml2);
+          e.x = ex2_approx(x.x);
+          e.y = ex2_approx(x.y);
+          se2 = __fadd2_rn(se2, e);
+          cnt2 = __hadd2(cnt2, __hgt2(w[k], xt2));            // 1.0 where the logit beats the target's
         }
-        const __half2 h = __floats2half2_rn(e0, e1);
+        const __half2 h = __floats2half2_rn(e.x, e.y);
         e16[4 * i + k] = *reinterpret_cast<const uint32_t*>(&h);
       }
     }
-    se = warp_sum(se);
+    float se = warp_sum(se2.x + se2.y);
+    int rank = int(__low2float(cnt2) + __high2float(cnt2));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
     if (lane == 0) { red_a[warp] = se; red_i[warp] = rank; }
@@ -335,14 +349,15 @@ __global__ void __launch_bounds__(CE_T, 2) masked_ce_bf16_stream_kernel(const __
       const float lse = m + logf(se);
       const float nll = lse - xt;
       const float smooth = lse - total / float(V);
-      row_loss[row] = (1.f - smoothing) * nll + smoothing * smooth;
+      row_loss[row] = (1.f - smoothing) * nll + (smoothing != 0.f ? smoothing * smooth : 0.f);
       if (row_rank != nullptr) row_rank[row] = rank;
     }
     if (dlogits != nullptr) {
       // d(sum CE)/dlogit_v = softmax_v - (1-eps) [v == t] - eps / V, times the upstream scale (may overwrite the logits:
       // the row was read completely, into shared memory, before its first store)
       __nv_bfloat16* dr = dlogits + row * ldd;
-      const float inv = grad_scale / se, u = grad_scale * smoothing / float(V), hot = grad_scale * (1.f - smoothing);
+      const float inv = grad_scale / se, u_s = grad_scale * smoothing / float(V), hot = grad_scale * (1.f - smoothing);
+      const float2 inv2 = make_float2(inv, inv), nu2 = make_float2(-u_s, -u_s);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = (threadIdx.x + CE_T * i) * 8;
@@ -351,15 +366,17 @@ __global__ void __launch_bounds__(CE_T, 2) masked_ce_bf16_stream_kernel(const __
           uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&e16[4 * i + k]));
-            float g0 = fmaf(e.x, inv, -u);
-            float g1 = fmaf(e.y, inv, -u);
-            if (tgt == c + 2 * k) g0 -= hot;
-            if (tgt == c + 2 * k + 1) g1 -= hot;
-            ow[k] = pack_bf16x2(g0, g1);
+            const float2 g2 = __ffma2_rn(__half22float2(*reinterpret_cast<const __half2*>(&e16[4 * i + k])), inv2, nu2);
+            ow[k] = pack_bf16x2(g2.x, g2.y);
           }
           *reinterpret_cast<uint4*>(dr + c) = o;
         }
+      }
+      // the target's entry also carries -(1 - eps): rewritten by the thread that owns its column, after its own store of
+      // the surrounding 16 bytes (same thread, program order)
+      if (tgt_ok && ((tgt >> 3) & (CE_T - 1)) == int(threadIdx.x)) {
+        const float e_t = ex2_approx(fmaf(xt, 1.4426950408889634f, -m * 1.4426950408889634f));
+        dr[tgt] = __float2bfloat16(fmaf(e_t, inv, -u_s) - hot);
       }
     }
     __syncthreads();                                          // red_* are reused by the next row
