@@ -514,7 +514,8 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
         def step_e2e():
             x = x_host.to(dev, non_blocking=True)
             out_host.copy_(model.draft_and_revise(x, None, **DNR), non_blocking=True)
-        w.extra = dict(noise="in-kernel philox (inverse CDF)", logits="bf16 materialised between the head GEMM and the sampling kernel (model.sampler_logits_dtype)")
+        w.extra = dict(noise="in-kernel (fused Gumbel-max in the head GEMM for draft / revise; Philox inverse CDF where scores are needed)", logits=("never materialised: draft / revise draw each token in the head GEMM's epilogue (Gumbel-max, counter-hash noise)"
+                               if workload != "maskgit16f" else "bf16 between the head GEMM and the sampling kernel (scores are needed for re-masking)"))
     w.device, w.e2e = step_device, step_e2e
     return w
 

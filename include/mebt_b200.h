@@ -349,6 +349,22 @@ int mebt_stack_forward_hoisted(const mebt_layer_t* layers, int n_layers, const f
                                const void* w_head, const mebt_enc_hoist_t* hoist, int B, int L, int NC, int NT, int D,
                                int H, int V, void* lat, void* ctx, void* tgt, void* logits, int logits_dtype,
                                void* workspace, size_t workspace_bytes, void* stream);
+/* The same forward with the sampling step fused into the head GEMM (K6): when sample_ids != NULL, ids[b*NT + i] is one
+ * categorical draw from softmax(logits / temperature) by the Gumbel-max rule - argmax_v(logit_v / T + G_v), G_v from a counter
+ * hash of (seed, offset, row, v) - taken in the GEMM epilogue from the fp32 accumulators, so the [B*NT, V] logits are never
+ * written (replaces mebt/modules/gpt.py:248 + sample_from_logits, mebt/transformer.py:843-889, on the draft / revise passes;
+ * no top-k / top-p, no scores).  logits may be NULL. */
+int mebt_stack_forward_sample(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                              const void* w_head, const mebt_enc_hoist_t* hoist, int B, int L, int NC, int NT, int D,
+                              int H, int V, void* lat, void* ctx, void* tgt, void* logits, int logits_dtype,
+                              int64_t* sample_ids, float temperature, unsigned long long seed, unsigned long long offset,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* The head + sampling step alone: ids[r] ~ softmax(x[r] . w_head^T / temperature), x bf16 [rows, D] (= ln_f(targets)),
+ * w_head bf16 [V, D]; workspace mebt_head_sample_workspace_bytes(rows). */
+size_t mebt_head_sample_workspace_bytes(long long rows);
+int mebt_head_sample(const void* x, int ldx, const void* w_head, int ldw, int rows, int V, int D, float temperature,
+                     unsigned long long seed, unsigned long long offset, int64_t* ids, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* ---- training step: forward that saves activations + full backward -------------------------------------- */
 /* fp32 gradient destinations of one Block, same geometry as mebt_layer_t (w_qkv = [3D,D] query|key|value rows). */

@@ -147,6 +147,12 @@ _SIGNATURES["mebt_stack_forward_hoisted"] = [ctypes.POINTER(LayerStruct), c_int,
                                              ctypes.POINTER(EncHoistStruct), c_int, c_int, c_int, c_int, c_int, c_int,
                                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                                              c_void_p]
+_SIGNATURES["mebt_stack_forward_sample"] = [ctypes.POINTER(LayerStruct), c_int, c_void_p, c_void_p, c_void_p,
+                                            ctypes.POINTER(EncHoistStruct), c_int, c_int, c_int, c_int, c_int, c_int,
+                                            c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float,
+                                            c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]
+_SIGNATURES["mebt_head_sample"] = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint64, c_void_p,
+                                   c_void_p, c_size_t, c_void_p]
 _SIGNATURES["mebt_stack_forward"] = [ctypes.POINTER(LayerStruct), c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p, c_size_t, c_void_p]
@@ -173,6 +179,8 @@ _lib.mebt_stack_forward_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, 
 _lib.mebt_stack_forward_workspace_bytes.restype = c_size_t
 _lib.mebt_latent_attention_fwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
 _lib.mebt_latent_attention_fwd_workspace_bytes.restype = c_size_t
+_lib.mebt_head_sample_workspace_bytes.argtypes = [c_longlong]
+_lib.mebt_head_sample_workspace_bytes.restype = c_size_t
 _lib.mebt_vq_argmin_workspace_bytes.argtypes = [c_longlong]
 _lib.mebt_vq_argmin_workspace_bytes.restype = c_size_t
 _lib.mebt_vq_argmin_tc_workspace_bytes.argtypes = [c_longlong, c_int]

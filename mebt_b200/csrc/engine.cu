@@ -10,6 +10,8 @@ namespace mebt {
 
 int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
               int K, const float* bias, const void* residual, int ldres, int flags, cudaStream_t stream);
+int gemm_bf16_sample(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float temperature,
+                     unsigned long long seed, unsigned long long offset, unsigned long long* packed, cudaStream_t stream);
 size_t latent_attention_fwd_workspace_bytes(int B, int H, int NQ);
 int latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, int ld1, int k1_col0, int v1_col0, int NK1,
                          const void* KV2, int ld2, int k2_col0, int v2_col0, int NK2, void* O, int ldo, float* lse, int B,
@@ -19,6 +21,16 @@ int layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const fl
               int out_dtype, int rows, int D, float eps, float* mean, float* rstd, cudaStream_t st);
 
 namespace {
+
+// fused head + sampling: the GEMM's packed (key << 32 | id) minima before / after
+__global__ void packed_init_kernel(unsigned long long* __restrict__ packed, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) packed[i] = ~0ull;
+}
+__global__ void packed_ids_kernel(const unsigned long long* __restrict__ packed, int64_t* __restrict__ ids, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = int64_t(packed[i] & 0xFFFFFFFFull);
+}
 
 struct Workspace {
   char* base;
@@ -62,6 +74,7 @@ size_t stack_workspace_bytes(int B, int L, int NC, int NT, int D, int n_enc_hois
   add(q_rows, D);        // maskgit concat stream
   add(size_t(B) * NC, size_t(n_enc_hoisted) * 2 * D);   // hoisted K|V of every latent_enc block
   total += attention_split_bytes(B, L, NC, NT, D);     // split-KV partials (small batches only)
+  total += (size_t(B) * NT * 8 + 255) & ~size_t(255);  // packed draws of the fused head + sampling form
   return total + 4096;
 }
 
@@ -90,6 +103,15 @@ int mebt_stack_forward_hoisted(const mebt_layer_t* layers, int n_layers, const f
                                const void* w_head, const mebt_enc_hoist_t* hoist, int B, int L, int NC, int NT, int D,
                                int H, int V, void* lat, void* ctx, void* tgt, void* logits, int logits_dtype,
                                void* workspace, size_t workspace_bytes, void* stream) {
+  return mebt_stack_forward_sample(layers, n_layers, lnf_w, lnf_b, w_head, hoist, B, L, NC, NT, D, H, V, lat, ctx, tgt, logits,
+                                   logits_dtype, nullptr, 0.f, 0ull, 0ull, workspace, workspace_bytes, stream);
+}
+
+int mebt_stack_forward_sample(const mebt_layer_t* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                              const void* w_head, const mebt_enc_hoist_t* hoist, int B, int L, int NC, int NT, int D,
+                              int H, int V, void* lat, void* ctx, void* tgt, void* logits, int logits_dtype,
+                              int64_t* sample_ids, float temperature, unsigned long long seed, unsigned long long offset,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   using namespace mebt;
   const int n_hoist = (hoist != nullptr && NC > 0) ? hoist->n_enc : 0;
   MEBT_REQUIRE(B > 0 && L > 0 && NC >= 0 && NT > 0 && D > 0 && H > 0 && D == H * 64, MEBT_ERR_SHAPE,
@@ -113,6 +135,7 @@ int mebt_stack_forward_hoisted(const mebt_layer_t* layers, int n_layers, const f
   void* kv_all = n_hoist > 0 ? ws.take(size_t(B) * NC * size_t(n_hoist) * 2 * D * 2) : nullptr;
   const size_t attn_ws_bytes = attention_split_bytes(B, L, NC, NT, D);
   void* attn_ws = attn_ws_bytes > 0 ? ws.take(attn_ws_bytes) : nullptr;
+  unsigned long long* packed = static_cast<unsigned long long*>(ws.take(size_t(B) * NT * 8));
   MEBT_REQUIRE(cat != nullptr && (n_hoist == 0 || kv_all != nullptr), MEBT_ERR_WORKSPACE,
                "stack_forward: workspace exhausted");
 
@@ -230,12 +253,41 @@ int mebt_stack_forward_hoisted(const mebt_layer_t* layers, int n_layers, const f
       }
     }
   }
-  if (logits != nullptr) {
-    TRY(LN(tgt, lnf_w, lnf_b, h, B * NT));
+  if (logits != nullptr || sample_ids != nullptr) TRY(LN(tgt, lnf_w, lnf_b, h, B * NT));
+  if (logits != nullptr)
     TRY(gemm_bf16(h, D, 0, w_head, D, 0, logits, V, B * NT, V, D, nullptr, nullptr, 0,
                   logits_dtype == MEBT_DTYPE_FP32 ? MEBT_GEMM_OUT_FP32 : 0, st));
+  if (sample_ids != nullptr) {
+    // head GEMM whose epilogue draws one token per row (Gumbel-max over the 16384 logits): no logits in HBM
+    const long long rows = (long long)B * NT;
+    packed_init_kernel<<<int((rows + 255) / 256), 256, 0, st>>>(packed, rows);
+    MEBT_LAUNCH_OK("packed_init_kernel");
+    TRY(gemm_bf16_sample(h, D, w_head, D, int(rows), V, D, temperature, seed, offset, packed, st));
+    packed_ids_kernel<<<int((rows + 255) / 256), 256, 0, st>>>(packed, sample_ids, rows);
+    MEBT_LAUNCH_OK("packed_ids_kernel");
   }
 #undef TRY
+  return MEBT_OK;
+}
+
+
+size_t mebt_head_sample_workspace_bytes(long long rows) { return size_t(rows) * 8; }
+
+int mebt_head_sample(const void* x, int ldx, const void* w_head, int ldw, int rows, int V, int D, float temperature,
+                     unsigned long long seed, unsigned long long offset, int64_t* ids, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  using namespace mebt;
+  MEBT_REQUIRE(rows >= 0 && V > 0 && D > 0, MEBT_ERR_SHAPE, "head_sample: bad shape");
+  if (rows == 0) return MEBT_OK;
+  MEBT_REQUIRE(workspace != nullptr && workspace_bytes >= size_t(rows) * 8, MEBT_ERR_WORKSPACE, "head_sample: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* packed = static_cast<unsigned long long*>(workspace);
+  packed_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(packed, rows);
+  MEBT_LAUNCH_OK("packed_init_kernel");
+  int rc = gemm_bf16_sample(x, ldx, w_head, ldw, rows, V, D, temperature, seed, offset, packed, st);
+  if (rc) return rc;
+  packed_ids_kernel<<<(rows + 255) / 256, 256, 0, st>>>(packed, ids, rows);
+  MEBT_LAUNCH_OK("packed_ids_kernel");
   return MEBT_OK;
 }
 

@@ -21,6 +21,9 @@ namespace mebt {
 namespace {
 
 constexpr int MEBT_GEMM_INTERNAL_ARGMIN = 1 << 30;   // not part of the C ABI
+constexpr int MEBT_GEMM_INTERNAL_SAMPLE = 1 << 29;
+struct SampleRequest { bool active; float scale; uint32_t k0, k1; };
+thread_local SampleRequest g_sample_req = {false, 0.f, 0u, 0u};
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
@@ -59,6 +62,12 @@ struct GemmParams {
   // columns, merged across tiles by a 64-bit atomicMin on (orderable d bits << 32 | col)
   unsigned long long* argmin_out;
   const float* row_sq;
+  // Gumbel-max sampling (K6 fused into the head GEMM): no C; per row the running maximum over all columns of
+  // acc * sample_scale - lg2(-lg2(u)), u = a counter hash of (sample key, row, column) in (0, 1), merged across tiles
+  // like the nearest-code search (argmin_out holds ~ordered(value) << 32 | column).  sample_scale = log2(e) / T.
+  int sample_mode;
+  float sample_scale;
+  uint32_t sample_k0, sample_k1;
   // split-K: `splits` CTAs share one output tile; each writes its fp32 partial accumulator to `partials`
   // ([tile][split][128][BN]) and the last one to arrive (per-tile counter) sums them in split order and runs the
   // epilogue.  Deterministic: the summation order does not depend on arrival order.
@@ -406,6 +415,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (*split_flag == 0) continue;
         __threadfence();
         my_partials = p.partials + size_t(tile) * p.splits * BM * BN + size_t(q * 32 + lane) * 4;
+      }
+      if (p.sample_mode) {
+        // categorical draw by the Gumbel-max rule: argmax_v (x_v / T + G_v), G = -ln(-ln u); in the log2 domain and up
+        // to a positive factor, argmax_v (x_v log2(e) / T - lg2(-lg2 u_v)).  The logits never leave the accumulator.
+        const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+        const uint32_t rk = mix32(p.sample_k0 ^ mix32(uint32_t(row) + p.sample_k1));
+        float bestv = -INFINITY;
+        int besti = 0x7fffffff;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_acc + uint32_t(c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t col = uint32_t(n0 + c * 32 + j);
+            const uint32_t hsh = mix32(rk + col * 0x9E3779B9u);
+            const float u = fmaf(float(hsh >> 9), 1.1920928955078125e-07f, 5.9604644775390625e-08f);   // (k + 0.5) 2^-23: in [2^-24, 1 - 2^-24], exact
+            const float v = fmaf(__uint_as_float(r[j]), p.sample_scale, -lg2_approx(-lg2_approx(u)));
+            if (v > bestv) { bestv = v; besti = int(col); }
+          }
+        }
+        tc_fence_before();
+        if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+        if (row_ok && besti != 0x7fffffff) {
+          const uint32_t ub = __float_as_uint(bestv);
+          const uint32_t key = ~((ub & 0x80000000u) ? ~ub : (ub | 0x80000000u));      // larger value -> smaller key
+          atomicMin(p.argmin_out + row, (static_cast<unsigned long long>(key) << 32) | uint32_t(besti));
+        }
+        continue;
       }
       if (p.argmin_out != nullptr) {
         // K9 epilogue: nothing is stored but each row's best (distance, code) over this tile's columns
@@ -883,6 +923,16 @@ int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b
   p.in_kind = (residual != nullptr && !(flags & MEBT_GEMM_INTERNAL_ARGMIN)) ? 1 : (p.dgelu ? 2 : 0);
   p.delta_out = delta_out; p.delta_nq = delta_nq; p.delta_h = delta_h;
   p.fp16_in = 0; p.argmin_out = nullptr; p.row_sq = nullptr;
+  p.sample_mode = 0; p.sample_scale = 0.f; p.sample_k0 = p.sample_k1 = 0u;
+  if (flags & MEBT_GEMM_INTERNAL_SAMPLE) {          // gemm_bf16_sample below: C carries the packed output
+    MEBT_REQUIRE(g_sample_req.active, MEBT_ERR_UNSUPPORTED, "gemm: internal flag");
+    p.sample_mode = 1;
+    p.sample_scale = g_sample_req.scale;
+    p.sample_k0 = g_sample_req.k0; p.sample_k1 = g_sample_req.k1;
+    p.argmin_out = static_cast<unsigned long long*>(C);
+    p.C = nullptr;
+    flags |= MEBT_GEMM_NO_SPLITK;
+  }
   if (flags & MEBT_GEMM_INTERNAL_ARGMIN) {          // gemm_f16_argmin below: C carries the packed output, residual the row norms
     p.fp16_in = 1;
     p.argmin_out = static_cast<unsigned long long*>(C);
@@ -962,6 +1012,23 @@ int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b
     case 128: return dispatch_major<128>(a_mn, b_mn, A, B, p, lda, ldb, stream);
     default: return dispatch_major<64>(a_mn, b_mn, A, B, p, lda, ldb, stream);
   }
+}
+
+// K6 fused into the head GEMM: packed[row] = (~ordered(best value) << 32 | argmax column) of the Gumbel-max draw over
+// all N columns of A B^T / T (bf16 operands); `packed` must be initialised to all ones.  No logits are written.
+int gemm_bf16_sample(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float temperature,
+                     unsigned long long seed, unsigned long long offset, unsigned long long* packed, cudaStream_t stream) {
+  MEBT_REQUIRE(packed != nullptr && temperature > 0.f, MEBT_ERR_SHAPE, "gemm_bf16_sample: bad arguments");
+  g_sample_req.active = true;
+  g_sample_req.scale = float(1.4426950408889634 / (double(temperature) + 1e-8));
+  unsigned long long sd = seed + (offset + 1) * 0x9E3779B97F4A7C15ull;
+  sd ^= sd >> 30; sd *= 0xBF58476D1CE4E5B9ull; sd ^= sd >> 27; sd *= 0x94D049BB133111EBull; sd ^= sd >> 31;   // splitmix64
+  g_sample_req.k0 = uint32_t(sd);
+  g_sample_req.k1 = uint32_t(sd >> 32);
+  const int rc = gemm_bf16_ex(A, lda, 0, B, ldb, 0, packed, 8, M, N, K, nullptr, nullptr, 0, nullptr, 0,
+                              MEBT_GEMM_INTERNAL_SAMPLE, nullptr, nullptr, 0, 0, stream);
+  g_sample_req.active = false;
+  return rc;
 }
 
 // K9 on the tensor cores: packed[row] = min over codes n of (order(d) << 32 | n), d = (row_sq[row] - 2 A[row].B[n]) + col_sq[n],

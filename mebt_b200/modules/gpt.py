@@ -12,6 +12,7 @@ import torch.nn as nn
 
 from .. import _lib, ops
 from ..stack import (LayerWeights, PreciseWeightPack, WeightPack, attention_core, block_forward, stack_forward,
+                     stack_forward_sample,
                      stack_forward_f32)
 
 
@@ -198,6 +199,13 @@ class GPT(nn.Module):
         if lat.dtype == torch.float32:
             return stack_forward_f32(self.precise_pack(), B, lat, ctx, tgt).to(logits_dtype)
         return stack_forward(self.weight_pack(), B, lat, ctx, tgt, logits_dtype)
+
+    def sample_rows(self, B, lat, ctx, tgt, temperature, seed, offset):
+        """Stack + head + one categorical draw per target row in the head GEMM's epilogue -> ids int64 [B*NT] (eval mode,
+        bf16 engine only): the sampler steps of draft / revise without materialised logits."""
+        if self.training or lat.dtype != torch.bfloat16:
+            raise _lib.MebtError("sample_rows: eval mode on the bf16 engine only")
+        return stack_forward_sample(self.weight_pack(), B, lat, ctx, tgt, temperature, seed, offset)
 
     def _forward_rows_dropout(self, B, lat, ctx, tgt, logits_dtype, seed):
         """Training-mode forward with the configured dropout (`model.train(); model(x, c, indices=...)` with the STL

@@ -141,6 +141,23 @@ def attention(q, q_col0, kv1, k1_col0, v1_col0, nk1, kv2, k2_col0, v2_col0, nk2,
     return out
 
 
+def head_sample(x, w_head, temperature=1.0, seed=0, offset=0):
+    """x bf16 [rows, D], w_head bf16 [V, D] -> ids int64 [rows], one draw per row from softmax(x w^T / temperature): the
+    head GEMM with the Gumbel-max epilogue (no logits written)."""
+    _need_cuda(x, w_head)
+    if x.dtype != torch.bfloat16 or w_head.dtype != torch.bfloat16:
+        raise MebtError("head_sample: bf16 operands expected")
+    rows, D, ldx = _rows2d(x)
+    V, D2, ldw = _rows2d(w_head)
+    if D != D2:
+        raise MebtError("head_sample: inner dimensions differ")
+    ids = torch.empty(rows, device=x.device, dtype=torch.int64)
+    ws = _ws(x.device, max(8 * rows, 8), "head_sample")
+    call("mebt_head_sample", x.data_ptr(), ldx, w_head.data_ptr(), ldw, rows, V, D, float(temperature), int(seed), int(offset),
+         ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    return ids
+
+
 def scatter_ids(x, tgt_idx, ids):
     """x[b, tgt_idx[b,i]] = ids[b,i] in place."""
     _need_cuda(x, tgt_idx, ids)

@@ -210,6 +210,26 @@ def stack_forward(pack: WeightPack, B: int, lat, ctx, tgt, logits_dtype=torch.fl
     return logits
 
 
+def stack_forward_sample(pack: WeightPack, B: int, lat, ctx, tgt, temperature: float, seed: int, offset: int, hoist=True):
+    """The eval forward with the sampling step fused into the head GEMM (`mebt_stack_forward_sample`): returns one
+    categorical draw per target row, ids int64 [B*NT], from softmax(logits / temperature) by the Gumbel-max rule with
+    in-kernel counter-hash noise; the [B*NT, V] logits never reach HBM (gpt.py:248 + transformer.py:843-889)."""
+    D = pack.D
+    L, NC, NT = lat.shape[0] // B, ctx.shape[0] // B, tgt.shape[0] // B
+    for t in (lat, ctx, tgt):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous():
+            raise _lib.MebtError("stack_forward streams must be contiguous bf16")
+    ids = torch.empty(B * NT, device=lat.device, dtype=torch.int64)
+    h = pack.hoist if (hoist and pack.hoist is not None and NC > 0) else None
+    nbytes = _lib.lib.mebt_stack_forward_hoisted_workspace_bytes(B, L, NC, NT, D, h.n_enc if h is not None else 0)
+    ws = _workspace(lat.device, nbytes)
+    _lib.call("mebt_stack_forward_sample", pack.c_layers, len(pack.layers), pack.lnf_w.data_ptr(), pack.lnf_b.data_ptr(),
+              pack.w_head.data_ptr(), ctypes.byref(h) if h is not None else None, B, L, NC, NT, D, pack.n_head, pack.V,
+              lat.data_ptr(), ctx.data_ptr(), tgt.data_ptr(), None, 0, ids.data_ptr(), float(temperature), int(seed),
+              int(offset), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    return ids
+
+
 def stack_forward_ops(pack: WeightPack, B: int, lat, ctx, tgt, logits_dtype=torch.float32, skip_dead=True):
     """Same computation composed op by op from Python (one C-ABI call per kernel); used by the per-module
     drop-in API and as a cross-check of the engine."""

@@ -188,6 +188,8 @@ class Net2NetTransformer(_Base):
         # leave the library: None = bf16 under precision "bf16" (half the head GEMM's store and the sampling kernel's read;
         # the rounding, 2^-9 relative, is below the bf16 forward's own 1e-2), fp32 under precision "fp32"
         self.sampler_logits_dtype = None
+        # draft / revise steps with in-kernel noise: draw the token in the head GEMM's epilogue, no logits in HBM
+        self.fused_head_sampling = True
         # "bf16": tcgen05 engine, logits within 1e-2 of the fp32 reference; "fp32": split-GEMM + fp32 attention path,
         # within 1e-4 (north_star tolerances).  Also settable from the config (`precision: fp32`).
         self.precision = str(getattr(transformer_config, "precision", "bf16"))
@@ -315,9 +317,24 @@ class Net2NetTransformer(_Base):
             context_indices, target_indices = context_indices.clone(), target_indices.clone()
         return context_indices, target_indices
 
-    def _predict_and_write(self, partial, ctx_idx, tgt_idx, temperature, top_k, top_p, want_probs=False):
-        """One sampler step: forward, sample every target, write the ids back.  -> (ids, scores, probs)"""
+    def _predict_and_write(self, partial, ctx_idx, tgt_idx, temperature, top_k, top_p, want_probs=False, want_scores=True):
+        """One sampler step: forward, sample every target, write the ids back.  -> (ids, scores, probs)
+        want_scores=False (the gibbs passes of draft / revise, which use only the ids) with in-kernel noise, no top-k /
+        top-p and the bf16 engine takes the FUSED form: the head GEMM's epilogue draws the token (Gumbel-max over the
+        fp32 accumulators, `mebt_stack_forward_sample`) and no logits are materialised (`fused_head_sampling`)."""
         B = partial.shape[0]
+        NT = tgt_idx.shape[1]
+        if (self.fused_head_sampling and not want_scores and not want_probs and self.rng_mode == "philox" and not top_k
+                and top_p is None and self.precision == "bf16" and temperature > 0 and NT > 0
+                and "_logits_rows" not in self.__dict__):
+            if not partial.is_cuda:
+                raise MebtError("mebt_b200 runs on CUDA tensors only (no CPU fallback); move the model and inputs to cuda")
+            ctx, tgt, lat = ops.embed_gather(partial, ctx_idx, tgt_idx, self.tok_emb.weight, self.pos_emb, self.mask_emb,
+                                             self.sos_emb, out_dtype=torch.bfloat16)
+            self._rng_offset += 1
+            ids = self.transformer.sample_rows(B, lat, ctx, tgt, float(temperature), self.rng_seed, self._rng_offset)
+            ops.scatter_ids(partial, tgt_idx, ids.view(B, NT))
+            return ids.view(B, NT), None, None
         dt = self.sampler_logits_dtype or (torch.bfloat16 if self.precision == "bf16" else torch.float32)
         logits = self._logits_rows(partial, ctx_idx, tgt_idx, dt)
         ids, scores, probs = self._sample_rows(logits, temperature, top_k, top_p, return_probs=want_probs)
@@ -413,7 +430,7 @@ class Net2NetTransformer(_Base):
         ctxs, tgts = make_masks(context_indices, target_indices, n_steps, x.device)
         assert not self.transformer.training
         for ctx_idx, tgt_idx in zip(ctxs, tgts):
-            self._predict_and_write(partial, ctx_idx, tgt_idx.view(B, -1), temperature, top_k, top_p)
+            self._predict_and_write(partial, ctx_idx, tgt_idx.view(B, -1), temperature, top_k, top_p, want_scores=False)
         return partial.view(B, -1)
 
     @torch.no_grad()

@@ -339,3 +339,35 @@ def test_latent_attention_split_kv(B, H, NQ, NK1, NK2):
     scale = max(1.0, ref.abs().max().item())
     assert (out.float() - ref).abs().max().item() < 2e-2 * scale
     assert (out.float() - unsplit.float()).abs().max().item() < 1e-2 * scale
+
+
+def test_head_sample_fused_gumbel_max():
+    """The sampling step fused into the head GEMM (no logits in HBM): draws follow softmax(logits / T) - checked on 60000
+    rows that share one logit vector, category by category within 5 sigma plus the total-variation distance -, differ
+    between (seed, offset) pairs and are reproducible for the same pair; a second, peaked row type checks the temperature."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    D, V, rows = 64, 1024, 60000
+    w = (0.35 * torch.randn(V, D, generator=g)).bfloat16()
+    x1 = torch.randn(D, generator=g).bfloat16()
+    for T in (1.0, 0.7):
+        x = x1.repeat(rows, 1).contiguous()
+        ids = ops.head_sample(x.cuda(), w.cuda(), T, seed=11, offset=3).cpu()
+        assert int(ids.min()) >= 0 and int(ids.max()) < V
+        logits = (w.float() @ x1.float()).double()                     # what the tensor cores accumulate (fp32) from bf16 operands
+        p = torch.softmax(logits / (T + 1e-8), 0)
+        emp = torch.bincount(ids, minlength=V).double() / rows
+        sigma = (p * (1 - p) / rows).sqrt()
+        assert ((emp - p).abs() <= 5 * sigma + 1e-4).all(), ((emp - p).abs() / (sigma + 1e-12)).max()
+        assert 0.5 * (emp - p).abs().sum() < 0.06                      # total variation (sampling noise alone gives ~0.05)
+    x = x1.repeat(rows, 1).contiguous().cuda()
+    a = ops.head_sample(x, w.cuda(), 1.0, seed=11, offset=3)
+    b = ops.head_sample(x, w.cuda(), 1.0, seed=11, offset=3)
+    c = ops.head_sample(x, w.cuda(), 1.0, seed=11, offset=4)
+    d = ops.head_sample(x, w.cuda(), 1.0, seed=12, offset=3)
+    assert torch.equal(a, b) and (a != c).float().mean() > 0.5 and (a != d).float().mean() > 0.5
+    # rows draw independently: neighbouring rows agree no more often than sum_v p_v^2 predicts
+    same = (a[1:] == a[:-1]).float().mean().item()
+    logits = (w.float() @ x1.float()).double()
+    p = torch.softmax(logits, 0)
+    assert abs(same - float((p * p).sum())) < 0.01
