@@ -45,13 +45,16 @@ def bidirect_sample(model, batch_size, total_length, step_size, context_size, te
     x = torch.zeros(shape, dtype=torch.long, device=device)
     context_indices = target_indices = None
     bs_partial_probs = None
+    # the script only ever gathers the dense [B, N, 16384] probability maps at the final codes: ask the sampler for that
+    # gather directly when it can provide it (mebt_b200's Net2NetTransformer), the dense maps otherwise
+    extra = dict(debug_probs="selected") if getattr(model, "selected_probs_supported", False) else {}
     if bootstrap > 0:
         x, context_indices, target_indices, _, _, bs_partial_probs = model.sample(
             x, None, 1., None, None, bootstrap, context_indices, target_indices, context_temperature=vid_c_temp,
-            skips=False, ctemp_schedule=ctemp_schedule, strategy="bootstrap", debug=True)
+            skips=False, ctemp_schedule=ctemp_schedule, strategy="bootstrap", debug=True, **extra)
     x, context_indices, _, _, _, final_partial_probs = model.sample(
         x, None, temperature, top_k, top_p, vid_n_steps, context_indices, target_indices,
-        context_temperature=vid_c_temp, skips=False, ctemp_schedule=ctemp_schedule, strategy=strategy, debug=True)
+        context_temperature=vid_c_temp, skips=False, ctemp_schedule=ctemp_schedule, strategy=strategy, debug=True, **extra)
     curr_t = step_size
     vq_x = x.reshape(shape)
     code_map.append(vq_x)
@@ -76,7 +79,10 @@ def bidirect_sample(model, batch_size, total_length, step_size, context_size, te
         final_prob_map = torch.where(final_partial_probs < 0., bs_partial_probs, final_partial_probs)
     else:
         final_prob_map = final_partial_probs
-    selected = torch.gather(final_prob_map, -1, code_map.reshape(batch_size, -1, 1)).squeeze(-1)
+    if final_prob_map.dim() == 2:          # already the probability of each position's final code
+        selected = final_prob_map
+    else:
+        selected = torch.gather(final_prob_map, -1, code_map.reshape(batch_size, -1, 1)).squeeze(-1)
     log["score"] = selected.log().sum(-1)
     return log
 

@@ -190,6 +190,7 @@ class Net2NetTransformer(_Base):
         self.sampler_logits_dtype = None
         # draft / revise steps with in-kernel noise: draw the token in the head GEMM's epilogue, no logits in HBM
         self.fused_head_sampling = True
+        self.selected_probs_supported = True      # sample(debug=True, debug_probs="selected"), see mebt_b200.pipelines
         # "bf16": tcgen05 engine, logits within 1e-2 of the fp32 reference; "fp32": split-GEMM + fp32 attention path,
         # within 1e-4 (north_star tolerances).  Also settable from the config (`precision: fp32`).
         self.precision = str(getattr(transformer_config, "precision", "bf16"))
@@ -345,8 +346,13 @@ class Net2NetTransformer(_Base):
     @torch.no_grad()
     def sample(self, x, c, temperature=1.0, top_k=None, top_p=None, n_steps=8, context_indices=None, target_indices=None,
                strategy="maskgit", context_temperature=4.5, phase_history=None, refine_steps=1, forget_pivot=False,
-               skips=[False, False, False], debug=False, ctemp_schedule="linear", edit=False):
-        """Iterative maskgit-style decoding with confidence re-masking (transformer.py:353-447)."""
+               skips=[False, False, False], debug=False, ctemp_schedule="linear", edit=False, debug_probs="dense"):
+        """Iterative maskgit-style decoding with confidence re-masking (transformer.py:353-447).
+        debug=True returns, like the reference, the dense [B, N, 16384] fp32 map of the last predictive distribution of
+        every position (2 GB at B = 32, 16 frames; 17 GB at 128 frames).  debug_probs="selected" (an extension; what the
+        sampling scripts actually consume, sample_vqgan_transformer_videos.py:85-89) returns instead the [B, N] map of the
+        probability of the token that was sampled at each position's last prediction (-1 where never predicted): the
+        gather of the dense map at the final code, without the dense map."""
         B = x.shape[0]
         N = int(np.prod(x.shape[1:]))
         edit_N = target_indices.shape[1] if edit else N
@@ -357,9 +363,10 @@ class Net2NetTransformer(_Base):
         context_indices, target_indices = self._initial_masks(partial, context_indices, target_indices, clone=True)
         ctemp_fn = _CTEMP_SCHEDULES[ctemp_schedule] if ctemp_schedule in _CTEMP_SCHEDULES else eval(ctemp_schedule)
         history, context_history, partial_probs = [], [], None
+        sparse = debug and debug_probs == "selected"
         if debug:
             history.append(partial.clone())
-            partial_probs = -torch.ones(B, N, 16384, device=x.device)
+            partial_probs = -torch.ones((B, N) if sparse else (B, N, 16384), device=x.device)
         self.mask_sampler.rng_mode, self.mask_sampler.rng_seed = self.rng_mode, self.rng_seed + 1
         for t_next in np.linspace(0, 1, n_steps + 1)[1:]:
             t = torch.full((B,), fill_value=t_next, device=x.device)              # float32
@@ -370,8 +377,10 @@ class Net2NetTransformer(_Base):
                 continue                                                           # context already larger than asked
             target_indices = target_indices.view(B, -1)
             _, scores, probs = self._predict_and_write(partial, context_indices, target_indices, temperature, top_k,
-                                                       top_p, want_probs=debug)
-            if debug:
+                                                       top_p, want_probs=debug and not sparse)
+            if sparse:
+                partial_probs.scatter_(1, target_indices, scores)
+            elif debug:
                 partial_probs.scatter_(1, target_indices.unsqueeze(-1).expand(-1, -1, probs.shape[-1]), probs)
                 history.append(partial.clone())
                 context_history.append(context_indices)

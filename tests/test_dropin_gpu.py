@@ -243,3 +243,28 @@ def test_sampling_script_pipelines_on_the_cuda_model():
     assert torch.equal(cm2[:, :4], start)                    # the given tokens are kept
     assert int(cm2.min()) >= 0 and int(cm2.max()) < 16384
     assert not torch.equal(cm2[:, 4:6], cm2[:, 6:8])
+
+
+def test_sample_debug_selected_probs_equal_the_gather_of_the_dense_map():
+    """sample(debug=True, debug_probs="selected") returns the [B, N] probabilities of the finally chosen codes - the
+    gather the sampling scripts apply to the dense [B, N, 16384] map (sample_vqgan_transformer_videos.py:85-89) - and is
+    identical to that gather on the dense map of an identically seeded run."""
+    from oracle import mebt_oracle as O
+    z, cfg = load_golden("sampling_micro")
+    P = O.make_weights(cfg, int(z["wseed"]))
+    model = build_model(cfg, P, schedule="cosine")
+    model.rng_mode, model.rng_seed = "philox", 77
+    x0 = torch.zeros(2, 256, dtype=torch.long, device="cuda")
+    outs = []
+    for mode in ("dense", "selected"):
+        model._rng_offset = 0
+        model.mask_sampler.rng_offset = 0
+        # top_k = V filters nothing but keeps both runs on the same sampling kernel (without it the run that needs no
+        # probabilities takes the streaming inverse-CDF kernel, whose prefix sums round differently)
+        outs.append(model.sample(x0, None, 1.0, 16384, None, n_steps=5, strategy="maskgit", context_temperature=4.5,
+                                 debug=True, debug_probs=mode))
+    (xd, cd, td, _, _, dense), (xs, cs, ts, _, _, sel) = outs
+    assert torch.equal(xd, xs) and torch.equal(cd, cs) and torch.equal(td, ts)
+    assert dense.shape == (2, 256, 16384) and sel.shape == (2, 256)
+    gathered = torch.gather(dense, -1, xd.unsqueeze(-1)).squeeze(-1)
+    assert torch.allclose(gathered, sel, rtol=1e-6, atol=0)
