@@ -91,6 +91,21 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(pl) + (__float_as_int(xf) << 23));
 }
 
+// the same for two values at once on the packed f32x2 FMA path (half the issue slots per element)
+__device__ __forceinline__ float2 ex2_poly_x2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 xf = __fadd2_rn(x, magic);
+  const float2 fl = __fadd2_rn(xf, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(fl, make_float2(-1.f, -1.f), x);
+  float2 pl = __ffma2_rn(make_float2(0.0551716685f, 0.0551716685f), f, make_float2(0.2426111251f, 0.2426111251f));
+  pl = __ffma2_rn(pl, f, make_float2(0.6932609677f, 0.6932609677f));
+  pl = __ffma2_rn(pl, f, make_float2(0.9999280572f, 0.9999280572f));
+  return make_float2(__int_as_float(__float_as_int(pl.x) + (__float_as_int(xf.x) << 23)),
+                     __int_as_float(__float_as_int(pl.y) + (__float_as_int(xf.y) << 23)));
+}
+
 template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv1,
@@ -194,10 +209,14 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
 #define MTR_BEGIN
 #define MTR_END(i)
 #endif
+      constexpr uint32_t kDescHi = smem_desc_hi_sw128(1024);
+      const uint32_t q_lo0 = smem_desc_lo(smem_u32(smem + AT_SMEM_Q), 16);          // Q, K: K-major, 32 B per K = 16 step
+      const uint32_t k_lo0 = smem_desc_lo(smem_u32(smem + AT_SMEM_K), 16);
+      const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem + AT_SMEM_V), 64 * 128);    // V: MN-major, 2048 B per 16 keys
       // step g = 2 * (K/V tile counter gj) + warpgroup t
       const int total = my_items * nts * 2;
       // S_t of tile gj: legal once warpgroup t has consumed the S of tile gj-1
-      auto issue_s = [&](int g) {
+      auto issue_s = [&](int g, bool commit) {
         const int gj = g >> 1, t = g & 1;
         const int n = gj / nts, j = gj - n * nts;
         if (t == 0) {
@@ -207,16 +226,16 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
           MTR_END(1);
           tc_fence_after();
         }
-        const uint32_t sQ = smem_u32(smem + AT_SMEM_Q + (2 * (n & 1) + t) * AT_TILE_BYTES);
-        const uint32_t sK = smem_u32(smem + AT_SMEM_K + (gj % AT_KV_STAGES) * AT_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < AT_HS / 16; ++k)
-          umma_bf16_ss(tmem_base + t * 128, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
-                       make_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[t]);
+        // the issuing thread is what bounds this kernel (tools/mma_probe.cu: ~48 clk per instruction issued from one
+        // block over precomputed descriptor words against ~97 with a descriptor rebuilt per instruction; ~165 clk per
+        // commit, ~163 per barrier wait), so: four / eight instructions per asm block, descriptor low words advanced by adds
+        const uint32_t q_lo = q_lo0 + uint32_t(2 * (n & 1) + t) * uint32_t(AT_TILE_BYTES >> 4);
+        const uint32_t k_lo = k_lo0 + uint32_t(gj % AT_KV_STAGES) * uint32_t(AT_TILE_BYTES >> 4);
+        umma_bf16_ss_x4<false>(tmem_base + t * 128, q_lo, k_lo, 2, 2, kDescHi, kDescHi, idesc_s, 0u);
+        if (commit) umma_commit(&s_full[t]);
         if (t == 1 && j == nts - 1) umma_commit(&q_empty[n & 1]);     // the item's last S: its Q buffer is free
       };
-      if (total > 0) { issue_s(0); issue_s(1); }
+      if (total > 0) { issue_s(0, true); issue_s(1, true); }
       for (int g = 0; g < total; ++g) {
         const int t = g & 1, gj = g >> 1;
         const int j = gj % nts;
@@ -225,13 +244,21 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         mbar_wait(&p_full[t], gj & 1);
         MTR_END(0);
         tc_fence_after();
-        if (g + 2 < total) issue_s(g + 2);       // the warpgroup's next S first: it is what the warpgroup waits for
-        const uint32_t sV = smem_u32(smem + AT_SMEM_V + (gj % AT_KV_STAGES) * AT_TILE_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < AT_BKV / 16; ++kk)
-          umma_bf16_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + kk * 8,
-                       make_smem_desc_sw128(sV + kk * 2048, 64 * 128, 1024), idesc_o, (j != 0 || kk != 0) ? 1u : 0u);
-        umma_commit(&pv_done[t]);
+        // PV of this tile, then the warpgroup's next S, then ONE commit on s_full[t]: "S of tile gj+1 is ready" then also
+        // means "PV of tile gj has retired" (O includes it, P may be overwritten), which saves a commit here (~165 clk of
+        // this thread) and a barrier wait in the warpgroup (~160-250 clk) per tile; the kernel is bound by these
+        // hand-offs, not by the tensor pipe (tools/mma_probe.cu).  The very last PV of a warpgroup signals pv_done.
+        const uint32_t v_lo = v_lo0 + uint32_t(gj % AT_KV_STAGES) * uint32_t(AT_TILE_BYTES >> 4);
+        MTR_BEGIN;
+        umma_bf16_ts_x8(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64, 8u, v_lo, 2048u >> 4, kDescHi, idesc_o,
+                        j != 0 ? 1u : 0u);
+        MTR_END(2);
+        if (g + 2 < total) {
+          issue_s(g + 2, false);
+          umma_commit(&s_full[t]);
+        } else {
+          umma_commit(&pv_done[t]);
+        }
         if (t == 1) umma_commit(&kv_empty[gj % AT_KV_STAGES]);   // both warpgroups' S and PV of this K/V stage are done
       }
 #ifdef MEBT_ATTN_TRACE
@@ -314,12 +341,7 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
               m = mx;
               mb = mx * p.scale_log2;
             }
-            if (k > 0) {
-              ATR_BEGIN;
-              mbar_wait(&pv_done[t], (k - 1) & 1);
-              ATR_END(1);
-              tc_fence_after();
-            }
+            // (s_full of this tile was committed behind the previous tile's PV: P may be overwritten, O is up to date)
             chunk(full_tag, ra, 0, mb, l4, m4);
             tmem_ld_wait_regs(rb);
             tmem_ld_32x32(tmem_s + 64, ra);
@@ -332,12 +354,72 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
             l_tile = (l4[0] + l4[1]) + (l4[2] + l4[3]);
             mx_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           };
+          // Fast pass (full tiles without dropout - all but a source's last tile): the softmax warps are bound by their
+          // own issue slots and the MUFU pipe (two warps share a scheduler: per K/V tile 2 x 128 elements x (~6.5 slots,
+          // 8 MUFU clk for three in four)), so the arithmetic is PACKED: exponent argument and row sum in f32x2, three
+          // pairs in eight exponentiated by the packed polynomial, and instead of the running maximum of the raw
+          // scores the maximum of the bf16 P pairs (one HMNMX2 per pair): P > 2^8 is exactly the lazy stabiliser's
+          // overflow test, and only then (rare) does the slow pass below run to find the new maximum.
+          auto chunk_fast = [&](const uint32_t (&r)[32], int c, const float2 sc2, const float2 nmb2, float2& lsum,
+                                __nv_bfloat162& pmax) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, nmb2);
+              float2 pv;
+              if (MEBT_ATTN_POLY && ((i & 7) == 1 || (i & 7) == 4 || (i & 7) == 6)) {
+                pv = ex2_poly_x2(x);
+              } else {
+                pv.x = ex2_approx(x.x);
+                pv.y = ex2_approx(x.y);
+              }
+              lsum = __fadd2_rn(lsum, pv);
+              pk[i] = pack_bf16x2(pv.x, pv.y);
+              pmax = __hmax2(pmax, *reinterpret_cast<const __nv_bfloat162*>(&pk[i]));
+            }
+            tmem_st_32x16(tmem_p + c * 16, pk);
+          };
+          auto row_pass_fast = [&](float& l_tile, bool seed) -> bool {
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(tmem_s, ra);
+            tmem_ld_32x32(tmem_s + 32, rb);
+            tmem_ld_wait_regs(ra);
+            if (seed) {                               // seed the stabiliser from the first 32 scores
+              float mx = __uint_as_float(ra[0]);
+#pragma unroll
+              for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
+              m = mx;
+            }
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+            const float2 nmb2 = make_float2(-m * p.scale_log2, -m * p.scale_log2);
+            float2 lsum = make_float2(0.f, 0.f);
+            __nv_bfloat162 pmax = __float2bfloat162_rn(0.f);
+            chunk_fast(ra, 0, sc2, nmb2, lsum, pmax);
+            tmem_ld_wait_regs(rb);
+            tmem_ld_32x32(tmem_s + 64, ra);
+            chunk_fast(rb, 1, sc2, nmb2, lsum, pmax);
+            tmem_ld_wait_regs(ra);
+            tmem_ld_32x32(tmem_s + 96, rb);
+            chunk_fast(ra, 2, sc2, nmb2, lsum, pmax);
+            tmem_ld_wait_regs(rb);
+            chunk_fast(rb, 3, sc2, nmb2, lsum, pmax);
+            l_tile = lsum.x + lsum.y;
+            const float pm = fmaxf(__low2float(pmax), __high2float(pmax));
+            return !(pm <= 256.0f);                   // also true for inf / NaN
+          };
           float l_tile, mx_tile;
 #ifdef MEBT_ATTN_TRACE
           const long long rp0 = clock64(), w0 = tr_acc[1];
 #endif
-          if (full) row_pass(std::true_type{}, m * p.scale_log2, l_tile, mx_tile, j == 0);
-          else row_pass(std::false_type{}, m * p.scale_log2, l_tile, mx_tile, j == 0);
+          bool need_slow = true;
+          if (full && !DROP) need_slow = __any_sync(0xffffffffu, row_pass_fast(l_tile, j == 0));
+          mx_tile = m;
+          if (need_slow) {
+            // (after a fast pass that overflowed the stabiliser is already seeded: do not re-seed)
+            const bool seed_here = j == 0 && !(full && !DROP);
+            if (full) row_pass(std::true_type{}, m * p.scale_log2, l_tile, mx_tile, seed_here);
+            else row_pass(std::false_type{}, m * p.scale_log2, l_tile, mx_tile, seed_here);
+          }
 #ifdef MEBT_ATTN_TRACE
           tr_acc[2] += (clock64() - rp0) - (tr_acc[1] - w0);
 #endif
@@ -368,7 +450,9 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       const int qrow = qt * AT_BQ + row;
       if (nt > 0) {                     // the item's last PV: O complete
         ATR_BEGIN;
-        mbar_wait(&pv_done[t], (k - 1) & 1);
+        // ... signalled with the next item's first S (same commit), or, behind this CTA's last tile, on pv_done
+        if (n + 1 < my_items) mbar_wait(&s_full[t], k & 1);
+        else mbar_wait(&pv_done[t], 0);
         ATR_END(1);
         tc_fence_after();
       }

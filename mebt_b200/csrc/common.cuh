@@ -404,6 +404,38 @@ __device__ __forceinline__ void umma_bf16_ss_x4(uint32_t tmem_d, uint32_t a_lo, 
 #undef MEBT_MMA4
 }
 
+// Eight K = 16 steps with the A operand in tensor memory (attention's O += P V over one 128-key tile): A advances by
+// a_step TMEM columns per step, B's descriptor low word by b_step.
+__device__ __forceinline__ void umma_bf16_ts_x8(uint32_t tmem_d, uint32_t tmem_a, uint32_t a_step, uint32_t b_lo,
+                                                uint32_t b_step, uint32_t b_hi, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, t;\n"
+      ".reg .b64 db;\n"
+      ".reg .b32 ta, bl;\n"
+      "setp.ne.b32 p, %7, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "mov.b64 db, {%3, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %6, p;\n"
+      "add.u32 ta, %1, %2;\n add.u32 bl, %3, %4;\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %6, t;\n"
+      "add.u32 ta, ta, %2;\n add.u32 bl, bl, %4;\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %6, t;\n"
+      "add.u32 ta, ta, %2;\n add.u32 bl, bl, %4;\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %6, t;\n"
+      "add.u32 ta, ta, %2;\n add.u32 bl, bl, %4;\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %6, t;\n"
+      "add.u32 ta, ta, %2;\n add.u32 bl, bl, %4;\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %6, t;\n"
+      "add.u32 ta, ta, %2;\n add.u32 bl, bl, %4;\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %6, t;\n"
+      "add.u32 ta, ta, %2;\n add.u32 bl, bl, %4;\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %6, t;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(a_step), "r"(b_lo), "r"(b_step), "r"(b_hi), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M x K, K-major) is read from tensor memory - row m in lane m,
 // two bf16 per 32-bit column, element k in column k / 2 (low half = even k).  A K = 16 step consumes 8 columns.
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,

@@ -39,8 +39,8 @@ int main() {
     printf("%-12s B=%2d NQ=%5d NK=%5d | %8.1f us | per softmax WG: wait S %8.0f  wait O %8.0f  row pass %8.0f  total %8.0f clk | ~%.0f tiles per CTA -> %.0f clk per 128x128 tile\n",
            s.name, s.B, s.NQ, s.NK, ms * 1e3 / 20, a[0], a[1], a[2], a[3], tiles, a[3] / tiles);
 #ifndef NO_TRACE
-    { double s0 = 0, s1 = 0, s3 = 0; int c = 0; for (int i = 0; i < 148; ++i) if (h[148 * 8 + 4 * i + 3]) { ++c; s0 += h[148 * 8 + 4 * i]; s1 += h[148 * 8 + 4 * i + 1]; s3 += h[148 * 8 + 4 * i + 3]; }
-      if (c) printf("   mma thread: wait P %.0f  wait K/V,Q %.0f  total %.0f clk (%.0f steps)\n", s0 / c, s1 / c, s3 / c, tiles); }
+    { double s0 = 0, s1 = 0, s2 = 0, s3 = 0; int c = 0; for (int i = 0; i < 148; ++i) if (h[148 * 8 + 4 * i + 3]) { ++c; s0 += h[148 * 8 + 4 * i]; s1 += h[148 * 8 + 4 * i + 1]; s2 += h[148 * 8 + 4 * i + 2]; s3 += h[148 * 8 + 4 * i + 3]; }
+      if (c) printf("   mma thread: wait P %.0f  wait K/V,Q %.0f  PV issue (8 MMAs) %.0f  total %.0f clk (%.0f steps)\n", s0 / c, s1 / c, s2 / c, s3 / c, tiles); }
 #endif
     cudaFree(q); cudaFree(kv); cudaFree(o);
   }
