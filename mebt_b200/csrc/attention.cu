@@ -36,7 +36,10 @@ namespace {
 constexpr int AT_BQ = 128;
 constexpr int AT_BKV = 128;
 constexpr int AT_HS = 64;
-constexpr int AT_THREADS = 320;
+#ifndef MEBT_ATTN_TWO_ISSUERS
+#define MEBT_ATTN_TWO_ISSUERS 1     // 1: S = Q K^T and O += P V are issued by two different threads (warps 9 and 10)
+#endif
+constexpr int AT_THREADS = MEBT_ATTN_TWO_ISSUERS ? 352 : 320;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;      // 16 KiB: a [128 x 64] bf16 tile (Q, K or V)
 constexpr int AT_KV_STAGES = 5;
 constexpr int AT_MAX_SPLITS = 8;                 // split-KV fan-out (workspace = AT_MAX_SPLITS partial outputs)
@@ -196,6 +199,75 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         }
       }
     }
+#if MEBT_ATTN_TWO_ISSUERS
+  // Two MMA-issuing threads.  With one, that thread was busy ~83 % of the kernel (tools/attn_bench.cu: ~1700 clk per
+  // (query tile, K/V tile) step, 1000 of them inside the eight PV instructions, whose issue competes for scheduler slots
+  // with the two softmax warps of its sub-partition) while the softmax warpgroups spent 63 % of their time waiting for S.
+  // S = Q K^T (warp 9) and O += P V (warp 10) touch different accumulators and are ordered through the warpgroups'
+  // barriers, so the result does not depend on how the two threads interleave.
+  } else if (warp == 9) {
+    if (lane == 0 && nt > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
+      constexpr uint32_t kDescHi = smem_desc_hi_sw128(1024);
+      const uint32_t q_lo0 = smem_desc_lo(smem_u32(smem + AT_SMEM_Q), 16);          // Q, K: K-major, 32 B per K = 16 step
+      const uint32_t k_lo0 = smem_desc_lo(smem_u32(smem + AT_SMEM_K), 16);
+      const int total = my_items * nts * 2;       // step g = 2 * (K/V tile counter gj) + warpgroup t
+      for (int g = 0; g < total; ++g) {
+        const int gj = g >> 1, t = g & 1;
+        const int n = gj / nts, j = gj - n * nts;
+        if (t == 0) {
+          if (j == 0) mbar_wait(&q_full[n & 1], (n >> 1) & 1);
+          mbar_wait(&kv_full[gj % AT_KV_STAGES], (gj / AT_KV_STAGES) & 1);
+        }
+        if (gj > 0) mbar_wait(&p_full[t], (gj - 1) & 1);     // warpgroup t has consumed the S of tile gj-1
+        tc_fence_after();
+        const uint32_t q_lo = q_lo0 + uint32_t(2 * (n & 1) + t) * uint32_t(AT_TILE_BYTES >> 4);
+        const uint32_t k_lo = k_lo0 + uint32_t(gj % AT_KV_STAGES) * uint32_t(AT_TILE_BYTES >> 4);
+        umma_bf16_ss_x4<false>(tmem_base + t * 128, q_lo, k_lo, 2, 2, kDescHi, kDescHi, idesc_s, 0u);
+        umma_commit(&s_full[t]);
+        if (t == 1 && j == nts - 1) umma_commit(&q_empty[n & 1]);     // the item's last S: its Q buffer is free
+      }
+    }
+  } else if (warp == 10) {
+    if (lane == 0 && nt > 0) {
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // P (TMEM, K-major) x V (MN-major: hs contiguous)
+      constexpr uint32_t kDescHi = smem_desc_hi_sw128(1024);
+      const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem + AT_SMEM_V), 64 * 128);    // V: MN-major, 2048 B per 16 keys
+#ifdef MEBT_ATTN_TRACE
+      long long mt[3] = {0, 0, 0}, mt0 = 0;
+      const long long mstart = clock64();
+#define MTR_BEGIN mt0 = clock64()
+#define MTR_END(i) mt[i] += clock64() - mt0
+#else
+#define MTR_BEGIN
+#define MTR_END(i)
+#endif
+      const int total = my_items * nts * 2;
+      for (int g = 0; g < total; ++g) {
+        const int t = g & 1, gj = g >> 1;
+        const int j = gj % nts;
+        MTR_BEGIN;
+        if (t == 0) mbar_wait(&kv_full[gj % AT_KV_STAGES], (gj / AT_KV_STAGES) & 1);     // (complete long ago: this thread's own view of V)
+        MTR_END(1);
+        // warpgroup t is done with tile gj: S consumed, P in TMEM (and, at j == 0, the previous item's O read)
+        MTR_BEGIN;
+        mbar_wait(&p_full[t], gj & 1);
+        MTR_END(0);
+        tc_fence_after();
+        const uint32_t v_lo = v_lo0 + uint32_t(gj % AT_KV_STAGES) * uint32_t(AT_TILE_BYTES >> 4);
+        MTR_BEGIN;
+        umma_bf16_ts_x8(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64, 8u, v_lo, 2048u >> 4, kDescHi, idesc_o,
+                        j != 0 ? 1u : 0u);
+        MTR_END(2);
+        umma_commit(&pv_done[t]);
+        // both warpgroups' PV of this K/V stage have retired, hence (through the warpgroups) their S as well
+        if (t == 1) umma_commit(&kv_empty[gj % AT_KV_STAGES]);
+      }
+#ifdef MEBT_ATTN_TRACE
+      if (p.trace != nullptr) { long long* o = p.trace + 148 * 8 + blockIdx.x * 4; o[0] = mt[0]; o[1] = mt[1]; o[2] = mt[2]; o[3] = clock64() - mstart; }
+#endif
+    }
+#else
   } else if (warp == 9) {
     if (lane == 0 && nt > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
@@ -265,6 +337,7 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       if (p.trace != nullptr) { long long* o = p.trace + 148 * 8 + blockIdx.x * 4; o[0] = mt[0]; o[1] = mt[1]; o[2] = mt[2]; o[3] = clock64() - mstart; }
 #endif
     }
+#endif
   } else {
     // ===== softmax warpgroups =====
     const int t = warp >> 2;                      // warpgroup: query tile 2 * pair + t
@@ -341,7 +414,15 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
               m = mx;
               mb = mx * p.scale_log2;
             }
-            // (s_full of this tile was committed behind the previous tile's PV: P may be overwritten, O is up to date)
+#if MEBT_ATTN_TWO_ISSUERS
+            if (k > 0) {                              // the previous tile's PV reads P: wait before overwriting it
+              ATR_BEGIN;
+              mbar_wait(&pv_done[t], (k - 1) & 1);
+              ATR_END(1);
+              tc_fence_after();
+            }
+#endif
+            // (one issuer: s_full of this tile was committed behind the previous tile's PV)
             chunk(full_tag, ra, 0, mb, l4, m4);
             tmem_ld_wait_regs(rb);
             tmem_ld_32x32(tmem_s + 64, ra);
@@ -394,6 +475,14 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
             const float2 nmb2 = make_float2(-m * p.scale_log2, -m * p.scale_log2);
             float2 lsum = make_float2(0.f, 0.f);
             __nv_bfloat162 pmax = __float2bfloat162_rn(0.f);
+#if MEBT_ATTN_TWO_ISSUERS
+            if (k > 0) {
+              ATR_BEGIN;
+              mbar_wait(&pv_done[t], (k - 1) & 1);
+              ATR_END(1);
+              tc_fence_after();
+            }
+#endif
             chunk_fast(ra, 0, sc2, nmb2, lsum, pmax);
             tmem_ld_wait_regs(rb);
             tmem_ld_32x32(tmem_s + 64, ra);
@@ -444,6 +533,11 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
           l += l_tile;
           tmem_st_wait();
         }
+#if MEBT_ATTN_TWO_ISSUERS
+        // a warpgroup without a tile (odd tile count) must not run ahead of the PV issuer either: parity waits alias
+        // when a barrier gets two phases ahead of a waiter
+        if (!active && k > 0) mbar_wait(&pv_done[t], (k - 1) & 1);
+#endif
         tc_fence_before();
         mbar_arrive(&p_full[t]);
       }
@@ -451,8 +545,12 @@ latent_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
       if (nt > 0) {                     // the item's last PV: O complete
         ATR_BEGIN;
         // ... signalled with the next item's first S (same commit), or, behind this CTA's last tile, on pv_done
+#if MEBT_ATTN_TWO_ISSUERS
+        mbar_wait(&pv_done[t], (k - 1) & 1);
+#else
         if (n + 1 < my_items) mbar_wait(&s_full[t], k & 1);
         else mbar_wait(&pv_done[t], 0);
+#endif
         ATR_END(1);
         tc_fence_after();
       }
