@@ -23,9 +23,15 @@ int attn_delta(const void* dO, int lddo, const void* O, int ldo, float* delta, i
 
 namespace {
 
-constexpr int AB_THREADS = 192;
+// warp 0: TMA producer, warp 1: MMA issuer, then AB_GROUPS softmax warpgroups.  The groups split the 128 keys of a tile
+// (a warp may only touch the TMEM lanes of its quarter, warp % 4, so the split is over columns): with one group the
+// kernel ran one warp per scheduler and exposed every tcgen05.ld / MUFU latency (10 % of the tensor pipe, round 1).
+constexpr int AB_GROUPS = 2;
+constexpr int AB_THREADS = 64 + 128 * AB_GROUPS;
+constexpr int AB_CHUNKS = 4 / AB_GROUPS;   // 32-key chunks of a tile per softmax thread
 constexpr int TILE = 128 * 64 * 2;    // 16 KiB, a [128 x 64] bf16 tile
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr uint32_t kHi = smem_desc_hi_sw128(1024);
 
 struct BwdParams {
   int NQ, H;
@@ -43,72 +49,96 @@ struct BwdParams {
   int dq_first;              // blockIdx.x order: 1 = dq tiles, then dkv source 0, then source 1; 0 = dkv tiles first
 };
 
-// One thread = one query row of the current [128 q x 128 k] tile pair (S and dP in TMEM).  Computes P and dS for
-// 32 keys at a time and stores them as bf16 into the 128B-swizzled [q][k] shared-memory tiles.
-__device__ __forceinline__ void softmax_bwd_row(uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_addr, int row,
-                                                bool row_ok, int valid_keys, float lse_l2, float delta, float scale,
+// One thread = one query row and AB_CHUNKS 32-key chunks (from chunk c0) of the current [128 q x 128 k] tile pair (S and dP
+// in TMEM).  Computes P and dS and stores them as bf16 into the 128B-swizzled [q][k] shared-memory tiles.  Arithmetic
+// in f32x2 pairs; FULL = every row and key of the tile is valid; `reuse_bar` (if any) is waited on just before the first
+// store: the previous tile's P / dS are still being read by its dV / dK (dQ) products while this tile's values are formed.
+//   p  = exp2(s * scale_log2 - lse_l2) [* f]          f = dropout keep factor (0 or 1/(1-p)) of the forward
+//   dS = p0 * (dP * f - delta) * scale                 p0 = the undropped probability
+template <bool FULL, bool DROP, bool WANT_P>
+__device__ __forceinline__ void softmax_bwd_row(uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_addr, int row, int c0,
+                                                bool row_ok, int valid_keys, float nlse_l2, float ndelta_s, float scale,
                                                 float scale_log2, uint8_t* sP, uint8_t* sdS, const DropKey& dk,
-                                                uint32_t row_key, uint32_t pair0) {
-  // With dropout (keep factor f = 0 or 1/(1-p) per score): O = (P.f) V, so dV takes P.f, and dP = (dO V^T).f
-  const bool drop = dk.thr != 0;
+                                                uint32_t row_key, uint32_t pair0, uint64_t* reuse_bar, uint32_t reuse_parity) {
+  const float fs = DROP ? dk.inv_keep * scale : scale;
+  const uint32_t thr16 = dk.thr << 16;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int cc = 0; cc < AB_CHUNKS; ++cc) {
+    const int c = c0 + cc;
     uint32_t rs[32], rd[32];
     tmem_ld_32x32(tmem_s + lane_addr + c * 32, rs);
     tmem_ld_32x32(tmem_dp + lane_addr + c * 32, rd);
     tmem_ld_wait();
-    float p[32], ds[32], f[32];
-    if (drop) {
+    uint32_t pk[16], dsk[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) drop_pair(dk, row_key, pair0 + uint32_t(c * 16 + (i >> 1)), f[i], f[i + 1]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = 1.f;
+    for (int i = 0; i < 16; ++i) {
+      const float2 x = __ffma2_rn(make_float2(__uint_as_float(rs[2 * i]), __uint_as_float(rs[2 * i + 1])), splat2(scale_log2),
+                                  splat2(nlse_l2));
+      float2 pv = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+      if (!FULL) {
+        pv.x = (row_ok && c * 32 + 2 * i < valid_keys) ? pv.x : 0.f;
+        pv.y = (row_ok && c * 32 + 2 * i + 1 < valid_keys) ? pv.y : 0.f;
+      }
+      float2 dp = make_float2(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
+      float2 pf = pv;
+      if (DROP) {      // the two 16-bit halves of one hash decide elements 2 * pair and 2 * pair + 1 (drop_pair)
+        const uint32_t h = mix32(row_key + (pair0 + uint32_t(c * 16 + i)) * 0x9E3779B9u);
+        const bool k0 = (h << 16) >= thr16, k1 = h >= thr16;
+        dp.x = k0 ? dp.x : 0.f;
+        dp.y = k1 ? dp.y : 0.f;
+        if (WANT_P) {
+          pf = __fmul2_rn(pv, splat2(dk.inv_keep));
+          pf.x = k0 ? pf.x : 0.f;
+          pf.y = k1 ? pf.y : 0.f;
+        }
+      }
+      const float2 ds = __fmul2_rn(pv, __ffma2_rn(dp, splat2(fs), splat2(ndelta_s)));
+      if (WANT_P) pk[i] = pack_bf16x2(pf.x, pf.y);
+      dsk[i] = pack_bf16x2(ds.x, ds.y);
     }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const bool ok = row_ok && (c * 32 + i < valid_keys);
-      const float pv = ok ? ex2_approx(fmaf(__uint_as_float(rs[i]), scale_log2, -lse_l2)) : 0.f;
-      p[i] = pv * f[i];
-      ds[i] = ok ? pv * (__uint_as_float(rd[i]) * f[i] - delta) * scale : 0.f;
-    }
-    const int off = (c >> 1) * (2 * TILE) / 2 + row * 128;     // half (64 keys) = one 16 KiB swizzle-atom column
+    if (cc == 0 && reuse_bar != nullptr) mbar_wait(reuse_bar, reuse_parity);
+    const int off = (c >> 1) * TILE + row * 128;     // half (64 keys) = one 16 KiB swizzle-atom column
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int chunk = (c & 1) * 4 + g;
       const int sw = (chunk ^ (row & 7)) << 4;
-      if (sP != nullptr) {
-        uint4 u;
-        u.x = pack_bf16x2(p[8 * g + 0], p[8 * g + 1]); u.y = pack_bf16x2(p[8 * g + 2], p[8 * g + 3]);
-        u.z = pack_bf16x2(p[8 * g + 4], p[8 * g + 5]); u.w = pack_bf16x2(p[8 * g + 6], p[8 * g + 7]);
-        *reinterpret_cast<uint4*>(sP + off + sw) = u;
-      }
-      uint4 w;
-      w.x = pack_bf16x2(ds[8 * g + 0], ds[8 * g + 1]); w.y = pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]);
-      w.z = pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]); w.w = pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]);
-      *reinterpret_cast<uint4*>(sdS + off + sw) = w;
+      if (WANT_P) *reinterpret_cast<uint4*>(sP + off + sw) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      *reinterpret_cast<uint4*>(sdS + off + sw) = make_uint4(dsk[4 * g], dsk[4 * g + 1], dsk[4 * g + 2], dsk[4 * g + 3]);
     }
   }
 }
 
-// store a [128 rows x 64] fp32 TMEM tile (lanes = rows) as bf16 into global memory
-__device__ __forceinline__ void store_tmem_rows(uint32_t tmem_addr, uint32_t lane_addr, __nv_bfloat16* dst, bool ok) {
+template <bool WANT_P>
+__device__ __forceinline__ void softmax_bwd_dispatch(bool full, uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_addr, int row,
+                                                     int c0, bool row_ok, int valid_keys, float nlse_l2, float ndelta_s,
+                                                     float scale, float scale_log2, uint8_t* sP, uint8_t* sdS,
+                                                     const DropKey& dk, uint32_t row_key, uint32_t pair0, uint64_t* reuse_bar,
+                                                     uint32_t reuse_parity) {
+#define MEBT_SM_ARGS tmem_s, tmem_dp, lane_addr, row, c0, row_ok, valid_keys, nlse_l2, ndelta_s, scale, scale_log2, sP, sdS, \
+                     dk, row_key, pair0, reuse_bar, reuse_parity
+  if (dk.thr != 0) {
+    if (full) softmax_bwd_row<true, true, WANT_P>(MEBT_SM_ARGS); else softmax_bwd_row<false, true, WANT_P>(MEBT_SM_ARGS);
+  } else {
+    if (full) softmax_bwd_row<true, false, WANT_P>(MEBT_SM_ARGS); else softmax_bwd_row<false, false, WANT_P>(MEBT_SM_ARGS);
+  }
+#undef MEBT_SM_ARGS
+}
+
+// store 32 columns (from column c * 32) of a [128 rows x 64] fp32 TMEM tile (lanes = rows) as bf16 into global memory
+__device__ __forceinline__ void store_tmem_chunk(uint32_t tmem_addr, uint32_t lane_addr, int c, __nv_bfloat16* dst, bool ok) {
+  uint32_t r[32];
+  tmem_ld_32x32(tmem_addr + lane_addr + c * 32, r);
+  tmem_ld_wait();
+  if (ok) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(tmem_addr + lane_addr + c * 32, r);
-    tmem_ld_wait();
-    if (ok) {
-      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
-        u.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
-        u.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-        u.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-        d4[g] = u;
-      }
+    for (int g = 0; g < 4; ++g) {
+      uint4 u;
+      u.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
+      u.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+      u.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+      u.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+      d4[g] = u;
     }
   }
 }
@@ -139,7 +169,7 @@ __device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorM
     prefetch_tensormap(&tm_q); prefetch_tensormap(&tm_do); prefetch_tensormap(&tm_kv);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-    mbar_init(sp_full, 1); mbar_init(pds_full, 128); mbar_init(dkv_done, 1);
+    mbar_init(sp_full, 1); mbar_init(pds_full, 128 * AB_GROUPS); mbar_init(dkv_done, 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
@@ -173,14 +203,10 @@ __device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorM
       const uint32_t sP = smem_u32(smem + DKV_SMEM_P), sdS = smem_u32(smem + DKV_SMEM_DS);
       auto issue_s_dp = [&](int i) {
         const uint32_t sQ = smem_u32(smem + DKV_SMEM_Q + (i & 1) * TILE), sdO = smem_u32(smem + DKV_SMEM_DO + (i & 1) * TILE);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_s, make_smem_desc_sw128(sQ + k * 32, 16, 1024), make_smem_desc_sw128(sK + k * 32, 16, 1024),
-                       idesc_qk, k != 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_dp, make_smem_desc_sw128(sdO + k * 32, 16, 1024), make_smem_desc_sw128(sV + k * 32, 16, 1024),
-                       idesc_qk, k != 0);
+        // four instructions per asm block over split descriptor words (tools/mma_probe.cu: 48-64 clk per instruction
+        // against ~97 when each rebuilds its descriptors)
+        umma_bf16_ss_x4<false>(tmem_s, smem_desc_lo(sQ, 16), smem_desc_lo(sK, 16), 2, 2, kHi, kHi, idesc_qk, 0u);
+        umma_bf16_ss_x4<false>(tmem_dp, smem_desc_lo(sdO, 16), smem_desc_lo(sV, 16), 2, 2, kHi, kHi, idesc_qk, 0u);
         umma_commit(sp_full);
       };
       mbar_wait(kv_full, 0);
@@ -193,39 +219,42 @@ __device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorM
         tc_fence_after();
         if (i + 1 < nq) issue_s_dp(i + 1);
         const uint32_t sQ = smem_u32(smem + DKV_SMEM_Q + (i & 1) * TILE), sdO = smem_u32(smem + DKV_SMEM_DO + (i & 1) * TILE);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {     // reduction over the 128 queries of this tile, 16 at a time
-          // A: [q rows][k cols] tile read as MN-major (M = keys): two 64-key atoms 16 KiB apart, 8 q-rows per 1 KiB
-          const uint64_t a_p = make_smem_desc_sw128(sP + kk * 2048, TILE, 1024);
-          const uint64_t a_ds = make_smem_desc_sw128(sdS + kk * 2048, TILE, 1024);
-          const uint64_t b_do = make_smem_desc_sw128(sdO + kk * 2048, TILE, 1024);
-          const uint64_t b_q = make_smem_desc_sw128(sQ + kk * 2048, TILE, 1024);
-          umma_bf16_ss(tmem_dv, a_p, b_do, idesc_t, (i | kk) != 0);
-          umma_bf16_ss(tmem_dk, a_ds, b_q, idesc_t, (i | kk) != 0);
+        // reduction over the 128 queries of this tile, 16 (= 2048 B of every operand) at a time.  A: the [q rows][k cols]
+        // tile read as MN-major (M = keys): two 64-key atoms 16 KiB apart, 8 q-rows per 1 KiB
+        {
+          const uint32_t st = 2048u >> 4;
+          const uint32_t p_lo = smem_desc_lo(sP, TILE), ds_lo = smem_desc_lo(sdS, TILE);
+          const uint32_t do_lo = smem_desc_lo(sdO, TILE), q_lo = smem_desc_lo(sQ, TILE);
+          umma_bf16_ss_x4<false>(tmem_dv, p_lo, do_lo, st, st, kHi, kHi, idesc_t, i != 0 ? 1u : 0u);
+          umma_bf16_ss_x4<false>(tmem_dv, p_lo + 4 * st, do_lo + 4 * st, st, st, kHi, kHi, idesc_t, 1u);
+          umma_bf16_ss_x4<false>(tmem_dk, ds_lo, q_lo, st, st, kHi, kHi, idesc_t, i != 0 ? 1u : 0u);
+          umma_bf16_ss_x4<false>(tmem_dk, ds_lo + 4 * st, q_lo + 4 * st, st, st, kHi, kHi, idesc_t, 1u);
         }
         umma_commit(&q_empty[i & 1]);
         umma_commit(dkv_done);
       }
     }
   } else {
-    const int q4 = warp & 3;
+    const int q4 = warp & 3, grp = (warp - 2) >> 2;
     const int row = q4 * 32 + lane;
     const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
     for (int i = 0; i < nq; ++i) {
       const int qrow = i * 128 + row;
       const bool row_ok = qrow < p.NQ;
-      float lse_l2 = 0.f, delta = 0.f;
+      float nlse_l2 = 0.f, ndelta_s = 0.f;
       if (row_ok) {
         const size_t o = (size_t(b) * p.H + h) * p.NQ + qrow;
-        lse_l2 = p.lse[o] * LOG2E;
-        delta = p.delta[o];
+        nlse_l2 = -p.lse[o] * LOG2E;
+        ndelta_s = -p.delta[o] * p.scale;
       }
       mbar_wait(sp_full, i & 1);
       tc_fence_after();
-      if (i > 0) mbar_wait(dkv_done, (i - 1) & 1);    // the previous tile's P / dS are no longer being read
-      softmax_bwd_row(tmem_s, tmem_dp, lane_addr, row, row_ok, valid_keys, lse_l2, delta, p.scale, p.scale_log2,
-                      smem + DKV_SMEM_P, smem + DKV_SMEM_DS, p.drop,
-                      drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qrow)), (uint32_t(src) << 19) | uint32_t(jt * 64));
+      // the previous tile's P / dS must no longer be read when this tile's are stored (waited on inside, before the stores)
+      softmax_bwd_dispatch<true>(valid_keys == 128 && (i + 1) * 128 <= p.NQ, tmem_s, tmem_dp, lane_addr, row,
+                                 grp * AB_CHUNKS, row_ok, valid_keys, nlse_l2, ndelta_s, p.scale, p.scale_log2,
+                                 smem + DKV_SMEM_P, smem + DKV_SMEM_DS, p.drop,
+                                 drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qrow)),
+                                 (uint32_t(src) << 19) | uint32_t(jt * 64), i > 0 ? dkv_done : nullptr, (i - 1) & 1);
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(pds_full);
@@ -234,8 +263,12 @@ __device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorM
     tc_fence_after();
     const bool ok = row < valid_keys;            // TMEM lanes are key rows here
     __nv_bfloat16* base = p.dKV[src] + (size_t(b) * NK + jt * 128 + row) * p.lddkv[src] + h * 64;
-    store_tmem_rows(tmem_dv, lane_addr, base + p.dv_col0[src], ok);
-    store_tmem_rows(tmem_dk, lane_addr, base + p.dk_col0[src], ok);
+    // the four 32-column chunks of [dV | dK] are split over the groups
+    for (int cc = 0; cc < AB_CHUNKS; ++cc) {
+      const int c = grp * AB_CHUNKS + cc;
+      if (c < 2) store_tmem_chunk(tmem_dv, lane_addr, c, base + p.dv_col0[src], ok);
+      else store_tmem_chunk(tmem_dk, lane_addr, c - 2, base + p.dk_col0[src], ok);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -268,7 +301,7 @@ __device__ __forceinline__ void attn_bwd_dq_body(uint8_t* smem, const CUtensorMa
     prefetch_tensormap(&tm_q); prefetch_tensormap(&tm_do); prefetch_tensormap(&tm_kv1); prefetch_tensormap(&tm_kv2);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(sp_full, 1); mbar_init(ds_full, 128); mbar_init(dq_done, 1);
+    mbar_init(sp_full, 1); mbar_init(ds_full, 128 * AB_GROUPS); mbar_init(dq_done, 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
@@ -307,14 +340,8 @@ __device__ __forceinline__ void attn_bwd_dq_body(uint8_t* smem, const CUtensorMa
       const uint32_t sQ = smem_u32(smem + DQ_SMEM_Q), sdO = smem_u32(smem + DQ_SMEM_DO), sdS = smem_u32(smem + DQ_SMEM_DS);
       auto issue_s_dp = [&](int j) {
         const uint32_t sK = smem_u32(smem + DQ_SMEM_K + (j & 1) * TILE), sV = smem_u32(smem + DQ_SMEM_V + (j & 1) * TILE);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_s, make_smem_desc_sw128(sQ + k * 32, 16, 1024), make_smem_desc_sw128(sK + k * 32, 16, 1024),
-                       idesc_qk, k != 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_dp, make_smem_desc_sw128(sdO + k * 32, 16, 1024), make_smem_desc_sw128(sV + k * 32, 16, 1024),
-                       idesc_qk, k != 0);
+        umma_bf16_ss_x4<false>(tmem_s, smem_desc_lo(sQ, 16), smem_desc_lo(sK, 16), 2, 2, kHi, kHi, idesc_qk, 0u);
+        umma_bf16_ss_x4<false>(tmem_dp, smem_desc_lo(sdO, 16), smem_desc_lo(sV, 16), 2, 2, kHi, kHi, idesc_qk, 0u);
         umma_commit(sp_full);
       };
       mbar_wait(q_full, 0);
@@ -327,46 +354,51 @@ __device__ __forceinline__ void attn_bwd_dq_body(uint8_t* smem, const CUtensorMa
         tc_fence_after();
         if (j + 1 < nt) issue_s_dp(j + 1);
         const uint32_t sK = smem_u32(smem + DQ_SMEM_K + (j & 1) * TILE);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(sdS + (kk >> 2) * TILE + (kk & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sK + kk * 2048, TILE, 1024);
-          umma_bf16_ss(tmem_dq, da, db, idesc_dq, (j | kk) != 0);
-        }
+        // dQ += dS K over the 128 keys of the tile: dS K-major (two 64-key halves 16 KiB apart), K MN-major
+        umma_bf16_ss_x4<false>(tmem_dq, smem_desc_lo(sdS, 16), smem_desc_lo(sK, TILE), 2, 2048u >> 4, kHi, kHi, idesc_dq,
+                               j != 0 ? 1u : 0u);
+        umma_bf16_ss_x4<false>(tmem_dq, smem_desc_lo(sdS + TILE, 16), smem_desc_lo(sK, TILE) + 4 * (2048u >> 4), 2, 2048u >> 4,
+                               kHi, kHi, idesc_dq, 1u);
         umma_commit(&kv_empty[j & 1]);
         umma_commit(dq_done);
       }
     }
   } else {
-    const int q4 = warp & 3;
+    const int q4 = warp & 3, grp = (warp - 2) >> 2;
     const int row = q4 * 32 + lane;
     const uint32_t lane_addr = uint32_t(q4 * 32) << 16;
     const int qrow = qt * 128 + row;
     const bool row_ok = qrow < p.NQ;
-    float lse_l2 = 0.f, delta = 0.f;
+    float nlse_l2 = 0.f, ndelta_s = 0.f;
     if (row_ok) {
       const size_t o = (size_t(b) * p.H + h) * p.NQ + qrow;
-      lse_l2 = p.lse[o] * LOG2E;
-      delta = p.delta[o];
+      nlse_l2 = -p.lse[o] * LOG2E;
+      ndelta_s = -p.delta[o] * p.scale;
     }
+    const uint32_t row_key = drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qrow));
     for (int j = 0; j < nt; ++j) {
       const int valid = j < tiles1 ? min(128, NK1 - j * 128) : min(128, NK2 - (j - tiles1) * 128);
       mbar_wait(sp_full, j & 1);
       tc_fence_after();
-      if (j > 0) mbar_wait(dq_done, (j - 1) & 1);
-      softmax_bwd_row(tmem_s, tmem_dp, lane_addr, row, row_ok, valid, lse_l2, delta, p.scale, p.scale_log2, nullptr,
-                      smem + DQ_SMEM_DS, p.drop, drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qrow)),
-                      j < tiles1 ? uint32_t(j * 64) : (1u << 19) | uint32_t((j - tiles1) * 64));
+      softmax_bwd_dispatch<false>(valid == 128 && (qt + 1) * 128 <= p.NQ, tmem_s, tmem_dp, lane_addr, row, grp * AB_CHUNKS,
+                                  row_ok, valid, nlse_l2, ndelta_s, p.scale, p.scale_log2, nullptr, smem + DQ_SMEM_DS, p.drop,
+                                  row_key, j < tiles1 ? uint32_t(j * 64) : (1u << 19) | uint32_t((j - tiles1) * 64),
+                                  j > 0 ? dq_done : nullptr, (j - 1) & 1);
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(ds_full);
     }
     __nv_bfloat16* dst = p.dQ + (size_t(b) * p.NQ + qrow) * p.lddq + p.dq_col0 + h * 64;
+    // the two 32-column chunks of dQ go to the first two of (up to four) groups' chunk slots
+    constexpr int DQ_PER_GROUP = AB_GROUPS == 1 ? 2 : 1;
     if (nt > 0) {
       mbar_wait(dq_done, (nt - 1) & 1);
       tc_fence_after();
-      store_tmem_rows(tmem_dq, lane_addr, dst, row_ok);
-    } else if (row_ok) {
+      for (int cc = 0; cc < DQ_PER_GROUP; ++cc) {
+        const int c = grp * DQ_PER_GROUP + cc;
+        if (c < 2) store_tmem_chunk(tmem_dq, lane_addr, c, dst, row_ok);
+      }
+    } else if (row_ok && grp == 0) {
       uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
       for (int g = 0; g < 8; ++g) d4[g] = make_uint4(0, 0, 0, 0);

@@ -30,6 +30,8 @@ def main():
     head = r(16384, 1024)
     for _ in range(1):
         logits = ops.gemm(a, head, out_dtype=torch.float32)                  # head GEMM, fp32 logits
+    # K6 fused into the head GEMM (Gumbel-max epilogue, no logits written)
+    ops.head_sample(a, head, 1.0, seed=1, offset=1)
     # K6 sampling (fast mode) and K5 masked CE over the materialised logits
     for _ in range(1):
         ops.sample_logits(logits, 1.0, None, None, noise=None, seed=1, offset=1)
@@ -65,6 +67,9 @@ def main():
     for _ in range(1):
         ops.attention(q, 0, kv3, 0, D, 8192, None, 0, 0, 0, Bq, H, 256)
         ops.attention(qkv3, 0, qkv3, D, 2 * D, 256, kv3, 0, D, 8192, Bq, H, 256)
+    # split-KV form (batch 2 at 8192 keys: 32 work items split 4 ways + the merge kernel)
+    q2b, kv2b = r(2 * 256, D), r(2 * 8192, 2 * D)
+    ops.attention(q2b, 0, kv2b, 0, D, 8192, None, 0, 0, 0, 2, H, 256)
     # training-step kernels at the 16-frame shapes (B = 6: 1536 latent rows, 3072 token rows)
     rows = 3072
     xs2, dy2 = r(rows, 1024), r(rows, 1024)
