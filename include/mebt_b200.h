@@ -421,6 +421,34 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
                                 void* d_ctx, void* d_tgt, int layer_begin, int layer_end, int grad_accumulate,
                                 const mebt_dropout_t* drop, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward with the optimizer step of the blocks' Linear weights FUSED into their weight-gradient GEMMs (single GPU, no
+ * gradient accumulation): the epilogue of the grouped weight-gradient kernel applies torch's fused-AdamW arithmetic
+ * (mebt_adamw_flat) to its fp32 accumulator tile - reads p / m / v, writes p / m / v and the bf16 operand copy - so the
+ * gradients of those weights are never written and the optimizer's HBM traffic runs under the tensor work.  What the
+ * reference does as loss.backward() followed by optimizer.step() (mebt/transformer.py:665-681, :749-798) for these tensors.
+ * grad_base: the flat gradient buffer the dW pointers of mebt_layer_grads_t point into; p, m, v, p_bf16: flat buffers of the
+ * same layout.  decay_blocks / block_shift: as mebt_adamw_flat.  step >= 1 is the step being taken.  Afterwards
+ * mebt_adamw_flat must still run over every other parameter: its decay_blocks table takes bit 1 (value 2) = "skip,
+ * already updated".  fuse == NULL: identical to mebt_stack_backward_dropout. */
+typedef struct {
+  const float* grad_base;
+  float* p;
+  float* m;
+  float* v;
+  void* p_bf16;
+  const unsigned char* decay_blocks;
+  int block_shift;
+  float lr, beta1, beta2, eps, weight_decay;
+  int step;
+} mebt_fused_adamw_t;
+int mebt_stack_backward_fused(const mebt_layer_t* layers, const mebt_layer_grads_t* grads, int n_layers,
+                              const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const void* w_head, float* d_w_head,
+                              int B, int L, int NC, int NT, int D, int H, int V, const void* lat0, const void* ctx,
+                              const void* tgt0, const void* dlogits, void* saved, size_t saved_bytes, void* d_lat,
+                              void* d_ctx, void* d_tgt, int layer_begin, int layer_end, int grad_accumulate,
+                              const mebt_dropout_t* drop, const mebt_fused_adamw_t* fuse, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

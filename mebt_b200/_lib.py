@@ -113,6 +113,15 @@ _SIGNATURES["mebt_stack_forward_train_dropout"] = _SIGNATURES["mebt_stack_forwar
     ctypes.POINTER(DropoutStruct), c_void_p]
 _SIGNATURES["mebt_stack_backward_dropout"] = _SIGNATURES["mebt_stack_backward"][:-3] + [
     ctypes.POINTER(DropoutStruct), c_void_p, c_size_t, c_void_p]
+class FusedAdamwStruct(ctypes.Structure):
+    """mebt_fused_adamw_t"""
+    _fields_ = [("grad_base", c_void_p), ("p", c_void_p), ("m", c_void_p), ("v", c_void_p), ("p_bf16", c_void_p),
+                ("decay_blocks", c_void_p), ("block_shift", c_int), ("lr", c_float), ("beta1", c_float), ("beta2", c_float),
+                ("eps", c_float), ("weight_decay", c_float), ("step", c_int)]
+
+
+_SIGNATURES["mebt_stack_backward_fused"] = _SIGNATURES["mebt_stack_backward"][:-3] + [
+    ctypes.POINTER(DropoutStruct), ctypes.POINTER(FusedAdamwStruct), c_void_p, c_size_t, c_void_p]
 _SIGNATURES["mebt_split_f32_bf16x3"] = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
 _SIGNATURES["mebt_latent_attention_fwd_f32"] = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                                 c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,

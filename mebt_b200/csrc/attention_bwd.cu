@@ -15,6 +15,8 @@
 // used to be separate launches (dq, dkv of source 1, dkv of source 2): at the training shapes each was less than two
 // waves of short CTAs, so three launch boundaries cost more than the work; now the heavier kind is scheduled first
 // and the lighter one fills the tail.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mebt {
@@ -23,12 +25,10 @@ int attn_delta(const void* dO, int lddo, const void* O, int ldo, float* delta, i
 
 namespace {
 
-// warp 0: TMA producer, warp 1: MMA issuer, then AB_GROUPS softmax warpgroups.  The groups split the 128 keys of a tile
+// warp 0: TMA producer, warp 1: MMA issuer, then NG softmax warpgroups.  The groups split the 128 keys of a tile
 // (a warp may only touch the TMEM lanes of its quarter, warp % 4, so the split is over columns): with one group the
 // kernel ran one warp per scheduler and exposed every tcgen05.ld / MUFU latency (10 % of the tensor pipe, round 1).
-constexpr int AB_GROUPS = 2;
-constexpr int AB_THREADS = 64 + 128 * AB_GROUPS;
-constexpr int AB_CHUNKS = 4 / AB_GROUPS;   // 32-key chunks of a tile per softmax thread
+// NG (template parameter of everything below) = number of groups: 2 (320 threads, 64 keys per thread) or 4 (576 threads).
 constexpr int TILE = 128 * 64 * 2;    // 16 KiB, a [128 x 64] bf16 tile
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr uint32_t kHi = smem_desc_hi_sw128(1024);
@@ -49,13 +49,13 @@ struct BwdParams {
   int dq_first;              // blockIdx.x order: 1 = dq tiles, then dkv source 0, then source 1; 0 = dkv tiles first
 };
 
-// One thread = one query row and AB_CHUNKS 32-key chunks (from chunk c0) of the current [128 q x 128 k] tile pair (S and dP
+// One thread = one query row and 4 / NG 32-key chunks (from chunk c0) of the current [128 q x 128 k] tile pair (S and dP
 // in TMEM).  Computes P and dS and stores them as bf16 into the 128B-swizzled [q][k] shared-memory tiles.  Arithmetic
 // in f32x2 pairs; FULL = every row and key of the tile is valid; `reuse_bar` (if any) is waited on just before the first
 // store: the previous tile's P / dS are still being read by its dV / dK (dQ) products while this tile's values are formed.
 //   p  = exp2(s * scale_log2 - lse_l2) [* f]          f = dropout keep factor (0 or 1/(1-p)) of the forward
 //   dS = p0 * (dP * f - delta) * scale                 p0 = the undropped probability
-template <bool FULL, bool DROP, bool WANT_P>
+template <int NG, bool FULL, bool DROP, bool WANT_P>
 __device__ __forceinline__ void softmax_bwd_row(uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_addr, int row, int c0,
                                                 bool row_ok, int valid_keys, float nlse_l2, float ndelta_s, float scale,
                                                 float scale_log2, uint8_t* sP, uint8_t* sdS, const DropKey& dk,
@@ -63,7 +63,7 @@ __device__ __forceinline__ void softmax_bwd_row(uint32_t tmem_s, uint32_t tmem_d
   const float fs = DROP ? dk.inv_keep * scale : scale;
   const uint32_t thr16 = dk.thr << 16;
 #pragma unroll 1
-  for (int cc = 0; cc < AB_CHUNKS; ++cc) {
+  for (int cc = 0; cc < 4 / NG; ++cc) {
     const int c = c0 + cc;
     uint32_t rs[32], rd[32];
     tmem_ld_32x32(tmem_s + lane_addr + c * 32, rs);
@@ -108,7 +108,7 @@ __device__ __forceinline__ void softmax_bwd_row(uint32_t tmem_s, uint32_t tmem_d
   }
 }
 
-template <bool WANT_P>
+template <int NG, bool WANT_P>
 __device__ __forceinline__ void softmax_bwd_dispatch(bool full, uint32_t tmem_s, uint32_t tmem_dp, uint32_t lane_addr, int row,
                                                      int c0, bool row_ok, int valid_keys, float nlse_l2, float ndelta_s,
                                                      float scale, float scale_log2, uint8_t* sP, uint8_t* sdS,
@@ -117,9 +117,9 @@ __device__ __forceinline__ void softmax_bwd_dispatch(bool full, uint32_t tmem_s,
 #define MEBT_SM_ARGS tmem_s, tmem_dp, lane_addr, row, c0, row_ok, valid_keys, nlse_l2, ndelta_s, scale, scale_log2, sP, sdS, \
                      dk, row_key, pair0, reuse_bar, reuse_parity
   if (dk.thr != 0) {
-    if (full) softmax_bwd_row<true, true, WANT_P>(MEBT_SM_ARGS); else softmax_bwd_row<false, true, WANT_P>(MEBT_SM_ARGS);
+    if (full) softmax_bwd_row<NG, true, true, WANT_P>(MEBT_SM_ARGS); else softmax_bwd_row<NG, false, true, WANT_P>(MEBT_SM_ARGS);
   } else {
-    if (full) softmax_bwd_row<true, false, WANT_P>(MEBT_SM_ARGS); else softmax_bwd_row<false, false, WANT_P>(MEBT_SM_ARGS);
+    if (full) softmax_bwd_row<NG, true, false, WANT_P>(MEBT_SM_ARGS); else softmax_bwd_row<NG, false, false, WANT_P>(MEBT_SM_ARGS);
   }
 #undef MEBT_SM_ARGS
 }
@@ -149,6 +149,7 @@ __device__ __forceinline__ void store_tmem_chunk(uint32_t tmem_addr, uint32_t la
 constexpr int DKV_SMEM_K = 0, DKV_SMEM_V = TILE, DKV_SMEM_Q = 2 * TILE /* 2 stages */, DKV_SMEM_DO = 4 * TILE /* 2 stages */,
               DKV_SMEM_P = 6 * TILE, DKV_SMEM_DS = 8 * TILE, DKV_SMEM_BAR = 10 * TILE, DKV_SMEM_TOTAL = DKV_SMEM_BAR + 128;
 
+template <int NG>
 __device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorMap& tm_q, const CUtensorMap& tm_do,
                                                   const CUtensorMap& tm_kv, const BwdParams& p, const int src,
                                                   const int jt, const int h, const int b) {
@@ -169,7 +170,7 @@ __device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorM
     prefetch_tensormap(&tm_q); prefetch_tensormap(&tm_do); prefetch_tensormap(&tm_kv);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-    mbar_init(sp_full, 1); mbar_init(pds_full, 128 * AB_GROUPS); mbar_init(dkv_done, 1);
+    mbar_init(sp_full, 1); mbar_init(pds_full, 128 * NG); mbar_init(dkv_done, 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
@@ -250,8 +251,8 @@ __device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorM
       mbar_wait(sp_full, i & 1);
       tc_fence_after();
       // the previous tile's P / dS must no longer be read when this tile's are stored (waited on inside, before the stores)
-      softmax_bwd_dispatch<true>(valid_keys == 128 && (i + 1) * 128 <= p.NQ, tmem_s, tmem_dp, lane_addr, row,
-                                 grp * AB_CHUNKS, row_ok, valid_keys, nlse_l2, ndelta_s, p.scale, p.scale_log2,
+      softmax_bwd_dispatch<NG, true>(valid_keys == 128 && (i + 1) * 128 <= p.NQ, tmem_s, tmem_dp, lane_addr, row,
+                                 grp * (4 / NG), row_ok, valid_keys, nlse_l2, ndelta_s, p.scale, p.scale_log2,
                                  smem + DKV_SMEM_P, smem + DKV_SMEM_DS, p.drop,
                                  drop_row_key(p.drop, uint32_t((b * p.H + h) * p.NQ + qrow)),
                                  (uint32_t(src) << 19) | uint32_t(jt * 64), i > 0 ? dkv_done : nullptr, (i - 1) & 1);
@@ -264,8 +265,8 @@ __device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorM
     const bool ok = row < valid_keys;            // TMEM lanes are key rows here
     __nv_bfloat16* base = p.dKV[src] + (size_t(b) * NK + jt * 128 + row) * p.lddkv[src] + h * 64;
     // the four 32-column chunks of [dV | dK] are split over the groups
-    for (int cc = 0; cc < AB_CHUNKS; ++cc) {
-      const int c = grp * AB_CHUNKS + cc;
+    for (int cc = 0; cc < 4 / NG; ++cc) {
+      const int c = grp * (4 / NG) + cc;
       if (c < 2) store_tmem_chunk(tmem_dv, lane_addr, c, base + p.dv_col0[src], ok);
       else store_tmem_chunk(tmem_dk, lane_addr, c - 2, base + p.dk_col0[src], ok);
     }
@@ -281,6 +282,7 @@ __device__ __forceinline__ void attn_bwd_dkv_body(uint8_t* smem, const CUtensorM
 constexpr int DQ_SMEM_Q = 0, DQ_SMEM_DO = TILE, DQ_SMEM_K = 2 * TILE /* 2 stages */, DQ_SMEM_V = 4 * TILE /* 2 stages */,
               DQ_SMEM_DS = 6 * TILE, DQ_SMEM_BAR = 8 * TILE, DQ_SMEM_TOTAL = DQ_SMEM_BAR + 128;
 
+template <int NG>
 __device__ __forceinline__ void attn_bwd_dq_body(uint8_t* smem, const CUtensorMap& tm_q, const CUtensorMap& tm_do,
                                                  const CUtensorMap& tm_kv1, const CUtensorMap& tm_kv2,
                                                  const BwdParams& p, const int qt, const int h, const int b) {
@@ -301,7 +303,7 @@ __device__ __forceinline__ void attn_bwd_dq_body(uint8_t* smem, const CUtensorMa
     prefetch_tensormap(&tm_q); prefetch_tensormap(&tm_do); prefetch_tensormap(&tm_kv1); prefetch_tensormap(&tm_kv2);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(sp_full, 1); mbar_init(ds_full, 128 * AB_GROUPS); mbar_init(dq_done, 1);
+    mbar_init(sp_full, 1); mbar_init(ds_full, 128 * NG); mbar_init(dq_done, 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
@@ -380,7 +382,7 @@ __device__ __forceinline__ void attn_bwd_dq_body(uint8_t* smem, const CUtensorMa
       const int valid = j < tiles1 ? min(128, NK1 - j * 128) : min(128, NK2 - (j - tiles1) * 128);
       mbar_wait(sp_full, j & 1);
       tc_fence_after();
-      softmax_bwd_dispatch<false>(valid == 128 && (qt + 1) * 128 <= p.NQ, tmem_s, tmem_dp, lane_addr, row, grp * AB_CHUNKS,
+      softmax_bwd_dispatch<NG, false>(valid == 128 && (qt + 1) * 128 <= p.NQ, tmem_s, tmem_dp, lane_addr, row, grp * (4 / NG),
                                   row_ok, valid, nlse_l2, ndelta_s, p.scale, p.scale_log2, nullptr, smem + DQ_SMEM_DS, p.drop,
                                   row_key, j < tiles1 ? uint32_t(j * 64) : (1u << 19) | uint32_t((j - tiles1) * 64),
                                   j > 0 ? dq_done : nullptr, (j - 1) & 1);
@@ -390,7 +392,7 @@ __device__ __forceinline__ void attn_bwd_dq_body(uint8_t* smem, const CUtensorMa
     }
     __nv_bfloat16* dst = p.dQ + (size_t(b) * p.NQ + qrow) * p.lddq + p.dq_col0 + h * 64;
     // the two 32-column chunks of dQ go to the first two of (up to four) groups' chunk slots
-    constexpr int DQ_PER_GROUP = AB_GROUPS == 1 ? 2 : 1;
+    constexpr int DQ_PER_GROUP = NG == 1 ? 2 : 1;
     if (nt > 0) {
       mbar_wait(dq_done, (nt - 1) & 1);
       tc_fence_after();
@@ -412,7 +414,8 @@ __device__ __forceinline__ void attn_bwd_dq_body(uint8_t* smem, const CUtensorMa
 constexpr int AB_SMEM_TOTAL = DKV_SMEM_TOTAL > DQ_SMEM_TOTAL ? DKV_SMEM_TOTAL : DQ_SMEM_TOTAL;
 
 // grid (n_dq + n_dkv0 + n_dkv1, H, B): the kind of a CTA is a function of blockIdx.x alone (block-uniform branch)
-__global__ void __launch_bounds__(AB_THREADS, 1)
+template <int NG>
+__global__ void __launch_bounds__(64 + 128 * NG, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_kv1, const __grid_constant__ CUtensorMap tm_kv2, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -424,11 +427,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (p.dq_first) { is_dq = x < p.n_dq; if (!is_dq) x -= p.n_dq; }
   else { is_dq = x >= n_dkv; if (is_dq) x -= n_dkv; }
   if (is_dq) {
-    attn_bwd_dq_body(smem, tm_q, tm_do, tm_kv1, tm_kv2, p, x, h, b);
+    attn_bwd_dq_body<NG>(smem, tm_q, tm_do, tm_kv1, tm_kv2, p, x, h, b);
   } else if (x < p.n_dkv0) {
-    attn_bwd_dkv_body(smem, tm_q, tm_do, tm_kv1, p, 0, x, h, b);
+    attn_bwd_dkv_body<NG>(smem, tm_q, tm_do, tm_kv1, p, 0, x, h, b);
   } else {
-    attn_bwd_dkv_body(smem, tm_q, tm_do, tm_kv2, p, 1, x - p.n_dkv0, h, b);
+    attn_bwd_dkv_body<NG>(smem, tm_q, tm_do, tm_kv2, p, 1, x - p.n_dkv0, h, b);
   }
 }
 
@@ -466,9 +469,11 @@ int latent_attention_bwd_launch(const void* Q, int ldq, int q_col0, const void* 
   t1 = tq; t2 = tq;
   if (NK1 > 0) { rc = get_tensor_map_2d(&t1, KV1, 2, uint64_t(ld1), uint64_t(B) * NK1, uint64_t(ld1) * 2, 64, 128); if (rc) return rc; }
   if (NK2 > 0) { rc = get_tensor_map_2d(&t2, KV2, 2, uint64_t(ld2), uint64_t(B) * NK2, uint64_t(ld2) * 2, 64, 128); if (rc) return rc; }
+  static const int groups = [] { const char* e = getenv("MEBT_ATTN_BWD_GROUPS"); return e != nullptr && atoi(e) == 4 ? 4 : 2; }();
   static bool attr = false;
   if (!attr) {
-    MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_TOTAL));
+    MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_TOTAL));
+    MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_TOTAL));
     attr = true;
   }
   BwdParams p;
@@ -491,8 +496,9 @@ int latent_attention_bwd_launch(const void* Q, int ldq, int q_col0, const void* 
   const double flops_tile = 2.0 * 128 * 128 * 64;
   {
     LaunchScope ls(FAM_ATTENTION, 7.0 * flops_tile * double(B) * H * nqt * (nkt0 + nkt1), st);
-    MEBT_CUDA_OK(launch_pdl(attn_bwd_kernel, dim3(nqt + nkt0 + nkt1, H, B), dim3(AB_THREADS), AB_SMEM_TOTAL, st, tq, tdo,
-                            t1, t2, p));
+    const dim3 grid(nqt + nkt0 + nkt1, H, B);
+    if (groups == 4) MEBT_CUDA_OK(launch_pdl(attn_bwd_kernel<4>, grid, dim3(64 + 128 * 4), AB_SMEM_TOTAL, st, tq, tdo, t1, t2, p));
+    else MEBT_CUDA_OK(launch_pdl(attn_bwd_kernel<2>, grid, dim3(64 + 128 * 2), AB_SMEM_TOTAL, st, tq, tdo, t1, t2, p));
   }
   MEBT_LAUNCH_OK("attn_bwd_kernel");
   return MEBT_OK;

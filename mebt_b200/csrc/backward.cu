@@ -193,6 +193,94 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const LnDxProblem
   }
 }
 
+// The production width (D = 1024) as its own kernel: the generic one holds xhat, g, the residual and gamma of a row in
+// fp32 (123 registers, two 8-row CTAs per SM -> 3072 rows need a second wave); here a lane owns 4 x 8 consecutive columns,
+// every access is 16 bytes, x and the residual stay packed, gamma is re-read (L1) in the second pass: four rows per
+// 128-thread CTA, five CTAs per SM (740 of the 768 CTAs of 3072 rows resident at once).
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__global__ void __launch_bounds__(128, 5) layernorm_bwd_dx1024_kernel(const LnDxProblem p0, const LnDxProblem p1, int blocks0,
+                                                                      const float* __restrict__ gamma) {
+  constexpr int D = 1024;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool second = int(blockIdx.x) >= blocks0;
+  const LnDxProblem& q = second ? p1 : p0;
+  griddep_wait();
+  const long long row = (long long)(int(blockIdx.x) - (second ? blocks0 : 0)) * 4 + warp;
+  if (row >= q.rows) return;
+  const uint4* x4 = reinterpret_cast<const uint4*>(q.x + row * D);
+  const uint4* dy4 = reinterpret_cast<const uint4*>(q.dy + row * D);
+  const uint4* add4 = q.dy_add != nullptr ? reinterpret_cast<const uint4*>(q.dy_add + row * D) : nullptr;
+  const uint4* res4 = q.resid != nullptr ? reinterpret_cast<const uint4*>(q.resid + row * D) : nullptr;
+  const float4* gm4 = reinterpret_cast<const float4*>(gamma);
+  uint4 xp[4], dp[4], ap[4], rp[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int v = lane + 32 * i;
+    xp[i] = x4[v];
+    dp[i] = dy4[v];
+    if (add4 != nullptr) ap[i] = add4[v];
+    if (res4 != nullptr) rp[i] = res4[v];       // dx = resid + ln'(dy); resid may alias dx
+  }
+  const float mu = q.mean[row], rs = q.rstd[row];
+  float g[4][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int v = lane + 32 * i;
+    float xv[8], dv[8];
+    unpack8(xp[i], xv);
+    unpack8(dp[i], dv);
+    if (add4 != nullptr) {
+      float av[8];
+      unpack8(ap[i], av);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dv[k] += av[k];
+    }
+    const float4 ga = __ldg(gm4 + 2 * v), gb = __ldg(gm4 + 2 * v + 1);
+    const float gmv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      g[i][k] = dv[k] * gmv[k];
+      s1 += g[i][k];
+      s2 = fmaf(g[i][k], (xv[k] - mu) * rs, s2);
+    }
+  }
+  s1 = warp_sum(s1) * (1.0f / D);
+  s2 = warp_sum(s2) * (1.0f / D);
+  const uint32_t rk = drop_row_key(q.drop, uint32_t(row));
+  uint4* dx4 = reinterpret_cast<uint4*>(q.dx + row * D);
+  uint4* dd4 = q.dx_drop != nullptr ? reinterpret_cast<uint4*>(q.dx_drop + row * D) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int v = lane + 32 * i;
+    float xv[8], o[8];
+    unpack8(xp[i], xv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = rs * (g[i][k] - s1 - (xv[k] - mu) * rs * s2);
+    if (res4 != nullptr) {
+      float rv[8];
+      unpack8(rp[i], rv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += rv[k];
+    }
+    const uint4 out = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    dx4[v] = out;
+    if (dd4 != nullptr) {
+      // the standalone kernel masks the bf16-rounded gradient: mask the rounded values so that both forms agree bit for bit
+      float r[8];
+      unpack8(out, r);
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) drop_pair(q.drop, rk, uint32_t(v * 4 + k), f[2 * k], f[2 * k + 1]);
+      dd4[v] = make_uint4(pack_bf16x2(r[0] * f[0], r[1] * f[1]), pack_bf16x2(r[2] * f[2], r[3] * f[3]),
+                          pack_bf16x2(r[4] * f[4], r[5] * f[5]), pack_bf16x2(r[6] * f[6], r[7] * f[7]));
+    }
+  }
+}
+
 // dgamma[c] (+)= sum_r dy[r,c] * xhat[r,c],  dbeta[c] (+)= sum_r dy[r,c].  grid (D / 128, slabs), 256 threads =
 // 32 column-quads x 8 row lanes; partial: [slabs][2][D].
 __global__ void __launch_bounds__(256) layernorm_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
@@ -414,8 +502,14 @@ int layernorm_bwd_dx_multi(const LnDxDesc* d, int n, const float* gamma, int D, 
                                       (p[i].dx_drop != nullptr ? 2.0 : 0.0));
   }
   if (blocks[0] + blocks[1] == 0) return MEBT_OK;
-  const dim3 grid(blocks[0] + blocks[1]);
   LaunchScope ls(FAM_LAYERNORM, bytes, st);
+  if (D == 1024) {
+    const int b0 = (p[0].rows + 3) / 4, b1 = (p[1].rows + 3) / 4;
+    MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx1024_kernel, dim3(b0 + b1), dim3(128), 0, st, p[0], p[1], b0, gamma));
+    MEBT_LAUNCH_OK("layernorm_bwd_dx1024_kernel");
+    return MEBT_OK;
+  }
+  const dim3 grid(blocks[0] + blocks[1]);
   if (D <= 256) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<2>, grid, dim3(256), 0, st, p[0], p[1], blocks[0], gamma, D));
   else if (D <= 512) MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<4>, grid, dim3(256), 0, st, p[0], p[1], blocks[0], gamma, D));
   else MEBT_CUDA_OK(launch_pdl(layernorm_bwd_dx_kernel<8>, grid, dim3(256), 0, st, p[0], p[1], blocks[0], gamma, D));

@@ -310,6 +310,10 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_sr
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// asynchronous request of `bytes` (multiple of 16, 16-byte aligned) of global memory into L2
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -551,6 +555,21 @@ __host__ __device__ __forceinline__ void drop_pair(const DropKey& k, uint32_t ro
   const uint32_t h = mix32(row_key + pair * 0x9E3779B9u);
   f0 = (h & 0xffffu) >= k.thr ? k.inv_keep : 0.f;
   f1 = (h >> 16) >= k.thr ? k.inv_keep : 0.f;
+}
+
+// ---- AdamW element update: torch.optim.AdamW(fused=True) arithmetic (decoupled decay, bias-corrected moments), shared by
+// adamw_flat_kernel and the fused epilogue of the grouped weight-gradient GEMM so that both produce the same bits ----
+struct AdamScalars {
+  float lr, beta1, beta2, eps, wd;
+  float step_size;        // lr / (1 - beta1^step)
+  float inv_bc2_sqrt;     // 1 / sqrt(1 - beta2^step)
+};
+__device__ __forceinline__ void adamw_element(float& p, const float g, float& m, float& v, const float keep, const AdamScalars& a) {
+  p *= keep;
+  m = m + (1.f - a.beta1) * (g - m);
+  v = a.beta2 * v + (1.f - a.beta2) * g * g;
+  const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
+  p -= a.step_size * (m / denom);
 }
 
 // ---- small numeric helpers ----

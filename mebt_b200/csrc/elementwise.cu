@@ -380,26 +380,21 @@ int layernorm(const void* x, int ldx, int in_dtype, const float* gamma, const fl
 __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                          float* __restrict__ v, __nv_bfloat16* __restrict__ p16,
                                                          const unsigned char* __restrict__ decay, int shift, long long n4,
-                                                         float lr, float beta1, float beta2, float eps, float wd,
-                                                         float step_size, float inv_bc2_sqrt) {
+                                                         const AdamScalars a) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned char flag = decay[(i * 4) >> shift];
+    if (flag & 2) continue;                  // updated by the fused weight-gradient epilogue (mebt_stack_backward_fused)
     float4 pv = reinterpret_cast<const float4*>(p)[i];
     const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
     float4 mv = reinterpret_cast<const float4*>(m)[i];
     float4 vv = reinterpret_cast<const float4*>(v)[i];
-    const float keep = decay[(i * 4) >> shift] ? 1.f - lr * wd : 1.f;
+    const float keep = (flag & 1) ? 1.f - a.lr * a.wd : 1.f;
     float* pp = reinterpret_cast<float*>(&pv);
     const float* gg = reinterpret_cast<const float*>(&gv);
     float* mm = reinterpret_cast<float*>(&mv);
     float* vq = reinterpret_cast<float*>(&vv);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      pp[k] *= keep;
-      mm[k] = mm[k] + (1.f - beta1) * (gg[k] - mm[k]);
-      vq[k] = beta2 * vq[k] + (1.f - beta2) * gg[k] * gg[k];
-      const float denom = sqrtf(vq[k]) * inv_bc2_sqrt + eps;
-      pp[k] -= step_size * (mm[k] / denom);
-    }
+    for (int k = 0; k < 4; ++k) adamw_element(pp[k], gg[k], mm[k], vq[k], keep, a);
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(m)[i] = mv;
     reinterpret_cast<float4*>(v)[i] = vv;
@@ -410,19 +405,23 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
   }
 }
 
+AdamScalars make_adam_scalars(float lr, float beta1, float beta2, float eps, float wd, int step) {
+  const double bc1 = 1.0 - pow(double(beta1), double(step));
+  const double bc2 = 1.0 - pow(double(beta2), double(step));
+  return AdamScalars{lr, beta1, beta2, eps, wd, float(double(lr) / bc1), float(1.0 / sqrt(bc2))};
+}
+
 int adamw_flat(float* p, const float* g, float* m, float* v, void* p16, const unsigned char* decay, int shift, long long n,
                float lr, float beta1, float beta2, float eps, float wd, int step, int max_ctas, cudaStream_t st) {
   MEBT_REQUIRE(n >= 0 && n % 4 == 0 && shift >= 2 && step >= 1, MEBT_ERR_SHAPE, "adamw: n %% 4 != 0, shift < 2 or step < 1");
   if (n == 0) return MEBT_OK;
-  const double bc1 = 1.0 - pow(double(beta1), double(step));
-  const double bc2 = 1.0 - pow(double(beta2), double(step));
   {
     LaunchScope ls(FAM_OTHER, double(n) * 30.0, st);
     // max_ctas > 0: a background update - few CTAs trickle through the buffers while latency-bound kernels of another
     // stream (the rest of backward) keep the SMs; the full grid saturates HBM and is for an update nothing overlaps
     const int grid = max_ctas > 0 && max_ctas < 148 * 8 ? max_ctas : 148 * 8;
-    adamw_flat_kernel<<<grid, 256, 0, st>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p16), decay, shift, n / 4, lr, beta1,
-                                               beta2, eps, wd, float(double(lr) / bc1), float(1.0 / sqrt(bc2)));
+    adamw_flat_kernel<<<grid, 256, 0, st>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p16), decay, shift, n / 4,
+                                               make_adam_scalars(lr, beta1, beta2, eps, wd, step));
   }
   MEBT_LAUNCH_OK("adamw_flat_kernel");
   return MEBT_OK;

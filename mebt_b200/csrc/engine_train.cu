@@ -52,6 +52,20 @@ struct WgradDesc {           // csrc/gemm_grouped.cu
   int n_out, k_in, rows, accumulate;
 };
 int gemm_grouped_wgrad(const WgradDesc* d, int n, cudaStream_t stream);
+struct WgradDescEx {         // csrc/gemm_grouped.cu: optional second reduction segment dW (+)= dY^T X + dY2^T X2
+  const void* dY; int ld_dy;
+  const void* X; int ldx;
+  float* dW; int ldw;
+  int n_out, k_in, rows, accumulate;
+  const void* dY2; int ld_dy2;
+  const void* X2; int ldx2;
+  int rows2;
+};
+struct AdamFuseHost {        // csrc/gemm_grouped.cu: the optimizer step in the weight-gradient epilogue
+  const float* grad_base; float* p; float* m; float* v; void* p16; const unsigned char* decay; int shift;
+  float lr, beta1, beta2, eps, wd; int step;
+};
+int gemm_grouped_wgrad_ex(const WgradDescEx* d, int n, const AdamFuseHost* fuse, cudaStream_t stream);
 int layernorm_bwd_params(const void* dy, const void* x, const float* mean, const float* rstd, float* dgamma, float* dbeta,
                          int accumulate_params, int rows, int D, float* workspace, size_t ws_bytes, cudaStream_t st);
 int layernorm_bwd_dx(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
@@ -125,6 +139,7 @@ struct SideStreams {
   // B: the mlp.2 bias gradient).  end_*[block parity]: all of the block's side work is done (it reads the scratch
   // buffers the block after next reuses).  kdgrad_c[parity]: the key-side data gradient (stream C) exists.
   cudaEvent_t fc2_a[OWED_RING] = {}, fc2_b[OWED_RING] = {}, end_a[2] = {}, end_b[2] = {}, end_c[2] = {}, kdgrad_c[2] = {};
+  cudaEvent_t qdgrad[2] = {};           // fused optimizer: the block's last reader of its bf16 weights on the main stream is done
   std::vector<cudaEvent_t> fwd_k;       // forward: block i's key/value projection (stream C) is ready
   bool ok = false;
 };
@@ -140,7 +155,7 @@ SideStreams& side_streams() {
     make(s.fork, 8);
     make(&s.join_a, 1); make(&s.join_b, 1); make(&s.join_c, 1);
     make(s.fc2_a, OWED_RING); make(s.fc2_b, OWED_RING);
-    make(s.end_a, 2); make(s.end_b, 2); make(s.end_c, 2); make(s.kdgrad_c, 2);
+    make(s.end_a, 2); make(s.end_b, 2); make(s.end_c, 2); make(s.kdgrad_c, 2); make(s.qdgrad, 2);
     s.ok = good;
   }
   return s;
@@ -355,7 +370,31 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
                                 const void* tgt0, const void* dlogits, void* saved, size_t saved_bytes, void* d_lat,
                                 void* d_ctx, void* d_tgt, int layer_begin, int layer_end, int grad_accumulate,
                                 const mebt_dropout_t* drop, void* workspace, size_t workspace_bytes, void* stream) {
+  return mebt_stack_backward_fused(layers, grads, n_layers, lnf_w, d_lnf_w, d_lnf_b, w_head, d_w_head, B, L, NC, NT, D, H, V,
+                                   lat0, ctx, tgt0, dlogits, saved, saved_bytes, d_lat, d_ctx, d_tgt, layer_begin, layer_end,
+                                   grad_accumulate, drop, nullptr, workspace, workspace_bytes, stream);
+}
+
+int mebt_stack_backward_fused(const mebt_layer_t* layers, const mebt_layer_grads_t* grads, int n_layers,
+                              const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const void* w_head, float* d_w_head,
+                              int B, int L, int NC, int NT, int D, int H, int V, const void* lat0, const void* ctx,
+                              const void* tgt0, const void* dlogits, void* saved, size_t saved_bytes, void* d_lat,
+                              void* d_ctx, void* d_tgt, int layer_begin, int layer_end, int grad_accumulate,
+                              const mebt_dropout_t* drop, const mebt_fused_adamw_t* fuse, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   using namespace mebt;
+  // The optimizer step of the blocks' Linear weights inside their weight-gradient GEMMs: every block must then produce
+  // each weight's whole gradient in ONE accumulator (no accumulation into earlier gradients, no second launch adding
+  // the key|value rows of lt2l: a two-segment problem instead) and must not overwrite bf16 weights a data-gradient GEMM
+  // of the same block still reads (the grouped launch waits for them).
+  MEBT_REQUIRE(fuse == nullptr || (!grad_accumulate && NC > 0 && fuse->step >= 1 && fuse->grad_base != nullptr &&
+                                   fuse->p != nullptr && fuse->m != nullptr && fuse->v != nullptr && fuse->p_bf16 != nullptr &&
+                                   fuse->decay_blocks != nullptr && D % 256 == 0),
+               MEBT_ERR_UNSUPPORTED, "backward: the fused optimizer step needs NC > 0, D %% 256 == 0, no gradient accumulation and all flat buffers");
+  AdamFuseHost fuse_h;
+  if (fuse != nullptr)
+    fuse_h = AdamFuseHost{fuse->grad_base, fuse->p, fuse->m, fuse->v, fuse->p_bf16, fuse->decay_blocks, fuse->block_shift,
+                          fuse->lr, fuse->beta1, fuse->beta2, fuse->eps, fuse->weight_decay, fuse->step};
   const float attn_p = drop != nullptr ? drop->attn_p : 0.f, resid_p = drop != nullptr ? drop->resid_p : 0.f;
   const unsigned long long seed = drop != nullptr ? drop->seed : 0ull;
   MEBT_REQUIRE(attn_p >= 0.f && attn_p < 1.f && resid_p >= 0.f && resid_p < 1.f, MEBT_ERR_SHAPE, "backward: bad dropout p");
@@ -570,7 +609,9 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
                                       stream));
     // ---- weight gradients of the whole block: one grouped launch on side stream A ----
     const int qw = fused ? 3 * D : D;
-    {
+    WgradDescEx wx[5];
+    int nx = 0;
+    if (fuse == nullptr) {
       WgradDesc wd[5];
       int n = 0;
       wd[n++] = WgradDesc{d_mlp, D, S + s.u, 4 * D, g.w_fc2, 4 * D, D, 4 * D, rq, acc};
@@ -588,6 +629,24 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
         TRY(gemm_grouped_wgrad(&kv, 1, sa));
       }
       MEBT_CUDA_OK(cudaEventRecord(side.fc2_a[ring], sa));
+    } else {
+      // fused optimizer step: launched further down, once the qkv data gradients (the last readers of this block's bf16
+      // weights) are done.  lt2l: the key|value rows take both of their sources as one two-segment reduction.
+      const __nv_bfloat16* dqkv_b = static_cast<const __nv_bfloat16*>(dqkv);
+      wx[nx++] = WgradDescEx{d_mlp, D, S + s.u, 4 * D, g.w_fc2, 4 * D, D, 4 * D, rq, 0, nullptr, 0, nullptr, 0, 0};
+      wx[nx++] = WgradDescEx{da, 4 * D, S + s.h, D, g.w_fc1, D, 4 * D, D, rq, 0, nullptr, 0, nullptr, 0, 0};
+      wx[nx++] = WgradDescEx{d_proj, D, S + s.att, D, g.w_proj, D, D, D, rq, 0, nullptr, 0, nullptr, 0, 0};
+      if (fused && rk > 0) {
+        wx[nx++] = WgradDescEx{dqkv, qw, S + s.qn, D, g.w_qkv, D, D, D, rq, 0, nullptr, 0, nullptr, 0, 0};
+        wx[nx++] = WgradDescEx{dqkv_b + D, qw, S + s.qn, D, g.w_qkv + size_t(D) * D, D, 2 * D, D, rq, 0, dkv, 2 * D, S + s.kn, D, rk};
+      } else {
+        wx[nx++] = WgradDescEx{dqkv, qw, S + s.qn, D, g.w_qkv, D, qw, D, rq, 0, nullptr, 0, nullptr, 0, 0};
+        if (rk > 0) wx[nx++] = WgradDescEx{dkv, 2 * D, S + s.kn, D, g.w_qkv + size_t(D) * D, D, 2 * D, D, rk, 0, nullptr, 0, nullptr, 0, 0};
+      }
+      TRY(FORK());
+      if (rk > 0) MEBT_CUDA_OK(cudaStreamWaitEvent(sc, side.fork[(fork_slot + 7) & 7], 0));   // stream C forks here too
+    }
+    {
       TRY(colsum(dqkv, qw, rq, qw, g.b_qkv, acc, red_b, red_bytes, sb));
       if (rk > 0) {
         TRY(colsum(dkv, 2 * D, rk, 2 * D, g.b_qkv + D, fused ? 1 : acc, red_b, red_bytes, sb));
@@ -610,6 +669,13 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
       MEBT_CUDA_OK(cudaEventRecord(side.end_c[par], sc));
     }
     TRY(DGRAD(dqkv, qw, wqkv, D, dqn, rq, D, qw, dx, nullptr, 0, 0));                                       // dqn = dx + dQKV Wqkv
+    if (fuse != nullptr) {
+      MEBT_CUDA_OK(cudaEventRecord(side.qdgrad[par], st));
+      MEBT_CUDA_OK(cudaStreamWaitEvent(sa, side.qdgrad[par], 0));
+      if (rk > 0) MEBT_CUDA_OK(cudaStreamWaitEvent(sa, side.kdgrad_c[par], 0));
+      TRY(gemm_grouped_wgrad_ex(wx, nx, &fuse_h, sa));
+      MEBT_CUDA_OK(cudaEventRecord(side.fc2_a[ring], sa));
+    }
     // ---- ln1, query side ----  parameter gradients on side stream B (query side, then key side: they add into the
     // same vectors); the dx kernel also writes the masked copy an earlier block's GEMMs will read
     TRY(FORK());

@@ -972,6 +972,9 @@ int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b
       if (N % widths[i] == 0 && int64_t(p.num_m_blocks) * (N / widths[i]) <= sm_count()) { bn = widths[i]; chosen = true; }
     if (!chosen) bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
   }
+  // Tried: 256-wide tiles split three ways along K for the K = 4096 latent MLP GEMMs (1536 x 1024 x 4096: 48 tiles x 3
+  // splits instead of 96 unsplit 128-wide tiles): 27.6 us against 25.1 us - the partial round trip costs more than
+  // the shorter k-loop saves.
   if (flags & MEBT_GEMM_FORCE_BN256) { MEBT_REQUIRE(N % 256 == 0, MEBT_ERR_SHAPE, "BN256 needs N%%256==0"); bn = 256; }
   if (flags & MEBT_GEMM_FORCE_BN128) { MEBT_REQUIRE(N % 128 == 0, MEBT_ERR_SHAPE, "BN128 needs N%%128==0"); bn = 128; }
   if (flags & MEBT_GEMM_FORCE_BN64) bn = 64;

@@ -223,11 +223,14 @@ class TrainState:
             self._grads_dirty = False
         return self._grads_dirty
 
-    def backward(self, dlogits, accumulate=False, world_size=1, optimizer=None, sharded=False):
+    def backward(self, dlogits, accumulate=False, world_size=1, optimizer=None, sharded=False, fuse=None):
         """Stack + stem backward into the flat gradient buffer; with world_size > 1 each finished chunk of blocks is
         all-reduced (averaged) on a side stream while the next chunk runs.  With a `FlatAdamW` passed as `optimizer` the
         parameter update of a finished chunk is issued on that side stream too, right behind its all-reduce: blocks
-        that backward has left are never read again in this step, so their AdamW overlaps the rest of backward."""
+        that backward has left are never read again in this step, so their AdamW overlaps the rest of backward.
+        fuse: a `FlatAdamW` whose step for the blocks' Linear weights runs INSIDE their weight-gradient GEMMs
+        (`mebt_stack_backward_fused`; single GPU, no accumulation, NC > 0); the caller then finishes the step with
+        `fuse.step_rest()`."""
         if not self._pending:
             raise MebtError("backward: no forward is pending (each forward's activations serve exactly one backward)")
         B, NC, NT, x_indices, ctx_idx, tgt_idx, lat, ctx, tgt, drop, embd_p, seed = self._ctx
@@ -245,9 +248,14 @@ class TrainState:
             lo, hi = self.emb_slice
             self.flat_grad[lo:hi].zero_()                       # embedding gradients are scatter-added
         works = []
+        fuse_struct = None
+        if fuse is not None:
+            if accumulate or world_size > 1 or sharded or optimizer is not None or NC == 0:
+                raise MebtError("backward(fuse=...): single GPU, no gradient accumulation, NC > 0 only")
+            fuse_struct = ctypes.byref(fuse.fused_struct())
         for ci in range(len(self.chunks) - 1, -1, -1):
             lb, le = self.chunks[ci]
-            call("mebt_stack_backward_dropout", self.c_layers, self.c_grads, n,
+            call("mebt_stack_backward_fused", self.c_layers, self.c_grads, n,
                  self._view(self.flat, "transformer.ln_f.weight").data_ptr(),
                  self._view(self.flat_grad, "transformer.ln_f.weight").data_ptr(),
                  self._view(self.flat_grad, "transformer.ln_f.bias").data_ptr(),
@@ -255,7 +263,7 @@ class TrainState:
                  self._view(self.flat_grad, "transformer.head.weight").data_ptr(), B, self.L, NC, NT, self.D, self.H, self.V,
                  lat.data_ptr(), ctx.data_ptr(), tgt.data_ptr(), dlogits.data_ptr(), saved.data_ptr(), saved.numel(),
                  d_lat.data_ptr(), d_ctx.data_ptr(), d_tgt.data_ptr(), lb, le, int(accumulate),
-                 ctypes.byref(drop) if drop is not None else None, ws.data_ptr(), ws.numel(), cur.cuda_stream)
+                 ctypes.byref(drop) if drop is not None else None, fuse_struct, ws.data_ptr(), ws.numel(), cur.cuda_stream)
             lo, hi = self.block_slices[lb][0], self.block_slices[le - 1][1]
             if sharded:
                 self._exchange_sharded(optimizer, lo, hi, cur)
@@ -357,7 +365,8 @@ class TrainState:
             # for the collective, so that later work on it (the chunk's AdamW) and `wait_stream` see averaged gradients
             return parallel.allreduce_mean_(self.flat_grad[lo:hi], async_op=False)
 
-    def loss_and_backward(self, x_indices, indices, t=None, world_size=1, defer_backward=False, optimizer=None, sharded=False):
+    def loss_and_backward(self, x_indices, indices, t=None, world_size=1, defer_backward=False, optimizer=None, sharded=False,
+                          fuse=None):
         """shared_step + backward fused: -> dict(loss, acc1, acc5, ratio) as device tensors / floats.
         loss = CE_sum / (B * seq_len * ratio**avg_loss) (mebt/transformer.py:723-730).
         defer_backward=True stops after the loss and returns (dict, dlogits) for a later `backward(dlogits)`
@@ -378,7 +387,10 @@ class TrainState:
         out = dict(loss=stats[0] * scale, acc1=stats[1] * (100.0 / n), acc5=stats[2] * (100.0 / n), ratio=ratio)
         if defer_backward:
             return out, logits                                  # logits now hold d(loss)/d(logits)
-        self.backward(logits, world_size=world_size, optimizer=optimizer, sharded=sharded)
+        if fuse is not None and NC == 0:
+            fuse = None                                          # the key|value weights of latent_enc get no GEMM: plain step
+        self.backward(logits, world_size=world_size, optimizer=optimizer, sharded=sharded, fuse=fuse)
+        out["fused_update"] = fuse is not None
         return out
 
     def make_optimizer(self, lr=1.08e-5, weight_decay=0.01, flat=True):
@@ -392,11 +404,18 @@ class TrainState:
             return torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.95), fused=True)
         return FlatAdamW(self, groups, lr=lr, betas=(0.9, 0.95), weight_decay=weight_decay)
 
-    def train_step(self, optimizer, x_indices, indices, t=None, world_size=1, overlap_update=False, sharded=True):
+    def train_step(self, optimizer, x_indices, indices, t=None, world_size=1, overlap_update=False, sharded=True,
+                   fused_update=False):
         """fwd + loss + bwd (+ all-reduce) + AdamW + operand refresh.  Returns the loss statistics.
         overlap_update=True (FlatAdamW only) issues the update of each finished chunk of blocks on the side stream while
         backward continues; measured on B200 at the 16-frame shapes it gains 0.8 % per step (13.81 -> 13.70 ms) because the
-        HBM-bound update slows the latency-bound backward kernels it overlaps, so it is off by default."""
+        HBM-bound update slows the latency-bound backward kernels it overlaps, so it is off by default.
+        fused_update=True (FlatAdamW, one GPU, no pending accumulated gradient): AdamW of the blocks' Linear weights inside
+        their weight-gradient GEMMs (`mebt_stack_backward_fused`); the gradients of those weights are then not
+        materialised in `p.grad`.  Measured on B200 at the 16-frame shapes it LOSES 1.3 ms per step (11.37 -> 12.66 ms):
+        the epilogue's row-strided 128-byte accesses to p / m / v (one weight row per thread, as the accumulator lies in
+        tensor memory) reach a fraction of the 6.2 TB/s the flat kernel streams at, also with the state prefetched into
+        L2 a tile ahead and with approximate sqrt / division; off by default, kept as a tested option."""
         if isinstance(optimizer, FlatAdamW) and world_size > 1 and sharded:
             # data parallel with the fused optimizer: reduce-scatter -> AdamW on this rank's shard -> bf16 all-gather
             optimizer.begin_step()
@@ -406,6 +425,15 @@ class TrainState:
         if isinstance(optimizer, FlatAdamW) and overlap_update:
             optimizer.begin_step()
             return self.loss_and_backward(x_indices, indices, t, world_size, optimizer=optimizer)
+        if (isinstance(optimizer, FlatAdamW) and fused_update and world_size == 1 and self.D % 256 == 0
+                and not self.grads_pending()):
+            # single GPU: the step of the blocks' Linear weights (302 M of the 337 M parameters of STL-16f) runs in the
+            # epilogue of their weight-gradient GEMMs; one AdamW launch over everything else finishes the step
+            optimizer.begin_step()
+            out = self.loss_and_backward(x_indices, indices, t, world_size, fuse=optimizer)
+            optimizer.step_rest(fused=out.pop("fused_update"))
+            self._grads_dirty = False
+            return out
         out = self.loss_and_backward(x_indices, indices, t, world_size)
         optimizer.step()
         self._grads_dirty = False                               # train_step owns the whole step: the gradient is consumed
@@ -440,6 +468,16 @@ class FlatAdamW:
             o, k = ts.offsets[name]
             flags[o >> shift:(o + k) >> shift] = 1
         self.flags = torch.from_numpy(flags).to(ts.device)
+        # fused mode: bit 1 marks what the weight-gradient epilogues update (the Linear weights of every block that can
+        # reach the logits: blocks behind the last latent_dec get zero gradients through the plain kernel)
+        last = max((i for i, md in enumerate(ts.modes) if md == "latent_dec"), default=-1)
+        fflags = flags.copy()
+        for i in range(last + 1):
+            for suffix in ("attn.query.weight", "attn.key.weight", "attn.value.weight", "attn.proj.weight", "mlp.0.weight",
+                           "mlp.2.weight"):
+                o, k = ts.offsets[f"transformer.blocks.{i}.{suffix}"]
+                fflags[o >> shift:(o + k) >> shift] |= 2
+        self.flags_fused = torch.from_numpy(fflags).to(ts.device)
         if n % 4:
             raise MebtError("FlatAdamW: the flat parameter buffer must hold a multiple of 4 elements")
 
@@ -467,6 +505,28 @@ class FlatAdamW:
     def step(self):
         self.begin_step()
         self.step_range(0, self.ts.flat.numel())
+
+    def fused_struct(self):
+        """mebt_fused_adamw_t of the step opened by `begin_step` (TrainState.backward(fuse=self))."""
+        ts = self.ts
+        self._fused = _lib.FusedAdamwStruct(ts.flat_grad.data_ptr(), ts.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                            ts.flat_bf16.data_ptr(), self.flags.data_ptr(), self.shift,
+                                            float(self.param_groups[0]["lr"]), self.betas[0], self.betas[1], self.eps,
+                                            self.weight_decay, self.steps)
+        return self._fused
+
+    def step_rest(self, fused=True):
+        """Finishes a step whose block Linear weights were updated inside the backward: one launch over the flat buffers
+        that skips them (bit 1 of the flag table).  fused=False: the backward could not fuse (NC = 0): the whole update."""
+        ts = self.ts
+        if not fused:
+            return self.step_range(0, ts.flat.numel())
+        lr = float(self.param_groups[0]["lr"])
+        call("mebt_adamw_flat_bg", ts.flat.data_ptr(), ts.flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+             ts.flat_bf16.data_ptr(), self.flags_fused.data_ptr(), self.shift, ts.flat.numel(), lr, self.betas[0], self.betas[1],
+             self.eps, self.weight_decay, self.steps, 0, torch.cuda.current_stream().cuda_stream)
+        _lib.bump_write_epoch()
+        ts._grads_dirty = False
 
     def state_dict(self):
         return dict(m=self.m, v=self.v, steps=self.steps, lr=[g["lr"] for g in self.param_groups])

@@ -266,3 +266,58 @@ def test_maskgit_block_mode_training_is_refused():
     model = build_model(cfg).train()
     with pytest.raises(NotImplementedError, match="four latent block modes"):
         TrainState(model)
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_fused_wgrad_adamw_matches_backward_then_step(dropout):
+    """train_step(fused_update=True): AdamW of the blocks' Linear weights inside the epilogue of their weight-gradient
+    GEMMs (mebt_stack_backward_fused; lt2l's key|value rows as a two-segment reduction) gives the parameters, moments and
+    bf16 operand copies of backward followed by one whole-buffer step (loss.backward(); optimizer.step() in the
+    reference, mebt/transformer.py:665-681).  D = 256: the narrowest width the grouped kernel tiles."""
+    from mebt_b200.training import TrainState
+    from oracle import mebt_oracle as O
+    cfg = dict(n_embd=256, n_head=4, sos_emb=64, block_size=256, shape=[1, 16, 16], n_layer=6, vocab_size=16384,
+               mode=["latent_enc", "latent_self", "latent_dec", "lt2l", "latent_dec", "latent_self"], avg_loss=1.0,
+               embd_pdrop=dropout, resid_pdrop=dropout, attn_pdrop=dropout)
+    P = O.make_weights(cfg, 3)
+    model = build_model(cfg, P)
+    model.transformer.train()
+    ts = TrainState(model, n_buckets=2)
+    ts.dropout_seed = 11
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, 16384, (3, 256), generator=g).cuda()
+    indices = torch.stack([torch.randperm(256, generator=g) for _ in range(3)]).cuda()
+    start = ts.flat.clone()
+
+    def run(fused, steps):
+        ts.flat.copy_(start)
+        ts.refresh_operands()
+        opt = ts.make_optimizer(lr=1e-3, weight_decay=0.05)
+        losses = [float(ts.train_step(opt, x, indices, t=0.5, fused_update=fused)["loss"]) for _ in range(steps)]
+        assert opt.steps == steps
+        torch.cuda.synchronize()
+        return losses, ts.flat.clone(), opt.m.clone(), opt.v.clone(), ts.flat_bf16.clone()
+
+    # ONE step: weight gradients are leaves of the backward, so both paths see the same accumulators everywhere except
+    # lt2l's key|value rows (block 3: one two-segment reduction instead of two launches added in fp32) and the
+    # atomically accumulated embedding gradients: parameters, moments and operand copies are bit-identical elsewhere
+    l1, p1, m1, v1, b1 = run(True, 1)
+    l0, p0, m0, v0, b0 = run(False, 1)
+    assert l1 == l0
+    lo = ts.emb_slice[0]
+    same = torch.ones(lo, dtype=torch.bool, device=p1.device)
+    for suffix in ("attn.key.weight", "attn.value.weight"):
+        o, k = ts.offsets[f"transformer.blocks.3.{suffix}"]
+        same[o:o + k] = False
+        assert (m1[o:o + k] - m0[o:o + k]).abs().max() <= 1e-4 * m0[o:o + k].abs().max()     # m = 0.1 g after one step
+        assert (p1[o:o + k] - p0[o:o + k]).abs().max() <= 2.1e-3                              # Adam: at most a flipped +-lr
+        assert ((p1[o:o + k] - p0[o:o + k]).abs() > 1e-6).float().mean() < 1e-2
+    for a_, b_ in ((p1, p0), (m1, m0), (v1, v0), (b1, b0)):
+        assert torch.equal(a_[:lo][same], b_[:lo][same]), float((a_[:lo][same].float() - b_[:lo][same].float()).abs().max())
+    # three steps: the trajectories stay together
+    l1, p1, _, _, _ = run(True, 3)
+    l0, p0, _, _, _ = run(False, 3)
+    assert np.allclose(l1, l0, rtol=1e-4), (l1, l0)
+    # the block after the last latent_dec is dead: its weights still decay through the plain kernel
+    o, k = ts.offsets["transformer.blocks.5.mlp.2.weight"]
+    assert not torch.equal(p1[o:o + k], start[o:o + k])
