@@ -421,6 +421,29 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
                                 void* d_ctx, void* d_tgt, int layer_begin, int layer_end, int grad_accumulate,
                                 const mebt_dropout_t* drop, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- VQGAN encoder / decoder convolutions (mebt/vqgan.py:263-405) ------------------------------------
+ * Activations are channels-last bf16 [B, T, H, W, ld] (ld >= C, both multiples of 8).
+ *
+ * mebt_pad_norm_act: y = replicate_pad(act(norm(x))) - F.pad(..., mode='replicate') of SamePadConv3d /
+ * SamePadConvTranspose3d (vqgan.py:381,404) fused with the Normalize + SiLU in front of it (ResBlock.forward :344-349,
+ * Encoder / Decoder.final_block).  pad6 = (t_before, t_after, h_before, h_after, w_before, w_after); norm: 0 none,
+ * 1 GroupNorm(groups, eps) with weight gamma / bias beta, 2 per-channel affine x * gamma + beta (eval-mode BatchNorm folded);
+ * act: 0 none, 1 SiLU.  y has C real channels per position, [C, ldy) zeroed.  workspace: mebt_groupnorm_workspace_bytes.
+ *
+ * mebt_conv3d_ndhwc: implicit-GEMM convolution on the tensor cores over an ALREADY PADDED input,
+ *   y[b, t*ystep+yorigin, ..., co] = bias[co] + resid[b,t,h,w,co] + sum_{taps, c} xp[b, t*step + origin + dt, ..., c] * w[co][(dt,dh,dw)][c]
+ * w: bf16 [cout][taps * ceil64(cin)] (zero padded per tap).  nn.Conv3d: taps = kernel, step = stride.  nn.ConvTranspose3d
+ * (kernel 4, stride 2): one launch per output parity with 2 taps, origin = ystep-origin = parity, ystep = 2 (the caller
+ * packs the matching kernel slices).  odims3 = positions computed per dimension (must tile into 128-position patches). */
+size_t mebt_groupnorm_workspace_bytes(int B, int groups);
+int mebt_pad_norm_act(const void* x, int ldx, void* y, int ldy, int B, int T, int H, int W, int C, const int* pad6, int norm,
+                      int act, int groups, float eps, const float* gamma, const float* beta, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w, int cin, const float* bias,
+                      const void* resid, int ldr, void* y, int ldy, const int* ydims4, int cout, const int* taps3,
+                      const int* step3, const int* origin3, const int* ystep3, const int* yorigin3, const int* odims3,
+                      void* stream);
+
 /* Backward with the optimizer step of the blocks' Linear weights FUSED into their weight-gradient GEMMs (single GPU, no
  * gradient accumulation): the epilogue of the grouped weight-gradient kernel applies torch's fused-AdamW arithmetic
  * (mebt_adamw_flat) to its fp32 accumulator tile - reads p / m / v, writes p / m / v and the bf16 operand copy - so the

@@ -113,6 +113,13 @@ _SIGNATURES["mebt_stack_forward_train_dropout"] = _SIGNATURES["mebt_stack_forwar
     ctypes.POINTER(DropoutStruct), c_void_p]
 _SIGNATURES["mebt_stack_backward_dropout"] = _SIGNATURES["mebt_stack_backward"][:-3] + [
     ctypes.POINTER(DropoutStruct), c_void_p, c_size_t, c_void_p]
+_I3, _I4, _I6 = ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)
+_SIGNATURES["mebt_pad_norm_act"] = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, _I6, c_int, c_int,
+                                    c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+_SIGNATURES["mebt_conv3d_ndhwc"] = [c_void_p, c_int, _I4, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, _I4,
+                                    c_int, _I3, _I3, _I3, _I3, _I3, _I3, c_void_p]
+
+
 class FusedAdamwStruct(ctypes.Structure):
     """mebt_fused_adamw_t"""
     _fields_ = [("grad_base", c_void_p), ("p", c_void_p), ("m", c_void_p), ("v", c_void_p), ("p_bf16", c_void_p),
@@ -170,6 +177,8 @@ for _n, _a in (("mebt_colsum_workspace_bytes", [c_int]), ("mebt_layernorm_bwd_wo
                ("mebt_latent_attention_bwd_workspace_bytes", [c_int, c_int, c_int])):
     getattr(_lib, _n).argtypes = _a
     getattr(_lib, _n).restype = c_size_t
+_lib.mebt_groupnorm_workspace_bytes.argtypes = [c_int, c_int]
+_lib.mebt_groupnorm_workspace_bytes.restype = c_size_t
 _lib.mebt_stack_train_saved_bytes.argtypes = [ctypes.POINTER(LayerStruct), c_int, c_int, c_int, c_int, c_int, c_int, c_int]
 _lib.mebt_stack_train_saved_bytes.restype = c_size_t
 _lib.mebt_stack_backward_workspace_bytes.argtypes = [c_int] * 6

@@ -1,0 +1,503 @@
+// 3-D convolution of the VQGAN encoder / decoder as an implicit GEMM on the tensor cores:
+// replaces nn.Conv3d / nn.ConvTranspose3d behind SamePadConv3d / SamePadConvTranspose3d (mebt/vqgan.py:358-405), the
+// GroupNorm + SiLU that precedes every ResBlock convolution (:255-260, :336-356) and the replicate padding (F.pad, :381,404).
+//
+// Layout: activations channels-last bf16, X[b][t][h][w][c].  A convolution with taps (KT, KH, KW) and strides
+// (ST, SH, SW) over the ALREADY PADDED input is
+//     Y[b,t,h,w,co] = bias[co] + sum_{dt,dh,dw,c} Xp[b, t ST + dt + OT, h SH + dh + OH, w SW + dw + OW, c] * W[co][(dt,dh,dw)][c]
+// = a GEMM with M = output positions, N = Cout, K = taps x Cin whose A operand needs no im2col buffer: one output tile is
+// a patch of PT x PH x PW = 128 positions, and the A tile of (tap, 64-channel block) is ONE 5-D TMA box
+// {64 c, PW, PH, PT, 1} of Xp at the tap's offset (element strides = the convolution strides), landing in shared memory
+// as the 128 x 64 K-major, 128B-swizzled tile tcgen05.mma reads.  B = packed weights [Cout][taps * Cp] (Cp = channels
+// rounded up to 64, zero padded; TMA zero-fills the activations' missing channels).  The transposed convolutions of the
+// decoder run as one such stride-1 convolution per output parity class (2 taps per up-sampled dimension, origin offset
+// = parity), written into the interleaved positions of the up-sampled tensor by the 5-D TMA store (element strides 2).
+//
+// Kernel = csrc/gemm_grouped.cu's structure: 192 threads (TMA producer warp, one MMA-issuing thread, 4 epilogue warps),
+// 3-6 stage operand ring, two TMEM accumulators, epilogue (bias, residual, bf16) through a 4-slot staging ring and TMA store.
+// pad_norm_act_kernel writes Xp: replicate padding fused with GroupNorm(32) / eval BatchNorm + SiLU of the source.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mebt {
+
+int get_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+int get_tensor_map_5d(CUtensorMap* out, const void* ptr, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                      const uint32_t box[5], const uint32_t elem_strides[5]);
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int CV_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int EPI_SLOTS = 4;
+constexpr int EPI_SLOT_BYTES = 128 * 128;
+
+template <int BN>
+struct ConvSmem {
+  static constexpr int STAGES = BN == 256 ? 3 : 6;
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_SLOTS * EPI_SLOT_BYTES;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
+  static constexpr int TOTAL = BIAS_OFFSET + BN * 4 + 1024;
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+struct ConvParams {
+  int PT, PH, PW;             // output patch of one tile (PT * PH * PW = 128)
+  int nt_t, nt_h, nt_w;       // tiles per output dimension
+  int tiles_m, num_n_blocks, total_tiles;
+  int KT, KH, KW;             // taps
+  int ST, SH, SW;             // input step per output position
+  int OT, OH, OW;             // origin offset in the padded input
+  int YT, YH, YW;             // output step per output position in the destination tensor (transposed convolution: 2) ...
+  int Y0T, Y0H, Y0W;          // ... and its origin (the parity)
+  int cblocks;                // Cp / 64
+  int Cout;
+  const float* bias;          // [Cout] or nullptr
+  const __nv_bfloat16* resid; // dense [B, To, Ho, Wo, ldr] or nullptr (added after the bias)
+  long long res_b, res_t, res_h, res_w;   // residual strides in elements
+};
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
+// tile number -> (n block, batch element, patch origin in output positions)
+__device__ __forceinline__ void locate(const ConvParams& p, int work, int& ni, int& b, int& t0, int& h0, int& w0) {
+  ni = work / p.tiles_m;
+  int m = work - ni * p.tiles_m;
+  const int wi = m % p.nt_w; m /= p.nt_w;
+  const int hi = m % p.nt_h; m /= p.nt_h;
+  const int ti = m % p.nt_t; m /= p.nt_t;
+  b = m;
+  t0 = ti * p.PT; h0 = hi * p.PH; w0 = wi * p.PW;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
+                    const __grid_constant__ CUtensorMap tma_y, const ConvParams p) {
+  using L = ConvSmem<BN>;
+  constexpr int STAGES = L::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tma_x);
+    prefetch_tensormap(&tma_w);
+    prefetch_tensormap(&tma_y);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_ptr_smem, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  griddep_wait();
+
+  const int work0 = int(blockIdx.x), work_stride = int(gridDim.x);
+  const int taps = p.KT * p.KH * p.KW;
+  const int nkb = taps * p.cblocks;
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = work0; work < p.total_tiles; work += work_stride) {
+        int ni, b, t0, h0, w0;
+        locate(p, work, ni, b, t0, h0, w0);
+        const int xt = t0 * p.ST + p.OT, xh = h0 * p.SH + p.OH, xw = w0 * p.SW + p.OW;
+        int kb = 0;
+        for (int dt = 0; dt < p.KT; ++dt)
+          for (int dh = 0; dh < p.KH; ++dh)
+            for (int dw = 0; dw < p.KW; ++dw)
+              for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * L::STAGE_BYTES;
+                uint8_t* sB = sA + A_TILE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                tma_load_5d(sA, &tma_x, &full_bar[stage], cb * BK, xw + dw, xh + dh, xt + dt, b);   // box {64 c, PW, PH, PT, 1}
+                tma_load_2d(sB, &tma_w, &full_bar[stage], kb * BK, ni * BN);                        // box [64 k][BN n]
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int work = work0; work < p.total_tiles; work += work_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          // K-major operands: a K = 16 step advances 32 bytes inside the 128-byte swizzle row (csrc/gemm.cu)
+          const uint32_t a_lo = smem_desc_lo(smem_u32(smem + stage * L::STAGE_BYTES), 16);
+          umma_bf16_ss_x4<false>(tmem_d, a_lo, a_lo + uint32_t(A_TILE_BYTES >> 4), (UMMA_K * 2) >> 4, (UMMA_K * 2) >> 4, desc_hi,
+                                 desc_hi, idesc, kb > 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == nkb - 1) umma_commit(&tmem_full_bar[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5): TMEM -> (+ bias, + residual) -> bf16 -> staging slot -> 5-D TMA store
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
+    uint8_t* slots = smem + L::EPI_OFFSET;
+    float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+    const bool epi_t0 = threadIdx.x == 64;
+    const int sw = lane & 7;
+    const int r = q * 32 + lane;                              // row of the tile = position of the patch, w fastest
+    const int pw = r % p.PW, ph = (r / p.PW) % p.PH, pt = r / (p.PW * p.PH);
+    int it = 0;
+    int gu = 0;                                               // stored 64-channel chunks so far: consecutive staging slots
+    for (int work = work0; work < p.total_tiles; work += work_stride, ++it) {
+      int ni, b, t0, h0, w0;
+      locate(p, work, ni, b, t0, h0, w0);
+      const int n0 = ni * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // the previous tile's readers of s_bias are done
+      for (int c = threadIdx.x - 64; c < BN; c += 128) s_bias[c] = (p.bias != nullptr && n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const __nv_bfloat16* res_row =
+          p.resid != nullptr ? p.resid + b * p.res_b + (long long)(t0 + pt) * p.res_t + (long long)(h0 + ph) * p.res_h +
+                                   (long long)(w0 + pw) * p.res_w : nullptr;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+      // only the 64-channel chunks that hold real output channels are stored
+      const int chunks = min(BN / 64, (p.Cout - n0 + 63) / 64);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 64; ++ch) {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(t_acc + uint32_t(ch * 64), ra);
+        tmem_ld_32x32(t_acc + uint32_t(ch * 64 + 32), rb);
+        tmem_ld_wait();
+        if (ch == BN / 64 - 1) {                               // accumulator fully read: hand it back before the last stores
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (ch >= chunks) continue;                            // block-uniform
+        const int s_c = gu & 3;
+        ++gu;
+        uint8_t* row_c = slots + s_c * EPI_SLOT_BYTES + r * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t* rr = half == 0 ? ra : rb;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) + s_bias[ch * 64 + half * 32 + j];
+          if (res_row != nullptr) {
+            const int c0 = n0 + ch * 64 + half * 32;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (c0 + 8 * j < p.Cout) {                       // channel counts are multiples of 8
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 8 * j));
+                const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+                v[8 * j + 0] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += bb.x; v[8 * j + 3] += bb.y;
+                v[8 * j + 4] += c2.x; v[8 * j + 5] += c2.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(row_c + (((half * 4 + j) ^ sw) << 4)) = o;
+          }
+        }
+        // one barrier per chunk: behind it every row of the slot is written (and fenced towards the async proxy), and
+        // the slot the NEXT chunk writes has been read out by its previous store (epi_t0 checks before arriving)
+        fence_proxy_async_smem();
+        if (epi_t0) tma_store_wait_read<2>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_t0) {
+          tma_store_5d(&tma_y, slots + s_c * EPI_SLOT_BYTES, n0 + ch * 64, w0 * p.YW + p.Y0W, h0 * p.YH + p.Y0H,
+                       t0 * p.YT + p.Y0T, b);
+          tma_store_commit();
+        }
+      }
+    }
+    if (epi_t0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- GroupNorm statistics: partial (sum, sum of squares) per (batch element, group, slab of positions) ---------------
+// x dense channels-last [B, P, ldc] (P = T*H*W positions); grid (slabs, G, B); partial[b][g][slab][2].
+__global__ void __launch_bounds__(256) groupnorm_partial_kernel(const __nv_bfloat16* __restrict__ x, long long P, int ldc, int cg,
+                                                                int slabs, float* __restrict__ partial) {
+  const int slab = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+  const long long p0 = P * slab / slabs, p1 = P * (slab + 1) / slabs;
+  const __nv_bfloat16* base = x + (size_t(b) * P) * ldc + g * cg;
+  float s1 = 0.f, s2 = 0.f;
+  // cg is a multiple of 2 (channels are multiples of 64 / 32 groups); one thread walks positions, all channels of the group
+  for (long long pos = p0 + threadIdx.x; pos < p1; pos += 256) {
+    const __nv_bfloat16* row = base + pos * ldc;
+    for (int c = 0; c < cg; c += 2) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + c));
+      s1 += v.x + v.y;
+      s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, s2));
+    }
+  }
+  __shared__ float red[2][8];
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; c += red[1][i]; }
+    float* o = partial + ((size_t(b) * gridDim.y + g) * slabs + slab) * 2;
+    o[0] = a; o[1] = c;
+  }
+}
+
+// ---- y = pad_replicate(act(norm(x))) : the operand of the next convolution -----------------------------------------------
+// x dense [B, T, H, W, ldx]; y [B, T + pt0 + pt1, H + ph0 + ph1, W + pw0 + pw1, ldy] with C real channels (ldy >= C; the
+// channels [C, ldy) are zeroed).  norm: 0 none, 1 GroupNorm from `partial` (G groups, eps), 2 per-channel affine
+// (eval BatchNorm folded into scale / shift).  act: 0 none, 1 SiLU.  One thread = 8 channels of one padded position.
+struct PadParams {
+  int B, T, H, W, C, ldx, ldy;
+  int pt0, ph0, pw0, Tp, Hp, Wp;
+  int norm, act, G, slabs;
+  float eps;
+  const float* partial;
+  const float* gamma;        // norm 1: weight, norm 2: scale
+  const float* beta;         // norm 1: bias, norm 2: shift
+};
+__global__ void __launch_bounds__(256) pad_norm_act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                           const PadParams p) {
+  const int cv = p.ldy / 8;
+  const long long total = (long long)p.B * p.Tp * p.Hp * p.Wp * cv;
+  const int cg = p.norm == 1 ? p.C / p.G : 1;
+  const float inv_n = p.norm == 1 ? 1.f / (float(p.T) * p.H * p.W * cg) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = int(i % cv) * 8;
+    long long r = i / cv;
+    const int w = int(r % p.Wp); r /= p.Wp;
+    const int h = int(r % p.Hp); r /= p.Hp;
+    const int t = int(r % p.Tp); r /= p.Tp;
+    const int b = int(r);
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (c0 < p.C) {
+      const int ts = min(max(t - p.pt0, 0), p.T - 1), hs = min(max(h - p.ph0, 0), p.H - 1), ws = min(max(w - p.pw0, 0), p.W - 1);
+      const uint4 u = *reinterpret_cast<const uint4*>(x + ((((size_t)b * p.T + ts) * p.H + hs) * p.W + ws) * p.ldx + c0);
+      float v[8];
+      { const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        v[0] = a.x; v[1] = a.y; v[2] = bb.x; v[3] = bb.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y; }
+      int cur_g = -1;
+      float mean = 0.f, rstd = 1.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        float xv = v[k];
+        if (c >= p.C) { v[k] = 0.f; continue; }
+        if (p.norm == 1) {
+          const int g = c / cg;
+          if (g != cur_g) {                                    // partial sums in slab order: reproducible
+            const float* pp = p.partial + (size_t(b) * p.G + g) * p.slabs * 2;
+            float s1 = 0.f, s2 = 0.f;
+            for (int s = 0; s < p.slabs; ++s) { s1 += pp[2 * s]; s2 += pp[2 * s + 1]; }
+            mean = s1 * inv_n;
+            rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
+            cur_g = g;
+          }
+          xv = (xv - mean) * rstd * p.gamma[c] + p.beta[c];
+        } else if (p.norm == 2) {
+          xv = xv * p.gamma[c] + p.beta[c];
+        }
+        if (p.act == 1) xv = xv / (1.f + __expf(-xv));
+        v[k] = xv;
+      }
+      out = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+    *reinterpret_cast<uint4*>(y + (size_t)(i / cv) * p.ldy + c0) = out;
+  }
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p, double flops,
+                cudaStream_t st) {
+  using L = ConvSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MEBT_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  LaunchScope ls(FAM_GEMM, flops, st);
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  MEBT_CUDA_OK(launch_pdl(conv3d_igemm_kernel<BN>, dim3(grid), dim3(CV_THREADS), L::TOTAL, st, tx, tw, ty, p));
+  MEBT_LAUNCH_OK("conv3d_igemm_kernel");
+  return MEBT_OK;
+}
+
+}  // namespace
+}  // namespace mebt
+
+extern "C" {
+
+size_t mebt_groupnorm_workspace_bytes(int B, int groups) { return size_t(B) * groups * 16 * 2 * sizeof(float); }
+
+int mebt_pad_norm_act(const void* x, int ldx, void* y, int ldy, int B, int T, int H, int W, int C, const int* pad6, int norm,
+                      int act, int groups, float eps, const float* gamma, const float* beta, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  using namespace mebt;
+  MEBT_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && C > 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C, MEBT_ERR_SHAPE,
+               "pad_norm_act: bad shape (channel strides must be multiples of 8)");
+  MEBT_REQUIRE(norm >= 0 && norm <= 2 && act >= 0 && act <= 1, MEBT_ERR_UNSUPPORTED, "pad_norm_act: norm %d act %d", norm, act);
+  for (int i = 0; i < 6; ++i) MEBT_REQUIRE(pad6[i] >= 0 && pad6[i] <= 8, MEBT_ERR_SHAPE, "pad_norm_act: pad[%d] = %d", i, pad6[i]);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PadParams p;
+  p.B = B; p.T = T; p.H = H; p.W = W; p.C = C; p.ldx = ldx; p.ldy = ldy;
+  p.pt0 = pad6[0]; p.ph0 = pad6[2]; p.pw0 = pad6[4];
+  p.Tp = T + pad6[0] + pad6[1]; p.Hp = H + pad6[2] + pad6[3]; p.Wp = W + pad6[4] + pad6[5];
+  p.norm = norm; p.act = act; p.G = groups; p.slabs = 16; p.eps = eps;
+  p.partial = static_cast<const float*>(workspace); p.gamma = gamma; p.beta = beta;
+  if (norm == 1) {
+    MEBT_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 2 == 0 && gamma != nullptr && beta != nullptr, MEBT_ERR_SHAPE,
+                 "pad_norm_act: GroupNorm needs C %% groups == 0 and an even group width (C=%d groups=%d)", C, groups);
+    MEBT_REQUIRE(workspace != nullptr && workspace_bytes >= mebt_groupnorm_workspace_bytes(B, groups), MEBT_ERR_WORKSPACE,
+                 "pad_norm_act: workspace too small");
+    LaunchScope ls(FAM_LAYERNORM, double(B) * T * H * W * C * 2.0, st);
+    groupnorm_partial_kernel<<<dim3(16, groups, B), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), (long long)T * H * W, ldx,
+                                                                   C / groups, 16, static_cast<float*>(workspace));
+    MEBT_LAUNCH_OK("groupnorm_partial_kernel");
+  } else if (norm == 2) {
+    MEBT_REQUIRE(gamma != nullptr && beta != nullptr, MEBT_ERR_SHAPE, "pad_norm_act: affine norm needs scale and shift");
+  }
+  const long long total = (long long)B * p.Tp * p.Hp * p.Wp * (ldy / 8);
+  LaunchScope ls(FAM_LAYERNORM, double(total) * 16.0 * 2.0, st);
+  const int grid = int(std::min<long long>((total + 255) / 256, 148 * 16));
+  pad_norm_act_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), p);
+  MEBT_LAUNCH_OK("pad_norm_act_kernel");
+  return MEBT_OK;
+}
+
+int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w, int cin, const float* bias,
+                      const void* resid, int ldr, void* y, int ldy, const int* ydims4, int cout, const int* taps3,
+                      const int* step3, const int* origin3, const int* ystep3, const int* yorigin3, const int* odims3,
+                      void* stream) {
+  // xp: padded input [B, Tp, Hp, Wp, ldx] (xdims4 = B, Tp, Hp, Wp); y: destination [B, Ty, Hy, Wy, ldy] (ydims4);
+  // odims3 = (To, Ho, Wo) output positions computed by this launch; they land at y[b, t * ystep + yorigin, ...].
+  using namespace mebt;
+  const int B = xdims4[0];
+  const int To = odims3[0], Ho = odims3[1], Wo = odims3[2];
+  MEBT_REQUIRE(B > 0 && To > 0 && Ho > 0 && Wo > 0 && cin > 0 && cout > 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cin && ldy >= cout &&
+               cout % 8 == 0 && ydims4[0] == B, MEBT_ERR_SHAPE, "conv3d: bad shape (channel counts / strides must be multiples of 8)");
+  for (int d = 0; d < 3; ++d) {
+    MEBT_REQUIRE(taps3[d] >= 1 && taps3[d] <= 4 && step3[d] >= 1 && step3[d] <= 2 && ystep3[d] >= 1 && ystep3[d] <= 2 &&
+                 origin3[d] >= 0 && yorigin3[d] >= 0, MEBT_ERR_UNSUPPORTED, "conv3d: taps 1-4, steps 1-2");
+    MEBT_REQUIRE((odims3[d] - 1) * step3[d] + origin3[d] + taps3[d] <= xdims4[1 + d], MEBT_ERR_SHAPE,
+                 "conv3d: the input (dim %d: %d) is too small for %d outputs", d, xdims4[1 + d], odims3[d]);
+    MEBT_REQUIRE((odims3[d] - 1) * ystep3[d] + yorigin3[d] < ydims4[1 + d], MEBT_ERR_SHAPE, "conv3d: the destination is too small");
+  }
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  // patch: as wide as possible along w, then h, then t (each a power of two dividing the output extent)
+  auto pow2_div = [](int n, int cap) { int v = 1; while (v * 2 <= cap && n % (v * 2) == 0) v *= 2; return v; };
+  p.PW = pow2_div(Wo, 16);
+  p.PH = pow2_div(Ho, 128 / p.PW);
+  p.PT = pow2_div(To, 128 / (p.PW * p.PH));
+  MEBT_REQUIRE(p.PT * p.PH * p.PW == 128, MEBT_ERR_UNSUPPORTED,
+               "conv3d: the output extent %d x %d x %d does not tile into 128-position patches", To, Ho, Wo);
+  p.nt_t = To / p.PT; p.nt_h = Ho / p.PH; p.nt_w = Wo / p.PW;
+  p.tiles_m = B * p.nt_t * p.nt_h * p.nt_w;
+  const int bn = cout <= 64 ? 64 : 256;
+  p.num_n_blocks = (cout + bn - 1) / bn;
+  p.total_tiles = p.tiles_m * p.num_n_blocks;
+  p.KT = taps3[0]; p.KH = taps3[1]; p.KW = taps3[2];
+  p.ST = step3[0]; p.SH = step3[1]; p.SW = step3[2];
+  p.OT = origin3[0]; p.OH = origin3[1]; p.OW = origin3[2];
+  p.YT = ystep3[0]; p.YH = ystep3[1]; p.YW = ystep3[2];
+  p.Y0T = yorigin3[0]; p.Y0H = yorigin3[1]; p.Y0W = yorigin3[2];
+  p.cblocks = (cin + 63) / 64;
+  p.Cout = cout;
+  p.bias = bias;
+  p.resid = static_cast<const __nv_bfloat16*>(resid);
+  if (resid != nullptr) {
+    MEBT_REQUIRE(ldr % 8 == 0 && ldr >= cout, MEBT_ERR_SHAPE, "conv3d: residual stride");
+    p.res_w = ldr; p.res_h = (long long)Wo * ldr; p.res_t = (long long)Ho * Wo * ldr; p.res_b = (long long)To * Ho * Wo * ldr;
+  }
+  const int taps = p.KT * p.KH * p.KW;
+  const uint64_t Kp = uint64_t(taps) * p.cblocks * 64;
+  CUtensorMap tx, tw, ty;
+  {
+    const uint64_t dims[5] = {uint64_t(cin), uint64_t(xdims4[3]), uint64_t(xdims4[2]), uint64_t(xdims4[1]), uint64_t(B)};
+    const uint64_t strides[4] = {uint64_t(ldx) * 2, uint64_t(xdims4[3]) * ldx * 2, uint64_t(xdims4[2]) * xdims4[3] * ldx * 2,
+                                 uint64_t(xdims4[1]) * xdims4[2] * xdims4[3] * ldx * 2};
+    const uint32_t box[5] = {64, uint32_t(p.PW * p.SW), uint32_t(p.PH * p.SH), uint32_t(p.PT * p.ST), 1};
+    const uint32_t es[5] = {1, uint32_t(p.SW), uint32_t(p.SH), uint32_t(p.ST), 1};
+    int rc = get_tensor_map_5d(&tx, xp, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  {
+    int rc = get_tensor_map_2d(&tw, w, 2, Kp, uint64_t(cout), Kp * 2, 64, uint32_t(bn));
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[5] = {uint64_t(cout), uint64_t(ydims4[3]), uint64_t(ydims4[2]), uint64_t(ydims4[1]), uint64_t(B)};
+    const uint64_t strides[4] = {uint64_t(ldy) * 2, uint64_t(ydims4[3]) * ldy * 2, uint64_t(ydims4[2]) * ydims4[3] * ldy * 2,
+                                 uint64_t(ydims4[1]) * ydims4[2] * ydims4[3] * ldy * 2};
+    const uint32_t box[5] = {64, uint32_t(p.PW * p.YW), uint32_t(p.PH * p.YH), uint32_t(p.PT * p.YT), 1};
+    const uint32_t es[5] = {1, uint32_t(p.YW), uint32_t(p.YH), uint32_t(p.YT), 1};
+    int rc = get_tensor_map_5d(&ty, y, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  const double flops = 2.0 * double(p.tiles_m) * 128.0 * double(cout) * double(taps) * double(cin);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return bn == 64 ? launch_conv<64>(tx, tw, ty, p, flops, st) : launch_conv<256>(tx, tw, ty, p, flops, st);
+}
+
+}  // extern "C"

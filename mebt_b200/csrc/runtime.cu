@@ -183,6 +183,33 @@ int get_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_
   return MEBT_OK;
 }
 
+// 5-D tiled map over a channels-last activation tensor (csrc/conv3d.cu): dims / box innermost first, 128-byte swizzle,
+// element strides > 1 = one element every `stride` along that dimension (the box then holds ceil(box / stride) of them).
+// Not cached: a convolution launch is tens of microseconds and the encode is host arithmetic.
+int get_tensor_map_5d(CUtensorMap* out, const void* ptr, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                      const uint32_t box[5], const uint32_t elem_strides[5]) {
+  EncodeTiledFn fn = encode_fn();
+  MEBT_REQUIRE(fn != nullptr, MEBT_ERR_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  MEBT_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, MEBT_ERR_SHAPE, "TMA operand must be 16-byte aligned (ptr=%p)", ptr);
+  cuuint64_t d[5]; cuuint64_t s[4]; cuuint32_t b[5]; cuuint32_t e[5];
+  for (int i = 0; i < 5; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides[i]; }
+  for (int i = 0; i < 4; ++i) {
+    MEBT_REQUIRE((strides_bytes[i] & 15) == 0, MEBT_ERR_SHAPE, "TMA strides must be multiples of 16 bytes (dim %d: %llu)", i + 1,
+                 (unsigned long long)strides_bytes[i]);
+    s[i] = strides_bytes[i];
+  }
+  MEBT_REQUIRE(box[0] * 2 == 128, MEBT_ERR_SHAPE, "TMA box must be 128 bytes wide");
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MEBT_REQUIRE(r == CUDA_SUCCESS, MEBT_ERR_CUDA,
+               "cuTensorMapEncodeTiled(5d) failed (%d) dims=%llu,%llu,%llu,%llu,%llu box=%u,%u,%u,%u,%u estr=%u,%u,%u,%u,%u", int(r),
+               (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)d[2], (unsigned long long)d[3],
+               (unsigned long long)d[4], b[0], b[1], b[2], b[3], b[4], e[0], e[1], e[2], e[3], e[4]);
+  *out = m;
+  return MEBT_OK;
+}
+
 }  // namespace mebt
 
 extern "C" {

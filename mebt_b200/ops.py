@@ -5,6 +5,8 @@ hand-written sm_100a kernel and raises `MebtError` on any failure.  There is no 
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -455,4 +457,40 @@ def attention_f32(q, q_col0, kv1, k1_col0, v1_col0, nk1, kv2, k2_col0, v2_col0, 
          _ptr(kv1) if nk1 > 0 else None, kv1.stride(0) if nk1 > 0 else 0, k1_col0, v1_col0, nk1,
          _ptr(kv2) if nk2 > 0 else None, kv2.stride(0) if nk2 > 0 else 0, k2_col0, v2_col0, nk2,
          out.data_ptr(), out.stride(0), B, H, NQ, 64, _stream())
+    return out
+
+
+# ---- VQGAN encoder / decoder convolutions (csrc/conv3d.cu); activations channels-last bf16 [B, T, H, W, C] -------------------
+def _ints(*v):
+    return (ctypes.c_int * len(v))(*v)
+
+
+def pad_norm_act(x, pad6, norm=0, act=0, groups=32, eps=1e-6, gamma=None, beta=None):
+    """replicate_pad(act(norm(x))): x [B, T, H, W, C] bf16 (C % 8 == 0) -> [B, T + pads, H + pads, W + pads, C].
+    pad6 = (t0, t1, h0, h1, w0, w1).  norm: 0 none, 1 GroupNorm(groups, eps; gamma, beta), 2 affine x * gamma + beta.
+    act: 0 none, 1 SiLU.  (F.pad(mode='replicate') + Normalize + silu of mebt/vqgan.py:255-260,344-349,381.)"""
+    _need_cuda(x)
+    if x.dtype != torch.bfloat16 or x.dim() != 5 or not x.is_contiguous():
+        raise MebtError("pad_norm_act: contiguous bf16 [B, T, H, W, C] expected")
+    B, T, H, W, C = x.shape
+    y = torch.empty(B, T + pad6[0] + pad6[1], H + pad6[2] + pad6[3], W + pad6[4] + pad6[5], C, device=x.device,
+                    dtype=torch.bfloat16)
+    ws = _ws(x.device, _lib.lib.mebt_groupnorm_workspace_bytes(B, groups) if norm == 1 else 16, "gn")
+    call("mebt_pad_norm_act", x.data_ptr(), C, y.data_ptr(), C, B, T, H, W, C, _ints(*pad6), int(norm), int(act), int(groups),
+         float(eps), _ptr(gamma), _ptr(beta), ws.data_ptr(), ws.numel(), _stream())
+    return y
+
+
+def conv3d_ndhwc(xp, w_packed, cin, cout, taps, step, odims, bias=None, resid=None, out=None, origin=(0, 0, 0),
+                 ystep=(1, 1, 1), yorigin=(0, 0, 0)):
+    """Implicit-GEMM 3-D convolution over an already padded channels-last input (mebt_conv3d_ndhwc).
+    xp [B, Tp, Hp, Wp, C]; w_packed bf16 [cout, prod(taps) * ceil64(cin)]; odims = (To, Ho, Wo) positions computed; they
+    are written to out[b, t * ystep + yorigin, ...] (out defaults to a dense [B, To, Ho, Wo, cout] tensor)."""
+    _need_cuda(xp, w_packed, resid)
+    B = xp.shape[0]
+    if out is None:
+        out = torch.empty(B, *odims, cout, device=xp.device, dtype=torch.bfloat16)
+    call("mebt_conv3d_ndhwc", xp.data_ptr(), xp.shape[4], _ints(*xp.shape[:4]), w_packed.data_ptr(), int(cin), _ptr(bias),
+         _ptr(resid), resid.shape[4] if resid is not None else 0, out.data_ptr(), out.shape[4], _ints(*out.shape[:4]), int(cout),
+         _ints(*taps), _ints(*step), _ints(*origin), _ints(*ystep), _ints(*yorigin), _ints(*odims), _stream())
     return out

@@ -390,6 +390,53 @@ def gen_grads_dropout(cfg_name, B, wseed, dseed, t, p, mseed):
     save(f"grads_dropout_{cfg_name}", cfg, **arrays)
 
 
+def gen_vqgan():
+    """VQGAN encoder / decoder of the unmodified reference (mebt/vqgan.py) with oracle.vqgan_oracle.make_weights:
+    pre-VQ latent of a random video and the decoded video of random code grids, group- and batch-norm variants."""
+    import argparse
+    try:                                   # mebt.modules.lpips imports torchvision / requests: stub what is missing
+        import mebt.modules.lpips  # noqa: F401
+    except Exception:
+        for name in ("torchvision", "torchvision.models", "requests", "tqdm"):
+            if name not in sys.modules:
+                try:
+                    __import__(name)
+                except Exception:
+                    sys.modules[name] = types.ModuleType(name)
+        if not hasattr(sys.modules["torchvision"], "models"):
+            sys.modules["torchvision"].models = sys.modules["torchvision.models"]
+    from mebt import vqgan as RV
+    from oracle import vqgan_oracle as VO
+
+    for tag, norm, ds in (("small", "group", (2, 4, 4)), ("bn", "batch", (4, 2, 2))):
+        args = argparse.Namespace(embedding_dim=64, n_codes=128, n_hiddens=32, downsample=ds, image_channels=3, norm_type=norm,
+                                  padding_type="replicate")
+        enc = RV.Encoder(args.n_hiddens, args.downsample, args.image_channels, args.norm_type, args.padding_type)
+        dec = RV.Decoder(args.n_hiddens, args.downsample, args.image_channels, args.norm_type)
+        pre = RV.SamePadConv3d(enc.out_channels, args.embedding_dim, 1, padding_type=args.padding_type)
+        post = RV.SamePadConv3d(args.embedding_dim, enc.out_channels, 1)
+        mods = {"encoder": enc, "decoder": dec, "pre_vq_conv": pre, "post_vq_conv": post}
+        shapes = {f"{n}.{k}": tuple(v.shape) for n, m in mods.items() for k, v in m.state_dict().items()}
+        shapes["codebook.embeddings"] = (args.n_codes, args.embedding_dim)
+        P = VO.make_weights(shapes, 7)
+        for n, m in mods.items():
+            m.load_state_dict({k[len(n) + 1:]: v for k, v in P.items() if k.startswith(n + ".")}, strict=True)
+            m.eval()
+        g = torch.Generator().manual_seed(11)
+        x = torch.rand(1, 3, 8, 32, 32, generator=g) - 0.5
+        lat = tuple(s // d for s, d in zip((8, 32, 32), ds))
+        codes = torch.randint(0, args.n_codes, (1, *lat), generator=g)
+        with torch.no_grad():
+            z = pre(enc(x))
+            h = torch.nn.functional.embedding(codes, P["codebook.embeddings"])
+            rec = dec(post(RV.shift_dim(h, -1, 1)))
+        cfg = dict(vars(args))
+        np.savez_compressed(HERE / f"vqgan_{tag}.npz", cfg_json=json.dumps(cfg), wseed=7, x=x.numpy(), codes=codes.numpy(),
+                            z=z.numpy(), rec=rec.numpy(), keys=np.array(sorted(shapes)),
+                            shapes_json=json.dumps({k: list(v) for k, v in shapes.items()}))
+        print("vqgan", tag, tuple(z.shape), tuple(rec.shape), float(z.abs().mean()), float(rec.abs().mean()))
+
+
 def _reference_script_functions():
     """bidirect_sample / extrapolate exactly as written in the reference's sample_vqgan_transformer_videos.py: the two
     FunctionDefs are compiled out of the script's source (the module itself imports lightning, omegaconf, matplotlib...)."""
@@ -462,7 +509,12 @@ def main():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "pipelines":
+    if len(sys.argv) > 1 and sys.argv[1] == "vqgan":
+        install_stubs()
+        sys.path.insert(0, REF)
+        sys.path.insert(1, str(REPO))
+        gen_vqgan()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pipelines":
         sys.path.insert(1, str(REPO))
         gen_pipelines()
     elif len(sys.argv) > 1 and sys.argv[1] == "entp":        # only the fixture added in round 2

@@ -191,3 +191,21 @@ def test_flop_model_matches_survey():
                mode=(["latent_enc", "latent_self"] * 6 + ["latent_enc"] + ["latent_dec", "lt2l"] * 5 + ["latent_dec"]))
     assert abs(O.forward_flops(cfg, 512, 512) / 1e9 - 234.9) < 0.1
     assert abs(O.forward_flops(cfg, 4096, 4096) / 1e9 - 1054.1) < 0.1
+
+
+@pytest.mark.parametrize("tag", ["small", "bn"])
+def test_vqgan_oracle_vs_reference_golden(tag):
+    """oracle.vqgan_oracle (the CPU restatement of the VQGAN encoder / decoder, mebt/vqgan.py:263-405) against the
+    unmodified reference's outputs: pre-VQ latent of a random video and the decoded video of random code grids, GroupNorm
+    and eval-BatchNorm variants, strides (2,4,4) and (4,2,2)."""
+    import json
+
+    from oracle import vqgan_oracle as VO
+    z, cfg = load_golden(f"vqgan_{tag}")
+    shapes = {k: tuple(v) for k, v in json.loads(str(z["shapes_json"])).items()}
+    P = VO.make_weights(shapes, int(z["wseed"]))
+    ds = tuple(cfg["downsample"])
+    lat = VO.pre_quant(P, torch.from_numpy(z["x"]), ds)
+    rec = VO.decode(P, torch.from_numpy(z["codes"]), ds)
+    np.testing.assert_allclose(lat.numpy(), z["z"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rec.numpy(), z["rec"], rtol=1e-4, atol=1e-5)

@@ -1,0 +1,145 @@
+"""VQGAN encoder / decoder on the tensor-core convolution path (csrc/conv3d.cu, mebt_b200/vqgan.py) against the CPU oracle
+(oracle/vqgan_oracle.py, pinned to the unmodified reference by tests/golden/vqgan_*.npz) and against those fixtures.
+bf16 activations through ~20 convolutions: tolerance 3e-2 of the output's RMS (north_star's bf16 tolerance is 1e-2 per
+GEMM; errors of a chain add in quadrature)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt())
+
+
+def test_pad_norm_act_vs_torch():
+    from mebt_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 8, 16, 64, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    xb = x.to(torch.bfloat16)
+    ref = torch.nn.functional.group_norm(xb.float().permute(0, 4, 1, 2, 3), 32, gamma, beta, 1e-6)
+    ref = ref * torch.sigmoid(ref)
+    ref = torch.nn.functional.pad(ref, (2, 1, 1, 1, 0, 1), mode="replicate").permute(0, 2, 3, 4, 1)
+    got = ops.pad_norm_act(xb.cuda(), (0, 1, 1, 1, 2, 1), norm=1, act=1, groups=32, eps=1e-6, gamma=gamma.cuda(), beta=beta.cuda())
+    assert got.shape == ref.shape
+    assert (got.float().cpu() - ref).abs().max() < 3e-2
+    plain = ops.pad_norm_act(xb.cuda(), (1, 1, 1, 1, 1, 1))
+    ref2 = torch.nn.functional.pad(xb.float().permute(0, 4, 1, 2, 3), (1,) * 6, mode="replicate").permute(0, 2, 3, 4, 1)
+    assert torch.equal(plain.float().cpu(), ref2)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dims", [(64, 64, 3, (1, 1, 1), (2, 8, 16)), (24, 96, 3, (1, 1, 1), (4, 8, 8)),
+                                                    (32, 64, 4, (2, 2, 2), (4, 16, 16)), (64, 320, 4, (1, 2, 2), (4, 16, 32)),
+                                                    (128, 8, 1, (1, 1, 1), (2, 8, 8)), (8, 32, 3, (1, 1, 1), (1, 16, 16))])
+def test_same_pad_conv3d_vs_torch(cin, cout, k, stride, dims):
+    """One SamePadConv3d (vqgan.py:358-381) incl. channel counts that are not multiples of 64 and strided kernels."""
+    from mebt_b200.vqgan import SamePadConv3d
+    torch.manual_seed(1)
+    m = SamePadConv3d(cin, cout, k, stride=stride).cuda()
+    x = torch.randn(2, cin, *dims)
+    xb = x.to(torch.bfloat16).float()
+    w = m.conv.weight.detach().cpu().to(torch.bfloat16).float()
+    pad = sum([list(m.pads[2]), list(m.pads[1]), list(m.pads[0])], [])
+    ref = torch.nn.functional.conv3d(torch.nn.functional.pad(xb, pad, mode="replicate"), w, m.conv.bias.detach().cpu(), stride=stride)
+    got = m(xb.cuda()).cpu()
+    assert got.shape == ref.shape
+    assert _rel(got, ref) < 6e-3, _rel(got, ref)
+
+
+@pytest.mark.parametrize("stride,dims", [((2, 2, 2), (2, 8, 8)), ((1, 2, 2), (4, 8, 16))])
+def test_same_pad_conv_transpose3d_vs_torch(stride, dims):
+    """SamePadConvTranspose3d (vqgan.py:384-405) as one 2-tap convolution per output parity."""
+    from mebt_b200.vqgan import SamePadConvTranspose3d
+    torch.manual_seed(2)
+    m = SamePadConvTranspose3d(64, 32, 4, stride=stride).cuda()
+    x = torch.randn(2, 64, *dims)
+    xb = x.to(torch.bfloat16).float()
+    w = m.convt.weight.detach().cpu().to(torch.bfloat16).float()
+    pad = sum([list(m.pads[2]), list(m.pads[1]), list(m.pads[0])], [])
+    ref = torch.nn.functional.conv_transpose3d(torch.nn.functional.pad(xb, pad, mode="replicate"), w, m.convt.bias.detach().cpu(),
+                                               stride=stride, padding=(3, 3, 3))
+    got = m(xb.cuda()).cpu()
+    assert got.shape == ref.shape
+    assert _rel(got, ref) < 6e-3, _rel(got, ref)
+
+
+@pytest.mark.parametrize("tag", ["small", "bn"])
+def test_vqgan_encode_decode_vs_reference_golden(tag):
+    from mebt_b200.vqgan import VQGAN, _Args
+    from oracle import vqgan_oracle as VO
+    z, cfg = load_golden(f"vqgan_{tag}")
+    shapes = {k: tuple(v) for k, v in json.loads(str(z["shapes_json"])).items()}
+    P = VO.make_weights(shapes, int(z["wseed"]))
+    model = VQGAN(_Args(cfg))
+    own = model.state_dict()
+    assert set(shapes) <= set(own) and all(tuple(own[k].shape) == shapes[k] for k in shapes)
+    model.load_state_dict({**own, **P})
+    model = model.cuda().eval()
+    lat = model.pre_quant(torch.from_numpy(z["x"]).cuda()).cpu()
+    ref_lat = torch.from_numpy(z["z"])
+    assert lat.shape == ref_lat.shape and _rel(lat, ref_lat) < 3e-2, _rel(lat, ref_lat)
+    rec = model.decode(torch.from_numpy(z["codes"]).cuda()).cpu()
+    ref_rec = torch.from_numpy(z["rec"])
+    assert rec.shape == ref_rec.shape and _rel(rec, ref_rec) < 3e-2, _rel(rec, ref_rec)
+    # encode end to end: the codes of the oracle's latent, except where the two nearest codes are a near-tie
+    codes = model.encode(torch.from_numpy(z["x"]).cuda()).cpu()
+    E = P["codebook.embeddings"]
+    flat = ref_lat.permute(0, 2, 3, 4, 1).reshape(-1, E.shape[1])
+    d = (flat ** 2).sum(1, keepdim=True) - 2 * flat @ E.t() + (E ** 2).sum(1)[None]
+    ref_codes = d.argmin(1).view(codes.shape)
+    mism = codes != ref_codes
+    if mism.any():
+        top2 = d.topk(2, dim=1, largest=False).values
+        gap = ((top2[:, 1] - top2[:, 0]) / top2[:, 0].abs().clamp_min(1e-6)).view(codes.shape)
+        assert (gap[mism] < 0.1).all() and mism.float().mean() < 0.1, (int(mism.sum()), float(gap[mism].max()))
+
+
+def test_vqgan_oracle_parity_at_16_frame_latent_shape():
+    """The shape the MeBT configs use: 16 x 64 x 64 video -> 4 x 16 x 16 code grid (downsample 4, 4, 4)."""
+    from mebt_b200.vqgan import VQGAN, _Args
+    from oracle import vqgan_oracle as VO
+    cfg = dict(embedding_dim=256, n_codes=1024, n_hiddens=32, downsample=(4, 4, 4), image_channels=3, norm_type="group",
+               padding_type="replicate")
+    model = VQGAN(_Args(cfg))
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith("codebook.") or k == "codebook.embeddings"}
+    P = VO.make_weights(shapes, 3)
+    model.load_state_dict({**model.state_dict(), **P})
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(1, 3, 16, 64, 64, generator=g) - 0.5
+    codes = torch.randint(0, 1024, (1, 4, 16, 16), generator=g)
+    lat = model.pre_quant(x.cuda()).cpu()
+    ref = VO.pre_quant(P, x, (4, 4, 4))
+    assert lat.shape == (1, 256, 4, 16, 16) and _rel(lat, ref) < 3e-2, _rel(lat, ref)
+    rec = model.decode(codes.cuda()).cpu()
+    ref = VO.decode(P, codes, (4, 4, 4))
+    assert rec.shape == (1, 3, 16, 64, 64) and _rel(rec, ref) < 3e-2, _rel(rec, ref)
+
+
+def test_vqgan_checkpoint_and_npy_formats(tmp_path):
+    from mebt_b200 import vqgan as V
+    cfg = dict(embedding_dim=64, n_codes=128, n_hiddens=32, downsample=(2, 4, 4), image_channels=3, norm_type="group",
+               padding_type="replicate", sequence_length=8, sample_every_n_frames=1, resolution=32)
+    model = V.VQGAN(V._Args(cfg))
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["image_discriminator.model0.0.weight"] = torch.zeros(3)          # ignored extras of a training checkpoint
+    ckpt = tmp_path / "vqgan.ckpt"
+    torch.save({"hyper_parameters": {"args": V._Args(cfg)}, "state_dict": sd}, ckpt)
+    loaded = V.load_vqgan(str(ckpt))
+    assert loaded.latent_shape == (4, 8, 8)
+    for k, v in loaded.state_dict().items():
+        assert torch.equal(v.cpu(), model.state_dict()[k]), k
+    codes = [torch.randint(0, 128, (2, 4, 8, 8)) for _ in range(3)]
+    f = V.save_codemaps(str(tmp_path / "run"), codes)
+    back = V.load_codemaps(f, device="cpu")
+    assert back.shape == (6, 4, 8, 8) and torch.equal(back, torch.cat(codes))
+    vids = [np.random.rand(2, 3, 8, 32, 32).astype(np.float32) for _ in range(2)]
+    out = V.save_samples(str(tmp_path / "pix"), vids, 8, 32, n_sample=3, rng=np.random.RandomState(0))
+    assert out.shape == (3, 8, 32, 32, 3) and out.dtype == np.uint8
+    assert np.array_equal(np.load(str(tmp_path / "pix.npy")), out)
