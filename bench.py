@@ -54,8 +54,11 @@ CONFIGS = {
     "sample128f": dict(_BASE, block_size=8192, shape=[32, 16, 16]),
     "maskgit16f": dict(_BASE, block_size=1024, shape=[4, 16, 16]),
     "vq16f": dict(_BASE, block_size=1024, shape=[4, 16, 16]),
+    "vqgan16f": dict(_BASE, block_size=1024, shape=[4, 16, 16]),
 }
-DEFAULT_BATCH = {"train16f": 6, "maskgit16f": 32, "vq16f": 64, "sample128f": 32, "sample16f": 32}
+VQGAN_ARGS = dict(embedding_dim=256, n_codes=16384, n_hiddens=32, downsample=(4, 8, 8), image_channels=3, norm_type="group",
+                  padding_type="replicate", sequence_length=16, sample_every_n_frames=1, resolution=128)
+DEFAULT_BATCH = {"train16f": 6, "maskgit16f": 32, "vq16f": 64, "vqgan16f": 8, "sample128f": 32, "sample16f": 32}
 SECONDARY_BATCH = {"sample128f": 32}     # videos per GPU when sample128f rides along with the default line (a step is ~0.7 s)
 MASKGIT = dict(temperature=1.0, top_k=None, top_p=None, n_steps=128, strategy="maskgit", context_temperature=6.0)
 DNR = dict(n_draft=8, draft_t=1.0, n_revise=8, revise_t=1.0, M=2)
@@ -179,6 +182,12 @@ def workload_config(workload, cfg, B, dropout, world):
     elif workload == "vq16f":
         config = {"workload": "vq16f", "videos_per_gpu": B, "latent": [256, 4, 16, 16], "codebook": [16384, 256],
                   "unit_note": "a token = one quantised latent vector (distance + argmin, then both gathers)"}
+    elif workload == "vqgan16f":
+        config = {"workload": "vqgan16f", "videos_per_gpu": B, "video": [3, 16, 128, 128], "vqgan": dict(VQGAN_ARGS),
+                  "weights": "random (oracle.vqgan_oracle.make_weights, seed 0)",
+                  "unit_note": "a token = one code of the 4 x 16 x 16 grid; a step = VQGAN.encode (conv encoder + codebook) + "
+                               "VQGAN.decode (gather + conv decoder) of every video",
+                  "l2": "activations of one step (8 videos: 0.5 GB per full-resolution layer) exceed the 126 MB L2"}
     elif workload == "maskgit16f":
         config.update(sampler=MASKGIT, schedule="cosine", masked_tokens_per_video=maskgit_masked_tokens(N, 128))
     else:
@@ -276,6 +285,17 @@ def reference_model(cfg, state, pdrop, schedule="linear"):
     return model
 
 
+def vqgan_weights_and_video(B, seed):
+    """Seeded weights with the reference's state_dict names / shapes and B synthetic videos in [-0.5, 0.5]."""
+    from mebt_b200.vqgan import VQGAN, _Args
+    from oracle import vqgan_oracle as VO
+    shapes = {k: tuple(v.shape) for k, v in VQGAN(_Args(VQGAN_ARGS)).state_dict().items()
+              if not k.startswith("codebook.") or k == "codebook.embeddings"}
+    P = VO.make_weights(shapes, 0)
+    x = torch.rand(B, 3, 16, 128, 128, generator=torch.Generator().manual_seed(5 + seed)) - 0.5
+    return P, x
+
+
 def cpu_leg(workload, cfg, B, dropout, state, use_reference):
     """-> (step, units per step, description, kind).  A bounded sample of the workload (a few seconds per step)."""
     N = int(np.prod(cfg["shape"]))
@@ -290,6 +310,18 @@ def cpu_leg(workload, cfg, B, dropout, state, use_reference):
                 out = O.codebook_quantise(z, E)
                 O.codebook_decode_gather(out["encodings"], E)
         return step, 8 * 1024, "Codebook.forward + decode gather on 8 videos (fp32 torch-CPU oracle port)", "port"
+    if workload == "vqgan16f":
+        from oracle import vqgan_oracle as VO
+        P, x = vqgan_weights_and_video(1, 0)
+
+        def step():
+            with torch.no_grad():
+                z = VO.pre_quant(P, x, VQGAN_ARGS["downsample"])
+                E = P["codebook.embeddings"]
+                flat = z.permute(0, 2, 3, 4, 1).reshape(-1, E.shape[1])
+                codes = ((flat ** 2).sum(1, keepdim=True) - 2 * flat @ E.t() + (E ** 2).sum(1)[None]).argmin(1).view(1, 4, 16, 16)
+                VO.decode(P, codes, VQGAN_ARGS["downsample"])
+        return step, 1024, "VQGAN encode + decode of 1 video [3,16,128,128] (fp32 torch-CPU oracle port)", "port"
     if workload == "train16f":
         x, indices = synth_batch(cfg, B, 1)
         what = f"full training step (fwd + CE + autograd bwd + AdamW), B={B}, t={TRAIN_T}, dropout {dropout}"
@@ -379,7 +411,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     state = synth_weights(cfg)
-    use_ref = find_reference() is not None and workload != "vq16f" and not args.port
+    use_ref = find_reference() is not None and workload not in ("vq16f", "vqgan16f") and not args.port
     try:
         step, units, desc, kind = cpu_leg(workload, cfg, B, args.dropout, state, use_ref)
     except Exception as exc:  # noqa: BLE001  (an unimportable reference tree must not cost the line)
@@ -440,6 +472,26 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
             enc_host.copy_(enc, non_blocking=True)
         w.device, w.e2e = step_device, step_e2e
         w.h2d, w.d2h = int(z_host.numel() * 4), int(enc_host.numel() * 8)
+        return w
+    if workload == "vqgan16f":
+        # the 3-D conv VQGAN around the codebook, 16 x 128 x 128 videos <-> 4 x 16 x 16 code grids
+        from mebt_b200.vqgan import VQGAN, _Args
+        P, x_host = vqgan_weights_and_video(B, rank)
+        vq = VQGAN(_Args(VQGAN_ARGS))
+        vq.load_state_dict({**vq.state_dict(), **P})
+        vq = vq.to(dev).eval()
+        x_host = x_host.pin_memory()
+        rec_host = torch.empty(B, 3, 16, 128, 128).pin_memory()
+        x_dev = x_host.to(dev)
+        w.tokens_per_step = B * 1024
+
+        def step_device():
+            return vq.decode(vq.encode(x_dev))
+
+        def step_e2e():
+            rec_host.copy_(vq.decode(vq.encode(x_host.to(dev, non_blocking=True))), non_blocking=True)
+        w.device, w.e2e = step_device, step_e2e
+        w.h2d, w.d2h = int(x_host.numel() * 4), int(rec_host.numel() * 4)
         return w
     w.state = synth_weights(cfg)                          # same weights on every rank (seed 0)
     model = build_native_model(cfg, w.state, dropout if workload == "train16f" else 0.0, dev)
@@ -601,7 +653,8 @@ def measure(w, steps, warmup, world, rank, dev, with_cpu_baseline):
     achieved = dom["work"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
     if fam == "gemm":
         roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["tf_sustained"], "traffic": None, "kernel": "gemm_bf16_kernel (tcgen05)",
+                    "frac": achieved / pk["tf_sustained"], "traffic": None,
+                    "kernel": "conv3d_igemm_kernel (tcgen05, 5-D TMA implicit GEMM)" if w.workload == "vqgan16f" else "gemm_bf16_kernel (tcgen05)",
                     "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step)"}
     else:
         roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",

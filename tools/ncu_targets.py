@@ -104,5 +104,28 @@ def main():
     print("done")
 
 
+
+
+def vqgan_targets():
+    """VQGAN convolution kernels at the 16-frame shapes (n_hiddens 32, downsample 4 8 8): full-resolution 32-channel
+    ResBlock convolution, the 256-channel bottleneck convolution, a strided down convolution, one parity class of an up
+    convolution, and the GroupNorm + SiLU + padding pass."""
+    import torch
+    from mebt_b200.vqgan import SamePadConv3d, SamePadConvTranspose3d, to_channels_last, norm_args
+    torch.manual_seed(0)
+    dev = "cuda"
+    for cin, cout, k, stride, dims in ((32, 32, 3, 1, (16, 128, 128)), (256, 256, 3, 1, (4, 16, 16)), (64, 128, 4, 2, (8, 64, 64))):
+        m = SamePadConv3d(cin, cout, k, stride=stride).to(dev)
+        x = to_channels_last(torch.randn(2, cin, *dims, device=dev))
+        gn = torch.nn.GroupNorm(32, cin, eps=1e-6).to(dev)
+        m.forward_cl(x, pre=norm_args(gn), act=1)
+    up = SamePadConvTranspose3d(256, 128, 4, stride=(1, 2, 2)).to(dev)
+    up.forward_cl(to_channels_last(torch.randn(2, 256, 4, 16, 16, device=dev)))
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
-    main()
+    if "--vqgan" in sys.argv:
+        vqgan_targets()
+    else:
+        main()
