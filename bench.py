@@ -499,7 +499,11 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
     if workload == "train16f":
         from mebt_b200.training import TrainState
         model.train()
-        ts = TrainState(model, n_buckets=8 if world > 1 else 4)
+        topt = dict(kv.split("=") for kv in os.environ.get("MEBT_TRAIN_OPTS", "").split(",") if kv)   # experiment knobs
+        ts = TrainState(model, n_buckets=int(topt.get("buckets", 8 if world > 1 else 4)))
+        if "ctas" in topt:
+            ts.update_ctas = int(topt["ctas"])
+        step_kw = dict(overlap_update=bool(int(topt.get("overlap", 0))))
         opt = ts.make_optimizer(lr=1.08e-5, weight_decay=0.01)
         w.ts = ts
         x_cpu, idx_cpu = synth_batch(cfg, B, 100 + rank)  # each rank its own batch (DistributedSampler)
@@ -509,12 +513,12 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
         w.tokens_per_step = B * (N // 2)
 
         def step_device():
-            return ts.train_step(opt, x_dev, idx_dev, t=TRAIN_T, world_size=world)
+            return ts.train_step(opt, x_dev, idx_dev, t=TRAIN_T, world_size=world, **step_kw)
 
         def step_e2e():
             x = x_host.to(dev, non_blocking=True)
             idx = idx_host.to(dev, non_blocking=True)
-            out = ts.train_step(opt, x, idx, t=TRAIN_T, world_size=world)
+            out = ts.train_step(opt, x, idx, t=TRAIN_T, world_size=world, **step_kw)
             loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
 
         def replicas_in_sync():

@@ -428,7 +428,8 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
  * SamePadConvTranspose3d (vqgan.py:381,404) fused with the Normalize + SiLU in front of it (ResBlock.forward :344-349,
  * Encoder / Decoder.final_block).  pad6 = (t_before, t_after, h_before, h_after, w_before, w_after); norm: 0 none,
  * 1 GroupNorm(groups, eps) with weight gamma / bias beta, 2 per-channel affine x * gamma + beta (eval-mode BatchNorm folded);
- * act: 0 none, 1 SiLU.  y has C real channels per position, [C, ldy) zeroed.  workspace: mebt_groupnorm_workspace_bytes.
+ * act: 0 none, 1 SiLU.  y has C real channels per position, [C, ldy) zeroed.  workspace: mebt_groupnorm_workspace_bytes
+ * (partial sums per slab of positions + the per-(batch element, channel) scale / shift; C <= 2048, groups <= 256).
  *
  * mebt_conv3d_ndhwc: implicit-GEMM convolution on the tensor cores over an ALREADY PADDED input,
  *   y[b, t*ystep+yorigin, ..., co] = bias[co] + resid[b,t,h,w,co] + sum_{taps, c} xp[b, t*step + origin + dt, ..., c] * w[co][(dt,dh,dw)][c]

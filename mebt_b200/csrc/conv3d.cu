@@ -276,94 +276,124 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
 }
 
 // ---- GroupNorm statistics: partial (sum, sum of squares) per (batch element, group, slab of positions) ---------------
-// x dense channels-last [B, P, ldc] (P = T*H*W positions); grid (slabs, G, B); partial[b][g][slab][2].
+// x channels-last [B, P, ldc] (P = T*H*W positions); grid (slabs, B); partial[b][g][slab][2].  HBM-bound: one thread reads
+// 16 bytes (8 channels) of a position, a warp whole contiguous rows; the 256 / (ldc / 8) positions a block reads per
+// iteration are summed per thread and channel pair, then per group in a fixed order (reproducible sums).
+constexpr int GN_MAX_SLABS = 64;
+constexpr int GN_MAX_C = 2048;
 __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const __nv_bfloat16* __restrict__ x, long long P, int ldc, int cg,
-                                                                int slabs, float* __restrict__ partial) {
-  const int slab = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+                                                                int G, int slabs, float* __restrict__ partial) {
+  __shared__ float sm1[1024], sm2[1024];
+  const int slab = blockIdx.x, b = blockIdx.y;
+  const int cv = ldc >> 3, R = 256 / cv, Q = cv * 4;         // vectors per position, positions per iteration, channel pairs
+  const int v = threadIdx.x % cv, r = threadIdx.x / cv;
   const long long p0 = P * slab / slabs, p1 = P * (slab + 1) / slabs;
-  const __nv_bfloat16* base = x + (size_t(b) * P) * ldc + g * cg;
-  float s1 = 0.f, s2 = 0.f;
-  // cg is a multiple of 2 (channels are multiples of 64 / 32 groups); one thread walks positions, all channels of the group
-  for (long long pos = p0 + threadIdx.x; pos < p1; pos += 256) {
-    const __nv_bfloat16* row = base + pos * ldc;
-    for (int c = 0; c < cg; c += 2) {
-      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + c));
-      s1 += v.x + v.y;
-      s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, s2));
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (r < R) {
+    const __nv_bfloat16* base = x + (size_t(b) * P) * ldc + v * 8;
+    auto acc = [&](const uint4& u) {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        s1[k] += f.x + f.y;
+        s2[k] = fmaf(f.x, f.x, fmaf(f.y, f.y, s2[k]));
+      }
+    };
+    long long pos = p0 + r;
+    for (; pos + 3LL * R < p1; pos += 4LL * R) {              // four independent 16-byte loads in flight per thread
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + pos * ldc));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (pos + R) * ldc));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (pos + 2LL * R) * ldc));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (pos + 3LL * R) * ldc));
+      acc(u0); acc(u1); acc(u2); acc(u3);
     }
+    for (; pos < p1; pos += R) acc(__ldg(reinterpret_cast<const uint4*>(base + pos * ldc)));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sm1[r * Q + v * 4 + k] = s1[k]; sm2[r * Q + v * 4 + k] = s2[k]; }
   }
-  __shared__ float red[2][8];
-  s1 = warp_sum(s1); s2 = warp_sum(s2);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  for (int g = threadIdx.x; g < G; g += 256) {
     float a = 0.f, c = 0.f;
-    for (int i = 0; i < 8; ++i) { a += red[0][i]; c += red[1][i]; }
-    float* o = partial + ((size_t(b) * gridDim.y + g) * slabs + slab) * 2;
+    const int q0 = g * (cg >> 1), q1 = q0 + (cg >> 1);
+    for (int rr = 0; rr < R; ++rr)
+      for (int q = q0; q < q1; ++q) { a += sm1[rr * Q + q]; c += sm2[rr * Q + q]; }
+    float* o = partial + ((size_t(b) * G + g) * slabs + slab) * 2;
     o[0] = a; o[1] = c;
   }
 }
 
+// per (batch element, channel): y = x * a + s with a = rstd * gamma, s = beta - mean * a; coef[b][c] = (a, s)
+__global__ void __launch_bounds__(256) groupnorm_coef_kernel(const float* __restrict__ partial, int C, int cg, int G, int slabs,
+                                                             float inv_n, float eps, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float2* __restrict__ coef) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cg;
+    const float2* pp = reinterpret_cast<const float2*>(partial) + (size_t(b) * G + g) * slabs;
+    float s1 = 0.f, s2 = 0.f;
+    for (int s = 0; s < slabs; ++s) { const float2 t = pp[s]; s1 += t.x; s2 += t.y; }       // slab order: reproducible
+    const float mean = s1 * inv_n;
+    const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
+    const float a = rstd * gamma[c];
+    coef[size_t(b) * C + c] = make_float2(a, fmaf(-mean, a, beta[c]));
+  }
+}
+
 // ---- y = pad_replicate(act(norm(x))) : the operand of the next convolution -----------------------------------------------
-// x dense [B, T, H, W, ldx]; y [B, T + pt0 + pt1, H + ph0 + ph1, W + pw0 + pw1, ldy] with C real channels (ldy >= C; the
-// channels [C, ldy) are zeroed).  norm: 0 none, 1 GroupNorm from `partial` (G groups, eps), 2 per-channel affine
-// (eval BatchNorm folded into scale / shift).  act: 0 none, 1 SiLU.  One thread = 8 channels of one padded position.
+// x [B, T, H, W, ldx]; y [B, T + pt0 + pt1, H + ph0 + ph1, W + pw0 + pw1, ldy] with C real channels (ldy >= C; the
+// channels [C, ldy) are zeroed).  norm: 0 none, 1 GroupNorm (coef[b][c] from groupnorm_coef_kernel), 2 per-channel affine
+// (eval BatchNorm folded into scale / shift).  act: 0 none, 1 SiLU.  One block = one padded (b, t, h) row of Wp positions,
+// one thread = 8 channels of one position: 16-byte loads / stores, no per-element index arithmetic beyond one division.
 struct PadParams {
   int B, T, H, W, C, ldx, ldy;
   int pt0, ph0, pw0, Tp, Hp, Wp;
-  int norm, act, G, slabs;
-  float eps;
-  const float* partial;
-  const float* gamma;        // norm 1: weight, norm 2: scale
-  const float* beta;         // norm 1: bias, norm 2: shift
+  int norm, act;
+  const float2* coef;        // norm 1: [B][C] (a, s)
+  const float* gamma;        // norm 2: scale
+  const float* beta;         // norm 2: shift
 };
 __global__ void __launch_bounds__(256) pad_norm_act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                            const PadParams p) {
-  const int cv = p.ldy / 8;
-  const long long total = (long long)p.B * p.Tp * p.Hp * p.Wp * cv;
-  const int cg = p.norm == 1 ? p.C / p.G : 1;
-  const float inv_n = p.norm == 1 ? 1.f / (float(p.T) * p.H * p.W * cg) : 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = int(i % cv) * 8;
-    long long r = i / cv;
-    const int w = int(r % p.Wp); r /= p.Wp;
-    const int h = int(r % p.Hp); r /= p.Hp;
-    const int t = int(r % p.Tp); r /= p.Tp;
-    const int b = int(r);
+  extern __shared__ float2 cf[];                               // [C] (a, s) of this batch element
+  const int row = blockIdx.x;
+  const int h = row % p.Hp, t = (row / p.Hp) % p.Tp, b = row / (p.Hp * p.Tp);
+  if (p.norm == 1) {
+    for (int c = threadIdx.x; c < p.C; c += 256) cf[c] = p.coef[size_t(b) * p.C + c];
+    __syncthreads();
+  } else if (p.norm == 2) {
+    for (int c = threadIdx.x; c < p.C; c += 256) cf[c] = make_float2(p.gamma[c], p.beta[c]);
+    __syncthreads();
+  }
+  const int ts = min(max(t - p.pt0, 0), p.T - 1), hs = min(max(h - p.ph0, 0), p.H - 1);
+  const __nv_bfloat16* xs = x + ((size_t(b) * p.T + ts) * p.H + hs) * p.W * size_t(p.ldx);
+  __nv_bfloat16* yd = y + size_t(row) * p.Wp * p.ldy;
+  const int cv = p.ldy >> 3, n = p.Wp * cv;
+  const bool ragged = (p.C & 7) != 0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int w = i / cv, c0 = (i - w * cv) * 8;
     uint4 out = make_uint4(0, 0, 0, 0);
     if (c0 < p.C) {
-      const int ts = min(max(t - p.pt0, 0), p.T - 1), hs = min(max(h - p.ph0, 0), p.H - 1), ws = min(max(w - p.pw0, 0), p.W - 1);
-      const uint4 u = *reinterpret_cast<const uint4*>(x + ((((size_t)b * p.T + ts) * p.H + hs) * p.W + ws) * p.ldx + c0);
-      float v[8];
-      { const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-        v[0] = a.x; v[1] = a.y; v[2] = bb.x; v[3] = bb.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y; }
-      int cur_g = -1;
-      float mean = 0.f, rstd = 1.f;
+      const int ws = min(max(w - p.pw0, 0), p.W - 1);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xs + size_t(ws) * p.ldx + c0));
+      if (p.norm == 0 && p.act == 0 && !ragged) {
+        out = u;
+      } else {
+        float v[8];
+        { const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+          v[0] = a.x; v[1] = a.y; v[2] = bb.x; v[3] = bb.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y; }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int c = c0 + k;
-        float xv = v[k];
-        if (c >= p.C) { v[k] = 0.f; continue; }
-        if (p.norm == 1) {
-          const int g = c / cg;
-          if (g != cur_g) {                                    // partial sums in slab order: reproducible
-            const float* pp = p.partial + (size_t(b) * p.G + g) * p.slabs * 2;
-            float s1 = 0.f, s2 = 0.f;
-            for (int s = 0; s < p.slabs; ++s) { s1 += pp[2 * s]; s2 += pp[2 * s + 1]; }
-            mean = s1 * inv_n;
-            rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
-            cur_g = g;
-          }
-          xv = (xv - mean) * rstd * p.gamma[c] + p.beta[c];
-        } else if (p.norm == 2) {
-          xv = xv * p.gamma[c] + p.beta[c];
+        for (int k = 0; k < 8; ++k) {
+          float xv = v[k];
+          if (ragged && c0 + k >= p.C) { v[k] = 0.f; continue; }
+          if (p.norm != 0) { const float2 as = cf[c0 + k]; xv = fmaf(xv, as.x, as.y); }
+          if (p.act == 1) xv = __fdividef(xv, 1.f + __expf(-xv));
+          v[k] = xv;
         }
-        if (p.act == 1) xv = xv / (1.f + __expf(-xv));
-        v[k] = xv;
+        out = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
       }
-      out = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
-    *reinterpret_cast<uint4*>(y + (size_t)(i / cv) * p.ldy + c0) = out;
+    *reinterpret_cast<uint4*>(yd + size_t(i) * 8) = out;
   }
 }
 
@@ -388,7 +418,10 @@ int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap&
 
 extern "C" {
 
-size_t mebt_groupnorm_workspace_bytes(int B, int groups) { return size_t(B) * groups * 16 * 2 * sizeof(float); }
+size_t mebt_groupnorm_workspace_bytes(int B, int groups) {
+  // partial sums [B][groups][GN_MAX_SLABS][2] + per-channel coefficients [B][GN_MAX_C] float2
+  return size_t(B) * groups * mebt::GN_MAX_SLABS * 2 * sizeof(float) + size_t(B) * mebt::GN_MAX_C * sizeof(float2);
+}
 
 int mebt_pad_norm_act(const void* x, int ldx, void* y, int ldy, int B, int T, int H, int W, int C, const int* pad6, int norm,
                       int act, int groups, float eps, const float* gamma, const float* beta, void* workspace,
@@ -403,24 +436,38 @@ int mebt_pad_norm_act(const void* x, int ldx, void* y, int ldy, int B, int T, in
   p.B = B; p.T = T; p.H = H; p.W = W; p.C = C; p.ldx = ldx; p.ldy = ldy;
   p.pt0 = pad6[0]; p.ph0 = pad6[2]; p.pw0 = pad6[4];
   p.Tp = T + pad6[0] + pad6[1]; p.Hp = H + pad6[2] + pad6[3]; p.Wp = W + pad6[4] + pad6[5];
-  p.norm = norm; p.act = act; p.G = groups; p.slabs = 16; p.eps = eps;
-  p.partial = static_cast<const float*>(workspace); p.gamma = gamma; p.beta = beta;
+  p.norm = norm; p.act = act;
+  p.coef = nullptr; p.gamma = gamma; p.beta = beta;
+  const long long rows = (long long)B * p.Tp * p.Hp;
+  MEBT_REQUIRE(rows < (1LL << 31) && (long long)p.Wp * (ldy / 8) < (1LL << 31), MEBT_ERR_SHAPE, "pad_norm_act: tensor too large");
   if (norm == 1) {
-    MEBT_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 2 == 0 && gamma != nullptr && beta != nullptr, MEBT_ERR_SHAPE,
-                 "pad_norm_act: GroupNorm needs C %% groups == 0 and an even group width (C=%d groups=%d)", C, groups);
+    MEBT_REQUIRE(groups > 0 && groups <= 256 && C % groups == 0 && (C / groups) % 2 == 0 && gamma != nullptr && beta != nullptr,
+                 MEBT_ERR_SHAPE, "pad_norm_act: GroupNorm needs C %% groups == 0 and an even group width (C=%d groups=%d)", C, groups);
+    MEBT_REQUIRE(C <= GN_MAX_C && ldx <= GN_MAX_C, MEBT_ERR_UNSUPPORTED, "pad_norm_act: GroupNorm over at most %d channels", GN_MAX_C);
     MEBT_REQUIRE(workspace != nullptr && workspace_bytes >= mebt_groupnorm_workspace_bytes(B, groups), MEBT_ERR_WORKSPACE,
                  "pad_norm_act: workspace too small");
+    const long long P = (long long)T * H * W;
+    // slabs: enough blocks to keep every SM's memory pipe full, at least 256 positions each
+    int slabs = int(std::min<long long>(GN_MAX_SLABS, std::max<long long>(1, (sm_count() * 4 + B - 1) / B)));
+    slabs = int(std::max<long long>(1, std::min<long long>(slabs, P / 256)));
+    float* partial = static_cast<float*>(workspace);
+    float2* coef = reinterpret_cast<float2*>(partial + size_t(B) * groups * GN_MAX_SLABS * 2);
     LaunchScope ls(FAM_LAYERNORM, double(B) * T * H * W * C * 2.0, st);
-    groupnorm_partial_kernel<<<dim3(16, groups, B), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), (long long)T * H * W, ldx,
-                                                                   C / groups, 16, static_cast<float*>(workspace));
+    groupnorm_partial_kernel<<<dim3(slabs, B), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), P, ldx, C / groups, groups,
+                                                             slabs, partial);
     MEBT_LAUNCH_OK("groupnorm_partial_kernel");
+    groupnorm_coef_kernel<<<B, 256, 0, st>>>(partial, C, C / groups, groups, slabs, 1.f / (float(T) * H * W * (C / groups)), eps,
+                                             gamma, beta, coef);
+    MEBT_LAUNCH_OK("groupnorm_coef_kernel");
+    p.coef = coef;
   } else if (norm == 2) {
     MEBT_REQUIRE(gamma != nullptr && beta != nullptr, MEBT_ERR_SHAPE, "pad_norm_act: affine norm needs scale and shift");
+    MEBT_REQUIRE(C <= GN_MAX_C, MEBT_ERR_UNSUPPORTED, "pad_norm_act: affine norm over at most %d channels", GN_MAX_C);
   }
-  const long long total = (long long)B * p.Tp * p.Hp * p.Wp * (ldy / 8);
+  const long long total = rows * p.Wp * (ldy / 8);
   LaunchScope ls(FAM_LAYERNORM, double(total) * 16.0 * 2.0, st);
-  const int grid = int(std::min<long long>((total + 255) / 256, 148 * 16));
-  pad_norm_act_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), p);
+  pad_norm_act_kernel<<<int(rows), 256, norm != 0 ? size_t(C) * sizeof(float2) : 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), p);
   MEBT_LAUNCH_OK("pad_norm_act_kernel");
   return MEBT_OK;
 }

@@ -34,6 +34,32 @@ def test_pad_norm_act_vs_torch():
     assert torch.equal(plain.float().cpu(), ref2)
 
 
+@pytest.mark.parametrize("C,dims,B", [(128, (4, 16, 24), 2), (256, (2, 8, 8), 3), (192, (3, 16, 16), 1), (64, (8, 64, 64), 2),
+                                       (512, (1, 8, 8), 1)])
+def test_pad_norm_act_group_widths(C, dims, B):
+    """GroupNorm(32, C) + SiLU + replicate padding at group widths 2 .. 16, channel counts whose 16-byte vectors do not
+    divide a 256-thread block (192), several slabs of positions per batch element, and a non-zero mean (the statistics
+    are E[x^2] - E[x]^2 in fp32).  vqgan.py:255-260,344-349,381."""
+    from mebt_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    x = (0.7 + 1.3 * torch.randn(B, *dims, C, generator=g)) * (1 + torch.arange(C) % 5).float()
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    xb = x.to(torch.bfloat16)
+    ref = torch.nn.functional.group_norm(xb.float().permute(0, 4, 1, 2, 3), 32, gamma, beta, 1e-6)
+    ref = ref * torch.sigmoid(ref)
+    ref = torch.nn.functional.pad(ref, (1, 2, 1, 1, 1, 0), mode="replicate").permute(0, 2, 3, 4, 1)
+    got = ops.pad_norm_act(xb.cuda(), (1, 0, 1, 1, 1, 2), norm=1, act=1, groups=32, eps=1e-6, gamma=gamma.cuda(), beta=beta.cuda())
+    assert got.shape == ref.shape
+    assert (got.float().cpu() - ref).abs().max() < 3e-2
+    assert _rel(got.float().cpu(), ref) < 4e-3
+    again = ops.pad_norm_act(xb.cuda(), (1, 0, 1, 1, 1, 2), norm=1, act=1, groups=32, eps=1e-6, gamma=gamma.cuda(), beta=beta.cuda())
+    assert torch.equal(got, again)                                    # fixed summation order
+    # eval-mode BatchNorm folded into a per-channel affine (norm = 2), no activation
+    aff = ops.pad_norm_act(xb.cuda(), (0, 0, 1, 1, 0, 0), norm=2, act=0, gamma=gamma.cuda(), beta=beta.cuda())
+    ref3 = torch.nn.functional.pad((xb.float() * gamma + beta).permute(0, 4, 1, 2, 3), (0, 0, 1, 1, 0, 0), mode="replicate")
+    assert (aff.float().cpu() - ref3.permute(0, 2, 3, 4, 1)).abs().max() <= 2 ** -7 * ref3.abs().max()
+
+
 @pytest.mark.parametrize("cin,cout,k,stride,dims", [(64, 64, 3, (1, 1, 1), (2, 8, 16)), (24, 96, 3, (1, 1, 1), (4, 8, 8)),
                                                     (32, 64, 4, (2, 2, 2), (4, 16, 16)), (64, 320, 4, (1, 2, 2), (4, 16, 32)),
                                                     (128, 8, 1, (1, 1, 1), (2, 8, 8)), (8, 32, 3, (1, 1, 1), (1, 16, 16))])

@@ -107,14 +107,14 @@ def main():
 
 
 def vqgan_targets():
-    """VQGAN convolution kernels at the 16-frame shapes (n_hiddens 32, downsample 4 8 8): full-resolution 32-channel
+    """VQGAN convolution kernels at the 16-frame shapes (n_hiddens 32, downsample 4 8 8): full-resolution 64-channel
     ResBlock convolution, the 256-channel bottleneck convolution, a strided down convolution, one parity class of an up
     convolution, and the GroupNorm + SiLU + padding pass."""
     import torch
     from mebt_b200.vqgan import SamePadConv3d, SamePadConvTranspose3d, to_channels_last, norm_args
     torch.manual_seed(0)
     dev = "cuda"
-    for cin, cout, k, stride, dims in ((32, 32, 3, 1, (16, 128, 128)), (256, 256, 3, 1, (4, 16, 16)), (64, 128, 4, 2, (8, 64, 64))):
+    for cin, cout, k, stride, dims in ((64, 64, 3, 1, (16, 128, 128)), (256, 256, 3, 1, (4, 16, 16)), (64, 128, 4, 2, (8, 64, 64))):
         m = SamePadConv3d(cin, cout, k, stride=stride).to(dev)
         x = to_channels_last(torch.randn(2, cin, *dims, device=dev))
         gn = torch.nn.GroupNorm(32, cin, eps=1e-6).to(dev)
