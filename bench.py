@@ -504,6 +504,7 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
         if "ctas" in topt:
             ts.update_ctas = int(topt["ctas"])
         step_kw = dict(overlap_update=bool(int(topt.get("overlap", 0))))
+        hp_stream = torch.cuda.Stream(device=dev, priority=-1) if int(topt.get("hp", 0)) else None
         opt = ts.make_optimizer(lr=1.08e-5, weight_decay=0.01)
         w.ts = ts
         x_cpu, idx_cpu = synth_batch(cfg, B, 100 + rank)  # each rank its own batch (DistributedSampler)
@@ -513,6 +514,12 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
         w.tokens_per_step = B * (N // 2)
 
         def step_device():
+            if hp_stream is not None:                     # experiment: the step on a high-priority stream
+                hp_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(hp_stream):
+                    out = ts.train_step(opt, x_dev, idx_dev, t=TRAIN_T, world_size=world, **step_kw)
+                torch.cuda.current_stream().wait_stream(hp_stream)
+                return out
             return ts.train_step(opt, x_dev, idx_dev, t=TRAIN_T, world_size=world, **step_kw)
 
         def step_e2e():

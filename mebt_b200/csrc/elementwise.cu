@@ -419,7 +419,13 @@ int adamw_flat(float* p, const float* g, float* m, float* v, void* p16, const un
     LaunchScope ls(FAM_OTHER, double(n) * 30.0, st);
     // max_ctas > 0: a background update - few CTAs trickle through the buffers while latency-bound kernels of another
     // stream (the rest of backward) keep the SMs; the full grid saturates HBM and is for an update nothing overlaps
-    const int grid = max_ctas > 0 && max_ctas < 148 * 8 ? max_ctas : 148 * 8;
+    // max_ctas < 0: a background update of SHORT-LIVED CTAs (-max_ctas 16-byte groups per thread): the grid is as large as
+    // the range, so SM slots keep freeing up for the kernels of a higher-priority stream that arrive meanwhile
+    int grid = max_ctas > 0 && max_ctas < 148 * 8 ? max_ctas : 148 * 8;
+    if (max_ctas < 0) {
+      const long long per_cta = 256LL * std::min(-max_ctas, 16);
+      grid = int(std::min<long long>((n / 4 + per_cta - 1) / per_cta, 1 << 30));
+    }
     adamw_flat_kernel<<<grid, 256, 0, st>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p16), decay, shift, n / 4,
                                                make_adam_scalars(lr, beta1, beta2, eps, wd, step));
   }
