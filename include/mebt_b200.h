@@ -11,6 +11,11 @@
  *   - all pointers are DEVICE pointers into caller-owned (torch-owned) storage unless the name says
  *     `host`; inputs are const, outputs pre-allocated by the caller.
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and never synchronise.
+ *   - library-owned device memory (allocated on first use, per device, never on the data path's steady state):
+ *     the split-K scratch of mebt_gemm_bf16 (96 MiB + tile counters per stream, at most four streams; only shapes
+ *     with few tiles and K >= 2048 use it), 4 KiB of reduction tickets per (device, stream) for the column-sum /
+ *     LayerNorm-parameter reductions (zeroed on that stream), a 4-byte error flag, and the three side streams +
+ *     events of the training engine.  Everything else is the caller's.
  *   - bf16 = __nv_bfloat16 bits, row-major; `ld*` are row strides in ELEMENTS.
  *   - there is no CPU fallback: without an sm_100 device every compute entry point fails.
  */

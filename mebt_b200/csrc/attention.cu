@@ -702,10 +702,9 @@ int latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, in
 #endif
   const bool drop = p.drop.thr != 0;
   auto kernel = drop ? latent_attention_fwd_kernel<true> : latent_attention_fwd_kernel<false>;
-  static bool attr[2] = {false, false};
-  if (!attr[drop]) {
+  static bool attr[2][64] = {};
+  if (first_use_on_device(attr[drop])) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_TOTAL));
-    attr[drop] = true;
   }
   const int base_items = B * H * (((NQ + AT_BQ - 1) / AT_BQ + 1) / 2);
   const int nt = (NK1 + AT_BKV - 1) / AT_BKV + (NK2 + AT_BKV - 1) / AT_BKV;

@@ -470,11 +470,10 @@ int latent_attention_bwd_launch(const void* Q, int ldq, int q_col0, const void* 
   if (NK1 > 0) { rc = get_tensor_map_2d(&t1, KV1, 2, uint64_t(ld1), uint64_t(B) * NK1, uint64_t(ld1) * 2, 64, 128); if (rc) return rc; }
   if (NK2 > 0) { rc = get_tensor_map_2d(&t2, KV2, 2, uint64_t(ld2), uint64_t(B) * NK2, uint64_t(ld2) * 2, 64, 128); if (rc) return rc; }
   static const int groups = [] { const char* e = getenv("MEBT_ATTN_BWD_GROUPS"); return e != nullptr && atoi(e) == 4 ? 4 : 2; }();
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_use_on_device(attr)) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_TOTAL));
     MEBT_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_TOTAL));
-    attr = true;
   }
   BwdParams p;
   p.NQ = NQ; p.H = H; p.NK[0] = NK1; p.NK[1] = NK2;

@@ -91,15 +91,17 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ X, int ld, int r
 // of one stream are serialised; the training backward runs its bias-gradient sums on a second stream).
 int* reduce_counters(cudaStream_t st) {
   static std::mutex mu;
-  static std::map<cudaStream_t, int*> table;
+  static std::map<std::pair<int, cudaStream_t>, int*> table;
   std::lock_guard<std::mutex> lock(mu);
-  auto it = table.find(st);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = table.find({dev, st});
   if (it != table.end()) return it->second;
   int* p = nullptr;
   if (cudaMalloc(&p, 1024 * sizeof(int)) != cudaSuccess) return nullptr;
-  if (cudaMemset(p, 0, 1024 * sizeof(int)) != cudaSuccess) return nullptr;
-  cudaDeviceSynchronize();
-  table[st] = p;
+  // zeroed on the stream that will use them: ordered before its first reduction, no device-wide synchronisation
+  if (cudaMemsetAsync(p, 0, 1024 * sizeof(int), st) != cudaSuccess) { cudaFree(p); return nullptr; }
+  table[{dev, st}] = p;
   return p;
 }
 

@@ -50,6 +50,15 @@ int get_tensor_map_slabs(CUtensorMap* out, const void* ptr, int elem_bytes, uint
                          uint64_t row_stride_bytes, uint32_t box_outer, uint32_t slabs);
 
 int sm_count();
+// cudaFuncSetAttribute is per device: `seen` is the per-call-site record of the devices a kernel was configured on
+inline bool first_use_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
 
 // ---- lightweight in-library accounting (bench.py's gpu_launches and per-kernel roofline numbers) ----------
 enum KernelFamily : int {

@@ -401,10 +401,9 @@ template <int BN>
 int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p, double flops,
                 cudaStream_t st) {
   using L = ConvSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
   }
   LaunchScope ls(FAM_GEMM, flops, st);
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();

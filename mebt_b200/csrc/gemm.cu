@@ -790,10 +790,9 @@ int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda,
     if (rc) return rc;
   }
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
   }
   LaunchScope ls(FAM_GEMM, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
   if constexpr (PAIR) {

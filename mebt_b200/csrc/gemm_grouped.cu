@@ -424,11 +424,10 @@ int gemm_grouped_wgrad_ex(const WgradDescEx* d, int n, const AdamFuseHost* fuse,
     maps.a[s] = maps.a[0]; maps.b[s] = maps.b[0]; maps.c[s] = maps.c[0]; maps.a2[s] = maps.a[0]; maps.b2[s] = maps.b[0];
   }
   p.total_tiles = tiles;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(gemm_grouped_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MEBT_CUDA_OK(cudaFuncSetAttribute(gemm_grouped_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    attr_set = true;
   }
   LaunchScope ls(FAM_GEMM, flops, stream);
   static const int cta_cap = getenv("MEBT_WGRAD_CTAS") != nullptr ? atoi(getenv("MEBT_WGRAD_CTAS")) : 0;   // experiment knob

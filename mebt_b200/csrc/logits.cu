@@ -871,10 +871,9 @@ int mebt_masked_ce(const void* logits, long long ld, int dtype, const int64_t* t
                                                  row_loss, row_rank, static_cast<float*>(dlogits), ld_d, grad_scale);
   else if (dtype == MEBT_DTYPE_BF16 && V % 8 == 0 && V <= CE_T * 64 && ld % 8 == 0 && (dlogits == nullptr || ld_d % 8 == 0) &&
            rows >= 2 * sm_count()) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (first_use_on_device(attr_set)) {
       MEBT_CUDA_OK(cudaFuncSetAttribute(masked_ce_bf16_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_STAGES * CE_ROW_BYTES));
-      attr_set = true;
     }
     const int grid = rows < 2 * sm_count() ? rows : 2 * sm_count();
     masked_ce_bf16_stream_kernel<<<grid, CE_T, CE_STAGES * CE_ROW_BYTES, st>>>(static_cast<const __nv_bfloat16*>(logits), ld, targets,

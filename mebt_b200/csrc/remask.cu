@@ -121,10 +121,9 @@ extern "C" int mebt_remask_sort(const float* score, const float* noise, float ct
   int n_pow2 = 2;
   while (n_pow2 < NT) n_pow2 <<= 1;
   const size_t smem = size_t(n_pow2) * 8;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static bool configured[64] = {};
+  if (smem > 48 * 1024 && first_use_on_device(configured)) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(remask_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(128 * 1024)));
-    configured = 128 * 1024;
   }
   LaunchScope ls(FAM_REMASK, double(B) * (double(NT) * (4.0 + (noise != nullptr ? 4.0 : 0.0) + 16.0) + double(NC) * 16.0),
                  static_cast<cudaStream_t>(stream));

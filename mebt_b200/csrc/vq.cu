@@ -232,10 +232,9 @@ int mebt_vq_argmin(const float* z_channel_first, int batch, int C, int S, const 
                "vq_argmin: workspace too small (%zu < %zu)", workspace_bytes, size_t(M) * 8);
   const size_t smem = (size_t(C) * VQ_BM + VQ_BK * (VQ_BN + 4) + VQ_BM) * sizeof(float);
   MEBT_REQUIRE(smem <= 200 * 1024, MEBT_ERR_UNSUPPORTED, "vq_argmin: embedding_dim %d too large for the smem tile", C);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_use_on_device(attr)) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* packed = static_cast<unsigned long long*>(workspace);
@@ -287,10 +286,9 @@ int mebt_vq_argmin_tc(const float* z_channel_first, int batch, int C, int S, con
   float* zsq = reinterpret_cast<float*>(W + ((size_t(M) * 3 * C * 2 + 255) & ~size_t(255)));
   unsigned long long* packed = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(zsq) + ((size_t(M) * 4 + 255) & ~size_t(255)));
   const size_t smem = size_t(C) * 33 * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_use_on_device(attr)) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(vq_split_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
-    attr = true;
   }
   {
     LaunchScope ls(FAM_VQ, 0.0, st);
