@@ -499,12 +499,7 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
     if workload == "train16f":
         from mebt_b200.training import TrainState
         model.train()
-        topt = dict(kv.split("=") for kv in os.environ.get("MEBT_TRAIN_OPTS", "").split(",") if kv)   # experiment knobs
-        ts = TrainState(model, n_buckets=int(topt.get("buckets", 8 if world > 1 else 4)))
-        if "ctas" in topt:
-            ts.update_ctas = int(topt["ctas"])
-        step_kw = dict(overlap_update=bool(int(topt.get("overlap", 0))))
-        hp_stream = torch.cuda.Stream(device=dev, priority=-1) if int(topt.get("hp", 0)) else None
+        ts = TrainState(model, n_buckets=8 if world > 1 else 4)
         opt = ts.make_optimizer(lr=1.08e-5, weight_decay=0.01)
         w.ts = ts
         x_cpu, idx_cpu = synth_batch(cfg, B, 100 + rank)  # each rank its own batch (DistributedSampler)
@@ -514,18 +509,12 @@ def make_step(workload, cfg, B, dropout, dev, rank, world):
         w.tokens_per_step = B * (N // 2)
 
         def step_device():
-            if hp_stream is not None:                     # experiment: the step on a high-priority stream
-                hp_stream.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(hp_stream):
-                    out = ts.train_step(opt, x_dev, idx_dev, t=TRAIN_T, world_size=world, **step_kw)
-                torch.cuda.current_stream().wait_stream(hp_stream)
-                return out
-            return ts.train_step(opt, x_dev, idx_dev, t=TRAIN_T, world_size=world, **step_kw)
+            return ts.train_step(opt, x_dev, idx_dev, t=TRAIN_T, world_size=world)
 
         def step_e2e():
             x = x_host.to(dev, non_blocking=True)
             idx = idx_host.to(dev, non_blocking=True)
-            out = ts.train_step(opt, x, idx, t=TRAIN_T, world_size=world, **step_kw)
+            out = ts.train_step(opt, x, idx, t=TRAIN_T, world_size=world)
             loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
 
         def replicas_in_sync():

@@ -408,8 +408,11 @@ class TrainState:
                    fused_update=False):
         """fwd + loss + bwd (+ all-reduce) + AdamW + operand refresh.  Returns the loss statistics.
         overlap_update=True (FlatAdamW only) issues the update of each finished chunk of blocks on the side stream while
-        backward continues; measured on B200 at the 16-frame shapes it gains 0.8 % per step (13.81 -> 13.70 ms) because the
-        HBM-bound update slows the latency-bound backward kernels it overlaps, so it is off by default.
+        backward continues.  Measured on B200 at the 16-frame shapes (round 2, 11.3 ms per step without it): as a 48-CTA
+        trickle 13.5 ms (the trickle becomes the critical path), as 96 CTAs with 8 chunks 11.85 ms, as short-lived CTAs
+        over the whole range (`update_ctas = -1`) 11.25 ms, the same with the step on a high-priority stream 11.8 ms: the
+        HBM-bound update slows the latency-bound backward kernels it overlaps by as much as it hides, so it is off by
+        default.
         fused_update=True (FlatAdamW, one GPU, no pending accumulated gradient): AdamW of the blocks' Linear weights inside
         their weight-gradient GEMMs (`mebt_stack_backward_fused`); the gradients of those weights are then not
         materialised in `p.grad`.  Measured on B200 at the 16-frame shapes it LOSES 1.3 ms per step (11.37 -> 12.66 ms):
