@@ -38,16 +38,26 @@ constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int EPI_SLOTS = 4;
 constexpr int EPI_SLOT_BYTES = 128 * 128;
 
-template <int BN>
+// ROW mode (stride 1 along w, output rows of 128 positions): one tile = one output row, and the A operands of ALL the
+// taps along w come from ONE box {64 c, 128 + KW - 1 positions}: tap dw is the same shared-memory rows shifted by dw
+// (descriptor start address + dw * 128 bytes; the 128-byte swizzle is a function of the absolute address, so a shifted
+// start reads what TMA wrote).  A stage then holds KW k-blocks: a third of the L2 -> smem operand traffic of the 64-wide
+// tiles (which is what bounds them) and one barrier hand-off per KW k-blocks instead of one per k-block.
+constexpr int ROW_A_BYTES = 17 * 1024;   // up to 136 rows of 128 bytes
+constexpr int ROW_MAX_KW = 4;
+
+template <int BN, bool ROW = false>
 struct ConvSmem {
-  static constexpr int STAGES = BN == 256 ? 3 : 6;
+  static constexpr int STAGES = ROW ? 3 : (BN == 256 ? 3 : (BN == 128 ? 5 : 6));
   static constexpr int B_TILE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int A_BYTES = ROW ? ROW_A_BYTES : A_TILE_BYTES;
+  static constexpr int STAGE_BYTES = ROW ? ROW_A_BYTES + ROW_MAX_KW * B_TILE_BYTES : A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_SLOTS * EPI_SLOT_BYTES;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
   static constexpr int TOTAL = BIAS_OFFSET + BN * 4 + 1024;
   static_assert(TOTAL <= 232448, "shared memory budget");
+  static_assert(STAGE_BYTES % 1024 == 0, "stages keep the 1024-byte alignment of the swizzle pattern");
 };
 
 struct ConvParams {
@@ -60,6 +70,7 @@ struct ConvParams {
   int YT, YH, YW;             // output step per output position in the destination tensor (transposed convolution: 2) ...
   int Y0T, Y0H, Y0W;          // ... and its origin (the parity)
   int cblocks;                // Cp / 64
+  int base_offset;            // ROW mode: set the descriptor's matrix-base-offset field for the shifted A operands
   int Cout;
   const float* bias;          // [Cout] or nullptr
   const __nv_bfloat16* resid; // dense [B, To, Ho, Wo, ldr] or nullptr (added after the bias)
@@ -90,11 +101,11 @@ __device__ __forceinline__ void locate(const ConvParams& p, int work, int& ni, i
   t0 = ti * p.PT; h0 = hi * p.PH; w0 = wi * p.PW;
 }
 
-template <int BN>
+template <int BN, bool ROW>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
                     const __grid_constant__ CUtensorMap tma_y, const ConvParams p) {
-  using L = ConvSmem<BN>;
+  using L = ConvSmem<BN, ROW>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -140,19 +151,36 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         int ni, b, t0, h0, w0;
         locate(p, work, ni, b, t0, h0, w0);
         const int xt = t0 * p.ST + p.OT, xh = h0 * p.SH + p.OH, xw = w0 * p.SW + p.OW;
-        int kb = 0;
-        for (int dt = 0; dt < p.KT; ++dt)
-          for (int dh = 0; dh < p.KH; ++dh)
-            for (int dw = 0; dw < p.KW; ++dw)
-              for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+        if constexpr (ROW) {
+          const uint32_t stage_tx = uint32_t((128 + p.KW - 1) * 128 + p.KW * L::B_TILE_BYTES);
+          for (int dt = 0; dt < p.KT; ++dt)
+            for (int dh = 0; dh < p.KH; ++dh)
+              for (int cb = 0; cb < p.cblocks; ++cb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sA = smem + stage * L::STAGE_BYTES;
-                uint8_t* sB = sA + A_TILE_BYTES;
-                mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                tma_load_5d(sA, &tma_x, &full_bar[stage], cb * BK, xw + dw, xh + dh, xt + dt, b);   // box {64 c, PW, PH, PT, 1}
-                tma_load_2d(sB, &tma_w, &full_bar[stage], kb * BK, ni * BN);                        // box [64 k][BN n]
+                uint8_t* sB = sA + ROW_A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                tma_load_5d(sA, &tma_x, &full_bar[stage], cb * BK, xw, xh + dh, xt + dt, b);       // box {64 c, 128 + KW - 1, 1, 1, 1}
+                for (int dw = 0; dw < p.KW; ++dw)
+                  tma_load_2d(sB + dw * L::B_TILE_BYTES, &tma_w, &full_bar[stage],
+                              (((dt * p.KH + dh) * p.KW + dw) * p.cblocks + cb) * BK, ni * BN);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
+        } else {
+          int kb = 0;
+          for (int dt = 0; dt < p.KT; ++dt)
+            for (int dh = 0; dh < p.KH; ++dh)
+              for (int dw = 0; dw < p.KW; ++dw)
+                for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+                  mbar_wait(&empty_bar[stage], phase ^ 1);
+                  uint8_t* sA = smem + stage * L::STAGE_BYTES;
+                  uint8_t* sB = sA + A_TILE_BYTES;
+                  mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                  tma_load_5d(sA, &tma_x, &full_bar[stage], cb * BK, xw + dw, xh + dh, xt + dt, b);   // box {64 c, PW, PH, PT, 1}
+                  tma_load_2d(sB, &tma_w, &full_bar[stage], kb * BK, ni * BN);                        // box [64 k][BN n]
+                  if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
       }
     }
   } else if (warp == 1) {
@@ -169,6 +197,26 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
+        if constexpr (ROW) {
+          const int nst = p.KT * p.KH * p.cblocks;
+          for (int st = 0; st < nst; ++st) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t base = smem_u32(smem + stage * L::STAGE_BYTES);
+            for (int dw = 0; dw < p.KW; ++dw) {
+              // tap dw: the same rows, dw positions (128 bytes each) further; B: the tap's own [BN][64] tile
+              const uint32_t a_lo = smem_desc_lo(base + uint32_t(dw) * 128u, 16);
+              const uint32_t b_lo = smem_desc_lo(base + uint32_t(ROW_A_BYTES + dw * L::B_TILE_BYTES), 16);
+              const uint32_t a_hi = desc_hi | (p.base_offset ? (uint32_t(dw) & 7u) << 17 : 0u);
+              umma_bf16_ss_x4<false>(tmem_d, a_lo, b_lo, (UMMA_K * 2) >> 4, (UMMA_K * 2) >> 4, a_hi, desc_hi, idesc,
+                                     (st > 0 || dw > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (st == nst - 1) umma_commit(&tmem_full_bar[acc]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
