@@ -40,8 +40,9 @@ constexpr int EPI_SLOT_BYTES = 128 * 128;
 
 // ROW mode (stride 1 along w, output rows of 128 positions): one tile = one output row, and the A operands of ALL the
 // taps along w come from ONE box {64 c, 128 + KW - 1 positions}: tap dw is the same shared-memory rows shifted by dw
-// (descriptor start address + dw * 128 bytes; the 128-byte swizzle is a function of the absolute address, so a shifted
-// start reads what TMA wrote).  A stage then holds KW k-blocks: a third of the L2 -> smem operand traffic of the 64-wide
+// (descriptor start address + dw * 128 bytes; the 128-byte swizzle is a function of the absolute shared-memory address,
+// so a start that is not 1024-byte aligned reads what TMA wrote - measured: correct with the descriptor's matrix-base-offset
+// field left 0, wrong with it set to (address >> 7) & 7).  A stage then holds KW k-blocks: a third of the L2 -> smem operand traffic of the 64-wide
 // tiles (which is what bounds them) and one barrier hand-off per KW k-blocks instead of one per k-block.
 constexpr int ROW_A_BYTES = 17 * 1024;   // up to 136 rows of 128 bytes
 constexpr int ROW_MAX_KW = 4;
@@ -70,7 +71,6 @@ struct ConvParams {
   int YT, YH, YW;             // output step per output position in the destination tensor (transposed convolution: 2) ...
   int Y0T, Y0H, Y0W;          // ... and its origin (the parity)
   int cblocks;                // Cp / 64
-  int base_offset;            // ROW mode: set the descriptor's matrix-base-offset field for the shifted A operands
   int Cout;
   const float* bias;          // [Cout] or nullptr
   const __nv_bfloat16* resid; // dense [B, To, Ho, Wo, ldr] or nullptr (added after the bias)
@@ -207,8 +207,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
               // tap dw: the same rows, dw positions (128 bytes each) further; B: the tap's own [BN][64] tile
               const uint32_t a_lo = smem_desc_lo(base + uint32_t(dw) * 128u, 16);
               const uint32_t b_lo = smem_desc_lo(base + uint32_t(ROW_A_BYTES + dw * L::B_TILE_BYTES), 16);
-              const uint32_t a_hi = desc_hi | (p.base_offset ? (uint32_t(dw) & 7u) << 17 : 0u);
-              umma_bf16_ss_x4<false>(tmem_d, a_lo, b_lo, (UMMA_K * 2) >> 4, (UMMA_K * 2) >> 4, a_hi, desc_hi, idesc,
+              umma_bf16_ss_x4<false>(tmem_d, a_lo, b_lo, (UMMA_K * 2) >> 4, (UMMA_K * 2) >> 4, desc_hi, desc_hi, idesc,
                                      (st > 0 || dw > 0) ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);
@@ -445,17 +444,17 @@ __global__ void __launch_bounds__(256) pad_norm_act_kernel(const __nv_bfloat16* 
   }
 }
 
-template <int BN>
+template <int BN, bool ROW>
 int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p, double flops,
                 cudaStream_t st) {
-  using L = ConvSmem<BN>;
+  using L = ConvSmem<BN, ROW>;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
-    MEBT_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    MEBT_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel<BN, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   }
   LaunchScope ls(FAM_GEMM, flops, st);
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  MEBT_CUDA_OK(launch_pdl(conv3d_igemm_kernel<BN>, dim3(grid), dim3(CV_THREADS), L::TOTAL, st, tx, tw, ty, p));
+  MEBT_CUDA_OK(launch_pdl(conv3d_igemm_kernel<BN, ROW>, dim3(grid), dim3(CV_THREADS), L::TOTAL, st, tx, tw, ty, p));
   MEBT_LAUNCH_OK("conv3d_igemm_kernel");
   return MEBT_OK;
 }
@@ -541,14 +540,22 @@ int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w,
   memset(&p, 0, sizeof(p));
   // patch: as wide as possible along w, then h, then t (each a power of two dividing the output extent)
   auto pow2_div = [](int n, int cap) { int v = 1; while (v * 2 <= cap && n % (v * 2) == 0) v *= 2; return v; };
-  p.PW = pow2_div(Wo, 16);
-  p.PH = pow2_div(Ho, 128 / p.PW);
-  p.PT = pow2_div(To, 128 / (p.PW * p.PH));
+  const int bn = cout <= 64 ? 64 : (cout <= 128 ? 128 : 256);
+  // ROW mode (see ConvSmem): whole output rows of 128 positions, the taps along w served by one box
+  static const int row_env = [] { const char* e = getenv("MEBT_CONV_ROW"); return e != nullptr ? atoi(e) : 1; }();
+  const bool row = row_env != 0 && bn == 64 && Wo % 128 == 0 && step3[2] == 1 && ystep3[2] == 1 && taps3[2] >= 2 &&
+                   taps3[2] <= ROW_MAX_KW;
+  if (row) {
+    p.PW = 128; p.PH = 1; p.PT = 1;
+  } else {
+    p.PW = pow2_div(Wo, 16);
+    p.PH = pow2_div(Ho, 128 / p.PW);
+    p.PT = pow2_div(To, 128 / (p.PW * p.PH));
+  }
   MEBT_REQUIRE(p.PT * p.PH * p.PW == 128, MEBT_ERR_UNSUPPORTED,
                "conv3d: the output extent %d x %d x %d does not tile into 128-position patches", To, Ho, Wo);
   p.nt_t = To / p.PT; p.nt_h = Ho / p.PH; p.nt_w = Wo / p.PW;
   p.tiles_m = B * p.nt_t * p.nt_h * p.nt_w;
-  const int bn = cout <= 64 ? 64 : 256;
   p.num_n_blocks = (cout + bn - 1) / bn;
   p.total_tiles = p.tiles_m * p.num_n_blocks;
   p.KT = taps3[0]; p.KH = taps3[1]; p.KW = taps3[2];
@@ -571,8 +578,10 @@ int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w,
     const uint64_t dims[5] = {uint64_t(cin), uint64_t(xdims4[3]), uint64_t(xdims4[2]), uint64_t(xdims4[1]), uint64_t(B)};
     const uint64_t strides[4] = {uint64_t(ldx) * 2, uint64_t(xdims4[3]) * ldx * 2, uint64_t(xdims4[2]) * xdims4[3] * ldx * 2,
                                  uint64_t(xdims4[1]) * xdims4[2] * xdims4[3] * ldx * 2};
-    const uint32_t box[5] = {64, uint32_t(p.PW * p.SW), uint32_t(p.PH * p.SH), uint32_t(p.PT * p.ST), 1};
-    const uint32_t es[5] = {1, uint32_t(p.SW), uint32_t(p.SH), uint32_t(p.ST), 1};
+    // ROW: one box = the row's 128 positions + the KW - 1 further ones its last taps read (h / t: a single line)
+    const uint32_t box[5] = {64, uint32_t(row ? 128 + p.KW - 1 : p.PW * p.SW), uint32_t(row ? 1 : p.PH * p.SH),
+                             uint32_t(row ? 1 : p.PT * p.ST), 1};
+    const uint32_t es[5] = {1, uint32_t(row ? 1 : p.SW), uint32_t(row ? 1 : p.SH), uint32_t(row ? 1 : p.ST), 1};
     int rc = get_tensor_map_5d(&tx, xp, dims, strides, box, es);
     if (rc) return rc;
   }
@@ -591,7 +600,10 @@ int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w,
   }
   const double flops = 2.0 * double(p.tiles_m) * 128.0 * double(cout) * double(taps) * double(cin);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return bn == 64 ? launch_conv<64>(tx, tw, ty, p, flops, st) : launch_conv<256>(tx, tw, ty, p, flops, st);
+  if (row) return launch_conv<64, true>(tx, tw, ty, p, flops, st);
+  if (bn == 64) return launch_conv<64, false>(tx, tw, ty, p, flops, st);
+  if (bn == 128) return launch_conv<128, false>(tx, tw, ty, p, flops, st);
+  return launch_conv<256, false>(tx, tw, ty, p, flops, st);
 }
 
 }  // extern "C"

@@ -62,7 +62,12 @@ def test_pad_norm_act_group_widths(C, dims, B):
 
 @pytest.mark.parametrize("cin,cout,k,stride,dims", [(64, 64, 3, (1, 1, 1), (2, 8, 16)), (24, 96, 3, (1, 1, 1), (4, 8, 8)),
                                                     (32, 64, 4, (2, 2, 2), (4, 16, 16)), (64, 320, 4, (1, 2, 2), (4, 16, 32)),
-                                                    (128, 8, 1, (1, 1, 1), (2, 8, 8)), (8, 32, 3, (1, 1, 1), (1, 16, 16))])
+                                                    (128, 8, 1, (1, 1, 1), (2, 8, 8)), (8, 32, 3, (1, 1, 1), (1, 16, 16)),
+                                                    # rows of 128 positions: the taps along w share one TMA box (ROW mode)
+                                                    (64, 64, 3, (1, 1, 1), (2, 4, 128)), (8, 32, 3, (1, 1, 1), (1, 2, 128)),
+                                                    (64, 8, 3, (1, 1, 1), (2, 2, 256)), (128, 64, 3, (1, 1, 1), (1, 3, 128)),
+                                                    # 128-wide output tiles
+                                                    (64, 128, 3, (1, 1, 1), (2, 8, 16)), (128, 128, 4, (2, 2, 2), (4, 16, 16))])
 def test_same_pad_conv3d_vs_torch(cin, cout, k, stride, dims):
     """One SamePadConv3d (vqgan.py:358-381) incl. channel counts that are not multiples of 64 and strided kernels."""
     from mebt_b200.vqgan import SamePadConv3d
