@@ -721,7 +721,7 @@ int latent_attention_fwd(const void* Q, int ldq, int q_col0, const void* KV1, in
   p.part_o = static_cast<float*>(workspace);
   p.part_ml = p.part_o != nullptr ? p.part_o + size_t(splits) * B * H * NQ * AT_HS : nullptr;
   const int n_items = base_items * splits;
-  dim3 grid(n_items < sm_count() ? n_items : sm_count());
+  dim3 grid(n_items < grid_cap() ? n_items : grid_cap());
   {
     LaunchScope ls(FAM_ATTENTION, 4.0 * double(B) * H * double(NQ) * double(NK1 + NK2) * AT_HS,
                    static_cast<cudaStream_t>(stream));

@@ -50,6 +50,14 @@ int get_tensor_map_slabs(CUtensorMap* out, const void* ptr, int elem_bytes, uint
                          uint64_t row_stride_bytes, uint32_t box_outer, uint32_t slabs);
 
 int sm_count();
+// SMs a persistent kernel launched now may occupy: sm_count() unless a GridCapScope is open on this thread (the training
+// backward leaves a share of the SMs to its side-stream weight-gradient launch)
+int grid_cap();
+struct GridCapScope {
+  int prev;
+  explicit GridCapScope(int cap);
+  ~GridCapScope();
+};
 // cudaFuncSetAttribute is per device: `seen` is the per-call-site record of the devices a kernel was configured on
 inline bool first_use_on_device(bool (&seen)[64]) {
   int dev = 0;

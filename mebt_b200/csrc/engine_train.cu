@@ -383,6 +383,10 @@ int mebt_stack_backward_fused(const mebt_layer_t* layers, const mebt_layer_grads
                               const mebt_dropout_t* drop, const mebt_fused_adamw_t* fuse, void* workspace,
                               size_t workspace_bytes, void* stream) {
   using namespace mebt;
+  // experiment knob: SMs the persistent kernels of the data-gradient chain may take (the rest stays with the side-stream
+  // weight-gradient launch, whose grid MEBT_WGRAD_CTAS caps)
+  static const int chain_cap = getenv("MEBT_BWD_CHAIN_SMS") != nullptr ? atoi(getenv("MEBT_BWD_CHAIN_SMS")) : 0;
+  GridCapScope cap_scope(chain_cap);
   // The optimizer step of the blocks' Linear weights inside their weight-gradient GEMMs: every block must then produce
   // each weight's whole gradient in ONE accumulator (no accumulation into earlier gradients, no second launch adding
   // the key|value rows of lt2l: a two-segment problem instead) and must not overwrite bf16 weights a data-gradient GEMM

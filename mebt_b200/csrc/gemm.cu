@@ -797,12 +797,12 @@ int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda,
   LaunchScope ls(FAM_GEMM, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
   if constexpr (PAIR) {
     const int pairs = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
-    int clusters = sm_count() / 2;
+    int clusters = grid_cap() / 2;
     if (clusters > pairs) clusters = pairs;
     MEBT_CUDA_OK(launch_pdl_cluster2(kern, dim3(2 * clusters), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, tc, taux, tin, p));
   } else {
     const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
-    const int grid = tiles < sm_count() ? tiles : sm_count();
+    const int grid = tiles < grid_cap() ? tiles : grid_cap();
     const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, tc, taux, tin, p);
     if (le != cudaSuccess) {
       cudaFuncAttributes fa;

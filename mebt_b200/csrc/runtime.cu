@@ -37,6 +37,14 @@ int sm_count() {
   return cached;
 }
 
+static thread_local int g_grid_cap = 0;
+int grid_cap() {
+  const int n = sm_count();
+  return g_grid_cap > 0 && g_grid_cap < n ? g_grid_cap : n;
+}
+GridCapScope::GridCapScope(int cap) : prev(g_grid_cap) { if (cap > 0) g_grid_cap = cap; }
+GridCapScope::~GridCapScope() { g_grid_cap = prev; }
+
 // ---- launch accounting / per-family event timing ------------------------------------------------
 struct ProfRec { cudaEvent_t e0, e1; int family; double work; };
 static std::mutex g_prof_mu;
