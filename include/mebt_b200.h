@@ -440,7 +440,10 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
  *   y[b, t*ystep+yorigin, ..., co] = bias[co] + resid[b,t,h,w,co] + sum_{taps, c} xp[b, t*step + origin + dt, ..., c] * w[co][(dt,dh,dw)][c]
  * w: bf16 [cout][taps * ceil64(cin)] (zero padded per tap).  nn.Conv3d: taps = kernel, step = stride.  nn.ConvTranspose3d
  * (kernel 4, stride 2): one launch per output parity with 2 taps, origin = ystep-origin = parity, ystep = 2 (the caller
- * packs the matching kernel slices).  odims3 = positions computed per dimension (must tile into 128-position patches). */
+ * packs the matching kernel slices).  odims3 = positions computed per dimension (must tile into 128-position patches).
+ * Window mode (cin = 64 > ldx, one tap and unit step along w): the K slice of a position is the 64 consecutive ELEMENTS from
+ * its first channel, i.e. the 64 / ldx positions from it on - the taps along w of a few-channel input (the RGB video) packed
+ * into one k-block; w: [cout][taps_t * taps_h][(dw, c)], zero where dw >= the kernel width; rows padded by 64 / ldx - 1. */
 size_t mebt_groupnorm_workspace_bytes(int B, int groups);
 int mebt_pad_norm_act(const void* x, int ldx, void* y, int ldy, int B, int T, int H, int W, int C, const int* pad6, int norm,
                       int act, int groups, float eps, const float* gamma, const float* beta, void* workspace,

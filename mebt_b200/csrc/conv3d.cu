@@ -527,8 +527,15 @@ int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w,
   using namespace mebt;
   const int B = xdims4[0];
   const int To = odims3[0], Ho = odims3[1], Wo = odims3[2];
-  MEBT_REQUIRE(B > 0 && To > 0 && Ho > 0 && Wo > 0 && cin > 0 && cout > 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cin && ldy >= cout &&
+  // WINDOW mode (cin = 64 > ldx): the 64-element K slice of a position runs on into the following positions of its row
+  // (ldx channels each) - the taps along w of a few-channel input packed into ONE k-block: taps3[2] must be 1 and the
+  // weights hold [cout][taps][(dw, c)] with dw < 64 / ldx.  The caller pads the row so that every window stays inside it.
+  const bool window = cin > ldx;
+  const int wpos = window ? cin / ldx : 1;
+  MEBT_REQUIRE(B > 0 && To > 0 && Ho > 0 && Wo > 0 && cin > 0 && cout > 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldy >= cout &&
                cout % 8 == 0 && ydims4[0] == B, MEBT_ERR_SHAPE, "conv3d: bad shape (channel counts / strides must be multiples of 8)");
+  MEBT_REQUIRE(!window || (cin == 64 && taps3[2] == 1 && step3[2] == 1 && (odims3[2] - 1) + origin3[2] + wpos <= xdims4[3]),
+               MEBT_ERR_SHAPE, "conv3d: ldx < cin is the window mode (cin = 64, one tap and unit step along w, rows padded by 64 / ldx - 1)");
   for (int d = 0; d < 3; ++d) {
     MEBT_REQUIRE(taps3[d] >= 1 && taps3[d] <= 4 && step3[d] >= 1 && step3[d] <= 2 && ystep3[d] >= 1 && ystep3[d] <= 2 &&
                  origin3[d] >= 0 && yorigin3[d] >= 0, MEBT_ERR_UNSUPPORTED, "conv3d: taps 1-4, steps 1-2");
@@ -543,7 +550,7 @@ int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w,
   const int bn = cout <= 64 ? 64 : (cout <= 128 ? 128 : 256);
   // ROW mode (see ConvSmem): whole output rows of 128 positions, the taps along w served by one box
   static const int row_env = [] { const char* e = getenv("MEBT_CONV_ROW"); return e != nullptr ? atoi(e) : 1; }();
-  const bool row = row_env != 0 && bn == 64 && Wo % 128 == 0 && step3[2] == 1 && ystep3[2] == 1 && taps3[2] >= 2 &&
+  const bool row = row_env != 0 && bn == 64 && Wo % 128 == 0 && step3[2] == 1 && ystep3[2] == 1 && taps3[2] >= 1 &&
                    taps3[2] <= ROW_MAX_KW;
   if (row) {
     p.PW = 128; p.PH = 1; p.PT = 1;
@@ -575,7 +582,7 @@ int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w,
   const uint64_t Kp = uint64_t(taps) * p.cblocks * 64;
   CUtensorMap tx, tw, ty;
   {
-    const uint64_t dims[5] = {uint64_t(cin), uint64_t(xdims4[3]), uint64_t(xdims4[2]), uint64_t(xdims4[1]), uint64_t(B)};
+    const uint64_t dims[5] = {uint64_t(cin), uint64_t(xdims4[3] - (wpos - 1)), uint64_t(xdims4[2]), uint64_t(xdims4[1]), uint64_t(B)};
     const uint64_t strides[4] = {uint64_t(ldx) * 2, uint64_t(xdims4[3]) * ldx * 2, uint64_t(xdims4[2]) * xdims4[3] * ldx * 2,
                                  uint64_t(xdims4[1]) * xdims4[2] * xdims4[3] * ldx * 2};
     // ROW: one box = the row's 128 positions + the KW - 1 further ones its last taps read (h / t: a single line)
@@ -598,7 +605,8 @@ int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w,
     int rc = get_tensor_map_5d(&ty, y, dims, strides, box, es);
     if (rc) return rc;
   }
-  const double flops = 2.0 * double(p.tiles_m) * 128.0 * double(cout) * double(taps) * double(cin);
+  // window mode: counted as one tap of ldx channels per window (the zero-weighted slots are not work)
+  const double flops = 2.0 * double(p.tiles_m) * 128.0 * double(cout) * double(taps) * double(window ? ldx : cin);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (row) return launch_conv<64, true>(tx, tw, ty, p, flops, st);
   if (bn == 64) return launch_conv<64, false>(tx, tw, ty, p, flops, st);

@@ -109,6 +109,7 @@ class SamePadConv3d(nn.Module):
         self.padding_type = padding_type
         self.conv = nn.Conv3d(in_channels, out_channels, kernel_size, stride=stride, padding=0, bias=bias)
         self._packed = _Packed()
+        self._packed_w = _Packed()
 
     def _operands(self):
         conv = self.conv
@@ -125,9 +126,37 @@ class SamePadConv3d(nn.Module):
             return wp.reshape(cop, -1).to(torch.bfloat16).contiguous(), b.contiguous()
         return self._packed.get([conv.weight] + ([conv.bias] if conv.bias is not None else []), build)
 
+    def _window(self, x):
+        """Few-channel input (the RGB video), unit strides, output rows of 128 positions: the taps along w are packed
+        into one 64-element K slice (8 positions x 8 channels; `mebt_conv3d_ndhwc` window mode)."""
+        return (self.conv.in_channels <= 8 and x.shape[4] == 8 and self.stride == (1, 1, 1) and self.kernel_size[2] <= 8
+                and x.shape[3] % 128 == 0 and self.conv.out_channels <= 64)
+
+    def _operands_window(self):
+        conv = self.conv
+
+        def build():
+            w = conv.weight.detach().float()                                 # [Cout, Cin, kt, kh, kw]
+            co, ci, kt, kh, kw = w.shape
+            cop = _ceil(co, 8)
+            wp = torch.zeros(cop, kt, kh, 64, device=w.device)
+            for dw in range(kw):
+                wp[:co, :, :, dw * 8:dw * 8 + ci] = w[..., dw].permute(0, 2, 3, 1)
+            b = torch.zeros(cop, device=w.device)
+            if conv.bias is not None:
+                b[:co] = conv.bias.detach().float()
+            return wp.reshape(cop, -1).to(torch.bfloat16).contiguous(), b.contiguous()
+        return self._packed_w.get([conv.weight] + ([conv.bias] if conv.bias is not None else []), build)
+
     def forward_cl(self, x, pre=None, act=0, resid=None):
-        w, b = self._operands()
         pads = self.pads
+        if self._window(x):
+            w, b = self._operands_window()
+            kt, kh, kw = self.kernel_size
+            xp = ops.pad_norm_act(x, (pads[0][0], pads[0][1], pads[1][0], pads[1][1], pads[2][0], pads[2][1] + 8 - kw), act=act,
+                                  **(pre or {}))
+            return ops.conv3d_ndhwc(xp, w, 64, w.shape[0], (kt, kh, 1), (1, 1, 1), tuple(x.shape[1:4]), bias=b, resid=resid)
+        w, b = self._operands()
         xp = ops.pad_norm_act(x, (pads[0][0], pads[0][1], pads[1][0], pads[1][1], pads[2][0], pads[2][1]), act=act,
                               **(pre or {}))
         odims = tuple(d // s for d, s in zip(x.shape[1:4], self.stride))
