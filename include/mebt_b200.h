@@ -438,7 +438,7 @@ int mebt_stack_backward_dropout(const mebt_layer_t* layers, const mebt_layer_gra
  *
  * mebt_conv3d_ndhwc: implicit-GEMM convolution on the tensor cores over an ALREADY PADDED input,
  *   y[b, t*ystep+yorigin, ..., co] = bias[co] + resid[b,t,h,w,co] + sum_{taps, c} xp[b, t*step + origin + dt, ..., c] * w[co][(dt,dh,dw)][c]
- * w: bf16 [cout][taps * ceil64(cin)] (zero padded per tap).  nn.Conv3d: taps = kernel, step = stride.  nn.ConvTranspose3d
+ * w: bf16 [ceil64(cout)][taps * ceil64(cin)] (zero padded per tap; zero rows behind cout).  nn.Conv3d: taps = kernel, step = stride.  nn.ConvTranspose3d
  * (kernel 4, stride 2): one launch per output parity with 2 taps, origin = ystep-origin = parity, ystep = 2 (the caller
  * packs the matching kernel slices).  odims3 = positions computed per dimension (must tile into 128-position patches).
  * Window mode (cin = 64 > ldx, one tap and unit step along w): the K slice of a position is the 64 consecutive ELEMENTS from

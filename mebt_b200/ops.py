@@ -484,7 +484,7 @@ def pad_norm_act(x, pad6, norm=0, act=0, groups=32, eps=1e-6, gamma=None, beta=N
 def conv3d_ndhwc(xp, w_packed, cin, cout, taps, step, odims, bias=None, resid=None, out=None, origin=(0, 0, 0),
                  ystep=(1, 1, 1), yorigin=(0, 0, 0)):
     """Implicit-GEMM 3-D convolution over an already padded channels-last input (mebt_conv3d_ndhwc).
-    xp [B, Tp, Hp, Wp, C]; w_packed bf16 [cout, prod(taps) * ceil64(cin)]; odims = (To, Ho, Wo) positions computed; they
+    xp [B, Tp, Hp, Wp, C]; w_packed bf16 [ceil64(cout), prod(taps) * ceil64(cin)] (zero rows behind cout); odims = (To, Ho, Wo) positions computed; they
     are written to out[b, t * ystep + yorigin, ...] (out defaults to a dense [B, To, Ho, Wo, cout] tensor)."""
     _need_cuda(xp, w_packed, resid)
     B = xp.shape[0]

@@ -118,12 +118,12 @@ class SamePadConv3d(nn.Module):
             w = conv.weight.detach().float()                                 # [Cout, Cin, kt, kh, kw]
             co, ci = w.shape[:2]
             cp, cop = _ceil(ci, 64), _ceil(co, 8)
-            wp = torch.zeros(cop, *w.shape[2:], cp, device=w.device)
+            wp = torch.zeros(_ceil(cop, 64), *w.shape[2:], cp, device=w.device)     # rows in whole 64-wide tiles (no TMA fill)
             wp[:co, ..., :ci] = w.permute(0, 2, 3, 4, 1)
             b = torch.zeros(cop, device=w.device)
             if conv.bias is not None:
                 b[:co] = conv.bias.detach().float()
-            return wp.reshape(cop, -1).to(torch.bfloat16).contiguous(), b.contiguous()
+            return wp.reshape(wp.shape[0], -1).to(torch.bfloat16).contiguous(), b.contiguous()
         return self._packed.get([conv.weight] + ([conv.bias] if conv.bias is not None else []), build)
 
     def _window(self, x):
@@ -139,13 +139,13 @@ class SamePadConv3d(nn.Module):
             w = conv.weight.detach().float()                                 # [Cout, Cin, kt, kh, kw]
             co, ci, kt, kh, kw = w.shape
             cop = _ceil(co, 8)
-            wp = torch.zeros(cop, kt, kh, 64, device=w.device)
+            wp = torch.zeros(_ceil(cop, 64), kt, kh, 64, device=w.device)
             for dw in range(kw):
                 wp[:co, :, :, dw * 8:dw * 8 + ci] = w[..., dw].permute(0, 2, 3, 1)
             b = torch.zeros(cop, device=w.device)
             if conv.bias is not None:
                 b[:co] = conv.bias.detach().float()
-            return wp.reshape(cop, -1).to(torch.bfloat16).contiguous(), b.contiguous()
+            return wp.reshape(wp.shape[0], -1).to(torch.bfloat16).contiguous(), b.contiguous()
         return self._packed_w.get([conv.weight] + ([conv.bias] if conv.bias is not None else []), build)
 
     def forward_cl(self, x, pre=None, act=0, resid=None):
@@ -155,12 +155,12 @@ class SamePadConv3d(nn.Module):
             kt, kh, kw = self.kernel_size
             xp = ops.pad_norm_act(x, (pads[0][0], pads[0][1], pads[1][0], pads[1][1], pads[2][0], pads[2][1] + 8 - kw), act=act,
                                   **(pre or {}))
-            return ops.conv3d_ndhwc(xp, w, 64, w.shape[0], (kt, kh, 1), (1, 1, 1), tuple(x.shape[1:4]), bias=b, resid=resid)
+            return ops.conv3d_ndhwc(xp, w, 64, b.shape[0], (kt, kh, 1), (1, 1, 1), tuple(x.shape[1:4]), bias=b, resid=resid)
         w, b = self._operands()
         xp = ops.pad_norm_act(x, (pads[0][0], pads[0][1], pads[1][0], pads[1][1], pads[2][0], pads[2][1]), act=act,
                               **(pre or {}))
         odims = tuple(d // s for d, s in zip(x.shape[1:4], self.stride))
-        return ops.conv3d_ndhwc(xp, w, self.conv.in_channels, w.shape[0], self.kernel_size, self.stride, odims, bias=b,
+        return ops.conv3d_ndhwc(xp, w, self.conv.in_channels, b.shape[0], self.kernel_size, self.stride, odims, bias=b,
                                 resid=resid)
 
     def forward(self, x):
@@ -210,9 +210,9 @@ class SamePadConvTranspose3d(nn.Module):
                         idx = [[3 - p - 2 * d for d in range(2)] if s == 2 else [3 - d for d in range(4)]
                                for p, s in zip(par, self.stride)]
                         sub = w[:, :, idx[0]][:, :, :, idx[1]][:, :, :, :, idx[2]]          # [Cin, Cout, nt, nh, nw]
-                        wp = torch.zeros(cop, *sub.shape[2:], cp, device=w.device)
+                        wp = torch.zeros(_ceil(cop, 64), *sub.shape[2:], cp, device=w.device)
                         wp[:co, ..., :ci] = sub.permute(1, 2, 3, 4, 0)
-                        classes.append((par, tuple(sub.shape[2:]), wp.reshape(cop, -1).to(torch.bfloat16).contiguous()))
+                        classes.append((par, tuple(sub.shape[2:]), wp.reshape(wp.shape[0], -1).to(torch.bfloat16).contiguous()))
             return classes, b.contiguous()
         return self._packed.get([convt.weight] + ([convt.bias] if convt.bias is not None else []), build)
 

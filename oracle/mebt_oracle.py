@@ -427,16 +427,23 @@ def draft_and_revise(P, cfg, x, rng, n_draft=8, draft_t=1.0, draft_k=None, draft
 
 
 def sample_maskgit(P, cfg, x, rng, temperature=1.0, top_k=None, top_p=None, n_steps=8, strategy="maskgit",
-                   context_temperature=4.5, schedule_name="cosine"):
-    """Net2NetTransformer.sample, transformer.py:353-447 (ctemp_schedule='linear', edit=False)."""
+                   context_temperature=4.5, schedule_name="cosine", context_indices=None, target_indices=None, edit=False):
+    """Net2NetTransformer.sample, transformer.py:353-447 (ctemp_schedule='linear').  With `context_indices` /
+    `target_indices` the loop starts from that split (:387-389); `edit=True` sizes the mask schedule by the number of
+    TARGETS instead of the sequence length (:373-376,399) - the sliding-window extrapolation of
+    sample_vqgan_transformer_videos.py:95-157 re-samples only the new frames."""
     B = x.shape[0]
     x = x.reshape(B, -1)
     N = x.shape[1]
-    ctx_idx = torch.empty(B, 0, dtype=torch.long)
-    tgt_idx = torch.arange(N).repeat(B, 1)
+    if context_indices is None:
+        ctx_idx = torch.empty(B, 0, dtype=torch.long)
+        tgt_idx = torch.arange(N).repeat(B, 1)
+    else:
+        ctx_idx, tgt_idx = context_indices.clone(), target_indices.clone()
+    edit_N = tgt_idx.shape[1] if edit else N
     for t_next in np.linspace(0, 1, n_steps + 1)[1:]:
         t = torch.full((B,), fill_value=t_next)                      # float32 (transformer.py:398)
-        n_masked_t = torch.ceil(schedule(schedule_name, t) * N)
+        n_masked_t = torch.ceil(schedule(schedule_name, t) * edit_N)
         if int((n_masked_t > tgt_idx.shape[-1]).sum()) == B:
             continue
         logits = reconstruct_mask(P, cfg, x, ctx_idx, tgt_idx)

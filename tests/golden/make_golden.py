@@ -250,6 +250,28 @@ def gen_entp(cfg_name, B, wseed, seed):
     save(f"entp_{cfg_name}", cfg, **arrays)
 
 
+def gen_edit(cfg_name, B, wseed, seed):
+    """`sample(..., context_indices, target_indices, edit=...)` (transformer.py:373-376,387-389,399): the call the sliding
+    window of `extrapolate()` makes (sample_vqgan_transformer_videos.py:95-157) - a given context that is never rewritten,
+    and with edit=True a mask schedule sized by the number of targets."""
+    cfg = CONFIGS[cfg_name]
+    model, _ = build_reference(cfg, "cosine", wseed)
+    N = int(np.prod(cfg["shape"]))
+    arrays = dict(wseed=wseed, seed=seed, B=B)
+    for tag, edit, steps, n_keep in (("a", True, 5, 192), ("b", True, 4, 64), ("c", False, 6, 128)):
+        g = torch.Generator().manual_seed(7)
+        x0 = torch.randint(0, cfg["vocab_size"], (B, N), generator=g)
+        ctx0 = torch.stack([torch.randperm(n_keep, generator=g) for _ in range(B)])
+        tgt0 = torch.stack([n_keep + torch.randperm(N - n_keep, generator=g) for _ in range(B)])
+        torch.manual_seed(seed)
+        ids, ctx, tgt = model.sample(x0.view(B, *cfg["shape"]), None, temperature=1.0, top_k=None, top_p=None, n_steps=steps,
+                                     context_indices=ctx0, target_indices=tgt0, strategy="maskgit", context_temperature=4.5,
+                                     edit=edit)
+        arrays.update({f"{tag}_edit": int(edit), f"{tag}_steps": steps, f"{tag}_keep": n_keep, f"{tag}_x0": x0, f"{tag}_ctx0": ctx0,
+                       f"{tag}_tgt0": tgt0, f"{tag}_ids": ids, f"{tag}_ctx": ctx, f"{tag}_tgt": tgt})
+    save(f"edit_{cfg_name}", cfg, **arrays)
+
+
 def gen_sample_from_logits():
     """sample_from_logits / top-k / top-p / gumbel on random logits: ids + probs digests."""
     from mebt.transformer import sample_from_logits
@@ -505,6 +527,7 @@ def main():
     gen_sampling("micro", 2, wseed=1, seed=9)
     gen_sampling("tiny", 2, wseed=1, seed=9)
     gen_entp("micro", 2, wseed=1, seed=13)
+    gen_edit("micro", 2, wseed=1, seed=47)
     gen_pipelines()
 
 
@@ -517,6 +540,12 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "pipelines":
         sys.path.insert(1, str(REPO))
         gen_pipelines()
+    elif len(sys.argv) > 1 and sys.argv[1] == "edit":        # only the fixture of the fixed-context / edit sampling loop
+        install_stubs()
+        sys.path.insert(0, REF)
+        sys.path.insert(1, str(REPO))
+        torch.set_num_threads(8)
+        gen_edit("micro", 2, wseed=1, seed=47)
     elif len(sys.argv) > 1 and sys.argv[1] == "entp":        # only the fixture added in round 2
         install_stubs()
         sys.path.insert(0, REF)

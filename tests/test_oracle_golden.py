@@ -173,6 +173,25 @@ def test_entp_sampler_bit_exact():
         assert (tgt.numpy() == z[f"entp_{strat}_tgt"]).all(), strat
 
 
+def test_sample_with_fixed_context_and_edit_bit_exact():
+    """oracle.sample_maskgit(context_indices, target_indices, edit) against the unmodified reference's
+    `sample(..., edit=True / False)` from a given context (fixture edit_micro.npz; transformer.py:373-376,387-389): the
+    sliding-window call of `extrapolate()`.  Ids, final context and target index tensors bit for bit."""
+    z, cfg = load_golden("edit_micro")
+    P = O.make_weights(cfg, int(z["wseed"]))
+    seed = int(z["seed"])
+    for tag in ("a", "b", "c"):
+        x0, ctx0, tgt0 = (torch.from_numpy(z[f"{tag}_{k}"]) for k in ("x0", "ctx0", "tgt0"))
+        ids, ctx, tgt = O.sample_maskgit(P, cfg, x0, O.TorchRng(seed), n_steps=int(z[f"{tag}_steps"]), strategy="maskgit",
+                                         context_temperature=4.5, schedule_name="cosine", context_indices=ctx0,
+                                         target_indices=tgt0, edit=bool(z[f"{tag}_edit"]))
+        assert (ids.numpy() == z[f"{tag}_ids"]).all(), tag
+        assert (ctx.numpy() == z[f"{tag}_ctx"]).all(), tag
+        assert (tgt.numpy() == z[f"{tag}_tgt"]).all(), tag
+        keep = int(z[f"{tag}_keep"])
+        assert (ids.numpy()[:, :keep] == z[f"{tag}_x0"][:, :keep]).all()
+
+
 def test_codebook_bit_exact():
     z, _ = load_golden("codebook")
     torch.manual_seed(int(z["cb_seed"]))

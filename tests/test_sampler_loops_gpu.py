@@ -155,6 +155,36 @@ def test_sample_loop_teacher_forced(micro, strategy, steps, T, k, ctemp):
     assert torch.equal(ids.cpu(), ref_ids) and torch.equal(ctx.cpu(), ref_ctx) and torch.equal(tgt.cpu(), ref_tgt)
 
 
+@pytest.mark.parametrize("edit,steps,n_keep", [(True, 5, 192), (True, 4, 64), (False, 6, 128)])
+def test_sample_loop_with_fixed_context_and_edit_teacher_forced(micro, edit, steps, n_keep):
+    """`sample(..., context_indices, target_indices, edit=True)` - the call `extrapolate()` makes for every window of a
+    long video (sample_vqgan_transformer_videos.py:95-157): the first `n_keep` tokens are given context, only the rest is
+    re-sampled, and with `edit` the schedule counts masked tokens against the number of TARGETS (transformer.py:373-376).
+    Teacher-forced like the loops above: every step's logits within tolerance, then ids / masks bit for bit."""
+    from oracle import mebt_oracle as O
+    cfg, P, model = micro
+    B, N = 2, 256
+    g = torch.Generator().manual_seed(7)
+    x0 = torch.randint(0, cfg["vocab_size"], (B, N), generator=g)
+    ctx0 = torch.stack([torch.randperm(n_keep, generator=g) for _ in range(B)])          # kept frames, in some order
+    tgt0 = torch.stack([n_keep + torch.randperm(N - n_keep, generator=g) for _ in range(B)])
+    ref_ids, ref_ctx, ref_tgt = O.sample_maskgit(P, cfg, x0, O.TorchRng(47), temperature=1.0, n_steps=steps, strategy="maskgit",
+                                                 context_temperature=4.5, schedule_name="cosine", context_indices=ctx0,
+                                                 target_indices=tgt0, edit=edit)
+    teacher = Teacher(model, P, cfg, 1.0, None, None, entropy=False)
+    teacher.install()
+    try:
+        torch.manual_seed(47)
+        ids, ctx, tgt = model.sample(x0.cuda(), None, 1.0, None, None, n_steps=steps, strategy="maskgit", context_temperature=4.5,
+                                     context_indices=ctx0.cuda(), target_indices=tgt0.cuda(), edit=edit)
+    finally:
+        teacher.remove()
+    assert teacher.steps >= 2
+    assert torch.equal(ids.cpu(), ref_ids) and torch.equal(ctx.cpu(), ref_ctx) and torch.equal(tgt.cpu(), ref_tgt)
+    assert torch.equal(ids.cpu()[:, :n_keep], x0[:, :n_keep])                             # the given context is never rewritten
+    assert torch.equal(ctx.cpu()[:, :n_keep], ctx0)
+
+
 @pytest.mark.parametrize("strategy,steps", [("maskgit", 5), ("random", 4), ("bootstrap", 3)])
 def test_entp_sample_loop_teacher_forced(micro, strategy, steps):
     from oracle import mebt_oracle as O
