@@ -76,6 +76,7 @@ struct GemmParams {
   float* partials;
   int* counters;
   int pair;                            // host-side only: launch the cta_group::2 (SM pair) variant
+  int dual;                            // host-side only: launch the two-issuer variant (DUAL, 128-wide tiles)
   DropKey drop;                        // residual-site dropout applied to (acc + bias) before the residual add (thr 0: off)
 #ifdef MEBT_GEMM_TRACE
   long long* trace;                    // [grid][8] cycle counters (tools/gemm_bench.cu)
@@ -124,8 +125,14 @@ struct SmemLayout {
 // Handshake: both CTAs' TMA loads complete on the LEADER's full barrier; the leader's tcgen05.commit (multicast)
 // releases the stage in both CTAs and publishes the accumulator to both epilogues; both epilogues arrive on the
 // leader's tmem_empty barrier.
-template <int BN, bool A_MN, bool B_MN, int STAGES, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// DUAL (128-wide tiles, one CTA per tile): TWO MMA-issuing threads (warp 1 and warp 6).  One issuer spends ~520 clk per
+// k-block on its barrier wait + tcgen05.commit while a 128-wide k-block is 256 clk of tensor work (tools/mma_probe.cu), so
+// the main loop is hand-off-bound.  Issuer j takes the k-blocks with (index in the tile) % 2 == j and accumulates them in
+// ITS OWN TMEM accumulator; the epilogue adds the two halves.  The summation order is fixed (even k-blocks in order, odd
+// k-blocks in order, one final add), so results stay bitwise reproducible - two issuers on ONE accumulator would make the
+// order depend on their interleaving.
+template <int BN, bool A_MN, bool B_MN, int STAGES, bool PAIR, bool DUAL = false>
+__global__ void __launch_bounds__(DUAL ? GEMM_THREADS + 32 : GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_aux,
                  const __grid_constant__ CUtensorMap tma_in, const GemmParams p) {
@@ -175,7 +182,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     n0 = ni * BN;
   };
   int* split_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);
-  constexpr uint32_t TMEM_COLS = 2 * BN;   // 128, 256 or 512 (power of two >= 32)
+  static_assert(!DUAL || (!PAIR && BN <= 128), "DUAL: one CTA per tile, two accumulator halves of <= 128 columns");
+  constexpr uint32_t ACC_STRIDE = DUAL ? 2 * BN : BN;      // TMEM columns per accumulator buffer
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;           // 128, 256 or 512 (power of two >= 32)
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tma_a);
@@ -187,7 +196,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_full_bar[s], DUAL ? 2 : 1);       // DUAL: each issuer commits its half
       mbar_init(&tmem_empty_bar[s], PAIR ? 256 : 128);   // pair: the leader waits for both CTAs' epilogues
     }
     fence_barrier_init();
@@ -269,9 +278,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       TR_FLUSH(0, 1);
     }
+  } else if (DUAL && (warp == 1 || warp == 6)) {
+    // ================= the two MMA issuers of the DUAL variant =================
+    if (lane == 0) {
+      const uint32_t j = warp == 6 ? 1u : 0u;                 // this issuer's k-block parity and accumulator half
+      const uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0) &
+                             (p.fp16_in ? ~((1u << 7) | (1u << 10)) : ~0u);
+      constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), A_MN ? BK * 128 : 16);
+      const uint32_t b_off = uint32_t(A_TILE_BYTES >> 4) + ((uint32_t((B_MN ? BK * 128 : 16) >> 4) - uint32_t((A_MN ? BK * 128 : 16) >> 4)) << 16);
+      const uint32_t nkb = uint32_t(p.num_k_blocks);          // no split-K in this variant
+      uint32_t cnt = 0;                                       // k-blocks of this CTA's earlier tiles: ring position of k-block 0
+      int it = 0;
+      for (int work = work0; work < num_work; work += work_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // the epilogue drained both halves of this buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(acc) * ACC_STRIDE + j * uint32_t(BN);
+        for (uint32_t i = j; i < nkb; i += 2) {
+          const uint32_t g = cnt + i;
+          const uint32_t stage = g % uint32_t(STAGES), phase = (g / uint32_t(STAGES)) & 1u;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + stage * uint32_t(L::STAGE_BYTES >> 4);
+          umma_bf16_ss_x4<false>(tmem_d, a_lo, a_lo + b_off, A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4,
+                                 B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4, desc_hi, desc_hi, idesc, i >= 2 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);                     // the producer may refill the stage once these MMAs retire
+        }
+        umma_commit(&tmem_full_bar[acc]);                     // this half is complete (the barrier counts both issuers)
+        cnt += nkb;
+      }
+    }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0 && pair_rank == 0) {       // pair mode: only the leader CTA issues
+    if (lane == 0 && pair_rank == 0 && !DUAL) {       // pair mode: only the leader CTA issues
       const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0) &
                              (p.fp16_in ? ~((1u << 7) | (1u << 10)) : ~0u);            // A/B format: 1 = bf16, 0 = fp16
       int stage = 0;
@@ -293,7 +334,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue drained this accumulator
         TR_END(1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
+        const uint32_t tmem_d = tmem_base + uint32_t(acc) * ACC_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
           TR_BEGIN;
           mbar_wait(&full_bar[stage], phase);
@@ -394,7 +435,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + c * 32), r);
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * ACC_STRIDE + uint32_t(c * 32), r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -419,7 +460,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (p.sample_mode) {
         // categorical draw by the Gumbel-max rule: argmax_v (x_v / T + G_v), G = -ln(-ln u); in the log2 domain and up
         // to a positive factor, argmax_v (x_v log2(e) / T - lg2(-lg2 u_v)).  The logits never leave the accumulator.
-        const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+        const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * ACC_STRIDE;
         const uint32_t rk = mix32(p.sample_k0 ^ mix32(uint32_t(row) + p.sample_k1));
         float bestv = -INFINITY;
         int besti = 0x7fffffff;
@@ -449,7 +490,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       if (p.argmin_out != nullptr) {
         // K9 epilogue: nothing is stored but each row's best (distance, code) over this tile's columns
-        const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+        const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * ACC_STRIDE;
         const float zq = row_ok ? __ldg(p.row_sq + row) : 0.f;
         float bestd = INFINITY;
         int besti = 0x7fffffff;
@@ -700,19 +741,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       };
       if (my_partials == nullptr) {
         // software pipeline over the accumulator: the TMEM load of unit u+1 is in flight while unit u is finished
-        const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+        const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * ACC_STRIDE;
         uint32_t ra[32], rb[32];
+        // DUAL: the odd k-blocks' half of the accumulator, BN columns further, is added in (fixed order: reproducible)
+        auto add_half = [&](uint32_t (&r)[32], int c) {
+          if constexpr (DUAL) {
+            uint32_t r2[32];
+            tmem_ld_32x32(t_acc + uint32_t(BN + c * 32), r2);
+            tmem_ld_wait_regs(r2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
+        };
         tmem_ld_32x32(t_acc, ra);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; c += 2) {
           TR_BEGIN;
           tmem_ld_wait_regs(ra);
           TR_END(4);
+          add_half(ra, c);
           tmem_ld_32x32(t_acc + uint32_t((c + 1) * 32), rb);
           staged_unit(ra, c);
           TR_BEGIN;
           tmem_ld_wait_regs(rb);
           TR_END(4);
+          add_half(rb, c + 1);
           if (c + 2 < BN / 32) tmem_ld_32x32(t_acc + uint32_t((c + 2) * 32), ra);
           else {                                   // accumulator fully read: hand it back before the last stores
             tc_fence_before();
@@ -760,7 +813,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, bool PAIR, bool DUAL = false>
 int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda, int ldb, cudaStream_t stream) {
   // 64 KiB of the 227 KiB go to the epilogue staging ring; the rest is the operand ring
   constexpr int STAGES = PAIR ? (BN == 256 ? 5 : 6) : ((BN == 256) ? 3 : (BN == 128 ? 5 : 6));
@@ -789,7 +842,7 @@ int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda,
     if (p.in_kind == 3) rc = get_tensor_map_2d(&tin, p.aux, 2, uint64_t(p.N), uint64_t(p.M), uint64_t(p.ldaux) * 2, 64, 128);
     if (rc) return rc;
   }
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, PAIR>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, PAIR, DUAL>;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -803,7 +856,7 @@ int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda,
   } else {
     const int tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
     const int grid = tiles < grid_cap() ? tiles : grid_cap();
-    const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, tc, taux, tin, p);
+    const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(DUAL ? GEMM_THREADS + 32 : GEMM_THREADS), L::TOTAL, stream, ta, tb, tc, taux, tin, p);
     if (le != cudaSuccess) {
       cudaFuncAttributes fa;
       cudaFuncGetAttributes(&fa, kern);
@@ -821,6 +874,9 @@ template <int BN, bool A_MN, bool B_MN>
 int launch_gemm(const void* A, const void* B, const GemmParams& p, int lda, int ldb, cudaStream_t stream) {
   if constexpr (BN >= 128) {
     if (p.pair) return launch_gemm_impl<BN, A_MN, B_MN, true>(A, B, p, lda, ldb, stream);
+  }
+  if constexpr (BN == 128) {
+    if (p.dual) return launch_gemm_impl<BN, A_MN, B_MN, false, true>(A, B, p, lda, ldb, stream);
   }
   return launch_gemm_impl<BN, A_MN, B_MN, false>(A, B, p, lda, ldb, stream);
 }
@@ -1009,6 +1065,10 @@ int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b
       }
     }
   }
+  // two issuing threads for the 128-wide tiles (DUAL): plain TMA epilogue only, and enough k-blocks for both halves
+  static const int dual_env = [] { const char* e = getenv("MEBT_GEMM_DUAL"); return e != nullptr ? atoi(e) : 1; }();
+  p.dual = dual_env != 0 && bn == 128 && !p.pair && p.splits == 1 && p.argmin_out == nullptr && !p.sample_mode &&
+           p.num_k_blocks >= 4;
   switch (bn) {
     case 256: return dispatch_major<256>(a_mn, b_mn, A, B, p, lda, ldb, stream);
     case 128: return dispatch_major<128>(a_mn, b_mn, A, B, p, lda, ldb, stream);
