@@ -103,8 +103,11 @@ __device__ __forceinline__ void locate(const ConvParams& p, int work, int& ni, i
   t0 = ti * p.PT; h0 = hi * p.PH; w0 = wi * p.PW;
 }
 
-template <int BN, bool ROW>
-__global__ void __launch_bounds__(CV_THREADS, 1)
+// DUAL (per-tap form, <= 128-wide tiles): two MMA-issuing threads (warps 1 and 6), each accumulating every other k-block in
+// its own TMEM half; the epilogue adds the halves (csrc/gemm.cu, DUAL: one issuer's barrier wait + commit cost ~520 clk per
+// k-block against 184 / 256 clk of tensor work for a 64- / 128-wide k-block).
+template <int BN, bool ROW, bool DUAL>
+__global__ void __launch_bounds__(DUAL ? CV_THREADS + 32 : CV_THREADS, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
                     const __grid_constant__ CUtensorMap tma_y, const ConvParams p) {
   using L = ConvSmem<BN, ROW>;
@@ -118,7 +121,9 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
+  static_assert(!DUAL || (!ROW && BN <= 128), "DUAL: per-tap form, two accumulator halves");
+  constexpr uint32_t ACC_STRIDE = DUAL ? 2 * BN : BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tma_x);
@@ -129,7 +134,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_full_bar[s], DUAL ? 2 : 1);
       mbar_init(&tmem_empty_bar[s], 128);
     }
     fence_barrier_init();
@@ -185,6 +190,34 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         }
       }
     }
+  } else if (DUAL && (warp == 1 || warp == 6)) {
+    // ================= the two MMA issuers of the DUAL variant =================
+    if (lane == 0) {
+      const uint32_t j = warp == 6 ? 1u : 0u;
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
+      uint32_t cnt = 0;
+      int it = 0;
+      for (int work = work0; work < p.total_tiles; work += work_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(acc) * ACC_STRIDE + j * uint32_t(BN);
+        for (uint32_t i = j; i < uint32_t(nkb); i += 2) {
+          const uint32_t g = cnt + i;
+          const uint32_t stage = g % uint32_t(STAGES), phase = (g / uint32_t(STAGES)) & 1u;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = smem_desc_lo(smem_u32(smem + stage * L::STAGE_BYTES), 16);
+          umma_bf16_ss_x4<false>(tmem_d, a_lo, a_lo + uint32_t(A_TILE_BYTES >> 4), (UMMA_K * 2) >> 4, (UMMA_K * 2) >> 4, desc_hi,
+                                 desc_hi, idesc, i >= 2 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        cnt += uint32_t(nkb);
+      }
+    }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
@@ -198,7 +231,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
+        const uint32_t tmem_d = tmem_base + uint32_t(acc) * ACC_STRIDE;
         if constexpr (ROW) {
           const int nst = p.KT * p.KH * p.cblocks;
           for (int st = 0; st < nst; ++st) {
@@ -256,7 +289,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
                                    (long long)(w0 + pw) * p.res_w : nullptr;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+      const uint32_t t_acc = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * ACC_STRIDE;
       // only the 64-channel chunks that hold real output channels are stored
       const int chunks = min(BN / 64, (p.Cout - n0 + 63) / 64);
 #pragma unroll 1
@@ -265,6 +298,17 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         tmem_ld_32x32(t_acc + uint32_t(ch * 64), ra);
         tmem_ld_32x32(t_acc + uint32_t(ch * 64 + 32), rb);
         tmem_ld_wait();
+        if constexpr (DUAL) {                                  // + the odd k-blocks' half (fixed order: reproducible)
+          uint32_t ra2[32], rb2[32];
+          tmem_ld_32x32(t_acc + uint32_t(BN + ch * 64), ra2);
+          tmem_ld_32x32(t_acc + uint32_t(BN + ch * 64 + 32), rb2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(ra2[j]));
+            rb[j] = __float_as_uint(__uint_as_float(rb[j]) + __uint_as_float(rb2[j]));
+          }
+        }
         if (ch == BN / 64 - 1) {                               // accumulator fully read: hand it back before the last stores
           tc_fence_before();
           mbar_arrive(&tmem_empty_bar[acc]);
@@ -459,17 +503,17 @@ __global__ void __launch_bounds__(256) pad_norm_act_kernel(const __nv_bfloat16* 
   }
 }
 
-template <int BN, bool ROW>
+template <int BN, bool ROW, bool DUAL = false>
 int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p, double flops,
                 cudaStream_t st) {
   using L = ConvSmem<BN, ROW>;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
-    MEBT_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel<BN, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    MEBT_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel<BN, ROW, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   }
   LaunchScope ls(FAM_GEMM, flops, st);
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  MEBT_CUDA_OK(launch_pdl(conv3d_igemm_kernel<BN, ROW>, dim3(grid), dim3(CV_THREADS), L::TOTAL, st, tx, tw, ty, p));
+  MEBT_CUDA_OK(launch_pdl(conv3d_igemm_kernel<BN, ROW, DUAL>, dim3(grid), dim3(DUAL ? CV_THREADS + 32 : CV_THREADS), L::TOTAL, st, tx, tw, ty, p));
   MEBT_LAUNCH_OK("conv3d_igemm_kernel");
   return MEBT_OK;
 }
@@ -631,9 +675,11 @@ int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w,
   // window mode: counted as one tap of ldx channels per window (the zero-weighted slots are not work)
   const double flops = 2.0 * double(p.tiles_m) * 128.0 * double(cout) * double(taps) * double(window ? ldx : cin);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const int dual_env = [] { const char* e = getenv("MEBT_CONV_DUAL"); return e != nullptr ? atoi(e) : 1; }();
+  const bool dual = dual_env != 0 && taps * p.cblocks >= 4;
   if (row) return launch_conv<64, true>(tx, tw, ty, p, flops, st);
-  if (bn == 64) return launch_conv<64, false>(tx, tw, ty, p, flops, st);
-  if (bn == 128) return launch_conv<128, false>(tx, tw, ty, p, flops, st);
+  if (bn == 64) return dual ? launch_conv<64, false, true>(tx, tw, ty, p, flops, st) : launch_conv<64, false>(tx, tw, ty, p, flops, st);
+  if (bn == 128) return dual ? launch_conv<128, false, true>(tx, tw, ty, p, flops, st) : launch_conv<128, false>(tx, tw, ty, p, flops, st);
   return launch_conv<256, false>(tx, tw, ty, p, flops, st);
 }
 
