@@ -84,6 +84,9 @@ def main():
         ob = ops.attention(qb, D, kvb, 0, D, 512, None, 0, 0, 0, 6, H, 256, lse=lse, drop_p=0.1, drop_seed=3)
         ops.attention_bwd(qb, D, kvb, 0, D, 512, None, 0, 0, 0, ob, dob, lse, torch.zeros_like(qb), D, torch.zeros_like(kvb),
                           0, D, None, 0, 0, 6, H, 256, drop_p=0.1, drop_seed=3)
+    # the training step's GEMM shapes (B = 6): 128-wide DUAL tiles (1536 x 1024 x 1024 / x 4096), pair-mode 256-wide tiles
+    for (m, n, k) in ((1536, 1024, 1024), (1536, 1024, 4096), (1536, 4096, 1024), (3072, 1024, 4096), (1536, 3072, 1024)):
+        ops.gemm(r(m, k), r(n, k), torch.zeros(n, device=dev))
     # masked CE at the training shape (3072 rows: the streaming kernel) and the grouped weight-gradient launch of a block
     lt = r(3072, 16384)
     ops.masked_ce(lt, torch.randint(0, 16384, (3072,), device=dev), 0.0, dlogits=lt, grad_scale=1.0)
