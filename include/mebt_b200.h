@@ -65,7 +65,8 @@ enum {
   MEBT_GEMM_FORCE_BN64 = 64,
   MEBT_GEMM_NO_SPLITK = 128,  /* never split the reduction across CTAs */
   MEBT_GEMM_NO_PAIR = 256,    /* never use the 2-CTA cluster variant (B tile shared by TMA multicast) */
-  MEBT_GEMM_FORCE_PAIR = 512
+  MEBT_GEMM_FORCE_PAIR = 512,
+  MEBT_GEMM_DUAL = 1024       /* 128-wide tiles: two MMA-issuing threads with an accumulator half each (opt-in) */
 };
 /*
  * C[M,N] = act( A * B^T + bias ) + residual, tcgen05/TMEM/TMA.

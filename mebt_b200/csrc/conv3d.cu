@@ -47,9 +47,9 @@ constexpr int EPI_SLOT_BYTES = 128 * 128;
 constexpr int ROW_A_BYTES = 17 * 1024;   // up to 136 rows of 128 bytes
 constexpr int ROW_MAX_KW = 4;
 
-template <int BN, bool ROW = false>
+template <int BN, bool ROW = false, bool DUAL = false>
 struct ConvSmem {
-  static constexpr int STAGES = ROW ? 3 : (BN == 256 ? 3 : (BN == 128 ? 5 : 6));
+  static constexpr int STAGES = ROW ? 3 : (BN == 256 ? 3 : (BN == 128 ? (DUAL ? 4 : 5) : 6));
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int A_BYTES = ROW ? ROW_A_BYTES : A_TILE_BYTES;
   static constexpr int STAGE_BYTES = ROW ? ROW_A_BYTES + ROW_MAX_KW * B_TILE_BYTES : A_TILE_BYTES + B_TILE_BYTES;
@@ -110,7 +110,7 @@ template <int BN, bool ROW, bool DUAL>
 __global__ void __launch_bounds__(DUAL ? CV_THREADS + 32 : CV_THREADS, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
                     const __grid_constant__ CUtensorMap tma_y, const ConvParams p) {
-  using L = ConvSmem<BN, ROW>;
+  using L = ConvSmem<BN, ROW, DUAL>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -121,7 +121,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  static_assert(!DUAL || (!ROW && BN <= 128), "DUAL: per-tap form, two accumulator halves");
+  static_assert(!DUAL || (!ROW && BN <= 128 && STAGES % 2 == 0), "DUAL: per-tap form, two accumulator halves, even ring");
   constexpr uint32_t ACC_STRIDE = DUAL ? 2 * BN : BN;
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
 
@@ -204,7 +204,11 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc) * ACC_STRIDE + j * uint32_t(BN);
-        for (uint32_t i = j; i < uint32_t(nkb); i += 2) {
+        // Issuer j takes the k-blocks whose RING position g is of parity j: with an even number of stages a stage then always
+        // belongs to the same issuer, who waits for its phases strictly in order.  (Splitting by the index inside the tile let
+        // one issuer reach a stage a whole ring ahead of the other: a parity wait for phase k + 1 on a barrier still in an
+        // incomplete phase k succeeds at once - stale operands, seen as rare wrong results / launch failures under stress.)
+        for (uint32_t i = ((cnt & 1u) == j) ? 0u : 1u; i < uint32_t(nkb); i += 2) {
           const uint32_t g = cnt + i;
           const uint32_t stage = g % uint32_t(STAGES), phase = (g / uint32_t(STAGES)) & 1u;
           mbar_wait(&full_bar[stage], phase);
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(256) pad_norm_act_kernel(const __nv_bfloat16* 
 template <int BN, bool ROW, bool DUAL = false>
 int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p, double flops,
                 cudaStream_t st) {
-  using L = ConvSmem<BN, ROW>;
+  using L = ConvSmem<BN, ROW, DUAL>;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
     MEBT_CUDA_OK(cudaFuncSetAttribute(conv3d_igemm_kernel<BN, ROW, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));

@@ -182,7 +182,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     n0 = ni * BN;
   };
   int* split_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);
-  static_assert(!DUAL || (!PAIR && BN <= 128), "DUAL: one CTA per tile, two accumulator halves of <= 128 columns");
+  static_assert(!DUAL || (!PAIR && BN <= 128 && STAGES % 2 == 0), "DUAL: one CTA per tile, two accumulator halves, even ring");
   constexpr uint32_t ACC_STRIDE = DUAL ? 2 * BN : BN;      // TMEM columns per accumulator buffer
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;           // 128, 256 or 512 (power of two >= 32)
 
@@ -296,7 +296,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // the epilogue drained both halves of this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc) * ACC_STRIDE + j * uint32_t(BN);
-        for (uint32_t i = j; i < nkb; i += 2) {
+        // Issuer j takes the k-blocks whose RING position g is of parity j: with an even number of stages a stage then always
+        // belongs to the same issuer, who waits for its phases strictly in order.  (Splitting by the index inside the tile let
+        // one issuer reach a stage a whole ring ahead of the other: a parity wait for phase k + 1 on a barrier still in an
+        // incomplete phase k succeeds at once - stale operands, seen as rare wrong results / launch failures under stress.)
+        for (uint32_t i = ((cnt & 1u) == j) ? 0u : 1u; i < nkb; i += 2) {
           const uint32_t g = cnt + i;
           const uint32_t stage = g % uint32_t(STAGES), phase = (g / uint32_t(STAGES)) & 1u;
           mbar_wait(&full_bar[stage], phase);
@@ -815,8 +819,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
 template <int BN, bool A_MN, bool B_MN, bool PAIR, bool DUAL = false>
 int launch_gemm_impl(const void* A, const void* B, const GemmParams& p, int lda, int ldb, cudaStream_t stream) {
-  // 64 KiB of the 227 KiB go to the epilogue staging ring; the rest is the operand ring
-  constexpr int STAGES = PAIR ? (BN == 256 ? 5 : 6) : ((BN == 256) ? 3 : (BN == 128 ? 5 : 6));
+  // 64 KiB of the 227 KiB go to the epilogue staging ring; the rest is the operand ring (DUAL: an even number of stages)
+  constexpr int STAGES = PAIR ? (BN == 256 ? 5 : 6) : ((BN == 256) ? 3 : (BN == 128 ? (DUAL ? 4 : 5) : 6));
   using L = SmemLayout<BN, STAGES, PAIR>;
   CUtensorMap ta, tb;
   int rc;
@@ -1066,8 +1070,11 @@ int gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b
     }
   }
   // two issuing threads for the 128-wide tiles (DUAL): plain TMA epilogue only, and enough k-blocks for both halves
-  static const int dual_env = [] { const char* e = getenv("MEBT_GEMM_DUAL"); return e != nullptr ? atoi(e) : 1; }();
-  p.dual = dual_env != 0 && bn == 128 && !p.pair && p.splits == 1 && p.argmin_out == nullptr && !p.sample_mode &&
+  // Opt-in (flag MEBT_GEMM_DUAL or MEBT_GEMM_DUAL=1): with the even ring it needs (4 stages instead of 5) the training step
+  // gains 0.4 % (11.31 -> 11.26 ms) - not worth a second code path by default; the convolution kernel, whose 64-wide
+  // k-blocks are 184 clk of tensor work, keeps it on (csrc/conv3d.cu).
+  static const int dual_env = [] { const char* e = getenv("MEBT_GEMM_DUAL"); return e != nullptr ? atoi(e) : 0; }();
+  p.dual = (dual_env != 0 || (flags & MEBT_GEMM_DUAL)) && bn == 128 && !p.pair && p.splits == 1 && p.argmin_out == nullptr && !p.sample_mode &&
            p.num_k_blocks >= 4;
   switch (bn) {
     case 256: return dispatch_major<256>(a_mn, b_mn, A, B, p, lda, ldb, stream);

@@ -5,6 +5,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GELU, OUT_FP32, ACC, BN256, BN128, BN64, NO_SPLITK, NO_PAIR, PAIR = 1, 2, 4, 16, 32, 64, 128, 256, 512
+DUAL = 1024    # two MMA-issuing threads, an accumulator half each (128-wide tiles; opt-in)
 
 CASES = [
     # M, N, K, a_mn, b_mn, flags, bias, resid
@@ -43,6 +44,12 @@ CASES = [
     (128, 256, 128, 0, 0, PAIR, True, False),
     (8192, 4096, 1024, 0, 0, 0, True, False),            # large enough to take the pair path on its own
     (8192, 4096, 1024, 0, 0, NO_PAIR, True, False),
+    # two-issuer variant: all operand majors, odd / even k-block counts, several tiles per CTA (2304 > 148 tiles), residual
+    (1536, 1024, 4096, 0, 0, DUAL, True, True),
+    (1536, 1024, 1024, 0, 1, DUAL | BN128, True, False),
+    (1024, 1024, 1536, 1, 1, DUAL | BN128 | OUT_FP32, False, False),
+    (512, 256, 448, 1, 0, DUAL | BN128, True, False),
+    (4608, 8192, 320, 0, 0, DUAL | BN128 | NO_PAIR, True, False),
 ]
 
 
@@ -63,7 +70,7 @@ def test_gemm(M, N, K, a_mn, b_mn, flags, bias, resid):
         C0 = torch.randn(M, N, device="cuda", generator=g)
         C.copy_(C0)
     ops.gemm(A_st, B_st, bias_t, res_t, gelu=bool(flags & GELU), out=C, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn),
-             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK | NO_PAIR | PAIR))
+             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK | NO_PAIR | PAIR | DUAL))
     torch.cuda.synchronize()
     ref = A.float() @ B.float().t()
     if bias:
@@ -83,7 +90,7 @@ def test_gemm(M, N, K, a_mn, b_mn, flags, bias, resid):
     if C0 is not None:
         C2.copy_(C0)
     ops.gemm(A_st, B_st, bias_t, res_t, gelu=bool(flags & GELU), out=C2, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn),
-             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK | NO_PAIR | PAIR))
+             accumulate=bool(flags & ACC), flags_extra=flags & (BN256 | BN128 | BN64 | NO_SPLITK | NO_PAIR | PAIR | DUAL))
     assert torch.equal(C, C2)
 
 
