@@ -125,3 +125,26 @@ def test_grouped_wgrad(rows_q, rows_k, D):
     # same arithmetic as the stand-alone GEMM (fp32 accumulation in TMEM over the same k-blocks in the same order)
     single = ops.gemm(d_mlp, u, out_dtype=torch.float32, a_mn_major=True, b_mn_major=True, flags_extra=16 | 128)
     assert torch.equal(single, outs[0])
+
+
+def test_gemm_dual_repeated_launches_are_bit_identical():
+    """The two-issuer variant sums in a fixed order (even ring positions into one accumulator half, odd ones into the other,
+    one final add): 600 launches of the training step's 1536 x 1024 x 4096 shape next to a copy stream all equal the first
+    bit for bit, and agree with the single-issuer kernel within the accumulation-order rounding."""
+    from mebt_b200 import ops
+    torch.manual_seed(3)
+    a = torch.randn(1536, 4096, device="cuda").to(torch.bfloat16)
+    b = torch.randn(1024, 4096, device="cuda").to(torch.bfloat16)
+    ref = ops.gemm(a, b, flags_extra=DUAL | BN128)
+    single = ops.gemm(a, b, flags_extra=BN128)
+    assert (ref.float() - single.float()).abs().max() <= 2 ** -6 * single.float().abs().max()
+    side = torch.cuda.Stream()
+    big = torch.empty(2, 32 << 20, device="cuda", dtype=torch.uint8)
+    for it in range(600):
+        if it % 7 == 0:
+            with torch.cuda.stream(side):
+                big[1].copy_(big[0], non_blocking=True)
+        out = ops.gemm(a, b, flags_extra=DUAL | BN128)
+        if it % 5 == 0:
+            assert torch.equal(out, ref), f"launch {it} differs"
+    torch.cuda.synchronize()

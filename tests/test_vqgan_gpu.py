@@ -155,6 +155,33 @@ def test_vqgan_oracle_parity_at_16_frame_latent_shape():
     assert rec.shape == (1, 3, 16, 64, 64) and _rel(rec, ref) < 3e-2, _rel(rec, ref)
 
 
+def test_vqgan_repeated_steps_are_bit_identical():
+    """150 end-to-end encode + decode steps (host input, a synchronise per step, device steps in between) of the 16-frame
+    VQGAN configuration give the same reconstruction bit for bit: every kernel on the path sums in a fixed order, so any
+    difference is a race.  (This loop is what exposed a barrier parity aliasing in the first two-issuer convolution kernel;
+    tools/vqgan_stress.py is the long form.)"""
+    from mebt_b200.vqgan import VQGAN, _Args
+    from oracle import vqgan_oracle as VO
+    args = dict(embedding_dim=256, n_codes=16384, n_hiddens=32, downsample=(4, 8, 8), image_channels=3, norm_type="group",
+                padding_type="replicate", sequence_length=16, sample_every_n_frames=1, resolution=128)
+    vq = VQGAN(_Args(args))
+    shapes = {k: tuple(v.shape) for k, v in vq.state_dict().items() if not k.startswith("codebook.") or k == "codebook.embeddings"}
+    vq.load_state_dict({**vq.state_dict(), **VO.make_weights(shapes, 0)})
+    vq = vq.cuda().eval()
+    x_host = (torch.rand(2, 3, 16, 128, 128, generator=torch.Generator().manual_seed(5)) - 0.5).pin_memory()
+    ref = None
+    for i in range(150):
+        rec = vq.decode(vq.encode(x_host.to("cuda", non_blocking=True)))
+        torch.cuda.synchronize()
+        if i % 3 == 0:
+            rec = vq.decode(vq.encode(x_host.cuda()))
+        if ref is None:
+            ref = rec.clone()
+        elif i % 10 == 0:
+            assert torch.equal(rec, ref), f"step {i}: the reconstruction changed between identical steps"
+    assert torch.isfinite(ref).all()
+
+
 def test_vqgan_checkpoint_and_npy_formats(tmp_path):
     from mebt_b200 import vqgan as V
     cfg = dict(embedding_dim=64, n_codes=128, n_hiddens=32, downsample=(2, 4, 4), image_channels=3, norm_type="group",
