@@ -47,14 +47,19 @@ constexpr int EPI_SLOT_BYTES = 128 * 128;
 constexpr int ROW_A_BYTES = 17 * 1024;   // up to 136 rows of 128 bytes
 constexpr int ROW_MAX_KW = 4;
 
-template <int BN, bool ROW = false, bool DUAL = false>
+// ROW = 2 (row pairs): the CTA works on TWO of its output rows at a time - two activation boxes per stage, ONE set of weight
+// tiles for both (the weights are the same for every tile and are 60 % of a ROW-mode stage's bytes), four TMEM accumulators.
+template <int BN, int ROW = 0, bool DUAL = false>
 struct ConvSmem {
   static constexpr int STAGES = ROW ? 3 : (BN == 256 ? 3 : (BN == 128 ? (DUAL ? 4 : 5) : 6));
   static constexpr int B_TILE_BYTES = BN * BK * 2;
-  static constexpr int A_BYTES = ROW ? ROW_A_BYTES : A_TILE_BYTES;
-  static constexpr int STAGE_BYTES = ROW ? ROW_A_BYTES + ROW_MAX_KW * B_TILE_BYTES : A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int ROW_KW = ROW == 2 ? 3 : ROW_MAX_KW;            // weight tiles a stage holds
+  static constexpr int A_BYTES = ROW ? ROW * ROW_A_BYTES : A_TILE_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + (ROW ? ROW_KW : 1) * B_TILE_BYTES;
+  static constexpr int EPI_SLOTS_N = ROW == 2 ? 2 : EPI_SLOTS;
+  static constexpr int NACC = ROW == 2 ? 4 : 2;                        // TMEM accumulator buffers
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_SLOTS * EPI_SLOT_BYTES;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_SLOTS_N * EPI_SLOT_BYTES;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
   static constexpr int TOTAL = BIAS_OFFSET + BN * 4 + 1024;
   static_assert(TOTAL <= 232448, "shared memory budget");
@@ -106,7 +111,7 @@ __device__ __forceinline__ void locate(const ConvParams& p, int work, int& ni, i
 // DUAL (per-tap form, <= 128-wide tiles): two MMA-issuing threads (warps 1 and 6), each accumulating every other k-block in
 // its own TMEM half; the epilogue adds the halves (csrc/gemm.cu, DUAL: one issuer's barrier wait + commit cost ~520 clk per
 // k-block against 184 / 256 clk of tensor work for a 64- / 128-wide k-block).
-template <int BN, bool ROW, bool DUAL>
+template <int BN, int ROW, bool DUAL>
 __global__ void __launch_bounds__(DUAL ? CV_THREADS + 32 : CV_THREADS, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
                     const __grid_constant__ CUtensorMap tma_y, const ConvParams p) {
@@ -117,13 +122,15 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  constexpr int NACC = L::NACC;
+  uint64_t* tmem_empty_bar = tmem_full_bar + NACC;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + NACC);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   static_assert(!DUAL || (!ROW && BN <= 128 && STAGES % 2 == 0), "DUAL: per-tap form, two accumulator halves, even ring");
   constexpr uint32_t ACC_STRIDE = DUAL ? 2 * BN : BN;
-  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+  constexpr uint32_t TMEM_COLS = NACC * ACC_STRIDE;
+  static_assert(ROW != 2 || (BN == 64 && !DUAL), "row pairs: 64-wide tiles");
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tma_x);
@@ -133,7 +140,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       mbar_init(&tmem_full_bar[s], DUAL ? 2 : 1);
       mbar_init(&tmem_empty_bar[s], 128);
     }
@@ -154,6 +161,32 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (ROW == 2) {
+        // row pairs: the CTA's tiles two at a time (work, work + stride): two activation boxes, one set of weight tiles
+        for (int work = work0; work < p.total_tiles; work += 2 * work_stride) {
+          const bool has_b = work + work_stride < p.total_tiles;
+          int ni, b, t0, h0, w0, ni2 = 0, b2 = 0, t2 = 0, h2 = 0, w2 = 0;
+          locate(p, work, ni, b, t0, h0, w0);
+          if (has_b) locate(p, work + work_stride, ni2, b2, t2, h2, w2);
+          const uint32_t stage_tx = uint32_t((has_b ? 2 : 1) * (128 + p.KW - 1) * 128 + p.KW * L::B_TILE_BYTES);
+          for (int dt = 0; dt < p.KT; ++dt)
+            for (int dh = 0; dh < p.KH; ++dh)
+              for (int cb = 0; cb < p.cblocks; ++cb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * L::STAGE_BYTES;
+                uint8_t* sB = sA + 2 * ROW_A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                tma_load_5d(sA, &tma_x, &full_bar[stage], cb * BK, w0 * p.SW + p.OW, h0 * p.SH + p.OH + dh, t0 * p.ST + p.OT + dt, b);
+                if (has_b)
+                  tma_load_5d(sA + ROW_A_BYTES, &tma_x, &full_bar[stage], cb * BK, w2 * p.SW + p.OW, h2 * p.SH + p.OH + dh,
+                              t2 * p.ST + p.OT + dt, b2);
+                for (int dw = 0; dw < p.KW; ++dw)
+                  tma_load_2d(sB + dw * L::B_TILE_BYTES, &tma_w, &full_bar[stage],
+                              (((dt * p.KH + dh) * p.KW + dw) * p.cblocks + cb) * BK, ni * BN);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+        }
+      } else
       for (int work = work0; work < p.total_tiles; work += work_stride) {
         int ni, b, t0, h0, w0;
         locate(p, work, ni, b, t0, h0, w0);
@@ -230,6 +263,42 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if constexpr (ROW == 2) {
+        const int nst = p.KT * p.KH * p.cblocks;
+        for (int work = work0; work < p.total_tiles; work += 2 * work_stride, it += 2) {
+          const bool has_b = work + work_stride < p.total_tiles;
+          const int acc = it & 3;                             // tiles it and it + 1: accumulators acc and acc + 1
+          const uint32_t acc_phase = (it >> 2) & 1;
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+          if (has_b) mbar_wait(&tmem_empty_bar[acc + 1], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_a = tmem_base + uint32_t(acc) * ACC_STRIDE, tmem_b = tmem_a + ACC_STRIDE;
+          for (int st = 0; st < nst; ++st) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t base = smem_u32(smem + stage * L::STAGE_BYTES);
+            for (int dw = 0; dw < p.KW; ++dw) {
+              const uint32_t a_lo = smem_desc_lo(base + uint32_t(dw) * 128u, 16);
+              const uint32_t b_lo = smem_desc_lo(base + uint32_t(2 * ROW_A_BYTES + dw * L::B_TILE_BYTES), 16);
+              umma_bf16_ss_x4<false>(tmem_a, a_lo, b_lo, (UMMA_K * 2) >> 4, (UMMA_K * 2) >> 4, desc_hi, desc_hi, idesc,
+                                     (st > 0 || dw > 0) ? 1u : 0u);
+            }
+            if (has_b)
+              for (int dw = 0; dw < p.KW; ++dw) {
+                const uint32_t a_lo = smem_desc_lo(base + uint32_t(ROW_A_BYTES) + uint32_t(dw) * 128u, 16);
+                const uint32_t b_lo = smem_desc_lo(base + uint32_t(2 * ROW_A_BYTES + dw * L::B_TILE_BYTES), 16);
+                umma_bf16_ss_x4<false>(tmem_b, a_lo, b_lo, (UMMA_K * 2) >> 4, (UMMA_K * 2) >> 4, desc_hi, desc_hi, idesc,
+                                       (st > 0 || dw > 0) ? 1u : 0u);
+              }
+            umma_commit(&empty_bar[stage]);
+            if (st == nst - 1) {
+              umma_commit(&tmem_full_bar[acc]);
+              if (has_b) umma_commit(&tmem_full_bar[acc + 1]);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else
       for (int work = work0; work < p.total_tiles; work += work_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -283,8 +352,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
       int ni, b, t0, h0, w0;
       locate(p, work, ni, b, t0, h0, w0);
       const int n0 = ni * BN;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it & (NACC - 1);
+      const uint32_t acc_phase = (it / NACC) & 1;
       asm volatile("bar.sync 1, 128;" ::: "memory");          // the previous tile's readers of s_bias are done
       for (int c = threadIdx.x - 64; c < BN; c += 128) s_bias[c] = (p.bias != nullptr && n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -331,7 +400,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
                                     (long long)(w0 + pw) * p.yd_w) = o;
           continue;
         }
-        const int s_c = gu & 3;
+        const int s_c = gu & (L::EPI_SLOTS_N - 1);
         ++gu;
         uint8_t* row_c = slots + s_c * EPI_SLOT_BYTES + r * 128;
 #pragma unroll
@@ -365,7 +434,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         // one barrier per chunk: behind it every row of the slot is written (and fenced towards the async proxy), and
         // the slot the NEXT chunk writes has been read out by its previous store (epi_t0 checks before arriving)
         fence_proxy_async_smem();
-        if (epi_t0) tma_store_wait_read<2>();
+        if (epi_t0) { if constexpr (L::EPI_SLOTS_N == 4) tma_store_wait_read<2>(); else tma_store_wait_read<0>(); }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (epi_t0) {
           tma_store_5d(&tma_y, slots + s_c * EPI_SLOT_BYTES, n0 + ch * 64, w0 * p.YW + p.Y0W, h0 * p.YH + p.Y0H,
@@ -507,7 +576,7 @@ __global__ void __launch_bounds__(256) pad_norm_act_kernel(const __nv_bfloat16* 
   }
 }
 
-template <int BN, bool ROW, bool DUAL = false>
+template <int BN, int ROW, bool DUAL = false>
 int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvParams& p, double flops,
                 cudaStream_t st) {
   using L = ConvSmem<BN, ROW, DUAL>;
@@ -681,10 +750,13 @@ int mebt_conv3d_ndhwc(const void* xp, int ldx, const int* xdims4, const void* w,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static const int dual_env = [] { const char* e = getenv("MEBT_CONV_DUAL"); return e != nullptr ? atoi(e) : 1; }();
   const bool dual = dual_env != 0 && taps * p.cblocks >= 4;
-  if (row) return launch_conv<64, true>(tx, tw, ty, p, flops, st);
-  if (bn == 64) return dual ? launch_conv<64, false, true>(tx, tw, ty, p, flops, st) : launch_conv<64, false>(tx, tw, ty, p, flops, st);
-  if (bn == 128) return dual ? launch_conv<128, false, true>(tx, tw, ty, p, flops, st) : launch_conv<128, false>(tx, tw, ty, p, flops, st);
-  return launch_conv<256, false>(tx, tw, ty, p, flops, st);
+  // row pairs once every SM has at least two rows (two tiles share the weight tiles of a stage)
+  static const int row2_env = [] { const char* e = getenv("MEBT_CONV_ROW2"); return e != nullptr ? atoi(e) : 1; }();
+  if (row && row2_env != 0 && p.KW <= 3 && p.total_tiles >= 2 * sm_count()) return launch_conv<64, 2>(tx, tw, ty, p, flops, st);
+  if (row) return launch_conv<64, 1>(tx, tw, ty, p, flops, st);
+  if (bn == 64) return dual ? launch_conv<64, 0, true>(tx, tw, ty, p, flops, st) : launch_conv<64, 0>(tx, tw, ty, p, flops, st);
+  if (bn == 128) return dual ? launch_conv<128, 0, true>(tx, tw, ty, p, flops, st) : launch_conv<128, 0>(tx, tw, ty, p, flops, st);
+  return launch_conv<256, 0>(tx, tw, ty, p, flops, st);
 }
 
 }  // extern "C"

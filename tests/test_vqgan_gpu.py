@@ -66,6 +66,8 @@ def test_pad_norm_act_group_widths(C, dims, B):
                                                     # rows of 128 positions: the taps along w share one TMA box (ROW mode)
                                                     (64, 64, 3, (1, 1, 1), (2, 4, 128)), (8, 32, 3, (1, 1, 1), (1, 2, 128)),
                                                     (64, 8, 3, (1, 1, 1), (2, 2, 256)), (128, 64, 3, (1, 1, 1), (1, 3, 128)),
+                                                    # >= 2 rows per SM: row pairs share the weight tiles (ROW = 2), even and odd tile counts per CTA
+                                                    (64, 64, 3, (1, 1, 1), (4, 40, 128)), (64, 32, 3, (1, 1, 1), (5, 31, 128)),
                                                     # 3 input channels: the taps along w packed into one k-block (window mode)
                                                     (3, 32, 3, (1, 1, 1), (3, 4, 128)), (5, 64, 3, (1, 1, 1), (1, 2, 256)),
                                                     # 128-wide output tiles
