@@ -1,0 +1,107 @@
+"""Host logic of the VQGAN convolution wrappers (mebt_b200/vqgan.py) without a GPU: the packed operands and the launch
+arguments they hand to `mebt_conv3d_ndhwc` are run through a plain-torch restatement of that entry point's CONTRACT
+(include/mebt_b200.h: y[b, t*ystep+yorigin, ...] = bias + sum_{taps, c} xp[b, t*step + origin + dt, ...] * w[co][(tap)][c],
+window mode when cin > ldx) and compared with torch.nn.functional on the reference's formulation
+(mebt/vqgan.py:358-405: F.pad(replicate) + Conv3d / ConvTranspose3d(padding = k - 1))."""
+import itertools
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mebt_b200 import vqgan as V
+
+
+def conv3d_ndhwc_contract(xp, w, cin, cout, taps, step, odims, bias, out=None, origin=(0, 0, 0), ystep=(1, 1, 1), yorigin=(0, 0, 0)):
+    """xp [B, Tp, Hp, Wp, ld] fp32, w [rows >= cout, prod(taps) * ceil64(cin)]; -> channels-last fp32 output."""
+    B, Tp, Hp, Wp, ld = xp.shape
+    window = cin > ld
+    cp = -(-cin // 64) * 64
+    assert w.shape[0] % 64 == 0 and w.shape[0] >= cout and w.shape[1] == taps[0] * taps[1] * taps[2] * cp
+    wf = w.float().view(w.shape[0], *taps, cp)
+    assert float(wf[cout:].abs().max() if w.shape[0] > cout else 0.0) == 0.0          # zero rows behind cout
+    To, Ho, Wo = odims
+    y = torch.zeros(B, To, Ho, Wo, cout)
+    rows = xp.reshape(B, Tp, Hp, Wp * ld)
+    for dt, dh, dw in itertools.product(*(range(k) for k in taps)):
+        ts = origin[0] + dt + step[0] * torch.arange(To)
+        hs = origin[1] + dh + step[1] * torch.arange(Ho)
+        ws = origin[2] + dw + step[2] * torch.arange(Wo)
+        if window:          # the K slice of a position: the cin consecutive ELEMENTS from its first channel on
+            assert taps[2] == 1 and step[2] == 1 and int(ws[-1]) * ld + cin <= Wp * ld
+            a = torch.stack([rows[:, ts][:, :, hs][..., int(w0) * ld:int(w0) * ld + cin] for w0 in ws], dim=3)
+        else:
+            a = xp[:, ts][:, :, hs][:, :, :, ws][..., :cin]
+        y += a @ wf[:cout, dt, dh, dw, :cin].t()
+    y += bias[:cout]
+    if out is None:
+        return y
+    out[:, yorigin[0]::ystep[0], yorigin[1]::ystep[1], yorigin[2]::ystep[2], :cout] = y
+    return out
+
+
+def channels_last(x, ld):
+    out = torch.zeros(x.shape[0], *x.shape[2:], ld)
+    out[..., :x.shape[1]] = x.permute(0, 2, 3, 4, 1)
+    return out
+
+
+def pad_cl(x, pads6):       # replicate padding of a channels-last tensor, pads6 = (t0, t1, h0, h1, w0, w1)
+    y = F.pad(x.permute(0, 4, 1, 2, 3), (pads6[4], pads6[5], pads6[2], pads6[3], pads6[0], pads6[1]), mode="replicate")
+    return y.permute(0, 2, 3, 4, 1).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dims", [(16, 24, 3, (1, 1, 1), (3, 5, 6)), (8, 40, 4, (2, 2, 2), (4, 6, 8)),
+                                                    (70, 8, 4, (1, 2, 2), (3, 4, 6)), (5, 3, 1, (1, 1, 1), (2, 3, 4))])
+def test_same_pad_conv3d_packing(cin, cout, k, stride, dims):
+    torch.manual_seed(0)
+    m = V.SamePadConv3d(cin, cout, k, stride=stride)
+    x = torch.randn(2, cin, *dims)
+    ref = F.conv3d(F.pad(x, m.pad_input, mode="replicate"), m.conv.weight.to(torch.bfloat16).float(), m.conv.bias, stride=stride)
+    w, b = m._operands()
+    pads = m.pads
+    xp = pad_cl(channels_last(x, -(-cin // 8) * 8), (pads[0][0], pads[0][1], pads[1][0], pads[1][1], pads[2][0], pads[2][1]))
+    odims = tuple(d // s for d, s in zip(dims, stride))
+    got = conv3d_ndhwc_contract(xp, w, cin, b.shape[0], m.kernel_size, m.stride, odims, b)
+    assert b.shape[0] == -(-cout // 8) * 8 and w.shape[0] == -(-cout // 64) * 64
+    assert torch.allclose(got[..., :cout].permute(0, 4, 1, 2, 3), ref, atol=2e-4, rtol=1e-4)
+    assert float(got[..., cout:].abs().max() if got.shape[-1] > cout else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("cin,kw", [(3, 3), (8, 3), (2, 5)])
+def test_window_mode_packing_of_a_few_channel_input(cin, kw):
+    """The 3-channel first convolution: the taps along w packed into one 64-element K slice (8 positions x 8 channels);
+    the row padded by 8 - kw extra positions on the right (`SamePadConv3d._window` / `_operands_window`)."""
+    torch.manual_seed(1)
+    m = V.SamePadConv3d(cin, 32, (3, 3, kw))
+    x = torch.randn(1, cin, 2, 3, 128)
+    xcl = channels_last(x, 8)
+    assert m._window(xcl)
+    ref = F.conv3d(F.pad(x, m.pad_input, mode="replicate"), m.conv.weight.to(torch.bfloat16).float(), m.conv.bias)
+    w, b = m._operands_window()
+    pads = m.pads
+    xp = pad_cl(xcl, (pads[0][0], pads[0][1], pads[1][0], pads[1][1], pads[2][0], pads[2][1] + 8 - kw))
+    got = conv3d_ndhwc_contract(xp, w, 64, b.shape[0], (3, 3, 1), (1, 1, 1), (2, 3, 128), b)
+    assert w.shape == (64, 9 * 64)
+    assert torch.allclose(got.permute(0, 4, 1, 2, 3), ref, atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
+def test_transposed_convolution_as_parity_classes(stride):
+    """ConvTranspose3d(kernel 4, stride s, padding 3) over the replicate-padded input = one stride-1 convolution per output
+    parity with the matching kernel slices, written to the interleaved positions (vqgan.py:384-405)."""
+    torch.manual_seed(2)
+    m = V.SamePadConvTranspose3d(12, 20, 4, stride=stride)
+    x = torch.randn(2, 12, 3, 4, 5)
+    ref = F.conv_transpose3d(F.pad(x, m.pad_input, mode="replicate"), m.convt.weight.to(torch.bfloat16).float(), m.convt.bias,
+                             stride=stride, padding=3)
+    classes, b = m._operands()
+    assert len(classes) == 2 ** sum(s == 2 for s in stride)
+    pads = m.pads
+    xp = pad_cl(channels_last(x, 16), (pads[0][0], pads[0][1], pads[1][0], pads[1][1], pads[2][0], pads[2][1]))
+    odims = (3, 4, 5)
+    out = torch.zeros(2, *(d * s for d, s in zip(odims, stride)), b.shape[0])
+    for par, taps, w in classes:
+        conv3d_ndhwc_contract(xp, w, 12, b.shape[0], taps, (1, 1, 1), odims, b, out=out, origin=par, ystep=stride, yorigin=par)
+    assert ref.shape[2:] == out.shape[1:4]
+    assert torch.allclose(out[..., :20].permute(0, 4, 1, 2, 3), ref, atol=2e-4, rtol=1e-4)
