@@ -16,6 +16,19 @@
 // Kernel = csrc/gemm_grouped.cu's structure: 192 threads (TMA producer warp, one MMA-issuing thread, 4 epilogue warps),
 // 3-6 stage operand ring, two TMEM accumulators, epilogue (bias, residual, bf16) through a 4-slot staging ring and TMA store.
 // pad_norm_act_kernel writes Xp: replicate padding fused with GroupNorm(32) / eval BatchNorm + SiLU of the source.
+//
+// Variants of the main loop (template parameters of conv3d_igemm_kernel, chosen in mebt_conv3d_ndhwc):
+//   per-tap  (ROW = 0): a stage = one (tap, channel block); 64 / 128 / 256-wide tiles by output channels.  DUAL (<= 128-wide):
+//            two MMA-issuing threads, an accumulator half each, stages owned by ring parity (even ring).
+//   ROW = 1 : stride 1 along w, output rows of 128 positions, <= 64 output channels: a tile is one output row and ONE box of
+//            128 + KW - 1 positions serves all KW taps along w through descriptor starts shifted by dw * 128 bytes.
+//   ROW = 2 : the same with the CTA's rows taken two at a time: two activation boxes, one set of weight tiles per stage,
+//            four TMEM accumulators, two staging slots.
+//   window  (host side): cin = 64 > ldx - the K slice of a position runs on into the following positions of its row, i.e. the
+//            taps along w of a few-channel input (the RGB video) packed into one k-block.
+// Measured rules that shaped them (Findings): a 64-wide tile is bound by L2 -> shared-memory operand fills, not by
+// the tensor pipe; a TMA box partly outside its tensor (or with 16-byte rows) is filled at a fraction of the normal rate, so
+// operands come in whole boxes; two consumers of one barrier ring must each own their stages.
 #include <cstdlib>
 #include <cstring>
 
