@@ -7,8 +7,10 @@
 
 They are host orchestration over `Net2NetTransformer.sample` (whose forwards, sampling and re-masking run on the CUDA
 kernels) and return the reference's `log` dict at token level: `code_maps`, `class_label` and, for `bidirect_sample`,
-`score`.  Pixels (`log["samples"]`) need the VQGAN conv decoder, which is outside this repository's scope (SURVEY.md
-section 8(f) rank 4): pass `decode=<callable>` to get them exactly as the script computes them.
+`score`.  Pixels (`log["samples"]`) come from the VQGAN decoder exactly as the script computes them
+(`gpt.first_stage_model.decode`, :82,146): by default the model's own first stage (`mebt_b200.vqgan.VQGAN`, loaded by
+`init_first_stage_from_ckpt` when `vtokens: False`); `decode=<callable>` overrides it, and a token-only model
+(`vtokens: True`, no first stage) returns the token-level log.
 
 Reference quirks kept: the temporal ratio 0.25 is hard-coded (:29,104); `skips=False` is passed positionally as in the
 script; the windows after the first one in `bidirect_sample` are sampled WITHOUT `edit` (:62) while `extrapolate` uses
@@ -22,6 +24,9 @@ import torch
 
 
 def _decode(model, code_map, decode, total_length, log):
+    if decode is None:
+        first = getattr(model, "first_stage_model", None)
+        decode = first.decode if first is not None else None
     if decode is None:
         return
     img_x = decode(code_map)

@@ -207,10 +207,21 @@ class Net2NetTransformer(_Base):
         print(f"Restored from {path}")
 
     def init_first_stage_from_ckpt(self, config):
+        """transformer.py:180-192: with `vtokens: False` the frozen VQGAN of `first_stage_config.params.ckpt_path` (a
+        Lightning checkpoint of mebt.vqgan.VQGAN) encodes the videos to tokens; with `vtokens: True` the data already are
+        token grids and no first stage is loaded."""
         if not self.vtokens:
-            raise NotImplementedError(
-                "mebt_b200: loading a VQGAN checkpoint (conv encoder/decoder) is out of scope; use vtokens=True and "
-                "attach a first-stage model with `.first_stage_model = mebt_b200.vqgan.VQGAN(...)` if needed")
+            from .vqgan import load_vqgan
+            params = config["params"] if isinstance(config, dict) else config.params
+            ckpt = params["ckpt_path"] if isinstance(params, dict) else params.ckpt_path
+            self.first_stage_model = load_vqgan(ckpt, device="cpu")           # moves with the module (.to / .cuda)
+            for p in self.first_stage_model.parameters():
+                p.requires_grad = False
+            self.first_stage_model.codebook._need_init = False
+            self.first_stage_model.eval()
+            self.first_stage_model.train = disabled_train.__get__(self.first_stage_model)
+            self.first_stage_vocab_size = self.first_stage_model.codebook.n_codes
+            return
         self.first_stage_model = None
         self.first_stage_vocab_size = 16384
 

@@ -189,3 +189,40 @@ def test_header_is_plain_c():
     import re
     code = re.sub(r"/\*.*?\*/", "", hdr.read_text(), flags=re.S)          # declarations only, comments stripped
     assert "torch" not in code.lower() and "at::" not in code and "std::" not in code and "#include <c" not in code.replace("#include <cuda", "")
+
+
+def test_first_stage_vqgan_is_loaded_and_frozen_when_vtokens_is_false(tmp_path):
+    """`vtokens: False` (transformer.py:180-192): the VQGAN of first_stage_config.params.ckpt_path becomes the frozen
+    `first_stage_model` (reference key names in the state_dict, no gradients, train() is a no-op on it, vocabulary size from its
+    codebook), and the sampling-script pipelines decode through it by default."""
+    import torch
+    from helpers import STL_16F, to_attr
+    from mebt_b200 import vqgan as V
+    from mebt_b200.transformer import Net2NetTransformer
+    vcfg = dict(embedding_dim=64, n_codes=128, n_hiddens=32, downsample=(2, 4, 4), image_channels=3, norm_type="group",
+                padding_type="replicate", sequence_length=8, sample_every_n_frames=1, resolution=32)
+    vq = V.VQGAN(V._Args(vcfg))
+    ckpt = tmp_path / "vqgan.ckpt"
+    torch.save({"hyper_parameters": {"args": V._Args(vcfg)}, "state_dict": vq.state_dict()}, ckpt)
+    cfg = dict(STL_16F, n_embd=64, n_head=1, sos_emb=16, n_layer=4, mode=["latent_enc", "latent_self", "latent_dec", "lt2l"],
+               vocab_size=128, block_size=256, shape=[4, 8, 8])
+    params, _, mask = model_configs(cfg)
+    params.vtokens = False
+    first = to_attr(dict(params=dict(ckpt_path=str(ckpt), ignore_keys=["loss"])))
+    m = Net2NetTransformer(params, first, mask)
+    assert isinstance(m.first_stage_model, V.VQGAN) and m.first_stage_vocab_size == 128
+    assert m.first_stage_model.latent_shape == (4, 8, 8)
+    assert all(not p.requires_grad for p in m.first_stage_model.parameters())
+    assert m.first_stage_model.codebook._need_init is False
+    m.train()
+    assert m.transformer.training and not m.first_stage_model.training and not m.first_stage_model.encoder.training
+    keys = m.state_dict().keys()
+    assert "first_stage_model.encoder.conv_first.conv.weight" in keys and "first_stage_model.codebook.embeddings" in keys
+    assert torch.equal(m.first_stage_model.state_dict()["decoder.conv_last.conv.weight"], vq.state_dict()["decoder.conv_last.conv.weight"])
+    # the pipelines' default decoder is the model's own first stage
+    from mebt_b200 import pipelines
+    seen = {}
+    m.first_stage_model.decode = lambda codes: (seen.setdefault("codes", codes), torch.zeros(codes.shape[0], 3, 8, 32, 32))[1]
+    log = {}
+    pipelines._decode(m, torch.zeros(1, 4, 8, 8, dtype=torch.long), None, 8, log)
+    assert "codes" in seen and log["samples"].shape == (1, 3, 8, 32, 32)

@@ -268,3 +268,44 @@ def test_sample_debug_selected_probs_equal_the_gather_of_the_dense_map():
     assert dense.shape == (2, 256, 16384) and sel.shape == (2, 256)
     gathered = torch.gather(dense, -1, xd.unsqueeze(-1)).squeeze(-1)
     assert torch.allclose(gathered, sel, rtol=1e-6, atol=0)
+
+
+def test_vtokens_false_model_encodes_and_decodes_through_its_vqgan(tmp_path):
+    """`vtokens: False` end to end on the GPU: the transformer's frozen first stage (loaded from a Lightning-format VQGAN
+    checkpoint, transformer.py:180-192) turns videos into the token grid `encode_to_z` returns (:683-694), and the sampling
+    script's `bidirect_sample` decodes its code map to pixels through the same first stage by default
+    (sample_vqgan_transformer_videos.py:82)."""
+    from helpers import STL_16F, model_configs, to_attr
+    from mebt_b200 import pipelines, vqgan as V
+    from mebt_b200.transformer import Net2NetTransformer
+    from oracle import vqgan_oracle as VO
+    vcfg = dict(embedding_dim=64, n_codes=128, n_hiddens=32, downsample=(2, 4, 4), image_channels=3, norm_type="group",
+                padding_type="replicate", sequence_length=8, sample_every_n_frames=1, resolution=32)
+    vq = V.VQGAN(V._Args(vcfg))
+    shapes = {k: tuple(v.shape) for k, v in vq.state_dict().items() if not k.startswith("codebook.") or k == "codebook.embeddings"}
+    vq.load_state_dict({**vq.state_dict(), **VO.make_weights(shapes, 3)})
+    ckpt = tmp_path / "vqgan.ckpt"
+    torch.save({"hyper_parameters": {"args": V._Args(vcfg)}, "state_dict": vq.state_dict()}, ckpt)
+    cfg = dict(STL_16F, n_embd=64, n_head=1, sos_emb=16, n_layer=4, mode=["latent_enc", "latent_self", "lt2l", "latent_dec"],
+               vocab_size=128, block_size=256, shape=[4, 8, 8])
+    params, _, mask = model_configs(cfg, schedule="cosine")
+    params.vtokens = False
+    model = Net2NetTransformer(params, to_attr(dict(params=dict(ckpt_path=str(ckpt), ignore_keys=["loss"]))), mask).cuda().eval()
+    video = torch.rand(2, 3, 8, 32, 32, generator=torch.Generator().manual_seed(1)) - 0.5
+    emb, tokens = model.encode_to_z(video.cuda())
+    assert tokens.shape == (2, 256) and emb.shape == (2, 4, 8, 8, 64)
+    assert torch.equal(tokens.view(2, 4, 8, 8), model.first_stage_model.encode(video.cuda()))
+    # the oracle's encoder agrees except across near-ties of the code distances
+    P = {k: v for k, v in vq.state_dict().items()}
+    ref = VO.pre_quant(P, video, (2, 4, 4))
+    E = P["codebook.embeddings"]
+    flat = ref.permute(0, 2, 3, 4, 1).reshape(-1, 64)
+    ref_codes = ((flat ** 2).sum(1, keepdim=True) - 2 * flat @ E.t() + (E ** 2).sum(1)[None]).argmin(1).view(2, 4, 8, 8)
+    assert (tokens.view(2, 4, 8, 8).cpu() != ref_codes).float().mean() < 0.1
+    torch.manual_seed(0)
+    # the script hard-codes 4 video frames per latent frame (:29); this small VQGAN has 2, so 16 "frames" = its 4 latent frames
+    log = pipelines.bidirect_sample(model, 2, total_length=16, step_size=16, context_size=8, vid_n_steps=4)
+    assert log["code_maps"].shape == (2, 4, 8, 8)
+    assert log["samples"].shape == (2, 3, 8, 32, 32) and float(log["samples"].min()) >= 0.0 and float(log["samples"].max()) <= 1.0
+    again = torch.clamp(model.first_stage_model.decode(log["code_maps"]), -0.5, 0.5) + 0.5
+    assert torch.equal(again, log["samples"])

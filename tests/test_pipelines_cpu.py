@@ -72,5 +72,11 @@ def test_extrapolate_matches_reference_script():
     m = FakeSampler((4, 4, 4))
     log = extrapolate(m, vq, total_length=30, step_size=16, context_size=12, vid_n_steps=7, decode=m.first_stage_model.decode)
     _check("ex_odd", z, m, log)
-    no_pixels = extrapolate(FakeSampler((4, 4, 4)), vq, total_length=30, step_size=16, context_size=12, vid_n_steps=7)
+    # the default decoder is the model's own first stage (the script's gpt.first_stage_model.decode); a token-only model
+    # (vtokens: True, no first stage) returns the token-level log
+    default = extrapolate(FakeSampler((4, 4, 4)), vq, total_length=30, step_size=16, context_size=12, vid_n_steps=7)
+    assert torch.equal(default["code_maps"], log["code_maps"]) and torch.equal(default["samples"], log["samples"])
+    tokens_only = FakeSampler((4, 4, 4))
+    tokens_only.first_stage_model = None
+    no_pixels = extrapolate(tokens_only, vq, total_length=30, step_size=16, context_size=12, vid_n_steps=7)
     assert torch.equal(no_pixels["code_maps"], log["code_maps"]) and no_pixels["samples"] == []
