@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from conftest import load_golden
-from helpers import build_model, model_configs
+from helpers import model_configs
 
 pytestmark = pytest.mark.gpu
 

@@ -2,7 +2,6 @@
 (D = 1024, 16 heads, 256 latents) at 16 and 128 frames against the CPU oracle — the pair-mode / split-K GEMMs, the
 latent_enc K|V hoist over 7 blocks and 16-head attention at NK / NQ = 8192 are only reached at these widths.
 Tolerances are north_star's: 1e-2 relative for the bf16 engine."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
