@@ -105,3 +105,22 @@ def test_transposed_convolution_as_parity_classes(stride):
         conv3d_ndhwc_contract(xp, w, 12, b.shape[0], taps, (1, 1, 1), odims, b, out=out, origin=par, ystep=stride, yorigin=par)
     assert ref.shape[2:] == out.shape[1:4]
     assert torch.allclose(out[..., :20].permute(0, 4, 1, 2, 3), ref, atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("tag", ["small", "bn"])
+def test_vqgan_state_dict_names_and_shapes_equal_the_reference(tag):
+    """Drop-in contract of the checkpoint format: every encoder / decoder / pre- / post-quant parameter and buffer of the
+    unmodified reference's modules (names and shapes recorded by tests/golden/make_golden.py::gen_vqgan) exists in
+    `mebt_b200.vqgan.VQGAN` under the same name with the same shape, and nothing else does (codebook buffers aside) - so a
+    reference checkpoint loads with strict key matching."""
+    import json
+    from conftest import load_golden
+    z, _ = load_golden(f"vqgan_{tag}")
+    cfg = json.loads(str(z["cfg_json"]))
+    want = {k: tuple(v) for k, v in json.loads(str(z["shapes_json"])).items()}
+    cfg.update(sequence_length=8, sample_every_n_frames=1, resolution=32)
+    model = V.VQGAN(V._Args(cfg))
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    mine = {k: s for k, s in got.items() if not k.startswith("codebook.") or k == "codebook.embeddings"}
+    assert mine == want, (sorted(set(mine) ^ set(want))[:8], [k for k in mine if k in want and mine[k] != want[k]][:8])
+    assert {k for k in got if k.startswith("codebook.")} == {"codebook.embeddings", "codebook.N", "codebook.z_avg"}
