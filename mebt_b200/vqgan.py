@@ -86,9 +86,13 @@ def norm_args(m):
     return dict(norm=2, gamma=scale, beta=shift)
 
 
+def silu(x):
+    return x * torch.sigmoid(x)
+
+
 class SiLU(nn.Module):
     def forward(self, x):
-        return x * torch.sigmoid(x)
+        return silu(x)
 
 
 class SamePadConv3d(nn.Module):
@@ -341,14 +345,18 @@ class VQGAN(nn.Module):
     """`mebt.vqgan.VQGAN` for inference.  Two ways to build it:
     * `VQGAN(args)` with the reference's hyper-parameter namespace (`embedding_dim, n_codes, n_hiddens, downsample,
       image_channels, norm_type, padding_type, no_random_restart, restart_thres`; vqgan.py:36-52): the full model;
-    * `VQGAN(n_codes=..., embedding_dim=..., encoder=..., ...)`: the codebook with injected (or identity) callables around
+    * `VQGAN(n_codes, embedding_dim, encoder=..., ...)`: the codebook with injected (or identity) callables around
       it, which is what the synthetic-latent benchmark (config #4) uses."""
 
-    def __init__(self, n_codes=16384, embedding_dim=256, encoder=None, pre_vq_conv=None, post_vq_conv=None, decoder=None):
+    def __init__(self, args=16384, embedding_dim=256, encoder=None, pre_vq_conv=None, post_vq_conv=None, decoder=None,
+                 n_codes=None):
+        """`args`: the reference's hyper-parameter namespace (its only constructor argument, vqgan.py:36), or - second form -
+        the number of codes (also accepted as `n_codes=`)."""
         super().__init__()
         self.args = None
-        if hasattr(n_codes, "n_hiddens"):
-            args = n_codes
+        if n_codes is None:
+            n_codes = args
+        if hasattr(args, "n_hiddens"):
             self.args = args
             padding_type = getattr(args, "padding_type", "replicate")
             norm_type = getattr(args, "norm_type", "group")
@@ -371,6 +379,30 @@ class VQGAN(nn.Module):
         self.pre_vq_conv = pre_vq_conv if pre_vq_conv is not None else nn.Identity()
         self.post_vq_conv = post_vq_conv if post_vq_conv is not None else nn.Identity()
         self.decoder = decoder if decoder is not None else nn.Identity()
+
+    # hyper-parameters of the reference's command line (vqgan.py:229-252): (flag, type, default[, choices]).  The GAN-training
+    # ones are accepted (they are part of the namespace a checkpoint stores) and unused here.
+    _HPARAMS = (("embedding_dim", int, 256), ("n_codes", int, 2048), ("n_hiddens", int, 240), ("lr", float, 3e-4),
+                ("downsample", "ints", (4, 4, 4)), ("disc_channels", int, 64), ("disc_layers", int, 3),
+                ("discriminator_iter_start", int, 50000), ("disc_loss_type", str, "hinge", ("hinge", "vanilla")),
+                ("image_gan_weight", float, 1.0), ("video_gan_weight", float, 1.0), ("l1_weight", float, 4.0),
+                ("gan_feat_weight", float, 0.0), ("perceptual_weight", float, 0.0), ("i3d_feat", "flag", False),
+                ("restart_thres", float, 1.0), ("no_random_restart", "flag", False),
+                ("norm_type", str, "group", ("batch", "group")),
+                ("padding_type", str, "replicate", ("replicate", "constant", "reflect", "circular")))
+
+    @staticmethod
+    def add_model_specific_args(parent_parser):
+        import argparse
+        parser = argparse.ArgumentParser(parents=[parent_parser], add_help=False)
+        for name, kind, default, *choices in VQGAN._HPARAMS:
+            if kind == "flag":
+                parser.add_argument(f"--{name}", action="store_true")
+            elif kind == "ints":
+                parser.add_argument(f"--{name}", nargs="+", type=int, default=default)
+            else:
+                parser.add_argument(f"--{name}", type=kind, default=default, **({"choices": list(choices[0])} if choices else {}))
+        return parser
 
     @property
     def latent_shape(self):

@@ -124,3 +124,23 @@ def test_vqgan_state_dict_names_and_shapes_equal_the_reference(tag):
     mine = {k: s for k, s in got.items() if not k.startswith("codebook.") or k == "codebook.embeddings"}
     assert mine == want, (sorted(set(mine) ^ set(want))[:8], [k for k in mine if k in want and mine[k] != want[k]][:8])
     assert {k for k in got if k.startswith("codebook.")} == {"codebook.embeddings", "codebook.N", "codebook.z_avg"}
+
+
+def test_vqgan_command_line_hyperparameters():
+    """`VQGAN.add_model_specific_args` (vqgan.py:229-252): the flags, types and defaults of the reference's command line, so
+    that its training / sampling scripts parse unchanged and a default namespace builds the default model."""
+    import argparse
+    parser = V.VQGAN.add_model_specific_args(argparse.ArgumentParser(add_help=False))
+    d = vars(parser.parse_args([]))
+    assert d == dict(embedding_dim=256, n_codes=2048, n_hiddens=240, lr=3e-4, downsample=(4, 4, 4), disc_channels=64, disc_layers=3,
+                     discriminator_iter_start=50000, disc_loss_type="hinge", image_gan_weight=1.0, video_gan_weight=1.0,
+                     l1_weight=4.0, gan_feat_weight=0.0, perceptual_weight=0.0, i3d_feat=False, restart_thres=1.0,
+                     no_random_restart=False, norm_type="group", padding_type="replicate")
+    a = parser.parse_args(["--n_codes", "16384", "--n_hiddens", "32", "--downsample", "4", "8", "8", "--norm_type", "batch"])
+    assert a.downsample == [4, 8, 8] and a.norm_type == "batch"
+    with pytest.raises(SystemExit):
+        parser.parse_args(["--disc_loss_type", "wasserstein"])
+    model = V.VQGAN(args=a)                                   # the reference's only constructor argument is `args`
+    assert isinstance(model.encoder, V.Encoder) and model.codebook.n_codes == 16384
+    assert isinstance(model.encoder.final_block[0], torch.nn.BatchNorm3d)
+    assert float(V.silu(torch.tensor(0.0))) == 0.0 and abs(float(V.silu(torch.tensor(1.0))) - 0.7310586) < 1e-6
