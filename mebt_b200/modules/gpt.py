@@ -230,3 +230,12 @@ class GPT(nn.Module):
         B, NT = targets.shape[0], targets.shape[1]
         logits = self.forward_rows(B, _as_rows(sos_emb), _as_rows(contexts), _as_rows(targets))
         return logits.view(B, NT, -1), None
+
+
+def complement_idx(idx, dim):
+    """The indices of range(dim) that are NOT in the trailing dimension of `idx` ([N, *, K] -> [N, *, dim - K], ascending;
+    mebt/modules/gpt.py:19-42).  The indices of a row must be distinct."""
+    mask = torch.ones(*idx.shape[:-1], dim, dtype=torch.bool, device=idx.device)
+    mask.scatter_(-1, idx, False)
+    full = torch.arange(dim, device=idx.device).expand(*idx.shape[:-1], dim)
+    return full[mask].view(*idx.shape[:-1], dim - idx.shape[-1])

@@ -226,3 +226,30 @@ def test_first_stage_vqgan_is_loaded_and_frozen_when_vtokens_is_false(tmp_path):
     log = {}
     pipelines._decode(m, torch.zeros(1, 4, 8, 8, dtype=torch.long), None, 8, log)
     assert "codes" in seen and log["samples"].shape == (1, 3, 8, 32, 32)
+
+
+def test_small_utility_helpers():
+    """mebt/utils.py:55-124,174-178 and mebt/modules/gpt.py:19-42: generic helpers the reference's scripts import."""
+    import torch
+    from mebt_b200.modules.gpt import complement_idx
+    from mebt_b200.utils import accuracy, adopt_weight, comp_getattr, correct, tensor_slice, view_range
+    x = torch.arange(2 * 24 * 3).view(2, 24, 3)
+    assert view_range(x, 1, 2, (2, 3, 4)).shape == (2, 2, 3, 4, 3) and view_range(x, -2, -1, (4, 6)).shape == (2, 4, 6, 3)
+    assert view_range(x, 1, None, (8, 9)).shape == (2, 8, 9)
+    assert torch.equal(tensor_slice(x, (0, 4, 1), (-1, 5, 2)), x[:, 4:9, 1:3])
+    out = torch.tensor([[0.1, 0.9, 0.0], [0.8, 0.15, 0.05], [0.2, 0.3, 0.5]])
+    tgt = torch.tensor([1, 1, 0])
+    c1, c2 = correct(out, tgt, topk=(1, 2))
+    assert float(c1) == 1.0 and float(c2) == 2.0
+    a1, a2 = accuracy(out, tgt, topk=(1, 2))
+    assert abs(float(a1) - 100.0 / 3) < 1e-4 and abs(float(a2) - 200.0 / 3) < 1e-4
+    assert adopt_weight(10, threshold=50, value=0.0) == 0.0 and adopt_weight(50, threshold=50) == 1
+    assert comp_getattr(type("A", (), {"k": 3})(), "k") == 3 and comp_getattr(object(), "k", 7) == 7
+    g = torch.Generator().manual_seed(0)
+    idx = torch.stack([torch.stack([torch.randperm(10, generator=g)[:4] for _ in range(3)]) for _ in range(2)])     # [2, 3, 4]
+    comp = complement_idx(idx, 10)
+    assert comp.shape == (2, 3, 6)
+    for b in range(2):
+        for r in range(3):
+            assert comp[b, r].tolist() == sorted(set(range(10)) - set(idx[b, r].tolist()))
+    assert torch.equal(complement_idx(torch.empty(2, 0, dtype=torch.long), 5), torch.arange(5).repeat(2, 1))
