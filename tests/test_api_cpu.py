@@ -253,3 +253,32 @@ def test_small_utility_helpers():
         for r in range(3):
             assert comp[b, r].tolist() == sorted(set(range(10)) - set(idx[b, r].tolist()))
     assert torch.equal(complement_idx(torch.empty(2, 0, dtype=torch.long), 5), torch.arange(5).repeat(2, 1))
+
+
+def test_load_transformer_from_a_lightning_style_checkpoint(tmp_path):
+    """mebt/download.py:56-61: the model is re-created from the checkpoint's `hyper_parameters` (the constructor arguments
+    `save_hyperparameters()` records) and its `state_dict` is loaded strictly."""
+    import torch
+    from helpers import STL_16F
+    from mebt.download import load_transformer
+    from mebt_b200._lib import MebtError
+    from mebt_b200.transformer import Net2NetTransformer
+    cfg = dict(STL_16F, n_embd=64, n_head=1, sos_emb=16, n_layer=4, mode=["latent_enc", "latent_self", "lt2l", "latent_dec"],
+               vocab_size=128, block_size=256, shape=[4, 8, 8])
+    params, vq, mask = model_configs(cfg, schedule="cosine")
+    torch.manual_seed(3)
+    m = Net2NetTransformer(params, vq, mask)
+    ckpt = tmp_path / "gpt.ckpt"
+    torch.save({"state_dict": m.state_dict(), "hyper_parameters": dict(transformer_config=params, first_stage_config=vq, mask_config=mask,
+                                                                      ckpt_path="/nonexistent/previous/run.ckpt", first_stage_key="video",
+                                                                      cond_stage_key="label", pkeep=1.0, sos_token=0)}, ckpt)
+    got = load_transformer(str(ckpt), "ignored_vqgan.ckpt")
+    assert not got.training and got.mask_sampler.schedule == "cosine"
+    a, b = m.state_dict(), got.state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    try:
+        load_transformer({"state_dict": {}})
+        raised = False
+    except MebtError:
+        raised = True
+    assert raised
