@@ -282,3 +282,41 @@ def test_load_transformer_from_a_lightning_style_checkpoint(tmp_path):
     except MebtError:
         raised = True
     assert raised
+
+
+def test_out_of_scope_modules_resolve_to_the_reference_checkout(tmp_path, monkeypatch):
+    """`from mebt import VideoData`, `from mebt.data import preprocess`, `from mebt.utils import save_video_grid` (the imports
+    of the reference's scripts) resolve to `$MEBT_REF/mebt/{data,utils}.py`; without MEBT_REF they fail with a message naming it."""
+    import importlib
+    import sys
+    for k in [k for k in sys.modules if k in ("mebt.data",) or k.startswith("mebt._reference_")]:
+        del sys.modules[k]
+    monkeypatch.delenv("MEBT_REF", raising=False)
+    import mebt
+    try:
+        mebt.VideoData
+        raised = ""
+    except ImportError as exc:
+        raised = str(exc)
+    assert "MEBT_REF" in raised
+    try:
+        from mebt.utils import save_video_grid  # noqa: F401
+        ok = True
+    except ImportError as exc:
+        ok = "MEBT_REF" in str(exc) and False
+    assert not ok
+    fake = tmp_path / "MeBT" / "mebt"
+    fake.mkdir(parents=True)
+    (fake / "data.py").write_text("class VideoData:\n    tag = 'reference data module'\n\ndef preprocess(video, resolution):\n    return ('pre', resolution)\n")
+    (fake / "utils.py").write_text("def save_video_grid(video, fname, nrow=None):\n    return ('saved', fname)\n")
+    monkeypatch.setenv("MEBT_REF", str(tmp_path / "MeBT"))
+    for k in [k for k in sys.modules if k in ("mebt.data",) or k.startswith("mebt._reference_")]:
+        del sys.modules[k]
+    from mebt import VideoData
+    assert VideoData.tag == "reference data module"
+    data = importlib.import_module("mebt.data")
+    assert data.preprocess(None, 128) == ("pre", 128)
+    from mebt.utils import save_video_grid, shift_dim
+    assert save_video_grid(None, "x.mp4") == ("saved", "x.mp4") and callable(shift_dim)
+    for k in [k for k in sys.modules if k in ("mebt.data",) or k.startswith("mebt._reference_")]:
+        del sys.modules[k]
